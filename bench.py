@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- pseudo-labelled samples/s of the UBPL hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU baseline (oracle port)
+
+One step = one pass of the fused chain over one synthetic batch resident in HBM:
+K1 back-warp+flip+arg-max decode of all M*K teacher views -> K2 dispersion + selection ->
+K3 Gaussian render + masked joint-MSE forward + gradient -> K4 mean-teacher EMA of an HG2-sized
+parameter set.  Weak scaling: every rank owns a full per-GPU batch (no data-path collective; the
+global-quantile configs all-reduce the selection histograms over NCCL).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+# BASELINE.json configs (per-GPU batch under weak scaling)
+CONFIGS = {
+    "c1": dict(B=16, K=4, M=1, S=2, J=14, H=64, W=64, select="fixed", hg="hg2_j14",
+               desc="MT_UBPL LSP J=14 B=16 K=4 (the reference's CPU-runnable case)"),
+    "c2": dict(B=256, K=8, M=1, S=2, J=14, H=64, W=64, select="fixed", hg="hg2_j14",
+               desc="LSP J=14 B=256 K=8 mean-teacher pseudo-labels + EMA"),
+    "c3": dict(B=128, K=8, M=2, S=2, J=9, H=64, W=64, select="fixed", hg="hg2_j9",
+               desc="DualPose_UBPL FLIC J=9 B=1024/8 per GPU K=8 dual teachers"),
+    "c4": dict(B=256, K=16, M=1, S=2, J=17, H=64, W=64, select="quantile", hg="hg2_j17",
+               desc="AP-10K J=17 B=2048/8 per GPU K=16 global-quantile threshold (NCCL histogram all-reduce)"),
+    "c5": dict(B=32, K=16, M=1, S=2, J=32, H=128, W=128, select="fixed", hg="hg2_j32",
+               desc="fly J=32 128x128 K=16 bandwidth stress, chunk of 32 samples per step"),
+}
+DIST_THR_MAX = 3.0          # no reference default exists; ~half of the joints pass on the synthetic data
+METRIC = "pseudo-labelled samples/sec"
+
+
+def algorithmic_bytes_per_sample(c):
+    """teacher maps read once + student read once + gradient written once + target written once."""
+    return 4 * c["H"] * c["W"] * c["J"] * (c["M"] * c["K"] + c["S"] + c["S"] + 1)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's chain (the reference itself is pure Python and is not
+# mounted on the GPU box), all host cores, one process per core, bounded sample of the workload.
+# ---------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    cfgname, nb, seed = args
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    import ubpl_b200  # noqa: F401
+    from ubpl_b200 import synth
+    import ubpl_oracle as O
+    c = CONFIGS[cfgname]
+    d = synth.make_batch(B=nb, K=c["K"], J=c["J"], H=c["H"], W=c["W"], M=c["M"], S=c["S"], seed=seed)
+    n = {k: v.numpy() for k, v in d.items()}
+    t0 = time.perf_counter()
+    O.pseudo_label_chain(n["teacher"], n["student"], n["theta"], n["flip"], n["center"], n["scale"], n["islabeled"],
+                         select=c["select"], distThrMax=DIST_THR_MAX)
+    return time.perf_counter() - t0
+
+
+def cpu_chain_throughput(cfgname, per_proc, procs, repeats=1):
+    """samples/s of the oracle chain: `procs` processes x `per_proc` samples each, wall clock of the pool."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_worker, [(cfgname, 1, 7 + i) for i in range(procs)])          # warm the workers (imports)
+        t0 = time.perf_counter()
+        for r in range(repeats):
+            pool.map(_cpu_worker, [(cfgname, per_proc, 1388 + 1000 * r + i) for i in range(procs)])
+        dt = time.perf_counter() - t0
+    return procs * per_proc * repeats / dt, dt
+
+
+def cpu_ema_seconds(hg):
+    """numpy statement of utils/parameters.py:7-8 over the HG2 parameter list (timing variant:
+    plain multiply-add, one core)."""
+    import numpy as np
+    shapes = json.load(open(os.path.join(ROOT, "ubpl-poseestimation_b200", "hg_param_shapes.json")))[hg]
+    rng = np.random.default_rng(0)
+    ps = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    es = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    a = np.float32(0.75)
+    t0 = time.perf_counter()
+    for e, p in zip(es, ps):
+        e *= a
+        e += p * (np.float32(1) - a)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                     # rank 0 alone runs the CPU arm
+    c = CONFIGS[args.config]
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    per_proc = max(1, int(args.ref_samples_per_proc))
+    vals = []
+    for _ in range(args.warmup):
+        cpu_chain_throughput(args.config, 1, procs)
+    t_steps = []
+    for _ in range(args.steps):
+        v, dt = cpu_chain_throughput(args.config, per_proc, procs)
+        ema_s = cpu_ema_seconds(c["hg"])
+        n = procs * per_proc
+        tot = dt + ema_s * n / c["B"]               # one EMA per full batch of B samples, pro-rated
+        vals.append(n / tot)
+        t_steps.append(tot)
+    v = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_steps) / len(t_steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.config + ": " + c["desc"], "per_gpu_batch": c["B"], "K": c["K"], "M": c["M"],
+                   "J": c["J"], "S": c["S"], "heatmap": [c["H"], c["W"]], "select": c["select"]},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": procs, "kind": "port",
+                         "sample": "%d samples per step (%d processes x %d), oracle/ubpl_oracle.py chain + pro-rated numpy EMA"
+                                   % (procs * per_proc, procs, per_proc)},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import ubpl_b200  # noqa: F401
+    from ubpl_b200 import _lib, ops, pipeline, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=dev)
+        group = td.group.WORLD
+    c = CONFIGS[args.config]
+    B, K, M, S, J, H, W = (c[k] for k in "BKMSJHW")
+    d = synth.make_batch(B=B, K=K, J=J, H=H, W=W, M=M, S=S, seed=1388, rank=rank, device=dev)
+    dec = ops.decode_coeffs(d["center"], d["scale"], [H, W])
+    w = pipeline.nega_weights(d["islabeled"], 1.0)
+    cfg = pipeline.StepConfig(select=c["select"], distThrMax=DIST_THR_MAX)
+    shapes = json.load(open(os.path.join(ROOT, "ubpl-poseestimation_b200", "hg_param_shapes.json")))[c["hg"]]
+    g = torch.Generator(device=dev).manual_seed(5)
+    params = [torch.randn(*s, generator=g, device=dev) * 0.02 for s in shapes]
+    emas = [torch.randn(*s, generator=g, device=dev) * 0.02 for s in shapes]
+    plan = ops.EmaPlan(params, emas)
+    n_params = plan.n_elems
+    alpha = min(1 - 1 / (3 + 1), 0.999)              # args.epo = 3
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    stage_events = []
+
+    def step(timed=False, group=group):
+        evs = {}
+
+        def mark(name):
+            if timed:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                evs[name] = e
+        r = pipeline.pseudo_label_step(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, group=group,
+                                       stats=stats, timer=mark)
+        mark("ema0")
+        plan.step(alpha)
+        mark("ema1")
+        if timed:
+            stage_events.append(evs)
+        return r
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        r = step()
+    barrier()
+    # ---- device-resident timing ---------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    stats.zero_()
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        r = step(timed=True)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ms_step = float(t) / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # per-stage device time (CUDA events on the launching stream), averaged over the timed steps
+    def avg(a, b):
+        return sum(ev[a].elapsed_time(ev[b]) for ev in stage_events) / len(stage_events)
+    k1_ms, k2_ms, k3_ms, k4_ms = avg("k1_0", "k1_1"), avg("k1_1", "k3_0"), avg("k3_0", "k3_1"), avg("ema0", "ema1")
+    bytes_sample = algorithmic_bytes_per_sample(c)
+    k1_bytes = 4 * H * W * J * M * K * B
+    k3_bytes = 4 * H * W * J * (2 * S + 1) * B
+    ema_bytes = 12 * n_params
+    peak, peak_src = measured_peaks()
+    chain_gbs = bytes_sample * B / ((k1_ms + k2_ms + k3_ms) * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "warp_decode_kernel (K1: %d maps of %d B per launch)" % (M * K * B * J, 4 * H * W),
+            "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "stages_ms": {"k1_warp_decode": k1_ms, "k2_uncertainty_select": k2_ms, "k3_render_mse": k3_ms, "k4_ema": k4_ms},
+            "stages_gbs": {"k1": k1_bytes / (k1_ms * 1e-3) / 1e9, "k3": k3_bytes / (k3_ms * 1e-3) / 1e9,
+                           "k4": ema_bytes / (k4_ms * 1e-3) / 1e9, "chain_k1_k3": chain_gbs},
+            "chain_frac_of_peak": chain_gbs / peak, "chain_frac_of_8TBs": chain_gbs / 8000.0,
+            "algorithmic_bytes_per_sample": bytes_sample}
+    slow_frac = float(stats[0]) / max(1.0, float(stats[2]))
+
+    # ---- end-to-end: host buffers in, host scalars out, copies inside the timed region -------------
+    host = {k: d[k].cpu().pin_memory() for k in ("teacher", "student", "theta", "flip")}
+    devbuf = {k: torch.empty_like(d[k]) for k in host}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def e2e_step():
+        for k in host:
+            devbuf[k].copy_(host[k], non_blocking=True)
+        rr = pipeline.pseudo_label_step(devbuf["teacher"], devbuf["student"], devbuf["theta"], devbuf["flip"], dec, w,
+                                        cfg, group=group)
+        plan.step(alpha)
+        out = torch.cat([rr["summary"], rr["grad_scale"].double(), rr["count"].double()]).cpu()   # D2H + sync
+        return out
+    for _ in range(2):
+        out = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(2, min(args.steps, 10))
+    for _ in range(n_e2e):
+        out = e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    e2e_val = world * B / (float(t) * 1e-3)
+    d2h = out.numel() * out.element_size()
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            procs = max(1, min(os.cpu_count() or 1, 64))
+            v, dt = cpu_chain_throughput(args.config, 2, procs)
+            ema_s = cpu_ema_seconds(c["hg"])
+            n = procs * 2
+            cpu = {"value": n / (dt + ema_s * n / B), "unit": "samples/s", "cores": procs, "kind": "port",
+                   "sample": "%d samples (%d processes x 2) of %s through oracle/ubpl_oracle.py + pro-rated numpy EMA"
+                             % (n, procs, args.config)}
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.config + ": " + c["desc"], "per_gpu_batch": B, "K": K, "M": M, "J": J, "S": S,
+                       "heatmap": [H, W], "select": c["select"], "distThrMax": DIST_THR_MAX,
+                       "ema_params": n_params, "l2": "inputs (%.0f MB/step) larger than L2" % (bytes_sample * B / 1e6),
+                       "selected_frac": float(r["enable"].float().mean()), "exhaustive_decode_frac": slow_frac},
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(t)},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-samples-per-proc", type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+/*
+ * ubpl_b200.h -- C ABI of libubpl_b200.so: the B200 (sm_100a) pseudo-label hot path of
+ * Qi2019KB/UBPL-PoseEstimation.
+ *
+ * The reference is pure Python (no FFI of its own); every entry point below
+ * replaces the body of one reference function, cited as file:line relative to /root/reference.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every
+ *     buffer, kernels never allocate; outputs are pre-allocated by the caller;
+ *   - heat-maps: the inner [H, W] plane is contiguous; outer dims are addressed with ELEMENT
+ *     strides (the reference slices `outs_ema[m, a, :, -1]`, so outer strides are arbitrary);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns 0 on success or a negative code; ubpl_last_error() gives the text.
+ *     Nothing falls back to the CPU: without a usable sm_100 device the calls fail.
+ */
+#ifndef UBPL_B200_H
+#define UBPL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UBPL_OK 0
+#define UBPL_ERR_INVALID (-1)
+#define UBPL_ERR_CUDA (-2)
+#define UBPL_ERR_UNSUPPORTED (-3)
+
+const char* ubpl_last_error(void);
+int ubpl_version(void);
+/* sm count, compute capability and opt-in shared memory per block of the current device. */
+int ubpl_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_optin_bytes);
+
+/* ---- K1: back-warp + flip + arg-max decode, fused (each heat-map is read from HBM once) --------
+ * Replaces AugmentUtils.affine_back2 (utils/augment.py:37-47) followed by get_preds /
+ * final_preds (utils/udaap/evaluation.py:13-30,215-238), transform_preds
+ * (utils/udaap/transforms.py:151-168) and the scores of ProcessUtils.kps_fromHeatmap(_mul)
+ * (utils/process.py:321-336); refine != 0 adds the quarter-offset of kps_fromHeatmap2
+ * (utils/process.py:362-373).
+ *
+ * maps    [V, B, J, H, W] float32 with element strides (sV, sB, sJ)
+ * theta   [V, B, 2, 3] float32 contiguous, NULL when do_warp == 0 (plain decode of raw maps)
+ * flip    [V, B] uint8 contiguous (NULL = no flips)
+ * dec     [B, 4] float64 (a00, a02, a11, a12) of the inverse decode transform (NULL = skip the
+ *         image-space transform; out_xy then equals out_hm_xy)
+ * refine  0 = off (final_preds parity), 1 = joints 0 and 1 only (kps_fromHeatmap2 bug parity,
+ *         utils/process.py:363), 2 = all joints
+ * outputs, all contiguous [V, B, J]: out_idx int32 (flat arg-max index in the canonical frame,
+ *         first maximum in row-major order), out_max float32 (unmasked maximum = `scores`),
+ *         out_xy float32[2] (image space, integer valued), out_hm_xy float32[2] (1-based heat-map
+ *         coordinates after the max<=0 mask and the optional refinement); any may be NULL.
+ * stats   optional int64[4] device counters, incremented: [0] maps decoded by exhaustive
+ *         evaluation, [1] output pixels evaluated, [2] maps, [3] reserved.
+ */
+int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
+                     int V, int B, int J, int H, int W,
+                     const float* theta, const uint8_t* flip, const double* dec,
+                     int do_warp, int refine,
+                     int32_t* out_idx, float* out_max, float* out_xy, float* out_hm_xy,
+                     int64_t* stats, void* stream);
+
+/* Materialises the back-warped (and un-flipped) maps: the tensor AugmentUtils.affine_back2
+ * returns (utils/augment.py:37-47).  in [N, C, H, W] strides (sN, sC); out likewise (oN, oC);
+ * theta [N,2,3]; flip [N] uint8 or NULL.  Bit-identical to ATen's CPU grid_sample op order. */
+int ubpl_warp_materialize(const float* in, int64_t sN, int64_t sC, float* out, int64_t oN, int64_t oC,
+                          int N, int C, int H, int W, const float* theta, const uint8_t* flip,
+                          void* stream);
+
+/* ---- K2: per-joint uncertainty ----------------------------------------------------------------
+ * View dispersion of one teacher: EvaluationUtils.uncertainty_fromDistance
+ * (utils/evaluation.py:40-58) numerator.  preds [K, B, J, 2] float32 contiguous.
+ * out_mean [B,J,2] float32 (torch.mean over views), out_dist [B,J] float64 (mean distance to the
+ * mean), out_unc32 [B,J] float32 (the same, as the float32 tensor the reference builds),
+ * out_legal [B,J] uint8 (all views x>=0 and y>=0), max_bits: uint32 device scalar that receives
+ * atomicMax of the float32 bits of out_unc32 (caller zeroes it).  sentinel_illegal != 0 stores
+ * 999 in out_dist for items with an illegal view (the sentinel of utils/business.py:123). */
+int ubpl_view_dispersion(const float* preds, int K, int B, int J,
+                         float* out_mean, double* out_dist, float* out_unc32, uint8_t* out_legal,
+                         uint32_t* max_bits, int sentinel_illegal, void* stream);
+/* unc = unc32 / max, uncW = exp(-unc)  (utils/evaluation.py:56-57); n = B*J. */
+int ubpl_unc_normalize(const float* unc32, const uint32_t* max_bits, int64_t n,
+                       float* out_unc, float* out_uncW, void* stream);
+
+/* Two-teacher assessment: BusinessUtils.assess_pseudo_unc2 (utils/business.py:109-161) in array
+ * form.  p1, p2, pmean [B,J,2] float32; aug1, aug2 [K,B,J,2] float32.  Outputs float64 [B,J]:
+ * legal, intDist1, intDist2, extDist, w1, w2; coord [B,J,2] (+ coord32, its float32 copy);
+ * pmean NULL = bus.preds_mean(p1, p2) (business.py:297-300); zero_div: int32 device counter of
+ * items where intDist1+intDist2 == 0 (the reference raises ZeroDivisionError there,
+ * business.py:135; the kernel keeps w = 0.5/0.5 and counts). */
+int ubpl_assess_dual(const float* p1, const float* p2, const float* pmean,
+                     const float* aug1, const float* aug2, int K, int B, int J,
+                     double* legal, double* intDist1, double* intDist2, double* extDist,
+                     double* w1, double* w2, double* coord, float* coord32, int32_t* zero_div,
+                     void* stream);
+
+/* ---- K2: pseudo-label selection ---------------------------------------------------------------
+ * BusinessUtils.filter_pseudo2 (utils/business.py:173-217) / _calReliabilityThr (:43-46).
+ * Step 1: local extrema of dist (float64[n]; 999 = sentinel): ext[0] = max over dist<999 (0 if
+ * none), ext[1] = min over all.  On several GPUs the caller all-reduces ext (MAX / MIN). */
+int ubpl_dist_extrema(const double* dist, int64_t n, double* ext, void* stream);
+/* Step 2: reliability[n] (float64) from dist, legal and the GLOBAL extrema (ext as above, still
+ * raw: the dist_max==0 -> 999 and reliableDistMin clamps of business.py:181-182 are applied
+ * inside), plus the monotone uint64 sort key of every reliability. */
+int ubpl_reliability(const double* dist, const double* legal, int64_t n, const double* ext,
+                     double reliableDistMin, double* reliability, uint64_t* keys, void* stream);
+/* Step 3: exact k-th order statistic by radix select, 16 bits per pass.  hist[65536] uint32 of
+ * key bits [shift, shift+16) over the keys whose bits above shift+16 equal `prefix`'s (pass 0:
+ * shift = 48, all keys).  The caller all-reduces hist over ranks (SUM) between the passes. */
+int ubpl_key_histogram(const uint64_t* keys, int64_t n, const uint64_t* prefix, int shift,
+                       uint32_t* hist, void* stream);
+/* Given the (global) histogram of a pass, descend: finds the bin holding rank *k_rem (0-based,
+ * counted from the LARGEST key), updates *prefix |= bin << shift and *k_rem. */
+int ubpl_select_descend(const uint32_t* hist, int shift, uint64_t* prefix, int64_t* k_rem, void* stream);
+/* Step 4: thr = max(reliableThr, value(prefix)); enable[n] = reliability > thr (uint8; gate32 is
+ * the same as float32 0/1, either may be NULL);
+ * counts[J+1] int32 per-joint and total selected (item i is joint i % J); thr_out float64. */
+int ubpl_select_apply(const double* reliability, int64_t n, int J, const uint64_t* prefix,
+                      double reliableThr, uint8_t* enable, float* gate32, int32_t* counts,
+                      double* thr_out, void* stream);
+/* Fixed rule: enable = legal && 1-exp(-dist/5) <= 1-exp(-3*distThrMax/5)
+ * (BusinessUtils.pseudo_filter_mixUnc / _calUncValue, utils/business.py:237-261,375-376). */
+int ubpl_select_fixed(const double* dist, const double* legal, int64_t n, int J, double distThrMax,
+                      uint8_t* enable, float* gate32, int32_t* counts, double* unc_out, void* stream);
+
+/* ---- K3: Gaussian target render + masked joint-MSE, forward and gradient in one pass ----------
+ * ProcessUtils.kps_heatmap (utils/process.py:253-278,394-397) fused into JointMSELoss
+ * (utils/losses.py:8-29).  kps [B,J,2] float32 image-space coordinates; gate_in [B,J] float32
+ * (key-point weight / enable), may be NULL (=1); sample_w [B] float32 or NULL.
+ * pred [B,S,J,H,W] strides (pB,pS,pJ); grad same shape, strides (gB,gS,gJ), may be NULL;
+ * target [B,J,H,W] contiguous, may be NULL (not materialised).
+ * img_h/img_w: input resolution (256); stride = inpRes/outRes; sigma = kernelSize*sigma (3).
+ * gate_out [B,J] float32 = gate_in * visibility (process.py:267-268).
+ * per_loss [B,S,J] float32 = mean_HW (p-t)^2 * gate_out * sample_w.
+ * grad = grad_scale * 2/(HW) * gate_out * sample_w * (p - t); grad_scale is read from device
+ * memory (NULL = 1) so the caller can fold weight/n (MT_UBPL.py:266) without a host sync. */
+int ubpl_render_mse(const float* kps, const float* gate_in, const float* sample_w,
+                    const float* pred, int64_t pB, int64_t pS, int64_t pJ,
+                    float* grad, int64_t gB, int64_t gS, int64_t gJ,
+                    float* target, int B, int S, int J, int H, int W,
+                    int img_h, int img_w, float stride, float sigma,
+                    const float* grad_scale, float* gate_out, float* per_loss, void* stream);
+/* kps_heatmap alone (utils/process.py:253-278): kps [N,3] float32 (x,y,w) -> heatmap [N,H,W],
+ * kps_out [N,3] with w *= visibility. */
+int ubpl_render_targets(const float* kps, int N, int H, int W, int img_h, int img_w, float stride,
+                        float sigma, float* heatmap, float* kps_out, void* stream);
+
+/* Dense-target masked joint-MSE forward + gradient: JointMSELoss / JointDistLoss
+ * (utils/losses.py:8-53), JointPseudoLoss3 (:169-210), JointDistLoss_mt2 (:246-286).
+ * pred [B,S,J,H,W] strides (pB,pS,pJ).  tgt: M maps per (b,s,j), averaged in float32 in index
+ * order then divided by M (torch.mean): strides (tM,tB,tS,tJ); tS = 0 shares one target between
+ * the stacks.  coef [B,J] float32 = gate*sample weight (NULL = 1).
+ * mask_mode 0: none; 1: (max p >= thr) && (max t >= thr)  (losses.py:187-193);
+ *           2: (max t >= thr)  (losses.py:270-271).
+ * Outputs [B,S,J] float32: per_loss = mean_HW (p-t)^2 * coef (before the mask, as the
+ * reference counts `loss > 0` on it), mask, vmax_p, vmax_t (any may be NULL).
+ * grad (may be NULL) = grad_scale * 2/(HW) * coef * mask * (p - t). */
+int ubpl_dense_mse(const float* pred, int64_t pB, int64_t pS, int64_t pJ,
+                   const float* tgt, int M, int64_t tM, int64_t tB, int64_t tS, int64_t tJ,
+                   const float* coef, int mask_mode, float thr,
+                   float* grad, int64_t gB, int64_t gS, int64_t gJ,
+                   int B, int S, int J, int H, int W, const float* grad_scale,
+                   float* per_loss, float* mask, float* vmax_p, float* vmax_t, void* stream);
+/* Reduces the [B,S,J] planes: out[0] = sum(per_loss*mask) (mask NULL = 1), out[1] = #(per_loss>0),
+ * out[2] = #(mask>0), out[3] = #(gate>0) over gate[B,J] (NULL -> B*J); all as float64[4]. */
+int ubpl_loss_finalize(const float* per_loss, const float* mask, const float* gate,
+                       int B, int S, int J, double* out, void* stream);
+/* gate_out[n] = gate_in * visibility(kps) (utils/process.py:262-268; gate_in NULL = 1), count_out =
+ * S * #(gate_out > 0) (the `n` JointMSELoss returns, utils/losses.py:29) and *grad_scale =
+ * loss_weight / count (loss_weight if count == 0), the factor projects/MT_UBPL.py:266 applies to
+ * the criterion's sum -- computed on device so ubpl_render_mse can write the final gradient. */
+int ubpl_gate_prepare(const float* kps, const float* gate_in, int64_t n, int img_h, int img_w, float stride,
+                      float sigma, int S, float loss_weight, float* gate_out, float* grad_scale,
+                      int32_t* count_out, void* stream);
+/* x[0..n) *= *scale (device scalar) -- the backward of the autograd wrappers; x 16-byte aligned. */
+int ubpl_scale_inplace(float* x, int64_t n, const float* scale, void* stream);
+
+/* ---- K4: mean-teacher EMA, all parameter tensors in one launch ---------------------------------
+ * update_ema_variables (utils/parameters.py:4-8): ema = ema*alpha + (1-alpha)*param, float32,
+ * evaluated as fma(param, 1-alpha, ema*alpha) like ATen.  ema_ptrs/param_ptrs: device arrays of
+ * n_tensors device addresses; chunk_tensor/chunk_start: device arrays describing n_chunks work
+ * items (tensor id, first element); chunk_elems elements per chunk; numels[n_tensors]. */
+int ubpl_ema_multi_tensor(const uint64_t* ema_ptrs, const uint64_t* param_ptrs, const int64_t* numels,
+                          const int32_t* chunk_tensor, const int64_t* chunk_start, int64_t n_chunks,
+                          int chunk_elems, float alpha, float one_minus_alpha, void* stream);
+/* Contiguous special case (flattened parameter buffer). */
+int ubpl_ema_flat(float* ema, const float* param, int64_t n, float alpha, float one_minus_alpha,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UBPL_B200_H */

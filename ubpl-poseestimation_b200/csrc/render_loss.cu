@@ -1,0 +1,434 @@
+// K3: Gaussian target render + masked joint-MSE, forward and gradient in one pass over the maps.
+//
+// Reference semantics (file:line in /root/reference):
+//   utils/process.py:253-278,394-397  kps_heatmap / heatmap_gaussian (float64 exp(-D2/2/s/s),
+//                                     >1 -> 1, <0.01 -> 0, visibility test in image space)
+//   utils/losses.py:8-29     JointMSELoss      utils/losses.py:32-53    JointDistLoss
+//   utils/losses.py:169-210  JointPseudoLoss3  utils/losses.py:246-286  JointDistLoss_mt2
+//
+// Pure streaming kernels (HBM-bound): one CTA per (sample, joint); every student map is read once
+// with 128-bit loads, its gradient is written once, the rendered target is written once (or not at
+// all).  The Gaussian is separable, exp(-dx^2/2s^2) * exp(-dy^2/2s^2), evaluated in float32
+// (<= 5 ulp of the reference's float64 value, tolerance 1e-5); the 0.01 cut is re-evaluated in
+// float64 for the rare pixel within 1e-5 of it so the support is identical to the reference's.
+#include "common.cuh"
+
+namespace ubpl {
+
+__device__ __forceinline__ float4 load4(const float* base, int q, int n, bool vec) {
+  if (vec) return ldg_stream(reinterpret_cast<const float4*>(base) + q);
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int k = q << 2;
+  if (k < n) r.x = __ldg(base + k);
+  if (k + 1 < n) r.y = __ldg(base + k + 1);
+  if (k + 2 < n) r.z = __ldg(base + k + 2);
+  if (k + 3 < n) r.w = __ldg(base + k + 3);
+  return r;
+}
+__device__ __forceinline__ void store4(float* base, int q, int n, bool vec, const float4& v) {
+  if (vec) { stg_stream(reinterpret_cast<float4*>(base) + q, v); return; }
+  const int k = q << 2;
+  if (k < n) base[k] = v.x;
+  if (k + 1 < n) base[k + 1] = v.y;
+  if (k + 2 < n) base[k + 2] = v.z;
+  if (k + 3 < n) base[k + 3] = v.w;
+}
+
+// block-wide sum / max over blockDim.x threads (blockDim multiple of 32, <= 1024); result on all threads
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];      // fixed order: deterministic
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float t = -INFINITY;
+  for (int i = 0; i < nw; ++i) t = fmaxf(t, red[i]);
+  return t;
+}
+
+struct Gauss {
+  int kx, ky;       // int(kp): truncation toward zero
+  double cx, cy;    // int(kp) * 1.0 / stride
+  float vis;
+};
+
+// utils/process.py:262-272
+__device__ __forceinline__ Gauss gauss_setup(float kxf, float kyf, int img_h, int img_w, float stride, float sigma) {
+  Gauss g;
+  g.kx = (int)kxf;
+  g.ky = (int)kyf;
+  const int ulx = (int)((float)g.kx - sigma), uly = (int)((float)g.ky - sigma);
+  const int brx = (int)((float)g.kx + sigma + 1.f), bry = (int)((float)g.ky + sigma + 1.f);
+  g.vis = (brx >= img_w || bry >= img_h || ulx < 0 || uly < 0) ? 0.f : 1.f;
+  g.cx = (double)g.kx * 1.0 / (double)stride;
+  g.cy = (double)g.ky * 1.0 / (double)stride;
+  return g;
+}
+__device__ __forceinline__ float gauss_1d(int k, double c, float sigma) {
+  const float d = (float)((double)k - c);
+  return expf(-(d * d) / (2.f * sigma * sigma));
+}
+__device__ __forceinline__ float gauss_px(const float* ex, const float* ey, int x, int y, const Gauss& g, float sigma) {
+  float v = ex[x] * ey[y];
+  if (fabsf(v - 0.01f) < 1e-5f) {   // within rounding of the cut: decide like the reference, in float64
+    const double dx = (double)x - g.cx, dy = (double)y - g.cy;
+    const double D2 = dx * dx + dy * dy;
+    const double k = exp(-D2 / 2.0 / (double)sigma / (double)sigma);
+    return (k < 0.01) ? 0.f : (float)k;
+  }
+  return (v < 0.01f) ? 0.f : v;
+}
+
+__global__ void __launch_bounds__(256) render_mse_kernel(
+    const float* __restrict__ kps, const float* __restrict__ gate_in, const float* __restrict__ sample_w,
+    const float* __restrict__ pred, long long pB, long long pS, long long pJ, float* __restrict__ grad, long long gB,
+    long long gS, long long gJ, float* __restrict__ target, int B, int S, int J, int H, int W, int img_h, int img_w,
+    float stride, float sigma, const float* __restrict__ grad_scale, float* __restrict__ gate_out,
+    float* __restrict__ per_loss, int vec) {
+  extern __shared__ float sm[];
+  float* ex = sm;            // [W]
+  float* ey = sm + W;        // [H]
+  float* red = sm + W + H;   // [32]
+  const int HW = H * W, nq = (HW + 3) >> 2;
+  const float gs = grad_scale ? *grad_scale : 1.f;
+  const float inv_hw = 1.f / (float)HW;
+  for (long long item = blockIdx.x; item < (long long)B * J; item += gridDim.x) {
+    const int b = (int)(item / J), j = (int)(item % J);
+    const Gauss g = gauss_setup(kps[2 * item], kps[2 * item + 1], img_h, img_w, stride, sigma);
+    __syncthreads();
+    for (int k = threadIdx.x; k < W + H; k += blockDim.x) {
+      if (k < W) ex[k] = gauss_1d(k, g.cx, sigma); else ey[k - W] = gauss_1d(k - W, g.cy, sigma);
+    }
+    __syncthreads();
+    const float gate = (gate_in ? gate_in[item] : 1.f) * g.vis;
+    const float wb = sample_w ? sample_w[b] : 1.f;
+    const float gcoef = gs * 2.f * inv_hw * gate * wb;
+    if (threadIdx.x == 0 && gate_out) gate_out[item] = gate;
+    for (int s = 0; s < S; ++s) {
+      const float* p = pred + (long long)b * pB + (long long)s * pS + (long long)j * pJ;
+      float* gr = grad ? grad + (long long)b * gB + (long long)s * gS + (long long)j * gJ : nullptr;
+      float* tg = (target && s == 0) ? target + item * HW : nullptr;
+      float sse = 0.f;
+      for (int q0 = threadIdx.x; q0 < nq; q0 += 4 * blockDim.x) {
+        float4 pv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = q0 + u * blockDim.x;
+          if (q < nq) pv[u] = load4(p, q, HW, vec);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = q0 + u * blockDim.x;
+          if (q >= nq) continue;
+          const int k = q << 2;
+          float4 t;
+          if (vec) {                                    // W % 4 == 0: the four texels share a row
+            const int y = k / W, x = k - y * W;
+            t.x = gauss_px(ex, ey, x, y, g, sigma); t.y = gauss_px(ex, ey, x + 1, y, g, sigma);
+            t.z = gauss_px(ex, ey, x + 2, y, g, sigma); t.w = gauss_px(ex, ey, x + 3, y, g, sigma);
+          } else {
+            float tt[4];
+            for (int c = 0; c < 4; ++c) {
+              const int kk = min(k + c, HW - 1);
+              tt[c] = gauss_px(ex, ey, kk % W, kk / W, g, sigma);
+            }
+            t = make_float4(tt[0], tt[1], tt[2], tt[3]);
+            if (k + 1 >= HW) { pv[u].y = t.y; }       // padded lanes contribute zero error
+            if (k + 2 >= HW) { pv[u].z = t.z; }
+            if (k + 3 >= HW) { pv[u].w = t.w; }
+          }
+          const float4 d = make_float4(pv[u].x - t.x, pv[u].y - t.y, pv[u].z - t.z, pv[u].w - t.w);
+          sse += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+          if (gr) store4(gr, q, HW, vec, make_float4(gcoef * d.x, gcoef * d.y, gcoef * d.z, gcoef * d.w));
+          if (tg) store4(tg, q, HW, vec, t);
+        }
+      }
+      const float tot = block_sum(sse, red);
+      if (threadIdx.x == 0 && per_loss) per_loss[((long long)b * S + s) * J + j] = ((tot * inv_hw) * gate) * wb;
+    }
+  }
+}
+
+__global__ void render_targets_kernel(const float* __restrict__ kps, int N, int H, int W, int img_h, int img_w,
+                                      float stride, float sigma, float* __restrict__ heatmap,
+                                      float* __restrict__ kps_out) {
+  extern __shared__ float sm[];
+  float* ex = sm;
+  float* ey = sm + W;
+  const int HW = H * W;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    const Gauss g = gauss_setup(kps[3 * n], kps[3 * n + 1], img_h, img_w, stride, sigma);
+    __syncthreads();
+    for (int k = threadIdx.x; k < W + H; k += blockDim.x) {
+      if (k < W) ex[k] = gauss_1d(k, g.cx, sigma); else ey[k - W] = gauss_1d(k - W, g.cy, sigma);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < HW; k += blockDim.x) heatmap[(long long)n * HW + k] = gauss_px(ex, ey, k % W, k / W, g, sigma);
+    if (threadIdx.x == 0 && kps_out) {
+      kps_out[3 * n] = kps[3 * n];
+      kps_out[3 * n + 1] = kps[3 * n + 1];
+      kps_out[3 * n + 2] = kps[3 * n + 2] * g.vis;
+    }
+  }
+}
+
+// Dense-target loss: CH float4 chunks per thread kept in registers so the gradient (which depends
+// on the map's own max through the mask) is written from registers: one HBM read per map.
+template <int CH, int MAXT>
+__global__ void __launch_bounds__(MAXT) dense_mse_kernel(
+    const float* __restrict__ pred, long long pB, long long pS, long long pJ, const float* __restrict__ tgt, int M,
+    long long tM, long long tB, long long tS, long long tJ, const float* __restrict__ coef, int mask_mode, float thr,
+    float* __restrict__ grad, long long gB, long long gS, long long gJ, int B, int S, int J, int H, int W,
+    const float* __restrict__ grad_scale, float* __restrict__ per_loss, float* __restrict__ mask_o,
+    float* __restrict__ vmax_p_o, float* __restrict__ vmax_t_o, int vec) {
+  __shared__ float red[32];
+  const int HW = H * W, nq = (HW + 3) >> 2;
+  const float gs = grad_scale ? *grad_scale : 1.f;
+  const float inv_hw = 1.f / (float)HW;
+  const float invM = (float)M;
+  for (long long item = blockIdx.x; item < (long long)B * J; item += gridDim.x) {
+    const int b = (int)(item / J), j = (int)(item % J);
+    const float cf = coef ? coef[item] : 1.f;
+    float4 tb[CH];
+    float vt = -INFINITY;
+    for (int s = 0; s < S; ++s) {
+      if (s == 0 || tS != 0) {
+        // float32 mean over the M teacher maps in index order (torch.mean): sum, then one division
+        const float* t0 = tgt + (long long)b * tB + (long long)s * tS + (long long)j * tJ;
+        float tmx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+          const int q = threadIdx.x + u * blockDim.x;
+          if (q < nq) {
+            float4 a = load4(t0, q, HW, vec);
+            for (int m = 1; m < M; ++m) {
+              const float4 c = load4(t0 + (long long)m * tM, q, HW, vec);
+              a.x = __fadd_rn(a.x, c.x); a.y = __fadd_rn(a.y, c.y); a.z = __fadd_rn(a.z, c.z); a.w = __fadd_rn(a.w, c.w);
+            }
+            if (M > 1) { a.x = __fdiv_rn(a.x, invM); a.y = __fdiv_rn(a.y, invM); a.z = __fdiv_rn(a.z, invM); a.w = __fdiv_rn(a.w, invM); }
+            tb[u] = a;
+            const int k = q << 2;
+            tmx = fmaxf(tmx, a.x);
+            if (vec || k + 1 < HW) tmx = fmaxf(tmx, a.y);
+            if (vec || k + 2 < HW) tmx = fmaxf(tmx, a.z);
+            if (vec || k + 3 < HW) tmx = fmaxf(tmx, a.w);
+          }
+        }
+        if (mask_mode != 0 || vmax_t_o) vt = block_max(tmx, red);
+      }
+      const float* p = pred + (long long)b * pB + (long long)s * pS + (long long)j * pJ;
+      float4 d[CH];
+      float sse = 0.f, pmx = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int q = threadIdx.x + u * blockDim.x;
+        if (q < nq) d[u] = load4(p, q, HW, vec);
+      }
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int q = threadIdx.x + u * blockDim.x;
+        if (q < nq) {
+          const int k = q << 2;
+          const float4 pv = d[u];
+          pmx = fmaxf(pmx, pv.x);
+          if (vec || k + 1 < HW) pmx = fmaxf(pmx, pv.y);
+          if (vec || k + 2 < HW) pmx = fmaxf(pmx, pv.z);
+          if (vec || k + 3 < HW) pmx = fmaxf(pmx, pv.w);
+          d[u] = make_float4(pv.x - tb[u].x, pv.y - tb[u].y, pv.z - tb[u].z, pv.w - tb[u].w);
+          sse += d[u].x * d[u].x + d[u].y * d[u].y + d[u].z * d[u].z + d[u].w * d[u].w;   // padded lanes: 0-0
+        }
+      }
+      const float tot = block_sum(sse, red);
+      float mk = 1.f, vp = 0.f;
+      if (mask_mode == 1 || vmax_p_o) vp = block_max(pmx, red);
+      if (mask_mode == 1) mk = (vp >= thr && vt >= thr) ? 1.f : 0.f;
+      else if (mask_mode == 2) mk = (vt >= thr) ? 1.f : 0.f;
+      const long long o = ((long long)b * S + s) * J + j;
+      if (threadIdx.x == 0) {
+        if (per_loss) per_loss[o] = (tot * inv_hw) * cf;
+        if (mask_o) mask_o[o] = mk;
+        if (vmax_p_o) vmax_p_o[o] = vp;
+        if (vmax_t_o) vmax_t_o[o] = vt;
+      }
+      if (grad) {
+        float* gr = grad + (long long)b * gB + (long long)s * gS + (long long)j * gJ;
+        const float gcoef = gs * 2.f * inv_hw * cf * mk;
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+          const int q = threadIdx.x + u * blockDim.x;
+          if (q < nq) store4(gr, q, HW, vec, make_float4(gcoef * d[u].x, gcoef * d[u].y, gcoef * d[u].z, gcoef * d[u].w));
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) loss_finalize_kernel(const float* __restrict__ per_loss,
+                                                              const float* __restrict__ mask,
+                                                              const float* __restrict__ gate, long long BSJ,
+                                                              long long BJ, double* out) {
+  __shared__ double red[4][32];
+  double s = 0.0, np = 0.0, ns = 0.0, ng = 0.0;
+  for (long long i = threadIdx.x; i < BSJ; i += blockDim.x) {
+    const float l = per_loss[i], m = mask ? mask[i] : 1.f;
+    s += (double)l * (double)m;
+    np += (l > 0.f) ? 1.0 : 0.0;
+    ns += (m > 0.f) ? 1.0 : 0.0;
+  }
+  if (gate) { for (long long i = threadIdx.x; i < BJ; i += blockDim.x) ng += (gate[i] > 0.f) ? 1.0 : 0.0; }
+  else if (threadIdx.x == 0) ng = (double)BJ;
+  s = warp_sum(s); np = warp_sum(np); ns = warp_sum(ns); ng = warp_sum(ng);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[0][w] = s; red[1][w] = np; red[2][w] = ns; red[3][w] = ng; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[threadIdx.x][i];
+    out[threadIdx.x] = t;
+  }
+}
+
+// gate_out = gate_in * visibility(kps) (process.py:262-268); count = #(gate_out > 0);
+// *grad_scale = loss_weight / (S * count), or loss_weight when count == 0 (MT_UBPL.py:266).
+__global__ void __launch_bounds__(1024) gate_prepare_kernel(const float* __restrict__ kps, const float* __restrict__ gate_in,
+                                                             long long n, int img_h, int img_w, float stride, float sigma,
+                                                             int S, float loss_weight, float* __restrict__ gate_out,
+                                                             float* __restrict__ grad_scale, int32_t* __restrict__ count_out) {
+  __shared__ int red[32];
+  int c = 0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const Gauss g = gauss_setup(kps[2 * i], kps[2 * i + 1], img_h, img_w, stride, sigma);
+    const float gt = (gate_in ? gate_in[i] : 1.f) * g.vis;
+    if (gate_out) gate_out[i] = gt;
+    c += (gt > 0.f) ? 1 : 0;
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    if (count_out) *count_out = S * t;
+    if (grad_scale) *grad_scale = (t > 0) ? loss_weight / (float)(S * t) : loss_weight;
+  }
+}
+
+__global__ void scale_inplace_kernel(float* __restrict__ x, long long n, const float* __restrict__ scale) {
+  const float s = *scale;
+  const long long n4 = n >> 2;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = x4[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    x4[i] = v;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= s;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace ubpl
+
+using namespace ubpl;
+
+extern "C" int ubpl_render_mse(const float* kps, const float* gate_in, const float* sample_w, const float* pred,
+                               int64_t pB, int64_t pS, int64_t pJ, float* grad, int64_t gB, int64_t gS, int64_t gJ,
+                               float* target, int B, int S, int J, int H, int W, int img_h, int img_w, float stride,
+                               float sigma, const float* grad_scale, float* gate_out, float* per_loss, void* stream) {
+  UBPL_REQUIRE(kps && pred, "ubpl_render_mse: NULL pointer");
+  UBPL_REQUIRE(B >= 0 && S >= 1 && J >= 0 && H > 0 && W > 0 && stride > 0.f && sigma > 0.f, "ubpl_render_mse: bad arguments");
+  const long long BJ = (long long)B * J;
+  if (BJ == 0) return UBPL_OK;
+  const int HW = H * W;
+  int vec = (W % 4 == 0) && aligned16(pred) && pB % 4 == 0 && pS % 4 == 0 && pJ % 4 == 0;
+  if (grad) vec = vec && aligned16(grad) && gB % 4 == 0 && gS % 4 == 0 && gJ % 4 == 0;
+  if (target) vec = vec && aligned16(target) && (HW % 4 == 0);
+  const size_t smem = (size_t)(W + H + 32) * sizeof(float);
+  const int grid = (int)(BJ < (long long)sm_count() * 8 ? BJ : (long long)sm_count() * 8);
+  render_mse_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS,
+                                                               gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma,
+                                                               grad_scale, gate_out, per_loss, vec);
+  return check_launch("ubpl_render_mse");
+}
+
+extern "C" int ubpl_render_targets(const float* kps, int N, int H, int W, int img_h, int img_w, float stride,
+                                   float sigma, float* heatmap, float* kps_out, void* stream) {
+  UBPL_REQUIRE(kps && heatmap && N >= 0 && H > 0 && W > 0 && stride > 0.f && sigma > 0.f, "ubpl_render_targets: bad arguments");
+  if (N == 0) return UBPL_OK;
+  const int grid = N < sm_count() * 8 ? N : sm_count() * 8;
+  render_targets_kernel<<<grid, 256, (size_t)(W + H) * sizeof(float), (cudaStream_t)stream>>>(kps, N, H, W, img_h, img_w,
+                                                                                              stride, sigma, heatmap, kps_out);
+  return check_launch("ubpl_render_targets");
+}
+
+extern "C" int ubpl_dense_mse(const float* pred, int64_t pB, int64_t pS, int64_t pJ, const float* tgt, int M,
+                              int64_t tM, int64_t tB, int64_t tS, int64_t tJ, const float* coef, int mask_mode,
+                              float thr, float* grad, int64_t gB, int64_t gS, int64_t gJ, int B, int S, int J, int H,
+                              int W, const float* grad_scale, float* per_loss, float* mask, float* vmax_p,
+                              float* vmax_t, void* stream) {
+  UBPL_REQUIRE(pred && tgt, "ubpl_dense_mse: NULL pointer");
+  UBPL_REQUIRE(B >= 0 && S >= 1 && J >= 0 && H > 0 && W > 0 && M >= 1, "ubpl_dense_mse: bad dims");
+  UBPL_REQUIRE(mask_mode >= 0 && mask_mode <= 2, "ubpl_dense_mse: mask_mode must be 0, 1 or 2");
+  const long long BJ = (long long)B * J;
+  if (BJ == 0) return UBPL_OK;
+  const long long HW = (long long)H * W;
+  UBPL_REQUIRE(HW <= 65536, "ubpl_dense_mse: heat-maps above 65536 texels are not supported");
+  int vec = (HW % 4 == 0) && aligned16(pred) && pB % 4 == 0 && pS % 4 == 0 && pJ % 4 == 0 && aligned16(tgt) &&
+            tM % 4 == 0 && tB % 4 == 0 && tS % 4 == 0 && tJ % 4 == 0;
+  if (grad) vec = vec && aligned16(grad) && gB % 4 == 0 && gS % 4 == 0 && gJ % 4 == 0;
+  const int nq = (int)((HW + 3) / 4);
+  const int grid = (int)(BJ < (long long)sm_count() * 16 ? BJ : (long long)sm_count() * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nq <= 4 * 256) {
+    int threads = ((nq + 3) / 4 + 31) / 32 * 32;
+    if (threads < 32) threads = 32;
+    dense_mse_kernel<4, 256><<<grid, threads, 0, st>>>(pred, pB, pS, pJ, tgt, M, tM, tB, tS, tJ, coef, mask_mode, thr, grad,
+                                                       gB, gS, gJ, B, S, J, H, W, grad_scale, per_loss, mask, vmax_p, vmax_t, vec);
+  } else if (nq <= 4 * 1024) {
+    int threads = ((nq + 3) / 4 + 31) / 32 * 32;
+    dense_mse_kernel<4, 1024><<<grid, threads, 0, st>>>(pred, pB, pS, pJ, tgt, M, tM, tB, tS, tJ, coef, mask_mode, thr, grad,
+                                                  gB, gS, gJ, B, S, J, H, W, grad_scale, per_loss, mask, vmax_p, vmax_t, vec);
+  } else {
+    int threads = ((nq + 15) / 16 + 31) / 32 * 32;
+    dense_mse_kernel<16, 1024><<<grid, threads, 0, st>>>(pred, pB, pS, pJ, tgt, M, tM, tB, tS, tJ, coef, mask_mode, thr, grad,
+                                                   gB, gS, gJ, B, S, J, H, W, grad_scale, per_loss, mask, vmax_p, vmax_t, vec);
+  }
+  return check_launch("ubpl_dense_mse");
+}
+
+extern "C" int ubpl_loss_finalize(const float* per_loss, const float* mask, const float* gate, int B, int S, int J,
+                                  double* out, void* stream) {
+  UBPL_REQUIRE(per_loss && out && B >= 0 && S >= 1 && J >= 0, "ubpl_loss_finalize: bad arguments");
+  loss_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(per_loss, mask, gate, (long long)B * S * J, (long long)B * J, out);
+  return check_launch("ubpl_loss_finalize");
+}
+
+extern "C" int ubpl_gate_prepare(const float* kps, const float* gate_in, int64_t n, int img_h, int img_w, float stride,
+                                 float sigma, int S, float loss_weight, float* gate_out, float* grad_scale,
+                                 int32_t* count_out, void* stream) {
+  UBPL_REQUIRE(kps && n >= 0 && S >= 1 && stride > 0.f && sigma > 0.f, "ubpl_gate_prepare: bad arguments");
+  gate_prepare_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(kps, gate_in, n, img_h, img_w, stride, sigma, S, loss_weight,
+                                                            gate_out, grad_scale, count_out);
+  return check_launch("ubpl_gate_prepare");
+}
+
+extern "C" int ubpl_scale_inplace(float* x, int64_t n, const float* scale, void* stream) {
+  UBPL_REQUIRE(x && scale && n >= 0, "ubpl_scale_inplace: bad arguments");
+  UBPL_REQUIRE(aligned16(x), "ubpl_scale_inplace: x must be 16-byte aligned");
+  if (n == 0) return UBPL_OK;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+  if (blocks < 1) blocks = 1;
+  scale_inplace_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, scale);
+  return check_launch("ubpl_scale_inplace");
+}

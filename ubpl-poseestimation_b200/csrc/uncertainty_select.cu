@@ -1,0 +1,371 @@
+// K2: per-joint uncertainty (cross-view / cross-model dispersion) and pseudo-label selection.
+//
+// Reference semantics (file:line in /root/reference):
+//   utils/evaluation.py:40-58    uncertainty_fromDistance
+//   utils/process.py:53-68       coord_distance (python floats: ((dx)**2+(dy)**2)**0.5), coord_avgDistance
+//   utils/business.py:109-161    assess_pseudo_unc2 (two teachers: intDist, extDist, ensemble weights)
+//   utils/business.py:43-46,173-217  _calReliabilityThr / filter_pseudo2 (global quantile, strict >)
+//   utils/business.py:237-261,375-376  pseudo_filter_mixUnc / _calUncValue (fixed threshold)
+//
+// The data here is tiny (K*M*B*J coordinates); everything is float64 in the reference's python
+// expression order so the masks come out bit-identical.  One thread per (sample, joint).
+#include "common.cuh"
+
+namespace ubpl {
+
+int pow_table(const int32_t** keys, const double** vals, int* n, int* rmax);
+
+struct PowTab {
+  const int32_t* key;
+  const double* val;
+  int n, rmax;
+};
+
+// python: ((x1-x2)**2 + (y1-y2)**2) ** 0.5  == libm pow(r, 0.5); see api.cu for the table.
+__device__ __forceinline__ double py_dist(double x1, double y1, double x2, double y2, const PowTab& T) {
+  const double dx = __dsub_rn(x1, x2), dy = __dsub_rn(y1, y2);
+  const double r = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+  double d = sqrt(r);
+  if (r <= (double)T.rmax) {
+    const int ri = (int)r;
+    if ((double)ri == r) {
+      int lo = 0, hi = T.n - 1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int k = T.key[mid];
+        if (k == ri) { d = T.val[mid]; break; }
+        if (k < ri) lo = mid + 1; else hi = mid - 1;
+      }
+    }
+  }
+  return d;
+}
+
+__global__ void view_dispersion_kernel(const float* __restrict__ preds, int K, long long BJ, float* out_mean,
+                                       double* out_dist, float* out_unc32, uint8_t* out_legal, uint32_t* max_bits,
+                                       int sentinel_illegal, PowTab T) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float u32 = 0.f;
+  if (i < BJ) {
+    float sx = preds[2 * i], sy = preds[2 * i + 1];
+    bool legal = (sx >= 0.f) && (sy >= 0.f);
+    for (int k = 1; k < K; ++k) {
+      const float x = preds[2 * ((long long)k * BJ + i)], y = preds[2 * ((long long)k * BJ + i) + 1];
+      sx = __fadd_rn(sx, x);
+      sy = __fadd_rn(sy, y);
+      legal = legal && (x >= 0.f) && (y >= 0.f);
+    }
+    const float mx = __fdiv_rn(sx, (float)K), my = __fdiv_rn(sy, (float)K);   // torch.mean (float32)
+    double acc = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double x = (double)preds[2 * ((long long)k * BJ + i)], y = (double)preds[2 * ((long long)k * BJ + i) + 1];
+      acc = __dadd_rn(acc, py_dist(x, y, (double)mx, (double)my, T));        // sum(dists)
+    }
+    const double avg = __ddiv_rn(acc, (double)K);                             // / len(dists)
+    u32 = (float)avg;                                                         // torch.tensor(dist_avg)
+    if (out_mean) { out_mean[2 * i] = mx; out_mean[2 * i + 1] = my; }
+    if (out_dist) out_dist[i] = (sentinel_illegal && !legal) ? 999.0 : avg;   // business.py:123 sentinel
+    if (out_unc32) out_unc32[i] = u32;
+    if (out_legal) out_legal[i] = legal ? 1 : 0;
+  }
+  if (max_bits) {
+    const float m = warp_max(u32);                                            // distances are >= 0
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(max_bits, __float_as_uint(m));
+  }
+}
+
+__global__ void unc_normalize_kernel(const float* __restrict__ unc32, const uint32_t* __restrict__ max_bits,
+                                     long long n, float* out_unc, float* out_uncW) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float mx = __uint_as_float(*max_bits);
+  const float u = __fdiv_rn(unc32[i], mx);            // unc / unc.max()  (0/0 -> NaN like torch)
+  if (out_unc) out_unc[i] = u;
+  if (out_uncW) out_uncW[i] = expf(-u);
+}
+
+__global__ void assess_dual_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                                   const float* __restrict__ pmean, const float* __restrict__ a1,
+                                   const float* __restrict__ a2, int K, long long BJ, double* legal_o,
+                                   double* int1_o, double* int2_o, double* ext_o, double* w1_o, double* w2_o,
+                                   double* coord_o, float* coord32_o, int32_t* zero_div, PowTab T) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BJ) return;
+  const double x1 = p1[2 * i], y1 = p1[2 * i + 1], x2 = p2[2 * i], y2 = p2[2 * i + 1];
+  const bool ori_legal = (x1 >= 0 && y1 >= 0) && (x2 >= 0 && y2 >= 0);
+  bool g1 = true, g2 = true;
+  for (int k = 0; k < K; ++k) {
+    const long long o = 2 * ((long long)k * BJ + i);
+    g1 = g1 && (a1[o] >= 0.f) && (a1[o + 1] >= 0.f);
+    g2 = g2 && (a2[o] >= 0.f) && (a2[o + 1] >= 0.f);
+  }
+  double legal = ori_legal ? 1.0 : 0.0, w1 = 0.5, w2 = 0.5, d1 = 999.0, d2 = 999.0, ext = 999.0;
+  // third pred-set: bus.preds_mean(p1, p2) = torch.mean(stack([p1, p2], -1), -1) in float32 (business.py:297-300)
+  double cx = pmean ? (double)pmean[2 * i] : (double)__fdiv_rn(__fadd_rn(p1[2 * i], p2[2 * i]), 2.f);
+  double cy = pmean ? (double)pmean[2 * i + 1] : (double)__fdiv_rn(__fadd_rn(p1[2 * i + 1], p2[2 * i + 1]), 2.f);
+  if (ori_legal && g1 && g2) {
+    // coord_avgDistance: itertools.combinations order, sequential float64 sum, / count
+    double s1 = 0.0, s2 = 0.0;
+    int cnt = 0;
+    for (int u = 0; u < K; ++u)
+      for (int v = u + 1; v < K; ++v) {
+        const long long ou = 2 * ((long long)u * BJ + i), ov = 2 * ((long long)v * BJ + i);
+        s1 = __dadd_rn(s1, py_dist(a1[ou], a1[ou + 1], a1[ov], a1[ov + 1], T));
+        s2 = __dadd_rn(s2, py_dist(a2[ou], a2[ou + 1], a2[ov], a2[ov + 1], T));
+        ++cnt;
+      }
+    d1 = __ddiv_rn(s1, (double)cnt);      // K < 2: 0/0 -> NaN (the reference raises ZeroDivisionError)
+    d2 = __ddiv_rn(s2, (double)cnt);
+    const double den = __dadd_rn(d1, d2);
+    if (den == 0.0) {
+      atomicAdd(zero_div, 1);             // business.py:135 divides by zero here
+    } else {
+      w1 = __ddiv_rn(d1, den);
+      w2 = __ddiv_rn(d2, den);
+    }
+    cx = __dadd_rn(__dmul_rn(w1, x1), __dmul_rn(w2, x2));
+    cy = __dadd_rn(__dmul_rn(w1, y1), __dmul_rn(w2, y2));
+    legal = 1.0;
+    double se = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const long long o = 2 * ((long long)k * BJ + i);
+      se = __dadd_rn(se, py_dist(a1[o], a1[o + 1], a2[o], a2[o + 1], T));
+    }
+    ext = __ddiv_rn(se, (double)K);
+  }
+  if (legal_o) legal_o[i] = legal;
+  if (int1_o) int1_o[i] = d1;
+  if (int2_o) int2_o[i] = d2;
+  if (ext_o) ext_o[i] = ext;
+  if (w1_o) w1_o[i] = w1;
+  if (w2_o) w2_o[i] = w2;
+  if (coord_o) { coord_o[2 * i] = cx; coord_o[2 * i + 1] = cy; }
+  if (coord32_o) { coord32_o[2 * i] = (float)cx; coord32_o[2 * i + 1] = (float)cy; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// selection
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t key_of(double v) {
+  const uint64_t b = (uint64_t)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double value_of(uint64_t k) {
+  const uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+__global__ void extrema_init_kernel(double* ext) {
+  ext[0] = 0.0;     // dist_max over dist < 999 (business.py:176)
+  ext[1] = 999.0;   // dist_min
+}
+__global__ void extrema_kernel(const double* __restrict__ dist, long long n, double* ext) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double e = dist[i];
+  // distances are >= 0, so the raw bit pattern orders like the value
+  if (e > 0.0 && e < 999.0) atomicMax(reinterpret_cast<unsigned long long*>(ext), (unsigned long long)__double_as_longlong(e));
+  if (e >= 0.0 && e < 999.0) atomicMin(reinterpret_cast<unsigned long long*>(ext + 1), (unsigned long long)__double_as_longlong(e));
+}
+
+__global__ void reliability_kernel(const double* __restrict__ dist, const double* __restrict__ legal, long long n,
+                                   const double* __restrict__ ext, double reliableDistMin, double* rel,
+                                   uint64_t* keys) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double dmax = ext[0], dmin = ext[1];
+  if (dmax == 0.0) dmax = 999.0;                      // business.py:181
+  if (dmin > reliableDistMin) dmin = reliableDistMin; // business.py:182
+  const double e = dist[i];
+  const double e2 = (e != 999.0) ? e : dmax;
+  const double unc = (legal[i] > 0.0) ? __ddiv_rn(__dsub_rn(e2, dmin), __dsub_rn(dmax, dmin)) : 1.0;
+  const double r = __dsub_rn(1.0, unc);
+  rel[i] = r;
+  if (keys) keys[i] = key_of(r);
+}
+
+__global__ void key_hist_kernel(const uint64_t* __restrict__ keys, long long n, const uint64_t* __restrict__ prefix,
+                                int shift, uint32_t* hist) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = keys[i];
+  if (shift < 48) {
+    const uint64_t pf = *prefix;
+    if ((k >> (shift + 16)) != (pf >> (shift + 16))) return;
+  }
+  atomicAdd(hist + (uint32_t)((k >> shift) & 0xffffu), 1u);
+}
+
+// one CTA of 1024 threads; thread t owns the 64 bins [65535-64t-63, 65535-64t] (descending order)
+__global__ void __launch_bounds__(1024) select_descend_kernel(const uint32_t* __restrict__ hist, int shift,
+                                                               uint64_t* prefix, long long* k_rem) {
+  __shared__ unsigned long long part[1024];
+  const int t = threadIdx.x;
+  const int top = 65535 - 64 * t;
+  unsigned long long s = 0;
+  for (int q = 0; q < 64; ++q) s += hist[top - q];
+  part[t] = s;
+  __syncthreads();
+  if (t == 0) {
+    const unsigned long long k = (unsigned long long)*k_rem;
+    unsigned long long acc = 0;
+    int owner = 1023;
+    for (int u = 0; u < 1024; ++u) {
+      if (acc + part[u] > k) { owner = u; break; }
+      acc += part[u];
+    }
+    int bin = 65535 - 64 * owner;
+    for (int q = 0; q < 64; ++q) {
+      const unsigned long long c = hist[65535 - 64 * owner - q];
+      if (acc + c > k) { bin = 65535 - 64 * owner - q; break; }
+      acc += c;
+      bin = 65535 - 64 * owner - q;
+    }
+    const uint64_t mask = ~(0xffffull << shift);
+    *prefix = ((shift < 48 ? *prefix : 0ull) & mask) | ((uint64_t)bin << shift);
+    *k_rem = (long long)(k - acc);
+  }
+}
+
+__global__ void select_apply_kernel(const double* __restrict__ rel, long long n, int J,
+                                    const uint64_t* __restrict__ prefix, double reliableThr, uint8_t* enable,
+                                    float* gate32, int32_t* counts, double* thr_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const double kth = value_of(*prefix);
+  const double thr = (kth > reliableThr) ? kth : reliableThr;     // max(args.reliableThr, scores[k])
+  if (i == 0 && thr_out) *thr_out = thr;
+  if (i >= n) return;
+  const bool en = rel[i] > thr;
+  if (enable) enable[i] = en ? 1 : 0;
+  if (gate32) gate32[i] = en ? 1.f : 0.f;
+  if (en && counts) {
+    atomicAdd(counts + (int)(i % J), 1);
+    atomicAdd(counts + J, 1);
+  }
+}
+
+__global__ void select_fixed_kernel(const double* __restrict__ dist, const double* __restrict__ legal, long long n,
+                                    int J, double distThrMax, uint8_t* enable, float* gate32, int32_t* counts,
+                                    double* unc_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double thr = __dsub_rn(1.0, exp(-__ddiv_rn(__dmul_rn(distThrMax, 3.0), 5.0)));   // _calUncValue(distThrMax*3)
+  const double unc = __dsub_rn(1.0, exp(-__ddiv_rn(dist[i], 5.0)));
+  const bool en = (legal == nullptr || legal[i] > 0.0) && (unc <= thr);
+  if (enable) enable[i] = en ? 1 : 0;
+  if (gate32) gate32[i] = en ? 1.f : 0.f;
+  if (unc_out) unc_out[i] = unc;
+  if (en && counts) {
+    atomicAdd(counts + (int)(i % J), 1);
+    atomicAdd(counts + J, 1);
+  }
+}
+
+static inline int blocks_for(long long n, int t) { return (int)((n + t - 1) / t); }
+
+}  // namespace ubpl
+
+using namespace ubpl;
+
+#define GET_POWTAB(T)                                                            \
+  PowTab T;                                                                      \
+  {                                                                              \
+    int rc_ = pow_table(&T.key, &T.val, &T.n, &T.rmax);                           \
+    if (rc_ != UBPL_OK) return rc_;                                               \
+  }
+
+extern "C" int ubpl_view_dispersion(const float* preds, int K, int B, int J, float* out_mean, double* out_dist,
+                                    float* out_unc32, uint8_t* out_legal, uint32_t* max_bits, int sentinel_illegal,
+                                    void* stream) {
+  UBPL_REQUIRE(preds != nullptr && K >= 1 && B >= 0 && J >= 0, "ubpl_view_dispersion: bad arguments");
+  const long long BJ = (long long)B * J;
+  if (BJ == 0) return UBPL_OK;
+  GET_POWTAB(T);
+  view_dispersion_kernel<<<blocks_for(BJ, 128), 128, 0, (cudaStream_t)stream>>>(preds, K, BJ, out_mean, out_dist,
+                                                                                 out_unc32, out_legal, max_bits, sentinel_illegal, T);
+  return check_launch("ubpl_view_dispersion");
+}
+
+extern "C" int ubpl_unc_normalize(const float* unc32, const uint32_t* max_bits, int64_t n, float* out_unc,
+                                  float* out_uncW, void* stream) {
+  UBPL_REQUIRE(unc32 && max_bits && n >= 0, "ubpl_unc_normalize: bad arguments");
+  if (n == 0) return UBPL_OK;
+  unc_normalize_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(unc32, max_bits, n, out_unc, out_uncW);
+  return check_launch("ubpl_unc_normalize");
+}
+
+extern "C" int ubpl_assess_dual(const float* p1, const float* p2, const float* pmean, const float* aug1,
+                                const float* aug2, int K, int B, int J, double* legal, double* intDist1,
+                                double* intDist2, double* extDist, double* w1, double* w2, double* coord,
+                                float* coord32, int32_t* zero_div, void* stream) {
+  UBPL_REQUIRE(p1 && p2 && aug1 && aug2 && zero_div, "ubpl_assess_dual: NULL pointer");
+  UBPL_REQUIRE(K >= 1 && B >= 0 && J >= 0, "ubpl_assess_dual: bad dims");
+  const long long BJ = (long long)B * J;
+  if (BJ == 0) return UBPL_OK;
+  GET_POWTAB(T);
+  assess_dual_kernel<<<blocks_for(BJ, 128), 128, 0, (cudaStream_t)stream>>>(p1, p2, pmean, aug1, aug2, K, BJ, legal,
+                                                                             intDist1, intDist2, extDist, w1, w2,
+                                                                             coord, coord32, zero_div, T);
+  return check_launch("ubpl_assess_dual");
+}
+
+extern "C" int ubpl_dist_extrema(const double* dist, int64_t n, double* ext, void* stream) {
+  UBPL_REQUIRE(ext && (dist || n == 0) && n >= 0, "ubpl_dist_extrema: bad arguments");
+  extrema_init_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ext);
+  if (n > 0) extrema_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dist, n, ext);
+  return check_launch("ubpl_dist_extrema");
+}
+
+extern "C" int ubpl_reliability(const double* dist, const double* legal, int64_t n, const double* ext,
+                                double reliableDistMin, double* reliability, uint64_t* keys, void* stream) {
+  UBPL_REQUIRE(dist && legal && ext && reliability && n >= 0, "ubpl_reliability: bad arguments");
+  if (n == 0) return UBPL_OK;
+  reliability_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dist, legal, n, ext, reliableDistMin,
+                                                                            reliability, keys);
+  return check_launch("ubpl_reliability");
+}
+
+extern "C" int ubpl_key_histogram(const uint64_t* keys, int64_t n, const uint64_t* prefix, int shift,
+                                  uint32_t* hist, void* stream) {
+  UBPL_REQUIRE(hist && (keys || n == 0) && n >= 0, "ubpl_key_histogram: bad arguments");
+  UBPL_REQUIRE(shift == 48 || shift == 32 || shift == 16 || shift == 0, "ubpl_key_histogram: shift must be 48/32/16/0");
+  UBPL_REQUIRE(shift == 48 || prefix != nullptr, "ubpl_key_histogram: prefix is NULL");
+  cudaError_t e = cudaMemsetAsync(hist, 0, 65536 * sizeof(uint32_t), (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("ubpl_key_histogram: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+  if (n > 0) key_hist_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(keys, n, prefix, shift, hist);
+  return check_launch("ubpl_key_histogram");
+}
+
+extern "C" int ubpl_select_descend(const uint32_t* hist, int shift, uint64_t* prefix, int64_t* k_rem, void* stream) {
+  UBPL_REQUIRE(hist && prefix && k_rem, "ubpl_select_descend: NULL pointer");
+  UBPL_REQUIRE(shift == 48 || shift == 32 || shift == 16 || shift == 0, "ubpl_select_descend: bad shift");
+  select_descend_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(hist, shift, prefix, reinterpret_cast<long long*>(k_rem));
+  return check_launch("ubpl_select_descend");
+}
+
+extern "C" int ubpl_select_apply(const double* reliability, int64_t n, int J, const uint64_t* prefix,
+                                 double reliableThr, uint8_t* enable, float* gate32, int32_t* counts,
+                                 double* thr_out, void* stream) {
+  UBPL_REQUIRE(reliability && prefix && (enable || gate32) && n >= 0 && J >= 1, "ubpl_select_apply: bad arguments");
+  if (counts) {
+    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)(J + 1) * sizeof(int32_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("ubpl_select_apply: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+  }
+  const long long nn = n > 0 ? n : 1;
+  select_apply_kernel<<<blocks_for(nn, 256), 256, 0, (cudaStream_t)stream>>>(reliability, n, J, prefix, reliableThr,
+                                                                             enable, gate32, counts, thr_out);
+  return check_launch("ubpl_select_apply");
+}
+
+extern "C" int ubpl_select_fixed(const double* dist, const double* legal, int64_t n, int J, double distThrMax,
+                                 uint8_t* enable, float* gate32, int32_t* counts, double* unc_out, void* stream) {
+  UBPL_REQUIRE(dist && (enable || gate32) && n >= 0 && J >= 1, "ubpl_select_fixed: bad arguments");
+  if (counts) {
+    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)(J + 1) * sizeof(int32_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("ubpl_select_fixed: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+  }
+  if (n == 0) return UBPL_OK;
+  select_fixed_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dist, legal, n, J, distThrMax, enable,
+                                                                            gate32, counts, unc_out);
+  return check_launch("ubpl_select_fixed");
+}

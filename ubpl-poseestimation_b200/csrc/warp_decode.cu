@@ -1,0 +1,447 @@
+// K1: back-warp + flip + arg-max decode, fused; and the materialising warp (affine_back2).
+//
+// Reference semantics (file:line in /root/reference):
+//   utils/augment.py:37-47      affine_back2  = F.affine_grid + F.grid_sample(bilinear, zeros,
+//                               align_corners=True) + per-sample W mirror
+//   utils/udaap/evaluation.py:13-30   get_preds (first arg-max, 1-based, zero where max <= 0)
+//   utils/udaap/transforms.py:151-168 transform(invert=1) -> trunc + 1 (image space)
+//   utils/process.py:362-373    quarter-offset refinement (kps_fromHeatmap2)
+//
+// Float op order of the warp is ATen's CPU order, recovered bit-exactly (oracle/ubpl_oracle.py):
+//   base grid  lin(k) = k < n/2 ? fma(step,k,-1) : fma(-step,n-1-k,1),  step = 2/(n-1)
+//   gx = fma(y, t01, x*t00) + t02;  ix = (gx+1)*((W-1)/2);  w = ix-floor(ix); e = 1-w; ...
+//   out = fma(v_se, se, fma(v_sw, sw, fma(v_ne, ne, v_nw*nw)))
+// All of it is written with explicit _rn intrinsics so nvcc cannot contract or reassociate.
+//
+// Decode strategy (one warp per heat-map, map staged in shared memory by a 1-D bulk async copy):
+// a bilinear sample is a convex combination of its four corner texels (zero outside), so an
+// output pixel can only reach the maximum if one of its corners is >= the maximum.  The warp
+//   A) scans the staged map for its max / min / arg-max (conflict-free 128-bit LDS),
+//   L) evaluates exactly the <= 30 output pixels around the pre-image of the arg-max texel;
+//      their best value L is a lower bound of the warped maximum,
+//   B) rescans for "candidate" texels v >= T = L - (L + max|v|) * 2^-19 (the slack covers every
+//      rounding in the interpolation) and takes their bounding box,
+//   C) evaluates exactly every output pixel whose 2x2 footprint can touch that box and reduces
+//      (value, canonical index) with torch.max's first-index tie rule.
+// Pixels outside C have all four corners < T, hence a computed value < L: they cannot win or tie.
+// Maps where this does not apply (max <= 0 after warp, NaN/Inf, singular theta, huge candidate
+// box) are decoded exhaustively by the same warp, so the result is exact in every case.
+#include "common.cuh"
+
+namespace ubpl {
+
+struct WDParams {
+  const float* maps;
+  long long sV, sB, sJ;
+  int V, B, J, H, W;
+  const float* theta;
+  const uint8_t* flip;
+  const double* dec;
+  int do_warp, refine, use_bulk, nbuf;
+  int32_t* out_idx;
+  float* out_max;
+  float* out_xy;
+  float* out_hm_xy;
+  unsigned long long* stats;
+};
+
+struct Xform {
+  float t00, t01, t02, t10, t11, t12;
+  float stepx, stepy, sfx, sfy;
+  int H, W;
+  bool flip;
+};
+
+__device__ __forceinline__ float lin_coord(int k, int n, float step) {
+  if (n <= 1) return 0.f;  // ATen linspace_from_neg_one: a single step sits at 0
+  return (k < (n >> 1)) ? __fmaf_rn(step, (float)k, -1.f) : __fmaf_rn(-step, (float)(n - 1 - k), 1.f);
+}
+
+// Exact bilinear sample of output pixel (row i, column jw in the WARPED frame, i.e. before the
+// mirror) from the staged source map s[H*W].
+__device__ __forceinline__ float eval_px(const float* __restrict__ s, const Xform& X, int i, int jw) {
+  const float xl = lin_coord(jw, X.W, X.stepx);
+  const float yl = lin_coord(i, X.H, X.stepy);
+  const float gx = __fadd_rn(__fmaf_rn(yl, X.t01, __fmul_rn(xl, X.t00)), X.t02);
+  const float gy = __fadd_rn(__fmaf_rn(yl, X.t11, __fmul_rn(xl, X.t10)), X.t12);
+  const float ix = __fmul_rn(__fadd_rn(gx, 1.f), X.sfx);
+  const float iy = __fmul_rn(__fadd_rn(gy, 1.f), X.sfy);
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float w = __fsub_rn(ix, x0f), e = __fsub_rn(1.f, w);
+  const float n = __fsub_rn(iy, y0f), so = __fsub_rn(1.f, n);
+  const float nw = __fmul_rn(so, e), ne = __fmul_rn(so, w), sw = __fmul_rn(n, e), se = __fmul_rn(n, w);
+  const int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)(X.W + 1));
+  const int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)(X.H + 1));
+  const bool xa = (x0 >= 0) & (x0 < X.W), xb = (x0 + 1 >= 0) & (x0 + 1 < X.W);
+  const bool ya = (y0 >= 0) & (y0 < X.H), yb = (y0 + 1 >= 0) & (y0 + 1 < X.H);
+  const float* r0 = s + y0 * X.W + x0;
+  const float v_nw = (xa & ya) ? r0[0] : 0.f;
+  const float v_ne = (xb & ya) ? r0[1] : 0.f;
+  const float v_sw = (xa & yb) ? r0[X.W] : 0.f;
+  const float v_se = (xb & yb) ? r0[X.W + 1] : 0.f;
+  float acc = __fmul_rn(v_nw, nw);
+  acc = __fmaf_rn(v_ne, ne, acc);
+  acc = __fmaf_rn(v_sw, sw, acc);
+  acc = __fmaf_rn(v_se, se, acc);
+  return acc;
+}
+
+__device__ __forceinline__ void load_xform(Xform& X, const float* theta, const uint8_t* flip, long long vb, int H,
+                                           int W) {
+  const float* t = theta + vb * 6;
+  X.t00 = t[0]; X.t01 = t[1]; X.t02 = t[2]; X.t10 = t[3]; X.t11 = t[4]; X.t12 = t[5];
+  X.H = H; X.W = W;
+  X.stepx = (W > 1) ? __fdiv_rn(2.f, (float)(W - 1)) : 0.f;
+  X.stepy = (H > 1) ? __fdiv_rn(2.f, (float)(H - 1)) : 0.f;
+  X.sfx = (float)((double)(W - 1) / 2.0);
+  X.sfy = (float)((double)(H - 1) / 2.0);
+  X.flip = flip ? (flip[vb] != 0) : false;
+}
+
+// Exhaustive decode of the warped map in canonical (mirrored) pixel order.
+__device__ __forceinline__ void decode_exhaustive(const float* s, const Xform& X, int lane, float& bv, int& bi) {
+  const int HW = X.H * X.W;
+  bv = -INFINITY;
+  bi = 0x7fffffff;
+  for (int k = lane; k < HW; k += 32) {
+    const int i = k / X.W, jo = k - i * X.W;
+    const int jw = X.flip ? (X.W - 1 - jo) : jo;
+    const float v = eval_px(s, X, i, jw);
+    if (arg_better(v, k, bv, bi)) { bv = v; bi = k; }
+  }
+  warp_argmax(bv, bi);
+}
+
+// Arg-max of the raw staged map (no warp): torch.max semantics incl. NaN.
+__device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float& bv, int& bi, float& mn,
+                                         bool& nonfinite) {
+  bv = -INFINITY; bi = 0x7fffffff; mn = INFINITY; nonfinite = false;
+  const int nq = HW >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(s);
+#pragma unroll 4
+  for (int q = lane; q < nq; q += 32) {
+    const float4 x = s4[q];
+    const int k = q << 2;
+    if (x.x > bv) { bv = x.x; bi = k; }
+    if (x.y > bv) { bv = x.y; bi = k + 1; }
+    if (x.z > bv) { bv = x.z; bi = k + 2; }
+    if (x.w > bv) { bv = x.w; bi = k + 3; }
+    mn = fminf(fminf(mn, fminf(x.x, x.y)), fminf(x.z, x.w));
+    nonfinite |= !((fabsf(x.x) <= FLT_MAX) & (fabsf(x.y) <= FLT_MAX) & (fabsf(x.z) <= FLT_MAX) & (fabsf(x.w) <= FLT_MAX));
+  }
+  for (int k = (nq << 2) + lane; k < HW; k += 32) {
+    const float x = s[k];
+    if (x > bv) { bv = x; bi = k; }
+    mn = fminf(mn, x);
+    nonfinite |= !(fabsf(x) <= FLT_MAX);
+  }
+}
+
+__device__ __forceinline__ void issue_map(const WDParams& p, long long n, float* dst, uint64_t* bar, uint64_t pol,
+                                          uint32_t bytes) {
+  const int j = (int)(n % p.J);
+  const long long vb = n / p.J;
+  const int b = (int)(vb % p.B);
+  const long long v = vb / p.B;
+  const float* src = p.maps + v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
+  mbar_arrive_expect_tx(bar, bytes);
+  bulk_g2s(dst, src, bytes, bar, pol);
+}
+
+__global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = p.H, W = p.W, HW = H * W;
+  const uint32_t map_bytes = (uint32_t)HW * 4u;
+  const uint32_t buf_stride = (map_bytes + 127u) & ~127u;   // keep every buffer 128 B aligned
+  const int NB = p.nbuf;
+  float* buf0 = reinterpret_cast<float*>(smem_raw + (size_t)warp * NB * buf_stride);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warps * NB * buf_stride) + warp * NB;
+
+  const long long N = (long long)p.V * p.B * p.J;
+  const long long gw = (long long)blockIdx.x * warps + warp;
+  const long long TW = (long long)gridDim.x * warps;
+  uint64_t pol = 0;
+  if (p.use_bulk) {
+    if (lane == 0) {
+      for (int b = 0; b < NB; ++b) mbar_init(&bars[b], 1);
+      fence_mbar_init();
+      pol = l2_evict_first_policy();
+      for (int b = 0; b < NB; ++b) {
+        const long long n = gw + (long long)b * TW;
+        if (n < N) issue_map(p, n, buf0 + (size_t)b * (buf_stride >> 2), &bars[b], pol, map_bytes);
+      }
+    }
+    __syncwarp();
+  }
+
+  unsigned long long n_slow = 0, n_eval = 0, n_maps = 0;
+  long long it = 0;
+  for (long long n = gw; n < N; n += TW, ++it) {
+    const int bsel = (int)(it % NB);
+    float* s = buf0 + (size_t)bsel * (buf_stride >> 2);
+    const int j = (int)(n % p.J);
+    const long long vb = n / p.J;
+    const int b = (int)(vb % p.B);
+    if (p.use_bulk) {
+      mbar_wait(&bars[bsel], (uint32_t)((it / NB) & 1));
+    } else {
+      const long long v = vb / p.B;
+      const float* src = p.maps + v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
+      for (int k = lane; k < HW; k += 32) s[k] = __ldg(src + k);
+      __syncwarp();
+    }
+    ++n_maps;
+
+    // ---- pass A: raw max / arg-max / min -------------------------------------------------
+    float bv, mn; int bi; bool nonfinite;
+    scan_max(s, HW, lane, bv, bi, mn, nonfinite);
+    nonfinite = __any_sync(0xffffffffu, nonfinite);
+    float rv = bv; int ri = bi;           // result (value, canonical flat index)
+    Xform X;
+    if (!p.do_warp) {
+      if (nonfinite) {                    // torch.max: the first NaN wins
+        rv = -INFINITY; ri = 0x7fffffff;
+        for (int k = lane; k < HW; k += 32) { const float x = s[k]; if (arg_better(x, k, rv, ri)) { rv = x; ri = k; } }
+      }
+      warp_argmax(rv, ri);
+      X.H = H; X.W = W; X.flip = false;
+    } else {
+      load_xform(X, p.theta, p.flip, vb, H, W);
+      warp_argmax(bv, bi);                // warp-uniform source max / location
+      mn = -warp_max(-mn);
+      bool exhaustive = nonfinite;
+      // pixel-space affine  ix = a*jw + bb*i + c0 ; iy = d*jw + e*i + f0  (approximate, for boxes only)
+      const float a = X.t00 * X.stepx * X.sfx, bb = X.t01 * X.stepy * X.sfx;
+      const float d = X.t10 * X.stepx * X.sfy, e = X.t11 * X.stepy * X.sfy;
+      const float c0 = (X.t02 + 1.f - X.t00 - X.t01) * X.sfx, f0 = (X.t12 + 1.f - X.t10 - X.t11) * X.sfy;
+      const float det = a * e - bb * d;
+      const float nrm = fabsf(a) + fabsf(bb) + fabsf(d) + fabsf(e);
+      if (!(fabsf(det) > 1e-5f * nrm * nrm) || !(nrm < 1e4f) || W <= 1 || H <= 1) exhaustive = true;
+      float L = -INFINITY; int Li = 0x7fffffff;
+      const float idet = 1.f / det;
+      const float C00 = e * idet, C01 = -bb * idet, C10 = -d * idet, C11 = a * idet;
+      if (!exhaustive) {
+        // ---- phase L: lower bound from the pixels around the pre-image of the arg-max texel
+        const float sx = (float)(bi % W) - c0, sy = (float)(bi / W) - f0;
+        const float oj = C00 * sx + C01 * sy, oi = C10 * sx + C11 * sy;
+        if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 30) {
+          const int jw = (int)floorf(oj) - 2 + (lane % 6);
+          const int i = (int)floorf(oi) - 2 + (lane / 6);
+          if (jw >= 0 && jw < W && i >= 0 && i < H) {
+            L = eval_px(s, X, i, jw);
+            Li = i * W + (X.flip ? (W - 1 - jw) : jw);
+          }
+        }
+        n_eval += 30;
+        warp_argmax(L, Li);
+        const float amax = fmaxf(bv, -mn);
+        const float T = L - (L + amax) * 1.9073486328125e-06f;   // 2^-19
+        if (!(L > 0.f) || !(T > 0.f)) exhaustive = true;
+        if (!exhaustive) {
+          // ---- pass B: bounding box of the candidate texels (v >= T) -----------------------
+          int txmin = W, txmax = -1, tymin = H, tymax = -1;
+          const int nq = HW >> 2;
+          const float4* s4 = reinterpret_cast<const float4*>(s);
+#pragma unroll 4
+          for (int q = lane; q < nq; q += 32) {
+            const float4 x = s4[q];
+            if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= T) {
+              const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (xs[c] >= T) {
+                  const int k = (q << 2) + c, ty = k / W, tx = k - ty * W;
+                  txmin = min(txmin, tx); txmax = max(txmax, tx); tymin = min(tymin, ty); tymax = max(tymax, ty);
+                }
+            }
+          }
+          for (int k = (nq << 2) + lane; k < HW; k += 32)
+            if (s[k] >= T) {
+              const int ty = k / W, tx = k - ty * W;
+              txmin = min(txmin, tx); txmax = max(txmax, tx); tymin = min(tymin, ty); tymax = max(tymax, ty);
+            }
+          txmin = __reduce_min_sync(0xffffffffu, txmin); txmax = __reduce_max_sync(0xffffffffu, txmax);
+          tymin = __reduce_min_sync(0xffffffffu, tymin); tymax = __reduce_max_sync(0xffffffffu, tymax);
+          // pre-image of [txmin-1, txmax+1] x [tymin-1, tymax+1] -> bounding box in the warped frame
+          const float X0 = (float)(txmin - 1) - c0, X1 = (float)(txmax + 1) - c0;
+          const float Y0 = (float)(tymin - 1) - f0, Y1 = (float)(tymax + 1) - f0;
+          const float ja = C00 * X0, jb = C00 * X1, jc = C01 * Y0, jd = C01 * Y1;
+          const float ia = C10 * X0, ib = C10 * X1, ic = C11 * Y0, id = C11 * Y1;
+          const float jlo = fminf(ja, jb) + fminf(jc, jd), jhi = fmaxf(ja, jb) + fmaxf(jc, jd);
+          const float ilo = fminf(ia, ib) + fminf(ic, id), ihi = fmaxf(ia, ib) + fmaxf(ic, id);
+          const float m = 0.03f;
+          const int jmin = max(0, (int)ceilf(fmaxf(jlo - m, -1.f))), jmax = min(W - 1, (int)floorf(fminf(jhi + m, (float)W)));
+          const int imin = max(0, (int)ceilf(fmaxf(ilo - m, -1.f))), imax = min(H - 1, (int)floorf(fminf(ihi + m, (float)H)));
+          const int bw = jmax - jmin + 1, bh = imax - imin + 1;
+          const int area = (bw > 0 && bh > 0) ? bw * bh : 0;
+          if (area > 768 || area * 4 > HW) {
+            exhaustive = true;
+          } else {
+            // ---- phase C: exact evaluation of every pixel that can touch a candidate ---------
+            rv = L; ri = Li;
+            for (int t = lane; t < area; t += 32) {
+              const int i = imin + t / bw, jw = jmin + t % bw;
+              const float v = eval_px(s, X, i, jw);
+              const int k = i * W + (X.flip ? (W - 1 - jw) : jw);
+              if (arg_better(v, k, rv, ri)) { rv = v; ri = k; }
+            }
+            n_eval += area;
+            warp_argmax(rv, ri);
+          }
+        }
+      }
+      if (exhaustive) {
+        decode_exhaustive(s, X, lane, rv, ri);
+        ++n_slow;
+        n_eval += HW;
+      }
+    }
+
+    // ---- epilogue: coordinates -------------------------------------------------------------
+    const int ax = ri % W, ay = ri / W;                 // 0-based arg-max, canonical frame
+    float hx = 0.f, hy = 0.f;
+    const bool keep = rv > 0.f;                          // maxval.gt(0): NaN -> masked
+    if (keep) { hx = (float)(ax + 1); hy = (float)(ay + 1); }
+    const bool do_ref = (p.refine == 2) || (p.refine == 1 && j < 2);
+    if (do_ref) {
+      // process.py:366-371: 1 < px < res[0] and 1 < py < res[1] on the 1-based coordinates
+      if (keep && ax >= 1 && ax <= W - 2 && ay >= 1 && ay <= H - 2) {
+        float nb = 0.f;
+        if (lane < 4) {
+          const int di = (lane == 2) ? 1 : (lane == 3 ? -1 : 0);
+          const int dj = (lane == 0) ? 1 : (lane == 1 ? -1 : 0);
+          const int i = ay + di, jo = ax + dj;
+          nb = p.do_warp ? eval_px(s, X, i, X.flip ? (W - 1 - jo) : jo) : s[i * W + jo];
+        }
+        const float xp = __shfl_sync(0xffffffffu, nb, 0), xm = __shfl_sync(0xffffffffu, nb, 1);
+        const float yp = __shfl_sync(0xffffffffu, nb, 2), ym = __shfl_sync(0xffffffffu, nb, 3);
+        const float dx = xp - xm, dy = yp - ym;
+        hx += (dx > 0.f) ? 0.25f : ((dx < 0.f) ? -0.25f : 0.f);
+        hy += (dy > 0.f) ? 0.25f : ((dy < 0.f) ? -0.25f : 0.f);
+      }
+    }
+    if (p.refine != 0) { hx += 0.5f; hy += 0.5f; }      // process.py:372 (+0.5 for every joint)
+    if (lane == 0) {
+      if (p.out_idx) p.out_idx[n] = ri;
+      if (p.out_max) p.out_max[n] = rv;
+      if (p.out_hm_xy) { p.out_hm_xy[2 * n] = hx; p.out_hm_xy[2 * n + 1] = hy; }
+      if (p.out_xy) {
+        float ox = hx, oy = hy;
+        if (p.dec) {
+          const double* c = p.dec + (size_t)b * 4;
+          // np.dot row: (a00*(x-1) + 0*(y-1)) + a02, astype(int) truncation, +1
+          const double tx = __dadd_rn(__dmul_rn(c[0], (double)hx - 1.0), c[1]);
+          const double ty = __dadd_rn(__dmul_rn(c[2], (double)hy - 1.0), c[3]);
+          ox = (float)(trunc(tx) + 1.0);
+          oy = (float)(trunc(ty) + 1.0);
+        }
+        p.out_xy[2 * n] = ox; p.out_xy[2 * n + 1] = oy;
+      }
+    }
+    __syncwarp();
+    if (p.use_bulk && lane == 0) {
+      const long long nn = n + (long long)NB * TW;
+      if (nn < N) issue_map(p, nn, s, &bars[bsel], pol, map_bytes);
+    }
+  }
+  if (p.stats && lane == 0 && n_maps) {
+    atomicAdd(p.stats + 0, n_slow);
+    atomicAdd(p.stats + 1, n_eval);
+    atomicAdd(p.stats + 2, n_maps);
+  }
+}
+
+// -----------------------------------------------------------------------------------------------
+// affine_back2 materialised: one CTA per map, source staged in shared memory, coalesced stores.
+// -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) warp_materialize_kernel(const float* __restrict__ in, long long sN, long long sC,
+                                                               float* __restrict__ out, long long oN, long long oC,
+                                                               int N, int C, int H, int W,
+                                                               const float* __restrict__ theta,
+                                                               const uint8_t* __restrict__ flip) {
+  extern __shared__ __align__(16) float sm[];
+  const int HW = H * W;
+  for (long long m = blockIdx.x; m < (long long)N * C; m += gridDim.x) {
+    const long long n = m / C;
+    const int c = (int)(m % C);
+    const float* src = in + n * sN + (long long)c * sC;
+    float* dst = out + n * oN + (long long)c * oC;
+    __syncthreads();
+    for (int k = threadIdx.x; k < HW; k += blockDim.x) sm[k] = __ldg(src + k);
+    __syncthreads();
+    Xform X;
+    load_xform(X, theta, flip, n, H, W);
+    for (int k = threadIdx.x; k < HW; k += blockDim.x) {
+      const int i = k / W, jo = k - i * W;
+      dst[k] = eval_px(sm, X, i, X.flip ? (W - 1 - jo) : jo);
+    }
+  }
+}
+
+}  // namespace ubpl
+
+using namespace ubpl;
+
+extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64_t sJ, int V, int B, int J, int H,
+                                int W, const float* theta, const uint8_t* flip, const double* dec, int do_warp,
+                                int refine, int32_t* out_idx, float* out_max, float* out_xy, float* out_hm_xy,
+                                int64_t* stats, void* stream) {
+  UBPL_REQUIRE(maps != nullptr, "ubpl_warp_decode: maps is NULL");
+  UBPL_REQUIRE(V >= 0 && B >= 0 && J >= 0 && H > 0 && W > 0, "ubpl_warp_decode: bad dims V=%d B=%d J=%d H=%d W=%d", V, B, J, H, W);
+  UBPL_REQUIRE(!do_warp || theta != nullptr, "ubpl_warp_decode: theta is NULL with do_warp=1");
+  UBPL_REQUIRE(refine >= 0 && refine <= 2, "ubpl_warp_decode: refine must be 0, 1 or 2");
+  const long long N = (long long)V * B * J;
+  if (N == 0) return UBPL_OK;
+  const long long HW = (long long)H * W;
+  UBPL_REQUIRE(HW <= (1 << 24), "ubpl_warp_decode: heat-map too large (%lld texels)", HW);
+  const size_t map_bytes = (size_t)HW * 4;
+  const size_t buf_stride = (map_bytes + 127) & ~(size_t)127;
+  const int smem_cap = smem_optin() - 2048;
+  UBPL_REQUIRE((long long)buf_stride + 64 <= smem_cap, "ubpl_warp_decode: a %dx%d map does not fit in shared memory", H, W);
+  WDParams p;
+  p.maps = maps; p.sV = sV; p.sB = sB; p.sJ = sJ; p.V = V; p.B = B; p.J = J; p.H = H; p.W = W;
+  p.theta = theta; p.flip = flip; p.dec = dec; p.do_warp = do_warp; p.refine = refine;
+  p.out_idx = out_idx; p.out_max = out_max; p.out_xy = out_xy; p.out_hm_xy = out_hm_xy;
+  p.stats = reinterpret_cast<unsigned long long*>(stats);
+  // bulk async copy needs 16-byte aligned sources and sizes; otherwise the warp copies the map itself
+  p.use_bulk = ((reinterpret_cast<uintptr_t>(maps) & 15) == 0) && (map_bytes % 16 == 0) && (sV % 4 == 0) &&
+               (sB % 4 == 0) && (sJ % 4 == 0);
+  int total_bufs = (int)((size_t)smem_cap / (buf_stride + 8));
+  int warps, nbuf;
+  if (total_bufs >= 8) { nbuf = 2; warps = total_bufs / 2; } else { nbuf = 1; warps = total_bufs; }
+  if (warps > 16) warps = 16;
+  if (warps < 1) warps = 1;
+  p.nbuf = nbuf;
+  const size_t smem = (size_t)warps * nbuf * buf_stride + (size_t)warps * nbuf * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(warp_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+    if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+    attr_set = true;
+  }
+  long long need = (N + warps - 1) / warps;
+  int grid = (int)(need < sm_count() ? need : sm_count());
+  warp_decode_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(p);
+  return check_launch("ubpl_warp_decode");
+}
+
+extern "C" int ubpl_warp_materialize(const float* in, int64_t sN, int64_t sC, float* out, int64_t oN, int64_t oC,
+                                     int N, int C, int H, int W, const float* theta, const uint8_t* flip,
+                                     void* stream) {
+  UBPL_REQUIRE(in && out && theta, "ubpl_warp_materialize: NULL pointer");
+  UBPL_REQUIRE(N >= 0 && C >= 0 && H > 0 && W > 0, "ubpl_warp_materialize: bad dims");
+  if ((long long)N * C == 0) return UBPL_OK;
+  const size_t smem = (size_t)H * W * 4;
+  UBPL_REQUIRE((int)smem <= smem_optin(), "ubpl_warp_materialize: map does not fit in shared memory");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(warp_materialize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+    if (e != cudaSuccess) { set_error("ubpl_warp_materialize: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+    attr_set = true;
+  }
+  long long maps = (long long)N * C;
+  int grid = (int)(maps < (long long)sm_count() * 8 ? maps : (long long)sm_count() * 8);
+  warp_materialize_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, sN, sC, out, oN, oC, N, C, H, W, theta, flip);
+  return check_launch("ubpl_warp_materialize");
+}

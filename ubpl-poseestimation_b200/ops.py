@@ -1,0 +1,380 @@
+"""Tensor-level wrappers over the C ABI (include/ubpl_b200.h).  torch is used for device memory,
+streams and (in dist.py) the NCCL plumbing only; every computation is a kernel of libubpl_b200.so.
+All inputs must be CUDA tensors: there is no CPU path."""
+import torch
+
+from . import _lib
+
+_f32, _f64 = torch.float32, torch.float64
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.UbplError("ubpl_b200 ops run on CUDA tensors only (got a %s tensor); there is no CPU fallback"
+                                 % t.device.type)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _inner_contig(t):
+    """Heat-map planes must be contiguous in (H, W); outer dims may have any stride."""
+    W = t.shape[-1]
+    if t.stride(-1) == 1 and t.stride(-2) == W:
+        return t
+    return t.contiguous()
+
+
+# -------------------------------------------------------------------------------------------------
+# K1
+# -------------------------------------------------------------------------------------------------
+def decode_coeffs(center, scale, res):
+    """[B,4] float64 (a00, a02, a11, a12): the inverse of utils/udaap/transforms.py:119-130
+    `get_transform(center, scale, res)` exactly as `transform(..., invert=1)` (:151-158) obtains
+    it -- the arithmetic dtype follows the dtype of the `scale` tensor (float64 tensor -> float64,
+    anything else -> float32), then a00 = 1/t00, a02 = -(t02 * a00) in float64 (np.linalg.inv)."""
+    scale = torch.as_tensor(scale)
+    center = torch.as_tensor(center)
+    ft = _f64 if scale.dtype == _f64 else _f32
+    sc = scale.reshape(-1).to(ft)
+    c = center.reshape(-1, 2).to(_f64).to(ft)
+    h = sc * 200
+    t00 = float(res[1]) / h
+    t11 = float(res[0]) / h
+    t02 = res[1] * ((-c[:, 0]) / h + 0.5)
+    t12 = res[0] * ((-c[:, 1]) / h + 0.5)
+    t00, t11, t02, t12 = t00.to(_f64), t11.to(_f64), t02.to(_f64), t12.to(_f64)
+    a00 = 1.0 / t00
+    a11 = 1.0 / t11
+    return torch.stack([a00, -(t02 * a00), a11, -(t12 * a11)], -1).contiguous()
+
+
+def warp_decode(maps, theta=None, flip=None, dec=None, refine=0, stats=None, want_idx=True, want_hm=False):
+    """Fused back-warp + flip + arg-max decode (K1).  maps [V,B,J,H,W] or [B,J,H,W] (V=1);
+    theta [V,B,2,3] (None = plain decode of the raw maps), flip [V,B] bool/uint8, dec [B,4] float64
+    from decode_coeffs (None = heat-map coordinates).  Returns dict(idx, max, xy[, hm_xy]) shaped
+    like the leading dims of `maps`."""
+    _need_cuda(maps, theta, flip, dec, stats)
+    if maps.dtype != _f32:
+        raise _lib.UbplError("heat-maps must be float32")
+    squeeze = maps.dim() == 4
+    if squeeze:
+        maps = maps.unsqueeze(0)
+    maps = _inner_contig(maps)
+    V, B, J, H, W = maps.shape
+    dev = maps.device
+    if theta is not None:
+        theta = theta.reshape(V, B, 2, 3).to(_f32).contiguous()
+    if flip is not None:
+        flip = flip.reshape(V, B).to(torch.uint8).contiguous()
+    if dec is not None:
+        dec = dec.reshape(B, 4).to(_f64).contiguous()
+    out_idx = torch.empty(V, B, J, dtype=torch.int32, device=dev) if want_idx else None
+    out_max = torch.empty(V, B, J, dtype=_f32, device=dev)
+    out_xy = torch.empty(V, B, J, 2, dtype=_f32, device=dev)
+    out_hm = torch.empty(V, B, J, 2, dtype=_f32, device=dev) if want_hm else None
+    _lib.call("ubpl_warp_decode", maps.data_ptr(), maps.stride(0), maps.stride(1), maps.stride(2), V, B, J, H, W,
+              _p(theta), _p(flip), _p(dec), 1 if theta is not None else 0, int(refine),
+              _p(out_idx), _p(out_max), _p(out_xy), _p(out_hm), _p(stats), _stream())
+    res = dict(idx=out_idx, max=out_max, xy=out_xy, hm_xy=out_hm)
+    if squeeze:
+        res = {k: (v[0] if v is not None else None) for k, v in res.items()}
+    return res
+
+
+def warp_materialize(heatmap, warpmat, isflip):
+    """AugmentUtils.affine_back2 (utils/augment.py:37-47) as one kernel; returns a new tensor."""
+    _need_cuda(heatmap, warpmat, isflip)
+    x = _inner_contig(heatmap.to(_f32))
+    N, C, H, W = x.shape
+    out = torch.empty(N, C, H, W, dtype=_f32, device=x.device)
+    theta = warpmat.reshape(N, 2, 3).to(_f32).contiguous()
+    flip = None if isflip is None else torch.as_tensor(isflip, device=x.device).reshape(N).to(torch.uint8).contiguous()
+    _lib.call("ubpl_warp_materialize", x.data_ptr(), x.stride(0), x.stride(1), out.data_ptr(), out.stride(0),
+              out.stride(1), N, C, H, W, theta.data_ptr(), _p(flip), _stream())
+    return out
+
+
+# -------------------------------------------------------------------------------------------------
+# K2
+# -------------------------------------------------------------------------------------------------
+def view_dispersion(preds, sentinel_illegal=False):
+    """preds [K,B,J,2] float32 -> dict(mean [B,J,2] f32, dist [B,J] f64, unc32 [B,J] f32,
+    legal [B,J] uint8, max_bits uint32 scalar)   (utils/evaluation.py:40-55)."""
+    _need_cuda(preds)
+    preds = preds.to(_f32).contiguous()
+    K, B, J, _ = preds.shape
+    dev = preds.device
+    mean = torch.empty(B, J, 2, dtype=_f32, device=dev)
+    dist = torch.empty(B, J, dtype=_f64, device=dev)
+    unc32 = torch.empty(B, J, dtype=_f32, device=dev)
+    legal = torch.empty(B, J, dtype=torch.uint8, device=dev)
+    max_bits = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.call("ubpl_view_dispersion", preds.data_ptr(), K, B, J, mean.data_ptr(), dist.data_ptr(), unc32.data_ptr(),
+              legal.data_ptr(), max_bits.data_ptr(), 1 if sentinel_illegal else 0, _stream())
+    return dict(mean=mean, dist=dist, unc32=unc32, legal=legal, max_bits=max_bits)
+
+
+def unc_normalize(unc32, max_bits):
+    """unc/unc.max() and exp(-unc)  (utils/evaluation.py:56-57)."""
+    _need_cuda(unc32, max_bits)
+    unc = torch.empty_like(unc32)
+    uncW = torch.empty_like(unc32)
+    _lib.call("ubpl_unc_normalize", unc32.data_ptr(), max_bits.data_ptr(), unc32.numel(), unc.data_ptr(),
+              uncW.data_ptr(), _stream())
+    return unc, uncW
+
+
+def assess_dual(p1, p2, pmean, aug1, aug2):  # pmean None = bus.preds_mean(p1, p2)
+    """utils/business.py:109-161 in array form; all outputs float64 [B,J] (coord [B,J,2])."""
+    _need_cuda(p1, p2, pmean, aug1, aug2)
+    aug1 = aug1.to(_f32).contiguous()
+    aug2 = aug2.to(_f32).contiguous()
+    K, B, J, _ = aug1.shape
+    dev = aug1.device
+    p1, p2 = (t.to(_f32).contiguous() for t in (p1, p2))
+    pmean = None if pmean is None else pmean.to(_f32).contiguous()
+    o = {k: torch.empty(B, J, dtype=_f64, device=dev) for k in ("legal", "intDist1", "intDist2", "extDist", "w1", "w2")}
+    o["coord"] = torch.empty(B, J, 2, dtype=_f64, device=dev)
+    o["coord32"] = torch.empty(B, J, 2, dtype=_f32, device=dev)
+    o["zero_div"] = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.call("ubpl_assess_dual", p1.data_ptr(), p2.data_ptr(), _p(pmean), aug1.data_ptr(), aug2.data_ptr(),
+              K, B, J, o["legal"].data_ptr(), o["intDist1"].data_ptr(), o["intDist2"].data_ptr(),
+              o["extDist"].data_ptr(), o["w1"].data_ptr(), o["w2"].data_ptr(), o["coord"].data_ptr(),
+              o["coord32"].data_ptr(), o["zero_div"].data_ptr(), _stream())
+    return o
+
+
+def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, group=None, n_total=None):
+    """BusinessUtils.filter_pseudo2 (utils/business.py:173-217) on device: min/max normalise,
+    reliability = 1 - unc, exact k-th order statistic (k = int((n-1)*pct) from the top) by a
+    4-pass 16-bit radix select, enable = reliability > max(reliableThr, kth).
+
+    With a torch.distributed `group` the extrema and the four histograms are all-reduced (NCCL),
+    so every rank derives the same global threshold; each rank passes its own shard of items and
+    all shards are assumed equal in size unless n_total is given."""
+    _need_cuda(dist, legal)
+    dist = dist.reshape(-1).to(_f64).contiguous()
+    legal = legal.reshape(-1).to(_f64).contiguous()
+    n = dist.numel()
+    dev = dist.device
+    st = _stream()
+    world = 1
+    if group is not None:
+        import torch.distributed as td
+        world = td.get_world_size(group)
+    if n_total is None:
+        n_total = n * world
+    ext = torch.empty(2, dtype=_f64, device=dev)
+    _lib.call("ubpl_dist_extrema", dist.data_ptr(), n, ext.data_ptr(), st)
+    if world > 1:
+        td.all_reduce(ext[0:1], op=td.ReduceOp.MAX, group=group)
+        td.all_reduce(ext[1:2], op=td.ReduceOp.MIN, group=group)
+    rel = torch.empty(n, dtype=_f64, device=dev)
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    _lib.call("ubpl_reliability", dist.data_ptr(), legal.data_ptr(), n, ext.data_ptr(), float(reliableDistMin),
+              rel.data_ptr(), keys.data_ptr(), st)
+    if n_total < 1:
+        raise IndexError("list index out of range")          # scores[int(-1*pct)] on an empty list
+    k = int((n_total - 1) * reliablePCT)                     # utils/business.py:45
+    prefix = torch.zeros(1, dtype=torch.int64, device=dev)
+    k_rem = torch.full((1,), k, dtype=torch.int64, device=dev)
+    hist = torch.empty(65536, dtype=torch.int32, device=dev)
+    for shift in (48, 32, 16, 0):
+        _lib.call("ubpl_key_histogram", keys.data_ptr(), n, prefix.data_ptr(), shift, hist.data_ptr(), st)
+        if world > 1:
+            td.all_reduce(hist, op=td.ReduceOp.SUM, group=group)
+        _lib.call("ubpl_select_descend", hist.data_ptr(), shift, prefix.data_ptr(), k_rem.data_ptr(), st)
+    enable = torch.empty(n, dtype=torch.uint8, device=dev)
+    gate = torch.empty(n, dtype=_f32, device=dev)
+    counts = torch.empty(J + 1, dtype=torch.int32, device=dev)
+    thr = torch.empty(1, dtype=_f64, device=dev)
+    _lib.call("ubpl_select_apply", rel.data_ptr(), n, J, prefix.data_ptr(), float(reliableThr), enable.data_ptr(),
+              gate.data_ptr(), counts.data_ptr(), thr.data_ptr(), st)
+    return dict(reliability=rel, enable=enable, gate=gate, counts=counts, thr=thr, ext=ext)
+
+
+def select_fixed(dist, legal, J, distThrMax):
+    """enable = legal and 1-exp(-dist/5) <= 1-exp(-3*distThrMax/5)  (utils/business.py:237-261)."""
+    _need_cuda(dist, legal)
+    dist = dist.reshape(-1).to(_f64).contiguous()
+    legal = None if legal is None else legal.reshape(-1).to(_f64).contiguous()
+    n = dist.numel()
+    dev = dist.device
+    enable = torch.empty(n, dtype=torch.uint8, device=dev)
+    gate = torch.empty(n, dtype=_f32, device=dev)
+    counts = torch.empty(J + 1, dtype=torch.int32, device=dev)
+    unc = torch.empty(n, dtype=_f64, device=dev)
+    _lib.call("ubpl_select_fixed", dist.data_ptr(), _p(legal), n, J, float(distThrMax), enable.data_ptr(),
+              gate.data_ptr(), counts.data_ptr(), unc.data_ptr(), _stream())
+    return dict(enable=enable, gate=gate, counts=counts, unc=unc)
+
+
+# -------------------------------------------------------------------------------------------------
+# K3
+# -------------------------------------------------------------------------------------------------
+def render_targets(kps, H, W, img_h, img_w, stride=None, sigma=3.0):
+    """ProcessUtils.kps_heatmap (utils/process.py:253-278) for N key points: kps [N,3] ->
+    (heatmap [N,H,W], kps_out [N,3] with weight *= visibility)."""
+    _need_cuda(kps)
+    kps = kps.to(_f32).contiguous()
+    N = kps.shape[0]
+    if stride is None:
+        stride = img_w / W
+    hm = torch.empty(N, H, W, dtype=_f32, device=kps.device)
+    kout = torch.empty(N, 3, dtype=_f32, device=kps.device)
+    _lib.call("ubpl_render_targets", kps.data_ptr(), N, H, W, int(img_h), int(img_w), float(stride), float(sigma),
+              hm.data_ptr(), kout.data_ptr(), _stream())
+    return hm, kout
+
+
+def render_mse(kps, gate, sample_w, pred, img_h, img_w, stride=None, sigma=3.0, grad_scale=None,
+               want_grad=True, want_target=True):
+    """Fused Gaussian render + JointMSELoss forward + gradient (K3b).  kps [B,J,2] image space,
+    gate [B,J] or None, sample_w [B] / [B,1] or None, pred [B,S,J,H,W].  Returns dict(per_loss
+    [B,S,J], gate_out [B,J], grad, target)."""
+    _need_cuda(kps, gate, sample_w, pred, grad_scale)
+    pred = _inner_contig(pred)
+    B, S, J, H, W = pred.shape
+    dev = pred.device
+    kps = kps.reshape(B, J, 2).to(_f32).contiguous()
+    gate = None if gate is None else gate.reshape(B, J).to(_f32).contiguous()
+    sample_w = None if sample_w is None else sample_w.reshape(B).to(_f32).contiguous()
+    if stride is None:
+        stride = img_w / W
+    grad = torch.empty(B, S, J, H, W, dtype=_f32, device=dev) if want_grad else None
+    target = torch.empty(B, J, H, W, dtype=_f32, device=dev) if want_target else None
+    gate_out = torch.empty(B, J, dtype=_f32, device=dev)
+    per_loss = torch.empty(B, S, J, dtype=_f32, device=dev)
+    gs = (0, 0, 0) if grad is None else (grad.stride(0), grad.stride(1), grad.stride(2))
+    _lib.call("ubpl_render_mse", kps.data_ptr(), _p(gate), _p(sample_w), pred.data_ptr(), pred.stride(0),
+              pred.stride(1), pred.stride(2), _p(grad), gs[0], gs[1], gs[2], _p(target), B, S, J, H, W, int(img_h),
+              int(img_w), float(stride), float(sigma), _p(grad_scale), gate_out.data_ptr(), per_loss.data_ptr(),
+              _stream())
+    return dict(per_loss=per_loss, gate_out=gate_out, grad=grad, target=target)
+
+
+def dense_mse(pred, tgt, coef=None, mask_mode=0, thr=0.0, grad_scale=None, want_grad=True, want_scores=False):
+    """Dense-target masked joint-MSE forward + gradient (K3a/K3c).  pred [B,S,J,H,W];
+    tgt [M,B,S,J,H,W] (per-stack targets) or [M,B,J,H,W] (shared by the stacks); coef [B,J]."""
+    _need_cuda(pred, tgt, coef, grad_scale)
+    pred = _inner_contig(pred)
+    tgt = _inner_contig(tgt)
+    B, S, J, H, W = pred.shape
+    dev = pred.device
+    M = tgt.shape[0]
+    if tgt.dim() == 6:
+        tM, tB, tS, tJ = tgt.stride(0), tgt.stride(1), tgt.stride(2), tgt.stride(3)
+    else:
+        tM, tB, tS, tJ = tgt.stride(0), tgt.stride(1), 0, tgt.stride(2)
+    coef = None if coef is None else coef.reshape(B, J).to(_f32).contiguous()
+    grad = torch.empty(B, S, J, H, W, dtype=_f32, device=dev) if want_grad else None
+    per_loss = torch.empty(B, S, J, dtype=_f32, device=dev)
+    mask = torch.empty(B, S, J, dtype=_f32, device=dev)
+    vp = torch.empty(B, S, J, dtype=_f32, device=dev) if (want_scores or mask_mode == 1) else None
+    vt = torch.empty(B, S, J, dtype=_f32, device=dev) if (want_scores or mask_mode != 0) else None
+    gs = (0, 0, 0) if grad is None else (grad.stride(0), grad.stride(1), grad.stride(2))
+    _lib.call("ubpl_dense_mse", pred.data_ptr(), pred.stride(0), pred.stride(1), pred.stride(2), tgt.data_ptr(), M,
+              tM, tB, tS, tJ, _p(coef), int(mask_mode), float(thr), _p(grad), gs[0], gs[1], gs[2], B, S, J, H, W,
+              _p(grad_scale), per_loss.data_ptr(), mask.data_ptr(), _p(vp), _p(vt), _stream())
+    return dict(per_loss=per_loss, mask=mask, vmax_p=vp, vmax_t=vt, grad=grad)
+
+
+def loss_finalize(per_loss, mask=None, gate=None):
+    """float64[4] on device: sum(per_loss*mask), #(per_loss>0), #(mask>0), #(gate>0) (B*J if None)."""
+    _need_cuda(per_loss, mask, gate)
+    B, S, J = per_loss.shape
+    out = torch.empty(4, dtype=_f64, device=per_loss.device)
+    _lib.call("ubpl_loss_finalize", per_loss.data_ptr(), _p(mask), _p(gate), B, S, J, out.data_ptr(), _stream())
+    return out
+
+
+def gate_prepare(kps, gate_in, S, img_h, img_w, stride, sigma=3.0, loss_weight=1.0):
+    """gate_out = gate_in*visibility, count = S*#(gate_out>0), grad_scale = loss_weight/count, all on
+    device (utils/process.py:262-268, utils/losses.py:29, projects/MT_UBPL.py:266)."""
+    _need_cuda(kps, gate_in)
+    kps = kps.reshape(-1, 2).to(_f32).contiguous()
+    n = kps.shape[0]
+    gate_in = None if gate_in is None else gate_in.reshape(-1).to(_f32).contiguous()
+    dev = kps.device
+    gate_out = torch.empty(n, dtype=_f32, device=dev)
+    grad_scale = torch.empty(1, dtype=_f32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.call("ubpl_gate_prepare", kps.data_ptr(), _p(gate_in), n, int(img_h), int(img_w), float(stride), float(sigma),
+              int(S), float(loss_weight), gate_out.data_ptr(), grad_scale.data_ptr(), count.data_ptr(), _stream())
+    return gate_out, grad_scale, count
+
+
+def scale_inplace(x, scale):
+    """x *= scale, scale a float32 device scalar (no host sync)."""
+    _need_cuda(x, scale)
+    assert x.is_contiguous() and x.dtype == _f32
+    _lib.call("ubpl_scale_inplace", x.data_ptr(), x.numel(), scale.data_ptr(), _stream())
+    return x
+
+
+# -------------------------------------------------------------------------------------------------
+# K4
+# -------------------------------------------------------------------------------------------------
+class EmaPlan:
+    """Device-side pointer/chunk tables for the one-launch EMA of a (student, teacher) model pair
+    (utils/parameters.py:4-8).  Rebuilt automatically if any parameter storage moved."""
+    CHUNK = 8192
+
+    def __init__(self, params, ema_params):
+        self.params = list(params)
+        self.ema_params = list(ema_params)
+        if len(self.params) != len(self.ema_params):
+            raise ValueError("student and teacher have different parameter counts")
+        self._key = None
+        self._build()
+
+    def _ptr_key(self):
+        return tuple(p.data_ptr() for p in self.params) + tuple(e.data_ptr() for e in self.ema_params)
+
+    def _build(self):
+        dev = self.ema_params[0].device
+        _need_cuda(*self.params, *self.ema_params)
+        for p, e in zip(self.params, self.ema_params):
+            if p.dtype != _f32 or e.dtype != _f32 or not p.is_contiguous() or not e.is_contiguous():
+                raise _lib.UbplError("EMA expects contiguous float32 parameters")
+            if p.numel() != e.numel():
+                raise ValueError("parameter shape mismatch between student and teacher")
+        numels = [p.numel() for p in self.params]
+        ct, cs = [], []
+        for t, n in enumerate(numels):
+            for s in range(0, n, self.CHUNK):
+                ct.append(t)
+                cs.append(s)
+        self.n_chunks = len(ct)
+        self.n_elems = sum(numels)
+        self.ema_ptrs = torch.tensor([e.data_ptr() for e in self.ema_params], dtype=torch.int64, device=dev)
+        self.param_ptrs = torch.tensor([p.data_ptr() for p in self.params], dtype=torch.int64, device=dev)
+        self.numels = torch.tensor(numels, dtype=torch.int64, device=dev)
+        self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=dev)
+        self.chunk_start = torch.tensor(cs, dtype=torch.int64, device=dev)
+        self._key = self._ptr_key()
+
+    def step(self, alpha):
+        if self._ptr_key() != self._key:
+            self._build()
+        import numpy as np
+        a = float(np.float32(alpha))
+        oma = float(np.float32(1 - alpha))
+        _lib.call("ubpl_ema_multi_tensor", self.ema_ptrs.data_ptr(), self.param_ptrs.data_ptr(), self.numels.data_ptr(),
+                  self.chunk_tensor.data_ptr(), self.chunk_start.data_ptr(), self.n_chunks, self.CHUNK, a, oma, _stream())
+
+
+def ema_flat(ema, param, alpha):
+    _need_cuda(ema, param)
+    assert ema.is_contiguous() and param.is_contiguous() and ema.dtype == _f32 and param.dtype == _f32
+    import numpy as np
+    _lib.call("ubpl_ema_flat", ema.data_ptr(), param.data_ptr(), ema.numel(), float(np.float32(alpha)),
+              float(np.float32(1 - alpha)), _stream())
+    return ema
