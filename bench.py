@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -73,9 +73,14 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while not self.lines and time.time() - t0 < timeout and self.proc is not None:
+            time.sleep(0.02)
+
+    def stop(self, t_from=0.0, t_to=float("inf")):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -85,7 +90,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < t_from or ts > t_to:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -252,10 +259,12 @@ def run_ours(args):
     # ---- device-resident timing ---------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.wait_first()
     stats.zero_()
     _lib.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_load0 = time.time()
     e0.record()
     for _ in range(args.steps):
         r = step(timed=True)
@@ -263,7 +272,13 @@ def run_ours(args):
     barrier()
     launches = _lib.launch_count()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    # post-roll: keep the same load running (untimed) until nvidia-smi has had >= 0.6 s of it to sample
+    while time.time() - t_load0 < 0.6:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+    t_load1 = time.time()
+    clocks = sampler.stop(t_load0 + 0.05, t_load1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
@@ -349,8 +364,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")

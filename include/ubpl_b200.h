@@ -125,6 +125,15 @@ int ubpl_select_apply(const double* reliability, int64_t n, int J, const uint64_
 int ubpl_select_fixed(const double* dist, const double* legal, int64_t n, int J, double distThrMax,
                       uint8_t* enable, float* gate32, int32_t* counts, double* unc_out, void* stream);
 
+/* Fused K2 of the mean-teacher fixed-threshold path, one launch: ubpl_view_dispersion (with the 999
+ * sentinel) + ubpl_select_fixed + ubpl_gate_prepare.  preds [K,B,J,2]; outputs as in those three
+ * (out_mean is the pseudo key point the targets are rendered at); any of out_mean, out_dist,
+ * out_legal, enable, grad_scale, count_out may be NULL. */
+int ubpl_k2_view_fixed(const float* preds, int K, int B, int J, double distThrMax, int img_h, int img_w,
+                       float stride, float sigma, int S, float loss_weight, float* out_mean,
+                       double* out_dist, uint8_t* out_legal, uint8_t* enable, float* gate_out,
+                       float* grad_scale, int32_t* count_out, int32_t* counts, void* stream);
+
 /* ---- K3: Gaussian target render + masked joint-MSE, forward and gradient in one pass ----------
  * ProcessUtils.kps_heatmap (utils/process.py:253-278,394-397) fused into JointMSELoss
  * (utils/losses.py:8-29).  kps [B,J,2] float32 image-space coordinates; gate_in [B,J] float32

@@ -321,14 +321,15 @@ def test_ema_golden_bit_exact(ops):
 # ------------------------------------------------------------------------------------------------
 # the fused chain
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("M,select", [(1, "fixed"), (1, "quantile"), (2, "quantile"), (2, "fixed")])
-def test_pipeline_vs_oracle(ops, M, select):
+@pytest.mark.parametrize("M,select,fuse", [(1, "fixed", True), (1, "fixed", False), (1, "quantile", True),
+                                           (2, "quantile", True), (2, "fixed", True)])
+def test_pipeline_vs_oracle(ops, M, select, fuse):
     from ubpl_b200 import synth, pipeline
     d = synth.make_batch(B=8, K=4, J=6, M=M, S=2, seed=99 + M, jitter=0.5)
     n = {k: v.numpy() for k, v in d.items()}
     o = O.pseudo_label_chain(n["teacher"], n["student"], n["theta"], n["flip"], n["center"], n["scale"], n["islabeled"],
                              select=select, distThrMax=2.0, lossWeight=0.7)
-    cfg = pipeline.StepConfig(select=select, distThrMax=2.0, lossWeight=0.7)
+    cfg = pipeline.StepConfig(select=select, distThrMax=2.0, lossWeight=0.7, fuse_k2=fuse)
     dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64]).cuda()
     w = pipeline.nega_weights(d["islabeled"].cuda(), 1.0)
     r = pipeline.pseudo_label_step(d["teacher"].cuda(), d["student"].cuda(), d["theta"].cuda(), d["flip"].cuda(), dec, w, cfg)

@@ -31,6 +31,8 @@ SIGNATURES = {
     "ubpl_select_descend": [c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "ubpl_select_apply": [c_void_p, c_i64, c_int, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_select_fixed": [c_void_p, c_void_p, c_i64, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ubpl_k2_view_fixed": [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_float, c_float, c_int, c_float,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_render_mse": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_i64, c_i64, c_i64,
                         c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                         c_void_p, c_void_p, c_void_p, c_void_p],

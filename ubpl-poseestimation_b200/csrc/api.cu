@@ -100,6 +100,33 @@ int pow_table(const int32_t** keys, const double** vals, int* n, int* rmax) {
   return UBPL_OK;
 }
 
+// A ring of device counters for kernels that distribute work dynamically; each launch takes the
+// next slot and zeroes it on its stream (so concurrent launches on different streams, and CUDA
+// graph replays of one captured launch, never share a live counter).
+static unsigned long long* d_counters = nullptr;
+static int g_counter_dev = -1;
+static unsigned g_counter_next = 0;
+static const unsigned kCounters = 256;
+
+unsigned long long* work_counter(cudaStream_t stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_counter_dev != dev) {
+    if (cudaMalloc(&d_counters, kCounters * sizeof(unsigned long long)) != cudaSuccess) {
+      set_error("work_counter: cudaMalloc failed");
+      return nullptr;
+    }
+    g_counter_dev = dev;
+  }
+  unsigned long long* c = d_counters + (g_counter_next++ % kCounters);
+  if (cudaMemsetAsync(c, 0, sizeof(unsigned long long), stream) != cudaSuccess) {
+    set_error("work_counter: cudaMemsetAsync failed");
+    return nullptr;
+  }
+  return c;
+}
+
 }  // namespace ubpl
 
 extern "C" const char* ubpl_last_error(void) { return ubpl::g_err; }

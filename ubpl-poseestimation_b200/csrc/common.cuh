@@ -125,4 +125,25 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Gaussian target geometry shared by K2 (visibility gate) and K3 (render)
+// ---------------------------------------------------------------------------------------------
+struct Gauss {
+  int kx, ky;       // int(kp): truncation toward zero
+  double cx, cy;    // int(kp) * 1.0 / stride
+  float vis;
+};
+
+// utils/process.py:262-272
+__device__ __forceinline__ Gauss gauss_setup(float kxf, float kyf, int img_h, int img_w, float stride, float sigma) {
+  Gauss g;
+  g.kx = (int)kxf;
+  g.ky = (int)kyf;
+  const int ulx = (int)((float)g.kx - sigma), uly = (int)((float)g.ky - sigma);
+  const int brx = (int)((float)g.kx + sigma + 1.f), bry = (int)((float)g.ky + sigma + 1.f);
+  g.vis = (brx >= img_w || bry >= img_h || ulx < 0 || uly < 0) ? 0.f : 1.f;
+  g.cx = (double)g.kx * 1.0 / (double)stride;
+  g.cy = (double)g.ky * 1.0 / (double)stride;
+  return g;
+}
 }  // namespace ubpl

@@ -56,105 +56,95 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return t;
 }
 
-struct Gauss {
-  int kx, ky;       // int(kp): truncation toward zero
-  double cx, cy;    // int(kp) * 1.0 / stride
-  float vis;
-};
-
-// utils/process.py:262-272
-__device__ __forceinline__ Gauss gauss_setup(float kxf, float kyf, int img_h, int img_w, float stride, float sigma) {
-  Gauss g;
-  g.kx = (int)kxf;
-  g.ky = (int)kyf;
-  const int ulx = (int)((float)g.kx - sigma), uly = (int)((float)g.ky - sigma);
-  const int brx = (int)((float)g.kx + sigma + 1.f), bry = (int)((float)g.ky + sigma + 1.f);
-  g.vis = (brx >= img_w || bry >= img_h || ulx < 0 || uly < 0) ? 0.f : 1.f;
-  g.cx = (double)g.kx * 1.0 / (double)stride;
-  g.cy = (double)g.ky * 1.0 / (double)stride;
-  return g;
-}
 __device__ __forceinline__ float gauss_1d(int k, double c, float sigma) {
   const float d = (float)((double)k - c);
   return expf(-(d * d) / (2.f * sigma * sigma));
 }
+// the rare pixel within rounding of the 0.01 cut: decide like the reference, in float64
+__device__ __noinline__ float gauss_px_exact(int x, int y, double cx, double cy, float sigma) {
+  const double dx = (double)x - cx, dy = (double)y - cy;
+  const double D2 = dx * dx + dy * dy;
+  const double k = exp(-D2 / 2.0 / (double)sigma / (double)sigma);
+  return (k < 0.01) ? 0.f : (float)k;
+}
 __device__ __forceinline__ float gauss_px(const float* ex, const float* ey, int x, int y, const Gauss& g, float sigma) {
-  float v = ex[x] * ey[y];
-  if (fabsf(v - 0.01f) < 1e-5f) {   // within rounding of the cut: decide like the reference, in float64
-    const double dx = (double)x - g.cx, dy = (double)y - g.cy;
-    const double D2 = dx * dx + dy * dy;
-    const double k = exp(-D2 / 2.0 / (double)sigma / (double)sigma);
-    return (k < 0.01) ? 0.f : (float)k;
-  }
+  const float v = ex[x] * ey[y];
+  if (fabsf(v - 0.01f) < 1e-5f) return gauss_px_exact(x, y, g.cx, g.cy, sigma);
   return (v < 0.01f) ? 0.f : v;
 }
 
-__global__ void __launch_bounds__(256) render_mse_kernel(
+// One WARP per (sample, joint): no block barriers; every lane keeps 8 independent 128-bit loads in
+// flight; the separable Gaussian factors live in a per-warp shared-memory slice.
+template <bool VEC>
+__global__ void __launch_bounds__(256, 3) render_mse_kernel(
     const float* __restrict__ kps, const float* __restrict__ gate_in, const float* __restrict__ sample_w,
     const float* __restrict__ pred, long long pB, long long pS, long long pJ, float* __restrict__ grad, long long gB,
     long long gS, long long gJ, float* __restrict__ target, int B, int S, int J, int H, int W, int img_h, int img_w,
     float stride, float sigma, const float* __restrict__ grad_scale, float* __restrict__ gate_out,
-    float* __restrict__ per_loss, int vec) {
+    float* __restrict__ per_loss) {
   extern __shared__ float sm[];
-  float* ex = sm;            // [W]
-  float* ey = sm + W;        // [H]
-  float* red = sm + W + H;   // [32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float* ex = sm + (size_t)warp * (W + H);   // [W]
+  float* ey = ex + W;                        // [H]
   const int HW = H * W, nq = (HW + 3) >> 2;
   const float gs = grad_scale ? *grad_scale : 1.f;
   const float inv_hw = 1.f / (float)HW;
-  for (long long item = blockIdx.x; item < (long long)B * J; item += gridDim.x) {
+  const long long BJ = (long long)B * J;
+  constexpr int U = 8;
+  for (long long item = (long long)blockIdx.x * wpb + warp; item < BJ; item += (long long)gridDim.x * wpb) {
     const int b = (int)(item / J), j = (int)(item % J);
     const Gauss g = gauss_setup(kps[2 * item], kps[2 * item + 1], img_h, img_w, stride, sigma);
-    __syncthreads();
-    for (int k = threadIdx.x; k < W + H; k += blockDim.x) {
+    __syncwarp();
+    for (int k = lane; k < W + H; k += 32) {
       if (k < W) ex[k] = gauss_1d(k, g.cx, sigma); else ey[k - W] = gauss_1d(k - W, g.cy, sigma);
     }
-    __syncthreads();
+    __syncwarp();
     const float gate = (gate_in ? gate_in[item] : 1.f) * g.vis;
     const float wb = sample_w ? sample_w[b] : 1.f;
     const float gcoef = gs * 2.f * inv_hw * gate * wb;
-    if (threadIdx.x == 0 && gate_out) gate_out[item] = gate;
-    for (int s = 0; s < S; ++s) {
-      const float* p = pred + (long long)b * pB + (long long)s * pS + (long long)j * pJ;
-      float* gr = grad ? grad + (long long)b * gB + (long long)s * gS + (long long)j * gJ : nullptr;
-      float* tg = (target && s == 0) ? target + item * HW : nullptr;
+    if (lane == 0 && gate_out) gate_out[item] = gate;
+    for (int st = 0; st < S; ++st) {
+      const float* p = pred + (long long)b * pB + (long long)st * pS + (long long)j * pJ;
+      float* gr = grad ? grad + (long long)b * gB + (long long)st * gS + (long long)j * gJ : nullptr;
+      float* tg = (target && st == 0) ? target + item * HW : nullptr;
       float sse = 0.f;
-      for (int q0 = threadIdx.x; q0 < nq; q0 += 4 * blockDim.x) {
-        float4 pv[4];
+      for (int q0 = lane; q0 < nq; q0 += 32 * U) {
+        float4 pv[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int q = q0 + u * blockDim.x;
-          if (q < nq) pv[u] = load4(p, q, HW, vec);
+        for (int u = 0; u < U; ++u) {
+          const int q = q0 + 32 * u;
+          if (q < nq) pv[u] = load4(p, q, HW, VEC);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int q = q0 + u * blockDim.x;
+        for (int u = 0; u < U; ++u) {
+          const int q = q0 + 32 * u;
           if (q >= nq) continue;
           const int k = q << 2;
           float4 t;
-          if (vec) {                                    // W % 4 == 0: the four texels share a row
+          if (VEC) {                                    // W % 4 == 0: the four texels share a row
             const int y = k / W, x = k - y * W;
             t.x = gauss_px(ex, ey, x, y, g, sigma); t.y = gauss_px(ex, ey, x + 1, y, g, sigma);
             t.z = gauss_px(ex, ey, x + 2, y, g, sigma); t.w = gauss_px(ex, ey, x + 3, y, g, sigma);
           } else {
             float tt[4];
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
               const int kk = min(k + c, HW - 1);
               tt[c] = gauss_px(ex, ey, kk % W, kk / W, g, sigma);
             }
             t = make_float4(tt[0], tt[1], tt[2], tt[3]);
-            if (k + 1 >= HW) { pv[u].y = t.y; }       // padded lanes contribute zero error
-            if (k + 2 >= HW) { pv[u].z = t.z; }
-            if (k + 3 >= HW) { pv[u].w = t.w; }
+            if (k + 1 >= HW) pv[u].y = t.y;              // padded lanes contribute zero error
+            if (k + 2 >= HW) pv[u].z = t.z;
+            if (k + 3 >= HW) pv[u].w = t.w;
           }
           const float4 d = make_float4(pv[u].x - t.x, pv[u].y - t.y, pv[u].z - t.z, pv[u].w - t.w);
           sse += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
-          if (gr) store4(gr, q, HW, vec, make_float4(gcoef * d.x, gcoef * d.y, gcoef * d.z, gcoef * d.w));
-          if (tg) store4(tg, q, HW, vec, t);
+          if (gr) store4(gr, q, HW, VEC, make_float4(gcoef * d.x, gcoef * d.y, gcoef * d.z, gcoef * d.w));
+          if (tg) store4(tg, q, HW, VEC, t);
         }
       }
-      const float tot = block_sum(sse, red);
-      if (threadIdx.x == 0 && per_loss) per_loss[((long long)b * S + s) * J + j] = ((tot * inv_hw) * gate) * wb;
+      const float tot = warp_sum(sse);
+      if (lane == 0 && per_loss) per_loss[((long long)b * S + st) * J + j] = ((tot * inv_hw) * gate) * wb;
     }
   }
 }
@@ -353,11 +343,20 @@ extern "C" int ubpl_render_mse(const float* kps, const float* gate_in, const flo
   int vec = (W % 4 == 0) && aligned16(pred) && pB % 4 == 0 && pS % 4 == 0 && pJ % 4 == 0;
   if (grad) vec = vec && aligned16(grad) && gB % 4 == 0 && gS % 4 == 0 && gJ % 4 == 0;
   if (target) vec = vec && aligned16(target) && (HW % 4 == 0);
-  const size_t smem = (size_t)(W + H + 32) * sizeof(float);
-  const int grid = (int)(BJ < (long long)sm_count() * 8 ? BJ : (long long)sm_count() * 8);
-  render_mse_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS,
-                                                               gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma,
-                                                               grad_scale, gate_out, per_loss, vec);
+  const int wpb = 8;
+  const size_t smem = (size_t)wpb * (W + H) * sizeof(float);
+  UBPL_REQUIRE(smem <= 48 * 1024, "ubpl_render_mse: heat-map sides too large (%d x %d)", H, W);
+  const long long need = (BJ + wpb - 1) / wpb;
+  const long long cap = (long long)sm_count() * 8;
+  const int grid = (int)(need < cap ? need : cap);
+  if (vec)
+    render_mse_kernel<true><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS,
+                                                                            gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma,
+                                                                            grad_scale, gate_out, per_loss);
+  else
+    render_mse_kernel<false><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS,
+                                                                             gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma,
+                                                                             grad_scale, gate_out, per_loss);
   return check_launch("ubpl_render_mse");
 }
 

@@ -261,6 +261,59 @@ __global__ void select_fixed_kernel(const double* __restrict__ dist, const doubl
   }
 }
 
+// Fused K2 for the mean-teacher fixed-threshold path (one CTA, everything of K2 in one launch):
+// dispersion (evaluation.py:44-54) -> unc = 1-exp(-d/5) <= 1-exp(-3*distThrMax/5) (business.py:237-261,
+// 375-376) -> gate = enable * visibility (process.py:262-268) -> count and grad_scale (MT_UBPL.py:266).
+__global__ void __launch_bounds__(1024) k2_view_fixed_kernel(const float* __restrict__ preds, int K, long long BJ, int J,
+                                                              double distThrMax, int img_h, int img_w, float stride,
+                                                              float sigma, int S, float loss_weight, float* out_mean,
+                                                              double* out_dist, uint8_t* out_legal, uint8_t* enable,
+                                                              float* gate_out, float* grad_scale, int32_t* count_out,
+                                                              int32_t* counts, PowTab T) {
+  __shared__ int red[32];
+  const double thr = __dsub_rn(1.0, exp(-__ddiv_rn(__dmul_rn(distThrMax, 3.0), 5.0)));
+  for (int jj = threadIdx.x; jj <= J; jj += blockDim.x) counts[jj] = 0;
+  __syncthreads();
+  int c = 0;
+  for (long long i = threadIdx.x; i < BJ; i += blockDim.x) {
+    float sx = preds[2 * i], sy = preds[2 * i + 1];
+    bool legal = (sx >= 0.f) && (sy >= 0.f);
+    for (int k = 1; k < K; ++k) {
+      const float x = preds[2 * ((long long)k * BJ + i)], y = preds[2 * ((long long)k * BJ + i) + 1];
+      sx = __fadd_rn(sx, x);
+      sy = __fadd_rn(sy, y);
+      legal = legal && (x >= 0.f) && (y >= 0.f);
+    }
+    const float mx = __fdiv_rn(sx, (float)K), my = __fdiv_rn(sy, (float)K);
+    double acc = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double x = (double)preds[2 * ((long long)k * BJ + i)], y = (double)preds[2 * ((long long)k * BJ + i) + 1];
+      acc = __dadd_rn(acc, py_dist(x, y, (double)mx, (double)my, T));
+    }
+    const double dist = legal ? __ddiv_rn(acc, (double)K) : 999.0;
+    const double unc = __dsub_rn(1.0, exp(-__ddiv_rn(dist, 5.0)));
+    const bool en = legal && (unc <= thr);
+    const Gauss g = gauss_setup(mx, my, img_h, img_w, stride, sigma);
+    const float gt = (en ? 1.f : 0.f) * g.vis;
+    if (out_mean) { out_mean[2 * i] = mx; out_mean[2 * i + 1] = my; }
+    if (out_dist) out_dist[i] = dist;
+    if (out_legal) out_legal[i] = legal ? 1 : 0;
+    if (enable) enable[i] = en ? 1 : 0;
+    gate_out[i] = gt;
+    if (en) { atomicAdd(counts + (int)(i % J), 1); atomicAdd(counts + J, 1); }
+    c += (gt > 0.f) ? 1 : 0;
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    if (count_out) *count_out = S * t;
+    if (grad_scale) *grad_scale = (t > 0) ? loss_weight / (float)(S * t) : loss_weight;
+  }
+}
+
 static inline int blocks_for(long long n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace ubpl
@@ -368,4 +421,18 @@ extern "C" int ubpl_select_fixed(const double* dist, const double* legal, int64_
   select_fixed_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dist, legal, n, J, distThrMax, enable,
                                                                             gate32, counts, unc_out);
   return check_launch("ubpl_select_fixed");
+}
+
+extern "C" int ubpl_k2_view_fixed(const float* preds, int K, int B, int J, double distThrMax, int img_h, int img_w,
+                                  float stride, float sigma, int S, float loss_weight, float* out_mean,
+                                  double* out_dist, uint8_t* out_legal, uint8_t* enable, float* gate_out,
+                                  float* grad_scale, int32_t* count_out, int32_t* counts, void* stream) {
+  UBPL_REQUIRE(preds && gate_out && counts && K >= 1 && B >= 0 && J >= 1 && S >= 1 && stride > 0.f && sigma > 0.f,
+               "ubpl_k2_view_fixed: bad arguments");
+  GET_POWTAB(T);
+  k2_view_fixed_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(preds, K, (long long)B * J, J, distThrMax, img_h, img_w,
+                                                             stride, sigma, S, loss_weight, out_mean, out_dist,
+                                                             out_legal, enable, gate_out, grad_scale, count_out,
+                                                             counts, T);
+  return check_launch("ubpl_k2_view_fixed");
 }

@@ -30,6 +30,8 @@
 
 namespace ubpl {
 
+unsigned long long* work_counter(cudaStream_t stream);   // api.cu: a zeroed device counter for this launch
+
 struct WDParams {
   const float* maps;
   long long sV, sB, sJ;
@@ -43,6 +45,7 @@ struct WDParams {
   float* out_xy;
   float* out_hm_xy;
   unsigned long long* stats;
+  unsigned long long* work;   // global claim counter (zeroed before the launch)
 };
 
 struct Xform {
@@ -98,42 +101,72 @@ __device__ __forceinline__ void load_xform(Xform& X, const float* theta, const u
   X.flip = flip ? (flip[vb] != 0) : false;
 }
 
-// Exhaustive decode of the warped map in canonical (mirrored) pixel order.
-__device__ __forceinline__ void decode_exhaustive(const float* s, const Xform& X, int lane, float& bv, int& bi) {
-  const int HW = X.H * X.W;
+// Exhaustive decode of the warped map.  Each lane walks whole columns (the column terms of the
+// affine grid are hoisted), so the tie rule is carried by arg_better's index comparison.
+__device__ __noinline__ void decode_exhaustive(const float* s, const Xform& X, int lane, float& bv, int& bi) {
   bv = -INFINITY;
   bi = 0x7fffffff;
-  for (int k = lane; k < HW; k += 32) {
-    const int i = k / X.W, jo = k - i * X.W;
-    const int jw = X.flip ? (X.W - 1 - jo) : jo;
-    const float v = eval_px(s, X, i, jw);
-    if (arg_better(v, k, bv, bi)) { bv = v; bi = k; }
+  const int W = X.W, H = X.H;
+  for (int jo = lane; jo < W; jo += 32) {
+    const int jw = X.flip ? (W - 1 - jo) : jo;
+    const float xl = lin_coord(jw, W, X.stepx);
+    const float ax = __fmul_rn(xl, X.t00), ay = __fmul_rn(xl, X.t10);
+    for (int i = 0; i < H; ++i) {
+      const float yl = lin_coord(i, H, X.stepy);
+      const float gx = __fadd_rn(__fmaf_rn(yl, X.t01, ax), X.t02);
+      const float gy = __fadd_rn(__fmaf_rn(yl, X.t11, ay), X.t12);
+      const float ix = __fmul_rn(__fadd_rn(gx, 1.f), X.sfx);
+      const float iy = __fmul_rn(__fadd_rn(gy, 1.f), X.sfy);
+      const float x0f = floorf(ix), y0f = floorf(iy);
+      const float w = __fsub_rn(ix, x0f), e = __fsub_rn(1.f, w);
+      const float n = __fsub_rn(iy, y0f), so = __fsub_rn(1.f, n);
+      const int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)(W + 1));
+      const int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)(H + 1));
+      const bool xa = (unsigned)x0 < (unsigned)W, xb = (unsigned)(x0 + 1) < (unsigned)W;
+      const bool ya = (unsigned)y0 < (unsigned)H, yb = (unsigned)(y0 + 1) < (unsigned)H;
+      const float* r0 = s + y0 * W + x0;
+      const float v_nw = (xa & ya) ? r0[0] : 0.f;
+      const float v_ne = (xb & ya) ? r0[1] : 0.f;
+      const float v_sw = (xa & yb) ? r0[W] : 0.f;
+      const float v_se = (xb & yb) ? r0[W + 1] : 0.f;
+      float acc = __fmul_rn(v_nw, __fmul_rn(so, e));
+      acc = __fmaf_rn(v_ne, __fmul_rn(so, w), acc);
+      acc = __fmaf_rn(v_sw, __fmul_rn(n, e), acc);
+      acc = __fmaf_rn(v_se, __fmul_rn(n, w), acc);
+      const int k = i * W + jo;
+      if (arg_better(acc, k, bv, bi)) { bv = acc; bi = k; }
+    }
   }
   warp_argmax(bv, bi);
 }
 
-// Arg-max of the raw staged map (no warp): torch.max semantics incl. NaN.
-__device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float& bv, int& bi, float& mn,
-                                         bool& nonfinite) {
-  bv = -INFINITY; bi = 0x7fffffff; mn = INFINITY; nonfinite = false;
+// Pass A over the staged map at float4 granularity: per-lane max (value, first float4 index),
+// min, and a running sum that turns non-finite if any texel is NaN/Inf.
+__device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float& bv, int& bq, float& mn,
+                                         float& fsum) {
+  bv = -INFINITY; bq = 0; mn = INFINITY; fsum = 0.f;
   const int nq = HW >> 2;
   const float4* s4 = reinterpret_cast<const float4*>(s);
-#pragma unroll 4
-  for (int q = lane; q < nq; q += 32) {
-    const float4 x = s4[q];
-    const int k = q << 2;
-    if (x.x > bv) { bv = x.x; bi = k; }
-    if (x.y > bv) { bv = x.y; bi = k + 1; }
-    if (x.z > bv) { bv = x.z; bi = k + 2; }
-    if (x.w > bv) { bv = x.w; bi = k + 3; }
-    mn = fminf(fminf(mn, fminf(x.x, x.y)), fminf(x.z, x.w));
-    nonfinite |= !((fabsf(x.x) <= FLT_MAX) & (fabsf(x.y) <= FLT_MAX) & (fabsf(x.z) <= FLT_MAX) & (fabsf(x.w) <= FLT_MAX));
+  int q = lane;
+  for (; q + 96 < nq; q += 128) {
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = s4[q + 32 * u];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float m4 = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
+      const float n4 = fminf(fminf(x[u].x, x[u].y), fminf(x[u].z, x[u].w));
+      fsum += (x[u].x + x[u].y) + (x[u].z + x[u].w);
+      if (m4 > bv) { bv = m4; bq = q + 32 * u; }
+      mn = fminf(mn, n4);
+    }
   }
-  for (int k = (nq << 2) + lane; k < HW; k += 32) {
-    const float x = s[k];
-    if (x > bv) { bv = x; bi = k; }
-    mn = fminf(mn, x);
-    nonfinite |= !(fabsf(x) <= FLT_MAX);
+  for (; q < nq; q += 32) {
+    const float4 x = s4[q];
+    const float m4 = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+    fsum += (x.x + x.y) + (x.z + x.w);
+    if (m4 > bv) { bv = m4; bq = q; }
+    mn = fminf(mn, fminf(fminf(x.x, x.y), fminf(x.z, x.w)));
   }
 }
 
@@ -154,31 +187,38 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   const int H = p.H, W = p.W, HW = H * W;
   const uint32_t map_bytes = (uint32_t)HW * 4u;
   const uint32_t buf_stride = (map_bytes + 127u) & ~127u;   // keep every buffer 128 B aligned
-  const int NB = p.nbuf;
+  const int NB = p.nbuf;                                    // 1 or 2 buffers per warp
   float* buf0 = reinterpret_cast<float*>(smem_raw + (size_t)warp * NB * buf_stride);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warps * NB * buf_stride) + warp * NB;
 
   const long long N = (long long)p.V * p.B * p.J;
-  const long long gw = (long long)blockIdx.x * warps + warp;
-  const long long TW = (long long)gridDim.x * warps;
   uint64_t pol = 0;
-  if (p.use_bulk) {
-    if (lane == 0) {
-      for (int b = 0; b < NB; ++b) mbar_init(&bars[b], 1);
-      fence_mbar_init();
-      pol = l2_evict_first_policy();
-      for (int b = 0; b < NB; ++b) {
-        const long long n = gw + (long long)b * TW;
-        if (n < N) issue_map(p, n, buf0 + (size_t)b * (buf_stride >> 2), &bars[b], pol, map_bytes);
-      }
-    }
-    __syncwarp();
+  // dynamic work distribution: every warp claims the next map index from a global counter, so a
+  // warp that meets an exhaustively decoded map does not delay a fixed share of the work
+  auto claim = [&]() -> long long {
+    unsigned long long n = 0;
+    if (lane == 0) n = atomicAdd(p.work, 1ull);
+    return (long long)__shfl_sync(0xffffffffu, n, 0);
+  };
+  long long nxt0 = N, nxt1 = N;
+  if (p.use_bulk && lane == 0) {
+    for (int b = 0; b < NB; ++b) mbar_init(&bars[b], 1);
+    fence_mbar_init();
+    pol = l2_evict_first_policy();
+  }
+  __syncwarp();
+  nxt0 = claim();
+  if (p.use_bulk && lane == 0 && nxt0 < N) issue_map(p, nxt0, buf0, &bars[0], pol, map_bytes);
+  if (NB == 2) {
+    nxt1 = claim();
+    if (p.use_bulk && lane == 0 && nxt1 < N) issue_map(p, nxt1, buf0 + (buf_stride >> 2), &bars[1], pol, map_bytes);
   }
 
   unsigned long long n_slow = 0, n_eval = 0, n_maps = 0;
-  long long it = 0;
-  for (long long n = gw; n < N; n += TW, ++it) {
-    const int bsel = (int)(it % NB);
+  for (long long it = 0;; ++it) {
+    const int bsel = (NB == 2) ? (int)(it & 1) : 0;
+    const long long n = bsel ? nxt1 : nxt0;
+    if (n >= N) break;
     float* s = buf0 + (size_t)bsel * (buf_stride >> 2);
     const int j = (int)(n % p.J);
     const long long vb = n / p.J;
@@ -193,14 +233,25 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     }
     ++n_maps;
 
-    // ---- pass A: raw max / arg-max / min -------------------------------------------------
-    float bv, mn; int bi; bool nonfinite;
-    scan_max(s, HW, lane, bv, bi, mn, nonfinite);
-    nonfinite = __any_sync(0xffffffffu, nonfinite);
+    // ---- pass A: raw max / location / min / finiteness -----------------------------------------
+    float bv, mn, fsum; int bq;
+    scan_max(s, HW, lane, bv, bq, mn, fsum);
+    int bi = 0x7fffffff;                  // flat index of the lane's first maximum
+    if (bv > -INFINITY) {
+      const float4 x = reinterpret_cast<const float4*>(s)[bq];
+      bi = (bq << 2) + ((x.x == bv) ? 0 : (x.y == bv) ? 1 : (x.z == bv) ? 2 : 3);
+    }
+    for (int k = ((HW >> 2) << 2) + lane; k < HW; k += 32) {   // tail when H*W % 4 != 0
+      const float x = s[k];
+      fsum += x;
+      if (x > bv) { bv = x; bi = k; }
+      mn = fminf(mn, x);
+    }
+    const bool nonfinite = __any_sync(0xffffffffu, !(fabsf(fsum) <= FLT_MAX));
     float rv = bv; int ri = bi;           // result (value, canonical flat index)
     Xform X;
     if (!p.do_warp) {
-      if (nonfinite) {                    // torch.max: the first NaN wins
+      if (nonfinite) {                    // torch.max: the first NaN wins; +-Inf compare normally
         rv = -INFINITY; ri = 0x7fffffff;
         for (int k = lane; k < HW; k += 32) { const float x = s[k]; if (arg_better(x, k, rv, ri)) { rv = x; ri = k; } }
       }
@@ -340,10 +391,9 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       }
     }
     __syncwarp();
-    if (p.use_bulk && lane == 0) {
-      const long long nn = n + (long long)NB * TW;
-      if (nn < N) issue_map(p, nn, s, &bars[bsel], pol, map_bytes);
-    }
+    const long long nn = claim();
+    if (bsel) nxt1 = nn; else nxt0 = nn;
+    if (p.use_bulk && lane == 0 && nn < N) issue_map(p, nn, s, &bars[bsel], pol, map_bytes);
   }
   if (p.stats && lane == 0 && n_maps) {
     atomicAdd(p.stats + 0, n_slow);
@@ -420,6 +470,8 @@ extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64
     if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
     attr_set = true;
   }
+  p.work = work_counter((cudaStream_t)stream);
+  if (!p.work) return UBPL_ERR_CUDA;
   long long need = (N + warps - 1) / warps;
   int grid = (int)(need < sm_count() ? need : sm_count());
   warp_decode_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(p);

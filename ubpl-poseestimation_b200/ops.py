@@ -216,6 +216,28 @@ def select_fixed(dist, legal, J, distThrMax):
     return dict(enable=enable, gate=gate, counts=counts, unc=unc)
 
 
+def k2_view_fixed(preds, distThrMax, S, img_h, img_w, stride, sigma=3.0, loss_weight=1.0):
+    """One-launch K2 for the mean-teacher fixed-threshold path: dispersion + fixed rule + visibility gate +
+    count/grad_scale.  preds [K,B,J,2].  Same outputs as view_dispersion + select_fixed + gate_prepare."""
+    _need_cuda(preds)
+    preds = preds.to(_f32).contiguous()
+    K, B, J, _ = preds.shape
+    dev = preds.device
+    mean = torch.empty(B, J, 2, dtype=_f32, device=dev)
+    dist = torch.empty(B, J, dtype=_f64, device=dev)
+    legal = torch.empty(B, J, dtype=torch.uint8, device=dev)
+    enable = torch.empty(B, J, dtype=torch.uint8, device=dev)
+    gate = torch.empty(B, J, dtype=_f32, device=dev)
+    grad_scale = torch.empty(1, dtype=_f32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    counts = torch.empty(J + 1, dtype=torch.int32, device=dev)
+    _lib.call("ubpl_k2_view_fixed", preds.data_ptr(), K, B, J, float(distThrMax), int(img_h), int(img_w), float(stride),
+              float(sigma), int(S), float(loss_weight), mean.data_ptr(), dist.data_ptr(), legal.data_ptr(),
+              enable.data_ptr(), gate.data_ptr(), grad_scale.data_ptr(), count.data_ptr(), counts.data_ptr(), _stream())
+    return dict(mean=mean, dist=dist, legal=legal, enable=enable, gate=gate, grad_scale=grad_scale, count=count,
+                counts=counts)
+
+
 # -------------------------------------------------------------------------------------------------
 # K3
 # -------------------------------------------------------------------------------------------------

@@ -31,6 +31,7 @@ class StepConfig:
     sigma: float = 3.0               # kernelSize * sigma, process.py:258
     want_target: bool = True         # materialise the rendered targets (counted in the byte model)
     want_grad: bool = True
+    fuse_k2: bool = True             # one-launch K2 for the M=1 fixed-threshold path
 
 
 def nega_weights(islabeled, pseudoWeight):
@@ -68,25 +69,33 @@ def pseudo_label_step(teacher, student, theta, flip, dec, sample_w, cfg: StepCon
         idx = torch.stack([o["idx"] for o in outs])
     mark("k1_1")
     # ---- K2: dispersion + selection ----------------------------------------------------------------
-    if M == 1:
-        vd = ops.view_dispersion(xy[0], sentinel_illegal=True)
-        kps, dist, legal = vd["mean"], vd["dist"], vd["legal"]
-        extra = dict(unc32=vd["unc32"], max_bits=vd["max_bits"])
-    elif M == 2:
-        vd1, vd2 = ops.view_dispersion(xy[0]), ops.view_dispersion(xy[1])
-        ad = ops.assess_dual(vd1["mean"], vd2["mean"], None, xy[0], xy[1])
-        kps, dist, legal = ad["coord32"], ad["extDist"], ad["legal"]
-        extra = dict(assess=ad)
+    fused_k2 = (cfg.fuse_k2 and M == 1 and cfg.select == "fixed" and B * J <= 65536)
+    if fused_k2:
+        k2 = ops.k2_view_fixed(xy[0], cfg.distThrMax, S, img_h, img_w, stride, cfg.sigma, cfg.lossWeight)
+        kps, dist, legal = k2["mean"], k2["dist"], k2["legal"]
+        gate, grad_scale, count = k2["gate"], k2["grad_scale"], k2["count"]
+        sel = dict(enable=k2["enable"], counts=k2["counts"])
+        extra = {}
     else:
-        raise ValueError("pseudo_label_step supports M = 1 (mean teacher) or M = 2 (dual teachers)")
-    if cfg.select == "fixed":
-        sel = ops.select_fixed(dist, legal, J, cfg.distThrMax)
-    elif cfg.select == "quantile":
-        sel = ops.select_quantile(dist, legal, J, cfg.reliableThr, cfg.reliablePCT, cfg.reliableDistMin, group=group)
-    else:
-        raise ValueError("select must be 'fixed' or 'quantile'")
-    # ---- K3: render + masked MSE forward/backward --------------------------------------------------
-    gate, grad_scale, count = ops.gate_prepare(kps, sel["gate"], S, img_h, img_w, stride, cfg.sigma, cfg.lossWeight)
+        if M == 1:
+            vd = ops.view_dispersion(xy[0], sentinel_illegal=True)
+            kps, dist, legal = vd["mean"], vd["dist"], vd["legal"]
+            extra = dict(unc32=vd["unc32"], max_bits=vd["max_bits"])
+        elif M == 2:
+            vd1, vd2 = ops.view_dispersion(xy[0]), ops.view_dispersion(xy[1])
+            ad = ops.assess_dual(vd1["mean"], vd2["mean"], None, xy[0], xy[1])
+            kps, dist, legal = ad["coord32"], ad["extDist"], ad["legal"]
+            extra = dict(assess=ad)
+        else:
+            raise ValueError("pseudo_label_step supports M = 1 (mean teacher) or M = 2 (dual teachers)")
+        if cfg.select == "fixed":
+            sel = ops.select_fixed(dist, legal, J, cfg.distThrMax)
+        elif cfg.select == "quantile":
+            sel = ops.select_quantile(dist, legal, J, cfg.reliableThr, cfg.reliablePCT, cfg.reliableDistMin, group=group)
+        else:
+            raise ValueError("select must be 'fixed' or 'quantile'")
+        # ---- K3: render + masked MSE forward/backward ----------------------------------------------
+        gate, grad_scale, count = ops.gate_prepare(kps, sel["gate"], S, img_h, img_w, stride, cfg.sigma, cfg.lossWeight)
     mark("k3_0")
     r = ops.render_mse(kps, gate, sample_w, student, img_h, img_w, stride, cfg.sigma, grad_scale=grad_scale,
                        want_grad=cfg.want_grad, want_target=cfg.want_target)
