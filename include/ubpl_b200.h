@@ -183,8 +183,9 @@ int ubpl_loss_finalize(const float* per_loss, const float* mask, const float* ga
 int ubpl_gate_prepare(const float* kps, const float* gate_in, int64_t n, int img_h, int img_w, float stride,
                       float sigma, int S, float loss_weight, float* gate_out, float* grad_scale,
                       int32_t* count_out, void* stream);
-/* x[0..n) *= *scale (device scalar) -- the backward of the autograd wrappers; x 16-byte aligned. */
-int ubpl_scale_inplace(float* x, int64_t n, const float* scale, void* stream);
+/* dst[0..n) = src[0..n) * *scale (device scalar; dst may alias src) -- the backward of the autograd
+ * wrappers; both 16-byte aligned. */
+int ubpl_scale(float* dst, const float* src, int64_t n, const float* scale, void* stream);
 
 /* ---- K4: mean-teacher EMA, all parameter tensors in one launch ---------------------------------
  * update_ema_variables (utils/parameters.py:4-8): ema = ema*alpha + (1-alpha)*param, float32,

@@ -42,7 +42,7 @@ SIGNATURES = {
                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_loss_finalize": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "ubpl_gate_prepare": [c_void_p, c_void_p, c_i64, c_int, c_int, c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
-    "ubpl_scale_inplace": [c_void_p, c_i64, c_void_p, c_void_p],
+    "ubpl_scale": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p],
     "ubpl_ema_multi_tensor": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_float, c_void_p],
     "ubpl_ema_flat": [c_void_p, c_void_p, c_i64, c_float, c_float, c_void_p],
 }

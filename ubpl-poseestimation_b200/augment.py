@@ -1,0 +1,52 @@
+"""Drop-in for the heat-map side of utils/augment.py (AugmentUtils): same classmethod names and
+argument meaning.  The forward image augmentation (skimage / cv2, CPU data-loader side) is out of
+scope and stays with the reference."""
+import math
+
+import torch
+
+from . import ops
+
+
+def _to_cuda(t):
+    return t if t.is_cuda else t.cuda()
+
+
+class AugmentUtils:
+    @classmethod
+    def affine_back2(cls, heatmap, warpmat, isflip):
+        """utils/augment.py:37-47: back-warp (affine_grid + bilinear grid_sample, zeros padding,
+        align_corners=True) and per-sample W mirror, one kernel; returns a new tensor on the
+        input's device.  Bit-identical to ATen's CPU kernels."""
+        dev = heatmap.device
+        out = ops.warp_materialize(_to_cuda(heatmap.detach()), _to_cuda(warpmat.detach()),
+                                   _to_cuda(torch.as_tensor(isflip)))
+        return out.to(dev)
+
+    affine_back2_classification = affine_back2      # utils/augment.py:64-74 is the same function
+
+    @classmethod
+    def fliplr_back_tensor(cls, flip_output):
+        """utils/augment.py:247-252: mirror of the last (W) axis of a 3-D / 4-D tensor (no joint
+        swap).  Expressed as affine_back2 with an exact mirror: the identity warp is NOT an exact
+        copy in ATen, so the flip is done by the dedicated mirror path with theta unused."""
+        if flip_output.ndim not in (3, 4):
+            return None                              # the reference falls through and returns None
+        x = flip_output if flip_output.ndim == 4 else flip_output.unsqueeze(0)
+        dev = x.device
+        out = ops.mirror_w(_to_cuda(x.detach().to(torch.float32)))
+        out = out.to(dev)
+        return out if flip_output.ndim == 4 else out[0]
+
+    @classmethod
+    def affine_getWarpmat(cls, angle, scale, matrixRes=[64, 64]):
+        """utils/augment.py:159-164: cv2.getRotationMatrix2D(centre, angle, 1/scale) ->
+        cv2.invertAffineTransform -> translation zeroed -> float32 [2,3] (host scalars; OpenCV's
+        float64 formulas restated, no cv2 dependency)."""
+        ang = float(angle) * math.pi / 180.0
+        sc = 1.0 / float(scale)
+        alpha, beta = math.cos(ang) * sc, math.sin(ang) * sc
+        m00, m01, m10, m11 = alpha, beta, -beta, alpha
+        D = m00 * m11 - m01 * m10
+        D = 1.0 / D if D != 0 else 0.0
+        return torch.tensor([[m11 * D, m01 * (-D), 0.0], [m10 * (-D), m00 * D, 0.0]], dtype=torch.float64).float()

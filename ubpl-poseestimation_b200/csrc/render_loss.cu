@@ -313,16 +313,17 @@ __global__ void __launch_bounds__(1024) gate_prepare_kernel(const float* __restr
   }
 }
 
-__global__ void scale_inplace_kernel(float* __restrict__ x, long long n, const float* __restrict__ scale) {
+__global__ void scale_kernel(float* __restrict__ dst, const float* src, long long n, const float* __restrict__ scale) {
   const float s = *scale;
   const long long n4 = n >> 2;
-  float4* x4 = reinterpret_cast<float4*>(x);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const float4* x4 = reinterpret_cast<const float4*>(src);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = x4[i];
     v.x *= s; v.y *= s; v.z *= s; v.w *= s;
-    x4[i] = v;
+    d4[i] = v;
   }
-  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= s;
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i] * s;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -421,13 +422,13 @@ extern "C" int ubpl_gate_prepare(const float* kps, const float* gate_in, int64_t
   return check_launch("ubpl_gate_prepare");
 }
 
-extern "C" int ubpl_scale_inplace(float* x, int64_t n, const float* scale, void* stream) {
-  UBPL_REQUIRE(x && scale && n >= 0, "ubpl_scale_inplace: bad arguments");
-  UBPL_REQUIRE(aligned16(x), "ubpl_scale_inplace: x must be 16-byte aligned");
+extern "C" int ubpl_scale(float* dst, const float* src, int64_t n, const float* scale, void* stream) {
+  UBPL_REQUIRE(dst && src && scale && n >= 0, "ubpl_scale: bad arguments");
+  UBPL_REQUIRE(aligned16(dst) && aligned16(src), "ubpl_scale: buffers must be 16-byte aligned");
   if (n == 0) return UBPL_OK;
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
   if (blocks < 1) blocks = 1;
-  scale_inplace_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, scale);
-  return check_launch("ubpl_scale_inplace");
+  scale_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dst, src, n, scale);
+  return check_launch("ubpl_scale");
 }

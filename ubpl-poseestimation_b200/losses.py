@@ -1,0 +1,173 @@
+"""Drop-in replacements for the reference's heat-map criteria (utils/losses.py), same class
+names, constructor arguments, forward signatures and tuple returns (counts are python ints).
+
+    JointMSELoss       utils/losses.py:8-29      JointDistLoss       utils/losses.py:32-53
+    JointPseudoLoss3   utils/losses.py:169-210   JointDistLoss_mt2   utils/losses.py:246-286
+
+Each forward is ONE fused CUDA kernel over the student maps (ubpl_dense_mse: loss, score masks and
+the gradient in the same pass) plus a tiny reduction, and exactly one device->host sync for the
+python-int counts (the reference syncs B*J*S times).  Backward multiplies the stored
+gradient by the upstream scalar on the device.  Differences kept deliberately:
+  * gradients are produced for the prediction argument (and for preds2/targets when they require
+    grad, as minus the prediction gradient); `kpsGate`/`sampleWeight` never get one (the reference
+    marks them requires_grad through tools.py:57-62 but nothing consumes those gradients);
+  * inputs must be CUDA tensors.
+"""
+import torch
+from torch import nn
+
+from . import ops
+
+
+def _as5(x, nStack):
+    """[B,J,H,W] -> [B,1,J,H,W] when nStack == 1."""
+    return x.unsqueeze(1) if nStack == 1 else x
+
+
+class _DenseLossFn(torch.autograd.Function):
+    """loss = sum_{b,s,j} mean_HW (p - t)^2 * coef[b,j] * mask[b,s,j]."""
+
+    @staticmethod
+    def forward(ctx, pred5, tgt, coef, mask_mode, thr, gate_for_count, want_scores):
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        r = ops.dense_mse(pred5.detach(), tgt.detach(), coef=coef, mask_mode=mask_mode, thr=thr,
+                          want_grad=need_grad, want_scores=want_scores)
+        fin = ops.loss_finalize(r["per_loss"], r["mask"] if mask_mode else None, gate_for_count)
+        ctx.grad = r["grad"]
+        ctx.tgt_shape = tgt.shape
+        ctx.pred_shape = pred5.shape
+        ctx.mark_non_differentiable(fin)
+        aux = [t if t is not None else torch.empty(0, device=pred5.device) for t in (r["vmax_p"], r["vmax_t"], r["mask"])]
+        for a in aux:
+            ctx.mark_non_differentiable(a)
+        return (fin[0].to(torch.float32), fin) + tuple(aux)
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        g = ctx.grad
+        if g is None:
+            return (None,) * 7
+        scale = g_loss.detach().reshape(1).to(torch.float32).contiguous()
+        g = ops.scale(g, scale)                     # out of place: the node may be backwarded again (retain_graph)
+        g_pred = g if ctx.needs_input_grad[0] else None
+        g_tgt = None
+        if ctx.needs_input_grad[1]:
+            # d/dt = -d/dp, shared targets accumulate over the stacks, M teacher maps share 1/M each
+            M = ctx.tgt_shape[0]
+            gt = -g / M
+            if len(ctx.tgt_shape) == 5:             # [M,B,J,H,W]: shared by the stacks
+                gt = gt.sum(1)
+            g_tgt = gt.unsqueeze(0).expand(ctx.tgt_shape).contiguous()
+        return g_pred, g_tgt, None, None, None, None, None
+
+
+def _tgt(t):
+    """Targets get a gradient only when they are part of a graph (non-leaf); the leaf Variables the
+    drivers create with requires_grad=True (projects/tools.py:57-62) are treated as constants."""
+    return t if (t.requires_grad and not t.is_leaf) else t.detach()
+
+
+def _coef(B, J, device, kpsGate, useKPsGate, sampleWeight, useSampleWeight):
+    coef = None
+    if useKPsGate and kpsGate is not None:
+        coef = kpsGate.detach().to(device=device, dtype=torch.float32).reshape(B, J)
+    if useSampleWeight and sampleWeight is not None:
+        w = sampleWeight.detach().to(device=device, dtype=torch.float32).reshape(B, 1)
+        coef = w.expand(B, J) if coef is None else coef * w
+    return coef
+
+
+class JointMSELoss(nn.Module):
+    """utils/losses.py:8-29.  forward(preds, gts, kpsGate=None, sampleWeight=None) -> (sum, nStack*count)."""
+
+    def __init__(self, nStack=1, useKPsGate=False, useSampleWeight=False):
+        super().__init__()
+        self.nStack = nStack
+        self.useKPsGate = useKPsGate
+        self.useSampleWeight = useSampleWeight
+
+    def forward(self, preds, gts, kpsGate=None, sampleWeight=None):
+        p5 = _as5(preds, self.nStack)
+        B, S, J = p5.shape[:3]
+        coef = _coef(B, J, p5.device, kpsGate, self.useKPsGate, sampleWeight, self.useSampleWeight)
+        gate = None if kpsGate is None else kpsGate.detach().to(device=p5.device, dtype=torch.float32).reshape(B, J)
+        loss, fin, _, _, _ = _DenseLossFn.apply(p5, _tgt(gts).unsqueeze(0), coef, 0, 0.0, gate, False)
+        kpsNum = int(fin[3].item())                       # kps_getLabeledCount (process.py:382-383); B*J if no gate
+        return loss, self.nStack * kpsNum
+
+
+class JointDistLoss(nn.Module):
+    """utils/losses.py:32-53.  forward(preds1, preds2, kpsGate=None, sampleWeight=None)."""
+
+    def __init__(self, nStack=1, useKPsGate=False, useSampleWeight=False):
+        super().__init__()
+        self.nStack = nStack
+        self.useKPsGate = useKPsGate
+        self.useSampleWeight = useSampleWeight
+
+    def forward(self, preds1, preds2, kpsGate=None, sampleWeight=None):
+        p5 = _as5(preds1, self.nStack)
+        B, S, J = p5.shape[:3]
+        coef = _coef(B, J, p5.device, kpsGate, self.useKPsGate, sampleWeight, self.useSampleWeight)
+        gate = None if kpsGate is None else kpsGate.detach().to(device=p5.device, dtype=torch.float32).reshape(B, J)
+        t = _as5(_tgt(preds2), self.nStack).unsqueeze(0)  # [1,B,S,J,H,W]: stack s is compared with preds2[:, s]
+        loss, fin, _, _, _ = _DenseLossFn.apply(p5, t, coef, 0, 0.0, gate, False)
+        return loss, self.nStack * int(fin[3].item())
+
+
+def _score_mean(v, rows, cnt):
+    """mean over the rows with weight > 0 of a [B,S,J] score plane -> [S,J] (losses.py:196-203)."""
+    return (v * rows[:, None, None]).sum(0) / cnt
+
+
+class JointPseudoLoss3(nn.Module):
+    """utils/losses.py:169-210.  forward(preds, targets, sampleWeight) ->
+    (sum, num_pseudo, num_selected, joint_score_mean[J], scoreThr, scoreThr)."""
+
+    def __init__(self, nStack=1, scoreThr=0.5):
+        super().__init__()
+        self.nStack = nStack
+        self.scoreThr = scoreThr
+
+    def forward(self, preds, targets, sampleWeight):
+        p5 = _as5(preds, self.nStack)
+        B, S, J = p5.shape[:3]
+        targets = _tgt(targets)
+        t = targets if self.nStack == 1 else targets[:, :, -1]          # [M,B,J,H,W], losses.py:179
+        w = sampleWeight.detach().to(device=p5.device, dtype=torch.float32).reshape(B)
+        loss, fin, vp, vt, mask = _DenseLossFn.apply(p5, t, w.reshape(B, 1).expand(B, J), 1, float(self.scoreThr), None, True)
+        rows = (w > 0).to(torch.float32)
+        cnt = rows.sum()
+        host = torch.cat([fin, cnt.reshape(1).double()]).tolist()       # the one device->host sync
+        if host[4] == 0:
+            raise RuntimeError("stack expects a non-empty TensorList")  # losses.py:201 on an all-labeled batch
+        jsm = ((_score_mean(vp, rows, cnt) + _score_mean(vt, rows, cnt)) / 2).mean(0)
+        return loss, int(host[1]), int(host[2]), jsm, self.scoreThr, self.scoreThr
+
+
+class JointDistLoss_mt2(nn.Module):
+    """utils/losses.py:246-286.  forward(preds1, preds2, kpsGate=None, sampleWeight=None) ->
+    (sum, nStack*count, num_pseudo, num_selected, joint_score_mean[J])."""
+
+    def __init__(self, nStack=1, useKPsGate=False, useSampleWeight=False, scoreThr=0.5):
+        super().__init__()
+        self.nStack = nStack
+        self.useKPsGate = useKPsGate
+        self.useSampleWeight = useSampleWeight
+        self.scoreThr = scoreThr
+
+    def forward(self, preds1, preds2, kpsGate=None, sampleWeight=None):
+        p5 = _as5(preds1, self.nStack)
+        B, S, J = p5.shape[:3]
+        coef = _coef(B, J, p5.device, kpsGate, self.useKPsGate, sampleWeight, self.useSampleWeight)
+        gate = None if kpsGate is None else kpsGate.detach().to(device=p5.device, dtype=torch.float32).reshape(B, J)
+        t = _as5(_tgt(preds2), self.nStack).unsqueeze(0)
+        loss, fin, _, vt, mask = _DenseLossFn.apply(p5, t, coef, 2, float(self.scoreThr), gate, True)
+        w = sampleWeight.detach().to(device=p5.device, dtype=torch.float32).reshape(B)   # AttributeError on None, like :274
+        rows = (w > 0).to(torch.float32)
+        cnt = rows.sum()
+        host = torch.cat([fin, cnt.reshape(1).double()]).tolist()
+        if host[4] == 0:
+            raise RuntimeError("stack expects a non-empty TensorList")  # losses.py:279
+        jsm = _score_mean(vt, rows, cnt).mean(0)
+        return loss, self.nStack * int(host[3]), int(host[1]), int(host[2]), jsm

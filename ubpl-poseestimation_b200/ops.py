@@ -333,12 +333,18 @@ def gate_prepare(kps, gate_in, S, img_h, img_w, stride, sigma=3.0, loss_weight=1
     return gate_out, grad_scale, count
 
 
-def scale_inplace(x, scale):
-    """x *= scale, scale a float32 device scalar (no host sync)."""
+def scale(x, scale, out=None):
+    """out = x * scale with `scale` a float32 device scalar (no host sync); out=x scales in place."""
     _need_cuda(x, scale)
     assert x.is_contiguous() and x.dtype == _f32
-    _lib.call("ubpl_scale_inplace", x.data_ptr(), x.numel(), scale.data_ptr(), _stream())
-    return x
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.call("ubpl_scale", out.data_ptr(), x.data_ptr(), x.numel(), scale.data_ptr(), _stream())
+    return out
+
+
+def scale_inplace(x, s):
+    return scale(x, s, out=x)
 
 
 # -------------------------------------------------------------------------------------------------
