@@ -69,15 +69,20 @@ int ubpl_warp_materialize(const float* in, int64_t sN, int64_t sC, float* out, i
                           int N, int C, int H, int W, const float* theta, const uint8_t* flip,
                           void* stream);
 
+/* AugmentUtils.fliplr_back_tensor (utils/augment.py:247-252): out[r, x] = in[r, W-1-x] for `rows`
+ * contiguous rows of W floats. */
+int ubpl_mirror_w(const float* in, float* out, int64_t rows, int W, void* stream);
+
 /* ---- K2: per-joint uncertainty ----------------------------------------------------------------
  * View dispersion of one teacher: EvaluationUtils.uncertainty_fromDistance
- * (utils/evaluation.py:40-58) numerator.  preds [K, B, J, 2] float32 contiguous.
+ * (utils/evaluation.py:40-58) numerator.  preds [K, B, J, 2] float32 contiguous; mean_in [B,J,2]
+ * float32 = the caller's preds_mean, or NULL to use the float32 view mean.
  * out_mean [B,J,2] float32 (torch.mean over views), out_dist [B,J] float64 (mean distance to the
  * mean), out_unc32 [B,J] float32 (the same, as the float32 tensor the reference builds),
  * out_legal [B,J] uint8 (all views x>=0 and y>=0), max_bits: uint32 device scalar that receives
  * atomicMax of the float32 bits of out_unc32 (caller zeroes it).  sentinel_illegal != 0 stores
  * 999 in out_dist for items with an illegal view (the sentinel of utils/business.py:123). */
-int ubpl_view_dispersion(const float* preds, int K, int B, int J,
+int ubpl_view_dispersion(const float* preds, const float* mean_in, int K, int B, int J,
                          float* out_mean, double* out_dist, float* out_unc32, uint8_t* out_legal,
                          uint32_t* max_bits, int sentinel_illegal, void* stream);
 /* unc = unc32 / max, uncW = exp(-unc)  (utils/evaluation.py:56-57); n = B*J. */
@@ -95,6 +100,13 @@ int ubpl_assess_dual(const float* p1, const float* p2, const float* pmean,
                      double* legal, double* intDist1, double* intDist2, double* extDist,
                      double* w1, double* w2, double* coord, float* coord32, int32_t* zero_div,
                      void* stream);
+
+/* Prediction error and PCK flag against ground truth (BusinessUtils._check_predsQuality,
+ * utils/business.py:37-40; EvaluationUtils.acc_pck_pseudo(_norm), utils/evaluation.py:78-89) for
+ * n_sets prediction sets pred [n_sets,B,J,2] float64 against gt [B,J,gt_stride] float32 (x, y first):
+ * err = dist(pred, gt), acc = err / dist(gt[b,ref0], gt[b,ref1]) < pck_thr. */
+int ubpl_coord_error(const double* pred, const float* gt, int gt_stride, int64_t n_sets, int B, int J,
+                     int ref0, int ref1, double pck_thr, double* err, int32_t* acc, void* stream);
 
 /* ---- K2: pseudo-label selection ---------------------------------------------------------------
  * BusinessUtils.filter_pseudo2 (utils/business.py:173-217) / _calReliabilityThr (:43-46).
@@ -127,12 +139,13 @@ int ubpl_select_fixed(const double* dist, const double* legal, int64_t n, int J,
 
 /* Fused K2 of the mean-teacher fixed-threshold path, one launch: ubpl_view_dispersion (with the 999
  * sentinel) + ubpl_select_fixed + ubpl_gate_prepare.  preds [K,B,J,2]; outputs as in those three
- * (out_mean is the pseudo key point the targets are rendered at); any of out_mean, out_dist,
- * out_legal, enable, grad_scale, count_out may be NULL. */
+ * (out_mean is the pseudo key point the targets are rendered at); out_mean, out_dist, out_legal and
+ * enable may be NULL.  counts is int32[J+2]: per-joint and total selected, then count_out =
+ * &counts[J+1] = S * #(gate_out > 0), which ubpl_render_mse turns into the gradient scale. */
 int ubpl_k2_view_fixed(const float* preds, int K, int B, int J, double distThrMax, int img_h, int img_w,
-                       float stride, float sigma, int S, float loss_weight, float* out_mean,
-                       double* out_dist, uint8_t* out_legal, uint8_t* enable, float* gate_out,
-                       float* grad_scale, int32_t* count_out, int32_t* counts, void* stream);
+                       float stride, float sigma, int S, float* out_mean, double* out_dist,
+                       uint8_t* out_legal, uint8_t* enable, float* gate_out, int32_t* count_out,
+                       int32_t* counts, void* stream);
 
 /* ---- K3: Gaussian target render + masked joint-MSE, forward and gradient in one pass ----------
  * ProcessUtils.kps_heatmap (utils/process.py:253-278,394-397) fused into JointMSELoss
@@ -143,14 +156,17 @@ int ubpl_k2_view_fixed(const float* preds, int K, int B, int J, double distThrMa
  * img_h/img_w: input resolution (256); stride = inpRes/outRes; sigma = kernelSize*sigma (3).
  * gate_out [B,J] float32 = gate_in * visibility (process.py:267-268).
  * per_loss [B,S,J] float32 = mean_HW (p-t)^2 * gate_out * sample_w.
- * grad = grad_scale * 2/(HW) * gate_out * sample_w * (p - t); grad_scale is read from device
- * memory (NULL = 1) so the caller can fold weight/n (MT_UBPL.py:266) without a host sync. */
+ * grad = gs * 2/(HW) * gate_out * sample_w * (p - t) where gs is read from device memory so the
+ * caller can fold weight/n (MT_UBPL.py:266) without a host sync: gs = *grad_scale (NULL = 1), or,
+ * when count_in != NULL, gs = loss_weight / *count_in (loss_weight if the count is 0), which is
+ * also stored to *grad_scale_out. */
 int ubpl_render_mse(const float* kps, const float* gate_in, const float* sample_w,
                     const float* pred, int64_t pB, int64_t pS, int64_t pJ,
                     float* grad, int64_t gB, int64_t gS, int64_t gJ,
                     float* target, int B, int S, int J, int H, int W,
                     int img_h, int img_w, float stride, float sigma,
-                    const float* grad_scale, float* gate_out, float* per_loss, void* stream);
+                    const float* grad_scale, const int32_t* count_in, float loss_weight,
+                    float* grad_scale_out, float* gate_out, float* per_loss, void* stream);
 /* kps_heatmap alone (utils/process.py:253-278): kps [N,3] float32 (x,y,w) -> heatmap [N,H,W],
  * kps_out [N,3] with w *= visibility. */
 int ubpl_render_targets(const float* kps, int N, int H, int W, int img_h, int img_w, float stride,

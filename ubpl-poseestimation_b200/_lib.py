@@ -22,7 +22,9 @@ SIGNATURES = {
                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_warp_materialize": [c_void_p, c_i64, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p],
-    "ubpl_view_dispersion": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "ubpl_view_dispersion": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "ubpl_mirror_w": [c_void_p, c_void_p, c_i64, c_int, c_void_p],
+    "ubpl_coord_error": [c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p],
     "ubpl_unc_normalize": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p],
     "ubpl_assess_dual": [c_void_p] * 5 + [c_int, c_int, c_int] + [c_void_p] * 9 + [c_void_p],
     "ubpl_dist_extrema": [c_void_p, c_i64, c_void_p, c_void_p],
@@ -31,11 +33,11 @@ SIGNATURES = {
     "ubpl_select_descend": [c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "ubpl_select_apply": [c_void_p, c_i64, c_int, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_select_fixed": [c_void_p, c_void_p, c_i64, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
-    "ubpl_k2_view_fixed": [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_float, c_float, c_int, c_float,
-                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ubpl_k2_view_fixed": [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_float, c_float, c_int,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_render_mse": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_i64, c_i64, c_i64,
                         c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
-                        c_void_p, c_void_p, c_void_p, c_void_p],
+                        c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_render_targets": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p],
     "ubpl_dense_mse": [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_int, c_i64, c_i64, c_i64, c_i64, c_void_p, c_int, c_float,
                        c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p,

@@ -125,6 +125,25 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
   }
 }
 
+// n / d and n % d for 32-bit n with a host-computed magic pair: q = umulhi(n, mul) >> shr
+struct FastDiv {
+  unsigned mul, shr, d;
+  __host__ void init(unsigned div) {
+    d = div;
+    if (div == 1) { mul = 0; shr = 0; return; }
+    unsigned l = 0;
+    while ((1ull << l) < div) ++l;                       // l = ceil(log2 div)
+    const unsigned long long m = ((1ull << 32) * ((1ull << l) - div)) / div + 1;
+    mul = (unsigned)m; shr = l;
+  }
+  __device__ __forceinline__ unsigned div(unsigned n) const {
+    if (d == 1) return n;
+    const unsigned t = __umulhi(n, mul);
+    return (t + ((n - t) >> 1)) >> (shr - 1);
+  }
+  __device__ __forceinline__ void divmod(unsigned n, unsigned& q, unsigned& r) const { q = div(n); r = n - q * d; }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Gaussian target geometry shared by K2 (visibility gate) and K3 (render)
 // ---------------------------------------------------------------------------------------------

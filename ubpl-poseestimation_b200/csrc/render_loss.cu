@@ -80,14 +80,20 @@ __global__ void __launch_bounds__(256, 3) render_mse_kernel(
     const float* __restrict__ kps, const float* __restrict__ gate_in, const float* __restrict__ sample_w,
     const float* __restrict__ pred, long long pB, long long pS, long long pJ, float* __restrict__ grad, long long gB,
     long long gS, long long gJ, float* __restrict__ target, int B, int S, int J, int H, int W, int img_h, int img_w,
-    float stride, float sigma, const float* __restrict__ grad_scale, float* __restrict__ gate_out,
-    float* __restrict__ per_loss) {
+    float stride, float sigma, const float* __restrict__ grad_scale, const int32_t* __restrict__ count_in,
+    float loss_weight, float* __restrict__ grad_scale_out, float* __restrict__ gate_out,
+    float* __restrict__ per_loss, const FastDiv divW4) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   float* ex = sm + (size_t)warp * (W + H);   // [W]
   float* ey = ex + W;                        // [H]
   const int HW = H * W, nq = (HW + 3) >> 2;
-  const float gs = grad_scale ? *grad_scale : 1.f;
+  float gs = grad_scale ? *grad_scale : 1.f;
+  if (count_in) {                                    // weight / n, n = S * #(open gates)  (MT_UBPL.py:266)
+    const int cnt = *count_in;
+    gs = (cnt > 0) ? loss_weight / (float)cnt : loss_weight;
+    if (grad_scale_out && blockIdx.x == 0 && threadIdx.x == 0) *grad_scale_out = gs;
+  }
   const float inv_hw = 1.f / (float)HW;
   const long long BJ = (long long)B * J;
   constexpr int U = 8;
@@ -103,6 +109,10 @@ __global__ void __launch_bounds__(256, 3) render_mse_kernel(
     const float wb = sample_w ? sample_w[b] : 1.f;
     const float gcoef = gs * 2.f * inv_hw * gate * wb;
     if (lane == 0 && gate_out) gate_out[item] = gate;
+    // support box: exp(-r^2/2s^2) >= 0.01 needs r <= s*sqrt(2 ln 100) = 3.035 s; 3.05 s + 1 is a safe superset
+    const float rad = 3.05f * sigma + 1.f;
+    const int xlo = (int)floorf((float)g.cx - rad), xhi = (int)ceilf((float)g.cx + rad);
+    const int ylo = (int)floorf((float)g.cy - rad), yhi = (int)ceilf((float)g.cy + rad);
     for (int st = 0; st < S; ++st) {
       const float* p = pred + (long long)b * pB + (long long)st * pS + (long long)j * pJ;
       float* gr = grad ? grad + (long long)b * gB + (long long)st * gS + (long long)j * gJ : nullptr;
@@ -122,9 +132,16 @@ __global__ void __launch_bounds__(256, 3) render_mse_kernel(
           const int k = q << 2;
           float4 t;
           if (VEC) {                                    // W % 4 == 0: the four texels share a row
-            const int y = k / W, x = k - y * W;
-            t.x = gauss_px(ex, ey, x, y, g, sigma); t.y = gauss_px(ex, ey, x + 1, y, g, sigma);
-            t.z = gauss_px(ex, ey, x + 2, y, g, sigma); t.w = gauss_px(ex, ey, x + 3, y, g, sigma);
+            unsigned yu, xu;
+            divW4.divmod((unsigned)q, yu, xu);
+            const int y = (int)yu, x = (int)(xu << 2);
+            // outside the Gaussian's support box the target is exactly 0 (the 0.01 cut, process.py:275)
+            if (y < ylo || y > yhi || x + 3 < xlo || x > xhi) {
+              t = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+              t.x = gauss_px(ex, ey, x, y, g, sigma); t.y = gauss_px(ex, ey, x + 1, y, g, sigma);
+              t.z = gauss_px(ex, ey, x + 2, y, g, sigma); t.w = gauss_px(ex, ey, x + 3, y, g, sigma);
+            }
           } else {
             float tt[4];
 #pragma unroll
@@ -335,7 +352,8 @@ using namespace ubpl;
 extern "C" int ubpl_render_mse(const float* kps, const float* gate_in, const float* sample_w, const float* pred,
                                int64_t pB, int64_t pS, int64_t pJ, float* grad, int64_t gB, int64_t gS, int64_t gJ,
                                float* target, int B, int S, int J, int H, int W, int img_h, int img_w, float stride,
-                               float sigma, const float* grad_scale, float* gate_out, float* per_loss, void* stream) {
+                               float sigma, const float* grad_scale, const int32_t* count_in, float loss_weight,
+                               float* grad_scale_out, float* gate_out, float* per_loss, void* stream) {
   UBPL_REQUIRE(kps && pred, "ubpl_render_mse: NULL pointer");
   UBPL_REQUIRE(B >= 0 && S >= 1 && J >= 0 && H > 0 && W > 0 && stride > 0.f && sigma > 0.f, "ubpl_render_mse: bad arguments");
   const long long BJ = (long long)B * J;
@@ -344,6 +362,8 @@ extern "C" int ubpl_render_mse(const float* kps, const float* gate_in, const flo
   int vec = (W % 4 == 0) && aligned16(pred) && pB % 4 == 0 && pS % 4 == 0 && pJ % 4 == 0;
   if (grad) vec = vec && aligned16(grad) && gB % 4 == 0 && gS % 4 == 0 && gJ % 4 == 0;
   if (target) vec = vec && aligned16(target) && (HW % 4 == 0);
+  FastDiv divW4;
+  divW4.init((unsigned)(W >= 4 ? W / 4 : 1));
   const int wpb = 8;
   const size_t smem = (size_t)wpb * (W + H) * sizeof(float);
   UBPL_REQUIRE(smem <= 48 * 1024, "ubpl_render_mse: heat-map sides too large (%d x %d)", H, W);
@@ -353,11 +373,11 @@ extern "C" int ubpl_render_mse(const float* kps, const float* gate_in, const flo
   if (vec)
     render_mse_kernel<true><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS,
                                                                             gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma,
-                                                                            grad_scale, gate_out, per_loss);
+                                                                            grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4);
   else
     render_mse_kernel<false><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS,
                                                                              gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma,
-                                                                             grad_scale, gate_out, per_loss);
+                                                                             grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4);
   return check_launch("ubpl_render_mse");
 }
 

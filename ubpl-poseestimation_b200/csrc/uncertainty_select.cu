@@ -41,7 +41,8 @@ __device__ __forceinline__ double py_dist(double x1, double y1, double x2, doubl
   return d;
 }
 
-__global__ void view_dispersion_kernel(const float* __restrict__ preds, int K, long long BJ, float* out_mean,
+__global__ void view_dispersion_kernel(const float* __restrict__ preds, const float* __restrict__ mean_in, int K,
+                                       long long BJ, float* out_mean,
                                        double* out_dist, float* out_unc32, uint8_t* out_legal, uint32_t* max_bits,
                                        int sentinel_illegal, PowTab T) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,7 +56,8 @@ __global__ void view_dispersion_kernel(const float* __restrict__ preds, int K, l
       sy = __fadd_rn(sy, y);
       legal = legal && (x >= 0.f) && (y >= 0.f);
     }
-    const float mx = __fdiv_rn(sx, (float)K), my = __fdiv_rn(sy, (float)K);   // torch.mean (float32)
+    float mx = __fdiv_rn(sx, (float)K), my = __fdiv_rn(sy, (float)K);         // torch.mean (float32)
+    if (mean_in) { mx = mean_in[2 * i]; my = mean_in[2 * i + 1]; }            // caller-supplied preds_mean
     double acc = 0.0;
     for (int k = 0; k < K; ++k) {
       const double x = (double)preds[2 * ((long long)k * BJ + i)], y = (double)preds[2 * ((long long)k * BJ + i) + 1];
@@ -261,21 +263,18 @@ __global__ void select_fixed_kernel(const double* __restrict__ dist, const doubl
   }
 }
 
-// Fused K2 for the mean-teacher fixed-threshold path (one CTA, everything of K2 in one launch):
+// Fused K2 for the mean-teacher fixed-threshold path, one launch, one thread per (sample, joint):
 // dispersion (evaluation.py:44-54) -> unc = 1-exp(-d/5) <= 1-exp(-3*distThrMax/5) (business.py:237-261,
-// 375-376) -> gate = enable * visibility (process.py:262-268) -> count and grad_scale (MT_UBPL.py:266).
-__global__ void __launch_bounds__(1024) k2_view_fixed_kernel(const float* __restrict__ preds, int K, long long BJ, int J,
-                                                              double distThrMax, int img_h, int img_w, float stride,
-                                                              float sigma, int S, float loss_weight, float* out_mean,
-                                                              double* out_dist, uint8_t* out_legal, uint8_t* enable,
-                                                              float* gate_out, float* grad_scale, int32_t* count_out,
-                                                              int32_t* counts, PowTab T) {
-  __shared__ int red[32];
-  const double thr = __dsub_rn(1.0, exp(-__ddiv_rn(__dmul_rn(distThrMax, 3.0), 5.0)));
-  for (int jj = threadIdx.x; jj <= J; jj += blockDim.x) counts[jj] = 0;
-  __syncthreads();
-  int c = 0;
-  for (long long i = threadIdx.x; i < BJ; i += blockDim.x) {
+// 375-376) -> gate = enable * visibility (process.py:262-268) -> count += S per open gate (losses.py:29).
+__global__ void __launch_bounds__(128) k2_view_fixed_kernel(const float* __restrict__ preds, int K, long long BJ, int J,
+                                                             double distThrMax, int img_h, int img_w, float stride,
+                                                             float sigma, int S, float* out_mean, double* out_dist,
+                                                             uint8_t* out_legal, uint8_t* enable, float* gate_out,
+                                                             int32_t* count_out, int32_t* counts, PowTab T) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int open_gate = 0, sel = 0;
+  if (i < BJ) {
+    const double thr = __dsub_rn(1.0, exp(-__ddiv_rn(__dmul_rn(distThrMax, 3.0), 5.0)));
     float sx = preds[2 * i], sy = preds[2 * i + 1];
     bool legal = (sx >= 0.f) && (sy >= 0.f);
     for (int k = 1; k < K; ++k) {
@@ -300,18 +299,35 @@ __global__ void __launch_bounds__(1024) k2_view_fixed_kernel(const float* __rest
     if (out_legal) out_legal[i] = legal ? 1 : 0;
     if (enable) enable[i] = en ? 1 : 0;
     gate_out[i] = gt;
-    if (en) { atomicAdd(counts + (int)(i % J), 1); atomicAdd(counts + J, 1); }
-    c += (gt > 0.f) ? 1 : 0;
+    if (en) atomicAdd(counts + (int)(i % J), 1);
+    sel = en ? 1 : 0;
+    open_gate = (gt > 0.f) ? 1 : 0;
   }
-  c = __reduce_add_sync(0xffffffffu, c);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-    if (count_out) *count_out = S * t;
-    if (grad_scale) *grad_scale = (t > 0) ? loss_weight / (float)(S * t) : loss_weight;
+  open_gate = __reduce_add_sync(0xffffffffu, open_gate);
+  sel = __reduce_add_sync(0xffffffffu, sel);
+  if ((threadIdx.x & 31) == 0) {
+    if (open_gate) atomicAdd(count_out, S * open_gate);
+    if (sel) atomicAdd(counts + J, sel);
   }
+}
+
+// error / PCK flag of predictions against ground truth (business.py:37-40, evaluation.py:78-89):
+// error = dist(pred, gt); norm_b = dist(gt[b, ref0], gt[b, ref1]); acc = error / norm < pck_thr.
+__global__ void coord_error_kernel(const double* __restrict__ pred, const float* __restrict__ gt, int gt_stride,
+                                   long long n_sets, int B, int J, int ref0, int ref1, double pck_thr,
+                                   double* err, int32_t* acc, PowTab T) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long BJ = (long long)B * J;
+  if (i >= n_sets * BJ) return;
+  const long long bj = i % BJ;
+  const int b = (int)(bj / J);
+  const float* g = gt + bj * gt_stride;
+  const float* g0 = gt + ((long long)b * J + ref0) * gt_stride;
+  const float* g1 = gt + ((long long)b * J + ref1) * gt_stride;
+  const double e = py_dist(pred[2 * i], pred[2 * i + 1], (double)g[0], (double)g[1], T);
+  const double norm = py_dist((double)g0[0], (double)g0[1], (double)g1[0], (double)g1[1], T);
+  err[i] = e;
+  acc[i] = (__ddiv_rn(e, norm) < pck_thr) ? 1 : 0;
 }
 
 static inline int blocks_for(long long n, int t) { return (int)((n + t - 1) / t); }
@@ -327,14 +343,15 @@ using namespace ubpl;
     if (rc_ != UBPL_OK) return rc_;                                               \
   }
 
-extern "C" int ubpl_view_dispersion(const float* preds, int K, int B, int J, float* out_mean, double* out_dist,
+extern "C" int ubpl_view_dispersion(const float* preds, const float* mean_in, int K, int B, int J, float* out_mean,
+                                    double* out_dist,
                                     float* out_unc32, uint8_t* out_legal, uint32_t* max_bits, int sentinel_illegal,
                                     void* stream) {
   UBPL_REQUIRE(preds != nullptr && K >= 1 && B >= 0 && J >= 0, "ubpl_view_dispersion: bad arguments");
   const long long BJ = (long long)B * J;
   if (BJ == 0) return UBPL_OK;
   GET_POWTAB(T);
-  view_dispersion_kernel<<<blocks_for(BJ, 128), 128, 0, (cudaStream_t)stream>>>(preds, K, BJ, out_mean, out_dist,
+  view_dispersion_kernel<<<blocks_for(BJ, 128), 128, 0, (cudaStream_t)stream>>>(preds, mean_in, K, BJ, out_mean, out_dist,
                                                                                  out_unc32, out_legal, max_bits, sentinel_illegal, T);
   return check_launch("ubpl_view_dispersion");
 }
@@ -424,15 +441,31 @@ extern "C" int ubpl_select_fixed(const double* dist, const double* legal, int64_
 }
 
 extern "C" int ubpl_k2_view_fixed(const float* preds, int K, int B, int J, double distThrMax, int img_h, int img_w,
-                                  float stride, float sigma, int S, float loss_weight, float* out_mean,
-                                  double* out_dist, uint8_t* out_legal, uint8_t* enable, float* gate_out,
-                                  float* grad_scale, int32_t* count_out, int32_t* counts, void* stream) {
-  UBPL_REQUIRE(preds && gate_out && counts && K >= 1 && B >= 0 && J >= 1 && S >= 1 && stride > 0.f && sigma > 0.f,
+                                  float stride, float sigma, int S, float* out_mean, double* out_dist,
+                                  uint8_t* out_legal, uint8_t* enable, float* gate_out, int32_t* count_out,
+                                  int32_t* counts, void* stream) {
+  UBPL_REQUIRE(preds && gate_out && counts && count_out && K >= 1 && B >= 0 && J >= 1 && S >= 1 && stride > 0.f && sigma > 0.f,
                "ubpl_k2_view_fixed: bad arguments");
+  UBPL_REQUIRE(counts + J + 1 == count_out, "ubpl_k2_view_fixed: count_out must directly follow counts[J+1]");
+  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)(J + 2) * sizeof(int32_t), (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("ubpl_k2_view_fixed: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+  const long long BJ = (long long)B * J;
+  if (BJ == 0) return UBPL_OK;
   GET_POWTAB(T);
-  k2_view_fixed_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(preds, K, (long long)B * J, J, distThrMax, img_h, img_w,
-                                                             stride, sigma, S, loss_weight, out_mean, out_dist,
-                                                             out_legal, enable, gate_out, grad_scale, count_out,
-                                                             counts, T);
+  k2_view_fixed_kernel<<<blocks_for(BJ, 128), 128, 0, (cudaStream_t)stream>>>(preds, K, BJ, J, distThrMax, img_h, img_w,
+                                                                             stride, sigma, S, out_mean, out_dist, out_legal,
+                                                                             enable, gate_out, count_out, counts, T);
   return check_launch("ubpl_k2_view_fixed");
+}
+
+extern "C" int ubpl_coord_error(const double* pred, const float* gt, int gt_stride, int64_t n_sets, int B, int J,
+                                int ref0, int ref1, double pck_thr, double* err, int32_t* acc, void* stream) {
+  UBPL_REQUIRE(pred && gt && err && acc && gt_stride >= 2 && n_sets >= 0 && B >= 0 && J >= 1, "ubpl_coord_error: bad arguments");
+  UBPL_REQUIRE(ref0 >= 0 && ref0 < J && ref1 >= 0 && ref1 < J, "ubpl_coord_error: pck_ref out of range");
+  const long long n = n_sets * B * J;
+  if (n == 0) return UBPL_OK;
+  GET_POWTAB(T);
+  coord_error_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(pred, gt, gt_stride, n_sets, B, J, ref0, ref1,
+                                                                          pck_thr, err, acc, T);
+  return check_launch("ubpl_coord_error");
 }

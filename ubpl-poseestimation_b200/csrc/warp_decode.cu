@@ -27,12 +27,15 @@
 // Maps where this does not apply (max <= 0 after warp, NaN/Inf, singular theta, huge candidate
 // box) are decoded exhaustively by the same warp, so the result is exact in every case.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ubpl {
 
 unsigned long long* work_counter(cudaStream_t stream);   // api.cu: a zeroed device counter for this launch
 
 struct WDParams {
+  FastDiv divJ, divB, divW;
+  float stepx, stepy, sfx, sfy;
   const float* maps;
   long long sV, sB, sJ;
   int V, B, J, H, W;
@@ -94,16 +97,18 @@ __device__ __forceinline__ void load_xform(Xform& X, const float* theta, const u
   const float* t = theta + vb * 6;
   X.t00 = t[0]; X.t01 = t[1]; X.t02 = t[2]; X.t10 = t[3]; X.t11 = t[4]; X.t12 = t[5];
   X.H = H; X.W = W;
+  X.flip = flip ? (flip[vb] != 0) : false;
+}
+__device__ __forceinline__ void grid_consts(Xform& X, int H, int W) {
   X.stepx = (W > 1) ? __fdiv_rn(2.f, (float)(W - 1)) : 0.f;
   X.stepy = (H > 1) ? __fdiv_rn(2.f, (float)(H - 1)) : 0.f;
   X.sfx = (float)((double)(W - 1) / 2.0);
   X.sfy = (float)((double)(H - 1) / 2.0);
-  X.flip = flip ? (flip[vb] != 0) : false;
 }
 
 // Exhaustive decode of the warped map.  Each lane walks whole columns (the column terms of the
 // affine grid are hoisted), so the tie rule is carried by arg_better's index comparison.
-__device__ __noinline__ void decode_exhaustive(const float* s, const Xform& X, int lane, float& bv, int& bi) {
+__device__ __noinline__ void decode_exhaustive(const float* s, const Xform X, int lane, float& bv, int& bi) {
   bv = -INFINITY;
   bi = 0x7fffffff;
   const int W = X.W, H = X.H;
@@ -172,11 +177,10 @@ __device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float
 
 __device__ __forceinline__ void issue_map(const WDParams& p, long long n, float* dst, uint64_t* bar, uint64_t pol,
                                           uint32_t bytes) {
-  const int j = (int)(n % p.J);
-  const long long vb = n / p.J;
-  const int b = (int)(vb % p.B);
-  const long long v = vb / p.B;
-  const float* src = p.maps + v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
+  unsigned vb, j, v, b;
+  p.divJ.divmod((unsigned)n, vb, j);
+  p.divB.divmod(vb, v, b);
+  const float* src = p.maps + (long long)v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
   mbar_arrive_expect_tx(bar, bytes);
   bulk_g2s(dst, src, bytes, bar, pol);
 }
@@ -220,14 +224,15 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     const long long n = bsel ? nxt1 : nxt0;
     if (n >= N) break;
     float* s = buf0 + (size_t)bsel * (buf_stride >> 2);
-    const int j = (int)(n % p.J);
-    const long long vb = n / p.J;
-    const int b = (int)(vb % p.B);
+    unsigned vbu, ju, vu, bu;
+    p.divJ.divmod((unsigned)n, vbu, ju);
+    p.divB.divmod(vbu, vu, bu);
+    const int j = (int)ju, b = (int)bu;
+    const long long vb = (long long)vbu;
     if (p.use_bulk) {
       mbar_wait(&bars[bsel], (uint32_t)((it / NB) & 1));
     } else {
-      const long long v = vb / p.B;
-      const float* src = p.maps + v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
+      const float* src = p.maps + (long long)vu * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
       for (int k = lane; k < HW; k += 32) s[k] = __ldg(src + k);
       __syncwarp();
     }
@@ -236,6 +241,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     // ---- pass A: raw max / location / min / finiteness -----------------------------------------
     float bv, mn, fsum; int bq;
     scan_max(s, HW, lane, bv, bq, mn, fsum);
+    const float lane_max = bv;           // max over this lane's float4 residue class (pass B reuses it)
     int bi = 0x7fffffff;                  // flat index of the lane's first maximum
     if (bv > -INFINITY) {
       const float4 x = reinterpret_cast<const float4*>(s)[bq];
@@ -259,6 +265,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       X.H = H; X.W = W; X.flip = false;
     } else {
       load_xform(X, p.theta, p.flip, vb, H, W);
+      X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
       warp_argmax(bv, bi);                // warp-uniform source max / location
       mn = -warp_max(-mn);
       bool exhaustive = nonfinite;
@@ -274,7 +281,9 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       const float C00 = e * idet, C01 = -bb * idet, C10 = -d * idet, C11 = a * idet;
       if (!exhaustive) {
         // ---- phase L: lower bound from the pixels around the pre-image of the arg-max texel
-        const float sx = (float)(bi % W) - c0, sy = (float)(bi / W) - f0;
+        unsigned biy, bix;
+        p.divW.divmod((unsigned)bi, biy, bix);
+        const float sx = (float)bix - c0, sy = (float)biy - f0;
         const float oj = C00 * sx + C01 * sy, oi = C10 * sx + C11 * sy;
         if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 30) {
           const int jw = (int)floorf(oj) - 2 + (lane % 6);
@@ -294,23 +303,37 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
           int txmin = W, txmax = -1, tymin = H, tymax = -1;
           const int nq = HW >> 2;
           const float4* s4 = reinterpret_cast<const float4*>(s);
-#pragma unroll 4
-          for (int q = lane; q < nq; q += 32) {
-            const float4 x = s4[q];
+          auto visit = [&](const float4& x, int q) {
             if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= T) {
               const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 if (xs[c] >= T) {
-                  const int k = (q << 2) + c, ty = k / W, tx = k - ty * W;
-                  txmin = min(txmin, tx); txmax = max(txmax, tx); tymin = min(tymin, ty); tymax = max(tymax, ty);
+                  unsigned ty, tx;
+                  p.divW.divmod((unsigned)((q << 2) + c), ty, tx);
+                  txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
                 }
             }
+          };
+          // lane l scanned the float4s q = l (mod 32) in pass A and knows their maximum (lane_max):
+          // only the residue classes whose maximum reaches T can hold candidates.  All 32 lanes
+          // re-read one such class together (32 float4 per step).
+          unsigned hot = __ballot_sync(0xffffffffu, lane_max >= T);
+          if (__popc(hot) <= 12) {
+            while (hot) {
+              const int h = __ffs(hot) - 1;
+              hot &= hot - 1;
+              for (int q = h + 32 * lane; q < nq; q += 1024) visit(s4[q], q);
+            }
+          } else {
+#pragma unroll 4
+            for (int q = lane; q < nq; q += 32) visit(s4[q], q);
           }
           for (int k = (nq << 2) + lane; k < HW; k += 32)
             if (s[k] >= T) {
-              const int ty = k / W, tx = k - ty * W;
-              txmin = min(txmin, tx); txmax = max(txmax, tx); tymin = min(tymin, ty); tymax = max(tymax, ty);
+              unsigned ty, tx;
+              p.divW.divmod((unsigned)k, ty, tx);
+              txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
             }
           txmin = __reduce_min_sync(0xffffffffu, txmin); txmax = __reduce_max_sync(0xffffffffu, txmax);
           tymin = __reduce_min_sync(0xffffffffu, tymin); tymax = __reduce_max_sync(0xffffffffu, tymax);
@@ -331,8 +354,11 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
           } else {
             // ---- phase C: exact evaluation of every pixel that can touch a candidate ---------
             rv = L; ri = Li;
-            for (int t = lane; t < area; t += 32) {
-              const int i = imin + t / bw, jw = jmin + t % bw;
+            int ci = lane / bw, cj = lane - ci * bw;          // (row, col) of this lane's first pixel in the box
+            const int di = 32 / bw, dj = 32 - di * bw;
+            for (int t = lane; t < area; t += 32, ci += di, cj += dj) {
+              if (cj >= bw) { cj -= bw; ++ci; }
+              const int i = imin + ci, jw = jmin + cj;
               const float v = eval_px(s, X, i, jw);
               const int k = i * W + (X.flip ? (W - 1 - jw) : jw);
               if (arg_better(v, k, rv, ri)) { rv = v; ri = k; }
@@ -350,7 +376,9 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     }
 
     // ---- epilogue: coordinates -------------------------------------------------------------
-    const int ax = ri % W, ay = ri / W;                 // 0-based arg-max, canonical frame
+    unsigned ayu, axu;
+    p.divW.divmod((unsigned)ri & 0x7fffffffu, ayu, axu);
+    const int ax = (int)axu, ay = (int)ayu;             // 0-based arg-max, canonical frame
     float hx = 0.f, hy = 0.f;
     const bool keep = rv > 0.f;                          // maxval.gt(0): NaN -> masked
     if (keep) { hx = (float)(ax + 1); hy = (float)(ay + 1); }
@@ -422,11 +450,21 @@ __global__ void __launch_bounds__(256) warp_materialize_kernel(const float* __re
     __syncthreads();
     Xform X;
     load_xform(X, theta, flip, n, H, W);
+    grid_consts(X, H, W);
     for (int k = threadIdx.x; k < HW; k += blockDim.x) {
       const int i = k / W, jo = k - i * W;
       dst[k] = eval_px(sm, X, i, X.flip ? (W - 1 - jo) : jo);
     }
   }
+}
+
+// fliplr_back_tensor (utils/augment.py:247-252): exact mirror of the W axis, row per warp.
+__global__ void mirror_w_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int W) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* src = in + r * W;
+  float* dst = out + r * W;
+  for (int x = threadIdx.x & 31; x < W; x += 32) dst[x] = src[W - 1 - x];
 }
 
 }  // namespace ubpl
@@ -452,6 +490,12 @@ extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64
   WDParams p;
   p.maps = maps; p.sV = sV; p.sB = sB; p.sJ = sJ; p.V = V; p.B = B; p.J = J; p.H = H; p.W = W;
   p.theta = theta; p.flip = flip; p.dec = dec; p.do_warp = do_warp; p.refine = refine;
+  UBPL_REQUIRE(N < (1ll << 31), "ubpl_warp_decode: too many maps in one call (%lld)", N);
+  p.divJ.init((unsigned)J); p.divB.init((unsigned)B); p.divW.init((unsigned)W);
+  p.stepx = (W > 1) ? 2.f / (float)(W - 1) : 0.f;
+  p.stepy = (H > 1) ? 2.f / (float)(H - 1) : 0.f;
+  p.sfx = (float)((double)(W - 1) / 2.0);
+  p.sfy = (float)((double)(H - 1) / 2.0);
   p.out_idx = out_idx; p.out_max = out_max; p.out_xy = out_xy; p.out_hm_xy = out_hm_xy;
   p.stats = reinterpret_cast<unsigned long long*>(stats);
   // bulk async copy needs 16-byte aligned sources and sizes; otherwise the warp copies the map itself
@@ -459,7 +503,13 @@ extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64
                (sB % 4 == 0) && (sJ % 4 == 0);
   int total_bufs = (int)((size_t)smem_cap / (buf_stride + 8));
   int warps, nbuf;
-  if (total_bufs >= 8) { nbuf = 2; warps = total_bufs / 2; } else { nbuf = 1; warps = total_bufs; }
+  // tuning knobs (defaults chosen from B200 measurements): buffers per warp, warps per CTA
+  static const int env_nbuf = getenv("UBPL_K1_NBUF") ? atoi(getenv("UBPL_K1_NBUF")) : 0;
+  static const int env_warps = getenv("UBPL_K1_WARPS") ? atoi(getenv("UBPL_K1_WARPS")) : 0;
+  nbuf = (env_nbuf == 1 || env_nbuf == 2) ? env_nbuf : 1;
+  if (nbuf == 2 && total_bufs < 2) nbuf = 1;
+  warps = total_bufs / nbuf;
+  if (env_warps > 0 && env_warps < warps) warps = env_warps;
   if (warps > 16) warps = 16;
   if (warps < 1) warps = 1;
   p.nbuf = nbuf;
@@ -496,4 +546,12 @@ extern "C" int ubpl_warp_materialize(const float* in, int64_t sN, int64_t sC, fl
   int grid = (int)(maps < (long long)sm_count() * 8 ? maps : (long long)sm_count() * 8);
   warp_materialize_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, sN, sC, out, oN, oC, N, C, H, W, theta, flip);
   return check_launch("ubpl_warp_materialize");
+}
+
+extern "C" int ubpl_mirror_w(const float* in, float* out, int64_t rows, int W, void* stream) {
+  UBPL_REQUIRE(in && out && rows >= 0 && W > 0, "ubpl_mirror_w: bad arguments");
+  if (rows == 0) return UBPL_OK;
+  const int wpb = 8;
+  mirror_w_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(in, out, rows, W);
+  return check_launch("ubpl_mirror_w");
 }

@@ -101,10 +101,20 @@ def warp_materialize(heatmap, warpmat, isflip):
     return out
 
 
+def mirror_w(x):
+    """Exact mirror of the last axis (utils/augment.py:247-252)."""
+    _need_cuda(x)
+    x = x.to(_f32).contiguous()
+    out = torch.empty_like(x)
+    W = x.shape[-1]
+    _lib.call("ubpl_mirror_w", x.data_ptr(), out.data_ptr(), x.numel() // W, W, _stream())
+    return out
+
+
 # -------------------------------------------------------------------------------------------------
 # K2
 # -------------------------------------------------------------------------------------------------
-def view_dispersion(preds, sentinel_illegal=False):
+def view_dispersion(preds, sentinel_illegal=False, mean_in=None):
     """preds [K,B,J,2] float32 -> dict(mean [B,J,2] f32, dist [B,J] f64, unc32 [B,J] f32,
     legal [B,J] uint8, max_bits uint32 scalar)   (utils/evaluation.py:40-55)."""
     _need_cuda(preds)
@@ -116,7 +126,10 @@ def view_dispersion(preds, sentinel_illegal=False):
     unc32 = torch.empty(B, J, dtype=_f32, device=dev)
     legal = torch.empty(B, J, dtype=torch.uint8, device=dev)
     max_bits = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.call("ubpl_view_dispersion", preds.data_ptr(), K, B, J, mean.data_ptr(), dist.data_ptr(), unc32.data_ptr(),
+    if mean_in is not None:
+        _need_cuda(mean_in)
+        mean_in = mean_in.reshape(B, J, 2).to(_f32).contiguous()
+    _lib.call("ubpl_view_dispersion", preds.data_ptr(), _p(mean_in), K, B, J, mean.data_ptr(), dist.data_ptr(), unc32.data_ptr(),
               legal.data_ptr(), max_bits.data_ptr(), 1 if sentinel_illegal else 0, _stream())
     return dict(mean=mean, dist=dist, unc32=unc32, legal=legal, max_bits=max_bits)
 
@@ -149,6 +162,20 @@ def assess_dual(p1, p2, pmean, aug1, aug2):  # pmean None = bus.preds_mean(p1, p
               o["extDist"].data_ptr(), o["w1"].data_ptr(), o["w2"].data_ptr(), o["coord"].data_ptr(),
               o["coord32"].data_ptr(), o["zero_div"].data_ptr(), _stream())
     return o
+
+
+def coord_error(pred, gt, pck_ref, pck_thr):
+    """pred [n_sets,B,J,2] (any float dtype) vs gt [B,J,>=2] float32 -> (err float64, acc int32), both
+    [n_sets,B,J]  (utils/business.py:37-40, utils/evaluation.py:78-89)."""
+    _need_cuda(pred, gt)
+    pred = pred.to(_f64).contiguous()
+    gt = gt.to(_f32).contiguous()
+    n_sets, B, J, _ = pred.shape
+    err = torch.empty(n_sets, B, J, dtype=_f64, device=pred.device)
+    acc = torch.empty(n_sets, B, J, dtype=torch.int32, device=pred.device)
+    _lib.call("ubpl_coord_error", pred.data_ptr(), gt.data_ptr(), gt.shape[-1], n_sets, B, J, int(pck_ref[0]),
+              int(pck_ref[1]), float(pck_thr), err.data_ptr(), acc.data_ptr(), _stream())
+    return err, acc
 
 
 def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, group=None, n_total=None):
@@ -216,9 +243,9 @@ def select_fixed(dist, legal, J, distThrMax):
     return dict(enable=enable, gate=gate, counts=counts, unc=unc)
 
 
-def k2_view_fixed(preds, distThrMax, S, img_h, img_w, stride, sigma=3.0, loss_weight=1.0):
+def k2_view_fixed(preds, distThrMax, S, img_h, img_w, stride, sigma=3.0):
     """One-launch K2 for the mean-teacher fixed-threshold path: dispersion + fixed rule + visibility gate +
-    count/grad_scale.  preds [K,B,J,2].  Same outputs as view_dispersion + select_fixed + gate_prepare."""
+    open-gate count.  preds [K,B,J,2].  `count` (= S * #(gate > 0)) feeds render_mse(count_in=...)."""
     _need_cuda(preds)
     preds = preds.to(_f32).contiguous()
     K, B, J, _ = preds.shape
@@ -228,14 +255,12 @@ def k2_view_fixed(preds, distThrMax, S, img_h, img_w, stride, sigma=3.0, loss_we
     legal = torch.empty(B, J, dtype=torch.uint8, device=dev)
     enable = torch.empty(B, J, dtype=torch.uint8, device=dev)
     gate = torch.empty(B, J, dtype=_f32, device=dev)
-    grad_scale = torch.empty(1, dtype=_f32, device=dev)
-    count = torch.empty(1, dtype=torch.int32, device=dev)
-    counts = torch.empty(J + 1, dtype=torch.int32, device=dev)
+    counts = torch.empty(J + 2, dtype=torch.int32, device=dev)
+    count = counts[J + 1:]
     _lib.call("ubpl_k2_view_fixed", preds.data_ptr(), K, B, J, float(distThrMax), int(img_h), int(img_w), float(stride),
-              float(sigma), int(S), float(loss_weight), mean.data_ptr(), dist.data_ptr(), legal.data_ptr(),
-              enable.data_ptr(), gate.data_ptr(), grad_scale.data_ptr(), count.data_ptr(), counts.data_ptr(), _stream())
-    return dict(mean=mean, dist=dist, legal=legal, enable=enable, gate=gate, grad_scale=grad_scale, count=count,
-                counts=counts)
+              float(sigma), int(S), mean.data_ptr(), dist.data_ptr(), legal.data_ptr(), enable.data_ptr(),
+              gate.data_ptr(), count.data_ptr(), counts.data_ptr(), _stream())
+    return dict(mean=mean, dist=dist, legal=legal, enable=enable, gate=gate, count=count, counts=counts[:J + 1])
 
 
 # -------------------------------------------------------------------------------------------------
@@ -257,7 +282,7 @@ def render_targets(kps, H, W, img_h, img_w, stride=None, sigma=3.0):
 
 
 def render_mse(kps, gate, sample_w, pred, img_h, img_w, stride=None, sigma=3.0, grad_scale=None,
-               want_grad=True, want_target=True):
+               want_grad=True, want_target=True, count_in=None, loss_weight=1.0):
     """Fused Gaussian render + JointMSELoss forward + gradient (K3b).  kps [B,J,2] image space,
     gate [B,J] or None, sample_w [B] / [B,1] or None, pred [B,S,J,H,W].  Returns dict(per_loss
     [B,S,J], gate_out [B,J], grad, target)."""
@@ -274,12 +299,13 @@ def render_mse(kps, gate, sample_w, pred, img_h, img_w, stride=None, sigma=3.0, 
     target = torch.empty(B, J, H, W, dtype=_f32, device=dev) if want_target else None
     gate_out = torch.empty(B, J, dtype=_f32, device=dev)
     per_loss = torch.empty(B, S, J, dtype=_f32, device=dev)
+    gs_out = torch.empty(1, dtype=_f32, device=dev) if count_in is not None else None
     gs = (0, 0, 0) if grad is None else (grad.stride(0), grad.stride(1), grad.stride(2))
     _lib.call("ubpl_render_mse", kps.data_ptr(), _p(gate), _p(sample_w), pred.data_ptr(), pred.stride(0),
               pred.stride(1), pred.stride(2), _p(grad), gs[0], gs[1], gs[2], _p(target), B, S, J, H, W, int(img_h),
-              int(img_w), float(stride), float(sigma), _p(grad_scale), gate_out.data_ptr(), per_loss.data_ptr(),
-              _stream())
-    return dict(per_loss=per_loss, gate_out=gate_out, grad=grad, target=target)
+              int(img_w), float(stride), float(sigma), _p(grad_scale), _p(count_in), float(loss_weight), _p(gs_out),
+              gate_out.data_ptr(), per_loss.data_ptr(), _stream())
+    return dict(per_loss=per_loss, gate_out=gate_out, grad=grad, target=target, grad_scale=gs_out)
 
 
 def dense_mse(pred, tgt, coef=None, mask_mode=0, thr=0.0, grad_scale=None, want_grad=True, want_scores=False):

@@ -71,9 +71,9 @@ def pseudo_label_step(teacher, student, theta, flip, dec, sample_w, cfg: StepCon
     # ---- K2: dispersion + selection ----------------------------------------------------------------
     fused_k2 = (cfg.fuse_k2 and M == 1 and cfg.select == "fixed" and B * J <= 65536)
     if fused_k2:
-        k2 = ops.k2_view_fixed(xy[0], cfg.distThrMax, S, img_h, img_w, stride, cfg.sigma, cfg.lossWeight)
+        k2 = ops.k2_view_fixed(xy[0], cfg.distThrMax, S, img_h, img_w, stride, cfg.sigma)
         kps, dist, legal = k2["mean"], k2["dist"], k2["legal"]
-        gate, grad_scale, count = k2["gate"], k2["grad_scale"], k2["count"]
+        gate, grad_scale, count = k2["gate"], None, k2["count"]
         sel = dict(enable=k2["enable"], counts=k2["counts"])
         extra = {}
     else:
@@ -98,7 +98,10 @@ def pseudo_label_step(teacher, student, theta, flip, dec, sample_w, cfg: StepCon
         gate, grad_scale, count = ops.gate_prepare(kps, sel["gate"], S, img_h, img_w, stride, cfg.sigma, cfg.lossWeight)
     mark("k3_0")
     r = ops.render_mse(kps, gate, sample_w, student, img_h, img_w, stride, cfg.sigma, grad_scale=grad_scale,
-                       want_grad=cfg.want_grad, want_target=cfg.want_target)
+                       want_grad=cfg.want_grad, want_target=cfg.want_target,
+                       count_in=count if grad_scale is None else None, loss_weight=cfg.lossWeight)
+    if grad_scale is None:
+        grad_scale = r["grad_scale"]
     mark("k3_1")
     summary = ops.loss_finalize(r["per_loss"], None, gate.view(B, J))
     out = dict(summary=summary, grad_scale=grad_scale, count=count, grad=r["grad"], target=r["target"],
