@@ -134,6 +134,37 @@ def test_warp_decode_edge_cases(ops):
     assert np.array_equal(npy(r["xy"]), xy)
 
 
+def test_warp_decode_non_positive_maps(ops):
+    """All-negative / non-positive maps under many transforms: the maximum is 0 at the first pixel that
+    samples only padding, or a negative interior value when the frame stays inside the source."""
+    rng = np.random.default_rng(23)
+    V, B, J, H, W = 6, 8, 6, 64, 64
+    maps = -(np.abs(rng.standard_normal((V, B, J, H, W))) * 0.02 + 1e-3).astype(np.float32)
+    maps[:, :, 1] *= 50.0
+    maps[:, :, 2, 5:9, 7:11] = 0.0                         # maximum exactly 0 inside the map
+    maps[:, :, 3] = -1.0                                   # constant negative
+    maps[:, :, 4, 20, 20] = -1e-30                         # tiny magnitudes
+    maps[:, :, 5] = np.minimum(maps[:, :, 5], -0.5) + 0.4999
+    ang = rng.uniform(-0.8, 0.8, (V, B))
+    sc = rng.uniform(0.5, 1.7, (V, B))
+    th = np.zeros((V, B, 2, 3), np.float32)
+    th[..., 0, 0] = np.cos(ang) * sc; th[..., 0, 1] = np.sin(ang) * sc
+    th[..., 1, 0] = -np.sin(ang) * sc; th[..., 1, 1] = np.cos(ang) * sc
+    th[..., 2] = rng.uniform(-0.3, 0.3, (V, B, 2))
+    th[0, 0] = [[1, 0, 0], [0, 1, 0]]
+    th[0, 1] = [[1, 0, 2.0 / 63], [0, 1, 0]]                # shifted by exactly one texel: ix = W at the last column
+    th[0, 2] = [[1, 0, -2.0 / 63], [0, 1, -2.0 / 63]]       # ix = -1 exactly at column 0
+    th[0, 3] = [[0.5, 0, 0], [0, 0.5, 0]]                   # fully inside
+    fl = rng.integers(0, 2, (V, B)).astype(np.uint8)
+    idx, val, xy = _decode_oracle(maps, th, fl, np.full((B, 2), 128), np.full(B, 1.28, np.float32))
+    dec = ops.decode_coeffs(torch.full((B, 2), 128), torch.full((B,), 1.28), [H, W]).cuda()
+    stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    r = ops.warp_decode(cu(maps), cu(th), cu(fl), dec, stats=stats)
+    assert np.array_equal(npy(r["idx"]).astype(np.int64), idx)
+    assert np.array_equal(npy(r["max"]), val)
+    assert np.array_equal(npy(r["xy"]), xy)
+
+
 def test_warp_decode_strided_and_odd_shapes(ops):
     rng = np.random.default_rng(11)
     # the reference slices outs_ema[m, a, :, -1]: the S axis is skipped (SURVEY 3.5)

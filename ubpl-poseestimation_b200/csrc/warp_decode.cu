@@ -92,6 +92,17 @@ __device__ __forceinline__ float eval_px(const float* __restrict__ s, const Xfor
   return acc;
 }
 
+// The unnormalised source coordinates (ix, iy) of output pixel (row i, warped column jw), bit-identical
+// to the ones eval_px interpolates at.
+__device__ __forceinline__ void grid_px(const Xform& X, int i, int jw, float& ix, float& iy) {
+  const float xl = lin_coord(jw, X.W, X.stepx);
+  const float yl = lin_coord(i, X.H, X.stepy);
+  const float gx = __fadd_rn(__fmaf_rn(yl, X.t01, __fmul_rn(xl, X.t00)), X.t02);
+  const float gy = __fadd_rn(__fmaf_rn(yl, X.t11, __fmul_rn(xl, X.t10)), X.t12);
+  ix = __fmul_rn(__fadd_rn(gx, 1.f), X.sfx);
+  iy = __fmul_rn(__fadd_rn(gy, 1.f), X.sfy);
+}
+
 __device__ __forceinline__ void load_xform(Xform& X, const float* theta, const uint8_t* flip, long long vb, int H,
                                            int W) {
   const float* t = theta + vb * 6;
@@ -145,33 +156,42 @@ __device__ __noinline__ void decode_exhaustive(const float* s, const Xform X, in
   warp_argmax(bv, bi);
 }
 
-// Pass A over the staged map at float4 granularity: per-lane max (value, first float4 index),
-// min, and a running sum that turns non-finite if any texel is NaN/Inf.
-__device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float& bv, int& bq, float& mn,
-                                         float& fsum) {
-  bv = -INFINITY; bq = 0; mn = INFINITY; fsum = 0.f;
+// 3-input float min that PROPAGATES NaN (SASS FMNMX3.NAN): the running minimum turns NaN if any texel
+// is NaN and -inf if any is -inf, which is how pass A detects non-finite maps for free.
+__device__ __forceinline__ float min3_nan(float a, float b, float c) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// Pass A over the staged map at float4 granularity: per-lane max (value, first float4 index) and a
+// NaN-propagating running min.
+__device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float& bv, int& bq, float& mn) {
+  bv = -INFINITY; bq = 0; mn = INFINITY;
   const int nq = HW >> 2;
   const float4* s4 = reinterpret_cast<const float4*>(s);
   int q = lane;
-  for (; q + 96 < nq; q += 128) {
-    float4 x[4];
+  for (; q + 224 < nq; q += 256) {
+    float4 x[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) x[u] = s4[q + 32 * u];
+    for (int u = 0; u < 8; ++u) x[u] = s4[q + 32 * u];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float m4 = fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w));
-      const float n4 = fminf(fminf(x[u].x, x[u].y), fminf(x[u].z, x[u].w));
-      fsum += (x[u].x + x[u].y) + (x[u].z + x[u].w);
+    for (int u = 0; u < 8; ++u) {
+      const float m4 = fmaxf(max3(x[u].x, x[u].y, x[u].z), x[u].w);
+      mn = min3_nan(x[u].z, x[u].w, min3_nan(x[u].x, x[u].y, mn));
       if (m4 > bv) { bv = m4; bq = q + 32 * u; }
-      mn = fminf(mn, n4);
     }
   }
   for (; q < nq; q += 32) {
     const float4 x = s4[q];
-    const float m4 = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
-    fsum += (x.x + x.y) + (x.z + x.w);
+    const float m4 = fmaxf(max3(x.x, x.y, x.z), x.w);
+    mn = min3_nan(x.z, x.w, min3_nan(x.x, x.y, mn));
     if (m4 > bv) { bv = m4; bq = q; }
-    mn = fminf(mn, fminf(fminf(x.x, x.y), fminf(x.z, x.w)));
   }
 }
 
@@ -239,8 +259,8 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     ++n_maps;
 
     // ---- pass A: raw max / location / min / finiteness -----------------------------------------
-    float bv, mn, fsum; int bq;
-    scan_max(s, HW, lane, bv, bq, mn, fsum);
+    float bv, mn; int bq;
+    scan_max(s, HW, lane, bv, bq, mn);
     const float lane_max = bv;           // max over this lane's float4 residue class (pass B reuses it)
     int bi = 0x7fffffff;                  // flat index of the lane's first maximum
     if (bv > -INFINITY) {
@@ -249,11 +269,11 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     }
     for (int k = ((HW >> 2) << 2) + lane; k < HW; k += 32) {   // tail when H*W % 4 != 0
       const float x = s[k];
-      fsum += x;
       if (x > bv) { bv = x; bi = k; }
-      mn = fminf(mn, x);
+      mn = min3_nan(x, x, mn);
     }
-    const bool nonfinite = __any_sync(0xffffffffu, !(fabsf(fsum) <= FLT_MAX));
+    // NaN -> mn is NaN; -inf -> mn == -inf; +inf -> bv == +inf
+    const bool nonfinite = __any_sync(0xffffffffu, !(mn >= -FLT_MAX) || !(bv <= FLT_MAX));
     float rv = bv; int ri = bi;           // result (value, canonical flat index)
     Xform X;
     if (!p.do_warp) {
@@ -267,7 +287,6 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       load_xform(X, p.theta, p.flip, vb, H, W);
       X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
       warp_argmax(bv, bi);                // warp-uniform source max / location
-      mn = -warp_max(-mn);
       bool exhaustive = nonfinite;
       // pixel-space affine  ix = a*jw + bb*i + c0 ; iy = d*jw + e*i + f0  (approximate, for boxes only)
       const float a = X.t00 * X.stepx * X.sfx, bb = X.t01 * X.stepy * X.sfx;
@@ -295,10 +314,54 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
         }
         n_eval += 30;
         warp_argmax(L, Li);
-        const float amax = fmaxf(bv, -mn);
-        const float T = L - (L + amax) * 1.9073486328125e-06f;   // 2^-19
-        if (!(L > 0.f) || !(T > 0.f)) exhaustive = true;
-        if (!exhaustive) {
+        // Candidate threshold.  For a pixel whose four (zero-extended) corners are all < T the computed
+        // sample is < L: the rounding of the 4-term fma chain is at most 4 ulp of sum(w|v|), and negative
+        // corners lower the exact value by more than the rounding they add, so 2^-19 relative slack covers it.
+        const float T = L - fabsf(L) * 1.9073486328125e-06f;   // 2^-19
+        bool prune = (L > 0.f) && (T > 0.f);     // zero padding cannot be a candidate when T > 0
+        bool solved = false;
+        if (!prune) {
+          // The warped maximum is not known to be positive (e.g. an all-negative map).  Along a row the
+          // computed ix and iy are monotone in the column (every rounding step is monotone), so the row
+          // ends classify the whole frame:
+          //   inside : every pixel samples with all four corners in bounds -> the convex bound holds
+          //            for any sign and the pruned search stays valid;
+          //   Z      : pixels with ix <= -1 | ix >= W | iy <= -1 | iy >= H read nothing but padding
+          //            (value exactly 0); every other pixel of an all-negative map is < 0, so the
+          //            maximum is 0 at the first Z pixel in canonical order.
+          bool inside = true;
+          int zrow = 0x7fffffff;
+          for (int i = lane; i < H; i += 32) {
+#pragma unroll
+            for (int endc = 0; endc < 2; ++endc) {
+              float ix, iy;
+              grid_px(X, i, endc ? W - 1 : 0, ix, iy);
+              inside = inside && (ix >= 0.f) && (ix <= (float)(W - 1)) && (iy >= 0.f) && (iy <= (float)(H - 1));
+              const bool z = (ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H);
+              if (z) zrow = min(zrow, i);
+            }
+          }
+          inside = __all_sync(0xffffffffu, inside);
+          zrow = __reduce_min_sync(0xffffffffu, zrow);
+          if (inside && L > -INFINITY) {
+            prune = true;
+          } else if (bv < 0.f && bv < -1e-20f && zrow < H) {
+            int zcol = 0x7fffffff;
+            for (int jo = lane; jo < W; jo += 32) {
+              float ix, iy;
+              grid_px(X, zrow, X.flip ? (W - 1 - jo) : jo, ix, iy);
+              if ((ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H)) zcol = min(zcol, jo);
+            }
+            zcol = __reduce_min_sync(0xffffffffu, zcol);
+            rv = eval_px(s, X, zrow, X.flip ? (W - 1 - zcol) : zcol);   // +-0, exactly what the warp produces there
+            ri = zrow * W + zcol;
+            solved = true;
+            n_eval += 2 * H + W;
+          } else {
+            exhaustive = true;
+          }
+        }
+        if (prune && !solved) {
           // ---- pass B: bounding box of the candidate texels (v >= T) -----------------------
           int txmin = W, txmax = -1, tymin = H, tymax = -1;
           const int nq = HW >> 2;
