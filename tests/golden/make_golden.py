@@ -174,7 +174,34 @@ def ema_fixture():
     save("ema", **out)
 
 
+def business_fixture():
+    """assess_pseudo_unc2 + filter_pseudo2 records (utils/business.py:109-217) as JSON."""
+    import json
+    d = synth.make_batch(B=5, K=3, J=4, H=32, W=32, M=2, S=1, seed=31, jitter=0.7)
+    t = d["teacher"]
+    M, K, B, J = t.shape[:4]
+    dec = []
+    for m in range(M):
+        back = torch.stack([ref.aug.affine_back2(t[m, v], d["theta"][v], d["flip"][v]) for v in range(K)])
+        dec.append(ref.proc.kps_fromHeatmap_mul(back, d["center"], d["scale"], [32, 32]))
+    pm1, pm2 = dec[0][0], dec[1][0]
+    p1, p2 = dec[0][1].round(), dec[1][1].round()
+    pmean = ref.bus.preds_mean(p1, p2)
+    ids = ["img_%d" % b for b in range(B)]
+    gt = torch.cat([d["base_xy"] * 4 + 1, torch.ones(B, J, 1)], -1)
+    args = types.SimpleNamespace(pck_ref=[0, 1], pck_thr=0.5, br_inferAugNum=K, reliableThr=0.0, reliablePCT=0.5,
+                                 reliableDistMin=1.0, kpsCount=J)
+    pseudo, ori_a, aug_a = ref.bus.assess_pseudo_unc2(ids, gt, [p1, p2, pmean], [list(pm1), list(pm2)], args)
+    sel, cnt, errs, accs, thr = ref.bus.filter_pseudo2(copy.deepcopy(pseudo), args)
+    out = dict(ids=ids, gt=gt.tolist(), p1=p1.tolist(), p2=p2.tolist(), pmean=pmean.tolist(), pm1=pm1.tolist(),
+               pm2=pm2.tolist(), args=vars(args), pseudo=pseudo, ori_assess=ori_a, aug_assess=aug_a, sel=sel,
+               counts=cnt, errs=[float(e) for e in errs], accs=[float(a) for a in accs], thr=thr)
+    json.dump(out, open(os.path.join(HERE, "business.json"), "w"))
+    print("business", len(pseudo), "records", sum(cnt[:-1]), "selected")
+
+
 if __name__ == "__main__":
+    business_fixture()
     chain_fixture("chain_mt", B=2, K=3, J=3, H=64, W=64, M=1, seed=1388)
     chain_fixture("chain_dual", B=4, K=4, J=5, H=32, W=32, M=2, seed=1389)
     decode_fixture()

@@ -1,0 +1,201 @@
+"""The reference-facing Python surface (same names/signatures as utils/losses.py, utils/augment.py,
+utils/process.py, utils/evaluation.py, utils/business.py, utils/parameters.py) on the GPU, against
+the golden vectors produced by the unmodified reference.  These tests read like the reference's
+call sites: CPU tensors in / CPU tensors out where the drivers do that, python-int counts, tuple
+returns, the same exceptions."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import ubpl_oracle as O
+from golden_util import GOLDEN, load
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ubpl_b200
+    from ubpl_b200 import augment, business, evaluation, losses, parameters, process
+    return types.SimpleNamespace(aug=augment.AugmentUtils, bus=business.BusinessUtils, eval=evaluation.EvaluationUtils,
+                                 losses=losses, parameters=parameters, proc=process.ProcessUtils)
+
+
+def T(x):
+    return torch.as_tensor(np.ascontiguousarray(x))
+
+
+def test_losses_modules(pkg):
+    g = load("losses")
+    p = T(g["student"]).cuda().requires_grad_(True)
+    crit = pkg.losses.JointPseudoLoss3(nStack=2, scoreThr=0.8).cuda()
+    loss, n_p, n_s, jsm, t1, t2 = crit(p, T(g["targets"]).cuda(), T(g["nega"]).cuda())
+    assert isinstance(n_p, int) and isinstance(n_s, int) and (t1, t2) == (0.8, 0.8)
+    assert (n_p, n_s) == (int(g["p3_num_pseudo"]), int(g["p3_num_selected"]))
+    np.testing.assert_allclose(loss.item(), float(g["p3_loss"]), rtol=RTOL)
+    np.testing.assert_allclose(jsm.cpu().numpy(), g["p3_jsm"], rtol=RTOL)
+    (0.37 * loss / max(n_p, 1)).backward(retain_graph=True)                 # the drivers scale and divide, MT_UBPL.py:287
+    np.testing.assert_allclose(p.grad.cpu().numpy(), 0.37 / max(n_p, 1) * g["p3_grad"], rtol=RTOL, atol=1e-10)
+    p.grad = None
+    loss.backward()                                                          # second backward through the same node
+    np.testing.assert_allclose(p.grad.cpu().numpy(), g["p3_grad"], rtol=RTOL, atol=1e-10)
+    with pytest.raises(RuntimeError):                                        # losses.py:201 on an all-labeled batch
+        crit(p, T(g["targets"]).cuda(), torch.zeros(p.shape[0], 1, device="cuda"))
+
+    p1 = T(g["mt2_p"]).cuda().requires_grad_(True)
+    crit2 = pkg.losses.JointDistLoss_mt2(nStack=1, useKPsGate=False, useSampleWeight=True, scoreThr=0.8)
+    loss, n, n_p, n_s, jsm = crit2(p1, T(g["mt2_q"]).cuda(), sampleWeight=T(g["mt2_w"]).cuda())
+    assert (n, n_p, n_s) == (int(g["mt2_count"]), int(g["mt2_num_pseudo"]), int(g["mt2_num_selected"]))
+    np.testing.assert_allclose(loss.item(), float(g["mt2_loss"]), rtol=RTOL)
+    np.testing.assert_allclose(jsm.cpu().numpy(), g["mt2_jsm"], rtol=RTOL)
+    loss.backward()
+    np.testing.assert_allclose(p1.grad.cpu().numpy(), g["mt2_grad"], rtol=RTOL, atol=1e-10)
+
+    p2 = T(g["mt2_p"]).cuda().requires_grad_(True)
+    loss, n = pkg.losses.JointDistLoss()(p2, T(g["mt2_q"]).cuda())          # MT_UBPL.py:251
+    assert n == int(g["dist_count"])
+    np.testing.assert_allclose(loss.item(), float(g["dist_loss"]), rtol=RTOL)
+    loss.backward()
+    np.testing.assert_allclose(p2.grad.cpu().numpy(), g["dist_grad"], rtol=RTOL, atol=1e-10)
+
+    c = load("chain_mt")
+    ps = T(c["student"]).cuda().requires_grad_(True)
+    gts = torch.autograd.Variable(T(c["target"]).cuda(), requires_grad=True)   # tools.py:57-62 wraps targets like this
+    crit3 = pkg.losses.JointMSELoss(nStack=2, useKPsGate=True, useSampleWeight=True)
+    loss, n = crit3(ps, gts, T(c["gate"]).cuda(), T(c["weight"]).cuda())
+    assert n == int(c["mse_count"]) and isinstance(n, int)
+    np.testing.assert_allclose(loss.item(), float(c["mse_loss"]), rtol=RTOL)
+    loss.backward()
+    np.testing.assert_allclose(ps.grad.cpu().numpy(), c["mse_grad"], rtol=RTOL, atol=1e-10)
+    # a strided prediction view, as the drivers pass outs[m, a, :, -1] (MT_UBPL.py:251)
+    full = torch.randn(4, 3, 3, 32, 32, device="cuda", requires_grad=True)
+    tgt = torch.randn(4, 3, 32, 32, device="cuda")
+    loss, n = pkg.losses.JointDistLoss()(full[:, -1], tgt)
+    want, n_o, g_o = O.joint_mse(full[:, -1].detach().cpu().numpy(), tgt.cpu().numpy())
+    np.testing.assert_allclose(loss.item(), want, rtol=RTOL)
+    loss.backward()
+    np.testing.assert_allclose(full.grad[:, -1].cpu().numpy(), g_o, rtol=RTOL, atol=1e-10)
+    assert float(full.grad[:, 0].abs().sum()) == 0.0
+
+
+def test_augment(pkg):
+    g = load("chain_mt")
+    for v in range(g["teacher"].shape[1]):
+        out = pkg.aug.affine_back2(T(g["teacher"][0, v]), T(g["theta"][v]), T(g["flip"][v]))     # CPU in -> CPU out
+        assert out.device.type == "cpu" and np.array_equal(out.numpy(), g["back"][0, v])
+        out = pkg.aug.affine_back2(T(g["teacher"][0, v]).cuda(), T(g["theta"][v]).cuda(), T(g["flip"][v]).cuda())
+        assert out.is_cuda and np.array_equal(out.cpu().numpy(), g["back"][0, v])
+    x = torch.randn(2, 3, 5, 7)
+    assert torch.equal(pkg.aug.fliplr_back_tensor(x), x.flip(-1))
+    assert torch.equal(pkg.aug.fliplr_back_tensor(x[0].cuda()).cpu(), x[0].flip(-1))
+    for ang, sc in [(-20.0, 1 / 1.1), (13.7, 0.8), (0.0, 1.0), (30.0, 1 / 1.6)]:
+        assert np.array_equal(pkg.aug.affine_getWarpmat(ang, sc, [256, 256]).numpy(), O.affine_getWarpmat(ang, sc))
+
+
+def test_process(pkg):
+    g = load("decode")
+    for k in ("f32_128", "int_one", "f32_rand", "f64_rand"):
+        p, s = pkg.proc.kps_fromHeatmap(T(g["hm"]), T(g[k + "_center"]), T(g[k + "_scale"]), [64, 64])   # .cpu() call site
+        assert p.device.type == "cpu" and np.array_equal(p.numpy(), g[k + "_preds"]), k
+        assert np.array_equal(s.numpy(), g[k + "_scores"], equal_nan=True), k
+    one = pkg.proc.kps_fromHeatmap(T(g["hm"][1]), T(g["f32_128_center"][1]), T(g["f32_128_scale"][1]), [64, 64], mode="single")
+    assert np.array_equal(one.numpy(), g["f32_128_preds"][1])
+    q = pkg.proc.kps_fromHeatmap2(T(g["q_hm"]), torch.tensor([128, 128]), torch.tensor(1.28), [64, 64])
+    assert np.array_equal(q.numpy(), g["q_preds"])
+    c = load("chain_mt")
+    pm, pbar, sm, sbar = pkg.proc.kps_fromHeatmap_mul(T(c["back"][0]), T(c["center"]), T(c["scale"]), [64, 64])
+    assert np.array_equal(pm.numpy(), c["preds_multi"][0]) and np.array_equal(pbar.numpy(), c["preds_mean"][0])
+    assert np.array_equal(sm.numpy(), c["scores_multi"][0])
+    np.testing.assert_allclose(sbar.numpy(), c["scores_mean"][0], rtol=1e-6)
+    r = load("render")
+    kps = T(r["kps"]).clone()
+    hm, k2 = pkg.proc.kps_heatmap(kps, (3, 256, 256), 256, 64)
+    assert k2 is kps and np.array_equal(kps.numpy(), r["kps_out"])           # mutates its input like process.py:268
+    assert np.array_equal(hm.numpy() == 0, r["heatmap"] == 0)
+    np.testing.assert_allclose(hm.numpy(), r["heatmap"], rtol=RTOL)
+    assert pkg.proc.kps_getLabeledCount(torch.tensor([[1.0, 0.0], [0.5, -1.0]])) == 2
+    assert pkg.proc.coord_distance([0.0, 0.0], [3.0, 4.0]) == 5.0
+    with pytest.raises(ZeroDivisionError):
+        pkg.proc.coord_avgDistance([[1.0, 2.0]])
+
+
+def test_evaluation(pkg):
+    c = load("chain_mt")
+    unc, uncW = pkg.eval.uncertainty_fromDistance(T(c["preds_multi"][0]), T(c["preds_mean"][0]))
+    np.testing.assert_allclose(unc.numpy(), c["unc"], rtol=1e-6)
+    np.testing.assert_allclose(uncW.numpy(), c["uncW"], rtol=1e-6)
+
+
+def test_business(pkg):
+    g = json.load(open(os.path.join(GOLDEN, "business.json")))
+    args = types.SimpleNamespace(**g["args"])
+    f = lambda k: torch.tensor(g[k], dtype=torch.float32)
+    pseudo, ori_a, aug_a = pkg.bus.assess_pseudo_unc2(g["ids"], f("gt"), [f("p1"), f("p2"), f("pmean")],
+                                                      [list(f("pm1")), list(f("pm2"))], args)
+    exact = ("kpID", "imageID", "kIdx", "coord", "coord_gt", "coord_legal", "acc_flag", "coord_w1", "coord_w2",
+             "intDist1", "intDist2", "extDist")
+    assert len(pseudo) == len(g["pseudo"])
+    for got, want in zip(pseudo, g["pseudo"]):
+        for k in exact:
+            assert got[k] == want[k], (want["kpID"], k, got[k], want[k])     # float64 fields bit-exact
+        np.testing.assert_allclose(got["error"], want["error"], rtol=1e-12)
+    for got_set, want_set in zip(ori_a + [x for a in aug_a for x in a], g["ori_assess"] + [x for a in g["aug_assess"] for x in a]):
+        for got, want in zip(got_set, want_set):
+            assert got["coord"] == want["coord"] and got["coord_legal"] == want["coord_legal"]
+            assert got["acc_flag"] == want["acc_flag"]
+            np.testing.assert_allclose(got["error"], want["error"], rtol=1e-12)
+    sel, cnt, errs, accs, thr = pkg.bus.filter_pseudo2(pseudo, args)
+    assert thr == g["thr"] and cnt == g["counts"]
+    assert [it["kpID"] for it in sel] == [it["kpID"] for it in g["sel"]]      # same (stable) order
+    assert [it["enable"] for it in sel] == [it["enable"] for it in g["sel"]]   # masks bit-exact
+    assert [it["reliability"] for it in sel] == [it["reliability"] for it in g["sel"]]
+    np.testing.assert_allclose(errs, g["errs"], rtol=1e-12)
+    np.testing.assert_allclose(accs, g["accs"], rtol=1e-12)
+    with pytest.raises(IndexError):
+        pkg.bus.filter_pseudo2([], args)
+
+
+def test_update_ema_variables(pkg):
+    torch.manual_seed(0)
+    a = torch.nn.Sequential(torch.nn.Conv2d(3, 7, 3), torch.nn.BatchNorm2d(7), torch.nn.Linear(5, 9)).cuda()
+    b = torch.nn.Sequential(torch.nn.Conv2d(3, 7, 3), torch.nn.BatchNorm2d(7), torch.nn.Linear(5, 9)).cuda()
+    for p in b.parameters():
+        p.detach_()                                                           # models_ema are built with nograd
+    for epo in (0, 3, 2000):
+        before = [p.detach().cpu().numpy().copy() for p in b.parameters()]
+        bufs = [x.clone() for x in b.buffers()]
+        pkg.parameters.update_ema_variables(a, b, types.SimpleNamespace(epo=epo, ema_decay=0.999))
+        alpha = O.ema_alpha(epo, 0.999)
+        for e0, p, e1 in zip(before, a.parameters(), b.parameters()):
+            assert np.array_equal(O.ema_update(e0, p.detach().cpu().numpy(), alpha), e1.detach().cpu().numpy())
+        for x, y in zip(bufs, b.buffers()):
+            assert torch.equal(x, y)                                          # BN buffers are NOT averaged (parameters.py:7)
+    pkg.parameters.update_ema_variables(a, b, 0.99, 10)                       # utils_mt.py:34-39 signature
+
+
+def test_install_patches_a_module_tree(pkg, monkeypatch):
+    """install() rebinds attributes of the reference's modules; exercised on a stand-in tree because the
+    reference itself is not mounted on the GPU box."""
+    import sys
+    names = ["utils", "utils.losses", "utils.augment", "utils.process", "utils.evaluation", "utils.business",
+             "utils.parameters", "utils.udaap", "utils.udaap.utils_mt"]
+    for n in names:
+        monkeypatch.setitem(sys.modules, n, types.ModuleType(n))
+    sys.modules["utils.augment"].AugmentUtils = type("AugmentUtils", (), {})
+    sys.modules["utils.process"].ProcessUtils = type("ProcessUtils", (), {})
+    sys.modules["utils.evaluation"].EvaluationUtils = type("EvaluationUtils", (), {})
+    sys.modules["utils.business"].BusinessUtils = type("BusinessUtils", (), {})
+    from ubpl_b200 import install
+    done = install.install()
+    assert sys.modules["utils.losses"].JointPseudoLoss3 is pkg.losses.JointPseudoLoss3
+    assert "utils.parameters.update_ema_variables" in done
+    x = torch.randn(2, 3, 8, 8)
+    out = sys.modules["utils.augment"].AugmentUtils.fliplr_back_tensor(x)
+    assert torch.equal(out, x.flip(-1))

@@ -60,11 +60,12 @@ static double (*volatile g_pow)(double, double) = pow;   // volatile: no folding
 static std::vector<int32_t> g_exc_key;
 static std::vector<double> g_exc_val;
 static int32_t* d_exc_key = nullptr;
+static uint32_t* d_exc_bits = nullptr;   // bitmap over radicands: 1 = pow(v,0.5) != sqrt(v)
 static double* d_exc_val = nullptr;
 static int g_exc_n = 0, g_exc_dev = -1;
 static const int kPowTableMax = 1 << 21;   // radicands up to 2*1024^2: coordinates up to +-1024 px
 
-int pow_table(const int32_t** keys, const double** vals, int* n, int* rmax) {
+int pow_table(const int32_t** keys, const double** vals, const uint32_t** bits, int* n, int* rmax) {
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lk(g_mu);
@@ -91,10 +92,19 @@ int pow_table(const int32_t** keys, const double** vals, int* n, int* rmax) {
       cudaMemcpy(d_exc_key, g_exc_key.data(), g_exc_n * sizeof(int32_t), cudaMemcpyHostToDevice);
       cudaMemcpy(d_exc_val, g_exc_val.data(), g_exc_n * sizeof(double), cudaMemcpyHostToDevice);
     }
+    const size_t words = (size_t)kPowTableMax / 32 + 1;
+    std::vector<uint32_t> bm(words, 0u);
+    for (int r : g_exc_key) bm[(size_t)r >> 5] |= 1u << (r & 31);
+    if (cudaMalloc(&d_exc_bits, words * sizeof(uint32_t)) != cudaSuccess) {
+      set_error("pow_table: cudaMalloc failed");
+      return UBPL_ERR_CUDA;
+    }
+    cudaMemcpy(d_exc_bits, bm.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice);
     g_exc_dev = dev;
   }
   *keys = d_exc_key;
   *vals = d_exc_val;
+  *bits = d_exc_bits;
   *n = g_exc_n;
   *rmax = kPowTableMax;
   return UBPL_OK;

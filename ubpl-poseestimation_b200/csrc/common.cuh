@@ -71,6 +71,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
+// Asynchronous bulk prefetch of a contiguous global range into L2 (no registers, no smem): src 16-byte
+// aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // streaming 128-bit global accesses (read-once / write-once data: keep it out of L1)
 // ---------------------------------------------------------------------------------------------

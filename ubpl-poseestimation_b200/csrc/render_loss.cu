@@ -99,6 +99,12 @@ __global__ void __launch_bounds__(256, 3) render_mse_kernel(
   constexpr int U = 8;
   for (long long item = (long long)blockIdx.x * wpb + warp; item < BJ; item += (long long)gridDim.x * wpb) {
     const int b = (int)(item / J), j = (int)(item % J);
+    if (VEC && lane == 0) {
+      // pull this item's student maps towards L2 while the Gaussian factors are set up; the 128-bit
+      // loads below then see L2 latency instead of HBM latency
+      for (int st = 0; st < S; ++st)
+        bulk_prefetch_l2(pred + (long long)b * pB + (long long)st * pS + (long long)j * pJ, (uint32_t)HW * 4u);
+    }
     const Gauss g = gauss_setup(kps[2 * item], kps[2 * item + 1], img_h, img_w, stride, sigma);
     __syncwarp();
     for (int k = lane; k < W + H; k += 32) {

@@ -13,11 +13,12 @@
 
 namespace ubpl {
 
-int pow_table(const int32_t** keys, const double** vals, int* n, int* rmax);
+int pow_table(const int32_t** keys, const double** vals, const uint32_t** bits, int* n, int* rmax);
 
 struct PowTab {
   const int32_t* key;
   const double* val;
+  const uint32_t* bits;   // one bit per radicand: set where libm pow and sqrt disagree
   int n, rmax;
 };
 
@@ -28,7 +29,7 @@ __device__ __forceinline__ double py_dist(double x1, double y1, double x2, doubl
   double d = sqrt(r);
   if (r <= (double)T.rmax) {
     const int ri = (int)r;
-    if ((double)ri == r) {
+    if ((double)ri == r && ((__ldg(T.bits + (ri >> 5)) >> (ri & 31)) & 1u)) {
       int lo = 0, hi = T.n - 1;
       while (lo <= hi) {
         const int mid = (lo + hi) >> 1;
@@ -339,7 +340,7 @@ using namespace ubpl;
 #define GET_POWTAB(T)                                                            \
   PowTab T;                                                                      \
   {                                                                              \
-    int rc_ = pow_table(&T.key, &T.val, &T.n, &T.rmax);                           \
+    int rc_ = pow_table(&T.key, &T.val, &T.bits, &T.n, &T.rmax);                           \
     if (rc_ != UBPL_OK) return rc_;                                               \
   }
 

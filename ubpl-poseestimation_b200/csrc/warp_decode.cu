@@ -119,10 +119,14 @@ __device__ __forceinline__ void grid_consts(Xform& X, int H, int W) {
 
 // Exhaustive decode of the warped map.  Each lane walks whole columns (the column terms of the
 // affine grid are hoisted), so the tie rule is carried by arg_better's index comparison.
-__device__ __noinline__ void decode_exhaustive(const float* s, const Xform X, int lane, float& bv, int& bi) {
+__device__ __noinline__ void decode_exhaustive(const float* s, float t00, float t01, float t02, float t10, float t11,
+                                               float t12, float stepx, float stepy, float sfx, float sfy, int H, int W,
+                                               bool flip, int lane, float& bv, int& bi) {
   bv = -INFINITY;
   bi = 0x7fffffff;
-  const int W = X.W, H = X.H;
+  Xform X;
+  X.t00 = t00; X.t01 = t01; X.t02 = t02; X.t10 = t10; X.t11 = t11; X.t12 = t12;
+  X.stepx = stepx; X.stepy = stepy; X.sfx = sfx; X.sfy = sfy; X.H = H; X.W = W; X.flip = flip;
   for (int jo = lane; jo < W; jo += 32) {
     const int jw = X.flip ? (W - 1 - jo) : jo;
     const float xl = lin_coord(jw, W, X.stepx);
@@ -295,144 +299,171 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       const float det = a * e - bb * d;
       const float nrm = fabsf(a) + fabsf(bb) + fabsf(d) + fabsf(e);
       if (!(fabsf(det) > 1e-5f * nrm * nrm) || !(nrm < 1e4f) || W <= 1 || H <= 1) exhaustive = true;
-      float L = -INFINITY; int Li = 0x7fffffff;
       const float idet = 1.f / det;
       const float C00 = e * idet, C01 = -bb * idet, C10 = -d * idet, C11 = a * idet;
-      if (!exhaustive) {
-        // ---- phase L: lower bound from the pixels around the pre-image of the arg-max texel
-        unsigned biy, bix;
-        p.divW.divmod((unsigned)bi, biy, bix);
-        const float sx = (float)bix - c0, sy = (float)biy - f0;
-        const float oj = C00 * sx + C01 * sy, oi = C10 * sx + C11 * sy;
-        if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 30) {
-          const int jw = (int)floorf(oj) - 2 + (lane % 6);
-          const int i = (int)floorf(oi) - 2 + (lane / 6);
-          if (jw >= 0 && jw < W && i >= 0 && i < H) {
-            L = eval_px(s, X, i, jw);
-            Li = i * W + (X.flip ? (W - 1 - jw) : jw);
+
+      // Exact evaluation of every output pixel whose 2x2 footprint can touch the source texels
+      // [x0..x1] x [y0..y1]: the pre-image of [x0-1, x1+1] x [y0-1, y1+1], as a bounding box in the warped
+      // frame (+ slack for the approximate inverse).  Updates the lane-local best; returns the box area.
+      float lv = -INFINITY; int li = 0x7fffffff;        // lane-local best (value, canonical index)
+      auto eval_box = [&](int x0, int x1, int y0, int y1) -> int {
+        const float X0 = (float)(x0 - 1) - c0, X1 = (float)(x1 + 1) - c0;
+        const float Y0 = (float)(y0 - 1) - f0, Y1 = (float)(y1 + 1) - f0;
+        const float ja = C00 * X0, jb = C00 * X1, jc = C01 * Y0, jd = C01 * Y1;
+        const float ia = C10 * X0, ib = C10 * X1, ic = C11 * Y0, id = C11 * Y1;
+        const float jlo = fminf(ja, jb) + fminf(jc, jd), jhi = fmaxf(ja, jb) + fmaxf(jc, jd);
+        const float ilo = fminf(ia, ib) + fminf(ic, id), ihi = fmaxf(ia, ib) + fmaxf(ic, id);
+        const float m = 0.03f;
+        const int jmin = max(0, (int)ceilf(fmaxf(jlo - m, -1.f))), jmax = min(W - 1, (int)floorf(fminf(jhi + m, (float)W)));
+        const int imin = max(0, (int)ceilf(fmaxf(ilo - m, -1.f))), imax = min(H - 1, (int)floorf(fminf(ihi + m, (float)H)));
+        const int bw = jmax - jmin + 1, bh = imax - imin + 1;
+        const int area = (bw > 0 && bh > 0) ? bw * bh : 0;
+        if (area > 1024) return -1;                     // degenerate (huge magnification): let the caller fall back
+        if (area > 0) {
+          int ci = lane / bw, cj = lane - ci * bw;      // (row, col) of this lane's first pixel in the box
+          const int di = 32 / bw, dj = 32 - di * bw;
+          for (int t = lane; t < area; t += 32, ci += di, cj += dj) {
+            if (cj >= bw) { cj -= bw; ++ci; }
+            const int i = imin + ci, jw = jmin + cj;
+            const float v = eval_px(s, X, i, jw);
+            const int k = i * W + (X.flip ? (W - 1 - jw) : jw);
+            if (arg_better(v, k, lv, li)) { lv = v; li = k; }
           }
         }
-        n_eval += 30;
-        warp_argmax(L, Li);
-        // Candidate threshold.  For a pixel whose four (zero-extended) corners are all < T the computed
-        // sample is < L: the rounding of the 4-term fma chain is at most 4 ulp of sum(w|v|), and negative
-        // corners lower the exact value by more than the rounding they add, so 2^-19 relative slack covers it.
-        const float T = L - fabsf(L) * 1.9073486328125e-06f;   // 2^-19
-        bool prune = (L > 0.f) && (T > 0.f);     // zero padding cannot be a candidate when T > 0
-        bool solved = false;
-        if (!prune) {
-          // The warped maximum is not known to be positive (e.g. an all-negative map).  Along a row the
-          // computed ix and iy are monotone in the column (every rounding step is monotone), so the row
-          // ends classify the whole frame:
-          //   inside : every pixel samples with all four corners in bounds -> the convex bound holds
-          //            for any sign and the pruned search stays valid;
-          //   Z      : pixels with ix <= -1 | ix >= W | iy <= -1 | iy >= H read nothing but padding
-          //            (value exactly 0); every other pixel of an all-negative map is < 0, so the
-          //            maximum is 0 at the first Z pixel in canonical order.
-          bool inside = true;
-          int zrow = 0x7fffffff;
-          for (int i = lane; i < H; i += 32) {
+        return area;
+      };
+
+      bool solved = false;
+      bool inside = false;
+      auto classify = [&](int& zrow) {
+        // Along a row the computed ix and iy are monotone in the column (every rounding step is monotone),
+        // so the row ends classify the whole frame:
+        //   inside : every pixel samples with all four corners in bounds -> the convex bound holds for
+        //            any sign (no zero padding involved);
+        //   Z      : pixels with ix <= -1 | ix >= W | iy <= -1 | iy >= H read nothing but padding (value
+        //            exactly 0).
+        bool ins = true;
+        zrow = 0x7fffffff;
+        for (int i = lane; i < H; i += 32) {
 #pragma unroll
-            for (int endc = 0; endc < 2; ++endc) {
-              float ix, iy;
-              grid_px(X, i, endc ? W - 1 : 0, ix, iy);
-              inside = inside && (ix >= 0.f) && (ix <= (float)(W - 1)) && (iy >= 0.f) && (iy <= (float)(H - 1));
-              const bool z = (ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H);
-              if (z) zrow = min(zrow, i);
-            }
-          }
-          inside = __all_sync(0xffffffffu, inside);
-          zrow = __reduce_min_sync(0xffffffffu, zrow);
-          if (inside && L > -INFINITY) {
-            prune = true;
-          } else if (bv < 0.f && bv < -1e-20f && zrow < H) {
-            int zcol = 0x7fffffff;
-            for (int jo = lane; jo < W; jo += 32) {
-              float ix, iy;
-              grid_px(X, zrow, X.flip ? (W - 1 - jo) : jo, ix, iy);
-              if ((ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H)) zcol = min(zcol, jo);
-            }
-            zcol = __reduce_min_sync(0xffffffffu, zcol);
-            rv = eval_px(s, X, zrow, X.flip ? (W - 1 - zcol) : zcol);   // +-0, exactly what the warp produces there
-            ri = zrow * W + zcol;
-            solved = true;
-            n_eval += 2 * H + W;
-          } else {
-            exhaustive = true;
+          for (int endc = 0; endc < 2; ++endc) {
+            float ix, iy;
+            grid_px(X, i, endc ? W - 1 : 0, ix, iy);
+            ins = ins && (ix >= 0.f) && (ix <= (float)(W - 1)) && (iy >= 0.f) && (iy <= (float)(H - 1));
+            const bool z = (ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H);
+            if (z) zrow = min(zrow, i);
           }
         }
-        if (prune && !solved) {
-          // ---- pass B: bounding box of the candidate texels (v >= T) -----------------------
-          int txmin = W, txmax = -1, tymin = H, tymax = -1;
-          const int nq = HW >> 2;
-          const float4* s4 = reinterpret_cast<const float4*>(s);
-          auto visit = [&](const float4& x, int q) {
-            if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= T) {
-              const float xs[4] = {x.x, x.y, x.z, x.w};
+        inside = __all_sync(0xffffffffu, ins);
+        zrow = __reduce_min_sync(0xffffffffu, zrow);
+      };
+
+      if (!exhaustive && bv < 0.f) {
+        // All texels negative: every pixel with a live in-bounds corner is < 0, so if some pixel reads only
+        // padding the maximum is 0 at the first such pixel (canonical order); if the frame stays inside the
+        // source the candidate search below is valid for negative values; otherwise decode exhaustively.
+        int zrow;
+        classify(zrow);
+        if (zrow < H && bv < -1e-20f) {
+          int zcol = 0x7fffffff;
+          for (int jo = lane; jo < W; jo += 32) {
+            float ix, iy;
+            grid_px(X, zrow, X.flip ? (W - 1 - jo) : jo, ix, iy);
+            if ((ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H)) zcol = min(zcol, jo);
+          }
+          zcol = __reduce_min_sync(0xffffffffu, zcol);
+          rv = eval_px(s, X, zrow, X.flip ? (W - 1 - zcol) : zcol);   // +-0, exactly what the warp produces there
+          ri = zrow * W + zcol;
+          solved = true;
+          n_eval += 2 * H + W;
+        } else if (!inside) {
+          exhaustive = true;
+        }
+      }
+
+      if (!exhaustive && !solved) {
+        // ---- candidate search in descending order of the per-lane class maxima ------------------------
+        // L = best exactly evaluated sample so far (a lower bound of the warped maximum); a texel can only
+        // matter if it is >= T = L - |L| 2^-19 (for a pixel whose four zero-extended corners are all < T the
+        // computed sample is < L: the fma chain rounds by at most 4 ulp of sum(w|v|), and negative corners
+        // lower the exact value by more than the rounding they add).  Lane l knows the maximum of its float4
+        // residue class {q = l mod 32} from pass A; classes are visited best-first, each read cooperatively
+        // (one float4 per lane), and every texel >= T gets the pixels around its pre-image evaluated.
+        float L = -INFINITY; int Li = 0x7fffffff;
+        float T = -INFINITY;
+        float lm = lane_max;
+        int n_cand = 0;
+        const int nq = HW >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(s);
+        auto process_texel = [&](int k) {          // k warp-uniform
+          unsigned ty, tx;
+          p.divW.divmod((unsigned)k, ty, tx);
+          const int area = eval_box((int)tx, (int)tx, (int)ty, (int)ty);
+          if (area < 0) { exhaustive = true; return; }
+          n_eval += area;
+          float cv = lv; int ci2 = li;
+          warp_argmax(cv, ci2);
+          if (arg_better(cv, ci2, L, Li)) { L = cv; Li = ci2; T = L - fabsf(L) * 1.9073486328125e-06f; }
+          ++n_cand;
+        };
+        for (int k = (nq << 2); k < HW && !exhaustive; ++k) process_texel(k);     // tail when H*W % 4 != 0
+        while (!exhaustive) {
+          float cm = lm; int cl = lane;
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                if (xs[c] >= T) {
-                  unsigned ty, tx;
-                  p.divW.divmod((unsigned)((q << 2) + c), ty, tx);
-                  txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
-                }
-            }
-          };
-          // lane l scanned the float4s q = l (mod 32) in pass A and knows their maximum (lane_max):
-          // only the residue classes whose maximum reaches T can hold candidates.  All 32 lanes
-          // re-read one such class together (32 float4 per step).
-          unsigned hot = __ballot_sync(0xffffffffu, lane_max >= T);
-          if (__popc(hot) <= 12) {
-            while (hot) {
-              const int h = __ffs(hot) - 1;
-              hot &= hot - 1;
-              for (int q = h + 32 * lane; q < nq; q += 1024) visit(s4[q], q);
-            }
-          } else {
-#pragma unroll 4
-            for (int q = lane; q < nq; q += 32) visit(s4[q], q);
+          for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, cm, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, cl, o);
+            if (om > cm || (om == cm && ol < cl)) { cm = om; cl = ol; }
           }
-          for (int k = (nq << 2) + lane; k < HW; k += 32)
-            if (s[k] >= T) {
-              unsigned ty, tx;
-              p.divW.divmod((unsigned)k, ty, tx);
-              txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
+          if (!(cm >= T) || cm == -INFINITY) break;   // no remaining class can hold a candidate
+          for (int q = cl + 32 * lane; q < ((nq + 1023) & ~1023) && !exhaustive; q += 1024) {
+            float4 x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (q < nq) x = s4[q];
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+            unsigned pend = 0;
+            if (q < nq) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) pend |= (xs[c] >= T) ? (1u << c) : 0u;
             }
-          txmin = __reduce_min_sync(0xffffffffu, txmin); txmax = __reduce_max_sync(0xffffffffu, txmax);
-          tymin = __reduce_min_sync(0xffffffffu, tymin); tymax = __reduce_max_sync(0xffffffffu, tymax);
-          // pre-image of [txmin-1, txmax+1] x [tymin-1, tymax+1] -> bounding box in the warped frame
-          const float X0 = (float)(txmin - 1) - c0, X1 = (float)(txmax + 1) - c0;
-          const float Y0 = (float)(tymin - 1) - f0, Y1 = (float)(tymax + 1) - f0;
-          const float ja = C00 * X0, jb = C00 * X1, jc = C01 * Y0, jd = C01 * Y1;
-          const float ia = C10 * X0, ib = C10 * X1, ic = C11 * Y0, id = C11 * Y1;
-          const float jlo = fminf(ja, jb) + fminf(jc, jd), jhi = fmaxf(ja, jb) + fmaxf(jc, jd);
-          const float ilo = fminf(ia, ib) + fminf(ic, id), ihi = fmaxf(ia, ib) + fmaxf(ic, id);
-          const float m = 0.03f;
-          const int jmin = max(0, (int)ceilf(fmaxf(jlo - m, -1.f))), jmax = min(W - 1, (int)floorf(fminf(jhi + m, (float)W)));
-          const int imin = max(0, (int)ceilf(fmaxf(ilo - m, -1.f))), imax = min(H - 1, (int)floorf(fminf(ihi + m, (float)H)));
-          const int bw = jmax - jmin + 1, bh = imax - imin + 1;
-          const int area = (bw > 0 && bh > 0) ? bw * bh : 0;
-          if (area > 768 || area * 4 > HW) {
-            exhaustive = true;
-          } else {
-            // ---- phase C: exact evaluation of every pixel that can touch a candidate ---------
-            rv = L; ri = Li;
-            int ci = lane / bw, cj = lane - ci * bw;          // (row, col) of this lane's first pixel in the box
-            const int di = 32 / bw, dj = 32 - di * bw;
-            for (int t = lane; t < area; t += 32, ci += di, cj += dj) {
-              if (cj >= bw) { cj -= bw; ++ci; }
-              const int i = imin + ci, jw = jmin + cj;
-              const float v = eval_px(s, X, i, jw);
-              const int k = i * W + (X.flip ? (W - 1 - jw) : jw);
-              if (arg_better(v, k, rv, ri)) { rv = v; ri = k; }
+            while (!exhaustive) {
+              // best pending texel of the class first: after it L (and T) jump to the neighbourhood of the
+              // peak and the rest of the class usually drops out
+              float pv = -INFINITY; int pc = 0;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) if (((pend >> c) & 1u) && xs[c] > pv) { pv = xs[c]; pc = c; }   // finite values only here
+              const bool has = pend != 0;
+              float wv = has ? pv : -INFINITY; int wl = has ? lane : 64;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+                const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+                if (ol < 64 && (wl >= 64 || ov > wv || (ov == wv && ol < wl))) { wv = ov; wl = ol; }
+              }
+              if (wl >= 64) break;                 // nothing pending in this chunk
+              const int c = __shfl_sync(0xffffffffu, pc, wl);
+              const int sq = __shfl_sync(0xffffffffu, q, wl);
+              if (lane == wl) pend &= ~(1u << c);
+              process_texel((sq << 2) + c);
+              if (n_cand > 64) exhaustive = true;  // scattered near-ties: cheaper to decode exhaustively
+#pragma unroll
+              for (int c2 = 0; c2 < 4; ++c2) if (!(xs[c2] >= T)) pend &= ~(1u << c2);   // T only rises
             }
-            n_eval += area;
-            warp_argmax(rv, ri);
           }
+          if (lane == cl) lm = -INFINITY;
+        }
+        if (!exhaustive) {
+          if (!(T > 0.f) && !(bv < 0.f)) {
+            // zero padding would be a candidate too: fine only if no pixel touches it
+            int zrow;
+            classify(zrow);
+            if (!inside) exhaustive = true;
+          }
+          if (!(L > -INFINITY)) exhaustive = true;  // nothing on-frame was reachable from any candidate
+          rv = L; ri = Li;
         }
       }
       if (exhaustive) {
-        decode_exhaustive(s, X, lane, rv, ri);
+        decode_exhaustive(s, X.t00, X.t01, X.t02, X.t10, X.t11, X.t12, X.stepx, X.stepy, X.sfx, X.sfy, H, W, X.flip, lane, rv, ri);
         ++n_slow;
         n_eval += HW;
       }
