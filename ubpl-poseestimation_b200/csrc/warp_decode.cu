@@ -119,24 +119,21 @@ __device__ __forceinline__ void grid_consts(Xform& X, int H, int W) {
 
 // Exhaustive decode of the warped map.  Each lane walks whole columns (the column terms of the
 // affine grid are hoisted), so the tie rule is carried by arg_better's index comparison.
-__device__ __noinline__ void decode_exhaustive(const float* s, float t00, float t01, float t02, float t10, float t11,
-                                               float t12, float stepx, float stepy, float sfx, float sfy, int H, int W,
-                                               bool flip, int lane, float& bv, int& bi) {
+__device__ __noinline__ void decode_exhaustive(const float* __restrict__ s, float t00, float t01, float t02, float t10,
+                                               float t11, float t12, float stepx, float stepy, float sfx, float sfy,
+                                               int H, int W, bool flip, int lane, float& bv, int& bi) {
   bv = -INFINITY;
   bi = 0x7fffffff;
-  Xform X;
-  X.t00 = t00; X.t01 = t01; X.t02 = t02; X.t10 = t10; X.t11 = t11; X.t12 = t12;
-  X.stepx = stepx; X.stepy = stepy; X.sfx = sfx; X.sfy = sfy; X.H = H; X.W = W; X.flip = flip;
   for (int jo = lane; jo < W; jo += 32) {
-    const int jw = X.flip ? (W - 1 - jo) : jo;
-    const float xl = lin_coord(jw, W, X.stepx);
-    const float ax = __fmul_rn(xl, X.t00), ay = __fmul_rn(xl, X.t10);
+    const int jw = flip ? (W - 1 - jo) : jo;
+    const float xl = lin_coord(jw, W, stepx);
+    const float ax = __fmul_rn(xl, t00), ay = __fmul_rn(xl, t10);
     for (int i = 0; i < H; ++i) {
-      const float yl = lin_coord(i, H, X.stepy);
-      const float gx = __fadd_rn(__fmaf_rn(yl, X.t01, ax), X.t02);
-      const float gy = __fadd_rn(__fmaf_rn(yl, X.t11, ay), X.t12);
-      const float ix = __fmul_rn(__fadd_rn(gx, 1.f), X.sfx);
-      const float iy = __fmul_rn(__fadd_rn(gy, 1.f), X.sfy);
+      const float yl = lin_coord(i, H, stepy);
+      const float gx = __fadd_rn(__fmaf_rn(yl, t01, ax), t02);
+      const float gy = __fadd_rn(__fmaf_rn(yl, t11, ay), t12);
+      const float ix = __fmul_rn(__fadd_rn(gx, 1.f), sfx);
+      const float iy = __fmul_rn(__fadd_rn(gy, 1.f), sfy);
       const float x0f = floorf(ix), y0f = floorf(iy);
       const float w = __fsub_rn(ix, x0f), e = __fsub_rn(1.f, w);
       const float n = __fsub_rn(iy, y0f), so = __fsub_rn(1.f, n);
@@ -209,7 +206,13 @@ __device__ __forceinline__ void issue_map(const WDParams& p, long long n, float*
   bulk_g2s(dst, src, bytes, bar, pol);
 }
 
-__global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
+// STREAM = false: every warp stages its map in shared memory with a 1-D bulk async copy (TMA engine).
+// STREAM = true : no staging buffer -- the warp streams the map from global memory with 128-bit loads
+//                 (the lines stay in L1/L2 for the few gathers of the exact evaluation) and the TMA engine
+//                 prefetches the NEXT claimed map into L2 (cp.async.bulk.prefetch.L2); the CTA is then
+//                 limited by registers, not by 16 KB buffers, so twice as many warps hide the latencies.
+template <bool STREAM>
+__global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(const WDParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, W = p.W, HW = H * W;
@@ -229,36 +232,50 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     return (long long)__shfl_sync(0xffffffffu, n, 0);
   };
   long long nxt0 = N, nxt1 = N;
-  if (p.use_bulk && lane == 0) {
+  if (!STREAM && p.use_bulk && lane == 0) {
     for (int b = 0; b < NB; ++b) mbar_init(&bars[b], 1);
     fence_mbar_init();
     pol = l2_evict_first_policy();
   }
   __syncwarp();
+  auto map_ptr = [&](long long n) -> const float* {
+    unsigned vb, j, v, b;
+    p.divJ.divmod((unsigned)n, vb, j);
+    p.divB.divmod(vb, v, b);
+    return p.maps + (long long)v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
+  };
   nxt0 = claim();
-  if (p.use_bulk && lane == 0 && nxt0 < N) issue_map(p, nxt0, buf0, &bars[0], pol, map_bytes);
-  if (NB == 2) {
+  if (STREAM) {
+    // one map of look-ahead: the next claimed map is prefetched into L2 while the current one is decoded
+    if (p.use_bulk && lane == 0 && nxt0 < N) bulk_prefetch_l2(map_ptr(nxt0), map_bytes);
+    nxt1 = claim();
+    if (p.use_bulk && lane == 0 && nxt1 < N) bulk_prefetch_l2(map_ptr(nxt1), map_bytes);
+  } else if (p.use_bulk && lane == 0 && nxt0 < N) issue_map(p, nxt0, buf0, &bars[0], pol, map_bytes);
+  if (!STREAM && NB == 2) {
     nxt1 = claim();
     if (p.use_bulk && lane == 0 && nxt1 < N) issue_map(p, nxt1, buf0 + (buf_stride >> 2), &bars[1], pol, map_bytes);
   }
 
   unsigned long long n_slow = 0, n_eval = 0, n_maps = 0;
   for (long long it = 0;; ++it) {
-    const int bsel = (NB == 2) ? (int)(it & 1) : 0;
+    const int bsel = (!STREAM && NB == 2) ? (int)(it & 1) : 0;
     const long long n = bsel ? nxt1 : nxt0;
     if (n >= N) break;
-    float* s = buf0 + (size_t)bsel * (buf_stride >> 2);
+    const float* s = STREAM ? map_ptr(n) : buf0 + (size_t)bsel * (buf_stride >> 2);
     unsigned vbu, ju, vu, bu;
     p.divJ.divmod((unsigned)n, vbu, ju);
     p.divB.divmod(vbu, vu, bu);
     const int j = (int)ju, b = (int)bu;
     const long long vb = (long long)vbu;
-    if (p.use_bulk) {
-      mbar_wait(&bars[bsel], (uint32_t)((it / NB) & 1));
-    } else {
-      const float* src = p.maps + (long long)vu * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
-      for (int k = lane; k < HW; k += 32) s[k] = __ldg(src + k);
-      __syncwarp();
+    if (!STREAM) {
+      if (p.use_bulk) {
+        mbar_wait(&bars[bsel], (uint32_t)((it / NB) & 1));
+      } else {
+        float* sw = buf0 + (size_t)bsel * (buf_stride >> 2);
+        const float* src = p.maps + (long long)vu * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
+        for (int k = lane; k < HW; k += 32) sw[k] = __ldg(src + k);
+        __syncwarp();
+      }
     }
     ++n_maps;
 
@@ -299,167 +316,140 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       const float det = a * e - bb * d;
       const float nrm = fabsf(a) + fabsf(bb) + fabsf(d) + fabsf(e);
       if (!(fabsf(det) > 1e-5f * nrm * nrm) || !(nrm < 1e4f) || W <= 1 || H <= 1) exhaustive = true;
+      float L = -INFINITY; int Li = 0x7fffffff;
       const float idet = 1.f / det;
       const float C00 = e * idet, C01 = -bb * idet, C10 = -d * idet, C11 = a * idet;
-
-      // Exact evaluation of every output pixel whose 2x2 footprint can touch the source texels
-      // [x0..x1] x [y0..y1]: the pre-image of [x0-1, x1+1] x [y0-1, y1+1], as a bounding box in the warped
-      // frame (+ slack for the approximate inverse).  Updates the lane-local best; returns the box area.
-      float lv = -INFINITY; int li = 0x7fffffff;        // lane-local best (value, canonical index)
-      auto eval_box = [&](int x0, int x1, int y0, int y1) -> int {
-        const float X0 = (float)(x0 - 1) - c0, X1 = (float)(x1 + 1) - c0;
-        const float Y0 = (float)(y0 - 1) - f0, Y1 = (float)(y1 + 1) - f0;
-        const float ja = C00 * X0, jb = C00 * X1, jc = C01 * Y0, jd = C01 * Y1;
-        const float ia = C10 * X0, ib = C10 * X1, ic = C11 * Y0, id = C11 * Y1;
-        const float jlo = fminf(ja, jb) + fminf(jc, jd), jhi = fmaxf(ja, jb) + fmaxf(jc, jd);
-        const float ilo = fminf(ia, ib) + fminf(ic, id), ihi = fmaxf(ia, ib) + fmaxf(ic, id);
-        const float m = 0.03f;
-        const int jmin = max(0, (int)ceilf(fmaxf(jlo - m, -1.f))), jmax = min(W - 1, (int)floorf(fminf(jhi + m, (float)W)));
-        const int imin = max(0, (int)ceilf(fmaxf(ilo - m, -1.f))), imax = min(H - 1, (int)floorf(fminf(ihi + m, (float)H)));
-        const int bw = jmax - jmin + 1, bh = imax - imin + 1;
-        const int area = (bw > 0 && bh > 0) ? bw * bh : 0;
-        if (area > 1024) return -1;                     // degenerate (huge magnification): let the caller fall back
-        if (area > 0) {
-          int ci = lane / bw, cj = lane - ci * bw;      // (row, col) of this lane's first pixel in the box
-          const int di = 32 / bw, dj = 32 - di * bw;
-          for (int t = lane; t < area; t += 32, ci += di, cj += dj) {
-            if (cj >= bw) { cj -= bw; ++ci; }
-            const int i = imin + ci, jw = jmin + cj;
-            const float v = eval_px(s, X, i, jw);
-            const int k = i * W + (X.flip ? (W - 1 - jw) : jw);
-            if (arg_better(v, k, lv, li)) { lv = v; li = k; }
+      if (!exhaustive) {
+        // ---- phase L: lower bound from the pixels around the pre-image of the arg-max texel
+        unsigned biy, bix;
+        p.divW.divmod((unsigned)bi, biy, bix);
+        const float sx = (float)bix - c0, sy = (float)biy - f0;
+        const float oj = C00 * sx + C01 * sy, oi = C10 * sx + C11 * sy;
+        if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 30) {
+          const int jw = (int)floorf(oj) - 2 + (lane % 6);
+          const int i = (int)floorf(oi) - 2 + (lane / 6);
+          if (jw >= 0 && jw < W && i >= 0 && i < H) {
+            L = eval_px(s, X, i, jw);
+            Li = i * W + (X.flip ? (W - 1 - jw) : jw);
           }
         }
-        return area;
-      };
-
-      bool solved = false;
-      bool inside = false;
-      auto classify = [&](int& zrow) {
-        // Along a row the computed ix and iy are monotone in the column (every rounding step is monotone),
-        // so the row ends classify the whole frame:
-        //   inside : every pixel samples with all four corners in bounds -> the convex bound holds for
-        //            any sign (no zero padding involved);
-        //   Z      : pixels with ix <= -1 | ix >= W | iy <= -1 | iy >= H read nothing but padding (value
-        //            exactly 0).
-        bool ins = true;
-        zrow = 0x7fffffff;
-        for (int i = lane; i < H; i += 32) {
+        n_eval += 30;
+        warp_argmax(L, Li);
+        // Candidate threshold.  For a pixel whose four (zero-extended) corners are all < T the computed
+        // sample is < L: the rounding of the 4-term fma chain is at most 4 ulp of sum(w|v|), and negative
+        // corners lower the exact value by more than the rounding they add, so 2^-19 relative slack covers it.
+        const float T = L - fabsf(L) * 1.9073486328125e-06f;   // 2^-19
+        bool prune = (L > 0.f) && (T > 0.f);     // zero padding cannot be a candidate when T > 0
+        bool solved = false;
+        if (!prune) {
+          // The warped maximum is not known to be positive (e.g. an all-negative map).  Along a row the
+          // computed ix and iy are monotone in the column (every rounding step is monotone), so the row
+          // ends classify the whole frame:
+          //   inside : every pixel samples with all four corners in bounds -> the convex bound holds
+          //            for any sign and the pruned search stays valid;
+          //   Z      : pixels with ix <= -1 | ix >= W | iy <= -1 | iy >= H read nothing but padding
+          //            (value exactly 0); every other pixel of an all-negative map is < 0, so the
+          //            maximum is 0 at the first Z pixel in canonical order.
+          bool inside = true;
+          int zrow = 0x7fffffff;
+          for (int i = lane; i < H; i += 32) {
 #pragma unroll
-          for (int endc = 0; endc < 2; ++endc) {
-            float ix, iy;
-            grid_px(X, i, endc ? W - 1 : 0, ix, iy);
-            ins = ins && (ix >= 0.f) && (ix <= (float)(W - 1)) && (iy >= 0.f) && (iy <= (float)(H - 1));
-            const bool z = (ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H);
-            if (z) zrow = min(zrow, i);
-          }
-        }
-        inside = __all_sync(0xffffffffu, ins);
-        zrow = __reduce_min_sync(0xffffffffu, zrow);
-      };
-
-      if (!exhaustive && bv < 0.f) {
-        // All texels negative: every pixel with a live in-bounds corner is < 0, so if some pixel reads only
-        // padding the maximum is 0 at the first such pixel (canonical order); if the frame stays inside the
-        // source the candidate search below is valid for negative values; otherwise decode exhaustively.
-        int zrow;
-        classify(zrow);
-        if (zrow < H && bv < -1e-20f) {
-          int zcol = 0x7fffffff;
-          for (int jo = lane; jo < W; jo += 32) {
-            float ix, iy;
-            grid_px(X, zrow, X.flip ? (W - 1 - jo) : jo, ix, iy);
-            if ((ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H)) zcol = min(zcol, jo);
-          }
-          zcol = __reduce_min_sync(0xffffffffu, zcol);
-          rv = eval_px(s, X, zrow, X.flip ? (W - 1 - zcol) : zcol);   // +-0, exactly what the warp produces there
-          ri = zrow * W + zcol;
-          solved = true;
-          n_eval += 2 * H + W;
-        } else if (!inside) {
-          exhaustive = true;
-        }
-      }
-
-      if (!exhaustive && !solved) {
-        // ---- candidate search in descending order of the per-lane class maxima ------------------------
-        // L = best exactly evaluated sample so far (a lower bound of the warped maximum); a texel can only
-        // matter if it is >= T = L - |L| 2^-19 (for a pixel whose four zero-extended corners are all < T the
-        // computed sample is < L: the fma chain rounds by at most 4 ulp of sum(w|v|), and negative corners
-        // lower the exact value by more than the rounding they add).  Lane l knows the maximum of its float4
-        // residue class {q = l mod 32} from pass A; classes are visited best-first, each read cooperatively
-        // (one float4 per lane), and every texel >= T gets the pixels around its pre-image evaluated.
-        float L = -INFINITY; int Li = 0x7fffffff;
-        float T = -INFINITY;
-        float lm = lane_max;
-        int n_cand = 0;
-        const int nq = HW >> 2;
-        const float4* s4 = reinterpret_cast<const float4*>(s);
-        auto process_texel = [&](int k) {          // k warp-uniform
-          unsigned ty, tx;
-          p.divW.divmod((unsigned)k, ty, tx);
-          const int area = eval_box((int)tx, (int)tx, (int)ty, (int)ty);
-          if (area < 0) { exhaustive = true; return; }
-          n_eval += area;
-          float cv = lv; int ci2 = li;
-          warp_argmax(cv, ci2);
-          if (arg_better(cv, ci2, L, Li)) { L = cv; Li = ci2; T = L - fabsf(L) * 1.9073486328125e-06f; }
-          ++n_cand;
-        };
-        for (int k = (nq << 2); k < HW && !exhaustive; ++k) process_texel(k);     // tail when H*W % 4 != 0
-        while (!exhaustive) {
-          float cm = lm; int cl = lane;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float om = __shfl_xor_sync(0xffffffffu, cm, o);
-            const int ol = __shfl_xor_sync(0xffffffffu, cl, o);
-            if (om > cm || (om == cm && ol < cl)) { cm = om; cl = ol; }
-          }
-          if (!(cm >= T) || cm == -INFINITY) break;   // no remaining class can hold a candidate
-          for (int q = cl + 32 * lane; q < ((nq + 1023) & ~1023) && !exhaustive; q += 1024) {
-            float4 x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            if (q < nq) x = s4[q];
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-            unsigned pend = 0;
-            if (q < nq) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) pend |= (xs[c] >= T) ? (1u << c) : 0u;
-            }
-            while (!exhaustive) {
-              // best pending texel of the class first: after it L (and T) jump to the neighbourhood of the
-              // peak and the rest of the class usually drops out
-              float pv = -INFINITY; int pc = 0;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) if (((pend >> c) & 1u) && xs[c] > pv) { pv = xs[c]; pc = c; }   // finite values only here
-              const bool has = pend != 0;
-              float wv = has ? pv : -INFINITY; int wl = has ? lane : 64;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
-                const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
-                if (ol < 64 && (wl >= 64 || ov > wv || (ov == wv && ol < wl))) { wv = ov; wl = ol; }
-              }
-              if (wl >= 64) break;                 // nothing pending in this chunk
-              const int c = __shfl_sync(0xffffffffu, pc, wl);
-              const int sq = __shfl_sync(0xffffffffu, q, wl);
-              if (lane == wl) pend &= ~(1u << c);
-              process_texel((sq << 2) + c);
-              if (n_cand > 64) exhaustive = true;  // scattered near-ties: cheaper to decode exhaustively
-#pragma unroll
-              for (int c2 = 0; c2 < 4; ++c2) if (!(xs[c2] >= T)) pend &= ~(1u << c2);   // T only rises
+            for (int endc = 0; endc < 2; ++endc) {
+              float ix, iy;
+              grid_px(X, i, endc ? W - 1 : 0, ix, iy);
+              inside = inside && (ix >= 0.f) && (ix <= (float)(W - 1)) && (iy >= 0.f) && (iy <= (float)(H - 1));
+              const bool z = (ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H);
+              if (z) zrow = min(zrow, i);
             }
           }
-          if (lane == cl) lm = -INFINITY;
-        }
-        if (!exhaustive) {
-          if (!(T > 0.f) && !(bv < 0.f)) {
-            // zero padding would be a candidate too: fine only if no pixel touches it
-            int zrow;
-            classify(zrow);
-            if (!inside) exhaustive = true;
+          inside = __all_sync(0xffffffffu, inside);
+          zrow = __reduce_min_sync(0xffffffffu, zrow);
+          if (inside && L > -INFINITY) {
+            prune = true;
+          } else if (bv < 0.f && bv < -1e-20f && zrow < H) {
+            int zcol = 0x7fffffff;
+            for (int jo = lane; jo < W; jo += 32) {
+              float ix, iy;
+              grid_px(X, zrow, X.flip ? (W - 1 - jo) : jo, ix, iy);
+              if ((ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H)) zcol = min(zcol, jo);
+            }
+            zcol = __reduce_min_sync(0xffffffffu, zcol);
+            rv = eval_px(s, X, zrow, X.flip ? (W - 1 - zcol) : zcol);   // +-0, exactly what the warp produces there
+            ri = zrow * W + zcol;
+            solved = true;
+            n_eval += 2 * H + W;
+          } else {
+            exhaustive = true;
           }
-          if (!(L > -INFINITY)) exhaustive = true;  // nothing on-frame was reachable from any candidate
-          rv = L; ri = Li;
+        }
+        if (prune && !solved) {
+          // ---- pass B: bounding box of the candidate texels (v >= T) -----------------------
+          int txmin = W, txmax = -1, tymin = H, tymax = -1;
+          const int nq = HW >> 2;
+          const float4* s4 = reinterpret_cast<const float4*>(s);
+          auto visit = [&](const float4& x, int q) {
+            if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= T) {
+              const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (xs[c] >= T) {
+                  unsigned ty, tx;
+                  p.divW.divmod((unsigned)((q << 2) + c), ty, tx);
+                  txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
+                }
+            }
+          };
+          // lane l scanned the float4s q = l (mod 32) in pass A and knows their maximum (lane_max):
+          // only the residue classes whose maximum reaches T can hold candidates.  All 32 lanes
+          // re-read one such class together (32 float4 per step).
+          unsigned hot = __ballot_sync(0xffffffffu, lane_max >= T);
+          if (__popc(hot) <= 12) {
+            while (hot) {
+              const int h = __ffs(hot) - 1;
+              hot &= hot - 1;
+              for (int q = h + 32 * lane; q < nq; q += 1024) visit(s4[q], q);
+            }
+          } else {
+#pragma unroll 4
+            for (int q = lane; q < nq; q += 32) visit(s4[q], q);
+          }
+          for (int k = (nq << 2) + lane; k < HW; k += 32)
+            if (s[k] >= T) {
+              unsigned ty, tx;
+              p.divW.divmod((unsigned)k, ty, tx);
+              txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
+            }
+          txmin = __reduce_min_sync(0xffffffffu, txmin); txmax = __reduce_max_sync(0xffffffffu, txmax);
+          tymin = __reduce_min_sync(0xffffffffu, tymin); tymax = __reduce_max_sync(0xffffffffu, tymax);
+          // pre-image of [txmin-1, txmax+1] x [tymin-1, tymax+1] -> bounding box in the warped frame
+          const float X0 = (float)(txmin - 1) - c0, X1 = (float)(txmax + 1) - c0;
+          const float Y0 = (float)(tymin - 1) - f0, Y1 = (float)(tymax + 1) - f0;
+          const float ja = C00 * X0, jb = C00 * X1, jc = C01 * Y0, jd = C01 * Y1;
+          const float ia = C10 * X0, ib = C10 * X1, ic = C11 * Y0, id = C11 * Y1;
+          const float jlo = fminf(ja, jb) + fminf(jc, jd), jhi = fmaxf(ja, jb) + fmaxf(jc, jd);
+          const float ilo = fminf(ia, ib) + fminf(ic, id), ihi = fmaxf(ia, ib) + fmaxf(ic, id);
+          const float m = 0.03f;
+          const int jmin = max(0, (int)ceilf(fmaxf(jlo - m, -1.f))), jmax = min(W - 1, (int)floorf(fminf(jhi + m, (float)W)));
+          const int imin = max(0, (int)ceilf(fmaxf(ilo - m, -1.f))), imax = min(H - 1, (int)floorf(fminf(ihi + m, (float)H)));
+          const int bw = jmax - jmin + 1, bh = imax - imin + 1;
+          const int area = (bw > 0 && bh > 0) ? bw * bh : 0;
+          if (area > 768 || area * 4 > HW) {
+            exhaustive = true;
+          } else {
+            // ---- phase C: exact evaluation of every pixel that can touch a candidate ---------
+            rv = L; ri = Li;
+            int ci = lane / bw, cj = lane - ci * bw;          // (row, col) of this lane's first pixel in the box
+            const int di = 32 / bw, dj = 32 - di * bw;
+            for (int t = lane; t < area; t += 32, ci += di, cj += dj) {
+              if (cj >= bw) { cj -= bw; ++ci; }
+              const int i = imin + ci, jw = jmin + cj;
+              const float v = eval_px(s, X, i, jw);
+              const int k = i * W + (X.flip ? (W - 1 - jw) : jw);
+              if (arg_better(v, k, rv, ri)) { rv = v; ri = k; }
+            }
+            n_eval += area;
+            warp_argmax(rv, ri);
+          }
         }
       }
       if (exhaustive) {
@@ -514,8 +504,14 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     }
     __syncwarp();
     const long long nn = claim();
-    if (bsel) nxt1 = nn; else nxt0 = nn;
-    if (p.use_bulk && lane == 0 && nn < N) issue_map(p, nn, s, &bars[bsel], pol, map_bytes);
+    if (STREAM) {
+      nxt0 = nxt1; nxt1 = nn;
+      if (p.use_bulk && lane == 0 && nn < N) bulk_prefetch_l2(map_ptr(nn), map_bytes);
+    } else {
+      if (bsel) nxt1 = nn; else nxt0 = nn;
+      if (p.use_bulk && lane == 0 && nn < N)
+        issue_map(p, nn, buf0 + (size_t)bsel * (buf_stride >> 2), &bars[bsel], pol, map_bytes);
+    }
   }
   if (p.stats && lane == 0 && n_maps) {
     atomicAdd(p.stats + 0, n_slow);
@@ -607,18 +603,31 @@ extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64
   if (warps > 16) warps = 16;
   if (warps < 1) warps = 1;
   p.nbuf = nbuf;
+  // "stream" (default when the maps are 16-byte aligned): no staging buffers, register-limited CTAs of 24
+  // warps; "smem": TMA-staged buffers, 14 warps for 64x64 maps.  UBPL_K1_MODE=smem|stream overrides.
+  static const char* env_mode = getenv("UBPL_K1_MODE");
+  bool stream_mode = p.use_bulk && (map_bytes % 16 == 0);
+  if (env_mode && env_mode[0] == 's' && env_mode[1] == 'm') stream_mode = false;
+  p.work = work_counter((cudaStream_t)stream);
+  if (!p.work) return UBPL_ERR_CUDA;
+  if (stream_mode) {
+    int sw = 24;
+    if (env_warps > 0 && env_warps < sw) sw = env_warps;
+    long long need = (N + sw - 1) / sw;
+    int grid = (int)(need < sm_count() ? need : sm_count());
+    warp_decode_kernel<true><<<grid, sw * 32, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("ubpl_warp_decode");
+  }
   const size_t smem = (size_t)warps * nbuf * buf_stride + (size_t)warps * nbuf * 8;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(warp_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+    cudaError_t e = cudaFuncSetAttribute(warp_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
     if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
     attr_set = true;
   }
-  p.work = work_counter((cudaStream_t)stream);
-  if (!p.work) return UBPL_ERR_CUDA;
   long long need = (N + warps - 1) / warps;
   int grid = (int)(need < sm_count() ? need : sm_count());
-  warp_decode_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(p);
+  warp_decode_kernel<false><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(p);
   return check_launch("ubpl_warp_decode");
 }
 

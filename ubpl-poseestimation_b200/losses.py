@@ -36,10 +36,8 @@ class _DenseLossFn(torch.autograd.Function):
         ctx.grad = r["grad"]
         ctx.tgt_shape = tgt.shape
         ctx.pred_shape = pred5.shape
-        ctx.mark_non_differentiable(fin)
         aux = [t if t is not None else torch.empty(0, device=pred5.device) for t in (r["vmax_p"], r["vmax_t"], r["mask"])]
-        for a in aux:
-            ctx.mark_non_differentiable(a)
+        ctx.mark_non_differentiable(fin, *aux)        # one call: every call replaces the previous set
         return (fin[0].to(torch.float32), fin) + tuple(aux)
 
     @staticmethod

@@ -178,52 +178,82 @@ def coord_error(pred, gt, pck_ref, pck_thr):
     return err, acc
 
 
-def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, group=None, n_total=None):
+class _CudaSelectBackend:
+    """The five device primitives of the quantile selector (K2 kernels of libubpl_b200.so)."""
+
+    def prepare(self, dist, legal):
+        _need_cuda(dist, legal)
+        return dist.reshape(-1).to(_f64).contiguous(), legal.reshape(-1).to(_f64).contiguous()
+
+    def extrema(self, dist):
+        ext = torch.empty(2, dtype=_f64, device=dist.device)
+        _lib.call("ubpl_dist_extrema", dist.data_ptr(), dist.numel(), ext.data_ptr(), _stream())
+        return ext
+
+    def reliability(self, dist, legal, ext, reliableDistMin):
+        n = dist.numel()
+        rel = torch.empty(n, dtype=_f64, device=dist.device)
+        keys = torch.empty(n, dtype=torch.int64, device=dist.device)
+        _lib.call("ubpl_reliability", dist.data_ptr(), legal.data_ptr(), n, ext.data_ptr(), float(reliableDistMin),
+                  rel.data_ptr(), keys.data_ptr(), _stream())
+        return rel, keys
+
+    def state(self, k, device):
+        return (torch.zeros(1, dtype=torch.int64, device=device), torch.full((1,), k, dtype=torch.int64, device=device),
+                torch.empty(65536, dtype=torch.int32, device=device))
+
+    def histogram(self, keys, prefix, shift, hist):
+        _lib.call("ubpl_key_histogram", keys.data_ptr(), keys.numel(), prefix.data_ptr(), shift, hist.data_ptr(), _stream())
+
+    def descend(self, hist, shift, prefix, k_rem):
+        _lib.call("ubpl_select_descend", hist.data_ptr(), shift, prefix.data_ptr(), k_rem.data_ptr(), _stream())
+
+    def apply(self, rel, J, prefix, reliableThr):
+        n = rel.numel()
+        dev = rel.device
+        enable = torch.empty(n, dtype=torch.uint8, device=dev)
+        gate = torch.empty(n, dtype=_f32, device=dev)
+        counts = torch.empty(J + 1, dtype=torch.int32, device=dev)
+        thr = torch.empty(1, dtype=_f64, device=dev)
+        _lib.call("ubpl_select_apply", rel.data_ptr(), n, J, prefix.data_ptr(), float(reliableThr), enable.data_ptr(),
+                  gate.data_ptr(), counts.data_ptr(), thr.data_ptr(), _stream())
+        return enable, gate, counts, thr
+
+
+def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, group=None, n_total=None, backend=None):
     """BusinessUtils.filter_pseudo2 (utils/business.py:173-217) on device: min/max normalise,
     reliability = 1 - unc, exact k-th order statistic (k = int((n-1)*pct) from the top) by a
     4-pass 16-bit radix select, enable = reliability > max(reliableThr, kth).
 
     With a torch.distributed `group` the extrema and the four histograms are all-reduced (NCCL),
     so every rank derives the same global threshold; each rank passes its own shard of items and
-    all shards are assumed equal in size unless n_total is given."""
-    _need_cuda(dist, legal)
-    dist = dist.reshape(-1).to(_f64).contiguous()
-    legal = legal.reshape(-1).to(_f64).contiguous()
+    all shards are assumed equal in size unless n_total is given.  `backend` exists for the
+    world_size-2 gloo test of this control flow (tests/test_dist_gloo.py); the product always
+    uses the CUDA kernels."""
+    be = backend if backend is not None else _CudaSelectBackend()
+    dist, legal = be.prepare(dist, legal)
     n = dist.numel()
-    dev = dist.device
-    st = _stream()
     world = 1
     if group is not None:
         import torch.distributed as td
         world = td.get_world_size(group)
     if n_total is None:
         n_total = n * world
-    ext = torch.empty(2, dtype=_f64, device=dev)
-    _lib.call("ubpl_dist_extrema", dist.data_ptr(), n, ext.data_ptr(), st)
+    ext = be.extrema(dist)
     if world > 1:
         td.all_reduce(ext[0:1], op=td.ReduceOp.MAX, group=group)
         td.all_reduce(ext[1:2], op=td.ReduceOp.MIN, group=group)
-    rel = torch.empty(n, dtype=_f64, device=dev)
-    keys = torch.empty(n, dtype=torch.int64, device=dev)
-    _lib.call("ubpl_reliability", dist.data_ptr(), legal.data_ptr(), n, ext.data_ptr(), float(reliableDistMin),
-              rel.data_ptr(), keys.data_ptr(), st)
+    rel, keys = be.reliability(dist, legal, ext, reliableDistMin)
     if n_total < 1:
         raise IndexError("list index out of range")          # scores[int(-1*pct)] on an empty list
     k = int((n_total - 1) * reliablePCT)                     # utils/business.py:45
-    prefix = torch.zeros(1, dtype=torch.int64, device=dev)
-    k_rem = torch.full((1,), k, dtype=torch.int64, device=dev)
-    hist = torch.empty(65536, dtype=torch.int32, device=dev)
+    prefix, k_rem, hist = be.state(k, dist.device)
     for shift in (48, 32, 16, 0):
-        _lib.call("ubpl_key_histogram", keys.data_ptr(), n, prefix.data_ptr(), shift, hist.data_ptr(), st)
+        be.histogram(keys, prefix, shift, hist)
         if world > 1:
             td.all_reduce(hist, op=td.ReduceOp.SUM, group=group)
-        _lib.call("ubpl_select_descend", hist.data_ptr(), shift, prefix.data_ptr(), k_rem.data_ptr(), st)
-    enable = torch.empty(n, dtype=torch.uint8, device=dev)
-    gate = torch.empty(n, dtype=_f32, device=dev)
-    counts = torch.empty(J + 1, dtype=torch.int32, device=dev)
-    thr = torch.empty(1, dtype=_f64, device=dev)
-    _lib.call("ubpl_select_apply", rel.data_ptr(), n, J, prefix.data_ptr(), float(reliableThr), enable.data_ptr(),
-              gate.data_ptr(), counts.data_ptr(), thr.data_ptr(), st)
+        be.descend(hist, shift, prefix, k_rem)
+    enable, gate, counts, thr = be.apply(rel, J, prefix, reliableThr)
     return dict(reliability=rel, enable=enable, gate=gate, counts=counts, thr=thr, ext=ext)
 
 
