@@ -267,6 +267,27 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
     p.divB.divmod(vbu, vu, bu);
     const int j = (int)ju, b = (int)bu;
     const long long vb = (long long)vbu;
+    // ---- per-map transform set-up, issued BEFORE waiting for the staged map so that the global loads of
+    // theta / flip / dec and the inverse-affine arithmetic overlap the copy latency
+    Xform X;
+    X.H = H; X.W = W; X.flip = false;
+    float a = 0.f, bb = 0.f, d = 0.f, e = 0.f, c0 = 0.f, f0 = 0.f, C00 = 0.f, C01 = 0.f, C10 = 0.f, C11 = 0.f;
+    bool bad_xform = false;
+    double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
+    if (p.dec) { const double* c = p.dec + (size_t)b * 4; dc0 = c[0]; dc1 = c[1]; dc2 = c[2]; dc3 = c[3]; }
+    if (p.do_warp) {
+      load_xform(X, p.theta, p.flip, vb, H, W);
+      X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
+      // pixel-space affine  ix = a*jw + bb*i + c0 ; iy = d*jw + e*i + f0  (approximate, for boxes only)
+      a = X.t00 * X.stepx * X.sfx; bb = X.t01 * X.stepy * X.sfx;
+      d = X.t10 * X.stepx * X.sfy; e = X.t11 * X.stepy * X.sfy;
+      c0 = (X.t02 + 1.f - X.t00 - X.t01) * X.sfx; f0 = (X.t12 + 1.f - X.t10 - X.t11) * X.sfy;
+      const float det = a * e - bb * d;
+      const float nrm = fabsf(a) + fabsf(bb) + fabsf(d) + fabsf(e);
+      bad_xform = !(fabsf(det) > 1e-5f * nrm * nrm) || !(nrm < 1e4f) || W <= 1 || H <= 1;
+      const float idet = 1.f / det;
+      C00 = e * idet; C01 = -bb * idet; C10 = -d * idet; C11 = a * idet;
+    }
     if (!STREAM) {
       if (p.use_bulk) {
         mbar_wait(&bars[bsel], (uint32_t)((it / NB) & 1));
@@ -296,60 +317,53 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
     // NaN -> mn is NaN; -inf -> mn == -inf; +inf -> bv == +inf
     const bool nonfinite = __any_sync(0xffffffffu, !(mn >= -FLT_MAX) || !(bv <= FLT_MAX));
     float rv = bv; int ri = bi;           // result (value, canonical flat index)
-    Xform X;
     if (!p.do_warp) {
       if (nonfinite) {                    // torch.max: the first NaN wins; +-Inf compare normally
         rv = -INFINITY; ri = 0x7fffffff;
         for (int k = lane; k < HW; k += 32) { const float x = s[k]; if (arg_better(x, k, rv, ri)) { rv = x; ri = k; } }
       }
       warp_argmax(rv, ri);
-      X.H = H; X.W = W; X.flip = false;
     } else {
-      load_xform(X, p.theta, p.flip, vb, H, W);
-      X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
       warp_argmax(bv, bi);                // warp-uniform source max / location
-      bool exhaustive = nonfinite;
-      // pixel-space affine  ix = a*jw + bb*i + c0 ; iy = d*jw + e*i + f0  (approximate, for boxes only)
-      const float a = X.t00 * X.stepx * X.sfx, bb = X.t01 * X.stepy * X.sfx;
-      const float d = X.t10 * X.stepx * X.sfy, e = X.t11 * X.stepy * X.sfy;
-      const float c0 = (X.t02 + 1.f - X.t00 - X.t01) * X.sfx, f0 = (X.t12 + 1.f - X.t10 - X.t11) * X.sfy;
-      const float det = a * e - bb * d;
-      const float nrm = fabsf(a) + fabsf(bb) + fabsf(d) + fabsf(e);
-      if (!(fabsf(det) > 1e-5f * nrm * nrm) || !(nrm < 1e4f) || W <= 1 || H <= 1) exhaustive = true;
+      bool exhaustive = nonfinite || bad_xform;
       float L = -INFINITY; int Li = 0x7fffffff;
-      const float idet = 1.f / det;
-      const float C00 = e * idet, C01 = -bb * idet, C10 = -d * idet, C11 = a * idet;
       if (!exhaustive) {
-        // ---- phase L: lower bound from the pixels around the pre-image of the arg-max texel
-        unsigned biy, bix;
-        p.divW.divmod((unsigned)bi, biy, bix);
-        const float sx = (float)bix - c0, sy = (float)biy - f0;
-        const float oj = C00 * sx + C01 * sy, oi = C10 * sx + C11 * sy;
-        if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 30) {
-          const int jw = (int)floorf(oj) - 2 + (lane % 6);
-          const int i = (int)floorf(oi) - 2 + (lane / 6);
-          if (jw >= 0 && jw < W && i >= 0 && i < H) {
-            L = eval_px(s, X, i, jw);
-            Li = i * W + (X.flip ? (W - 1 - jw) : jw);
+        const float kSlack = 1.9073486328125e-06f;   // 2^-19
+        float T = 0.f;
+        bool prune = false, solved = false;
+        // bv > 0: start from the PROVISIONAL threshold 0.875*bv (the warped peak of a smooth response is
+        // within a few percent of its best texel), evaluate the box of the texels above it, and accept if
+        // the exact maximum L found there satisfies L*(1-2^-19) >= 0.875*bv -- then every texel that could
+        // matter (>= L*(1-2^-19)) was inside the candidate set.  Otherwise repeat once with the true bound.
+        const bool provisional = bv > 0.f;
+        if (provisional) {
+          T = bv * 0.875f;
+          prune = true;
+        } else {
+          // ---- phase L: lower bound from the pixels around the pre-image of the arg-max texel
+          unsigned biy, bix;
+          p.divW.divmod((unsigned)bi, biy, bix);
+          const float sx = (float)bix - c0, sy = (float)biy - f0;
+          const float oj = C00 * sx + C01 * sy, oi = C10 * sx + C11 * sy;
+          if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 30) {
+            const int jw = (int)floorf(oj) - 2 + (lane % 6);
+            const int i = (int)floorf(oi) - 2 + (lane / 6);
+            if (jw >= 0 && jw < W && i >= 0 && i < H) {
+              L = eval_px(s, X, i, jw);
+              Li = i * W + (X.flip ? (W - 1 - jw) : jw);
+            }
           }
-        }
-        n_eval += 30;
-        warp_argmax(L, Li);
-        // Candidate threshold.  For a pixel whose four (zero-extended) corners are all < T the computed
-        // sample is < L: the rounding of the 4-term fma chain is at most 4 ulp of sum(w|v|), and negative
-        // corners lower the exact value by more than the rounding they add, so 2^-19 relative slack covers it.
-        const float T = L - fabsf(L) * 1.9073486328125e-06f;   // 2^-19
-        bool prune = (L > 0.f) && (T > 0.f);     // zero padding cannot be a candidate when T > 0
-        bool solved = false;
-        if (!prune) {
-          // The warped maximum is not known to be positive (e.g. an all-negative map).  Along a row the
-          // computed ix and iy are monotone in the column (every rounding step is monotone), so the row
-          // ends classify the whole frame:
-          //   inside : every pixel samples with all four corners in bounds -> the convex bound holds
-          //            for any sign and the pruned search stays valid;
-          //   Z      : pixels with ix <= -1 | ix >= W | iy <= -1 | iy >= H read nothing but padding
-          //            (value exactly 0); every other pixel of an all-negative map is < 0, so the
-          //            maximum is 0 at the first Z pixel in canonical order.
+          n_eval += 30;
+          warp_argmax(L, Li);
+          T = L - fabsf(L) * kSlack;
+          // The warped maximum is not known to be positive (an all-negative map, or a map whose maximum is
+          // exactly 0).  Along a row the computed ix and iy are monotone in the column (every rounding step
+          // is monotone), so the row ends classify the whole frame:
+          //   inside : every pixel samples with all four corners in bounds -> the convex bound holds for any
+          //            sign (no zero padding involved) and the pruned search stays valid;
+          //   Z      : pixels with ix <= -1 | ix >= W | iy <= -1 | iy >= H read nothing but padding (value
+          //            exactly 0); every other pixel of an all-negative map is < 0, so the maximum is 0 at the
+          //            first Z pixel in canonical order.
           bool inside = true;
           int zrow = 0x7fffffff;
           for (int i = lane; i < H; i += 32) {
@@ -366,7 +380,7 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
           zrow = __reduce_min_sync(0xffffffffu, zrow);
           if (inside && L > -INFINITY) {
             prune = true;
-          } else if (bv < 0.f && bv < -1e-20f && zrow < H) {
+          } else if (bv < -1e-20f && zrow < H) {
             int zcol = 0x7fffffff;
             for (int jo = lane; jo < W; jo += 32) {
               float ix, iy;
@@ -382,7 +396,7 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
             exhaustive = true;
           }
         }
-        if (prune && !solved) {
+        for (int round = 0; prune && !solved && !exhaustive && round < 2; ++round) {
           // ---- pass B: bounding box of the candidate texels (v >= T) -----------------------
           int txmin = W, txmax = -1, tymin = H, tymax = -1;
           const int nq = HW >> 2;
@@ -435,21 +449,27 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
           const int area = (bw > 0 && bh > 0) ? bw * bh : 0;
           if (area > 768 || area * 4 > HW) {
             exhaustive = true;
-          } else {
-            // ---- phase C: exact evaluation of every pixel that can touch a candidate ---------
-            rv = L; ri = Li;
-            int ci = lane / bw, cj = lane - ci * bw;          // (row, col) of this lane's first pixel in the box
-            const int di = 32 / bw, dj = 32 - di * bw;
-            for (int t = lane; t < area; t += 32, ci += di, cj += dj) {
-              if (cj >= bw) { cj -= bw; ++ci; }
-              const int i = imin + ci, jw = jmin + cj;
-              const float v = eval_px(s, X, i, jw);
-              const int k = i * W + (X.flip ? (W - 1 - jw) : jw);
-              if (arg_better(v, k, rv, ri)) { rv = v; ri = k; }
-            }
-            n_eval += area;
-            warp_argmax(rv, ri);
+            break;
           }
+          // ---- phase C: exact evaluation of every pixel that can touch a candidate ---------
+          rv = L; ri = Li;
+          int ci = lane / max(bw, 1), cj = lane - ci * bw;          // (row, col) of this lane's first pixel in the box
+          const int di = 32 / max(bw, 1), dj = 32 - di * bw;
+          for (int t = lane; t < area; t += 32, ci += di, cj += dj) {
+            if (cj >= bw) { cj -= bw; ++ci; }
+            const int i = imin + ci, jw = jmin + cj;
+            const float v = eval_px(s, X, i, jw);
+            const int k = i * W + (X.flip ? (W - 1 - jw) : jw);
+            if (arg_better(v, k, rv, ri)) { rv = v; ri = k; }
+          }
+          n_eval += area;
+          warp_argmax(rv, ri);
+          if (!provisional || round == 1) break;
+          L = rv; Li = ri;
+          const float Tf = L - fabsf(L) * kSlack;
+          if (L > -INFINITY && Tf >= T) break;              // the provisional candidate set was sufficient
+          if (!(L > -INFINITY) || !(Tf > 0.f)) { exhaustive = true; break; }
+          T = Tf;                                           // rare: repeat once with the true threshold
         }
       }
       if (exhaustive) {
@@ -492,10 +512,9 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
       if (p.out_xy) {
         float ox = hx, oy = hy;
         if (p.dec) {
-          const double* c = p.dec + (size_t)b * 4;
           // np.dot row: (a00*(x-1) + 0*(y-1)) + a02, astype(int) truncation, +1
-          const double tx = __dadd_rn(__dmul_rn(c[0], (double)hx - 1.0), c[1]);
-          const double ty = __dadd_rn(__dmul_rn(c[2], (double)hy - 1.0), c[3]);
+          const double tx = __dadd_rn(__dmul_rn(dc0, (double)hx - 1.0), dc1);
+          const double ty = __dadd_rn(__dmul_rn(dc2, (double)hy - 1.0), dc3);
           ox = (float)(trunc(tx) + 1.0);
           oy = (float)(trunc(ty) + 1.0);
         }
@@ -603,11 +622,11 @@ extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64
   if (warps > 16) warps = 16;
   if (warps < 1) warps = 1;
   p.nbuf = nbuf;
-  // "stream" (default when the maps are 16-byte aligned): no staging buffers, register-limited CTAs of 24
-  // warps; "smem": TMA-staged buffers, 14 warps for 64x64 maps.  UBPL_K1_MODE=smem|stream overrides.
+  // "smem" (default): TMA-staged buffers, 14 warps per CTA for 64x64 maps; "stream" (UBPL_K1_MODE=stream):
+  // no staging buffers, register-limited CTAs of 24 warps, next map prefetched into L2.
   static const char* env_mode = getenv("UBPL_K1_MODE");
-  bool stream_mode = p.use_bulk && (map_bytes % 16 == 0);
-  if (env_mode && env_mode[0] == 's' && env_mode[1] == 'm') stream_mode = false;
+  bool stream_mode = false;   // measured on B200: the TMA-staged buffers win (profiles/README.md)
+  if (env_mode && env_mode[0] == 's' && env_mode[1] == 't' && p.use_bulk && (map_bytes % 16 == 0)) stream_mode = true;
   p.work = work_counter((cudaStream_t)stream);
   if (!p.work) return UBPL_ERR_CUDA;
   if (stream_mode) {
