@@ -132,6 +132,13 @@ int ubpl_select_descend(const uint32_t* hist, int shift, uint64_t* prefix, int64
 int ubpl_select_apply(const double* reliability, int64_t n, int J, const uint64_t* prefix,
                       double reliableThr, uint8_t* enable, float* gate32, int32_t* counts,
                       double* thr_out, void* stream);
+/* The whole of steps 1-4 in one launch for the single-GPU case (no collective needed): k_rank =
+ * int((n-1)*reliablePCT) counted from the largest reliability; keys is uint64[n] scratch; ext_out
+ * (float64[2], optional) receives the raw extrema. */
+int ubpl_select_quantile_local(const double* dist, const double* legal, int64_t n, int J, int64_t k_rank,
+                               double reliableThr, double reliableDistMin, double* reliability,
+                               uint64_t* keys, uint8_t* enable, float* gate32, int32_t* counts,
+                               double* thr_out, double* ext_out, void* stream);
 /* Fixed rule: enable = legal && 1-exp(-dist/5) <= 1-exp(-3*distThrMax/5)
  * (BusinessUtils.pseudo_filter_mixUnc / _calUncValue, utils/business.py:237-261,375-376). */
 int ubpl_select_fixed(const double* dist, const double* legal, int64_t n, int J, double distThrMax,

@@ -244,10 +244,12 @@ def test_quantile_select_random(ops):
         legal = (rng.random(n) < 0.9).astype(np.float64)
         for pct, rthr in ((0.5, 0.0), (0.1, 0.0), (0.99, 0.0), (0.5, 0.8), (0.0, 0.0), (1.0, 0.0)):
             rel, thr, en = O.filter_dual(dist, legal, rthr, pct, 1.0)
-            s = ops.select_quantile(cu(dist), cu(legal), J, rthr, pct, 1.0)
-            assert float(s["thr"]) == thr, (n, pct)
-            assert np.array_equal(npy(s["enable"]).astype(bool), en)
-            assert np.array_equal(npy(s["reliability"]), rel)
+            for backend in (None, ops._CudaSelectBackend()):      # one-launch path, then the multi-kernel (multi-GPU) path
+                s = ops.select_quantile(cu(dist), cu(legal), J, rthr, pct, 1.0, backend=backend)
+                assert float(s["thr"]) == thr, (n, pct)
+                assert np.array_equal(npy(s["enable"]).astype(bool), en)
+                assert np.array_equal(npy(s["reliability"]), rel)
+                assert int(s["counts"][-1]) == int(en.sum())
 
 
 def test_select_fixed(ops):

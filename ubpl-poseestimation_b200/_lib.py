@@ -32,6 +32,8 @@ SIGNATURES = {
     "ubpl_key_histogram": [c_void_p, c_i64, c_void_p, c_int, c_void_p, c_void_p],
     "ubpl_select_descend": [c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "ubpl_select_apply": [c_void_p, c_i64, c_int, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ubpl_select_quantile_local": [c_void_p, c_void_p, c_i64, c_int, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_select_fixed": [c_void_p, c_void_p, c_i64, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_k2_view_fixed": [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_float, c_float, c_int,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

@@ -331,6 +331,77 @@ __global__ void coord_error_kernel(const double* __restrict__ pred, const float*
   acc[i] = (__ddiv_rn(e, norm) < pck_thr) ? 1 : 0;
 }
 
+// Single-GPU quantile selection in ONE launch (one CTA): extrema -> reliability -> exact k-th order
+// statistic (8 passes of 8 bits over the monotone keys, 256-bin shared-memory histogram) -> masks.
+// Same arithmetic as the multi-kernel path (ubpl_dist_extrema ... ubpl_select_apply), which remains the
+// multi-GPU path because the histograms must be all-reduced between the passes.
+__global__ void __launch_bounds__(1024) select_quantile_local_kernel(const double* __restrict__ dist,
+                                                                      const double* __restrict__ legal, long long n,
+                                                                      int J, long long k_rank, double reliableThr,
+                                                                      double reliableDistMin, double* rel,
+                                                                      uint64_t* keys, uint8_t* enable, float* gate32,
+                                                                      int32_t* counts, double* thr_out, double* ext_out) {
+  __shared__ unsigned long long s_ext[2];
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ long long s_krem;
+  const int t = threadIdx.x;
+  if (t == 0) { s_ext[0] = 0ull; s_ext[1] = (unsigned long long)__double_as_longlong(999.0); s_prefix = 0ull; s_krem = k_rank; }
+  for (int j = t; j <= J; j += blockDim.x) counts[j] = 0;
+  __syncthreads();
+  for (long long i = t; i < n; i += blockDim.x) {
+    const double e = dist[i];
+    if (e > 0.0 && e < 999.0) atomicMax(&s_ext[0], (unsigned long long)__double_as_longlong(e));
+    if (e >= 0.0 && e < 999.0) atomicMin(&s_ext[1], (unsigned long long)__double_as_longlong(e));
+  }
+  __syncthreads();
+  double dmax = __longlong_as_double((long long)s_ext[0]), dmin = __longlong_as_double((long long)s_ext[1]);
+  if (t == 0 && ext_out) { ext_out[0] = dmax; ext_out[1] = dmin; }
+  if (dmax == 0.0) dmax = 999.0;
+  if (dmin > reliableDistMin) dmin = reliableDistMin;
+  for (long long i = t; i < n; i += blockDim.x) {
+    const double e = dist[i];
+    const double e2 = (e != 999.0) ? e : dmax;
+    const double unc = (legal[i] > 0.0) ? __ddiv_rn(__dsub_rn(e2, dmin), __dsub_rn(dmax, dmin)) : 1.0;
+    const double r = __dsub_rn(1.0, unc);
+    rel[i] = r;
+    keys[i] = key_of(r);
+  }
+  __syncthreads();
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    if (t < 256) s_hist[t] = 0u;
+    __syncthreads();
+    const unsigned long long pf = s_prefix;
+    for (long long i = t; i < n; i += blockDim.x) {
+      const uint64_t k = keys[i];
+      if (shift == 56 || (k >> (shift + 8)) == (pf >> (shift + 8))) atomicAdd(&s_hist[(unsigned)((k >> shift) & 0xffu)], 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+      long long acc = 0, k = s_krem;
+      int bin = 0;
+      for (int b = 255; b >= 0; --b) {
+        const long long c = s_hist[b];
+        bin = b;
+        if (acc + c > k) break;
+        acc += c;
+      }
+      s_prefix = pf | ((unsigned long long)bin << shift);
+      s_krem = k - acc;
+    }
+    __syncthreads();
+  }
+  const double kth = value_of(s_prefix);
+  const double thr = (kth > reliableThr) ? kth : reliableThr;
+  if (t == 0 && thr_out) *thr_out = thr;
+  for (long long i = t; i < n; i += blockDim.x) {
+    const bool en = rel[i] > thr;
+    if (enable) enable[i] = en ? 1 : 0;
+    if (gate32) gate32[i] = en ? 1.f : 0.f;
+    if (en) { atomicAdd(counts + (int)(i % J), 1); atomicAdd(counts + J, 1); }
+  }
+}
+
 static inline int blocks_for(long long n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace ubpl
@@ -469,4 +540,16 @@ extern "C" int ubpl_coord_error(const double* pred, const float* gt, int gt_stri
   coord_error_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(pred, gt, gt_stride, n_sets, B, J, ref0, ref1,
                                                                           pck_thr, err, acc, T);
   return check_launch("ubpl_coord_error");
+}
+
+extern "C" int ubpl_select_quantile_local(const double* dist, const double* legal, int64_t n, int J, int64_t k_rank,
+                                          double reliableThr, double reliableDistMin, double* reliability,
+                                          uint64_t* keys, uint8_t* enable, float* gate32, int32_t* counts,
+                                          double* thr_out, double* ext_out, void* stream) {
+  UBPL_REQUIRE(dist && legal && reliability && keys && counts && (enable || gate32) && n >= 1 && J >= 1,
+               "ubpl_select_quantile_local: bad arguments");
+  UBPL_REQUIRE(k_rank >= 0 && k_rank < n, "ubpl_select_quantile_local: rank out of range");
+  select_quantile_local_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dist, legal, n, J, k_rank, reliableThr, reliableDistMin,
+                                                                      reliability, keys, enable, gate32, counts, thr_out, ext_out);
+  return check_launch("ubpl_select_quantile_local");
 }

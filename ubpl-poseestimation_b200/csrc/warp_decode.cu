@@ -251,6 +251,12 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
     nxt1 = claim();
     if (p.use_bulk && lane == 0 && nxt1 < N) bulk_prefetch_l2(map_ptr(nxt1), map_bytes);
   } else if (p.use_bulk && lane == 0 && nxt0 < N) issue_map(p, nxt0, buf0, &bars[0], pol, map_bytes);
+  if (!STREAM && NB == 1) {
+    // look-ahead without a second buffer: the map after the staged one is prefetched into L2 by the TMA
+    // engine while the current map is decoded, so its smem copy later sees L2 latency, not HBM latency
+    nxt1 = claim();
+    if (p.use_bulk && lane == 0 && nxt1 < N) bulk_prefetch_l2(map_ptr(nxt1), map_bytes);
+  }
   if (!STREAM && NB == 2) {
     nxt1 = claim();
     if (p.use_bulk && lane == 0 && nxt1 < N) issue_map(p, nxt1, buf0 + (buf_stride >> 2), &bars[1], pol, map_bytes);
@@ -331,15 +337,7 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
         const float kSlack = 1.9073486328125e-06f;   // 2^-19
         float T = 0.f;
         bool prune = false, solved = false;
-        // bv > 0: start from the PROVISIONAL threshold 0.875*bv (the warped peak of a smooth response is
-        // within a few percent of its best texel), evaluate the box of the texels above it, and accept if
-        // the exact maximum L found there satisfies L*(1-2^-19) >= 0.875*bv -- then every texel that could
-        // matter (>= L*(1-2^-19)) was inside the candidate set.  Otherwise repeat once with the true bound.
-        const bool provisional = bv > 0.f;
-        if (provisional) {
-          T = bv * 0.875f;
-          prune = true;
-        } else {
+        {
           // ---- phase L: lower bound from the pixels around the pre-image of the arg-max texel
           unsigned biy, bix;
           p.divW.divmod((unsigned)bi, biy, bix);
@@ -355,7 +353,13 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
           }
           n_eval += 30;
           warp_argmax(L, Li);
+          // Candidate threshold.  For a pixel whose four (zero-extended) corners are all < T the computed sample
+          // is < L: the fma chain rounds by at most 4 ulp of sum(w|v|), and negative corners lower the exact
+          // value by more than the rounding they add, so 2^-19 relative slack covers it.
           T = L - fabsf(L) * kSlack;
+          prune = (L > 0.f) && (T > 0.f);          // zero padding cannot be a candidate when T > 0
+        }
+        if (!prune) {
           // The warped maximum is not known to be positive (an all-negative map, or a map whose maximum is
           // exactly 0).  Along a row the computed ix and iy are monotone in the column (every rounding step
           // is monotone), so the row ends classify the whole frame:
@@ -396,7 +400,7 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
             exhaustive = true;
           }
         }
-        for (int round = 0; prune && !solved && !exhaustive && round < 2; ++round) {
+        if (prune && !solved && !exhaustive) {
           // ---- pass B: bounding box of the candidate texels (v >= T) -----------------------
           int txmin = W, txmax = -1, tymin = H, tymax = -1;
           const int nq = HW >> 2;
@@ -449,8 +453,7 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
           const int area = (bw > 0 && bh > 0) ? bw * bh : 0;
           if (area > 768 || area * 4 > HW) {
             exhaustive = true;
-            break;
-          }
+          } else {
           // ---- phase C: exact evaluation of every pixel that can touch a candidate ---------
           rv = L; ri = Li;
           int ci = lane / max(bw, 1), cj = lane - ci * bw;          // (row, col) of this lane's first pixel in the box
@@ -464,12 +467,7 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
           }
           n_eval += area;
           warp_argmax(rv, ri);
-          if (!provisional || round == 1) break;
-          L = rv; Li = ri;
-          const float Tf = L - fabsf(L) * kSlack;
-          if (L > -INFINITY && Tf >= T) break;              // the provisional candidate set was sufficient
-          if (!(L > -INFINITY) || !(Tf > 0.f)) { exhaustive = true; break; }
-          T = Tf;                                           // rare: repeat once with the true threshold
+          }
         }
       }
       if (exhaustive) {
@@ -526,6 +524,12 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
     if (STREAM) {
       nxt0 = nxt1; nxt1 = nn;
       if (p.use_bulk && lane == 0 && nn < N) bulk_prefetch_l2(map_ptr(nn), map_bytes);
+    } else if (NB == 1) {
+      nxt0 = nxt1; nxt1 = nn;                 // stage the map that was prefetched during this iteration ...
+      if (p.use_bulk && lane == 0) {
+        if (nxt0 < N) issue_map(p, nxt0, buf0, &bars[0], pol, map_bytes);
+        if (nn < N) bulk_prefetch_l2(map_ptr(nn), map_bytes);   // ... and pull the one after it towards L2
+      }
     } else {
       if (bsel) nxt1 = nn; else nxt0 = nn;
       if (p.use_bulk && lane == 0 && nn < N)

@@ -239,6 +239,21 @@ def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, g
         world = td.get_world_size(group)
     if n_total is None:
         n_total = n * world
+    if world == 1 and backend is None and 1 <= n <= (1 << 20):
+        # single GPU: extrema, reliability, radix select and masks in ONE launch
+        dev = dist.device
+        k = int((n - 1) * reliablePCT)
+        rel = torch.empty(n, dtype=_f64, device=dev)
+        keys = torch.empty(n, dtype=torch.int64, device=dev)
+        enable = torch.empty(n, dtype=torch.uint8, device=dev)
+        gate = torch.empty(n, dtype=_f32, device=dev)
+        counts = torch.empty(J + 1, dtype=torch.int32, device=dev)
+        thr = torch.empty(1, dtype=_f64, device=dev)
+        ext = torch.empty(2, dtype=_f64, device=dev)
+        _lib.call("ubpl_select_quantile_local", dist.data_ptr(), legal.data_ptr(), n, J, k, float(reliableThr),
+                  float(reliableDistMin), rel.data_ptr(), keys.data_ptr(), enable.data_ptr(), gate.data_ptr(),
+                  counts.data_ptr(), thr.data_ptr(), ext.data_ptr(), _stream())
+        return dict(reliability=rel, enable=enable, gate=gate, counts=counts, thr=thr, ext=ext)
     ext = be.extrema(dist)
     if world > 1:
         td.all_reduce(ext[0:1], op=td.ReduceOp.MAX, group=group)
