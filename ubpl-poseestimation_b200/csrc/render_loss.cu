@@ -75,7 +75,7 @@ __device__ __forceinline__ float gauss_px(const float* ex, const float* ey, int 
 
 // One WARP per (sample, joint): no block barriers; every lane keeps 8 independent 128-bit loads in
 // flight; the separable Gaussian factors live in a per-warp shared-memory slice.
-template <bool VEC>
+template <bool VEC, int SS>
 __global__ void __launch_bounds__(256, 3) render_mse_kernel(
     const float* __restrict__ kps, const float* __restrict__ gate_in, const float* __restrict__ sample_w,
     const float* __restrict__ pred, long long pB, long long pS, long long pJ, float* __restrict__ grad, long long gB,
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256, 3) render_mse_kernel(
   }
   const float inv_hw = 1.f / (float)HW;
   const long long BJ = (long long)B * J;
-  constexpr int U = 8;
+  constexpr int U = 8 / SS;
   for (long long item = (long long)blockIdx.x * wpb + warp; item < BJ; item += (long long)gridDim.x * wpb) {
     const int b = (int)(item / J), j = (int)(item % J);
     if (VEC && lane == 0) {
@@ -119,17 +119,27 @@ __global__ void __launch_bounds__(256, 3) render_mse_kernel(
     const float rad = 3.05f * sigma + 1.f;
     const int xlo = (int)floorf((float)g.cx - rad), xhi = (int)ceilf((float)g.cx + rad);
     const int ylo = (int)floorf((float)g.cy - rad), yhi = (int)ceilf((float)g.cy + rad);
-    for (int st = 0; st < S; ++st) {
-      const float* p = pred + (long long)b * pB + (long long)st * pS + (long long)j * pJ;
-      float* gr = grad ? grad + (long long)b * gB + (long long)st * gS + (long long)j * gJ : nullptr;
-      float* tg = (target && st == 0) ? target + item * HW : nullptr;
-      float sse = 0.f;
-      for (int q0 = lane; q0 < nq; q0 += 32 * U) {
-        float4 pv[U];
+    // SS stacks are streamed together so that the target texels are computed once per float4 and shared
+    for (int st0 = 0; st0 < S; st0 += SS) {
+      const float* p[SS];
+      float* gr[SS];
+      float sse[SS];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int q = q0 + 32 * u;
-          if (q < nq) pv[u] = load4(p, q, HW, VEC);
+      for (int ss = 0; ss < SS; ++ss) {
+        p[ss] = pred + (long long)b * pB + (long long)(st0 + ss) * pS + (long long)j * pJ;
+        gr[ss] = grad ? grad + (long long)b * gB + (long long)(st0 + ss) * gS + (long long)j * gJ : nullptr;
+        sse[ss] = 0.f;
+      }
+      float* tg = (target && st0 == 0) ? target + item * HW : nullptr;
+      for (int q0 = lane; q0 < nq; q0 += 32 * U) {
+        float4 pv[SS][U];
+#pragma unroll
+        for (int ss = 0; ss < SS; ++ss) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int q = q0 + 32 * u;
+            if (q < nq) pv[ss][u] = load4(p[ss], q, HW, VEC);
+          }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -156,18 +166,27 @@ __global__ void __launch_bounds__(256, 3) render_mse_kernel(
               tt[c] = gauss_px(ex, ey, kk % W, kk / W, g, sigma);
             }
             t = make_float4(tt[0], tt[1], tt[2], tt[3]);
-            if (k + 1 >= HW) pv[u].y = t.y;              // padded lanes contribute zero error
-            if (k + 2 >= HW) pv[u].z = t.z;
-            if (k + 3 >= HW) pv[u].w = t.w;
           }
-          const float4 d = make_float4(pv[u].x - t.x, pv[u].y - t.y, pv[u].z - t.z, pv[u].w - t.w);
-          sse += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
-          if (gr) store4(gr, q, HW, VEC, make_float4(gcoef * d.x, gcoef * d.y, gcoef * d.z, gcoef * d.w));
+#pragma unroll
+          for (int ss = 0; ss < SS; ++ss) {
+            float4 v = pv[ss][u];
+            if (!VEC) {                                  // padded lanes contribute zero error
+              if (k + 1 >= HW) v.y = t.y;
+              if (k + 2 >= HW) v.z = t.z;
+              if (k + 3 >= HW) v.w = t.w;
+            }
+            const float4 d = make_float4(v.x - t.x, v.y - t.y, v.z - t.z, v.w - t.w);
+            sse[ss] += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+            if (gr[ss]) store4(gr[ss], q, HW, VEC, make_float4(gcoef * d.x, gcoef * d.y, gcoef * d.z, gcoef * d.w));
+          }
           if (tg) store4(tg, q, HW, VEC, t);
         }
       }
-      const float tot = warp_sum(sse);
-      if (lane == 0 && per_loss) per_loss[((long long)b * S + st) * J + j] = ((tot * inv_hw) * gate) * wb;
+#pragma unroll
+      for (int ss = 0; ss < SS; ++ss) {
+        const float tot = warp_sum(sse[ss]);
+        if (lane == 0 && per_loss) per_loss[((long long)b * S + st0 + ss) * J + j] = ((tot * inv_hw) * gate) * wb;
+      }
     }
   }
 }
@@ -376,14 +395,16 @@ extern "C" int ubpl_render_mse(const float* kps, const float* gate_in, const flo
   const long long need = (BJ + wpb - 1) / wpb;
   const long long cap = (long long)sm_count() * 8;
   const int grid = (int)(need < cap ? need : cap);
-  if (vec)
-    render_mse_kernel<true><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS,
-                                                                            gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma,
-                                                                            grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4);
-  else
-    render_mse_kernel<false><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS,
-                                                                             gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma,
-                                                                             grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4);
+#define UBPL_LAUNCH_RENDER(V, SSV)                                                                                     \
+  render_mse_kernel<V, SSV><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(                                         \
+      kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS, gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
+      grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4)
+  if (vec) {
+    if (S % 2 == 0) UBPL_LAUNCH_RENDER(true, 2); else UBPL_LAUNCH_RENDER(true, 1);
+  } else {
+    if (S % 2 == 0) UBPL_LAUNCH_RENDER(false, 2); else UBPL_LAUNCH_RENDER(false, 1);
+  }
+#undef UBPL_LAUNCH_RENDER
   return check_launch("ubpl_render_mse");
 }
 

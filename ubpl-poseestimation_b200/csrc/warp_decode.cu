@@ -251,12 +251,6 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
     nxt1 = claim();
     if (p.use_bulk && lane == 0 && nxt1 < N) bulk_prefetch_l2(map_ptr(nxt1), map_bytes);
   } else if (p.use_bulk && lane == 0 && nxt0 < N) issue_map(p, nxt0, buf0, &bars[0], pol, map_bytes);
-  if (!STREAM && NB == 1) {
-    // look-ahead without a second buffer: the map after the staged one is prefetched into L2 by the TMA
-    // engine while the current map is decoded, so its smem copy later sees L2 latency, not HBM latency
-    nxt1 = claim();
-    if (p.use_bulk && lane == 0 && nxt1 < N) bulk_prefetch_l2(map_ptr(nxt1), map_bytes);
-  }
   if (!STREAM && NB == 2) {
     nxt1 = claim();
     if (p.use_bulk && lane == 0 && nxt1 < N) issue_map(p, nxt1, buf0 + (buf_stride >> 2), &bars[1], pol, map_bytes);
@@ -524,12 +518,6 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
     if (STREAM) {
       nxt0 = nxt1; nxt1 = nn;
       if (p.use_bulk && lane == 0 && nn < N) bulk_prefetch_l2(map_ptr(nn), map_bytes);
-    } else if (NB == 1) {
-      nxt0 = nxt1; nxt1 = nn;                 // stage the map that was prefetched during this iteration ...
-      if (p.use_bulk && lane == 0) {
-        if (nxt0 < N) issue_map(p, nxt0, buf0, &bars[0], pol, map_bytes);
-        if (nn < N) bulk_prefetch_l2(map_ptr(nn), map_bytes);   // ... and pull the one after it towards L2
-      }
     } else {
       if (bsel) nxt1 = nn; else nxt0 = nn;
       if (p.use_bulk && lane == 0 && nn < N)

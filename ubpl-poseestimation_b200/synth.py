@@ -47,10 +47,15 @@ def canonical_to_view(cx, cy, theta, flip, H, W):
 
 
 def make_batch(B, K, J, H=64, W=64, M=1, S=2, seed=1388, rank=0, device="cpu",
-               neg_frac=0.05, jitter=1.5, noise=0.02, chunk=64):
+               neg_frac=0.05, jitter=1.5, noise=0.02, chunk=64, noise_only_frac=0.2):
     """Returns a dict with teacher[M,K,B,J,H,W], student[B,S,J,H,W], theta[K,B,2,3],
     flip[K,B] (bool), center[B,2] (int64), scale[B] (float32), islabeled[B] (bool; the LAST B/2
-    rows are labeled, utils/mt/data.py:121-129), base_xy[B,J,2]."""
+    rows are labeled, utils/mt/data.py:121-129), base_xy[B,J,2].
+
+    neg_frac of the teacher maps are all-negative (they exercise the max <= 0 mask of
+    utils/udaap/evaluation.py:27-29): most of them are weak responses -- the same smooth blob shifted
+    below zero, which is what a heat-map head emits for a low-confidence joint -- and a share
+    noise_only_frac of them is pure negative noise (no structure at all; the decoder's worst case)."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed + rank)
     theta, flip, _ = make_warpmats(K, B, gen, device)
@@ -70,7 +75,10 @@ def make_batch(B, K, J, H=64, W=64, M=1, S=2, seed=1388, rank=0, device="cpu",
         t = _blobs(qx, qy, amp, H, W, device)
         nz = torch.randn(M, K, nb, J, H, W, generator=gen, device=device) * noise
         neg = torch.rand(M, K, nb, J, generator=gen, device=device) < neg_frac
-        t = torch.where(neg[..., None, None], -(nz.abs() + 1e-3), t + nz)
+        noise_only = torch.rand(M, K, nb, J, generator=gen, device=device) < noise_only_frac
+        weak = t + nz - (amp[..., None, None] + 0.2)                    # max = amp + noise - amp - 0.2 < 0
+        negmap = torch.where(noise_only[..., None, None], -(nz.abs() + 1e-3), weak)
+        t = torch.where(neg[..., None, None], negmap, t + nz)
         teacher[:, :, b0:b1] = t
         sj = torch.randn(nb, S, J, 2, generator=gen, device=device) * jitter
         samp = 0.5 + 0.6 * torch.rand(nb, S, J, generator=gen, device=device)
