@@ -382,6 +382,31 @@ def test_pipeline_vs_oracle(ops, M, select, fuse):
     np.testing.assert_allclose(npy(r["grad"]), o["grad"], rtol=RTOL, atol=1e-10)
 
 
+def test_graphed_step_matches_eager(ops):
+    """The CUDA-graph capture of the chain (what bench.py times) gives bit-identical outputs and follows
+    new inputs copied into its bound buffers."""
+    from ubpl_b200 import synth, pipeline
+    d = synth.make_batch(B=8, K=4, J=6, M=1, S=2, seed=5, jitter=0.5, device="cuda")
+    d2 = synth.make_batch(B=8, K=4, J=6, M=1, S=2, seed=6, jitter=0.5, device="cuda")
+    dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64])
+    w = pipeline.nega_weights(d["islabeled"], 1.0)
+    cfg = pipeline.StepConfig(select="fixed", distThrMax=2.0)
+    e = torch.randn(1000, device="cuda"); p = torch.randn(1000, device="cuda")
+    plan = ops.EmaPlan([p], [e])
+    bufs = {k: d[k].clone() for k in ("teacher", "student", "theta", "flip")}
+    g = pipeline.GraphedStep(bufs["teacher"], bufs["student"], bufs["theta"], bufs["flip"], dec, w, cfg, ema=plan, alpha=0.5)
+    for data in (d, d2):
+        for k in ("teacher", "student", "theta"):
+            g.state[k].copy_(data[k])
+        g.state["flip"].copy_(data["flip"].to(torch.uint8))
+        e_before = e.clone()
+        st = g.run()
+        ref = pipeline.pseudo_label_step(data["teacher"], data["student"], data["theta"], data["flip"], dec, w, cfg)
+        for k in ("idx", "max", "xy", "enable", "gate", "grad", "target", "summary", "grad_scale", "count"):
+            assert torch.equal(st[k], ref[k]), k
+        assert torch.equal(e, torch.addcmul(e_before * 0.5, p, torch.full_like(p, 0.5)).float()) or torch.allclose(e, 0.5 * e_before + 0.5 * p, rtol=1e-6)
+
+
 def test_full_size_properties(ops):
     """BASELINE config 2 sizes (B=256, K=8, J=14, 64x64): size-independent properties."""
     from ubpl_b200 import synth, pipeline

@@ -40,72 +40,146 @@ def nega_weights(islabeled, pseudoWeight):
                        torch.full((), float(pseudoWeight), device=islabeled.device)).to(torch.float32)
 
 
+def stage_k1(st, stats=None):
+    """K1: back-warp + flip + arg-max decode of every (model, view) map, each read from HBM once."""
+    teacher, theta, flip, dec = st["teacher"], st["theta"], st["flip"], st["dec"]
+    M, K, B, J, H, W = teacher.shape
+    if teacher.stride(0) == K * teacher.stride(1):
+        dec_out = ops.warp_decode(teacher.view(M * K, B, J, H, W) if teacher.is_contiguous() else
+                                  teacher.as_strided((M * K, B, J, H, W), (teacher.stride(1),) + tuple(teacher.stride()[2:])),
+                                  theta.unsqueeze(0).expand(M, K, B, 2, 3).reshape(M * K, B, 2, 3),
+                                  flip.unsqueeze(0).expand(M, K, B).reshape(M * K, B), dec, stats=stats, want_idx=True)
+        st["xy"] = dec_out["xy"].view(M, K, B, J, 2)
+        st["max"] = dec_out["max"].view(M, K, B, J)
+        st["idx"] = dec_out["idx"].view(M, K, B, J)
+    else:
+        outs = [ops.warp_decode(teacher[m], theta, flip, dec, stats=stats) for m in range(M)]
+        st["xy"] = torch.stack([o["xy"] for o in outs])
+        st["max"] = torch.stack([o["max"] for o in outs])
+        st["idx"] = torch.stack([o["idx"] for o in outs])
+    return st
+
+
+def stage_k2(st, cfg, group=None):
+    """K2: per-joint dispersion -> selection mask -> visibility gate and open-gate count."""
+    xy = st["xy"]
+    M, K, B, J, _ = xy.shape
+    S = st["student"].shape[1]
+    H, W = st["student"].shape[-2:]
+    stride = cfg.stride
+    img_h, img_w = int(H * stride), int(W * stride)
+    if cfg.fuse_k2 and M == 1 and cfg.select == "fixed":
+        k2 = ops.k2_view_fixed(xy[0], cfg.distThrMax, S, img_h, img_w, stride, cfg.sigma)
+        st.update(kps=k2["mean"], dist=k2["dist"], legal=k2["legal"], gate=k2["gate"], grad_scale=None,
+                  count=k2["count"], enable=k2["enable"], counts=k2["counts"])
+        return st
+    if M == 1:
+        vd = ops.view_dispersion(xy[0], sentinel_illegal=True)
+        kps, dist, legal = vd["mean"], vd["dist"], vd["legal"]
+        st.update(unc32=vd["unc32"], max_bits=vd["max_bits"])
+    elif M == 2:
+        vd1, vd2 = ops.view_dispersion(xy[0]), ops.view_dispersion(xy[1])
+        ad = ops.assess_dual(vd1["mean"], vd2["mean"], None, xy[0], xy[1])
+        kps, dist, legal = ad["coord32"], ad["extDist"], ad["legal"]
+        st.update(assess=ad)
+    else:
+        raise ValueError("pseudo_label_step supports M = 1 (mean teacher) or M = 2 (dual teachers)")
+    if cfg.select == "fixed":
+        sel = ops.select_fixed(dist, legal, J, cfg.distThrMax)
+    elif cfg.select == "quantile":
+        sel = ops.select_quantile(dist, legal, J, cfg.reliableThr, cfg.reliablePCT, cfg.reliableDistMin, group=group)
+    else:
+        raise ValueError("select must be 'fixed' or 'quantile'")
+    gate, grad_scale, count = ops.gate_prepare(kps, sel["gate"], S, img_h, img_w, stride, cfg.sigma, cfg.lossWeight)
+    st.update(kps=kps, dist=dist, legal=legal, gate=gate, grad_scale=grad_scale, count=count, enable=sel["enable"],
+              counts=sel["counts"], sel=sel)
+    return st
+
+
+def stage_k3(st, cfg):
+    """K3: Gaussian target render + masked joint-MSE forward + gradient in one pass, then the loss reduction."""
+    student = st["student"]
+    B, S, J, H, W = student.shape
+    stride = cfg.stride
+    img_h, img_w = int(H * stride), int(W * stride)
+    gs = st["grad_scale"]
+    r = ops.render_mse(st["kps"], st["gate"], st["sample_w"], student, img_h, img_w, stride, cfg.sigma, grad_scale=gs,
+                       want_grad=cfg.want_grad, want_target=cfg.want_target,
+                       count_in=st["count"] if gs is None else None, loss_weight=cfg.lossWeight)
+    if gs is None:
+        st["grad_scale"] = r["grad_scale"]
+    st["gate"] = st["gate"].view(B, J)
+    st["enable"] = st["enable"].view(B, J)
+    st["summary"] = ops.loss_finalize(r["per_loss"], None, st["gate"])
+    st.update(grad=r["grad"], target=r["target"], per_loss=r["per_loss"])
+    return st
+
+
 def pseudo_label_step(teacher, student, theta, flip, dec, sample_w, cfg: StepConfig, group=None, stats=None,
                       timer=None):
     """teacher [M,K,B,J,H,W] (last-stack teacher maps of the K augmented views), student
     [B,S,J,H,W], theta [K,B,2,3], flip [K,B], dec [B,4] (ops.decode_coeffs), sample_w [B].
     Returns a dict of DEVICE tensors: summary float64[4] = (loss_sum, #loss>0, #mask>0, #gate>0),
     grad_scale, count, grad, target, gate, kps, enable, dist, decode outputs.  The scalar loss of
-    MT_UBPL.py:266 is summary[0] * grad_scale."""
-    M, K, B, J, H, W = teacher.shape
-    S = student.shape[1]
-    stride = cfg.stride
-    img_h, img_w = int(H * stride), int(W * stride)
-    mark = timer if timer is not None else (lambda name: None)   # bench.py records CUDA events at stage edges
-    # ---- K1: every (model, view) map read once ---------------------------------------------------
+    MT_UBPL.py:266 is summary[0] * grad_scale.  No host synchronisation anywhere."""
+    mark = timer if timer is not None else (lambda name: None)
+    st = dict(teacher=teacher, student=student, theta=theta, flip=flip, dec=dec, sample_w=sample_w)
     mark("k1_0")
-    if teacher.stride(0) == K * teacher.stride(1):
-        dec_out = ops.warp_decode(teacher.view(M * K, B, J, H, W) if teacher.is_contiguous() else
-                                  teacher.as_strided((M * K, B, J, H, W), (teacher.stride(1),) + tuple(teacher.stride()[2:])),
-                                  theta.unsqueeze(0).expand(M, K, B, 2, 3).reshape(M * K, B, 2, 3),
-                                  flip.unsqueeze(0).expand(M, K, B).reshape(M * K, B), dec, stats=stats, want_idx=True)
-        xy = dec_out["xy"].view(M, K, B, J, 2)
-        mx = dec_out["max"].view(M, K, B, J)
-        idx = dec_out["idx"].view(M, K, B, J)
-    else:
-        outs = [ops.warp_decode(teacher[m], theta, flip, dec, stats=stats) for m in range(M)]
-        xy = torch.stack([o["xy"] for o in outs])
-        mx = torch.stack([o["max"] for o in outs])
-        idx = torch.stack([o["idx"] for o in outs])
+    stage_k1(st, stats)
     mark("k1_1")
-    # ---- K2: dispersion + selection ----------------------------------------------------------------
-    fused_k2 = (cfg.fuse_k2 and M == 1 and cfg.select == "fixed" and B * J <= 65536)
-    if fused_k2:
-        k2 = ops.k2_view_fixed(xy[0], cfg.distThrMax, S, img_h, img_w, stride, cfg.sigma)
-        kps, dist, legal = k2["mean"], k2["dist"], k2["legal"]
-        gate, grad_scale, count = k2["gate"], None, k2["count"]
-        sel = dict(enable=k2["enable"], counts=k2["counts"])
-        extra = {}
-    else:
-        if M == 1:
-            vd = ops.view_dispersion(xy[0], sentinel_illegal=True)
-            kps, dist, legal = vd["mean"], vd["dist"], vd["legal"]
-            extra = dict(unc32=vd["unc32"], max_bits=vd["max_bits"])
-        elif M == 2:
-            vd1, vd2 = ops.view_dispersion(xy[0]), ops.view_dispersion(xy[1])
-            ad = ops.assess_dual(vd1["mean"], vd2["mean"], None, xy[0], xy[1])
-            kps, dist, legal = ad["coord32"], ad["extDist"], ad["legal"]
-            extra = dict(assess=ad)
-        else:
-            raise ValueError("pseudo_label_step supports M = 1 (mean teacher) or M = 2 (dual teachers)")
-        if cfg.select == "fixed":
-            sel = ops.select_fixed(dist, legal, J, cfg.distThrMax)
-        elif cfg.select == "quantile":
-            sel = ops.select_quantile(dist, legal, J, cfg.reliableThr, cfg.reliablePCT, cfg.reliableDistMin, group=group)
-        else:
-            raise ValueError("select must be 'fixed' or 'quantile'")
-        # ---- K3: render + masked MSE forward/backward ----------------------------------------------
-        gate, grad_scale, count = ops.gate_prepare(kps, sel["gate"], S, img_h, img_w, stride, cfg.sigma, cfg.lossWeight)
+    stage_k2(st, cfg, group)
     mark("k3_0")
-    r = ops.render_mse(kps, gate, sample_w, student, img_h, img_w, stride, cfg.sigma, grad_scale=grad_scale,
-                       want_grad=cfg.want_grad, want_target=cfg.want_target,
-                       count_in=count if grad_scale is None else None, loss_weight=cfg.lossWeight)
-    if grad_scale is None:
-        grad_scale = r["grad_scale"]
+    stage_k3(st, cfg)
     mark("k3_1")
-    summary = ops.loss_finalize(r["per_loss"], None, gate.view(B, J))
-    out = dict(summary=summary, grad_scale=grad_scale, count=count, grad=r["grad"], target=r["target"],
-               gate=gate.view(B, J), kps=kps, enable=sel["enable"].view(B, J), counts=sel["counts"], dist=dist,
-               legal=legal, xy=xy, max=mx, idx=idx, per_loss=r["per_loss"], sel=sel)
-    out.update(extra)
-    return out
+    return st
+
+
+class GraphedStep:
+    """The same chain captured into CUDA graphs, one per stage, for fixed shapes and fixed input
+    buffers: a step is then four graph launches instead of ~12 kernel launches plus allocator and
+    Python work, which matters because one step is only ~0.2 ms of GPU time.  Inputs are read from the
+    tensors given here (copy new batches into them); outputs live in `self.state`.
+    `ema` is an optional ops.EmaPlan whose update (K4) becomes the fourth graph."""
+
+    def __init__(self, teacher, student, theta, flip, dec, sample_w, cfg: StepConfig, group=None, stats=None,
+                 ema=None, alpha=None, warmup=3):
+        self.cfg, self.group, self.ema, self.alpha = cfg, group, ema, alpha
+        self.state = dict(teacher=teacher, student=student, theta=theta, flip=flip.to(torch.uint8), dec=dec,
+                          sample_w=sample_w)
+        self.graphs = {}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # first-call initialisation must not be captured
+                self._eager(stats)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        pool = None
+        for name, fn in (("k1", lambda: stage_k1(self.state, stats)), ("k2", lambda: stage_k2(self.state, cfg, group)),
+                         ("k3", lambda: stage_k3(self.state, cfg)), ("k4", self._ema)):
+            if name == "k4" and ema is None:
+                continue
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                fn()
+            pool = g.pool()
+            self.graphs[name] = g
+        self.order = [n for n in ("k1", "k2", "k3", "k4") if n in self.graphs]
+
+    def _ema(self):
+        self.ema.step(self.alpha)
+
+    def _eager(self, stats):
+        stage_k1(self.state, stats)
+        stage_k2(self.state, self.cfg, self.group)
+        stage_k3(self.state, self.cfg)
+        if self.ema is not None:
+            self._ema()
+
+    def run(self, timer=None):
+        mark = timer if timer is not None else (lambda name: None)
+        for n in self.order:
+            mark(n + "_0")
+            self.graphs[n].replay()
+            mark(n + "_1")
+        return self.state
