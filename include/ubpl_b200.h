@@ -54,13 +54,16 @@ int ubpl_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_opti
  *         coordinates after the max<=0 mask and the optional refinement); any may be NULL.
  * stats   optional int64[4] device counters, incremented: [0] maps decoded by exhaustive
  *         evaluation, [1] output pixels evaluated, [2] maps, [3] reserved.
+ * slow_ws optional int32[V*B*J + 1] device scratch: with it, the (rare) maps that need the exhaustive
+ *         decode are queued and decoded by whole CTAs in a second kernel launched right after the first
+ *         (better tail); NULL decodes them in place.
  */
 int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
                      int V, int B, int J, int H, int W,
                      const float* theta, const uint8_t* flip, const double* dec,
                      int do_warp, int refine,
                      int32_t* out_idx, float* out_max, float* out_xy, float* out_hm_xy,
-                     int64_t* stats, void* stream);
+                     int64_t* stats, int32_t* slow_ws, void* stream);
 
 /* Materialises the back-warped (and un-flipped) maps: the tensor AugmentUtils.affine_back2
  * returns (utils/augment.py:37-47).  in [N, C, H, W] strides (sN, sC); out likewise (oN, oC);

@@ -19,7 +19,7 @@ SIGNATURES = {
     "ubpl_device_info": [c_void_p] * 4,
     "ubpl_warp_decode": [c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
                          c_void_p, c_void_p, c_void_p, c_int, c_int,
-                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_warp_materialize": [c_void_p, c_i64, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p],
     "ubpl_view_dispersion": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
@@ -88,7 +88,7 @@ def lib():
 
 
 # kernels launched per successful call (cudaMemsetAsync is not counted); bench.py's gpu_launches
-LAUNCHES = {"ubpl_dist_extrema": 2}
+LAUNCHES = {"ubpl_dist_extrema": 2, "ubpl_warp_decode": 2}
 _launches = 0
 
 

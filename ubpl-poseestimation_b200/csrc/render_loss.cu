@@ -76,7 +76,7 @@ __device__ __forceinline__ float gauss_px(const float* ex, const float* ey, int 
 // One WARP per (sample, joint): no block barriers; every lane keeps 8 independent 128-bit loads in
 // flight; the separable Gaussian factors live in a per-warp shared-memory slice.
 template <bool VEC, int SS>
-__global__ void __launch_bounds__(256, 3) render_mse_kernel(
+__global__ void __launch_bounds__(128, 6) render_mse_kernel(
     const float* __restrict__ kps, const float* __restrict__ gate_in, const float* __restrict__ sample_w,
     const float* __restrict__ pred, long long pB, long long pS, long long pJ, float* __restrict__ grad, long long gB,
     long long gS, long long gJ, float* __restrict__ target, int B, int S, int J, int H, int W, int img_h, int img_w,
@@ -389,11 +389,11 @@ extern "C" int ubpl_render_mse(const float* kps, const float* gate_in, const flo
   if (target) vec = vec && aligned16(target) && (HW % 4 == 0);
   FastDiv divW4;
   divW4.init((unsigned)(W >= 4 ? W / 4 : 1));
-  const int wpb = 8;
+  const int wpb = 4;    // small CTAs: one (b,j) item per warp, finer-grained tail
   const size_t smem = (size_t)wpb * (W + H) * sizeof(float);
   UBPL_REQUIRE(smem <= 48 * 1024, "ubpl_render_mse: heat-map sides too large (%d x %d)", H, W);
   const long long need = (BJ + wpb - 1) / wpb;
-  const long long cap = (long long)sm_count() * 8;
+  const long long cap = (long long)sm_count() * 16;
   const int grid = (int)(need < cap ? need : cap);
 #define UBPL_LAUNCH_RENDER(V, SSV)                                                                                     \
   render_mse_kernel<V, SSV><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(                                         \

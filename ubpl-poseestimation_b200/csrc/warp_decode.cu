@@ -49,6 +49,8 @@ struct WDParams {
   float* out_hm_xy;
   unsigned long long* stats;
   unsigned long long* work;   // global claim counter (zeroed before the launch)
+  int* slow_list;             // [V*B*J] queue of maps left to the exhaustive kernel (NULL: decode in place)
+  unsigned* slow_count;
 };
 
 struct Xform {
@@ -121,14 +123,16 @@ __device__ __forceinline__ void grid_consts(Xform& X, int H, int W) {
 // affine grid are hoisted), so the tie rule is carried by arg_better's index comparison.
 __device__ __noinline__ void decode_exhaustive(const float* __restrict__ s, float t00, float t01, float t02, float t10,
                                                float t11, float t12, float stepx, float stepy, float sfx, float sfy,
-                                               int H, int W, bool flip, int lane, float& bv, int& bi) {
+                                               int H, int W, bool flip, int lane, float& bv, int& bi, int row0 = 0,
+                                               int row1 = -1) {
   bv = -INFINITY;
   bi = 0x7fffffff;
+  if (row1 < 0) row1 = H;
   for (int jo = lane; jo < W; jo += 32) {
     const int jw = flip ? (W - 1 - jo) : jo;
     const float xl = lin_coord(jw, W, stepx);
     const float ax = __fmul_rn(xl, t00), ay = __fmul_rn(xl, t10);
-    for (int i = 0; i < H; ++i) {
+    for (int i = row0; i < row1; ++i) {
       const float yl = lin_coord(i, H, stepy);
       const float gx = __fadd_rn(__fmaf_rn(yl, t01, ax), t02);
       const float gy = __fadd_rn(__fmaf_rn(yl, t11, ay), t12);
@@ -204,6 +208,54 @@ __device__ __forceinline__ void issue_map(const WDParams& p, long long n, float*
   const float* src = p.maps + (long long)v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
   mbar_arrive_expect_tx(bar, bytes);
   bulk_g2s(dst, src, bytes, bar, pol);
+}
+
+// Epilogue of one map (warp-wide call): arg-max -> heat-map coordinates (mask, optional quarter-offset
+// refinement) -> image-space coordinates -> outputs.
+__device__ __forceinline__ void finish_map(const WDParams& p, long long n, int j, const float* s, const Xform& X,
+                                           float rv, int ri, double dc0, double dc1, double dc2, double dc3, int lane) {
+  const int H = p.H, W = p.W;
+  unsigned ayu, axu;
+  p.divW.divmod((unsigned)ri & 0x7fffffffu, ayu, axu);
+  const int ax = (int)axu, ay = (int)ayu;             // 0-based arg-max, canonical frame
+  float hx = 0.f, hy = 0.f;
+  const bool keep = rv > 0.f;                          // maxval.gt(0): NaN -> masked
+  if (keep) { hx = (float)(ax + 1); hy = (float)(ay + 1); }
+  const bool do_ref = (p.refine == 2) || (p.refine == 1 && j < 2);
+  if (do_ref) {
+    // process.py:366-371: 1 < px < res[0] and 1 < py < res[1] on the 1-based coordinates
+    if (keep && ax >= 1 && ax <= W - 2 && ay >= 1 && ay <= H - 2) {
+      float nb = 0.f;
+      if (lane < 4) {
+        const int di = (lane == 2) ? 1 : (lane == 3 ? -1 : 0);
+        const int dj = (lane == 0) ? 1 : (lane == 1 ? -1 : 0);
+        const int i = ay + di, jo = ax + dj;
+        nb = p.do_warp ? eval_px(s, X, i, X.flip ? (W - 1 - jo) : jo) : s[i * W + jo];
+      }
+      const float xp = __shfl_sync(0xffffffffu, nb, 0), xm = __shfl_sync(0xffffffffu, nb, 1);
+      const float yp = __shfl_sync(0xffffffffu, nb, 2), ym = __shfl_sync(0xffffffffu, nb, 3);
+      const float dx = xp - xm, dy = yp - ym;
+      hx += (dx > 0.f) ? 0.25f : ((dx < 0.f) ? -0.25f : 0.f);
+      hy += (dy > 0.f) ? 0.25f : ((dy < 0.f) ? -0.25f : 0.f);
+    }
+  }
+  if (p.refine != 0) { hx += 0.5f; hy += 0.5f; }      // process.py:372 (+0.5 for every joint)
+  if (lane == 0) {
+    if (p.out_idx) p.out_idx[n] = ri;
+    if (p.out_max) p.out_max[n] = rv;
+    if (p.out_hm_xy) { p.out_hm_xy[2 * n] = hx; p.out_hm_xy[2 * n + 1] = hy; }
+    if (p.out_xy) {
+      float ox = hx, oy = hy;
+      if (p.dec) {
+        // np.dot row: (a00*(x-1) + 0*(y-1)) + a02, astype(int) truncation, +1
+        const double tx = __dadd_rn(__dmul_rn(dc0, (double)hx - 1.0), dc1);
+        const double ty = __dadd_rn(__dmul_rn(dc2, (double)hy - 1.0), dc3);
+        ox = (float)(trunc(tx) + 1.0);
+        oy = (float)(trunc(ty) + 1.0);
+      }
+      p.out_xy[2 * n] = ox; p.out_xy[2 * n + 1] = oy;
+    }
+  }
 }
 
 // STREAM = false: every warp stages its map in shared memory with a 1-D bulk async copy (TMA engine).
@@ -317,6 +369,7 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
     // NaN -> mn is NaN; -inf -> mn == -inf; +inf -> bv == +inf
     const bool nonfinite = __any_sync(0xffffffffu, !(mn >= -FLT_MAX) || !(bv <= FLT_MAX));
     float rv = bv; int ri = bi;           // result (value, canonical flat index)
+    bool deferred = false;
     if (!p.do_warp) {
       if (nonfinite) {                    // torch.max: the first NaN wins; +-Inf compare normally
         rv = -INFINITY; ri = 0x7fffffff;
@@ -464,55 +517,21 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
           }
         }
       }
-      if (exhaustive) {
+      if (exhaustive && p.slow_list) {
+        // Maps that need the exhaustive decode are not decoded here: one such map would keep this warp busy
+        // for ~25 us while the rest of the grid drains.  They are queued and decoded right after this kernel
+        // by whole CTAs (warp_decode_slow_kernel), four warps per map.
+        if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = (int)n;
+        deferred = true;
+        ++n_slow;
+      } else if (exhaustive) {
         decode_exhaustive(s, X.t00, X.t01, X.t02, X.t10, X.t11, X.t12, X.stepx, X.stepy, X.sfx, X.sfy, H, W, X.flip, lane, rv, ri);
         ++n_slow;
         n_eval += HW;
       }
     }
 
-    // ---- epilogue: coordinates -------------------------------------------------------------
-    unsigned ayu, axu;
-    p.divW.divmod((unsigned)ri & 0x7fffffffu, ayu, axu);
-    const int ax = (int)axu, ay = (int)ayu;             // 0-based arg-max, canonical frame
-    float hx = 0.f, hy = 0.f;
-    const bool keep = rv > 0.f;                          // maxval.gt(0): NaN -> masked
-    if (keep) { hx = (float)(ax + 1); hy = (float)(ay + 1); }
-    const bool do_ref = (p.refine == 2) || (p.refine == 1 && j < 2);
-    if (do_ref) {
-      // process.py:366-371: 1 < px < res[0] and 1 < py < res[1] on the 1-based coordinates
-      if (keep && ax >= 1 && ax <= W - 2 && ay >= 1 && ay <= H - 2) {
-        float nb = 0.f;
-        if (lane < 4) {
-          const int di = (lane == 2) ? 1 : (lane == 3 ? -1 : 0);
-          const int dj = (lane == 0) ? 1 : (lane == 1 ? -1 : 0);
-          const int i = ay + di, jo = ax + dj;
-          nb = p.do_warp ? eval_px(s, X, i, X.flip ? (W - 1 - jo) : jo) : s[i * W + jo];
-        }
-        const float xp = __shfl_sync(0xffffffffu, nb, 0), xm = __shfl_sync(0xffffffffu, nb, 1);
-        const float yp = __shfl_sync(0xffffffffu, nb, 2), ym = __shfl_sync(0xffffffffu, nb, 3);
-        const float dx = xp - xm, dy = yp - ym;
-        hx += (dx > 0.f) ? 0.25f : ((dx < 0.f) ? -0.25f : 0.f);
-        hy += (dy > 0.f) ? 0.25f : ((dy < 0.f) ? -0.25f : 0.f);
-      }
-    }
-    if (p.refine != 0) { hx += 0.5f; hy += 0.5f; }      // process.py:372 (+0.5 for every joint)
-    if (lane == 0) {
-      if (p.out_idx) p.out_idx[n] = ri;
-      if (p.out_max) p.out_max[n] = rv;
-      if (p.out_hm_xy) { p.out_hm_xy[2 * n] = hx; p.out_hm_xy[2 * n + 1] = hy; }
-      if (p.out_xy) {
-        float ox = hx, oy = hy;
-        if (p.dec) {
-          // np.dot row: (a00*(x-1) + 0*(y-1)) + a02, astype(int) truncation, +1
-          const double tx = __dadd_rn(__dmul_rn(dc0, (double)hx - 1.0), dc1);
-          const double ty = __dadd_rn(__dmul_rn(dc2, (double)hy - 1.0), dc3);
-          ox = (float)(trunc(tx) + 1.0);
-          oy = (float)(trunc(ty) + 1.0);
-        }
-        p.out_xy[2 * n] = ox; p.out_xy[2 * n + 1] = oy;
-      }
-    }
+    if (!deferred) finish_map(p, n, j, s, X, rv, ri, dc0, dc1, dc2, dc3, lane);
     __syncwarp();
     const long long nn = claim();
     if (STREAM) {
@@ -528,6 +547,50 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
     atomicAdd(p.stats + 0, n_slow);
     atomicAdd(p.stats + 1, n_eval);
     atomicAdd(p.stats + 2, n_maps);
+  }
+}
+
+// Exhaustive decode of the queued maps: one CTA of 4 warps per map (rows split four ways), map staged in
+// shared memory; warp 0 merges the four partial arg-maxes and writes the outputs.
+__global__ void __launch_bounds__(128) warp_decode_slow_kernel(const WDParams p) {
+  extern __shared__ __align__(16) float sm_map[];
+  __shared__ float s_v[4];
+  __shared__ int s_i[4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = p.H, W = p.W, HW = H * W;
+  const unsigned count = *p.slow_count;
+  for (unsigned item = blockIdx.x; item < count; item += gridDim.x) {
+    const long long n = p.slow_list[item];
+    unsigned vbu, ju, vu, bu;
+    p.divJ.divmod((unsigned)n, vbu, ju);
+    p.divB.divmod(vbu, vu, bu);
+    const float* src = p.maps + (long long)vu * p.sV + (long long)bu * p.sB + (long long)ju * p.sJ;
+    __syncthreads();
+    if (p.use_bulk) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(sm_map);
+      for (int q = threadIdx.x; q < (HW >> 2); q += blockDim.x) d4[q] = __ldg(s4 + q);
+    } else {
+      for (int k = threadIdx.x; k < HW; k += blockDim.x) sm_map[k] = __ldg(src + k);
+    }
+    __syncthreads();
+    Xform X;
+    load_xform(X, p.theta, p.flip, (long long)vbu, H, W);
+    X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
+    float rv; int ri;
+    const int r0 = (H * warp) / 4, r1 = (H * (warp + 1)) / 4;
+    decode_exhaustive(sm_map, X.t00, X.t01, X.t02, X.t10, X.t11, X.t12, X.stepx, X.stepy, X.sfx, X.sfy, H, W, X.flip,
+                      lane, rv, ri, r0, r1);
+    if (lane == 0) { s_v[warp] = rv; s_i[warp] = ri; }
+    __syncthreads();
+    if (warp == 0) {
+      rv = s_v[0]; ri = s_i[0];
+#pragma unroll
+      for (int w = 1; w < 4; ++w) if (arg_better(s_v[w], s_i[w], rv, ri)) { rv = s_v[w]; ri = s_i[w]; }
+      double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
+      if (p.dec) { const double* c = p.dec + (size_t)bu * 4; dc0 = c[0]; dc1 = c[1]; dc2 = c[2]; dc3 = c[3]; }
+      finish_map(p, n, (int)ju, sm_map, X, rv, ri, dc0, dc1, dc2, dc3, lane);
+    }
   }
 }
 
@@ -572,10 +635,21 @@ __global__ void mirror_w_kernel(const float* __restrict__ in, float* __restrict_
 
 using namespace ubpl;
 
+static int launch_slow(const WDParams& p, size_t map_bytes, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(warp_decode_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin() - 1024);
+    if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute(slow): %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+    attr_set = true;
+  }
+  warp_decode_slow_kernel<<<sm_count() * 4, 128, map_bytes, stream>>>(p);
+  return check_launch("ubpl_warp_decode(slow)");
+}
+
 extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64_t sJ, int V, int B, int J, int H,
                                 int W, const float* theta, const uint8_t* flip, const double* dec, int do_warp,
                                 int refine, int32_t* out_idx, float* out_max, float* out_xy, float* out_hm_xy,
-                                int64_t* stats, void* stream) {
+                                int64_t* stats, int32_t* slow_ws, void* stream) {
   UBPL_REQUIRE(maps != nullptr, "ubpl_warp_decode: maps is NULL");
   UBPL_REQUIRE(V >= 0 && B >= 0 && J >= 0 && H > 0 && W > 0, "ubpl_warp_decode: bad dims V=%d B=%d J=%d H=%d W=%d", V, B, J, H, W);
   UBPL_REQUIRE(!do_warp || theta != nullptr, "ubpl_warp_decode: theta is NULL with do_warp=1");
@@ -621,13 +695,22 @@ extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64
   if (env_mode && env_mode[0] == 's' && env_mode[1] == 't' && p.use_bulk && (map_bytes % 16 == 0)) stream_mode = true;
   p.work = work_counter((cudaStream_t)stream);
   if (!p.work) return UBPL_ERR_CUDA;
+  p.slow_list = nullptr; p.slow_count = nullptr;
+  if (slow_ws && do_warp) {
+    p.slow_count = reinterpret_cast<unsigned*>(slow_ws);
+    p.slow_list = slow_ws + 1;
+    cudaError_t e = cudaMemsetAsync(slow_ws, 0, sizeof(int32_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("ubpl_warp_decode: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+  }
   if (stream_mode) {
     int sw = 24;
     if (env_warps > 0 && env_warps < sw) sw = env_warps;
     long long need = (N + sw - 1) / sw;
     int grid = (int)(need < sm_count() ? need : sm_count());
     warp_decode_kernel<true><<<grid, sw * 32, 0, (cudaStream_t)stream>>>(p);
-    return check_launch("ubpl_warp_decode");
+    int rc = check_launch("ubpl_warp_decode");
+    if (rc != UBPL_OK || !p.slow_list) return rc;
+    return launch_slow(p, map_bytes, (cudaStream_t)stream);
   }
   const size_t smem = (size_t)warps * nbuf * buf_stride + (size_t)warps * nbuf * 8;
   static bool attr_set = false;
@@ -639,7 +722,9 @@ extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64
   long long need = (N + warps - 1) / warps;
   int grid = (int)(need < sm_count() ? need : sm_count());
   warp_decode_kernel<false><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(p);
-  return check_launch("ubpl_warp_decode");
+  int rc = check_launch("ubpl_warp_decode");
+  if (rc != UBPL_OK || !p.slow_list) return rc;
+  return launch_slow(p, map_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int ubpl_warp_materialize(const float* in, int64_t sN, int64_t sC, float* out, int64_t oN, int64_t oC,

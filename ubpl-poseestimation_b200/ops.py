@@ -55,7 +55,8 @@ def decode_coeffs(center, scale, res):
     return torch.stack([a00, -(t02 * a00), a11, -(t12 * a11)], -1).contiguous()
 
 
-def warp_decode(maps, theta=None, flip=None, dec=None, refine=0, stats=None, want_idx=True, want_hm=False):
+def warp_decode(maps, theta=None, flip=None, dec=None, refine=0, stats=None, want_idx=True, want_hm=False,
+                defer_exhaustive=True):
     """Fused back-warp + flip + arg-max decode (K1).  maps [V,B,J,H,W] or [B,J,H,W] (V=1);
     theta [V,B,2,3] (None = plain decode of the raw maps), flip [V,B] bool/uint8, dec [B,4] float64
     from decode_coeffs (None = heat-map coordinates).  Returns dict(idx, max, xy[, hm_xy]) shaped
@@ -79,9 +80,12 @@ def warp_decode(maps, theta=None, flip=None, dec=None, refine=0, stats=None, wan
     out_max = torch.empty(V, B, J, dtype=_f32, device=dev)
     out_xy = torch.empty(V, B, J, 2, dtype=_f32, device=dev)
     out_hm = torch.empty(V, B, J, 2, dtype=_f32, device=dev) if want_hm else None
+    slow_ws = torch.empty(V * B * J + 1, dtype=torch.int32, device=dev) if (defer_exhaustive and theta is not None) else None
     _lib.call("ubpl_warp_decode", maps.data_ptr(), maps.stride(0), maps.stride(1), maps.stride(2), V, B, J, H, W,
               _p(theta), _p(flip), _p(dec), 1 if theta is not None else 0, int(refine),
-              _p(out_idx), _p(out_max), _p(out_xy), _p(out_hm), _p(stats), _stream())
+              _p(out_idx), _p(out_max), _p(out_xy), _p(out_hm), _p(stats), _p(slow_ws), _stream())
+    if slow_ws is None:
+        _lib._launches -= 1                      # no second (exhaustive) kernel was launched
     res = dict(idx=out_idx, max=out_max, xy=out_xy, hm_xy=out_hm)
     if squeeze:
         res = {k: (v[0] if v is not None else None) for k, v in res.items()}
