@@ -31,7 +31,19 @@ __global__ void __launch_bounds__(256) ema_multi_kernel(const uint64_t* __restri
       const int n4 = n >> 2;
       float4* e4 = reinterpret_cast<float4*>(e);
       const float4* p4 = reinterpret_cast<const float4*>(p);
-      for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      int i = threadIdx.x;
+      for (; i + 3 * (int)blockDim.x < n4; i += 4 * blockDim.x) {      // 8 independent 128-bit loads in flight
+        float4 ev[4], pv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { ev[u] = e4[i + u * blockDim.x]; pv[u] = ldg_stream(p4 + i + u * blockDim.x); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          ev[u].x = ema1(ev[u].x, pv[u].x, a, oma); ev[u].y = ema1(ev[u].y, pv[u].y, a, oma);
+          ev[u].z = ema1(ev[u].z, pv[u].z, a, oma); ev[u].w = ema1(ev[u].w, pv[u].w, a, oma);
+          e4[i + u * blockDim.x] = ev[u];
+        }
+      }
+      for (; i < n4; i += blockDim.x) {
         float4 ev = e4[i];
         const float4 pv = __ldg(p4 + i);
         ev.x = ema1(ev.x, pv.x, a, oma); ev.y = ema1(ev.y, pv.y, a, oma);

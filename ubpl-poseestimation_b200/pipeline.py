@@ -155,16 +155,25 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         pool = None
+        self.eager = {}
         for name, fn in (("k1", lambda: stage_k1(self.state, stats)), ("k2", lambda: stage_k2(self.state, cfg, group)),
                          ("k3", lambda: stage_k3(self.state, cfg)), ("k4", self._ema)):
             if name == "k4" and ema is None:
+                continue
+            if name == "k2" and group is not None and cfg.select == "quantile":
+                # the NCCL all-reduces of the global-quantile selector stay outside the graphs: this stage is
+                # launched eagerly (its outputs are re-allocated every step, so K3 is eager as well)
+                self.eager["k2"] = fn
+                continue
+            if name == "k3" and "k2" in self.eager:
+                self.eager["k3"] = fn
                 continue
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
                 fn()
             pool = g.pool()
             self.graphs[name] = g
-        self.order = [n for n in ("k1", "k2", "k3", "k4") if n in self.graphs]
+        self.order = [n for n in ("k1", "k2", "k3", "k4") if n in self.graphs or n in self.eager]
 
     def _ema(self):
         self.ema.step(self.alpha)
@@ -180,6 +189,9 @@ class GraphedStep:
         mark = timer if timer is not None else (lambda name: None)
         for n in self.order:
             mark(n + "_0")
-            self.graphs[n].replay()
+            if n in self.graphs:
+                self.graphs[n].replay()
+            else:
+                self.eager[n]()
             mark(n + "_1")
         return self.state
