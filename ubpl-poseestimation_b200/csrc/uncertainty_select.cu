@@ -524,7 +524,7 @@ extern "C" int ubpl_k2_view_fixed(const float* preds, int K, int B, int J, doubl
   const long long BJ = (long long)B * J;
   if (BJ == 0) return UBPL_OK;
   GET_POWTAB(T);
-  k2_view_fixed_kernel<<<blocks_for(BJ, 128), 128, 0, (cudaStream_t)stream>>>(preds, K, BJ, J, distThrMax, img_h, img_w,
+  k2_view_fixed_kernel<<<blocks_for(BJ, 64), 64, 0, (cudaStream_t)stream>>>(preds, K, BJ, J, distThrMax, img_h, img_w,
                                                                              stride, sigma, S, out_mean, out_dist, out_legal,
                                                                              enable, gate_out, count_out, counts, T);
   return check_launch("ubpl_k2_view_fixed");
