@@ -297,7 +297,16 @@ def run_ours(args):
     # per-stage device time (CUDA events on the launching stream), averaged over the timed steps
     def avg(a, b):
         return sum(ev[a].elapsed_time(ev[b]) for ev in stage_events) / len(stage_events)
-    k1_ms, k2_ms, k3_ms, k4_ms = avg("k1_0", "k1_1"), avg("k2_0", "k2_1"), avg("k3_0", "k3_1"), avg("k4_0", "k4_1")
+    k1_ms, k2_ms, k3_ms = avg("k1_0", "k1_1"), avg("k2_0", "k2_1"), avg("k3_0", "k3_1")
+    # K4 runs concurrently with K1 inside the K1 graph; its stand-alone time is measured here, outside the timed region
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ee0.record()
+    for _ in range(20):
+        plan.step(alpha)
+    ee1.record()
+    torch.cuda.synchronize()
+    k4_ms = ee0.elapsed_time(ee1) / 20
     bytes_sample = algorithmic_bytes_per_sample(c)
     k1_bytes = 4 * H * W * J * M * K * B
     k3_bytes = 4 * H * W * J * (2 * S + 1) * B
@@ -307,7 +316,8 @@ def run_ours(args):
     roof = {"bound": "hbm", "kernel": "warp_decode_kernel (K1: %d maps of %d B per launch)" % (M * K * B * J, 4 * H * W),
             "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-            "stages_ms": {"k1_warp_decode": k1_ms, "k2_uncertainty_select": k2_ms, "k3_render_mse": k3_ms, "k4_ema": k4_ms},
+            "stages_ms": {"k1_warp_decode_with_k4_ema_overlapped": k1_ms, "k2_uncertainty_select": k2_ms, "k3_render_mse": k3_ms,
+                          "k4_ema_standalone": k4_ms},
             "stages_gbs": {"k1": k1_bytes / (k1_ms * 1e-3) / 1e9, "k3": k3_bytes / (k3_ms * 1e-3) / 1e9,
                            "k4": ema_bytes / (k4_ms * 1e-3) / 1e9, "chain_k1_k3": chain_gbs},
             "chain_frac_of_peak": chain_gbs / peak, "chain_frac_of_8TBs": chain_gbs / 8000.0,
@@ -359,7 +369,7 @@ def run_ours(args):
                        "heatmap": [H, W], "select": c["select"], "distThrMax": DIST_THR_MAX,
                        "ema_params": n_params, "l2": "inputs (%.0f MB/step) larger than L2" % (bytes_sample * B / 1e6),
                        "selected_frac": float(r["enable"].float().mean()), "exhaustive_decode_frac": slow_frac,
-                       "launch": "4 CUDA graphs per step (K1, K2, K3, K4), stage edges are CUDA events"},
+                       "launch": "3 CUDA graphs per step (K1 with the EMA forked onto a side stream, K2, K3), stage edges are CUDA events"},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(t)},

@@ -260,8 +260,9 @@ def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, g
         return dict(reliability=rel, enable=enable, gate=gate, counts=counts, thr=thr, ext=ext)
     ext = be.extrema(dist)
     if world > 1:
-        td.all_reduce(ext[0:1], op=td.ReduceOp.MAX, group=group)
-        td.all_reduce(ext[1:2], op=td.ReduceOp.MIN, group=group)
+        ext[1:2].neg_()                                       # one MAX all-reduce of (dist_max, -dist_min)
+        td.all_reduce(ext, op=td.ReduceOp.MAX, group=group)
+        ext[1:2].neg_()
     rel, keys = be.reliability(dist, legal, ext, reliableDistMin)
     if n_total < 1:
         raise IndexError("list index out of range")          # scores[int(-1*pct)] on an empty list

@@ -142,7 +142,7 @@ class GraphedStep:
     `ema` is an optional ops.EmaPlan whose update (K4) becomes the fourth graph."""
 
     def __init__(self, teacher, student, theta, flip, dec, sample_w, cfg: StepConfig, group=None, stats=None,
-                 ema=None, alpha=None, warmup=3):
+                 ema=None, alpha=None, warmup=3, overlap_ema=True):
         self.cfg, self.group, self.ema, self.alpha = cfg, group, ema, alpha
         self.state = dict(teacher=teacher, student=student, theta=theta, flip=flip.to(torch.uint8), dec=dec,
                           sample_w=sample_w)
@@ -156,23 +156,39 @@ class GraphedStep:
         torch.cuda.synchronize()
         pool = None
         self.eager = {}
-        for name, fn in (("k1", lambda: stage_k1(self.state, stats)), ("k2", lambda: stage_k2(self.state, cfg, group)),
-                         ("k3", lambda: stage_k3(self.state, cfg)), ("k4", self._ema)):
-            if name == "k4" and ema is None:
-                continue
-            if name == "k2" and group is not None and cfg.select == "quantile":
-                # the NCCL all-reduces of the global-quantile selector stay outside the graphs: this stage is
-                # launched eagerly (its outputs are re-allocated every step, so K3 is eager as well)
-                self.eager["k2"] = fn
-                continue
+        self.overlap_ema = bool(overlap_ema and ema is not None)
+        self._side = torch.cuda.Stream() if self.overlap_ema else None
+
+        def k1_fn():
+            if self.overlap_ema:
+                # K4 is independent of the chain and HBM-bound while K1 is issue-bound: fork it onto a side
+                # stream inside the same graph so the two run concurrently
+                self._side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side):
+                    self._ema()
+            stage_k1(self.state, stats)
+            if self.overlap_ema:
+                torch.cuda.current_stream().wait_stream(self._side)
+
+        stages = [("k1", k1_fn), ("k2", lambda: stage_k2(self.state, cfg, group)), ("k3", lambda: stage_k3(self.state, cfg))]
+        if ema is not None and not self.overlap_ema:
+            stages.append(("k4", self._ema))
+        for name, fn in stages:
             if name == "k3" and "k2" in self.eager:
-                self.eager["k3"] = fn
+                self.eager["k3"] = fn             # K2's outputs are re-allocated every step when it runs eagerly
                 continue
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
-                fn()
-            pool = g.pool()
-            self.graphs[name] = g
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    fn()
+                pool = g.pool()
+                self.graphs[name] = g
+            except Exception:
+                if name != "k2" or group is None:
+                    raise
+                # the NCCL all-reduces of the global-quantile selector could not be captured here: run eagerly
+                torch.cuda.synchronize()
+                self.eager["k2"] = fn
         self.order = [n for n in ("k1", "k2", "k3", "k4") if n in self.graphs or n in self.eager]
 
     def _ema(self):
