@@ -111,6 +111,9 @@ int ubpl_assess_dual(const float* p1, const float* p2, const float* pmean,
 int ubpl_coord_error(const double* pred, const float* gt, int gt_stride, int64_t n_sets, int B, int J,
                      int ref0, int ref1, double pck_thr, double* err, int32_t* acc, void* stream);
 
+/* ProcessUtils.coord_distance (utils/process.py:53-54) for n coordinate pairs, float64 [n,2] each. */
+int ubpl_pair_distance(const double* c1, const double* c2, int64_t n, double* out, void* stream);
+
 /* ---- K2: pseudo-label selection ---------------------------------------------------------------
  * BusinessUtils.filter_pseudo2 (utils/business.py:173-217) / _calReliabilityThr (:43-46).
  * Step 1: local extrema of dist (float64[n]; 999 = sentinel): ext[0] = max over dist<999 (0 if

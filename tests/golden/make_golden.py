@@ -193,7 +193,9 @@ def business_fixture():
                                  reliableDistMin=1.0, kpsCount=J)
     pseudo, ori_a, aug_a = ref.bus.assess_pseudo_unc2(ids, gt, [p1, p2, pmean], [list(pm1), list(pm2)], args)
     sel, cnt, errs, accs, thr = ref.bus.filter_pseudo2(copy.deepcopy(pseudo), args)
-    out = dict(ids=ids, gt=gt.tolist(), p1=p1.tolist(), p2=p2.tolist(), pmean=pmean.tolist(), pm1=pm1.tolist(),
+    fp_sel, fp_cnt, fp_errs, fp_accs, fp_thr = ref.bus.filter_pseudo([copy.deepcopy(ori_a[0]), copy.deepcopy(ori_a[1]), copy.deepcopy(ori_a[2])], args)
+    out = dict(fp_sel=fp_sel, fp_counts=fp_cnt, fp_errs=[float(e) for e in fp_errs], fp_accs=[float(a) for a in fp_accs], fp_thr=fp_thr,
+               ids=ids, gt=gt.tolist(), p1=p1.tolist(), p2=p2.tolist(), pmean=pmean.tolist(), pm1=pm1.tolist(),
                pm2=pm2.tolist(), args=vars(args), pseudo=pseudo, ori_assess=ori_a, aug_assess=aug_a, sel=sel,
                counts=cnt, errs=[float(e) for e in errs], accs=[float(a) for a in accs], thr=thr)
     json.dump(out, open(os.path.join(HERE, "business.json"), "w"))

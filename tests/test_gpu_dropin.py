@@ -160,6 +160,14 @@ def test_business(pkg):
     np.testing.assert_allclose(accs, g["accs"], rtol=1e-12)
     with pytest.raises(IndexError):
         pkg.bus.filter_pseudo2([], args)
+    # filter_pseudo (business.py:49-91): distance between the two teachers' own predictions
+    import copy
+    sel, cnt, errs, accs, thr = pkg.bus.filter_pseudo([copy.deepcopy(ori_a[0]), copy.deepcopy(ori_a[1]), copy.deepcopy(ori_a[2])], args)
+    assert thr == g["fp_thr"] and cnt == g["fp_counts"]
+    assert [it["kpID"] for it in sel] == [it["kpID"] for it in g["fp_sel"]]
+    assert [it["enable"] for it in sel] == [it["enable"] for it in g["fp_sel"]]
+    assert [it["reliability"] for it in sel] == [it["reliability"] for it in g["fp_sel"]]
+    assert [it["dist"] for it in sel] == [it["dist"] for it in g["fp_sel"]]
 
 
 def test_update_ema_variables(pkg):

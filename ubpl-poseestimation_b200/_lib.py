@@ -25,6 +25,7 @@ SIGNATURES = {
     "ubpl_view_dispersion": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "ubpl_mirror_w": [c_void_p, c_void_p, c_i64, c_int, c_void_p],
     "ubpl_coord_error": [c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p],
+    "ubpl_pair_distance": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p],
     "ubpl_unc_normalize": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p],
     "ubpl_assess_dual": [c_void_p] * 5 + [c_int, c_int, c_int] + [c_void_p] * 9 + [c_void_p],
     "ubpl_dist_extrema": [c_void_p, c_i64, c_void_p, c_void_p],

@@ -2,14 +2,15 @@
 
     assess_pseudo_unc    utils/business.py:16-35     assess_pseudo_unc2   utils/business.py:109-161
     filter_pseudo2       utils/business.py:173-217   preds_mean           utils/business.py:297-300
+    filter_pseudo        utils/business.py:49-91
 
 Same signatures and the same list-of-dict records (keys kpID, imageID, kIdx, coord, coord_gt,
 coord_legal, error, acc_flag, coord_w1, coord_w2, intDist1, intDist2, extDist, reliability,
 enable).  All arithmetic (pairwise dispersions, ensemble weights, errors / PCK flags,
 min-max normalisation, the exact global order statistic and the masks) runs in the float64
 kernels of K2; the host only assembles the python records the API has to return.
-`filter_pseudo`, `pseudo_cal_unc` and `pseudo_filter_mixUnc(2)` (the stateful LMA variant,
-business.py:49-91,220-294) are not covered yet and stay with the reference.
+`pseudo_cal_unc` and `pseudo_filter_mixUnc(2)` (the stateful 3-epoch LMA variant, business.py:220-294)
+are not covered yet and stay with the reference.
 """
 import copy
 
@@ -92,18 +93,30 @@ class BusinessUtils:
         return pseudoArray, ori_assess, augs_assess
 
     @classmethod
-    def filter_pseudo2(cls, pseudoArray, args):
-        """utils/business.py:173-217: min/max-normalised reliability, global quantile threshold, strict >."""
+    def filter_pseudo(cls, predsArraies, args):
+        """utils/business.py:49-91: reliability from the distance between the two teachers' coordinates
+        (np.min / np.max normalisation, dist_min floored by reliableDistMin), global quantile, strict >."""
+        predsArray_mds1, predsArray_mds2, pseudoArray = predsArraies
         if len(pseudoArray) == 0:
-            raise IndexError("list index out of range")                  # business.py:45 on an empty list
-        ext = torch.tensor([float(p["extDist"]) for p in pseudoArray], dtype=torch.float64).cuda()
-        legal = torch.tensor([float(p["coord_legal"]) for p in pseudoArray], dtype=torch.float64).cuda()
-        s = ops.select_quantile(ext, legal, args.kpsCount, args.reliableThr, args.reliablePCT, args.reliableDistMin)
-        rel = s["reliability"].cpu().tolist()
-        en = s["enable"].cpu().tolist()
+            raise ValueError("zero-size array to reduction operation maximum which has no identity")   # np.max([])
+        c1 = torch.tensor([p["coord"] for p in predsArray_mds1], dtype=torch.float64).cuda()
+        c2 = torch.tensor([p["coord"] for p in predsArray_mds2], dtype=torch.float64).cuda()
+        legal = torch.tensor([1.0 if (a["coord_legal"] and b["coord_legal"]) else 0.0
+                              for a, b in zip(predsArray_mds1, predsArray_mds2)], dtype=torch.float64).cuda()
+        dist = ops.pair_distance(c1, c2)
+        # same kernels as filter_pseudo2: identical arithmetic as long as no distance equals the 999 sentinel
+        s = ops.select_quantile(dist, legal, args.kpsCount, args.reliableThr, args.reliablePCT, args.reliableDistMin)
+        dl, rel, en = dist.cpu().tolist(), s["reliability"].cpu().tolist(), s["enable"].cpu().tolist()
         thr = float(s["thr"].item())
-        for p, r in zip(pseudoArray, rel):
-            p["reliability"] = r                                         # the reference mutates its input too (:189)
+        for i, p in enumerate(pseudoArray):
+            p["dist"] = dl[i]
+            p["coord_legal"] = predsArray_mds1[i]["coord_legal"] and predsArray_mds2[i]["coord_legal"]
+            p["reliability"] = rel[i]
+        return cls._collect(pseudoArray, rel, en, thr, args)
+
+    @classmethod
+    def _collect(cls, pseudoArray, rel, en, thr, args):
+        """The selection loop shared by filter_pseudo / filter_pseudo2 (business.py:69-91,195-217)."""
         order = sorted(range(len(pseudoArray)), key=lambda i: rel[i], reverse=True)   # stable, like sorted(..., reverse=True)
         n = args.kpsCount + 1
         selArray, selCounts, selErrs, selAccs = [], [0] * n, [0] * n, [0] * n
@@ -126,3 +139,18 @@ class BusinessUtils:
                 selErrs[idx] = selErrs[idx] / selCounts[idx]
                 selAccs[idx] = selAccs[idx] / selCounts[idx]
         return selArray, selCounts, selErrs, selAccs, thr
+
+    @classmethod
+    def filter_pseudo2(cls, pseudoArray, args):
+        """utils/business.py:173-217: min/max-normalised reliability, global quantile threshold, strict >."""
+        if len(pseudoArray) == 0:
+            raise IndexError("list index out of range")                  # business.py:45 on an empty list
+        ext = torch.tensor([float(p["extDist"]) for p in pseudoArray], dtype=torch.float64).cuda()
+        legal = torch.tensor([float(p["coord_legal"]) for p in pseudoArray], dtype=torch.float64).cuda()
+        s = ops.select_quantile(ext, legal, args.kpsCount, args.reliableThr, args.reliablePCT, args.reliableDistMin)
+        rel = s["reliability"].cpu().tolist()
+        en = s["enable"].cpu().tolist()
+        thr = float(s["thr"].item())
+        for p, r in zip(pseudoArray, rel):
+            p["reliability"] = r                                         # the reference mutates its input too (:189)
+        return cls._collect(pseudoArray, rel, en, thr, args)

@@ -402,6 +402,12 @@ __global__ void __launch_bounds__(1024) select_quantile_local_kernel(const doubl
   }
 }
 
+__global__ void pair_distance_kernel(const double* __restrict__ c1, const double* __restrict__ c2, long long n,
+                                     double* __restrict__ out, PowTab T) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = py_dist(c1[2 * i], c1[2 * i + 1], c2[2 * i], c2[2 * i + 1], T);
+}
+
 static inline int blocks_for(long long n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace ubpl
@@ -552,4 +558,12 @@ extern "C" int ubpl_select_quantile_local(const double* dist, const double* lega
   select_quantile_local_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dist, legal, n, J, k_rank, reliableThr, reliableDistMin,
                                                                       reliability, keys, enable, gate32, counts, thr_out, ext_out);
   return check_launch("ubpl_select_quantile_local");
+}
+
+extern "C" int ubpl_pair_distance(const double* c1, const double* c2, int64_t n, double* out, void* stream) {
+  UBPL_REQUIRE(c1 && c2 && out && n >= 0, "ubpl_pair_distance: bad arguments");
+  if (n == 0) return UBPL_OK;
+  GET_POWTAB(T);
+  pair_distance_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(c1, c2, n, out, T);
+  return check_launch("ubpl_pair_distance");
 }

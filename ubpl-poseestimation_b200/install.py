@@ -8,7 +8,7 @@ attributes of the reference's own modules:
     utils.process.ProcessUtils.{kps_fromHeatmap, kps_fromHeatmap_mul, kps_fromHeatmap2, kps_heatmap,
                                 kps_heatmap_mulKps, kps_getLabeledCount}
     utils.evaluation.EvaluationUtils.uncertainty_fromDistance
-    utils.business.BusinessUtils.{assess_pseudo_unc2, filter_pseudo2}
+    utils.business.BusinessUtils.{assess_pseudo_unc, assess_pseudo_unc2, filter_pseudo, filter_pseudo2}
     utils.parameters.update_ema_variables   (and utils.udaap.utils_mt.update_ema_variables)
 """
 import importlib
@@ -24,7 +24,7 @@ CLASS_PATCHES = {
     ("utils.process", "ProcessUtils"): (process.ProcessUtils, ("kps_fromHeatmap", "kps_fromHeatmap_mul", "kps_fromHeatmap2",
                                                                "kps_heatmap", "kps_heatmap_mulKps", "kps_getLabeledCount")),
     ("utils.evaluation", "EvaluationUtils"): (evaluation.EvaluationUtils, ("uncertainty_fromDistance",)),
-    ("utils.business", "BusinessUtils"): (business.BusinessUtils, ("assess_pseudo_unc2", "filter_pseudo2")),
+    ("utils.business", "BusinessUtils"): (business.BusinessUtils, ("assess_pseudo_unc", "assess_pseudo_unc2", "filter_pseudo", "filter_pseudo2")),
 }
 
 

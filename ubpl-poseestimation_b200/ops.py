@@ -224,6 +224,17 @@ class _CudaSelectBackend:
         return enable, gate, counts, thr
 
 
+def pair_distance(c1, c2):
+    """python-float distance between two coordinate sets [n,2] (utils/process.py:53-54) -> float64 [n]."""
+    _need_cuda(c1, c2)
+    c1 = c1.to(_f64).contiguous()
+    c2 = c2.to(_f64).contiguous()
+    n = c1.shape[0]
+    out = torch.empty(n, dtype=_f64, device=c1.device)
+    _lib.call("ubpl_pair_distance", c1.data_ptr(), c2.data_ptr(), n, out.data_ptr(), _stream())
+    return out
+
+
 def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, group=None, n_total=None, backend=None):
     """BusinessUtils.filter_pseudo2 (utils/business.py:173-217) on device: min/max normalise,
     reliability = 1 - unc, exact k-th order statistic (k = int((n-1)*pct) from the top) by a
