@@ -38,6 +38,9 @@ CONFIGS = {
 }
 DIST_THR_MAX = 3.0          # no reference default exists; ~half of the joints pass on the synthetic data
 METRIC = "pseudo-labelled samples/sec"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE warp_decode_kernel launch, from the ncu --set full capture
+# profiles/r01e_k1_k3_full.ncu-rep (c2: 469.93 MB read + 4.14 MB written vs 469.76 MB algorithmic)
+NCU_TRAFFIC = {"c2": 474.08e6}
 
 
 def algorithmic_bytes_per_sample(c):
@@ -217,6 +220,8 @@ def run_ours(args):
         import torch.distributed as td
         td.init_process_group("nccl", device_id=dev)
         group = td.group.WORLD
+        from ubpl_b200 import dist as ubpl_dist
+        ubpl_dist.init_nccl(group)                 # the library's own communicator for the histogram all-reduce
     c = CONFIGS[args.config]
     B, K, M, S, J, H, W = (c[k] for k in "BKMSJHW")
     d = synth.make_batch(B=B, K=K, J=J, H=H, W=W, M=M, S=S, seed=1388, rank=rank, device=dev)
@@ -315,7 +320,7 @@ def run_ours(args):
     chain_gbs = bytes_sample * B / ((k1_ms + k2_ms + k3_ms) * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "warp_decode_kernel (K1: %d maps of %d B per launch)" % (M * K * B * J, 4 * H * W),
             "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC.get(args.config), "peak_source": peak_src,
             "stages_ms": {"k1_warp_decode_with_k4_ema_overlapped": k1_ms, "k2_uncertainty_select": k2_ms, "k3_render_mse": k3_ms,
                           "k4_ema_standalone": k4_ms},
             "stages_gbs": {"k1": k1_bytes / (k1_ms * 1e-3) / 1e9, "k3": k3_bytes / (k3_ms * 1e-3) / 1e9,

@@ -145,6 +145,22 @@ int ubpl_select_quantile_local(const double* dist, const double* legal, int64_t 
                                double reliableThr, double reliableDistMin, double* reliability,
                                uint64_t* keys, uint8_t* enable, float* gate32, int32_t* counts,
                                double* thr_out, double* ext_out, void* stream);
+/* Multi-GPU form of steps 1-4: the extrema and the four key histograms are all-reduced with NCCL over
+ * the communicator created by ubpl_nccl_init (one process per GPU); kernels and collectives are enqueued
+ * on `stream` by this single call (capturable in a CUDA graph).  n = this rank's items, k_rank =
+ * int((n_total-1)*reliablePCT) over ALL ranks' items; ws = device scratch of UBPL_SELECT_WS_BYTES. */
+#define UBPL_SELECT_WS_BYTES (2 * 8 + 8 + 8 + 65536 * 4)
+int ubpl_select_quantile_dist(const double* dist, const double* legal, int64_t n, int J, int64_t k_rank,
+                              double reliableThr, double reliableDistMin, double* reliability,
+                              uint64_t* keys, uint8_t* enable, float* gate32, int32_t* counts,
+                              double* thr_out, void* ws, void* stream);
+/* NCCL plumbing for the call above (libnccl.so.2 is resolved with dlopen): rank 0 obtains a 128-byte
+ * unique id (host buffer), shares it by any means (torch.distributed broadcast), every rank calls init. */
+int ubpl_nccl_unique_id(void* out128_host);
+int ubpl_nccl_init(const void* id128_host, int nranks, int rank);
+int ubpl_nccl_destroy(void);
+int ubpl_nccl_ranks(void);   /* 0 when no communicator exists */
+
 /* Fixed rule: enable = legal && 1-exp(-dist/5) <= 1-exp(-3*distThrMax/5)
  * (BusinessUtils.pseudo_filter_mixUnc / _calUncValue, utils/business.py:237-261,375-376). */
 int ubpl_select_fixed(const double* dist, const double* legal, int64_t n, int J, double distThrMax,

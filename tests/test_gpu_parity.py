@@ -252,6 +252,29 @@ def test_quantile_select_random(ops):
                 assert int(s["counts"][-1]) == int(en.sum())
 
 
+def test_quantile_select_nccl_single_rank(ops):
+    """The NCCL-fused selector (the multi-GPU path) on a 1-rank communicator: same threshold and masks."""
+    import ctypes
+    from ubpl_b200 import _lib
+    buf = (ctypes.c_char * 128)()
+    _lib.call("ubpl_nccl_unique_id", ctypes.cast(buf, ctypes.c_void_p))
+    _lib.call("ubpl_nccl_init", ctypes.cast(buf, ctypes.c_void_p), 1, 0)
+    try:
+        rng = np.random.default_rng(9)
+        for n, J in ((7, 7), (4352, 17)):
+            dist = np.round(rng.gamma(2.0, 3.0, n) * 4) / 4
+            dist[rng.random(n) < 0.2] = 999.0
+            legal = (rng.random(n) < 0.9).astype(np.float64)
+            for pct in (0.5, 0.1, 0.99):
+                rel, thr, en = O.filter_dual(dist, legal, 0.0, pct, 1.0)
+                s = ops.select_quantile_nccl(cu(dist), cu(legal), J, int((n - 1) * pct), 0.0, 1.0)
+                assert float(s["thr"]) == thr
+                assert np.array_equal(npy(s["enable"]).astype(bool), en)
+                assert np.array_equal(npy(s["reliability"]), rel)
+    finally:
+        _lib.call("ubpl_nccl_destroy")
+
+
 def test_select_fixed(ops):
     rng = np.random.default_rng(5)
     dist = np.concatenate([rng.gamma(2.0, 2.0, 500), [3.0, 9.0, 0.0, 999.0]])

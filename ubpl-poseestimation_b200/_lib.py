@@ -35,6 +35,12 @@ SIGNATURES = {
     "ubpl_select_apply": [c_void_p, c_i64, c_int, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_select_quantile_local": [c_void_p, c_void_p, c_i64, c_int, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ubpl_select_quantile_dist": [c_void_p, c_void_p, c_i64, c_int, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ubpl_nccl_unique_id": [c_void_p],
+    "ubpl_nccl_init": [c_void_p, c_int, c_int],
+    "ubpl_nccl_destroy": [],
+    "ubpl_nccl_ranks": [],
     "ubpl_select_fixed": [c_void_p, c_void_p, c_i64, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_k2_view_fixed": [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_float, c_float, c_int,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -89,7 +95,8 @@ def lib():
 
 
 # kernels launched per successful call (cudaMemsetAsync is not counted); bench.py's gpu_launches
-LAUNCHES = {"ubpl_dist_extrema": 2, "ubpl_warp_decode": 2}
+LAUNCHES = {"ubpl_dist_extrema": 2, "ubpl_warp_decode": 2, "ubpl_select_quantile_dist": 16, "ubpl_nccl_unique_id": 0,
+            "ubpl_nccl_init": 0, "ubpl_nccl_destroy": 0}
 _launches = 0
 
 

@@ -567,3 +567,5 @@ extern "C" int ubpl_pair_distance(const double* c1, const double* c2, int64_t n,
   pair_distance_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(c1, c2, n, out, T);
   return check_launch("ubpl_pair_distance");
 }
+
+#include "nccl_select.inc"

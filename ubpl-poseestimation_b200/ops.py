@@ -269,6 +269,9 @@ def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, g
                   float(reliableDistMin), rel.data_ptr(), keys.data_ptr(), enable.data_ptr(), gate.data_ptr(),
                   counts.data_ptr(), thr.data_ptr(), ext.data_ptr(), _stream())
         return dict(reliability=rel, enable=enable, gate=gate, counts=counts, thr=thr, ext=ext)
+    if world > 1 and backend is None and int(_lib.lib().ubpl_nccl_ranks()) == world:
+        # the library's own NCCL communicator (dist.init_nccl): kernels and all-reduces enqueued by ONE call
+        return select_quantile_nccl(dist, legal, J, int((n_total - 1) * reliablePCT), reliableThr, reliableDistMin)
     ext = be.extrema(dist)
     if world > 1:
         ext[1:2].neg_()                                       # one MAX all-reduce of (dist_max, -dist_min)
@@ -286,6 +289,26 @@ def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, g
         be.descend(hist, shift, prefix, k_rem)
     enable, gate, counts, thr = be.apply(rel, J, prefix, reliableThr)
     return dict(reliability=rel, enable=enable, gate=gate, counts=counts, thr=thr, ext=ext)
+
+
+def select_quantile_nccl(dist, legal, J, k_rank, reliableThr, reliableDistMin):
+    """ubpl_select_quantile_dist: this rank's items against the global k-th order statistic (k_rank counted
+    over all ranks from the largest reliability), extrema and histograms all-reduced with NCCL."""
+    dist = dist.reshape(-1).to(_f64).contiguous()
+    legal = legal.reshape(-1).to(_f64).contiguous()
+    n = dist.numel()
+    dev = dist.device
+    rel = torch.empty(n, dtype=_f64, device=dev)
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    enable = torch.empty(n, dtype=torch.uint8, device=dev)
+    gate = torch.empty(n, dtype=_f32, device=dev)
+    counts = torch.empty(J + 1, dtype=torch.int32, device=dev)
+    thr = torch.empty(1, dtype=_f64, device=dev)
+    ws = torch.empty(4 + 65536 + 4, dtype=torch.int32, device=dev)      # UBPL_SELECT_WS_BYTES, 8-byte aligned
+    _lib.call("ubpl_select_quantile_dist", dist.data_ptr(), legal.data_ptr(), n, J, int(k_rank), float(reliableThr),
+              float(reliableDistMin), rel.data_ptr(), keys.data_ptr(), enable.data_ptr(), gate.data_ptr(),
+              counts.data_ptr(), thr.data_ptr(), ws.data_ptr(), _stream())
+    return dict(reliability=rel, enable=enable, gate=gate, counts=counts, thr=thr, ext=ws[:4].view(_f64))
 
 
 def select_fixed(dist, legal, J, distThrMax):

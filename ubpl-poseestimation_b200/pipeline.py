@@ -177,18 +177,16 @@ class GraphedStep:
             if name == "k3" and "k2" in self.eager:
                 self.eager["k3"] = fn             # K2's outputs are re-allocated every step when it runs eagerly
                 continue
-            try:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
-                    fn()
-                pool = g.pool()
-                self.graphs[name] = g
-            except Exception:
-                if name != "k2" or group is None:
-                    raise
-                # the NCCL all-reduces of the global-quantile selector could not be captured here: run eagerly
-                torch.cuda.synchronize()
+            if name == "k2" and group is not None and cfg.select == "quantile":
+                # the stage with the NCCL all-reduces is launched eagerly (one fused C call enqueues its kernels
+                # and collectives); its outputs are re-allocated every step, so K3 stays eager as well
                 self.eager["k2"] = fn
+                continue
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                fn()
+            pool = g.pool()
+            self.graphs[name] = g
         self.order = [n for n in ("k1", "k2", "k3", "k4") if n in self.graphs or n in self.eager]
 
     def _ema(self):
