@@ -128,10 +128,11 @@ int ubpl_reliability(const double* dist, const double* legal, int64_t n, const d
  * key bits [shift, shift+16) over the keys whose bits above shift+16 equal `prefix`'s (pass 0:
  * shift = 48, all keys).  The caller all-reduces hist over ranks (SUM) between the passes. */
 int ubpl_key_histogram(const uint64_t* keys, int64_t n, const uint64_t* prefix, int shift,
-                       uint32_t* hist, void* stream);
+                       uint32_t* hist, int clear_first, void* stream);
 /* Given the (global) histogram of a pass, descend: finds the bin holding rank *k_rem (0-based,
- * counted from the LARGEST key), updates *prefix |= bin << shift and *k_rem. */
-int ubpl_select_descend(const uint32_t* hist, int shift, uint64_t* prefix, int64_t* k_rem, void* stream);
+ * counted from the LARGEST key), updates *prefix |= bin << shift and *k_rem; zero_after != 0 clears the
+ * histogram afterwards (then the next ubpl_key_histogram can pass clear_first = 0). */
+int ubpl_select_descend(uint32_t* hist, int shift, uint64_t* prefix, int64_t* k_rem, int zero_after, void* stream);
 /* Step 4: thr = max(reliableThr, value(prefix)); enable[n] = reliability > thr (uint8; gate32 is
  * the same as float32 0/1, either may be NULL);
  * counts[J+1] int32 per-joint and total selected (item i is joint i % J); thr_out float64. */

@@ -30,8 +30,8 @@ SIGNATURES = {
     "ubpl_assess_dual": [c_void_p] * 5 + [c_int, c_int, c_int] + [c_void_p] * 9 + [c_void_p],
     "ubpl_dist_extrema": [c_void_p, c_i64, c_void_p, c_void_p],
     "ubpl_reliability": [c_void_p, c_void_p, c_i64, c_void_p, c_double, c_void_p, c_void_p, c_void_p],
-    "ubpl_key_histogram": [c_void_p, c_i64, c_void_p, c_int, c_void_p, c_void_p],
-    "ubpl_select_descend": [c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "ubpl_key_histogram": [c_void_p, c_i64, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "ubpl_select_descend": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "ubpl_select_apply": [c_void_p, c_i64, c_int, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_select_quantile_local": [c_void_p, c_void_p, c_i64, c_int, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

@@ -199,34 +199,85 @@ __global__ void key_hist_kernel(const uint64_t* __restrict__ keys, long long n, 
   atomicAdd(hist + (uint32_t)((k >> shift) & 0xffffu), 1u);
 }
 
-// one CTA of 1024 threads; thread t owns the 64 bins [65535-64t-63, 65535-64t] (descending order)
-__global__ void __launch_bounds__(1024) select_descend_kernel(const uint32_t* __restrict__ hist, int shift,
-                                                               uint64_t* prefix, long long* k_rem) {
-  __shared__ unsigned long long part[1024];
-  const int t = threadIdx.x;
-  const int top = 65535 - 64 * t;
-  unsigned long long s = 0;
-  for (int q = 0; q < 64; ++q) s += hist[top - q];
-  part[t] = s;
+// One CTA of 32 warps walks the 65536 bins from the TOP (largest keys first) and finds the bin that holds
+// rank *k_rem: coalesced reads (a warp sums 32 consecutive bins per step), then three short parallel scans
+// (warp totals -> 32-bin groups of the owning warp -> bins of the owning group).  zero_after != 0 clears
+// the histogram for the next pass once every thread has read it.
+__global__ void __launch_bounds__(1024) select_descend_kernel(uint32_t* __restrict__ hist, int shift, uint64_t* prefix,
+                                                               long long* k_rem, int zero_after) {
+  __shared__ unsigned part[2048];            // sums of 32-bin groups, descending order
+  __shared__ unsigned long long wtot[32];
+  __shared__ int s_w;
+  __shared__ unsigned long long s_acc;
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  unsigned long long wsum = 0;
+  for (int g = 0; g < 64; ++g) {
+    const int d = w * 2048 + g * 32 + lane;            // descending bin index
+    unsigned c = hist[65535 - d];
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) part[w * 64 + g] = c;
+    wsum += c;
+  }
+  if (lane == 0) wtot[w] = wsum;
   __syncthreads();
+  const unsigned long long k = (unsigned long long)*k_rem;
   if (t == 0) {
-    const unsigned long long k = (unsigned long long)*k_rem;
     unsigned long long acc = 0;
-    int owner = 1023;
-    for (int u = 0; u < 1024; ++u) {
-      if (acc + part[u] > k) { owner = u; break; }
-      acc += part[u];
+    int W = 31;
+    for (int u = 0; u < 32; ++u) {
+      if (acc + wtot[u] > k) { W = u; break; }
+      acc += wtot[u];
     }
-    int bin = 65535 - 64 * owner;
-    for (int q = 0; q < 64; ++q) {
-      const unsigned long long c = hist[65535 - 64 * owner - q];
-      if (acc + c > k) { bin = 65535 - 64 * owner - q; break; }
-      acc += c;
-      bin = 65535 - 64 * owner - q;
+    if (W == 31 && !(acc + wtot[31] > k)) {             // rank beyond the population: clamp to the lowest bin
+      acc = 0;
+      for (int u = 0; u < 31; ++u) acc += wtot[u];
     }
-    const uint64_t mask = ~(0xffffull << shift);
-    *prefix = ((shift < 48 ? *prefix : 0ull) & mask) | ((uint64_t)bin << shift);
-    *k_rem = (long long)(k - acc);
+    s_w = W; s_acc = acc;
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int W = s_w;
+    unsigned long long acc = s_acc;
+    // 64 groups of warp W, two per lane
+    const unsigned p0 = part[W * 64 + 2 * lane], p1 = part[W * 64 + 2 * lane + 1];
+    unsigned long long pair = (unsigned long long)p0 + p1, incl = pair;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned long long excl = incl - pair;
+    const bool hit = (acc + excl + pair > k);
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    int L = m ? (__ffs(m) - 1) : 31;
+    const unsigned long long base = acc + __shfl_sync(0xffffffffu, excl, L);
+    const unsigned q0 = __shfl_sync(0xffffffffu, p0, L);
+    int G = 2 * L;
+    unsigned long long acc2 = base;
+    if (!(base + q0 > k)) { G = 2 * L + 1; acc2 = base + q0; }
+    // the 32 bins of group G
+    const int d = W * 2048 + G * 32 + lane;
+    const unsigned c = hist[65535 - d];
+    unsigned long long ci = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, ci, o);
+      if (lane >= o) ci += v;
+    }
+    const unsigned long long ce = ci - c;
+    const bool hit2 = (acc2 + ce + c > k);
+    unsigned m2 = __ballot_sync(0xffffffffu, hit2);
+    const int B = m2 ? (__ffs(m2) - 1) : 31;
+    if (lane == B) {
+      const int bin = 65535 - d;
+      const uint64_t mask = ~(0xffffull << shift);
+      *prefix = ((shift < 48 ? *prefix : 0ull) & mask) | ((uint64_t)bin << shift);
+      *k_rem = (long long)(k - (acc2 + ce));
+    }
+  }
+  if (zero_after) {
+    __syncthreads();
+    for (int i = t; i < 65536; i += 1024) hist[i] = 0u;
   }
 }
 
@@ -474,20 +525,23 @@ extern "C" int ubpl_reliability(const double* dist, const double* legal, int64_t
 }
 
 extern "C" int ubpl_key_histogram(const uint64_t* keys, int64_t n, const uint64_t* prefix, int shift,
-                                  uint32_t* hist, void* stream) {
+                                  uint32_t* hist, int clear_first, void* stream) {
   UBPL_REQUIRE(hist && (keys || n == 0) && n >= 0, "ubpl_key_histogram: bad arguments");
   UBPL_REQUIRE(shift == 48 || shift == 32 || shift == 16 || shift == 0, "ubpl_key_histogram: shift must be 48/32/16/0");
   UBPL_REQUIRE(shift == 48 || prefix != nullptr, "ubpl_key_histogram: prefix is NULL");
-  cudaError_t e = cudaMemsetAsync(hist, 0, 65536 * sizeof(uint32_t), (cudaStream_t)stream);
-  if (e != cudaSuccess) { set_error("ubpl_key_histogram: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+  if (clear_first) {
+    cudaError_t e = cudaMemsetAsync(hist, 0, 65536 * sizeof(uint32_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("ubpl_key_histogram: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+  }
   if (n > 0) key_hist_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(keys, n, prefix, shift, hist);
   return check_launch("ubpl_key_histogram");
 }
 
-extern "C" int ubpl_select_descend(const uint32_t* hist, int shift, uint64_t* prefix, int64_t* k_rem, void* stream) {
+extern "C" int ubpl_select_descend(uint32_t* hist, int shift, uint64_t* prefix, int64_t* k_rem, int zero_after,
+                                   void* stream) {
   UBPL_REQUIRE(hist && prefix && k_rem, "ubpl_select_descend: NULL pointer");
   UBPL_REQUIRE(shift == 48 || shift == 32 || shift == 16 || shift == 0, "ubpl_select_descend: bad shift");
-  select_descend_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(hist, shift, prefix, reinterpret_cast<long long*>(k_rem));
+  select_descend_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(hist, shift, prefix, reinterpret_cast<long long*>(k_rem), zero_after);
   return check_launch("ubpl_select_descend");
 }
 

@@ -207,10 +207,10 @@ class _CudaSelectBackend:
                 torch.empty(65536, dtype=torch.int32, device=device))
 
     def histogram(self, keys, prefix, shift, hist):
-        _lib.call("ubpl_key_histogram", keys.data_ptr(), keys.numel(), prefix.data_ptr(), shift, hist.data_ptr(), _stream())
+        _lib.call("ubpl_key_histogram", keys.data_ptr(), keys.numel(), prefix.data_ptr(), shift, hist.data_ptr(), 1, _stream())
 
     def descend(self, hist, shift, prefix, k_rem):
-        _lib.call("ubpl_select_descend", hist.data_ptr(), shift, prefix.data_ptr(), k_rem.data_ptr(), _stream())
+        _lib.call("ubpl_select_descend", hist.data_ptr(), shift, prefix.data_ptr(), k_rem.data_ptr(), 0, _stream())
 
     def apply(self, rel, J, prefix, reliableThr):
         n = rel.numel()
