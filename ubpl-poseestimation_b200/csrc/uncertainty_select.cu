@@ -60,6 +60,7 @@ __global__ void view_dispersion_kernel(const float* __restrict__ preds, const fl
     float mx = __fdiv_rn(sx, (float)K), my = __fdiv_rn(sy, (float)K);         // torch.mean (float32)
     if (mean_in) { mx = mean_in[2 * i]; my = mean_in[2 * i + 1]; }            // caller-supplied preds_mean
     double acc = 0.0;
+#pragma unroll 4
     for (int k = 0; k < K; ++k) {
       const double x = (double)preds[2 * ((long long)k * BJ + i)], y = (double)preds[2 * ((long long)k * BJ + i) + 1];
       acc = __dadd_rn(acc, py_dist(x, y, (double)mx, (double)my, T));        // sum(dists)
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(128) k2_view_fixed_kernel(const float* __restr
     }
     const float mx = __fdiv_rn(sx, (float)K), my = __fdiv_rn(sy, (float)K);
     double acc = 0.0;
+#pragma unroll 4
     for (int k = 0; k < K; ++k) {
       const double x = (double)preds[2 * ((long long)k * BJ + i)], y = (double)preds[2 * ((long long)k * BJ + i) + 1];
       acc = __dadd_rn(acc, py_dist(x, y, (double)mx, (double)my, T));
