@@ -1,0 +1,81 @@
+"""CPU-only checks of the boundary: the C-ABI library builds/loads and exports every symbol that
+include/ubpl_b200.h declares (no compute calls without a GPU), the ctypes table mirrors the header, the
+host-side helpers agree with the oracle, and the product path refuses to run on CPU tensors."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import ubpl_oracle as O
+import ubpl_b200
+from ubpl_b200 import _lib, augment, ops, pipeline
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    hdr = open(os.path.join(ROOT, "include", "ubpl_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(ubpl_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    L = _lib.lib()
+    names = _header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), n
+    assert L.ubpl_version() >= 100
+
+
+def test_ctypes_table_matches_header():
+    hdr = open(os.path.join(ROOT, "include", "ubpl_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for name, args in _lib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+        assert m, name
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(args), (name, len(params), len(args))
+    assert set(_header_functions()) - {"ubpl_last_error"} == set(_lib.SIGNATURES)
+
+
+def test_no_cpu_fallback():
+    x = torch.zeros(1, 2, 8, 8)
+    with pytest.raises(_lib.UbplError):
+        ops.warp_decode(x, None, None, None)
+    with pytest.raises(_lib.UbplError):
+        ops.render_targets(torch.zeros(2, 3), 8, 8, 32, 32)
+    with pytest.raises(_lib.UbplError):
+        ops.ema_flat(torch.zeros(4), torch.zeros(4), 0.5)
+
+
+@pytest.mark.parametrize("kind", ["f32", "f64", "int"])
+def test_decode_coeffs_matches_oracle(kind):
+    g = torch.Generator().manual_seed(4)
+    B = 16
+    center = torch.randint(100, 156, (B, 2), generator=g)
+    if kind == "f32":
+        scale, sd = (0.8 + torch.rand(B, generator=g)).float(), "f32"
+    elif kind == "f64":
+        scale, sd = (0.8 + torch.rand(B, generator=g)).double(), "f64"
+        center = center.double() + 0.5
+    else:
+        scale, sd = torch.randint(1, 3, (B,), generator=g), "f32"
+    got = ops.decode_coeffs(center, scale, [64, 64]).numpy()
+    want = O.decode_coeffs(center.numpy(), scale.numpy(), [64, 64], sd)
+    assert np.array_equal(got, want)
+
+
+def test_host_helpers():
+    for ang, sc in [(-20.0, 1 / 1.1), (13.7, 0.8), (0.0, 1.0), (30.0, 1 / 1.6)]:
+        assert np.array_equal(augment.AugmentUtils.affine_getWarpmat(ang, sc, [256, 256]).numpy(), O.affine_getWarpmat(ang, sc))
+    lab = torch.tensor([True, False, False, True])
+    assert torch.equal(pipeline.nega_weights(lab, 0.7), torch.tensor([0.0, 0.7, 0.7, 0.0]))
+    import bench
+    for c in bench.CONFIGS.values():
+        assert bench.algorithmic_bytes_per_sample(c) == 4 * c["H"] * c["W"] * c["J"] * (c["M"] * c["K"] + 2 * c["S"] + 1)
+    assert bench.algorithmic_bytes_per_sample(bench.CONFIGS["c2"]) == 2981888
