@@ -112,6 +112,7 @@ __global__ void assess_dual_kernel(const float* __restrict__ p1, const float* __
     double s1 = 0.0, s2 = 0.0;
     int cnt = 0;
     for (int u = 0; u < K; ++u)
+#pragma unroll 4
       for (int v = u + 1; v < K; ++v) {
         const long long ou = 2 * ((long long)u * BJ + i), ov = 2 * ((long long)v * BJ + i);
         s1 = __dadd_rn(s1, py_dist(a1[ou], a1[ou + 1], a1[ov], a1[ov + 1], T));
@@ -131,6 +132,7 @@ __global__ void assess_dual_kernel(const float* __restrict__ p1, const float* __
     cy = __dadd_rn(__dmul_rn(w1, y1), __dmul_rn(w2, y2));
     legal = 1.0;
     double se = 0.0;
+#pragma unroll 4
     for (int k = 0; k < K; ++k) {
       const long long o = 2 * ((long long)k * BJ + i);
       se = __dadd_rn(se, py_dist(a1[o], a1[o + 1], a2[o], a2[o + 1], T));
