@@ -191,34 +191,35 @@ __global__ void reliability_kernel(const double* __restrict__ dist, const double
 }
 
 __global__ void key_hist_kernel(const uint64_t* __restrict__ keys, long long n, const uint64_t* __restrict__ prefix,
-                                int shift, uint32_t* hist) {
+                                int shift, uint32_t* hist, int bits = 16) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t k = keys[i];
-  if (shift < 48) {
+  if (shift + bits < 64) {
     const uint64_t pf = *prefix;
-    if ((k >> (shift + 16)) != (pf >> (shift + 16))) return;
+    if ((k >> (shift + bits)) != (pf >> (shift + bits))) return;
   }
-  atomicAdd(hist + (uint32_t)((k >> shift) & 0xffffu), 1u);
+  atomicAdd(hist + (uint32_t)((k >> shift) & ((1ull << bits) - 1ull)), 1u);
 }
 
-// One CTA of 32 warps walks the 65536 bins from the TOP (largest keys first) and finds the bin that holds
-// rank *k_rem: coalesced reads (a warp sums 32 consecutive bins per step), then three short parallel scans
-// (warp totals -> 32-bin groups of the owning warp -> bins of the owning group).  zero_after != 0 clears
-// the histogram for the next pass once every thread has read it.
+// One CTA of 32 warps walks the nb = 2^bits bins (1024 <= nb <= 65536) from the TOP (largest keys first)
+// and finds the bin that holds rank *k_rem: coalesced reads (a warp sums 32 consecutive bins per step),
+// then three short parallel scans (warp totals -> 32-bin groups of the owning warp -> bins of the owning
+// group).  zero_after != 0 clears the histogram for the next pass once every thread has read it.
 __global__ void __launch_bounds__(1024) select_descend_kernel(uint32_t* __restrict__ hist, int shift, uint64_t* prefix,
-                                                               long long* k_rem, int zero_after) {
+                                                               long long* k_rem, int zero_after, int bits = 16) {
   __shared__ unsigned part[2048];            // sums of 32-bin groups, descending order
   __shared__ unsigned long long wtot[32];
   __shared__ int s_w;
   __shared__ unsigned long long s_acc;
   const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  const int nb = 1 << bits, span = nb >> 5, gpw = span >> 5;      // bins per warp, 32-bin groups per warp
   unsigned long long wsum = 0;
-  for (int g = 0; g < 64; ++g) {
-    const int d = w * 2048 + g * 32 + lane;            // descending bin index
-    unsigned c = hist[65535 - d];
+  for (int g = 0; g < gpw; ++g) {
+    const int d = w * span + g * 32 + lane;            // descending bin index
+    unsigned c = hist[nb - 1 - d];
     c = __reduce_add_sync(0xffffffffu, c);
-    if (lane == 0) part[w * 64 + g] = c;
+    if (lane == 0) part[w * gpw + g] = c;
     wsum += c;
   }
   if (lane == 0) wtot[w] = wsum;
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(1024) select_descend_kernel(uint32_t* __restri
       if (acc + wtot[u] > k) { W = u; break; }
       acc += wtot[u];
     }
-    if (W == 31 && !(acc + wtot[31] > k)) {             // rank beyond the population: clamp to the lowest bin
+    if (W == 31 && !(acc + wtot[31] > k)) {             // rank beyond the population: clamp to the lowest bins
       acc = 0;
       for (int u = 0; u < 31; ++u) acc += wtot[u];
     }
@@ -240,10 +241,13 @@ __global__ void __launch_bounds__(1024) select_descend_kernel(uint32_t* __restri
   __syncthreads();
   if (w == 0) {
     const int W = s_w;
-    unsigned long long acc = s_acc;
-    // 64 groups of warp W, two per lane
-    const unsigned p0 = part[W * 64 + 2 * lane], p1 = part[W * 64 + 2 * lane + 1];
-    unsigned long long pair = (unsigned long long)p0 + p1, incl = pair;
+    const unsigned long long acc = s_acc;
+    const int per = (gpw + 31) >> 5;                     // groups per lane (1, or 2 when gpw = 64)
+    unsigned p0 = 0, p1 = 0;
+    if (lane * per < gpw) p0 = part[W * gpw + lane * per];
+    if (per == 2 && lane * per + 1 < gpw) p1 = part[W * gpw + lane * per + 1];
+    const unsigned long long pair = (unsigned long long)p0 + p1;
+    unsigned long long incl = pair;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -251,16 +255,16 @@ __global__ void __launch_bounds__(1024) select_descend_kernel(uint32_t* __restri
     }
     const unsigned long long excl = incl - pair;
     const bool hit = (acc + excl + pair > k);
-    unsigned m = __ballot_sync(0xffffffffu, hit);
-    int L = m ? (__ffs(m) - 1) : 31;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    const int L = m ? (__ffs(m) - 1) : min(31, (gpw - 1) / per);
     const unsigned long long base = acc + __shfl_sync(0xffffffffu, excl, L);
     const unsigned q0 = __shfl_sync(0xffffffffu, p0, L);
-    int G = 2 * L;
+    int G = L * per;
     unsigned long long acc2 = base;
-    if (!(base + q0 > k)) { G = 2 * L + 1; acc2 = base + q0; }
+    if (per == 2 && !(base + q0 > k)) { G = L * per + 1; acc2 = base + q0; }
     // the 32 bins of group G
-    const int d = W * 2048 + G * 32 + lane;
-    const unsigned c = hist[65535 - d];
+    const int d = W * span + G * 32 + lane;
+    const unsigned c = hist[nb - 1 - d];
     unsigned long long ci = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -269,18 +273,64 @@ __global__ void __launch_bounds__(1024) select_descend_kernel(uint32_t* __restri
     }
     const unsigned long long ce = ci - c;
     const bool hit2 = (acc2 + ce + c > k);
-    unsigned m2 = __ballot_sync(0xffffffffu, hit2);
+    const unsigned m2 = __ballot_sync(0xffffffffu, hit2);
     const int B = m2 ? (__ffs(m2) - 1) : 31;
     if (lane == B) {
-      const int bin = 65535 - d;
-      const uint64_t mask = ~(0xffffull << shift);
-      *prefix = ((shift < 48 ? *prefix : 0ull) & mask) | ((uint64_t)bin << shift);
+      const uint64_t bin = (uint64_t)(nb - 1 - d);
+      const uint64_t mask = ~(((1ull << bits) - 1ull) << shift);
+      *prefix = ((shift + bits < 64 ? *prefix : 0ull) & mask) | (bin << shift);
       *k_rem = (long long)(k - (acc2 + ce));
     }
   }
   if (zero_after) {
     __syncthreads();
-    for (int i = t; i < 65536; i += 1024) hist[i] = 0u;
+    for (int i = t; i < nb; i += 1024) hist[i] = 0u;
+  }
+}
+
+// ---- selection on the DISTANCE keys (multi-GPU path) ------------------------------------------------
+// reliability = 1 - (e2 - dmin)/(dmax - dmin) is a monotone non-increasing function of e2 (every IEEE step
+// is monotone), illegal and sentinel items have reliability exactly 0 = f(dmax), so the k-th LARGEST
+// reliability is f(k-th SMALLEST e') with e' = dist for legal non-sentinel items and +inf otherwise.  The
+// radix select can therefore run on keys that do not depend on the global extrema, and the extrema
+// all-reduce rides in the same NCCL group as the first histogram.  key' = ~key_of(e') turns "k-th smallest"
+// into the "k-th largest" the descend kernel finds.
+__global__ void dist_keys_extrema_kernel(const double* __restrict__ dist, const double* __restrict__ legal, long long n,
+                                         uint64_t* __restrict__ keys, double* ext) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double e = dist[i];
+  if (e > 0.0 && e < 999.0) atomicMax(reinterpret_cast<unsigned long long*>(ext), (unsigned long long)__double_as_longlong(e));
+  if (e >= 0.0 && e < 999.0) atomicMin(reinterpret_cast<unsigned long long*>(ext + 1), (unsigned long long)__double_as_longlong(e));
+  const double ep = (legal[i] > 0.0 && e != 999.0) ? e : __longlong_as_double(0x7ff0000000000000ll);
+  keys[i] = ~key_of(ep);
+}
+
+__global__ void apply_dist_kernel(const double* __restrict__ dist, const double* __restrict__ legal, long long n, int J,
+                                  const uint64_t* __restrict__ prefix, const double* __restrict__ ext,
+                                  double reliableDistMin, double reliableThr, double* rel, uint8_t* enable,
+                                  float* gate32, int32_t* counts, double* thr_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double dmax = ext[0], dmin = ext[1];
+  if (dmax == 0.0) dmax = 999.0;                      // business.py:181
+  if (dmin > reliableDistMin) dmin = reliableDistMin; // business.py:182
+  const double ek = value_of(~(*prefix));              // k-th smallest e'
+  const double den = __dsub_rn(dmax, dmin);
+  const double rk = (ek > 1.0e300) ? 0.0 : __dsub_rn(1.0, __ddiv_rn(__dsub_rn(ek, dmin), den));
+  const double thr = (rk > reliableThr) ? rk : reliableThr;
+  if (i == 0 && thr_out) *thr_out = thr;
+  if (i >= n) return;
+  const double e = dist[i];
+  const double e2 = (e != 999.0) ? e : dmax;
+  const double unc = (legal[i] > 0.0) ? __ddiv_rn(__dsub_rn(e2, dmin), den) : 1.0;
+  const double r = __dsub_rn(1.0, unc);
+  rel[i] = r;
+  const bool en = r > thr;
+  if (enable) enable[i] = en ? 1 : 0;
+  if (gate32) gate32[i] = en ? 1.f : 0.f;
+  if (en && counts) {
+    atomicAdd(counts + (int)(i % J), 1);
+    atomicAdd(counts + J, 1);
   }
 }
 
