@@ -87,6 +87,9 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ void stg_cs(float4* p, const float4& v) {       // evict-first streaming store
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w)

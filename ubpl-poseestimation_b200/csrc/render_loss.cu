@@ -12,6 +12,7 @@
 // (<= 5 ulp of the reference's float64 value, tolerance 1e-5); the 0.01 cut is re-evaluated in
 // float64 for the rare pixel within 1e-5 of it so the support is identical to the reference's.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ubpl {
 
@@ -25,8 +26,14 @@ __device__ __forceinline__ float4 load4(const float* base, int q, int n, bool ve
   if (k + 3 < n) r.w = __ldg(base + k + 3);
   return r;
 }
+__device__ int g_store_mode = 0;   // experiment knob (UBPL_K3_STORE): 0 = L1::no_allocate, 1 = .cs, 2 = default
 __device__ __forceinline__ void store4(float* base, int q, int n, bool vec, const float4& v) {
-  if (vec) { stg_stream(reinterpret_cast<float4*>(base) + q, v); return; }
+  if (vec) {
+    float4* p = reinterpret_cast<float4*>(base) + q;
+    const int m = g_store_mode;
+    if (m == 0) stg_stream(p, v); else if (m == 1) stg_cs(p, v); else *p = v;
+    return;
+  }
   const int k = q << 2;
   if (k < n) base[k] = v.x;
   if (k + 1 < n) base[k + 1] = v.y;
@@ -387,6 +394,12 @@ extern "C" int ubpl_render_mse(const float* kps, const float* gate_in, const flo
   int vec = (W % 4 == 0) && aligned16(pred) && pB % 4 == 0 && pS % 4 == 0 && pJ % 4 == 0;
   if (grad) vec = vec && aligned16(grad) && gB % 4 == 0 && gS % 4 == 0 && gJ % 4 == 0;
   if (target) vec = vec && aligned16(target) && (HW % 4 == 0);
+  static bool knob_set = false;
+  if (!knob_set) {
+    const int m = getenv("UBPL_K3_STORE") ? atoi(getenv("UBPL_K3_STORE")) : 0;
+    cudaMemcpyToSymbol(g_store_mode, &m, sizeof(int));
+    knob_set = true;
+  }
   FastDiv divW4;
   divW4.init((unsigned)(W >= 4 ? W / 4 : 1));
   const int wpb = 4;    // small CTAs: one (b,j) item per warp, finer-grained tail
