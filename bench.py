@@ -221,7 +221,7 @@ def run_ours(args):
         td.init_process_group("nccl", device_id=dev)
         group = td.group.WORLD
         from ubpl_b200 import dist as ubpl_dist
-        ubpl_dist.init_nccl(group)                 # the library's own communicator for the histogram all-reduce
+        # (the selector's communicator / exchange buffer is created below, once the config is known)
     c = CONFIGS[args.config]
     B, K, M, S, J, H, W = (c[k] for k in "BKMSJHW")
     d = synth.make_batch(B=B, K=K, J=J, H=H, W=W, M=M, S=S, seed=1388, rank=rank, device=dev)
@@ -240,21 +240,32 @@ def run_ours(args):
     # The step is captured into four CUDA graphs (K1, K2, K3+reduction, K4) so that the ~12 launches of a
     # 0.2 ms step do not leave the GPU waiting for the host; stage edges are still CUDA events on the
     # launching stream, recorded live in the timed region.
+    if group is not None and c["select"] == "quantile" and os.environ.get("UBPL_BENCH_P2P", "1") != "0":
+        # the fused selector exchanges the ranks' keys over NVLink peer memory inside its one kernel; when the
+        # IPC mapping is not possible the NCCL selector (eager K2/K3 stages) stays in use
+        p2p_ok = ubpl_dist.init_p2p(group, max_items=max(B * J, 1))
+    else:
+        p2p_ok = False
+    if group is not None and c["select"] == "quantile" and not p2p_ok:
+        ubpl_dist.init_nccl(group)                 # the library's own communicator for the histogram all-reduce
+    overlap = os.environ.get("UBPL_BENCH_OVERLAP_EMA", "0") != "0"
     gstep = pipeline.GraphedStep(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, group=group,
-                                 stats=stats, ema=plan, alpha=alpha)
+                                 stats=stats, ema=plan, alpha=alpha, overlap_ema=overlap,
+                                 mode=os.environ.get("UBPL_BENCH_GRAPH", "single"))
     r = gstep.state
+    single = gstep.mode == "single"
     stage_events = []
 
     def step(timed=False):
         evs = {}
 
         def mark(name):
-            if timed:
+            if timed and not single:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
                 evs[name] = e
         gstep.run(timer=mark)
-        if timed:
+        if timed and not single:
             stage_events.append(evs)
 
     def barrier():
@@ -286,6 +297,16 @@ def run_ours(args):
     barrier()
     launches = launches_per_step * args.steps
     ms_total = e0.elapsed_time(e1)
+    stage_samples = []
+    if single:
+        # the stage edges are event-record nodes INSIDE the step's graph: every timed step records them; they
+        # are read for the last timed step and for 32 more steps of the same loop (a read needs a sync, which
+        # must stay out of the timed region)
+        stage_samples.append(gstep.stage_ms())
+        for _ in range(32):
+            step()
+            torch.cuda.synchronize()
+            stage_samples.append(gstep.stage_ms())
     # post-roll: keep the same load running (untimed) until nvidia-smi has had >= 0.6 s of it to sample
     while time.time() - t_load0 < 0.6:
         for _ in range(20):
@@ -302,8 +323,16 @@ def run_ours(args):
     # per-stage device time (CUDA events on the launching stream), averaged over the timed steps
     def avg(a, b):
         return sum(ev[a].elapsed_time(ev[b]) for ev in stage_events) / len(stage_events)
-    k1_ms, k2_ms, k3_ms = avg("k1_0", "k1_1"), avg("k2_0", "k2_1"), avg("k3_0", "k3_1")
-    # K4 runs concurrently with K1 inside the K1 graph; its stand-alone time is measured here, outside the timed region
+
+    def savg(n):
+        return sum(sm[n] for sm in stage_samples) / len(stage_samples)
+    if single:
+        k1_ms, k2_ms, k3_ms = savg("k1"), savg("k2"), savg("k3")
+        k4_inline_ms = savg("k4") if "k4" in stage_samples[0] else None
+    else:
+        k1_ms, k2_ms, k3_ms = avg("k1_0", "k1_1"), avg("k2_0", "k2_1"), avg("k3_0", "k3_1")
+        k4_inline_ms = avg("k4_0", "k4_1") if "k4_0" in stage_events[0] else None
+    # the stand-alone time of K4 (one graph replay per launch), measured outside the timed region
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g4 = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g4):
@@ -324,11 +353,18 @@ def run_ours(args):
     roof = {"bound": "hbm", "kernel": "warp_decode_kernel (K1: %d maps of %d B per launch)" % (M * K * B * J, 4 * H * W),
             "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC.get(args.config), "peak_source": peak_src,
-            "stages_ms": {"k1_warp_decode_with_k4_ema_overlapped": k1_ms, "k2_uncertainty_select": k2_ms, "k3_render_mse": k3_ms,
-                          "k4_ema_standalone": k4_ms},
+            "stages_ms": {("k1_warp_decode_with_k4_ema_overlapped" if gstep.overlap_ema else "k1_warp_decode"): k1_ms,
+                          "k2_uncertainty_select": k2_ms, "k3_render_mse": k3_ms,
+                          "k4_ema_in_step": k4_inline_ms, "k4_ema_standalone": k4_ms},
+            "stages_note": ("stage edges are event-record nodes inside the step's single CUDA graph; mean of the last "
+                            "timed step and 32 further steps" if single else
+                            "stage edges are CUDA events recorded around each stage graph in every timed step"),
+            "k2_fused_into_k1": bool(cfg.fuse_k12 and M == 1),
             "stages_gbs": {"k1": k1_bytes / (k1_ms * 1e-3) / 1e9, "k3": k3_bytes / (k3_ms * 1e-3) / 1e9,
                            "k4": ema_bytes / (k4_ms * 1e-3) / 1e9, "chain_k1_k3": chain_gbs},
             "chain_frac_of_peak": chain_gbs / peak, "chain_frac_of_8TBs": chain_gbs / 8000.0,
+            "step_gbs_with_ema": (bytes_sample * B + ema_bytes) / (ms_step * 1e-3) / 1e9,
+            "step_frac_of_peak_with_ema": (bytes_sample * B + ema_bytes) / (ms_step * 1e-3) / 1e9 / peak,
             "algorithmic_bytes_per_sample": bytes_sample}
     slow_frac = float(stats[0]) / max(1.0, float(stats[2]))
 
@@ -377,7 +413,13 @@ def run_ours(args):
                        "heatmap": [H, W], "select": c["select"], "distThrMax": DIST_THR_MAX,
                        "ema_params": n_params, "l2": "inputs (%.0f MB/step) larger than L2" % (bytes_sample * B / 1e6),
                        "selected_frac": float(r["enable"].float().mean()), "exhaustive_decode_frac": slow_frac,
-                       "launch": "3 CUDA graphs per step (K1 with the EMA forked onto a side stream, K2, K3), stage edges are CUDA events"},
+                       "launch": ("1 CUDA graph per step" if single else "%d stage launches per step (%s)" % (len(gstep.order), ", ".join(
+                                      n + (":eager" if n in gstep.eager else ":graph") for n in gstep.order)))
+                                 + ("; EMA forked onto a side stream beside K1" if gstep.overlap_ema else "; EMA after K3"),
+                       "selector": ("fixed rule in K1's epilogue" if c["select"] == "fixed" and cfg.fuse_k12 and M == 1 else
+                                    "fused one-kernel quantile selector" + (" over NVLink peer memory" if p2p_ok else "")
+                                    if (world == 1 or p2p_ok) and c["select"] == "quantile" else
+                                    "NCCL histogram all-reduce" if c["select"] == "quantile" else "k2 kernels")},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(t)},

@@ -53,7 +53,8 @@ int ubpl_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_opti
  *         out_xy float32[2] (image space, integer valued), out_hm_xy float32[2] (1-based heat-map
  *         coordinates after the max<=0 mask and the optional refinement); any may be NULL.
  * stats   optional int64[4] device counters, incremented: [0] maps decoded by exhaustive
- *         evaluation, [1] output pixels evaluated, [2] maps, [3] reserved.
+ *         evaluation, [1] output pixels evaluated, [2] maps, [3] maps repeated on the full view after the
+ *         early-release window proved too small.
  * slow_ws optional int32[V*B*J + 1] device scratch: with it, the (rare) maps that need the exhaustive
  *         decode are queued and decoded by whole CTAs in a second kernel launched right after the first
  *         (better tail); NULL decodes them in place.
@@ -64,6 +65,27 @@ int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
                      int do_warp, int refine,
                      int32_t* out_idx, float* out_max, float* out_xy, float* out_hm_xy,
                      int64_t* stats, int32_t* slow_ws, void* stream);
+
+/* K1 with the per-joint part of K2 fused into its epilogue (mean-teacher path: one teacher, V = K views).
+ * Decodes like ubpl_warp_decode(do_warp = 1); in addition every decoded map bumps the arrival counter of
+ * its (sample, joint) and the warp that completes the K views computes, with the arithmetic of
+ * ubpl_view_dispersion / ubpl_k2_view_fixed (utils/evaluation.py:44-54, utils/business.py:237-261,375-376,
+ * utils/process.py:262-268, utils/losses.py:29):
+ *   k2_mode 1: mean [B,J,2] f32, dist [B,J] f64 (999 where a view is illegal), legal [B,J] u8
+ *   k2_mode 2: + enable [B,J] u8, gate [B,J] f32 (= enable * visibility) and the counts below
+ * so the chain needs no K2 launch (mode 2) or only the quantile selector (mode 1).
+ * ws   int32 workspace of ubpl_warp_decode_k2_ws_bytes(V, B, J) bytes, 8-byte aligned; the call clears its
+ *      head with one memset node.  After the launch ws[4 .. 4+J) = selected items per joint, ws[4+J] = total
+ *      selected, ws[4+J+1] = S * #(gate > 0) (mode 2) -- the `count_in` of ubpl_render_mse.
+ * Requires 1 <= V <= 32.  mean/dist/legal/enable may be NULL. */
+int64_t ubpl_warp_decode_k2_ws_bytes(int V, int B, int J);
+int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
+                        int V, int B, int J, int H, int W,
+                        const float* theta, const uint8_t* flip, const double* dec, int refine,
+                        int32_t* out_idx, float* out_max, float* out_xy,
+                        int k2_mode, double distThrMax, int img_h, int img_w, float stride, float sigma, int S,
+                        float* mean, double* dist, uint8_t* legal, uint8_t* enable, float* gate,
+                        int64_t* stats, int32_t* ws, int64_t ws_bytes, void* stream);
 
 /* Materialises the back-warped (and un-flipped) maps: the tensor AugmentUtils.affine_back2
  * returns (utils/augment.py:37-47).  in [N, C, H, W] strides (sN, sC); out likewise (oN, oC);
@@ -155,7 +177,35 @@ int ubpl_select_quantile_dist(const double* dist, const double* legal, int64_t n
                               double reliableThr, double reliableDistMin, double* reliability,
                               uint64_t* keys, uint8_t* enable, float* gate32, int32_t* counts,
                               double* thr_out, void* ws, void* stream);
-/* NCCL plumbing for the call above (libnccl.so.2 is resolved with dlopen): rank 0 obtains a 128-byte
+/* The selector as ONE kernel per GPU (single CTA), single- and multi-GPU:
+ *   use_p2p = 0: this GPU's n items are the whole population (k_rank < n; keys = uint64[n] scratch);
+ *   use_p2p = 1: every rank stores its distance keys, extrema and item count into its slot of every peer's
+ *                exchange buffer over NVLink (ubpl_p2p_alloc / ubpl_p2p_open), publishes an epoch flag, waits
+ *                for the peers' flags and then selects over all ranks' keys locally -- no NCCL call, no host
+ *                work, capturable in a CUDA graph; k_rank = int((n_total-1)*reliablePCT) over all ranks.
+ *                Every rank must make the same sequence of calls (it is a collective).
+ * legal: float64[n] or uint8[n] (exactly one non-NULL).  Outputs as ubpl_select_quantile_local.
+ * kps != NULL (float32 [n,2], image space) folds ubpl_gate_prepare into the launch: gate32 = enable *
+ * visibility, *count_out = S * #(gate32 > 0), *grad_scale = loss_weight / count. */
+int ubpl_select_quantile_fused(const double* dist, const double* legal_f64, const uint8_t* legal_u8, int64_t n,
+                               int J, int64_t k_rank, double reliableThr, double reliableDistMin,
+                               double* reliability, uint64_t* keys, uint8_t* enable, float* gate32,
+                               int32_t* counts, double* thr_out, double* ext_out,
+                               const float* kps, int img_h, int img_w, float stride, float sigma, int S,
+                               float loss_weight, float* grad_scale, int32_t* count_out,
+                               int use_p2p, void* stream);
+/* Peer-memory exchange buffer of the call above, one per process (= per GPU).  ubpl_p2p_alloc allocates it for
+ * `nranks` ranks of at most `max_items` items each and returns its 64-byte CUDA-IPC handle (host buffer); the
+ * handles of all ranks, concatenated in rank order (any transport, e.g. torch.distributed all_gather), go to
+ * ubpl_p2p_open, which maps the peers' buffers.  ubpl_p2p_status: 0, or 1 after a launch in which a peer did
+ * not arrive within the kernel's 4 s time-out (its outputs are then NaN-poisoned instead of hanging). */
+int64_t ubpl_p2p_buffer_bytes(int nranks, int64_t max_items);
+int ubpl_p2p_alloc(int nranks, int64_t max_items, void* handle_out64_host);
+int ubpl_p2p_open(const void* handles_host, int nranks, int rank);
+int ubpl_p2p_close(void);
+int ubpl_p2p_ranks(void);
+int ubpl_p2p_status(void);
+/* NCCL plumbing for ubpl_select_quantile_dist (libnccl.so.2 is resolved with dlopen): rank 0 obtains a 128-byte
  * unique id (host buffer), shares it by any means (torch.distributed broadcast), every rank calls init. */
 int ubpl_nccl_unique_id(void* out128_host);
 int ubpl_nccl_init(const void* id128_host, int nranks, int rank);
@@ -197,6 +247,18 @@ int ubpl_render_mse(const float* kps, const float* gate_in, const float* sample_
                     int img_h, int img_w, float stride, float sigma,
                     const float* grad_scale, const int32_t* count_in, float loss_weight,
                     float* grad_scale_out, float* gate_out, float* per_loss, void* stream);
+/* ubpl_render_mse with the loss reduction fused into the same launch: the CTA that finishes last writes
+ * summary float64[4] = (sum(per_loss), #(per_loss > 0), B*S*J, #(gate_out > 0)), i.e. what
+ * ubpl_loss_finalize(per_loss, NULL, gate_out) returns.  ticket: a device uint32 that is zero before the
+ * first launch; the kernel returns it to zero (launches sharing a ticket must not run concurrently). */
+int ubpl_render_mse_sum(const float* kps, const float* gate_in, const float* sample_w,
+                        const float* pred, int64_t pB, int64_t pS, int64_t pJ,
+                        float* grad, int64_t gB, int64_t gS, int64_t gJ,
+                        float* target, int B, int S, int J, int H, int W,
+                        int img_h, int img_w, float stride, float sigma,
+                        const float* grad_scale, const int32_t* count_in, float loss_weight,
+                        float* grad_scale_out, float* gate_out, float* per_loss,
+                        double* summary, uint32_t* ticket, void* stream);
 /* kps_heatmap alone (utils/process.py:253-278): kps [N,3] float32 (x,y,w) -> heatmap [N,H,W],
  * kps_out [N,3] with w *= visibility. */
 int ubpl_render_targets(const float* kps, int N, int H, int W, int img_h, int img_w, float stride,

@@ -1,0 +1,308 @@
+"""GPU parity tests of the fused / early-release variants added on top of the first CUDA path:
+K1 with the K2 epilogue (ubpl_warp_decode_k2), the early-release staging window and the L2 prefetch knob,
+K3 with the loss reduction in its last CTA (ubpl_render_mse_sum), the one-kernel quantile selector
+(ubpl_select_quantile_fused) and the single-graph step with event nodes.  Bars as in test_gpu_parity.py:
+indices, masks and float64 dispersions bit-exact; losses within 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ubpl_oracle as O
+from golden_util import load
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ubpl_b200
+    from ubpl_b200 import ops as _ops
+    return _ops
+
+
+def cu(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+class _Env:
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+KNOBS = [dict(UBPL_K1_EARLY=0, UBPL_K1_PF=0), dict(UBPL_K1_EARLY=1, UBPL_K1_PF=0), dict(UBPL_K1_EARLY=0, UBPL_K1_PF=1),
+         dict(UBPL_K1_EARLY=1, UBPL_K1_PF=1)]
+
+
+@pytest.mark.parametrize("knobs", KNOBS)
+@pytest.mark.parametrize("name", ["chain_mt", "chain_dual"])
+def test_k1_variants_golden(ops, knobs, name):
+    """Every staging variant of K1 reproduces the reference's indices, scores and coordinates."""
+    g = load(name)
+    t = g["teacher"]
+    M, K, B, J, H, W = t.shape
+    dec = ops.decode_coeffs(torch.as_tensor(g["center"]), torch.as_tensor(g["scale"]), [H, W]).cuda()
+    with _Env(**knobs):
+        for m in range(M):
+            for slow in (True, False):
+                r = ops.warp_decode(cu(t[m]), cu(g["theta"]), cu(g["flip"]), dec, defer_exhaustive=slow)
+                assert np.array_equal(npy(r["idx"]).astype(np.int64), g["argmax_idx"][m])
+                assert np.array_equal(npy(r["max"]), g["max_val"][m])
+                assert np.array_equal(npy(r["xy"]), g["preds_multi"][m])
+
+
+def _edge_maps():
+    H = W = 64
+    rng = np.random.default_rng(11)
+    maps = np.zeros((4, 3, 10, H, W), np.float32)
+    maps[:, :, 0] = 1.0                                    # constant: every tie -> first index
+    maps[:, :, 1] = -1.0                                   # all negative
+    maps[:, :, 2, 10, 20] = 0.5
+    maps[:, :, 2, 40, 3] = 0.5                             # exact tie between two far texels (window must be refused)
+    maps[:, :, 3] = rng.standard_normal((H, W)) * 1e-3     # noise only
+    maps[:, :, 4, 0, 0] = 2.0                              # peaks in the corners: window hangs over the map edge
+    maps[:, :, 5, 63, 63] = 2.0
+    maps[:, :, 6] = rng.standard_normal((H, W))
+    maps[:, :, 6, 30, 30] = np.nan
+    maps[:, :, 7] = np.abs(rng.standard_normal((H, W))) + 5.0
+    yy, xx = np.mgrid[0:H, 0:W]
+    maps[:, :, 8] = np.exp(-((xx - 3.2) ** 2 + (yy - 60.7) ** 2) / 18.0)           # blob near an edge
+    maps[:, :, 9] = np.exp(-((xx - 31.5) ** 2 + (yy - 31.5) ** 2) / 200.0)         # broad plateau: four tied texels
+    th = np.zeros((4, 3, 2, 3), np.float32)
+    for v in range(4):
+        for b in range(3):
+            ang = np.deg2rad(rng.uniform(-30, 30))
+            sc = rng.uniform(0.7, 1.4)
+            th[v, b] = [[np.cos(ang) * sc, -np.sin(ang) * sc, 0], [np.sin(ang) * sc, np.cos(ang) * sc, 0]]
+    th[0, 0] = [[1, 0, 0], [0, 1, 0]]
+    th[1, 1] = [[0.5, 0, 0.3], [0, 0.5, -0.2]]             # zoom + translation
+    th[2, 2] = [[2.5, 0, 0], [0, 2.5, 0]]                  # strong minification: wide footprints leave the window
+    fl = (rng.random((4, 3)) < 0.5).astype(np.uint8)
+    return maps, th, fl
+
+
+@pytest.mark.parametrize("knobs", KNOBS)
+def test_k1_variants_edge_cases_vs_oracle(ops, knobs):
+    maps, th, fl = _edge_maps()
+    V, B, J, H, W = maps.shape
+    center = np.full((B, 2), 128.0, np.float32)
+    scale = np.full((B,), 1.28, np.float32)
+    back = np.stack([O.affine_back2(maps[v], th[v], fl[v]) for v in range(V)])
+    val, idx = O.argmax_first(back)
+    xy = np.stack([O.final_preds(back[v], center, scale, [H, W], "f32") for v in range(V)])
+    dec = ops.decode_coeffs(torch.as_tensor(center), torch.as_tensor(scale), [H, W]).cuda()
+    with _Env(**knobs):
+        stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+        r = ops.warp_decode(cu(maps), cu(th), cu(fl), dec, stats=stats)
+    assert np.array_equal(npy(r["idx"]).astype(np.int64), idx)
+    assert np.array_equal(npy(r["max"]), val, equal_nan=True)
+    assert np.array_equal(npy(r["xy"]), xy)
+    assert int(stats[2]) == V * B * J
+
+
+def test_k1_early_release_full_size(ops):
+    """BASELINE config 2 sizes: the early-release kernel is bit-identical to the plain one on every map, and the
+    window suffices for the bulk of the maps (few repeats on the full view)."""
+    from ubpl_b200 import synth
+    B, K, J = 256, 8, 14
+    d = synth.make_batch(B=B, K=K, J=J, M=1, S=1, device="cuda")
+    dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64])
+    outs = {}
+    for early in (0, 1):
+        with _Env(UBPL_K1_EARLY=early, UBPL_K1_PF=0):
+            stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+            outs[early] = (ops.warp_decode(d["teacher"][0], d["theta"], d["flip"], dec, stats=stats), stats.cpu())
+    for k in ("idx", "max", "xy"):
+        assert torch.equal(outs[0][0][k], outs[1][0][k]), k
+    n_maps, n_miss = int(outs[1][1][2]), int(outs[1][1][3])
+    assert n_maps == K * B * J
+    assert n_miss < 0.10 * n_maps, (n_miss, n_maps)
+    assert int(outs[0][1][3]) == 0
+
+
+@pytest.mark.parametrize("knobs", KNOBS[:2])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_warp_decode_k2_matches_unfused(ops, knobs, mode):
+    """The K2 epilogue fused into K1 gives exactly what the separate K2 kernels give on the same decode."""
+    from ubpl_b200 import synth
+    for (B, K, J, seed) in ((8, 4, 6, 1), (33, 8, 14, 2), (5, 1, 3, 3), (4, 32, 2, 4)):
+        d = synth.make_batch(B=B, K=K, J=J, M=1, S=2, seed=seed, jitter=0.7, device="cuda")
+        dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64])
+        with _Env(**knobs):
+            r = ops.warp_decode_k2(d["teacher"][0], d["theta"], d["flip"], dec, mode, S=2, distThrMax=2.0)
+            ref = ops.warp_decode(d["teacher"][0], d["theta"], d["flip"], dec)
+        for k in ("idx", "max", "xy"):
+            assert torch.equal(r[k], ref[k]), k
+        if mode == 2:
+            k2 = ops.k2_view_fixed(ref["xy"], 2.0, 2, 256, 256, 4.0, 3.0)
+            for k in ("mean", "dist", "legal", "enable", "gate"):
+                assert torch.equal(r[k], k2[k]), k
+            assert torch.equal(r["counts"], k2["counts"])
+            assert int(r["count"]) == int(k2["count"])
+        else:
+            vd = ops.view_dispersion(ref["xy"], sentinel_illegal=True)
+            for k in ("mean", "dist", "legal"):
+                assert torch.equal(r[k], vd[k]), k
+        # the workspace cleans up after itself: arrival counters are back to zero
+        assert int(r["ws"][4 + ((J + 3) & ~1):4 + ((J + 3) & ~1) + B * J].abs().sum()) == 0
+
+
+def test_warp_decode_k2_golden(ops):
+    g = load("chain_mt")
+    t = g["teacher"]
+    M, K, B, J, H, W = t.shape
+    dec = ops.decode_coeffs(torch.as_tensor(g["center"]), torch.as_tensor(g["scale"]), [H, W]).cuda()
+    r = ops.warp_decode_k2(cu(t[0]), cu(g["theta"]), cu(g["flip"]), dec, 1)
+    assert np.array_equal(npy(r["xy"]), g["preds_multi"][0])
+    assert np.array_equal(npy(r["mean"]), g["preds_mean"][0])
+
+
+def test_render_mse_fused_summary(ops):
+    g = load("render")
+    rng = np.random.default_rng(2)
+    for (B, S, J) in ((4, 2, 6), (37, 1, 5), (256, 2, 14)):
+        kps = cu(rng.uniform(-10, 266, (B, J, 2)).astype(np.float32))
+        gate = cu((rng.random((B, J)) < 0.6).astype(np.float32))
+        w = cu((rng.random(B) < 0.7).astype(np.float32))
+        pred = cu(rng.standard_normal((B, S, J, 64, 64)).astype(np.float32) * 0.1)
+        a = ops.render_mse(kps, gate, w, pred, 256, 256, want_summary=True)
+        b = ops.render_mse(kps, gate, w, pred, 256, 256)
+        want = ops.loss_finalize(b["per_loss"], None, b["gate_out"])
+        assert torch.equal(a["per_loss"], b["per_loss"]) and torch.equal(a["grad"], b["grad"])
+        np.testing.assert_allclose(npy(a["summary"]), npy(want), rtol=1e-12)
+        assert npy(a["summary"])[1:].tolist() == npy(want)[1:].tolist()          # the counts are exact
+        # twice through the same ticket ring: the ticket returned to zero
+        a2 = ops.render_mse(kps, gate, w, pred, 256, 256, want_summary=True)
+        assert torch.equal(a2["summary"], a["summary"])
+
+
+def test_select_quantile_fused_vs_oracle(ops):
+    rng = np.random.default_rng(31)
+    for n, J in ((1, 1), (7, 7), (1000, 10), (4352, 17), (24576, 16), (24577, 17), (100000, 17)):
+        dist = np.round(rng.gamma(2.0, 3.0, n) * 4) / 4          # many exact ties
+        dist[rng.random(n) < 0.2] = 999.0
+        legal = (rng.random(n) < 0.9)
+        for pct, rthr in ((0.5, 0.0), (0.1, 0.0), (0.99, 0.0), (0.5, 0.8), (0.0, 0.0), (1.0, 0.0)):
+            rel, thr, en = O.filter_dual(dist, legal.astype(np.float64), rthr, pct, 1.0)
+            for lg in (cu(legal.astype(np.uint8)), cu(legal.astype(np.float64))):
+                s = ops.select_quantile_fused(cu(dist), lg, J, int((n - 1) * pct), rthr, 1.0)
+                assert float(s["thr"]) == thr, (n, pct)
+                assert np.array_equal(npy(s["enable"]).astype(bool), en)
+                assert np.array_equal(npy(s["reliability"]), rel)
+                assert int(s["counts"][-1]) == int(en.sum())
+    # continuous distances (no ties), all distinct exponents, and the all-illegal corner
+    for n in (513, 30000):
+        dist = np.minimum(rng.gamma(2.0, 3.0, n) * 10.0 ** rng.integers(-3, 2, n), 900.0)
+        legal = np.ones(n)
+        rel, thr, en = O.filter_dual(dist, legal, 0.0, 0.37, 1.0)
+        s = ops.select_quantile_fused(cu(dist), cu(legal), 3, int((n - 1) * 0.37), 0.0, 1.0)
+        assert float(s["thr"]) == thr and np.array_equal(npy(s["enable"]).astype(bool), en)
+    dist = np.full(64, 999.0)
+    legal = np.zeros(64)
+    rel, thr, en = O.filter_dual(dist, legal, 0.0, 0.5, 1.0)
+    s = ops.select_quantile_fused(cu(dist), cu(legal), 4, 31, 0.0, 1.0)
+    assert float(s["thr"]) == thr and np.array_equal(npy(s["enable"]).astype(bool), en)
+
+
+def test_select_quantile_fused_gate(ops):
+    """The gate_prepare fusion of the selector equals selector + ubpl_gate_prepare."""
+    rng = np.random.default_rng(8)
+    n, J, S = 4352, 17, 2
+    dist = np.round(rng.gamma(2.0, 3.0, n) * 4) / 4
+    legal = (rng.random(n) < 0.9).astype(np.uint8)
+    kps = cu(rng.uniform(-5, 261, (n, 2)).astype(np.float32))
+    a = ops.select_quantile_fused(cu(dist), cu(legal), J, (n - 1) // 2, 0.0, 1.0, gate=(kps, S, 256, 256, 4.0, 3.0, 0.7))
+    b = ops.select_quantile_fused(cu(dist), cu(legal), J, (n - 1) // 2, 0.0, 1.0)
+    gate, gs, cnt = ops.gate_prepare(kps, b["gate"], S, 256, 256, 4.0, 3.0, 0.7)
+    assert torch.equal(a["gate"], gate) and int(a["count"]) == int(cnt) and float(a["grad_scale"]) == float(gs)
+    assert torch.equal(a["enable"], b["enable"])
+
+
+def test_select_quantile_legacy_kernel_still_agrees(ops):
+    rng = np.random.default_rng(5)
+    n, J = 4352, 17
+    dist = np.round(rng.gamma(2.0, 3.0, n) * 4) / 4
+    dist[rng.random(n) < 0.2] = 999.0
+    legal = (rng.random(n) < 0.9).astype(np.float64)
+    a = ops.select_quantile(cu(dist), cu(legal), J, 0.0, 0.5, 1.0)
+    with _Env(UBPL_SELECT="legacy"):
+        b = ops.select_quantile(cu(dist), cu(legal), J, 0.0, 0.5, 1.0)
+    for k in ("thr", "enable", "reliability", "counts"):
+        assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("select", ["fixed", "quantile"])
+@pytest.mark.parametrize("k12", [True, False])
+def test_pipeline_fusion_flags_vs_oracle(ops, select, k12):
+    from ubpl_b200 import synth, pipeline
+    d = synth.make_batch(B=8, K=4, J=6, M=1, S=2, seed=77, jitter=0.5)
+    n = {k: v.numpy() for k, v in d.items()}
+    o = O.pseudo_label_chain(n["teacher"], n["student"], n["theta"], n["flip"], n["center"], n["scale"], n["islabeled"],
+                             select=select, distThrMax=2.0, lossWeight=0.7)
+    dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64]).cuda()
+    w = pipeline.nega_weights(d["islabeled"].cuda(), 1.0)
+    for fsum in (True, False):
+        cfg = pipeline.StepConfig(select=select, distThrMax=2.0, lossWeight=0.7, fuse_k12=k12, fuse_sum=fsum)
+        r = pipeline.pseudo_label_step(d["teacher"].cuda(), d["student"].cuda(), d["theta"].cuda(), d["flip"].cuda(), dec, w, cfg)
+        assert np.array_equal(npy(r["idx"]).astype(np.int64), o["idx"])
+        assert np.array_equal(npy(r["enable"]).astype(bool).reshape(o["enable"].shape), o["enable"])
+        assert np.array_equal(npy(r["gate"]).reshape(o["gate"].shape), o["gate"])
+        np.testing.assert_allclose(npy(r["dist"]).reshape(o["dist"].shape), o["dist"], rtol=1e-12)
+        assert int(r["count"]) == o["count"]
+        loss = float(r["summary"][0]) * float(r["grad_scale"])
+        np.testing.assert_allclose(loss, o["loss"], rtol=RTOL)
+        np.testing.assert_allclose(npy(r["grad"]), o["grad"], rtol=RTOL, atol=1e-10)
+
+
+@pytest.mark.parametrize("mode", ["single", "stages"])
+@pytest.mark.parametrize("select", ["fixed", "quantile"])
+def test_graphed_step_modes(ops, mode, select):
+    """One graph with event-record nodes (what bench.py times) == per-stage graphs == eager."""
+    from ubpl_b200 import synth, pipeline
+    d = synth.make_batch(B=8, K=4, J=6, M=1, S=2, seed=15, jitter=0.5, device="cuda")
+    d2 = synth.make_batch(B=8, K=4, J=6, M=1, S=2, seed=16, jitter=0.5, device="cuda")
+    dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64])
+    w = pipeline.nega_weights(d["islabeled"], 1.0)
+    cfg = pipeline.StepConfig(select=select, distThrMax=2.0)
+    e = torch.randn(1000, device="cuda"); p = torch.randn(1000, device="cuda")
+    plan = ops.EmaPlan([p], [e])
+    bufs = {k: d[k].clone() for k in ("teacher", "student", "theta", "flip")}
+    g = pipeline.GraphedStep(bufs["teacher"], bufs["student"], bufs["theta"], bufs["flip"], dec, w, cfg, ema=plan, alpha=0.5,
+                             mode=mode)
+    assert g.mode == mode
+    for data in (d, d2, d):
+        for k in ("teacher", "student", "theta"):
+            g.state[k].copy_(data[k])
+        g.state["flip"].copy_(data["flip"].to(torch.uint8))
+        st = g.run()
+        torch.cuda.synchronize()
+        ref = pipeline.pseudo_label_step(data["teacher"], data["student"], data["theta"], data["flip"], dec, w, cfg)
+        for k in ("idx", "max", "xy", "enable", "gate", "grad", "target", "summary", "grad_scale", "count"):
+            assert torch.equal(st[k].reshape(-1), ref[k].reshape(-1)), k
+        if mode == "single":
+            ms = g.stage_ms()
+            assert set(ms) >= {"k1", "k2", "k3"} and all(v >= 0.0 for v in ms.values())
+            assert 0.0 < sum(ms.values()) < 50.0

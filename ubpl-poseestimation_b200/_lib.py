@@ -20,6 +20,13 @@ SIGNATURES = {
     "ubpl_warp_decode": [c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
                          c_void_p, c_void_p, c_void_p, c_int, c_int,
                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ubpl_warp_decode_k2": [c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
+                            c_void_p, c_void_p, c_void_p, c_int,
+                            c_void_p, c_void_p, c_void_p,
+                            c_int, c_double, c_int, c_int, c_float, c_float, c_int,
+                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_void_p, c_i64, c_void_p],
+    "ubpl_warp_decode_k2_ws_bytes": [c_int, c_int, c_int],
     "ubpl_warp_materialize": [c_void_p, c_i64, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p],
     "ubpl_view_dispersion": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
@@ -37,6 +44,16 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_select_quantile_dist": [c_void_p, c_void_p, c_i64, c_int, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ubpl_select_quantile_fused": [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64, c_double, c_double,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_int, c_float, c_float, c_int, c_float, c_void_p, c_void_p,
+                                   c_int, c_void_p],
+    "ubpl_p2p_buffer_bytes": [c_int, c_i64],
+    "ubpl_p2p_alloc": [c_int, c_i64, c_void_p],
+    "ubpl_p2p_open": [c_void_p, c_int, c_int],
+    "ubpl_p2p_close": [],
+    "ubpl_p2p_ranks": [],
+    "ubpl_p2p_status": [],
     "ubpl_nccl_unique_id": [c_void_p],
     "ubpl_nccl_init": [c_void_p, c_int, c_int],
     "ubpl_nccl_destroy": [],
@@ -47,6 +64,9 @@ SIGNATURES = {
     "ubpl_render_mse": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_i64, c_i64, c_i64,
                         c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                         c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ubpl_render_mse_sum": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_i64, c_i64, c_i64,
+                            c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                            c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_render_targets": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p],
     "ubpl_dense_mse": [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_int, c_i64, c_i64, c_i64, c_i64, c_void_p, c_int, c_float,
                        c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p,
@@ -57,6 +77,8 @@ SIGNATURES = {
     "ubpl_ema_multi_tensor": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_float, c_void_p],
     "ubpl_ema_flat": [c_void_p, c_void_p, c_i64, c_float, c_float, c_void_p],
 }
+
+RESTYPES = {"ubpl_warp_decode_k2_ws_bytes": c_i64, "ubpl_p2p_buffer_bytes": c_i64}      # everything else returns an int status code
 
 _lib = None
 
@@ -89,14 +111,14 @@ def lib():
         for name, args in SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the header and the library disagree
             fn.argtypes = args
-            fn.restype = c_int
+            fn.restype = RESTYPES.get(name, c_int)
         _lib = L
     return _lib
 
 
 # kernels launched per successful call (cudaMemsetAsync is not counted); bench.py's gpu_launches
-LAUNCHES = {"ubpl_dist_extrema": 2, "ubpl_warp_decode": 2, "ubpl_select_quantile_dist": 16, "ubpl_nccl_unique_id": 0,
-            "ubpl_nccl_init": 0, "ubpl_nccl_destroy": 0}
+LAUNCHES = {"ubpl_dist_extrema": 2, "ubpl_warp_decode": 2, "ubpl_warp_decode_k2": 2, "ubpl_select_quantile_dist": 16, "ubpl_nccl_unique_id": 0,
+            "ubpl_nccl_init": 0, "ubpl_nccl_destroy": 0, "ubpl_p2p_alloc": 0, "ubpl_p2p_open": 0, "ubpl_p2p_close": 0}
 _launches = 0
 
 

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128, 6) render_mse_kernel(
     long long gS, long long gJ, float* __restrict__ target, int B, int S, int J, int H, int W, int img_h, int img_w,
     float stride, float sigma, const float* __restrict__ grad_scale, const int32_t* __restrict__ count_in,
     float loss_weight, float* __restrict__ grad_scale_out, float* __restrict__ gate_out,
-    float* __restrict__ per_loss, const FastDiv divW4) {
+    float* __restrict__ per_loss, const FastDiv divW4, double* __restrict__ summary, unsigned* __restrict__ ticket) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   float* ex = sm + (size_t)warp * (W + H);   // [W]
@@ -194,6 +194,37 @@ __global__ void __launch_bounds__(128, 6) render_mse_kernel(
         const float tot = warp_sum(sse[ss]);
         if (lane == 0 && per_loss) per_loss[((long long)b * S + st0 + ss) * J + j] = ((tot * inv_hw) * gate) * wb;
       }
+    }
+  }
+  if (summary) {
+    // Loss reduction fused into this launch: the CTA that takes the last ticket reduces the [B,S,J] losses and
+    // the [B,J] gates in a fixed order (what loss_finalize_kernel computes with mask = NULL), so the chain
+    // needs no separate reduction launch.  The ticket counter returns to zero for the next launch.
+    __shared__ unsigned s_last;
+    __shared__ double s_red[3][32];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const long long BSJ = BJ * S;
+      double s = 0.0, np = 0.0, ng = 0.0;
+      for (long long i = threadIdx.x; i < BSJ; i += blockDim.x) {
+        const float l = __ldcg(per_loss + i);
+        s += (double)l;
+        np += (l > 0.f) ? 1.0 : 0.0;
+      }
+      for (long long i = threadIdx.x; i < BJ; i += blockDim.x) ng += (__ldcg(gate_out + i) > 0.f) ? 1.0 : 0.0;
+      s = warp_sum(s); np = warp_sum(np); ng = warp_sum(ng);
+      if (lane == 0) { s_red[0][warp] = s; s_red[1][warp] = np; s_red[2][warp] = ng; }
+      __syncthreads();
+      if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int i = 0; i < wpb; ++i) t += s_red[threadIdx.x][i];
+        summary[threadIdx.x == 2 ? 3 : threadIdx.x] = t;
+      }
+      if (threadIdx.x == 3) { summary[2] = (double)BSJ; *ticket = 0u; }
     }
   }
 }
@@ -381,12 +412,14 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 using namespace ubpl;
 
-extern "C" int ubpl_render_mse(const float* kps, const float* gate_in, const float* sample_w, const float* pred,
-                               int64_t pB, int64_t pS, int64_t pJ, float* grad, int64_t gB, int64_t gS, int64_t gJ,
-                               float* target, int B, int S, int J, int H, int W, int img_h, int img_w, float stride,
-                               float sigma, const float* grad_scale, const int32_t* count_in, float loss_weight,
-                               float* grad_scale_out, float* gate_out, float* per_loss, void* stream) {
+static int render_mse_impl(const float* kps, const float* gate_in, const float* sample_w, const float* pred,
+                           int64_t pB, int64_t pS, int64_t pJ, float* grad, int64_t gB, int64_t gS, int64_t gJ,
+                           float* target, int B, int S, int J, int H, int W, int img_h, int img_w, float stride,
+                           float sigma, const float* grad_scale, const int32_t* count_in, float loss_weight,
+                           float* grad_scale_out, float* gate_out, float* per_loss, double* summary, unsigned* ticket,
+                           void* stream) {
   UBPL_REQUIRE(kps && pred, "ubpl_render_mse: NULL pointer");
+  UBPL_REQUIRE(!summary || (ticket && gate_out && per_loss), "ubpl_render_mse_sum: summary needs ticket, gate_out and per_loss");
   UBPL_REQUIRE(B >= 0 && S >= 1 && J >= 0 && H > 0 && W > 0 && stride > 0.f && sigma > 0.f, "ubpl_render_mse: bad arguments");
   const long long BJ = (long long)B * J;
   if (BJ == 0) return UBPL_OK;
@@ -411,7 +444,7 @@ extern "C" int ubpl_render_mse(const float* kps, const float* gate_in, const flo
 #define UBPL_LAUNCH_RENDER(V, SSV)                                                                                     \
   render_mse_kernel<V, SSV><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(                                         \
       kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS, gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
-      grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4)
+      grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, ticket)
   if (vec) {
     if (S % 2 == 0) UBPL_LAUNCH_RENDER(true, 2); else UBPL_LAUNCH_RENDER(true, 1);
   } else {
@@ -419,6 +452,33 @@ extern "C" int ubpl_render_mse(const float* kps, const float* gate_in, const flo
   }
 #undef UBPL_LAUNCH_RENDER
   return check_launch("ubpl_render_mse");
+}
+
+extern "C" int ubpl_render_mse(const float* kps, const float* gate_in, const float* sample_w, const float* pred,
+                               int64_t pB, int64_t pS, int64_t pJ, float* grad, int64_t gB, int64_t gS, int64_t gJ,
+                               float* target, int B, int S, int J, int H, int W, int img_h, int img_w, float stride,
+                               float sigma, const float* grad_scale, const int32_t* count_in, float loss_weight,
+                               float* grad_scale_out, float* gate_out, float* per_loss, void* stream) {
+  return render_mse_impl(kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS, gJ, target, B, S, J, H, W, img_h, img_w,
+                         stride, sigma, grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, nullptr,
+                         nullptr, stream);
+}
+
+extern "C" int ubpl_render_mse_sum(const float* kps, const float* gate_in, const float* sample_w, const float* pred,
+                                   int64_t pB, int64_t pS, int64_t pJ, float* grad, int64_t gB, int64_t gS, int64_t gJ,
+                                   float* target, int B, int S, int J, int H, int W, int img_h, int img_w, float stride,
+                                   float sigma, const float* grad_scale, const int32_t* count_in, float loss_weight,
+                                   float* grad_scale_out, float* gate_out, float* per_loss, double* summary,
+                                   uint32_t* ticket, void* stream) {
+  UBPL_REQUIRE(summary && ticket, "ubpl_render_mse_sum: summary and ticket are required");
+  if ((long long)B * J == 0) {
+    cudaError_t e = cudaMemsetAsync(summary, 0, 4 * sizeof(double), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("ubpl_render_mse_sum: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+    return UBPL_OK;
+  }
+  return render_mse_impl(kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS, gJ, target, B, S, J, H, W, img_h, img_w,
+                         stride, sigma, grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, summary,
+                         ticket, stream);
 }
 
 extern "C" int ubpl_render_targets(const float* kps, int N, int H, int W, int img_h, int img_w, float stride,

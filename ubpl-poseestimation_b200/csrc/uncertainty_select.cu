@@ -13,35 +13,6 @@
 
 namespace ubpl {
 
-int pow_table(const int32_t** keys, const double** vals, const uint32_t** bits, int* n, int* rmax);
-
-struct PowTab {
-  const int32_t* key;
-  const double* val;
-  const uint32_t* bits;   // one bit per radicand: set where libm pow and sqrt disagree
-  int n, rmax;
-};
-
-// python: ((x1-x2)**2 + (y1-y2)**2) ** 0.5  == libm pow(r, 0.5); see api.cu for the table.
-__device__ __forceinline__ double py_dist(double x1, double y1, double x2, double y2, const PowTab& T) {
-  const double dx = __dsub_rn(x1, x2), dy = __dsub_rn(y1, y2);
-  const double r = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-  double d = sqrt(r);
-  if (r <= (double)T.rmax) {
-    const int ri = (int)r;
-    if ((double)ri == r && ((__ldg(T.bits + (ri >> 5)) >> (ri & 31)) & 1u)) {
-      int lo = 0, hi = T.n - 1;
-      while (lo <= hi) {
-        const int mid = (lo + hi) >> 1;
-        const int k = T.key[mid];
-        if (k == ri) { d = T.val[mid]; break; }
-        if (k < ri) lo = mid + 1; else hi = mid - 1;
-      }
-    }
-  }
-  return d;
-}
-
 __global__ void view_dispersion_kernel(const float* __restrict__ preds, const float* __restrict__ mean_in, int K,
                                        long long BJ, float* out_mean,
                                        double* out_dist, float* out_unc32, uint8_t* out_legal, uint32_t* max_bits,
@@ -677,3 +648,4 @@ extern "C" int ubpl_pair_distance(const double* c1, const double* c2, int64_t n,
 }
 
 #include "nccl_select.inc"
+#include "p2p_select.inc"

@@ -28,10 +28,39 @@
 // box) are decoded exhaustively by the same warp, so the result is exact in every case.
 #include "common.cuh"
 #include <stdlib.h>
+#include <string.h>
+
+#ifndef UBPL_K1_EARLY_DEFAULT
+#define UBPL_K1_EARLY_DEFAULT 1
+#endif
+#ifndef UBPL_K1_PF_DEFAULT
+#define UBPL_K1_PF_DEFAULT 0
+#endif
 
 namespace ubpl {
 
 unsigned long long* work_counter(cudaStream_t stream);   // api.cu: a zeroed device counter for this launch
+
+// K2 fused into the K1 epilogue (mean-teacher path, M = 1): every map that finishes bumps the arrival
+// counter of its (sample, joint); the warp that brings it to K (all views decoded) computes the dispersion
+// (utils/evaluation.py:44-54) and, in mode 2, the fixed-threshold rule, the visibility gate and the counts
+// (business.py:237-261,375-376, process.py:262-268, losses.py:29) -- the arithmetic of
+// view_dispersion_kernel / k2_view_fixed_kernel, without a second launch.
+struct K2Fuse {
+  int mode;                   // 0 off, 1 dispersion only (mean, dist, legal), 2 + fixed rule, gate and counts
+  int K;                      // views per item (= V)
+  unsigned* arrive;           // [B*J] arrival counters, zero before the launch
+  double distThrMax;
+  int img_h, img_w, S;
+  float stride, sigma;
+  float* mean;                // [B*J, 2]
+  double* dist;               // [B*J]   (999 for items with an illegal view)
+  uint8_t* legal;             // [B*J]
+  uint8_t* enable;            // [B*J]   mode 2
+  float* gate;                // [B*J]   mode 2
+  int32_t* counts;            // [J+2]   mode 2: per-joint selected, total selected, S * #(open gates)
+  PowTab T;
+};
 
 struct WDParams {
   FastDiv divJ, divB, divW;
@@ -42,7 +71,7 @@ struct WDParams {
   const float* theta;
   const uint8_t* flip;
   const double* dec;
-  int do_warp, refine, use_bulk, nbuf;
+  int do_warp, refine, use_bulk;
   int32_t* out_idx;
   float* out_max;
   float* out_xy;
@@ -51,6 +80,8 @@ struct WDParams {
   unsigned long long* work;   // global claim counter (zeroed before the launch)
   int* slow_list;             // [V*B*J] queue of maps left to the exhaustive kernel (NULL: decode in place)
   unsigned* slow_count;
+  int pf;                     // 1: the map after next is pulled into L2 with per-line prefetches (two claims ahead)
+  K2Fuse k2;                  // optional K2 epilogue run by the warp that decodes the last view of a (sample, joint)
 };
 
 struct Xform {
@@ -175,9 +206,11 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 }
 
 // Pass A over the staged map at float4 granularity: per-lane max (value, first float4 index) and a
-// NaN-propagating running min.
-__device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float& bv, int& bq, float& mn) {
-  bv = -INFINITY; bq = 0; mn = INFINITY;
+// NaN-propagating running min.  TWO = true also keeps the lane's second-best float4 maximum (bv2), which
+// lets the early-release variant prove that every candidate texel of the lane sits in its best float4.
+template <bool TWO>
+__device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float& bv, int& bq, float& bv2, float& mn) {
+  bv = -INFINITY; bv2 = -INFINITY; bq = 0; mn = INFINITY;
   const int nq = HW >> 2;
   const float4* s4 = reinterpret_cast<const float4*>(s);
   int q = lane;
@@ -189,30 +222,132 @@ __device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float
     for (int u = 0; u < 8; ++u) {
       const float m4 = fmaxf(max3(x[u].x, x[u].y, x[u].z), x[u].w);
       mn = min3_nan(x[u].z, x[u].w, min3_nan(x[u].x, x[u].y, mn));
-      if (m4 > bv) { bv = m4; bq = q + 32 * u; }
+      if (m4 > bv) { if (TWO) bv2 = bv; bv = m4; bq = q + 32 * u; }
+      else if (TWO) bv2 = fmaxf(bv2, m4);
     }
   }
   for (; q < nq; q += 32) {
     const float4 x = s4[q];
     const float m4 = fmaxf(max3(x.x, x.y, x.z), x.w);
     mn = min3_nan(x.z, x.w, min3_nan(x.x, x.y, mn));
-    if (m4 > bv) { bv = m4; bq = q; }
+    if (m4 > bv) { if (TWO) bv2 = bv; bv = m4; bq = q; }
+    else if (TWO) bv2 = fmaxf(bv2, m4);
   }
+}
+
+__device__ __forceinline__ const float* map_src(const WDParams& p, long long n) {
+  unsigned vb, j, v, b;
+  p.divJ.divmod((unsigned)n, vb, j);
+  p.divB.divmod(vb, v, b);
+  return p.maps + (long long)v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
 }
 
 __device__ __forceinline__ void issue_map(const WDParams& p, long long n, float* dst, uint64_t* bar, uint64_t pol,
                                           uint32_t bytes) {
-  unsigned vb, j, v, b;
-  p.divJ.divmod((unsigned)n, vb, j);
-  p.divB.divmod(vb, v, b);
-  const float* src = p.maps + (long long)v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
   mbar_arrive_expect_tx(bar, bytes);
-  bulk_g2s(dst, src, bytes, bar, pol);
+  bulk_g2s(dst, map_src(p, n), bytes, bar, pol);
+}
+
+// Pull a map towards L2 with one prefetch per 128-byte line (LSU path: no registers, no shared memory, and
+// nothing queued on the TMA engine in front of the staged copies).
+__device__ __forceinline__ void prefetch_map_l2(const float* src, uint32_t bytes, int lane) {
+  const char* c = reinterpret_cast<const char*>(src);
+  for (uint32_t o = (uint32_t)lane * 128u; o < bytes; o += 32u * 128u)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Where the phases after pass A read the texels of the current map from: the staged map itself (smem),
+// the map in global memory (L2), or -- early-release variant -- a small window around the arg-max texel
+// copied out of the staging buffer so that the buffer can take the next map while this one is finished.
+// Texel (y, x) is base[y * ld + x]; only [x0, x1) x [y0, y1) may be dereferenced.
+// ---------------------------------------------------------------------------------------------------
+struct Src {
+  const float* base;
+  int ld, x0, y0, x1, y1;
+};
+
+// eval_px on a source view.  WIN = true: a corner that lies inside the map but outside the window sets
+// `miss` (the caller then repeats the map on the full view); nothing outside the window is dereferenced.
+template <bool WIN>
+__device__ __forceinline__ float eval_src(const Src& S, const Xform& X, int i, int jw, bool& miss) {
+  const float xl = lin_coord(jw, X.W, X.stepx);
+  const float yl = lin_coord(i, X.H, X.stepy);
+  const float gx = __fadd_rn(__fmaf_rn(yl, X.t01, __fmul_rn(xl, X.t00)), X.t02);
+  const float gy = __fadd_rn(__fmaf_rn(yl, X.t11, __fmul_rn(xl, X.t10)), X.t12);
+  const float ix = __fmul_rn(__fadd_rn(gx, 1.f), X.sfx);
+  const float iy = __fmul_rn(__fadd_rn(gy, 1.f), X.sfy);
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const float w = __fsub_rn(ix, x0f), e = __fsub_rn(1.f, w);
+  const float n = __fsub_rn(iy, y0f), so = __fsub_rn(1.f, n);
+  const float nw = __fmul_rn(so, e), ne = __fmul_rn(so, w), sw = __fmul_rn(n, e), se = __fmul_rn(n, w);
+  const int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)(X.W + 1));
+  const int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)(X.H + 1));
+  bool xa = (x0 >= 0) & (x0 < X.W), xb = (x0 + 1 >= 0) & (x0 + 1 < X.W);
+  bool ya = (y0 >= 0) & (y0 < X.H), yb = (y0 + 1 >= 0) & (y0 + 1 < X.H);
+  if (WIN) {
+    const bool wxa = (x0 >= S.x0) & (x0 < S.x1), wxb = (x0 + 1 >= S.x0) & (x0 + 1 < S.x1);
+    const bool wya = (y0 >= S.y0) & (y0 < S.y1), wyb = (y0 + 1 >= S.y0) & (y0 + 1 < S.y1);
+    miss = miss | ((xa & ya) & !(wxa & wya)) | ((xb & ya) & !(wxb & wya)) | ((xa & yb) & !(wxa & wyb)) |
+           ((xb & yb) & !(wxb & wyb));
+    xa &= wxa; xb &= wxb; ya &= wya; yb &= wyb;
+  }
+  const float* r0 = S.base + y0 * S.ld + x0;
+  const float v_nw = (xa & ya) ? r0[0] : 0.f;
+  const float v_ne = (xb & ya) ? r0[1] : 0.f;
+  const float v_sw = (xa & yb) ? r0[S.ld] : 0.f;
+  const float v_se = (xb & yb) ? r0[S.ld + 1] : 0.f;
+  float acc = __fmul_rn(v_nw, nw);
+  acc = __fmaf_rn(v_ne, ne, acc);
+  acc = __fmaf_rn(v_sw, sw, acc);
+  acc = __fmaf_rn(v_se, se, acc);
+  return acc;
+}
+
+// K2 of one (sample, joint), run by the warp that decoded its last view (see K2Fuse).  Same float op order
+// as view_dispersion_kernel / k2_view_fixed_kernel: float32 sequential sums for the mean, float64 python
+// distances summed in view order.
+__device__ __forceinline__ void k2_item(const WDParams& p, long long item, int j, int lane) {
+  const K2Fuse& f = p.k2;
+  const int K = f.K;
+  const long long BJ = (long long)p.B * p.J;
+  float x = 0.f, y = 0.f;
+  if (lane < K) {
+    const float2 v = __ldcg(reinterpret_cast<const float2*>(p.out_xy) + ((long long)lane * BJ + item));
+    x = v.x; y = v.y;
+  }
+  const bool legal = __all_sync(0xffffffffu, (lane >= K) || ((x >= 0.f) && (y >= 0.f)));
+  float sx = __shfl_sync(0xffffffffu, x, 0), sy = __shfl_sync(0xffffffffu, y, 0);
+  for (int k = 1; k < K; ++k) {
+    sx = __fadd_rn(sx, __shfl_sync(0xffffffffu, x, k));
+    sy = __fadd_rn(sy, __shfl_sync(0xffffffffu, y, k));
+  }
+  const float mx = __fdiv_rn(sx, (float)K), my = __fdiv_rn(sy, (float)K);        // torch.mean (float32)
+  double dk = 0.0;
+  if (lane < K) dk = py_dist((double)x, (double)y, (double)mx, (double)my, f.T);
+  double acc = 0.0;
+  for (int k = 0; k < K; ++k) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, dk, k));   // sum(dists), view order
+  if (lane != 0) return;
+  const double dist = legal ? __ddiv_rn(acc, (double)K) : 999.0;                  // business.py:123 sentinel
+  if (f.mean) { f.mean[2 * item] = mx; f.mean[2 * item + 1] = my; }
+  if (f.dist) f.dist[item] = dist;
+  if (f.legal) f.legal[item] = legal ? 1 : 0;
+  if (f.mode == 2) {
+    const double thr = __dsub_rn(1.0, exp(-__ddiv_rn(__dmul_rn(f.distThrMax, 3.0), 5.0)));
+    const double unc = __dsub_rn(1.0, exp(-__ddiv_rn(dist, 5.0)));
+    const bool en = legal && (unc <= thr);
+    const Gauss g = gauss_setup(mx, my, f.img_h, f.img_w, f.stride, f.sigma);
+    const float gt = (en ? 1.f : 0.f) * g.vis;
+    if (f.enable) f.enable[item] = en ? 1 : 0;
+    f.gate[item] = gt;
+    if (en) { atomicAdd(f.counts + j, 1); atomicAdd(f.counts + p.J, 1); }
+    if (gt > 0.f) atomicAdd(f.counts + p.J + 1, f.S);
+  }
 }
 
 // Epilogue of one map (warp-wide call): arg-max -> heat-map coordinates (mask, optional quarter-offset
-// refinement) -> image-space coordinates -> outputs.
-__device__ __forceinline__ void finish_map(const WDParams& p, long long n, int j, const float* s, const Xform& X,
+// refinement) -> image-space coordinates -> outputs -> (optional) arrival at the item's K2.
+__device__ __forceinline__ void finish_map(const WDParams& p, long long n, int b, int j, const float* s, const Xform& X,
                                            float rv, int ri, double dc0, double dc1, double dc2, double dc3, int lane) {
   const int H = p.H, W = p.W;
   unsigned ayu, axu;
@@ -256,23 +391,241 @@ __device__ __forceinline__ void finish_map(const WDParams& p, long long n, int j
       p.out_xy[2 * n] = ox; p.out_xy[2 * n + 1] = oy;
     }
   }
+  if (p.k2.mode) {
+    // release the coordinates, then count this view in; the warp that sees K-1 earlier arrivals owns the item
+    const long long item = (long long)b * p.J + j;
+    unsigned old = 0;
+    if (lane == 0) {
+      __threadfence();
+      old = atomicAdd(p.k2.arrive + item, 1u);
+    }
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old == (unsigned)(p.k2.K - 1)) {
+      __threadfence();
+      if (lane == 0) p.k2.arrive[item] = 0u;           // ready for the next launch on this workspace
+      k2_item(p, item, j, lane);
+    }
+  }
 }
 
-// STREAM = false: every warp stages its map in shared memory with a 1-D bulk async copy (TMA engine).
-// STREAM = true : no staging buffer -- the warp streams the map from global memory with 128-bit loads
-//                 (the lines stay in L1/L2 for the few gathers of the exact evaluation) and the TMA engine
-//                 prefetches the NEXT claimed map into L2 (cp.async.bulk.prefetch.L2); the CTA is then
-//                 limited by registers, not by 16 KB buffers, so twice as many warps hide the latencies.
-template <bool STREAM>
-__global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(const WDParams p) {
+// What pass A leaves for the later phases.
+struct PassA {
+  float bv; int bi;                  // warp-uniform source maximum and its first flat index
+  float lane_max, lane_max2; int bq; // this lane's best / second-best float4 maximum and the best one's index
+  float a, bb, d, e, c0, f0, C00, C01, C10, C11;   // approximate pixel-space affine and its inverse (boxes only)
+};
+
+// Phases L, B and C (see the header comment) on a source view.  On return: `exhaustive` asks for the
+// exhaustive decode, otherwise (rv, ri) is the exact result.  WIN = true (window view): `miss` reports that
+// the window did not cover everything the phases had to read -- the result is then void.
+template <bool WIN>
+__device__ __forceinline__ void decode_late(const WDParams& p, const Src& S, const Xform& X, const PassA& A, int lane,
+                                            float& rv, int& ri, bool& exhaustive, bool& miss,
+                                            unsigned long long& n_eval) {
+  const int H = p.H, W = p.W, HW = H * W;
+  const float c0 = A.c0, f0 = A.f0, C00 = A.C00, C01 = A.C01, C10 = A.C10, C11 = A.C11;
+  const float bv = A.bv;
+  const int bi = A.bi;
+  bool lmiss = false;
+  float L = -INFINITY; int Li = 0x7fffffff;
+  const float kSlack = 1.9073486328125e-06f;   // 2^-19
+  float T = 0.f;
+  bool prune = false, solved = false;
+  {
+    // ---- phase L: lower bound from the pixels around the pre-image of the arg-max texel
+    unsigned biy, bix;
+    p.divW.divmod((unsigned)bi, biy, bix);
+    const float sx = (float)bix - c0, sy = (float)biy - f0;
+    const float oj = C00 * sx + C01 * sy, oi = C10 * sx + C11 * sy;
+    if (WIN) {
+      // 4 x 4 pixels: their footprints stay within ~6 texels of the arg-max texel, inside the window
+      if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 16) {
+        const int jw = (int)floorf(oj) - 1 + (lane & 3);
+        const int i = (int)floorf(oi) - 1 + (lane >> 2);
+        if (jw >= 0 && jw < W && i >= 0 && i < H) {
+          L = eval_src<WIN>(S, X, i, jw, lmiss);
+          Li = i * W + (X.flip ? (W - 1 - jw) : jw);
+        }
+      }
+      n_eval += 16;
+    } else {
+      if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 30) {
+        const int jw = (int)floorf(oj) - 2 + (lane % 6);
+        const int i = (int)floorf(oi) - 2 + (lane / 6);
+        if (jw >= 0 && jw < W && i >= 0 && i < H) {
+          L = eval_src<WIN>(S, X, i, jw, lmiss);
+          Li = i * W + (X.flip ? (W - 1 - jw) : jw);
+        }
+      }
+      n_eval += 30;
+    }
+    if (WIN && __any_sync(0xffffffffu, lmiss)) { miss = true; return; }
+    warp_argmax(L, Li);
+    // Candidate threshold.  For a pixel whose four (zero-extended) corners are all < T the computed sample
+    // is < L: the fma chain rounds by at most 4 ulp of sum(w|v|), and negative corners lower the exact
+    // value by more than the rounding they add, so 2^-19 relative slack covers it.
+    T = L - fabsf(L) * kSlack;
+    prune = (L > 0.f) && (T > 0.f);          // zero padding cannot be a candidate when T > 0
+  }
+  if (!prune) {
+    // The warped maximum is not known to be positive (an all-negative map, or a map whose maximum is
+    // exactly 0).  Along a row the computed ix and iy are monotone in the column (every rounding step
+    // is monotone), so the row ends classify the whole frame:
+    //   inside : every pixel samples with all four corners in bounds -> the convex bound holds for any
+    //            sign (no zero padding involved) and the pruned search stays valid;
+    //   Z      : pixels with ix <= -1 | ix >= W | iy <= -1 | iy >= H read nothing but padding (value
+    //            exactly 0); every other pixel of an all-negative map is < 0, so the maximum is 0 at the
+    //            first Z pixel in canonical order.
+    bool inside = true;
+    int zrow = 0x7fffffff;
+    for (int i = lane; i < H; i += 32) {
+#pragma unroll
+      for (int endc = 0; endc < 2; ++endc) {
+        float ix, iy;
+        grid_px(X, i, endc ? W - 1 : 0, ix, iy);
+        inside = inside && (ix >= 0.f) && (ix <= (float)(W - 1)) && (iy >= 0.f) && (iy <= (float)(H - 1));
+        const bool z = (ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H);
+        if (z) zrow = min(zrow, i);
+      }
+    }
+    inside = __all_sync(0xffffffffu, inside);
+    zrow = __reduce_min_sync(0xffffffffu, zrow);
+    if (inside && L > -INFINITY) {
+      prune = true;
+    } else if (bv < -1e-20f && zrow < H) {
+      int zcol = 0x7fffffff;
+      for (int jo = lane; jo < W; jo += 32) {
+        float ix, iy;
+        grid_px(X, zrow, X.flip ? (W - 1 - jo) : jo, ix, iy);
+        if ((ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H)) zcol = min(zcol, jo);
+      }
+      zcol = __reduce_min_sync(0xffffffffu, zcol);
+      bool nomiss = false;                                               // a Z pixel dereferences no texel at all
+      rv = eval_src<WIN>(S, X, zrow, X.flip ? (W - 1 - zcol) : zcol, nomiss);   // +-0, exactly what the warp produces there
+      ri = zrow * W + zcol;
+      solved = true;
+      n_eval += 2 * H + W;
+    } else {
+      exhaustive = true;
+    }
+  }
+  if (prune && !solved && !exhaustive) {
+    // ---- pass B: bounding box of the candidate texels (v >= T) -----------------------
+    int txmin = W, txmax = -1, tymin = H, tymax = -1;
+    if (WIN) {
+      // Every candidate must sit inside the window: a lane whose second-best float4 reaches T may hold
+      // candidates anywhere, and a lane whose best float4 reaches T must have it inside the window.
+      const int w4 = W >> 2;
+      const int qy = A.bq / w4, qx = (A.bq - qy * w4) << 2;
+      const bool in_win = (qy >= S.y0) & (qy < S.y1) & (qx >= S.x0) & (qx + 3 < S.x1);
+      const bool bad = (A.lane_max2 >= T) || ((A.lane_max >= T) && !in_win);
+      if (__any_sync(0xffffffffu, bad)) { miss = true; return; }
+      const float* win = S.base + S.y0 * S.ld + S.x0;                   // the window's own storage, row stride ld
+      const int wq = (S.x1 - S.x0) >> 2, nwq = wq * (S.y1 - S.y0);
+      for (int t = lane; t < nwq; t += 32) {
+        const int r = t / wq, c4 = t - r * wq;
+        const int ty = S.y0 + r, tx0 = S.x0 + (c4 << 2);
+        if (ty < 0 || ty >= H || tx0 < 0 || tx0 >= W) continue;         // window cells outside the map
+        const float4 x = *reinterpret_cast<const float4*>(win + r * S.ld + (c4 << 2));
+        if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= T) {
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (xs[c] >= T) {
+              txmin = min(txmin, tx0 + c); txmax = max(txmax, tx0 + c); tymin = min(tymin, ty); tymax = max(tymax, ty);
+            }
+        }
+      }
+    } else {
+      const float* s = S.base;
+      const int nq = HW >> 2;
+      const float4* s4 = reinterpret_cast<const float4*>(s);
+      auto visit = [&](const float4& x, int q) {
+        if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= T) {
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (xs[c] >= T) {
+              unsigned ty, tx;
+              p.divW.divmod((unsigned)((q << 2) + c), ty, tx);
+              txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
+            }
+        }
+      };
+      // lane l scanned the float4s q = l (mod 32) in pass A and knows their maximum (lane_max):
+      // only the residue classes whose maximum reaches T can hold candidates.  All 32 lanes
+      // re-read one such class together (32 float4 per step).
+      unsigned hot = __ballot_sync(0xffffffffu, A.lane_max >= T);
+      if (__popc(hot) <= 12) {
+        while (hot) {
+          const int h = __ffs(hot) - 1;
+          hot &= hot - 1;
+          for (int q = h + 32 * lane; q < nq; q += 1024) visit(s4[q], q);
+        }
+      } else {
+#pragma unroll 4
+        for (int q = lane; q < nq; q += 32) visit(s4[q], q);
+      }
+      for (int k = (nq << 2) + lane; k < HW; k += 32)
+        if (s[k] >= T) {
+          unsigned ty, tx;
+          p.divW.divmod((unsigned)k, ty, tx);
+          txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
+        }
+    }
+    txmin = __reduce_min_sync(0xffffffffu, txmin); txmax = __reduce_max_sync(0xffffffffu, txmax);
+    tymin = __reduce_min_sync(0xffffffffu, tymin); tymax = __reduce_max_sync(0xffffffffu, tymax);
+    // pre-image of [txmin-1, txmax+1] x [tymin-1, tymax+1] -> bounding box in the warped frame
+    const float X0 = (float)(txmin - 1) - c0, X1 = (float)(txmax + 1) - c0;
+    const float Y0 = (float)(tymin - 1) - f0, Y1 = (float)(tymax + 1) - f0;
+    const float ja = C00 * X0, jb = C00 * X1, jc = C01 * Y0, jd = C01 * Y1;
+    const float ia = C10 * X0, ib = C10 * X1, ic = C11 * Y0, id = C11 * Y1;
+    const float jlo = fminf(ja, jb) + fminf(jc, jd), jhi = fmaxf(ja, jb) + fmaxf(jc, jd);
+    const float ilo = fminf(ia, ib) + fminf(ic, id), ihi = fmaxf(ia, ib) + fmaxf(ic, id);
+    const float m = 0.03f;
+    const int jmin = max(0, (int)ceilf(fmaxf(jlo - m, -1.f))), jmax = min(W - 1, (int)floorf(fminf(jhi + m, (float)W)));
+    const int imin = max(0, (int)ceilf(fmaxf(ilo - m, -1.f))), imax = min(H - 1, (int)floorf(fminf(ihi + m, (float)H)));
+    const int bw = jmax - jmin + 1, bh = imax - imin + 1;
+    const int area = (bw > 0 && bh > 0) ? bw * bh : 0;
+    if (area > 768 || area * 4 > HW) {
+      exhaustive = true;
+    } else {
+      // ---- phase C: exact evaluation of every pixel that can touch a candidate ---------
+      rv = L; ri = Li;
+      int ci = lane / max(bw, 1), cj = lane - ci * bw;          // (row, col) of this lane's first pixel in the box
+      const int di = 32 / max(bw, 1), dj = 32 - di * bw;
+      for (int t = lane; t < area; t += 32, ci += di, cj += dj) {
+        if (cj >= bw) { cj -= bw; ++ci; }
+        const int i = imin + ci, jw = jmin + cj;
+        const float v = eval_src<WIN>(S, X, i, jw, lmiss);
+        const int k = i * W + (X.flip ? (W - 1 - jw) : jw);
+        if (arg_better(v, k, rv, ri)) { rv = v; ri = k; }
+      }
+      n_eval += area;
+      if (WIN && __any_sync(0xffffffffu, lmiss)) { miss = true; return; }
+      warp_argmax(rv, ri);
+    }
+  }
+}
+
+// One warp per heat-map, maps claimed from a global counter, each staged in the warp's shared-memory buffer by
+// a 1-D bulk async copy (TMA engine).
+// EARLY = false: the staged map serves every phase; the next copy starts when the map is finished.
+// EARLY = true : after pass A a 16 x 16 window around the arg-max texel is copied aside and the buffer is
+//                handed to the next copy at once, so the copy latency overlaps phases L/B/C of this map.  The
+//                phases run on the window; the few maps whose candidates or footprints leave it are repeated
+//                on the map in global memory (L2), which gives the same exact result.
+constexpr int kWin = 16;                                    // window edge (texels)
+template <bool EARLY>
+__global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, W = p.W, HW = H * W;
   const uint32_t map_bytes = (uint32_t)HW * 4u;
-  const uint32_t buf_stride = (map_bytes + 127u) & ~127u;   // keep every buffer 128 B aligned
-  const int NB = p.nbuf;                                    // 1 or 2 buffers per warp
-  float* buf0 = reinterpret_cast<float*>(smem_raw + (size_t)warp * NB * buf_stride);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warps * NB * buf_stride) + warp * NB;
+  const uint32_t buf_stride = ((map_bytes + 127u) & ~127u) + (EARLY ? kWin * kWin * 4u : 0u);   // 128 B aligned
+  float* buf0 = reinterpret_cast<float*>(smem_raw + (size_t)warp * buf_stride);
+  float* winbuf = buf0 + (((map_bytes + 127u) & ~127u) >> 2);                                    // EARLY only
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warps * buf_stride) + warp;
 
   const long long N = (long long)p.V * p.B * p.J;
   uint64_t pol = 0;
@@ -283,47 +636,49 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
     if (lane == 0) n = atomicAdd(p.work, 1ull);
     return (long long)__shfl_sync(0xffffffffu, n, 0);
   };
-  long long nxt0 = N, nxt1 = N;
-  if (!STREAM && p.use_bulk && lane == 0) {
-    for (int b = 0; b < NB; ++b) mbar_init(&bars[b], 1);
+  if (p.use_bulk && lane == 0) {
+    mbar_init(bar, 1);
     fence_mbar_init();
     pol = l2_evict_first_policy();
   }
   __syncwarp();
-  auto map_ptr = [&](long long n) -> const float* {
-    unsigned vb, j, v, b;
-    p.divJ.divmod((unsigned)n, vb, j);
-    p.divB.divmod(vb, v, b);
-    return p.maps + (long long)v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
-  };
-  nxt0 = claim();
-  if (STREAM) {
-    // one map of look-ahead: the next claimed map is prefetched into L2 while the current one is decoded
-    if (p.use_bulk && lane == 0 && nxt0 < N) bulk_prefetch_l2(map_ptr(nxt0), map_bytes);
-    nxt1 = claim();
-    if (p.use_bulk && lane == 0 && nxt1 < N) bulk_prefetch_l2(map_ptr(nxt1), map_bytes);
-  } else if (p.use_bulk && lane == 0 && nxt0 < N) issue_map(p, nxt0, buf0, &bars[0], pol, map_bytes);
-  if (!STREAM && NB == 2) {
-    nxt1 = claim();
-    if (p.use_bulk && lane == 0 && nxt1 < N) issue_map(p, nxt1, buf0 + (buf_stride >> 2), &bars[1], pol, map_bytes);
+  long long cur = claim(), ahead = N;
+  if (p.use_bulk && lane == 0 && cur < N) issue_map(p, cur, buf0, bar, pol, map_bytes);
+  if (p.pf) {
+    ahead = claim();
+    if (ahead < N) prefetch_map_l2(map_src(p, ahead), map_bytes, lane);
   }
+  // hand the staging buffer to the next map: returns its index (>= N when the work is exhausted)
+  auto advance = [&]() -> long long {
+    long long nn;
+    if (p.pf) {
+      nn = ahead;
+      ahead = claim();
+      if (ahead < N) prefetch_map_l2(map_src(p, ahead), map_bytes, lane);
+    } else {
+      nn = claim();
+    }
+    if (p.use_bulk && lane == 0 && nn < N) issue_map(p, nn, buf0, bar, pol, map_bytes);
+    return nn;
+  };
 
-  unsigned long long n_slow = 0, n_eval = 0, n_maps = 0;
+  unsigned long long n_slow = 0, n_eval = 0, n_maps = 0, n_miss = 0;
   for (long long it = 0;; ++it) {
-    const int bsel = (!STREAM && NB == 2) ? (int)(it & 1) : 0;
-    const long long n = bsel ? nxt1 : nxt0;
+    const long long n = cur;
     if (n >= N) break;
-    const float* s = STREAM ? map_ptr(n) : buf0 + (size_t)bsel * (buf_stride >> 2);
+    const float* s = buf0;
     unsigned vbu, ju, vu, bu;
     p.divJ.divmod((unsigned)n, vbu, ju);
     p.divB.divmod(vbu, vu, bu);
     const int j = (int)ju, b = (int)bu;
     const long long vb = (long long)vbu;
+    const float* gsrc = p.maps + (long long)vu * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
     // ---- per-map transform set-up, issued BEFORE waiting for the staged map so that the global loads of
     // theta / flip / dec and the inverse-affine arithmetic overlap the copy latency
     Xform X;
     X.H = H; X.W = W; X.flip = false;
-    float a = 0.f, bb = 0.f, d = 0.f, e = 0.f, c0 = 0.f, f0 = 0.f, C00 = 0.f, C01 = 0.f, C10 = 0.f, C11 = 0.f;
+    PassA A;
+    A.a = A.bb = A.d = A.e = A.c0 = A.f0 = A.C00 = A.C01 = A.C10 = A.C11 = 0.f;
     bool bad_xform = false;
     double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
     if (p.dec) { const double* c = p.dec + (size_t)b * 4; dc0 = c[0]; dc1 = c[1]; dc2 = c[2]; dc3 = c[3]; }
@@ -331,31 +686,27 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
       load_xform(X, p.theta, p.flip, vb, H, W);
       X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
       // pixel-space affine  ix = a*jw + bb*i + c0 ; iy = d*jw + e*i + f0  (approximate, for boxes only)
-      a = X.t00 * X.stepx * X.sfx; bb = X.t01 * X.stepy * X.sfx;
-      d = X.t10 * X.stepx * X.sfy; e = X.t11 * X.stepy * X.sfy;
-      c0 = (X.t02 + 1.f - X.t00 - X.t01) * X.sfx; f0 = (X.t12 + 1.f - X.t10 - X.t11) * X.sfy;
-      const float det = a * e - bb * d;
-      const float nrm = fabsf(a) + fabsf(bb) + fabsf(d) + fabsf(e);
+      A.a = X.t00 * X.stepx * X.sfx; A.bb = X.t01 * X.stepy * X.sfx;
+      A.d = X.t10 * X.stepx * X.sfy; A.e = X.t11 * X.stepy * X.sfy;
+      A.c0 = (X.t02 + 1.f - X.t00 - X.t01) * X.sfx; A.f0 = (X.t12 + 1.f - X.t10 - X.t11) * X.sfy;
+      const float det = A.a * A.e - A.bb * A.d;
+      const float nrm = fabsf(A.a) + fabsf(A.bb) + fabsf(A.d) + fabsf(A.e);
       bad_xform = !(fabsf(det) > 1e-5f * nrm * nrm) || !(nrm < 1e4f) || W <= 1 || H <= 1;
       const float idet = 1.f / det;
-      C00 = e * idet; C01 = -bb * idet; C10 = -d * idet; C11 = a * idet;
+      A.C00 = A.e * idet; A.C01 = -A.bb * idet; A.C10 = -A.d * idet; A.C11 = A.a * idet;
     }
-    if (!STREAM) {
-      if (p.use_bulk) {
-        mbar_wait(&bars[bsel], (uint32_t)((it / NB) & 1));
-      } else {
-        float* sw = buf0 + (size_t)bsel * (buf_stride >> 2);
-        const float* src = p.maps + (long long)vu * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
-        for (int k = lane; k < HW; k += 32) sw[k] = __ldg(src + k);
-        __syncwarp();
-      }
+    if (p.use_bulk) {
+      mbar_wait(bar, (uint32_t)(it & 1));
+    } else {
+      for (int k = lane; k < HW; k += 32) buf0[k] = __ldg(gsrc + k);
+      __syncwarp();
     }
     ++n_maps;
 
     // ---- pass A: raw max / location / min / finiteness -----------------------------------------
-    float bv, mn; int bq;
-    scan_max(s, HW, lane, bv, bq, mn);
-    const float lane_max = bv;           // max over this lane's float4 residue class (pass B reuses it)
+    float bv, bv2, mn; int bq;
+    scan_max<EARLY>(s, HW, lane, bv, bq, bv2, mn);
+    A.lane_max = bv; A.lane_max2 = bv2; A.bq = bq;   // per-lane float4 maxima (pass B reuses them)
     int bi = 0x7fffffff;                  // flat index of the lane's first maximum
     if (bv > -INFINITY) {
       const float4 x = reinterpret_cast<const float4*>(s)[bq];
@@ -369,6 +720,36 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
     // NaN -> mn is NaN; -inf -> mn == -inf; +inf -> bv == +inf
     const bool nonfinite = __any_sync(0xffffffffu, !(mn >= -FLT_MAX) || !(bv <= FLT_MAX));
     float rv = bv; int ri = bi;           // result (value, canonical flat index)
+    if (p.do_warp) warp_argmax(bv, bi);   // warp-uniform source max / location
+    A.bv = bv; A.bi = bi;
+
+    long long nxt = N;
+    Src win;
+    if (EARLY) {
+      // copy the window around the arg-max texel aside, then release the staging buffer to the next map
+      unsigned biy = 0, bix = 0;
+      if (p.do_warp && bi != 0x7fffffff) p.divW.divmod((unsigned)bi, biy, bix);
+      win.ld = kWin;
+      win.x0 = (((int)bix - 6) >> 2) << 2;                  // multiple of 4: margins of 6..9 texels either side
+      win.y0 = (int)biy - 7;
+      win.x1 = win.x0 + kWin; win.y1 = win.y0 + kWin;
+      win.base = winbuf - (win.y0 * kWin + win.x0);
+      if (p.do_warp) {
+        const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int t = lane; t < kWin * kWin / 4; t += 32) {
+          const int r = t >> 2, c4 = t & 3;
+          const int y = win.y0 + r, x = win.x0 + (c4 << 2);
+          float4 v = ninf;
+          if (y >= 0 && y < H && x >= 0 && x + 3 < W) v = *reinterpret_cast<const float4*>(s + y * W + x);
+          reinterpret_cast<float4*>(winbuf)[t] = v;
+        }
+      }
+      __syncwarp();
+      nxt = advance();
+      s = gsrc;                             // anything else reads the map from global memory (L2)
+    }
+
     bool deferred = false;
     if (!p.do_warp) {
       if (nonfinite) {                    // torch.max: the first NaN wins; +-Inf compare normally
@@ -377,150 +758,27 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
       }
       warp_argmax(rv, ri);
     } else {
-      warp_argmax(bv, bi);                // warp-uniform source max / location
       bool exhaustive = nonfinite || bad_xform;
-      float L = -INFINITY; int Li = 0x7fffffff;
       if (!exhaustive) {
-        const float kSlack = 1.9073486328125e-06f;   // 2^-19
-        float T = 0.f;
-        bool prune = false, solved = false;
-        {
-          // ---- phase L: lower bound from the pixels around the pre-image of the arg-max texel
-          unsigned biy, bix;
-          p.divW.divmod((unsigned)bi, biy, bix);
-          const float sx = (float)bix - c0, sy = (float)biy - f0;
-          const float oj = C00 * sx + C01 * sy, oi = C10 * sx + C11 * sy;
-          if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 30) {
-            const int jw = (int)floorf(oj) - 2 + (lane % 6);
-            const int i = (int)floorf(oi) - 2 + (lane / 6);
-            if (jw >= 0 && jw < W && i >= 0 && i < H) {
-              L = eval_px(s, X, i, jw);
-              Li = i * W + (X.flip ? (W - 1 - jw) : jw);
-            }
+        const Src full = {s, W, 0, 0, W, H};
+        bool miss = false;
+        if (EARLY) {
+          decode_late<true>(p, win, X, A, lane, rv, ri, exhaustive, miss, n_eval);
+          if (miss) {
+            ++n_miss;
+            // the window was too small for this map: the hot float4 classes are unknown to pass B of the full
+            // view only through lane_max, which is still valid; repeat on the map in L2
+            exhaustive = false; miss = false;
+            decode_late<false>(p, full, X, A, lane, rv, ri, exhaustive, miss, n_eval);
           }
-          n_eval += 30;
-          warp_argmax(L, Li);
-          // Candidate threshold.  For a pixel whose four (zero-extended) corners are all < T the computed sample
-          // is < L: the fma chain rounds by at most 4 ulp of sum(w|v|), and negative corners lower the exact
-          // value by more than the rounding they add, so 2^-19 relative slack covers it.
-          T = L - fabsf(L) * kSlack;
-          prune = (L > 0.f) && (T > 0.f);          // zero padding cannot be a candidate when T > 0
-        }
-        if (!prune) {
-          // The warped maximum is not known to be positive (an all-negative map, or a map whose maximum is
-          // exactly 0).  Along a row the computed ix and iy are monotone in the column (every rounding step
-          // is monotone), so the row ends classify the whole frame:
-          //   inside : every pixel samples with all four corners in bounds -> the convex bound holds for any
-          //            sign (no zero padding involved) and the pruned search stays valid;
-          //   Z      : pixels with ix <= -1 | ix >= W | iy <= -1 | iy >= H read nothing but padding (value
-          //            exactly 0); every other pixel of an all-negative map is < 0, so the maximum is 0 at the
-          //            first Z pixel in canonical order.
-          bool inside = true;
-          int zrow = 0x7fffffff;
-          for (int i = lane; i < H; i += 32) {
-#pragma unroll
-            for (int endc = 0; endc < 2; ++endc) {
-              float ix, iy;
-              grid_px(X, i, endc ? W - 1 : 0, ix, iy);
-              inside = inside && (ix >= 0.f) && (ix <= (float)(W - 1)) && (iy >= 0.f) && (iy <= (float)(H - 1));
-              const bool z = (ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H);
-              if (z) zrow = min(zrow, i);
-            }
-          }
-          inside = __all_sync(0xffffffffu, inside);
-          zrow = __reduce_min_sync(0xffffffffu, zrow);
-          if (inside && L > -INFINITY) {
-            prune = true;
-          } else if (bv < -1e-20f && zrow < H) {
-            int zcol = 0x7fffffff;
-            for (int jo = lane; jo < W; jo += 32) {
-              float ix, iy;
-              grid_px(X, zrow, X.flip ? (W - 1 - jo) : jo, ix, iy);
-              if ((ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H)) zcol = min(zcol, jo);
-            }
-            zcol = __reduce_min_sync(0xffffffffu, zcol);
-            rv = eval_px(s, X, zrow, X.flip ? (W - 1 - zcol) : zcol);   // +-0, exactly what the warp produces there
-            ri = zrow * W + zcol;
-            solved = true;
-            n_eval += 2 * H + W;
-          } else {
-            exhaustive = true;
-          }
-        }
-        if (prune && !solved && !exhaustive) {
-          // ---- pass B: bounding box of the candidate texels (v >= T) -----------------------
-          int txmin = W, txmax = -1, tymin = H, tymax = -1;
-          const int nq = HW >> 2;
-          const float4* s4 = reinterpret_cast<const float4*>(s);
-          auto visit = [&](const float4& x, int q) {
-            if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= T) {
-              const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-              for (int c = 0; c < 4; ++c)
-                if (xs[c] >= T) {
-                  unsigned ty, tx;
-                  p.divW.divmod((unsigned)((q << 2) + c), ty, tx);
-                  txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
-                }
-            }
-          };
-          // lane l scanned the float4s q = l (mod 32) in pass A and knows their maximum (lane_max):
-          // only the residue classes whose maximum reaches T can hold candidates.  All 32 lanes
-          // re-read one such class together (32 float4 per step).
-          unsigned hot = __ballot_sync(0xffffffffu, lane_max >= T);
-          if (__popc(hot) <= 12) {
-            while (hot) {
-              const int h = __ffs(hot) - 1;
-              hot &= hot - 1;
-              for (int q = h + 32 * lane; q < nq; q += 1024) visit(s4[q], q);
-            }
-          } else {
-#pragma unroll 4
-            for (int q = lane; q < nq; q += 32) visit(s4[q], q);
-          }
-          for (int k = (nq << 2) + lane; k < HW; k += 32)
-            if (s[k] >= T) {
-              unsigned ty, tx;
-              p.divW.divmod((unsigned)k, ty, tx);
-              txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
-            }
-          txmin = __reduce_min_sync(0xffffffffu, txmin); txmax = __reduce_max_sync(0xffffffffu, txmax);
-          tymin = __reduce_min_sync(0xffffffffu, tymin); tymax = __reduce_max_sync(0xffffffffu, tymax);
-          // pre-image of [txmin-1, txmax+1] x [tymin-1, tymax+1] -> bounding box in the warped frame
-          const float X0 = (float)(txmin - 1) - c0, X1 = (float)(txmax + 1) - c0;
-          const float Y0 = (float)(tymin - 1) - f0, Y1 = (float)(tymax + 1) - f0;
-          const float ja = C00 * X0, jb = C00 * X1, jc = C01 * Y0, jd = C01 * Y1;
-          const float ia = C10 * X0, ib = C10 * X1, ic = C11 * Y0, id = C11 * Y1;
-          const float jlo = fminf(ja, jb) + fminf(jc, jd), jhi = fmaxf(ja, jb) + fmaxf(jc, jd);
-          const float ilo = fminf(ia, ib) + fminf(ic, id), ihi = fmaxf(ia, ib) + fmaxf(ic, id);
-          const float m = 0.03f;
-          const int jmin = max(0, (int)ceilf(fmaxf(jlo - m, -1.f))), jmax = min(W - 1, (int)floorf(fminf(jhi + m, (float)W)));
-          const int imin = max(0, (int)ceilf(fmaxf(ilo - m, -1.f))), imax = min(H - 1, (int)floorf(fminf(ihi + m, (float)H)));
-          const int bw = jmax - jmin + 1, bh = imax - imin + 1;
-          const int area = (bw > 0 && bh > 0) ? bw * bh : 0;
-          if (area > 768 || area * 4 > HW) {
-            exhaustive = true;
-          } else {
-          // ---- phase C: exact evaluation of every pixel that can touch a candidate ---------
-          rv = L; ri = Li;
-          int ci = lane / max(bw, 1), cj = lane - ci * bw;          // (row, col) of this lane's first pixel in the box
-          const int di = 32 / max(bw, 1), dj = 32 - di * bw;
-          for (int t = lane; t < area; t += 32, ci += di, cj += dj) {
-            if (cj >= bw) { cj -= bw; ++ci; }
-            const int i = imin + ci, jw = jmin + cj;
-            const float v = eval_px(s, X, i, jw);
-            const int k = i * W + (X.flip ? (W - 1 - jw) : jw);
-            if (arg_better(v, k, rv, ri)) { rv = v; ri = k; }
-          }
-          n_eval += area;
-          warp_argmax(rv, ri);
-          }
+        } else {
+          decode_late<false>(p, full, X, A, lane, rv, ri, exhaustive, miss, n_eval);
         }
       }
       if (exhaustive && p.slow_list) {
         // Maps that need the exhaustive decode are not decoded here: one such map would keep this warp busy
         // for ~25 us while the rest of the grid drains.  They are queued and decoded right after this kernel
-        // by whole CTAs (warp_decode_slow_kernel), four warps per map.
+        // by whole CTAs (warp_decode_slow_kernel).
         if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = (int)n;
         deferred = true;
         ++n_slow;
@@ -531,31 +789,25 @@ __global__ void __launch_bounds__(STREAM ? 768 : 512, 1) warp_decode_kernel(cons
       }
     }
 
-    if (!deferred) finish_map(p, n, j, s, X, rv, ri, dc0, dc1, dc2, dc3, lane);
+    if (!deferred) finish_map(p, n, b, j, s, X, rv, ri, dc0, dc1, dc2, dc3, lane);
     __syncwarp();
-    const long long nn = claim();
-    if (STREAM) {
-      nxt0 = nxt1; nxt1 = nn;
-      if (p.use_bulk && lane == 0 && nn < N) bulk_prefetch_l2(map_ptr(nn), map_bytes);
-    } else {
-      if (bsel) nxt1 = nn; else nxt0 = nn;
-      if (p.use_bulk && lane == 0 && nn < N)
-        issue_map(p, nn, buf0 + (size_t)bsel * (buf_stride >> 2), &bars[bsel], pol, map_bytes);
-    }
+    cur = EARLY ? nxt : advance();
   }
   if (p.stats && lane == 0 && n_maps) {
     atomicAdd(p.stats + 0, n_slow);
     atomicAdd(p.stats + 1, n_eval);
     atomicAdd(p.stats + 2, n_maps);
+    atomicAdd(p.stats + 3, n_miss);
   }
 }
 
-// Exhaustive decode of the queued maps: one CTA of 4 warps per map (rows split four ways), map staged in
-// shared memory; warp 0 merges the four partial arg-maxes and writes the outputs.
-__global__ void __launch_bounds__(128) warp_decode_slow_kernel(const WDParams p) {
+// Exhaustive decode of the queued maps: one CTA of 16 warps per map (rows split sixteen ways), map staged in
+// shared memory; warp 0 merges the partial arg-maxes and writes the outputs.
+constexpr int kSlowWarps = 16;
+__global__ void __launch_bounds__(kSlowWarps * 32) warp_decode_slow_kernel(const WDParams p) {
   extern __shared__ __align__(16) float sm_map[];
-  __shared__ float s_v[4];
-  __shared__ int s_i[4];
+  __shared__ float s_v[kSlowWarps];
+  __shared__ int s_i[kSlowWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, W = p.W, HW = H * W;
   const unsigned count = *p.slow_count;
@@ -578,7 +830,7 @@ __global__ void __launch_bounds__(128) warp_decode_slow_kernel(const WDParams p)
     load_xform(X, p.theta, p.flip, (long long)vbu, H, W);
     X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
     float rv; int ri;
-    const int r0 = (H * warp) / 4, r1 = (H * (warp + 1)) / 4;
+    const int r0 = (H * warp) / kSlowWarps, r1 = (H * (warp + 1)) / kSlowWarps;
     decode_exhaustive(sm_map, X.t00, X.t01, X.t02, X.t10, X.t11, X.t12, X.stepx, X.stepy, X.sfx, X.sfy, H, W, X.flip,
                       lane, rv, ri, r0, r1);
     if (lane == 0) { s_v[warp] = rv; s_i[warp] = ri; }
@@ -586,10 +838,10 @@ __global__ void __launch_bounds__(128) warp_decode_slow_kernel(const WDParams p)
     if (warp == 0) {
       rv = s_v[0]; ri = s_i[0];
 #pragma unroll
-      for (int w = 1; w < 4; ++w) if (arg_better(s_v[w], s_i[w], rv, ri)) { rv = s_v[w]; ri = s_i[w]; }
+      for (int w = 1; w < kSlowWarps; ++w) if (arg_better(s_v[w], s_i[w], rv, ri)) { rv = s_v[w]; ri = s_i[w]; }
       double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
       if (p.dec) { const double* c = p.dec + (size_t)bu * 4; dc0 = c[0]; dc1 = c[1]; dc2 = c[2]; dc3 = c[3]; }
-      finish_map(p, n, (int)ju, sm_map, X, rv, ri, dc0, dc1, dc2, dc3, lane);
+      finish_map(p, n, (int)bu, (int)ju, sm_map, X, rv, ri, dc0, dc1, dc2, dc3, lane);
     }
   }
 }
@@ -642,8 +894,61 @@ static int launch_slow(const WDParams& p, size_t map_bytes, cudaStream_t stream)
     if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute(slow): %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
     attr_set = true;
   }
-  warp_decode_slow_kernel<<<sm_count() * 4, 128, map_bytes, stream>>>(p);
+  warp_decode_slow_kernel<<<sm_count() * 2, kSlowWarps * 32, map_bytes, stream>>>(p);
   return check_launch("ubpl_warp_decode(slow)");
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// Fills the geometry / tuning fields of p and launches the main kernel (+ the exhaustive kernel when a queue
+// is given).  p.work, p.slow_*, p.k2 and the outputs are set by the caller.
+static int launch_k1(WDParams& p, cudaStream_t stream) {
+  const int H = p.H, W = p.W;
+  const long long N = (long long)p.V * p.B * p.J;
+  const long long HW = (long long)H * W;
+  UBPL_REQUIRE(HW <= (1 << 24), "ubpl_warp_decode: heat-map too large (%lld texels)", HW);
+  UBPL_REQUIRE(N < (1ll << 31), "ubpl_warp_decode: too many maps in one call (%lld)", N);
+  const size_t map_bytes = (size_t)HW * 4;
+  const int smem_cap = smem_optin() - 2048;
+  p.divJ.init((unsigned)p.J); p.divB.init((unsigned)p.B); p.divW.init((unsigned)W);
+  p.stepx = (W > 1) ? 2.f / (float)(W - 1) : 0.f;
+  p.stepy = (H > 1) ? 2.f / (float)(H - 1) : 0.f;
+  p.sfx = (float)((double)(W - 1) / 2.0);
+  p.sfy = (float)((double)(H - 1) / 2.0);
+  // bulk async copy needs 16-byte aligned sources and sizes; otherwise the warp copies the map itself
+  p.use_bulk = ((reinterpret_cast<uintptr_t>(p.maps) & 15) == 0) && (map_bytes % 16 == 0) && (p.sV % 4 == 0) &&
+               (p.sB % 4 == 0) && (p.sJ % 4 == 0);
+  // tuning knobs (read per call so that one process can compare them; defaults from B200 measurements):
+  //   UBPL_K1_EARLY  1 = release the staging buffer after pass A (window copy), 0 = after the whole map
+  //   UBPL_K1_PF     1 = per-line L2 prefetch of the map after next
+  //   UBPL_K1_WARPS  cap on the warps per CTA
+  const bool early = p.use_bulk && p.do_warp && (W % 4 == 0) && W >= 4 && env_int("UBPL_K1_EARLY", UBPL_K1_EARLY_DEFAULT) != 0;
+  p.pf = (p.use_bulk && env_int("UBPL_K1_PF", UBPL_K1_PF_DEFAULT) != 0) ? 1 : 0;
+  const size_t buf_stride = ((map_bytes + 127) & ~(size_t)127) + (early ? (size_t)kWin * kWin * 4 : 0);
+  UBPL_REQUIRE((long long)buf_stride + 64 <= smem_cap, "ubpl_warp_decode: a %dx%d map does not fit in shared memory", H, W);
+  int warps = (int)((size_t)smem_cap / (buf_stride + 8));
+  const int env_warps = env_int("UBPL_K1_WARPS", 0);
+  if (env_warps > 0 && env_warps < warps) warps = env_warps;
+  if (warps > 16) warps = 16;
+  if (warps < 1) warps = 1;
+  const size_t smem = (size_t)warps * buf_stride + (size_t)warps * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(warp_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(warp_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+    if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+    attr_set = true;
+  }
+  long long need = (N + warps - 1) / warps;
+  int grid = (int)(need < sm_count() ? need : sm_count());
+  if (early) warp_decode_kernel<true><<<grid, warps * 32, smem, stream>>>(p);
+  else warp_decode_kernel<false><<<grid, warps * 32, smem, stream>>>(p);
+  int rc = check_launch("ubpl_warp_decode");
+  if (rc != UBPL_OK || !p.slow_list) return rc;
+  return launch_slow(p, map_bytes, stream);
 }
 
 extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64_t sJ, int V, int B, int J, int H,
@@ -656,75 +961,69 @@ extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64
   UBPL_REQUIRE(refine >= 0 && refine <= 2, "ubpl_warp_decode: refine must be 0, 1 or 2");
   const long long N = (long long)V * B * J;
   if (N == 0) return UBPL_OK;
-  const long long HW = (long long)H * W;
-  UBPL_REQUIRE(HW <= (1 << 24), "ubpl_warp_decode: heat-map too large (%lld texels)", HW);
-  const size_t map_bytes = (size_t)HW * 4;
-  const size_t buf_stride = (map_bytes + 127) & ~(size_t)127;
-  const int smem_cap = smem_optin() - 2048;
-  UBPL_REQUIRE((long long)buf_stride + 64 <= smem_cap, "ubpl_warp_decode: a %dx%d map does not fit in shared memory", H, W);
   WDParams p;
+  memset(&p, 0, sizeof(p));
   p.maps = maps; p.sV = sV; p.sB = sB; p.sJ = sJ; p.V = V; p.B = B; p.J = J; p.H = H; p.W = W;
   p.theta = theta; p.flip = flip; p.dec = dec; p.do_warp = do_warp; p.refine = refine;
-  UBPL_REQUIRE(N < (1ll << 31), "ubpl_warp_decode: too many maps in one call (%lld)", N);
-  p.divJ.init((unsigned)J); p.divB.init((unsigned)B); p.divW.init((unsigned)W);
-  p.stepx = (W > 1) ? 2.f / (float)(W - 1) : 0.f;
-  p.stepy = (H > 1) ? 2.f / (float)(H - 1) : 0.f;
-  p.sfx = (float)((double)(W - 1) / 2.0);
-  p.sfy = (float)((double)(H - 1) / 2.0);
   p.out_idx = out_idx; p.out_max = out_max; p.out_xy = out_xy; p.out_hm_xy = out_hm_xy;
   p.stats = reinterpret_cast<unsigned long long*>(stats);
-  // bulk async copy needs 16-byte aligned sources and sizes; otherwise the warp copies the map itself
-  p.use_bulk = ((reinterpret_cast<uintptr_t>(maps) & 15) == 0) && (map_bytes % 16 == 0) && (sV % 4 == 0) &&
-               (sB % 4 == 0) && (sJ % 4 == 0);
-  int total_bufs = (int)((size_t)smem_cap / (buf_stride + 8));
-  int warps, nbuf;
-  // tuning knobs (defaults chosen from B200 measurements): buffers per warp, warps per CTA
-  static const int env_nbuf = getenv("UBPL_K1_NBUF") ? atoi(getenv("UBPL_K1_NBUF")) : 0;
-  static const int env_warps = getenv("UBPL_K1_WARPS") ? atoi(getenv("UBPL_K1_WARPS")) : 0;
-  nbuf = (env_nbuf == 1 || env_nbuf == 2) ? env_nbuf : 1;
-  if (nbuf == 2 && total_bufs < 2) nbuf = 1;
-  warps = total_bufs / nbuf;
-  if (env_warps > 0 && env_warps < warps) warps = env_warps;
-  if (warps > 16) warps = 16;
-  if (warps < 1) warps = 1;
-  p.nbuf = nbuf;
-  // "smem" (default): TMA-staged buffers, 14 warps per CTA for 64x64 maps; "stream" (UBPL_K1_MODE=stream):
-  // no staging buffers, register-limited CTAs of 24 warps, next map prefetched into L2.
-  static const char* env_mode = getenv("UBPL_K1_MODE");
-  bool stream_mode = false;   // measured on B200: the TMA-staged buffers win (profiles/README.md)
-  if (env_mode && env_mode[0] == 's' && env_mode[1] == 't' && p.use_bulk && (map_bytes % 16 == 0)) stream_mode = true;
   p.work = work_counter((cudaStream_t)stream);
   if (!p.work) return UBPL_ERR_CUDA;
-  p.slow_list = nullptr; p.slow_count = nullptr;
   if (slow_ws && do_warp) {
     p.slow_count = reinterpret_cast<unsigned*>(slow_ws);
     p.slow_list = slow_ws + 1;
     cudaError_t e = cudaMemsetAsync(slow_ws, 0, sizeof(int32_t), (cudaStream_t)stream);
     if (e != cudaSuccess) { set_error("ubpl_warp_decode: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
   }
-  if (stream_mode) {
-    int sw = 24;
-    if (env_warps > 0 && env_warps < sw) sw = env_warps;
-    long long need = (N + sw - 1) / sw;
-    int grid = (int)(need < sm_count() ? need : sm_count());
-    warp_decode_kernel<true><<<grid, sw * 32, 0, (cudaStream_t)stream>>>(p);
-    int rc = check_launch("ubpl_warp_decode");
-    if (rc != UBPL_OK || !p.slow_list) return rc;
-    return launch_slow(p, map_bytes, (cudaStream_t)stream);
-  }
-  const size_t smem = (size_t)warps * nbuf * buf_stride + (size_t)warps * nbuf * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(warp_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
-    if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
-    attr_set = true;
-  }
-  long long need = (N + warps - 1) / warps;
-  int grid = (int)(need < sm_count() ? need : sm_count());
-  warp_decode_kernel<false><<<grid, warps * 32, smem, (cudaStream_t)stream>>>(p);
-  int rc = check_launch("ubpl_warp_decode");
-  if (rc != UBPL_OK || !p.slow_list) return rc;
-  return launch_slow(p, map_bytes, (cudaStream_t)stream);
+  return launch_k1(p, (cudaStream_t)stream);
+}
+
+// Workspace of ubpl_warp_decode_k2, int32 words: [0,1] claim counter, [2] queue length, [3] pad,
+// [4, 4+J+2) counts, then the B*J arrival counters, then the queue of V*B*J map indices.  Everything in front
+// of the queue is cleared by ONE memset node per launch.
+static inline long long k2_ws_zero_words(int B, int J) { return 4 + ((J + 2 + 1) & ~1) + (long long)B * J; }
+
+extern "C" int64_t ubpl_warp_decode_k2_ws_bytes(int V, int B, int J) {
+  if (V < 0 || B < 0 || J < 0) return 0;
+  return 4 * (k2_ws_zero_words(B, J) + (int64_t)V * B * J + 4);
+}
+
+extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ, int V, int B, int J, int H,
+                                   int W, const float* theta, const uint8_t* flip, const double* dec, int refine,
+                                   int32_t* out_idx, float* out_max, float* out_xy, int k2_mode, double distThrMax,
+                                   int img_h, int img_w, float stride, float sigma, int S, float* mean, double* dist,
+                                   uint8_t* legal, uint8_t* enable, float* gate, int64_t* stats, int32_t* ws,
+                                   int64_t ws_bytes, void* stream) {
+  UBPL_REQUIRE(maps && theta && out_xy && ws, "ubpl_warp_decode_k2: NULL pointer");
+  UBPL_REQUIRE(V >= 1 && V <= 32 && B >= 0 && J >= 1 && H > 0 && W > 0, "ubpl_warp_decode_k2: bad dims V=%d B=%d J=%d H=%d W=%d (1 <= V <= 32)", V, B, J, H, W);
+  UBPL_REQUIRE(refine >= 0 && refine <= 2, "ubpl_warp_decode_k2: refine must be 0, 1 or 2");
+  UBPL_REQUIRE(k2_mode == 1 || k2_mode == 2, "ubpl_warp_decode_k2: k2_mode must be 1 (dispersion) or 2 (fixed rule)");
+  UBPL_REQUIRE(k2_mode == 1 || (gate && S >= 1 && stride > 0.f && sigma > 0.f), "ubpl_warp_decode_k2: mode 2 needs gate, S, stride, sigma");
+  UBPL_REQUIRE(ws_bytes >= ubpl_warp_decode_k2_ws_bytes(V, B, J), "ubpl_warp_decode_k2: workspace too small");
+  UBPL_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "ubpl_warp_decode_k2: workspace must be 8-byte aligned");
+  const long long zero_words = k2_ws_zero_words(B, J);
+  cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)zero_words * 4, (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("ubpl_warp_decode_k2: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+  const long long N = (long long)V * B * J;
+  if (N == 0) return UBPL_OK;
+  WDParams p;
+  memset(&p, 0, sizeof(p));
+  p.maps = maps; p.sV = sV; p.sB = sB; p.sJ = sJ; p.V = V; p.B = B; p.J = J; p.H = H; p.W = W;
+  p.theta = theta; p.flip = flip; p.dec = dec; p.do_warp = 1; p.refine = refine;
+  p.out_idx = out_idx; p.out_max = out_max; p.out_xy = out_xy; p.out_hm_xy = nullptr;
+  p.stats = reinterpret_cast<unsigned long long*>(stats);
+  p.work = reinterpret_cast<unsigned long long*>(ws);
+  p.slow_count = reinterpret_cast<unsigned*>(ws + 2);
+  p.slow_list = ws + zero_words;
+  K2Fuse& f = p.k2;
+  f.mode = k2_mode; f.K = V;
+  f.counts = ws + 4;
+  f.arrive = reinterpret_cast<unsigned*>(ws + 4 + ((J + 2 + 1) & ~1));
+  f.distThrMax = distThrMax; f.img_h = img_h; f.img_w = img_w; f.S = S; f.stride = stride; f.sigma = sigma;
+  f.mean = mean; f.dist = dist; f.legal = legal; f.enable = enable; f.gate = gate;
+  int rc = pow_table(&f.T.key, &f.T.val, &f.T.bits, &f.T.n, &f.T.rmax);
+  if (rc != UBPL_OK) return rc;
+  return launch_k1(p, (cudaStream_t)stream);
 }
 
 extern "C" int ubpl_warp_materialize(const float* in, int64_t sN, int64_t sC, float* out, int64_t oN, int64_t oC,

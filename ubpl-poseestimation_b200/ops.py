@@ -92,6 +92,42 @@ def warp_decode(maps, theta=None, flip=None, dec=None, refine=0, stats=None, wan
     return res
 
 
+def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stride=4.0, sigma=3.0, distThrMax=1.0,
+                   refine=0, stats=None, want_idx=True):
+    """K1 with the per-joint part of K2 fused into its epilogue (one teacher, maps [K,B,J,H,W], K <= 32).
+    mode 1: + mean [B,J,2], dist [B,J] f64 (999 = illegal), legal [B,J]   (utils/evaluation.py:44-54)
+    mode 2: + enable, gate = enable * visibility, counts [J+1], count = S * #(gate > 0)
+            (utils/business.py:237-261,375-376, utils/process.py:262-268, utils/losses.py:29)."""
+    _need_cuda(maps, theta, flip, dec, stats)
+    if maps.dtype != _f32:
+        raise _lib.UbplError("heat-maps must be float32")
+    maps = _inner_contig(maps)
+    K, B, J, H, W = maps.shape
+    if not 1 <= K <= 32:
+        raise _lib.UbplError("warp_decode_k2 supports 1..32 views")
+    dev = maps.device
+    theta = theta.reshape(K, B, 2, 3).to(_f32).contiguous()
+    flip = None if flip is None else flip.reshape(K, B).to(torch.uint8).contiguous()
+    dec = None if dec is None else dec.reshape(B, 4).to(_f64).contiguous()
+    out_idx = torch.empty(K, B, J, dtype=torch.int32, device=dev) if want_idx else None
+    out_max = torch.empty(K, B, J, dtype=_f32, device=dev)
+    out_xy = torch.empty(K, B, J, 2, dtype=_f32, device=dev)
+    mean = torch.empty(B, J, 2, dtype=_f32, device=dev)
+    dist = torch.empty(B, J, dtype=_f64, device=dev)
+    legal = torch.empty(B, J, dtype=torch.uint8, device=dev)
+    enable = torch.empty(B, J, dtype=torch.uint8, device=dev) if mode == 2 else None
+    gate = torch.empty(B, J, dtype=_f32, device=dev) if mode == 2 else None
+    ws_bytes = int(_lib.lib().ubpl_warp_decode_k2_ws_bytes(K, B, J))
+    ws = torch.empty(ws_bytes // 4, dtype=torch.int32, device=dev)
+    _lib.call("ubpl_warp_decode_k2", maps.data_ptr(), maps.stride(0), maps.stride(1), maps.stride(2), K, B, J, H, W,
+              theta.data_ptr(), _p(flip), _p(dec), int(refine), _p(out_idx), out_max.data_ptr(), out_xy.data_ptr(),
+              int(mode), float(distThrMax), int(img_h), int(img_w), float(stride), float(sigma), int(S),
+              mean.data_ptr(), dist.data_ptr(), legal.data_ptr(), _p(enable), _p(gate), _p(stats), ws.data_ptr(),
+              ws_bytes, _stream())
+    return dict(idx=out_idx, max=out_max, xy=out_xy, mean=mean, dist=dist, legal=legal, enable=enable, gate=gate,
+                counts=ws[4:4 + J + 1], count=ws[4 + J + 1:4 + J + 2], ws=ws)
+
+
 def warp_materialize(heatmap, warpmat, isflip):
     """AugmentUtils.affine_back2 (utils/augment.py:37-47) as one kernel; returns a new tensor."""
     _need_cuda(heatmap, warpmat, isflip)
@@ -235,7 +271,49 @@ def pair_distance(c1, c2):
     return out
 
 
-def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, group=None, n_total=None, backend=None):
+def select_quantile_fused(dist, legal, J, k_rank, reliableThr, reliableDistMin, gate=None, p2p=False):
+    """ubpl_select_quantile_fused: the whole quantile selection of this rank's items in ONE launch (single CTA).
+    p2p=False: the items are the whole population.  p2p=True: the keys of all ranks are exchanged through the
+    peer-memory buffer of dist.init_p2p (a collective: every rank calls it the same number of times).
+    `gate` = (kps [n,2] f32, S, img_h, img_w, stride, sigma, loss_weight) folds gate_prepare into the launch;
+    the result then carries the final gate, `count` and `grad_scale`."""
+    import os
+    _need_cuda(dist, legal)
+    dist = dist.reshape(-1).to(_f64).contiguous()
+    legal = legal.reshape(-1)
+    if legal.dtype in (torch.uint8, torch.bool):
+        legal = legal.to(torch.uint8).contiguous()
+        lf, lu = None, legal
+    else:
+        legal = legal.to(_f64).contiguous()
+        lf, lu = legal, None
+    n = dist.numel()
+    dev = dist.device
+    rel = torch.empty(n, dtype=_f64, device=dev)
+    keys = None if p2p else torch.empty(n, dtype=torch.int64, device=dev)
+    enable = torch.empty(n, dtype=torch.uint8, device=dev)
+    g32 = torch.empty(n, dtype=_f32, device=dev)
+    counts = torch.empty(J + 1, dtype=torch.int32, device=dev)
+    thr = torch.empty(1, dtype=_f64, device=dev)
+    ext = torch.empty(2, dtype=_f64, device=dev)
+    kps = grad_scale = count = None
+    S, img_h, img_w, stride, sigma, lw = 1, 0, 0, 1.0, 1.0, 1.0
+    if gate is not None:
+        kps, S, img_h, img_w, stride, sigma, lw = gate
+        _need_cuda(kps)
+        kps = kps.reshape(-1, 2).to(_f32).contiguous()
+        grad_scale = torch.empty(1, dtype=_f32, device=dev)
+        count = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.call("ubpl_select_quantile_fused", dist.data_ptr(), _p(lf), _p(lu), n, J, int(k_rank), float(reliableThr),
+              float(reliableDistMin), rel.data_ptr(), _p(keys), enable.data_ptr(), g32.data_ptr(), counts.data_ptr(),
+              thr.data_ptr(), ext.data_ptr(), _p(kps), int(img_h), int(img_w), float(stride), float(sigma), int(S),
+              float(lw), _p(grad_scale), _p(count), 1 if p2p else 0, _stream())
+    return dict(reliability=rel, enable=enable, gate=g32, counts=counts, thr=thr, ext=ext, grad_scale=grad_scale,
+                count=count, gate_fused=gate is not None)
+
+
+def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, group=None, n_total=None, backend=None,
+                    gate=None):
     """BusinessUtils.filter_pseudo2 (utils/business.py:173-217) on device: min/max normalise,
     reliability = 1 - unc, exact k-th order statistic (k = int((n-1)*pct) from the top) by a
     4-pass 16-bit radix select, enable = reliability > max(reliableThr, kth).
@@ -245,8 +323,8 @@ def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, g
     all shards are assumed equal in size unless n_total is given.  `backend` exists for the
     world_size-2 gloo test of this control flow (tests/test_dist_gloo.py); the product always
     uses the CUDA kernels."""
+    import os
     be = backend if backend is not None else _CudaSelectBackend()
-    dist, legal = be.prepare(dist, legal)
     n = dist.numel()
     world = 1
     if group is not None:
@@ -254,8 +332,18 @@ def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, g
         world = td.get_world_size(group)
     if n_total is None:
         n_total = n * world
+    legacy = os.environ.get("UBPL_SELECT", "") == "legacy"
+    if backend is None and not legacy and n >= 1:
+        from . import dist as _dist
+        if world == 1:
+            return select_quantile_fused(dist, legal, J, int((n - 1) * reliablePCT), reliableThr, reliableDistMin, gate=gate)
+        if _dist.p2p_ready(group):
+            # all ranks' keys are exchanged over NVLink peer memory inside the one kernel (no NCCL call)
+            return select_quantile_fused(dist, legal, J, int((n_total - 1) * reliablePCT), reliableThr, reliableDistMin,
+                                         gate=gate, p2p=True)
+    dist, legal = be.prepare(dist, legal)
     if world == 1 and backend is None and 1 <= n <= (1 << 20):
-        # single GPU: extrema, reliability, radix select and masks in ONE launch
+        # single GPU (legacy one-launch kernel): extrema, reliability, radix select and masks
         dev = dist.device
         k = int((n - 1) * reliablePCT)
         rel = torch.empty(n, dtype=_f64, device=dev)
@@ -365,11 +453,26 @@ def render_targets(kps, H, W, img_h, img_w, stride=None, sigma=3.0):
     return hm, kout
 
 
+_tickets = {}
+
+
+def _ticket(dev):
+    """A zero-initialised device uint32 for kernels that elect their last CTA (the kernel returns it to zero).
+    64 slots per device, handed out round-robin so that launches on different streams rarely share one."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    ring = _tickets.get(key)
+    if ring is None:
+        ring = _tickets[key] = [torch.zeros(64, dtype=torch.int32, device=dev), 0]
+    ring[1] = (ring[1] + 1) % 64
+    return ring[0][ring[1]:ring[1] + 1]
+
+
 def render_mse(kps, gate, sample_w, pred, img_h, img_w, stride=None, sigma=3.0, grad_scale=None,
-               want_grad=True, want_target=True, count_in=None, loss_weight=1.0):
+               want_grad=True, want_target=True, count_in=None, loss_weight=1.0, want_summary=False):
     """Fused Gaussian render + JointMSELoss forward + gradient (K3b).  kps [B,J,2] image space,
     gate [B,J] or None, sample_w [B] / [B,1] or None, pred [B,S,J,H,W].  Returns dict(per_loss
-    [B,S,J], gate_out [B,J], grad, target)."""
+    [B,S,J], gate_out [B,J], grad, target[, summary]); want_summary adds the float64[4] reduction of
+    loss_finalize(per_loss, None, gate_out) computed by the same launch."""
     _need_cuda(kps, gate, sample_w, pred, grad_scale)
     pred = _inner_contig(pred)
     B, S, J, H, W = pred.shape
@@ -385,11 +488,17 @@ def render_mse(kps, gate, sample_w, pred, img_h, img_w, stride=None, sigma=3.0, 
     per_loss = torch.empty(B, S, J, dtype=_f32, device=dev)
     gs_out = torch.empty(1, dtype=_f32, device=dev) if count_in is not None else None
     gs = (0, 0, 0) if grad is None else (grad.stride(0), grad.stride(1), grad.stride(2))
-    _lib.call("ubpl_render_mse", kps.data_ptr(), _p(gate), _p(sample_w), pred.data_ptr(), pred.stride(0),
-              pred.stride(1), pred.stride(2), _p(grad), gs[0], gs[1], gs[2], _p(target), B, S, J, H, W, int(img_h),
-              int(img_w), float(stride), float(sigma), _p(grad_scale), _p(count_in), float(loss_weight), _p(gs_out),
-              gate_out.data_ptr(), per_loss.data_ptr(), _stream())
-    return dict(per_loss=per_loss, gate_out=gate_out, grad=grad, target=target, grad_scale=gs_out)
+    args = (kps.data_ptr(), _p(gate), _p(sample_w), pred.data_ptr(), pred.stride(0),
+            pred.stride(1), pred.stride(2), _p(grad), gs[0], gs[1], gs[2], _p(target), B, S, J, H, W, int(img_h),
+            int(img_w), float(stride), float(sigma), _p(grad_scale), _p(count_in), float(loss_weight), _p(gs_out),
+            gate_out.data_ptr(), per_loss.data_ptr())
+    summary = None
+    if want_summary:
+        summary = torch.empty(4, dtype=_f64, device=dev)
+        _lib.call("ubpl_render_mse_sum", *args, summary.data_ptr(), _ticket(dev).data_ptr(), _stream())
+    else:
+        _lib.call("ubpl_render_mse", *args, _stream())
+    return dict(per_loss=per_loss, gate_out=gate_out, grad=grad, target=target, grad_scale=gs_out, summary=summary)
 
 
 def dense_mse(pred, tgt, coef=None, mask_mode=0, thr=0.0, grad_scale=None, want_grad=True, want_scores=False):

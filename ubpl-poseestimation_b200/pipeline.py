@@ -32,6 +32,8 @@ class StepConfig:
     want_target: bool = True         # materialise the rendered targets (counted in the byte model)
     want_grad: bool = True
     fuse_k2: bool = True             # one-launch K2 for the M=1 fixed-threshold path
+    fuse_k12: bool = True            # M=1: the per-joint part of K2 runs in K1's epilogue (no K2 launch on the fixed path)
+    fuse_sum: bool = True            # the loss reduction runs in K3's last CTA (no loss_finalize launch)
 
 
 def nega_weights(islabeled, pseudoWeight):
@@ -40,10 +42,22 @@ def nega_weights(islabeled, pseudoWeight):
                        torch.full((), float(pseudoWeight), device=islabeled.device)).to(torch.float32)
 
 
-def stage_k1(st, stats=None):
-    """K1: back-warp + flip + arg-max decode of every (model, view) map, each read from HBM once."""
+def stage_k1(st, stats=None, cfg=None):
+    """K1: back-warp + flip + arg-max decode of every (model, view) map, each read from HBM once.  With one
+    teacher (and cfg.fuse_k12) the per-joint dispersion -- and on the fixed path the whole selection -- is
+    computed by the warp that decodes the last view of a joint, inside the same launch."""
     teacher, theta, flip, dec = st["teacher"], st["theta"], st["flip"], st["dec"]
     M, K, B, J, H, W = teacher.shape
+    st.pop("k12", None)
+    if cfg is not None and cfg.fuse_k12 and M == 1 and K <= 32 and cfg.select in ("fixed", "quantile"):
+        S = st["student"].shape[1]
+        sH, sW = st["student"].shape[-2:]
+        r = ops.warp_decode_k2(teacher[0], theta, flip, dec, 2 if cfg.select == "fixed" else 1, S=S,
+                               img_h=int(sH * cfg.stride), img_w=int(sW * cfg.stride), stride=cfg.stride, sigma=cfg.sigma,
+                               distThrMax=cfg.distThrMax, stats=stats)
+        st["xy"], st["max"], st["idx"] = r["xy"].view(1, K, B, J, 2), r["max"].view(1, K, B, J), r["idx"].view(1, K, B, J)
+        st["k12"] = r
+        return st
     if teacher.stride(0) == K * teacher.stride(1):
         dec_out = ops.warp_decode(teacher.view(M * K, B, J, H, W) if teacher.is_contiguous() else
                                   teacher.as_strided((M * K, B, J, H, W), (teacher.stride(1),) + tuple(teacher.stride()[2:])),
@@ -68,6 +82,15 @@ def stage_k2(st, cfg, group=None):
     H, W = st["student"].shape[-2:]
     stride = cfg.stride
     img_h, img_w = int(H * stride), int(W * stride)
+    k12 = st.get("k12")
+    if k12 is not None and cfg.select == "fixed":            # everything was computed in K1's epilogue
+        st.update(kps=k12["mean"], dist=k12["dist"], legal=k12["legal"], gate=k12["gate"], grad_scale=None,
+                  count=k12["count"], enable=k12["enable"], counts=k12["counts"])
+        return st
+    if k12 is not None:                                      # quantile: the selector is the only K2 launch left
+        kps, dist, legal = k12["mean"], k12["dist"], k12["legal"]
+        _select_and_gate(st, cfg, group, kps, dist, legal, J, S, img_h, img_w)
+        return st
     if cfg.fuse_k2 and M == 1 and cfg.select == "fixed":
         k2 = ops.k2_view_fixed(xy[0], cfg.distThrMax, S, img_h, img_w, stride, cfg.sigma)
         st.update(kps=k2["mean"], dist=k2["dist"], legal=k2["legal"], gate=k2["gate"], grad_scale=None,
@@ -84,16 +107,26 @@ def stage_k2(st, cfg, group=None):
         st.update(assess=ad)
     else:
         raise ValueError("pseudo_label_step supports M = 1 (mean teacher) or M = 2 (dual teachers)")
+    _select_and_gate(st, cfg, group, kps, dist, legal, J, S, img_h, img_w)
+    return st
+
+
+def _select_and_gate(st, cfg, group, kps, dist, legal, J, S, img_h, img_w):
+    """selection mask -> visibility gate, open-gate count and gradient scale (one launch on the quantile path
+    when the fused selector is in use, else selector + gate_prepare)."""
     if cfg.select == "fixed":
         sel = ops.select_fixed(dist, legal, J, cfg.distThrMax)
     elif cfg.select == "quantile":
-        sel = ops.select_quantile(dist, legal, J, cfg.reliableThr, cfg.reliablePCT, cfg.reliableDistMin, group=group)
+        sel = ops.select_quantile(dist, legal, J, cfg.reliableThr, cfg.reliablePCT, cfg.reliableDistMin, group=group,
+                                  gate=(kps, S, img_h, img_w, cfg.stride, cfg.sigma, cfg.lossWeight))
     else:
         raise ValueError("select must be 'fixed' or 'quantile'")
-    gate, grad_scale, count = ops.gate_prepare(kps, sel["gate"], S, img_h, img_w, stride, cfg.sigma, cfg.lossWeight)
+    if sel.get("gate_fused"):
+        gate, grad_scale, count = sel["gate"], sel["grad_scale"], sel["count"]
+    else:
+        gate, grad_scale, count = ops.gate_prepare(kps, sel["gate"], S, img_h, img_w, cfg.stride, cfg.sigma, cfg.lossWeight)
     st.update(kps=kps, dist=dist, legal=legal, gate=gate, grad_scale=grad_scale, count=count, enable=sel["enable"],
               counts=sel["counts"], sel=sel)
-    return st
 
 
 def stage_k3(st, cfg):
@@ -105,12 +138,13 @@ def stage_k3(st, cfg):
     gs = st["grad_scale"]
     r = ops.render_mse(st["kps"], st["gate"], st["sample_w"], student, img_h, img_w, stride, cfg.sigma, grad_scale=gs,
                        want_grad=cfg.want_grad, want_target=cfg.want_target,
-                       count_in=st["count"] if gs is None else None, loss_weight=cfg.lossWeight)
+                       count_in=st["count"] if gs is None else None, loss_weight=cfg.lossWeight,
+                       want_summary=cfg.fuse_sum)
     if gs is None:
         st["grad_scale"] = r["grad_scale"]
     st["gate"] = st["gate"].view(B, J)
     st["enable"] = st["enable"].view(B, J)
-    st["summary"] = ops.loss_finalize(r["per_loss"], None, st["gate"])
+    st["summary"] = r["summary"] if cfg.fuse_sum else ops.loss_finalize(r["per_loss"], None, st["gate"])
     st.update(grad=r["grad"], target=r["target"], per_loss=r["per_loss"])
     return st
 
@@ -125,7 +159,7 @@ def pseudo_label_step(teacher, student, theta, flip, dec, sample_w, cfg: StepCon
     mark = timer if timer is not None else (lambda name: None)
     st = dict(teacher=teacher, student=student, theta=theta, flip=flip, dec=dec, sample_w=sample_w)
     mark("k1_0")
-    stage_k1(st, stats)
+    stage_k1(st, stats, cfg)
     mark("k1_1")
     stage_k2(st, cfg, group)
     mark("k3_0")
@@ -135,14 +169,19 @@ def pseudo_label_step(teacher, student, theta, flip, dec, sample_w, cfg: StepCon
 
 
 class GraphedStep:
-    """The same chain captured into CUDA graphs, one per stage, for fixed shapes and fixed input
-    buffers: a step is then four graph launches instead of ~12 kernel launches plus allocator and
-    Python work, which matters because one step is only ~0.2 ms of GPU time.  Inputs are read from the
-    tensors given here (copy new batches into them); outputs live in `self.state`.
-    `ema` is an optional ops.EmaPlan whose update (K4) becomes the fourth graph."""
+    """The same chain captured into CUDA graphs for fixed shapes and fixed input buffers: one step is only
+    ~0.2 ms of GPU time, so eager launches (plus allocator and Python work) would leave the GPU waiting for
+    the host.  Inputs are read from the tensors given here (copy new batches into them); outputs live in
+    `self.state`.  `ema` is an optional ops.EmaPlan whose update is K4.
+
+    mode "single" (default): ONE graph per step; the stage edges are external CUDA events recorded by
+    event-record nodes inside the graph, so `stage_ms()` gives the device time of each stage of the most
+    recent replay without splitting the step into several launches.
+    mode "stages": one graph per stage (K1, K2, K3, K4), stage edges recorded by the caller's `timer`.
+    A stage whose collective cannot be captured (the NCCL selector) runs eagerly and forces "stages"."""
 
     def __init__(self, teacher, student, theta, flip, dec, sample_w, cfg: StepConfig, group=None, stats=None,
-                 ema=None, alpha=None, warmup=3, overlap_ema=True):
+                 ema=None, alpha=None, warmup=3, overlap_ema=True, mode="single"):
         self.cfg, self.group, self.ema, self.alpha = cfg, group, ema, alpha
         self.state = dict(teacher=teacher, student=student, theta=theta, flip=flip.to(torch.uint8), dec=dec,
                           sample_w=sample_w)
@@ -158,26 +197,50 @@ class GraphedStep:
         self.eager = {}
         self.overlap_ema = bool(overlap_ema and ema is not None)
         self._side = torch.cuda.Stream() if self.overlap_ema else None
+        self.events = {}
 
         def k1_fn():
             if self.overlap_ema:
-                # K4 is independent of the chain and HBM-bound while K1 is issue-bound: fork it onto a side
-                # stream inside the same graph so the two run concurrently
+                # K4 is independent of the chain: fork it onto a side stream inside the same graph so that it
+                # runs concurrently with K1 (which is not bandwidth-saturated on its own)
                 self._side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(self._side):
                     self._ema()
-            stage_k1(self.state, stats)
+            stage_k1(self.state, stats, cfg)
             if self.overlap_ema:
                 torch.cuda.current_stream().wait_stream(self._side)
 
         stages = [("k1", k1_fn), ("k2", lambda: stage_k2(self.state, cfg, group)), ("k3", lambda: stage_k3(self.state, cfg))]
         if ema is not None and not self.overlap_ema:
             stages.append(("k4", self._ema))
+        from . import dist as _dist
+        nccl_eager = (group is not None and cfg.select == "quantile" and not _dist.p2p_ready(group))
+        if nccl_eager:
+            mode = "stages"
+        self.mode = mode
+        if mode == "single":
+            try:
+                ev = {n + e: torch.cuda.Event(enable_timing=True, external=True) for n, _ in stages for e in ("_0", "_1")}
+            except TypeError:                             # torch without external events
+                ev = None
+            if ev is not None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for name, fn in stages:
+                        ev[name + "_0"].record()
+                        fn()
+                        ev[name + "_1"].record()
+                self.graphs["step"] = g
+                self.events = ev
+                self.order = ["step"]
+                self.stage_names = [n for n, _ in stages]
+                return
+            self.mode = mode = "stages"
         for name, fn in stages:
             if name == "k3" and "k2" in self.eager:
                 self.eager["k3"] = fn             # K2's outputs are re-allocated every step when it runs eagerly
                 continue
-            if name == "k2" and group is not None and cfg.select == "quantile":
+            if name == "k2" and nccl_eager:
                 # the stage with the NCCL all-reduces is launched eagerly (one fused C call enqueues its kernels
                 # and collectives); its outputs are re-allocated every step, so K3 stays eager as well
                 self.eager["k2"] = fn
@@ -188,12 +251,13 @@ class GraphedStep:
             pool = g.pool()
             self.graphs[name] = g
         self.order = [n for n in ("k1", "k2", "k3", "k4") if n in self.graphs or n in self.eager]
+        self.stage_names = list(self.order)
 
     def _ema(self):
         self.ema.step(self.alpha)
 
     def _eager(self, stats):
-        stage_k1(self.state, stats)
+        stage_k1(self.state, stats, self.cfg)
         stage_k2(self.state, self.cfg, self.group)
         stage_k3(self.state, self.cfg)
         if self.ema is not None:
@@ -209,3 +273,10 @@ class GraphedStep:
                 self.eager[n]()
             mark(n + "_1")
         return self.state
+
+    def stage_ms(self):
+        """mode "single": device milliseconds of every stage of the most recent replay (the caller must have
+        synchronised), from the event-record nodes inside the graph."""
+        if not self.events:
+            return None
+        return {n: self.events[n + "_0"].elapsed_time(self.events[n + "_1"]) for n in self.stage_names}
