@@ -248,7 +248,7 @@ def run_ours(args):
         p2p_ok = False
     if group is not None and c["select"] == "quantile" and not p2p_ok:
         ubpl_dist.init_nccl(group)                 # the library's own communicator for the histogram all-reduce
-    overlap = os.environ.get("UBPL_BENCH_OVERLAP_EMA", "0") != "0"
+    overlap = os.environ.get("UBPL_BENCH_OVERLAP_EMA", "1") != "0"
     gstep = pipeline.GraphedStep(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, group=group,
                                  stats=stats, ema=plan, alpha=alpha, overlap_ema=overlap,
                                  mode=os.environ.get("UBPL_BENCH_GRAPH", "single"))

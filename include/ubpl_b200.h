@@ -247,10 +247,12 @@ int ubpl_render_mse(const float* kps, const float* gate_in, const float* sample_
                     int img_h, int img_w, float stride, float sigma,
                     const float* grad_scale, const int32_t* count_in, float loss_weight,
                     float* grad_scale_out, float* gate_out, float* per_loss, void* stream);
-/* ubpl_render_mse with the loss reduction fused into the same launch: the CTA that finishes last writes
- * summary float64[4] = (sum(per_loss), #(per_loss > 0), B*S*J, #(gate_out > 0)), i.e. what
- * ubpl_loss_finalize(per_loss, NULL, gate_out) returns.  ticket: a device uint32 that is zero before the
- * first launch; the kernel returns it to zero (launches sharing a ticket must not run concurrently). */
+/* ubpl_render_mse with the loss reduction fused into the same launch: every CTA leaves its partial sums in
+ * the workspace and the CTA that finishes last adds them in CTA order and writes summary float64[4] =
+ * (sum(per_loss), #(per_loss > 0), B*S*J, #(gate_out > 0)), i.e. what ubpl_loss_finalize(per_loss, NULL,
+ * gate_out) returns.  sum_ws: UBPL_RENDER_SUM_WS_BYTES of device memory, 16-byte aligned, whose first word is
+ * zero before the first launch; the kernel returns it to zero (launches sharing a workspace must not overlap). */
+#define UBPL_RENDER_SUM_WS_BYTES (16 + 24 * 4096)
 int ubpl_render_mse_sum(const float* kps, const float* gate_in, const float* sample_w,
                         const float* pred, int64_t pB, int64_t pS, int64_t pJ,
                         float* grad, int64_t gB, int64_t gS, int64_t gJ,
@@ -258,7 +260,7 @@ int ubpl_render_mse_sum(const float* kps, const float* gate_in, const float* sam
                         int img_h, int img_w, float stride, float sigma,
                         const float* grad_scale, const int32_t* count_in, float loss_weight,
                         float* grad_scale_out, float* gate_out, float* per_loss,
-                        double* summary, uint32_t* ticket, void* stream);
+                        double* summary, void* sum_ws, void* stream);
 /* kps_heatmap alone (utils/process.py:253-278): kps [N,3] float32 (x,y,w) -> heatmap [N,H,W],
  * kps_out [N,3] with w *= visibility. */
 int ubpl_render_targets(const float* kps, int N, int H, int W, int img_h, int img_w, float stride,

@@ -14,6 +14,11 @@
 #include "common.cuh"
 #include <stdlib.h>
 
+// resident CTAs per SM the streaming kernel is compiled for: 6 (80 registers, spills) or 5 (102 registers)
+#ifndef UBPL_K3_OCC_DEFAULT
+#define UBPL_K3_OCC_DEFAULT 6
+#endif
+
 namespace ubpl {
 
 __device__ __forceinline__ float4 load4(const float* base, int q, int n, bool vec) {
@@ -82,14 +87,14 @@ __device__ __forceinline__ float gauss_px(const float* ex, const float* ey, int 
 
 // One WARP per (sample, joint): no block barriers; every lane keeps 8 independent 128-bit loads in
 // flight; the separable Gaussian factors live in a per-warp shared-memory slice.
-template <bool VEC, int SS>
-__global__ void __launch_bounds__(128, 6) render_mse_kernel(
+template <bool VEC, int SS, int OCC>
+__global__ void __launch_bounds__(128, OCC) render_mse_kernel(
     const float* __restrict__ kps, const float* __restrict__ gate_in, const float* __restrict__ sample_w,
     const float* __restrict__ pred, long long pB, long long pS, long long pJ, float* __restrict__ grad, long long gB,
     long long gS, long long gJ, float* __restrict__ target, int B, int S, int J, int H, int W, int img_h, int img_w,
     float stride, float sigma, const float* __restrict__ grad_scale, const int32_t* __restrict__ count_in,
     float loss_weight, float* __restrict__ grad_scale_out, float* __restrict__ gate_out,
-    float* __restrict__ per_loss, const FastDiv divW4, double* __restrict__ summary, unsigned* __restrict__ ticket) {
+    float* __restrict__ per_loss, const FastDiv divW4, double* __restrict__ summary, unsigned char* __restrict__ sum_ws) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   float* ex = sm + (size_t)warp * (W + H);   // [W]
@@ -104,6 +109,10 @@ __global__ void __launch_bounds__(128, 6) render_mse_kernel(
   const float inv_hw = 1.f / (float)HW;
   const long long BJ = (long long)B * J;
   constexpr int U = 8 / SS;
+  // this warp's share of the fused reduction lives in shared memory (updated by lane 0 once per item): the
+  // streaming loop below is register-bound and must not carry accumulators
+  __shared__ double s_red[3][32];
+  if (lane == 0) { s_red[0][warp] = 0.0; s_red[1][warp] = 0.0; s_red[2][warp] = 0.0; }
   for (long long item = (long long)blockIdx.x * wpb + warp; item < BJ; item += (long long)gridDim.x * wpb) {
     const int b = (int)(item / J), j = (int)(item % J);
     if (VEC && lane == 0) {
@@ -192,39 +201,45 @@ __global__ void __launch_bounds__(128, 6) render_mse_kernel(
 #pragma unroll
       for (int ss = 0; ss < SS; ++ss) {
         const float tot = warp_sum(sse[ss]);
-        if (lane == 0 && per_loss) per_loss[((long long)b * S + st0 + ss) * J + j] = ((tot * inv_hw) * gate) * wb;
+        const float pl = ((tot * inv_hw) * gate) * wb;
+        if (lane == 0 && per_loss) per_loss[((long long)b * S + st0 + ss) * J + j] = pl;
+        if (summary && lane == 0) { s_red[0][warp] += (double)pl; s_red[1][warp] += (pl > 0.f) ? 1.0 : 0.0; }
       }
     }
+    if (summary && lane == 0) s_red[2][warp] += (gate > 0.f) ? 1.0 : 0.0;
   }
   if (summary) {
-    // Loss reduction fused into this launch: the CTA that takes the last ticket reduces the [B,S,J] losses and
-    // the [B,J] gates in a fixed order (what loss_finalize_kernel computes with mask = NULL), so the chain
-    // needs no separate reduction launch.  The ticket counter returns to zero for the next launch.
+    // Loss reduction fused into this launch (what loss_finalize_kernel computes with mask = NULL): every CTA
+    // leaves its partial sums in the workspace, the CTA that takes the last ticket adds the partials in CTA
+    // order (the item -> CTA mapping is static, so the result is reproducible) and returns the ticket to zero.
     __shared__ unsigned s_last;
-    __shared__ double s_red[3][32];
-    __threadfence();
+    double* part = reinterpret_cast<double*>(sum_ws + 16);
+    unsigned* ticket = reinterpret_cast<unsigned*>(sum_ws);
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    if (threadIdx.x == 0) {
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+      for (int i = 0; i < wpb; ++i) { t0 += s_red[0][i]; t1 += s_red[1][i]; t2 += s_red[2][i]; }
+      part[3 * blockIdx.x] = t0; part[3 * blockIdx.x + 1] = t1; part[3 * blockIdx.x + 2] = t2;
+      __threadfence();
+      s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
     __syncthreads();
     if (s_last) {
       __threadfence();
-      const long long BSJ = BJ * S;
-      double s = 0.0, np = 0.0, ng = 0.0;
-      for (long long i = threadIdx.x; i < BSJ; i += blockDim.x) {
-        const float l = __ldcg(per_loss + i);
-        s += (double)l;
-        np += (l > 0.f) ? 1.0 : 0.0;
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+      for (unsigned c = threadIdx.x; c < gridDim.x; c += blockDim.x) {
+        t0 += __ldcg(part + 3 * c); t1 += __ldcg(part + 3 * c + 1); t2 += __ldcg(part + 3 * c + 2);
       }
-      for (long long i = threadIdx.x; i < BJ; i += blockDim.x) ng += (__ldcg(gate_out + i) > 0.f) ? 1.0 : 0.0;
-      s = warp_sum(s); np = warp_sum(np); ng = warp_sum(ng);
-      if (lane == 0) { s_red[0][warp] = s; s_red[1][warp] = np; s_red[2][warp] = ng; }
+      t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
       __syncthreads();
-      if (threadIdx.x < 3) {
-        double t = 0.0;
-        for (int i = 0; i < wpb; ++i) t += s_red[threadIdx.x][i];
-        summary[threadIdx.x == 2 ? 3 : threadIdx.x] = t;
+      if (lane == 0) { s_red[0][warp] = t0; s_red[1][warp] = t1; s_red[2][warp] = t2; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+        for (int i = 0; i < wpb; ++i) { u0 += s_red[0][i]; u1 += s_red[1][i]; u2 += s_red[2][i]; }
+        summary[0] = u0; summary[1] = u1; summary[2] = (double)(BJ * S); summary[3] = u2;
+        *ticket = 0u;
       }
-      if (threadIdx.x == 3) { summary[2] = (double)BSJ; *ticket = 0u; }
     }
   }
 }
@@ -416,10 +431,10 @@ static int render_mse_impl(const float* kps, const float* gate_in, const float* 
                            int64_t pB, int64_t pS, int64_t pJ, float* grad, int64_t gB, int64_t gS, int64_t gJ,
                            float* target, int B, int S, int J, int H, int W, int img_h, int img_w, float stride,
                            float sigma, const float* grad_scale, const int32_t* count_in, float loss_weight,
-                           float* grad_scale_out, float* gate_out, float* per_loss, double* summary, unsigned* ticket,
+                           float* grad_scale_out, float* gate_out, float* per_loss, double* summary, unsigned char* sum_ws,
                            void* stream) {
   UBPL_REQUIRE(kps && pred, "ubpl_render_mse: NULL pointer");
-  UBPL_REQUIRE(!summary || (ticket && gate_out && per_loss), "ubpl_render_mse_sum: summary needs ticket, gate_out and per_loss");
+  UBPL_REQUIRE(!summary || sum_ws, "ubpl_render_mse_sum: summary needs the workspace");
   UBPL_REQUIRE(B >= 0 && S >= 1 && J >= 0 && H > 0 && W > 0 && stride > 0.f && sigma > 0.f, "ubpl_render_mse: bad arguments");
   const long long BJ = (long long)B * J;
   if (BJ == 0) return UBPL_OK;
@@ -433,18 +448,23 @@ static int render_mse_impl(const float* kps, const float* gate_in, const float* 
     cudaMemcpyToSymbol(g_store_mode, &m, sizeof(int));
     knob_set = true;
   }
+  const bool occ5 = getenv("UBPL_K3_OCC") ? atoi(getenv("UBPL_K3_OCC")) == 5 : (UBPL_K3_OCC_DEFAULT == 5);
   FastDiv divW4;
   divW4.init((unsigned)(W >= 4 ? W / 4 : 1));
   const int wpb = 4;    // small CTAs: one (b,j) item per warp, finer-grained tail
   const size_t smem = (size_t)wpb * (W + H) * sizeof(float);
   UBPL_REQUIRE(smem <= 48 * 1024, "ubpl_render_mse: heat-map sides too large (%d x %d)", H, W);
   const long long need = (BJ + wpb - 1) / wpb;
-  const long long cap = (long long)sm_count() * 16;
+  long long cap = (long long)sm_count() * 16;
+  if (cap > 4096) cap = 4096;             // UBPL_RENDER_SUM_WS_BYTES holds 4096 CTA partials
   const int grid = (int)(need < cap ? need : cap);
 #define UBPL_LAUNCH_RENDER(V, SSV)                                                                                     \
-  render_mse_kernel<V, SSV><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(                                         \
+  if (occ5) render_mse_kernel<V, SSV, 5><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(                              \
       kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS, gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
-      grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, ticket)
+      grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, sum_ws);                 \
+  else render_mse_kernel<V, SSV, 6><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(                                   \
+      kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS, gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
+      grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, sum_ws)
   if (vec) {
     if (S % 2 == 0) UBPL_LAUNCH_RENDER(true, 2); else UBPL_LAUNCH_RENDER(true, 1);
   } else {
@@ -469,8 +489,8 @@ extern "C" int ubpl_render_mse_sum(const float* kps, const float* gate_in, const
                                    float* target, int B, int S, int J, int H, int W, int img_h, int img_w, float stride,
                                    float sigma, const float* grad_scale, const int32_t* count_in, float loss_weight,
                                    float* grad_scale_out, float* gate_out, float* per_loss, double* summary,
-                                   uint32_t* ticket, void* stream) {
-  UBPL_REQUIRE(summary && ticket, "ubpl_render_mse_sum: summary and ticket are required");
+                                   void* sum_ws, void* stream) {
+  UBPL_REQUIRE(summary && sum_ws && (reinterpret_cast<uintptr_t>(sum_ws) & 15) == 0, "ubpl_render_mse_sum: summary and a 16-byte aligned workspace are required");
   if ((long long)B * J == 0) {
     cudaError_t e = cudaMemsetAsync(summary, 0, 4 * sizeof(double), (cudaStream_t)stream);
     if (e != cudaSuccess) { set_error("ubpl_render_mse_sum: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
@@ -478,7 +498,7 @@ extern "C" int ubpl_render_mse_sum(const float* kps, const float* gate_in, const
   }
   return render_mse_impl(kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS, gJ, target, B, S, J, H, W, img_h, img_w,
                          stride, sigma, grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, summary,
-                         ticket, stream);
+                         reinterpret_cast<unsigned char*>(sum_ws), stream);
 }
 
 extern "C" int ubpl_render_targets(const float* kps, int N, int H, int W, int img_h, int img_w, float stride,

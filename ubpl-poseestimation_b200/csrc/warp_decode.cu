@@ -31,7 +31,7 @@
 #include <string.h>
 
 #ifndef UBPL_K1_EARLY_DEFAULT
-#define UBPL_K1_EARLY_DEFAULT 1
+#define UBPL_K1_EARLY_DEFAULT 0
 #endif
 #ifndef UBPL_K1_PF_DEFAULT
 #define UBPL_K1_PF_DEFAULT 0
@@ -50,6 +50,7 @@ struct K2Fuse {
   int mode;                   // 0 off, 1 dispersion only (mean, dist, legal), 2 + fixed rule, gate and counts
   int K;                      // views per item (= V)
   unsigned* arrive;           // [B*J] arrival counters, zero before the launch
+  unsigned long long* slots;  // [K][B*J] hand-off words ~pack(x, y); 0 = not written yet (zero before the launch)
   double distThrMax;
   int img_h, img_w, S;
   float stride, sigma;
@@ -313,8 +314,17 @@ __device__ __forceinline__ void k2_item(const WDParams& p, long long item, int j
   const long long BJ = (long long)p.B * p.J;
   float x = 0.f, y = 0.f;
   if (lane < K) {
-    const float2 v = __ldcg(reinterpret_cast<const float2*>(p.out_xy) + ((long long)lane * BJ + item));
-    x = v.x; y = v.y;
+    // every view handed its coordinates over as ONE 64-bit word that is never zero once written, so the word
+    // is its own flag: no fence on the writer's side, a (rarely taken) spin here
+    unsigned long long* sp = f.slots + ((long long)lane * BJ + item);
+    unsigned long long v;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(sp) : "memory");
+    } while (v == 0ull);
+    v = ~v;
+    x = __uint_as_float((unsigned)(v & 0xffffffffull));
+    y = __uint_as_float((unsigned)(v >> 32));
+    *sp = 0ull;                                          // ready for the next launch on this workspace
   }
   const bool legal = __all_sync(0xffffffffu, (lane >= K) || ((x >= 0.f) && (y >= 0.f)));
   float sx = __shfl_sync(0xffffffffu, x, 0), sy = __shfl_sync(0xffffffffu, y, 0);
@@ -347,8 +357,9 @@ __device__ __forceinline__ void k2_item(const WDParams& p, long long item, int j
 
 // Epilogue of one map (warp-wide call): arg-max -> heat-map coordinates (mask, optional quarter-offset
 // refinement) -> image-space coordinates -> outputs -> (optional) arrival at the item's K2.
-__device__ __forceinline__ void finish_map(const WDParams& p, long long n, int b, int j, const float* s, const Xform& X,
-                                           float rv, int ri, double dc0, double dc1, double dc2, double dc3, int lane) {
+__device__ __forceinline__ void finish_map(const WDParams& p, long long n, int v, int b, int j, const float* s, const Xform& X,
+                                           float rv, int ri, double dc0, double dc1, double dc2, double dc3, int lane,
+                                           long long& pend_item, unsigned& pend_old) {
   const int H = p.H, W = p.W;
   unsigned ayu, axu;
   p.divW.divmod((unsigned)ri & 0x7fffffffu, ayu, axu);
@@ -375,12 +386,12 @@ __device__ __forceinline__ void finish_map(const WDParams& p, long long n, int b
     }
   }
   if (p.refine != 0) { hx += 0.5f; hy += 0.5f; }      // process.py:372 (+0.5 for every joint)
+  float ox = hx, oy = hy;
   if (lane == 0) {
     if (p.out_idx) p.out_idx[n] = ri;
     if (p.out_max) p.out_max[n] = rv;
     if (p.out_hm_xy) { p.out_hm_xy[2 * n] = hx; p.out_hm_xy[2 * n + 1] = hy; }
     if (p.out_xy) {
-      float ox = hx, oy = hy;
       if (p.dec) {
         // np.dot row: (a00*(x-1) + 0*(y-1)) + a02, astype(int) truncation, +1
         const double tx = __dadd_rn(__dmul_rn(dc0, (double)hx - 1.0), dc1);
@@ -392,20 +403,30 @@ __device__ __forceinline__ void finish_map(const WDParams& p, long long n, int b
     }
   }
   if (p.k2.mode) {
-    // release the coordinates, then count this view in; the warp that sees K-1 earlier arrivals owns the item
-    const long long item = (long long)b * p.J + j;
-    unsigned old = 0;
+    // Hand this view's coordinates to its (sample, joint) and count the view in.  No fence: the coordinates
+    // travel as one self-flagging 64-bit word (see k2_item), the counter is a relaxed atomic, and its result is
+    // not consumed here -- a release fence plus a blocking atomic per map cost ~13 us per launch on the warps'
+    // critical path.  The caller resolves the ticket one map later (k2_resolve).
+    pend_item = (long long)b * p.J + j;
     if (lane == 0) {
-      __threadfence();
-      old = atomicAdd(p.k2.arrive + item, 1u);
-    }
-    old = __shfl_sync(0xffffffffu, old, 0);
-    if (old == (unsigned)(p.k2.K - 1)) {
-      __threadfence();
-      if (lane == 0) p.k2.arrive[item] = 0u;           // ready for the next launch on this workspace
-      k2_item(p, item, j, lane);
+      const long long BJ = (long long)p.B * p.J;
+      const unsigned long long word = ~((unsigned long long)__float_as_uint(ox) | ((unsigned long long)__float_as_uint(oy) << 32));
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p.k2.slots + ((long long)v * BJ + pend_item)), "l"(word) : "memory");
+      asm volatile("atom.add.relaxed.gpu.global.u32 %0, [%1], 1;" : "=r"(pend_old) : "l"(p.k2.arrive + pend_item) : "memory");
     }
   }
+}
+
+// Second half of the K2 hand-off: the warp that saw K-1 earlier arrivals owns the item and computes its K2.
+__device__ __forceinline__ void k2_resolve(const WDParams& p, long long& pend_item, unsigned pend_old, int lane) {
+  if (pend_item < 0) return;
+  const unsigned old = __shfl_sync(0xffffffffu, pend_old, 0);
+  if (old == (unsigned)(p.k2.K - 1)) {
+    __syncwarp();
+    if (lane == 0) p.k2.arrive[pend_item] = 0u;          // ready for the next launch on this workspace
+    k2_item(p, pend_item, (int)(pend_item % p.J), lane);
+  }
+  pend_item = -1;
 }
 
 // What pass A leaves for the later phases.
@@ -663,6 +684,8 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   };
 
   unsigned long long n_slow = 0, n_eval = 0, n_maps = 0, n_miss = 0;
+  long long pend_item = -1;                              // K2 ticket of the previous map (see finish_map)
+  unsigned pend_old = 0;
   for (long long it = 0;; ++it) {
     const long long n = cur;
     if (n >= N) break;
@@ -789,10 +812,14 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       }
     }
 
-    if (!deferred) finish_map(p, n, b, j, s, X, rv, ri, dc0, dc1, dc2, dc3, lane);
+    if (!deferred) {
+      k2_resolve(p, pend_item, pend_old, lane);          // the previous map's ticket has long arrived by now
+      finish_map(p, n, (int)vu, b, j, s, X, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
+    }
     __syncwarp();
     cur = EARLY ? nxt : advance();
   }
+  k2_resolve(p, pend_item, pend_old, lane);
   if (p.stats && lane == 0 && n_maps) {
     atomicAdd(p.stats + 0, n_slow);
     atomicAdd(p.stats + 1, n_eval);
@@ -841,7 +868,10 @@ __global__ void __launch_bounds__(kSlowWarps * 32) warp_decode_slow_kernel(const
       for (int w = 1; w < kSlowWarps; ++w) if (arg_better(s_v[w], s_i[w], rv, ri)) { rv = s_v[w]; ri = s_i[w]; }
       double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
       if (p.dec) { const double* c = p.dec + (size_t)bu * 4; dc0 = c[0]; dc1 = c[1]; dc2 = c[2]; dc3 = c[3]; }
-      finish_map(p, n, (int)bu, (int)ju, sm_map, X, rv, ri, dc0, dc1, dc2, dc3, lane);
+      long long pend_item = -1;
+      unsigned pend_old = 0;
+      finish_map(p, n, (int)vu, (int)bu, (int)ju, sm_map, X, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
+      k2_resolve(p, pend_item, pend_old, lane);
     }
   }
 }
@@ -979,13 +1009,15 @@ extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64
 }
 
 // Workspace of ubpl_warp_decode_k2, int32 words: [0,1] claim counter, [2] queue length, [3] pad,
-// [4, 4+J+2) counts, then the B*J arrival counters, then the queue of V*B*J map indices.  Everything in front
-// of the queue is cleared by ONE memset node per launch.
-static inline long long k2_ws_zero_words(int B, int J) { return 4 + ((J + 2 + 1) & ~1) + (long long)B * J; }
+// [4, 4+J+2) counts, then the B*J arrival counters, the V*B*J 64-bit hand-off words, and last the queue of
+// V*B*J map indices.  Everything in front of the queue is cleared by ONE memset node per launch.
+static inline long long k2_ws_arrive_off(int J) { return 4 + ((J + 2 + 1) & ~1); }
+static inline long long k2_ws_slots_off(int B, int J) { return (k2_ws_arrive_off(J) + (long long)B * J + 1) & ~1ll; }
+static inline long long k2_ws_zero_words(int V, int B, int J) { return k2_ws_slots_off(B, J) + 2ll * V * B * J; }
 
 extern "C" int64_t ubpl_warp_decode_k2_ws_bytes(int V, int B, int J) {
   if (V < 0 || B < 0 || J < 0) return 0;
-  return 4 * (k2_ws_zero_words(B, J) + (int64_t)V * B * J + 4);
+  return 4 * (k2_ws_zero_words(V, B, J) + (int64_t)V * B * J + 4);
 }
 
 extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ, int V, int B, int J, int H,
@@ -1001,7 +1033,7 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
   UBPL_REQUIRE(k2_mode == 1 || (gate && S >= 1 && stride > 0.f && sigma > 0.f), "ubpl_warp_decode_k2: mode 2 needs gate, S, stride, sigma");
   UBPL_REQUIRE(ws_bytes >= ubpl_warp_decode_k2_ws_bytes(V, B, J), "ubpl_warp_decode_k2: workspace too small");
   UBPL_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "ubpl_warp_decode_k2: workspace must be 8-byte aligned");
-  const long long zero_words = k2_ws_zero_words(B, J);
+  const long long zero_words = k2_ws_zero_words(V, B, J);
   cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)zero_words * 4, (cudaStream_t)stream);
   if (e != cudaSuccess) { set_error("ubpl_warp_decode_k2: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
   const long long N = (long long)V * B * J;
@@ -1018,7 +1050,8 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
   K2Fuse& f = p.k2;
   f.mode = k2_mode; f.K = V;
   f.counts = ws + 4;
-  f.arrive = reinterpret_cast<unsigned*>(ws + 4 + ((J + 2 + 1) & ~1));
+  f.arrive = reinterpret_cast<unsigned*>(ws + k2_ws_arrive_off(J));
+  f.slots = reinterpret_cast<unsigned long long*>(ws + k2_ws_slots_off(B, J));
   f.distThrMax = distThrMax; f.img_h = img_h; f.img_w = img_w; f.S = S; f.stride = stride; f.sigma = sigma;
   f.mean = mean; f.dist = dist; f.legal = legal; f.enable = enable; f.gate = gate;
   int rc = pow_table(&f.T.key, &f.T.val, &f.T.bits, &f.T.n, &f.T.rmax);

@@ -453,18 +453,19 @@ def render_targets(kps, H, W, img_h, img_w, stride=None, sigma=3.0):
     return hm, kout
 
 
-_tickets = {}
+_sum_ws = {}
+_SUM_WS_WORDS = (16 + 24 * 4096) // 4 + 12          # UBPL_RENDER_SUM_WS_BYTES, padded to a multiple of 64 B
 
 
-def _ticket(dev):
-    """A zero-initialised device uint32 for kernels that elect their last CTA (the kernel returns it to zero).
-    64 slots per device, handed out round-robin so that launches on different streams rarely share one."""
+def _sum_workspace(dev):
+    """A zero-initialised workspace for kernels that elect their last CTA (the kernel returns its ticket word to
+    zero).  8 slots per device, handed out round-robin so that launches on different streams rarely share one."""
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
-    ring = _tickets.get(key)
+    ring = _sum_ws.get(key)
     if ring is None:
-        ring = _tickets[key] = [torch.zeros(64, dtype=torch.int32, device=dev), 0]
-    ring[1] = (ring[1] + 1) % 64
-    return ring[0][ring[1]:ring[1] + 1]
+        ring = _sum_ws[key] = [torch.zeros(8, _SUM_WS_WORDS, dtype=torch.int32, device=dev), 0]
+    ring[1] = (ring[1] + 1) % 8
+    return ring[0][ring[1]]
 
 
 def render_mse(kps, gate, sample_w, pred, img_h, img_w, stride=None, sigma=3.0, grad_scale=None,
@@ -495,7 +496,7 @@ def render_mse(kps, gate, sample_w, pred, img_h, img_w, stride=None, sigma=3.0, 
     summary = None
     if want_summary:
         summary = torch.empty(4, dtype=_f64, device=dev)
-        _lib.call("ubpl_render_mse_sum", *args, summary.data_ptr(), _ticket(dev).data_ptr(), _stream())
+        _lib.call("ubpl_render_mse_sum", *args, summary.data_ptr(), _sum_workspace(dev).data_ptr(), _stream())
     else:
         _lib.call("ubpl_render_mse", *args, _stream())
     return dict(per_loss=per_loss, gate_out=gate_out, grad=grad, target=target, grad_scale=gs_out, summary=summary)
