@@ -248,7 +248,7 @@ def run_ours(args):
         p2p_ok = False
     if group is not None and c["select"] == "quantile" and not p2p_ok:
         ubpl_dist.init_nccl(group)                 # the library's own communicator for the histogram all-reduce
-    overlap = os.environ.get("UBPL_BENCH_OVERLAP_EMA", "1") != "0"
+    overlap = {"0": False, "1": "k1", "k1": "k1", "k3": "k3"}[os.environ.get("UBPL_BENCH_OVERLAP_EMA", "k1")]
     gstep = pipeline.GraphedStep(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, group=group,
                                  stats=stats, ema=plan, alpha=alpha, overlap_ema=overlap,
                                  mode=os.environ.get("UBPL_BENCH_GRAPH", "single"))
@@ -353,8 +353,9 @@ def run_ours(args):
     roof = {"bound": "hbm", "kernel": "warp_decode_kernel (K1: %d maps of %d B per launch)" % (M * K * B * J, 4 * H * W),
             "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC.get(args.config), "peak_source": peak_src,
-            "stages_ms": {("k1_warp_decode_with_k4_ema_overlapped" if gstep.overlap_ema else "k1_warp_decode"): k1_ms,
-                          "k2_uncertainty_select": k2_ms, "k3_render_mse": k3_ms,
+            "stages_ms": {("k1_warp_decode_with_k4_ema_overlapped" if gstep.overlap_ema == "k1" else "k1_warp_decode"): k1_ms,
+                          "k2_uncertainty_select": k2_ms,
+                          ("k3_render_mse_with_k4_ema_overlapped" if gstep.overlap_ema == "k3" else "k3_render_mse"): k3_ms,
                           "k4_ema_in_step": k4_inline_ms, "k4_ema_standalone": k4_ms},
             "stages_note": ("stage edges are event-record nodes inside the step's single CUDA graph; mean of the last "
                             "timed step and 32 further steps" if single else
@@ -415,7 +416,7 @@ def run_ours(args):
                        "selected_frac": float(r["enable"].float().mean()), "exhaustive_decode_frac": slow_frac,
                        "launch": ("1 CUDA graph per step" if single else "%d stage launches per step (%s)" % (len(gstep.order), ", ".join(
                                       n + (":eager" if n in gstep.eager else ":graph") for n in gstep.order)))
-                                 + ("; EMA forked onto a side stream beside K1" if gstep.overlap_ema else "; EMA after K3"),
+                                 + ("; EMA forked onto a side stream beside %s" % gstep.overlap_ema.upper() if gstep.overlap_ema else "; EMA after K3"),
                        "selector": ("fixed rule in K1's epilogue" if c["select"] == "fixed" and cfg.fuse_k12 and M == 1 else
                                     "fused one-kernel quantile selector" + (" over NVLink peer memory" if p2p_ok else "")
                                     if (world == 1 or p2p_ok) and c["select"] == "quantile" else

@@ -75,8 +75,8 @@ int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
  *   k2_mode 2: + enable [B,J] u8, gate [B,J] f32 (= enable * visibility) and the counts below
  * so the chain needs no K2 launch (mode 2) or only the quantile selector (mode 1).
  * ws   int32 workspace of ubpl_warp_decode_k2_ws_bytes(V, B, J) bytes, 8-byte aligned; the call clears its
- *      head with one memset node.  After the launch ws[4 .. 4+J) = selected items per joint, ws[4+J] = total
- *      selected, ws[4+J+1] = S * #(gate > 0) (mode 2) -- the `count_in` of ubpl_render_mse.
+ *      head with one memset node.  After the launch ws[128 .. 128+J) = selected items per joint, ws[128+J] = total
+ *      selected, ws[128+J+1] = S * #(gate > 0) (mode 2) -- the `count_in` of ubpl_render_mse.
  * Requires 1 <= V <= 32.  mean/dist/legal/enable may be NULL. */
 int64_t ubpl_warp_decode_k2_ws_bytes(int V, int B, int J);
 int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ,

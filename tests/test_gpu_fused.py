@@ -1,5 +1,5 @@
 """GPU parity tests of the fused / early-release variants added on top of the first CUDA path:
-K1 with the K2 epilogue (ubpl_warp_decode_k2), the early-release staging window and the L2 prefetch knob,
+K1 with the K2 epilogue (ubpl_warp_decode_k2) and the early-release staging window,
 K3 with the loss reduction in its last CTA (ubpl_render_mse_sum), the one-kernel quantile selector
 (ubpl_select_quantile_fused) and the single-graph step with event nodes.  Bars as in test_gpu_parity.py:
 indices, masks and float64 dispersions bit-exact; losses within 1e-5 relative."""
@@ -53,8 +53,7 @@ class _Env:
                 os.environ[k] = v
 
 
-KNOBS = [dict(UBPL_K1_EARLY=0, UBPL_K1_PF=0), dict(UBPL_K1_EARLY=1, UBPL_K1_PF=0), dict(UBPL_K1_EARLY=0, UBPL_K1_PF=1),
-         dict(UBPL_K1_EARLY=1, UBPL_K1_PF=1)]
+KNOBS = [dict(UBPL_K1_EARLY=0), dict(UBPL_K1_EARLY=1), dict(UBPL_K1_EARLY=1, UBPL_K1_WARPS=3)]
 
 
 @pytest.mark.parametrize("knobs", KNOBS)
@@ -132,7 +131,7 @@ def test_k1_early_release_full_size(ops):
     dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64])
     outs = {}
     for early in (0, 1):
-        with _Env(UBPL_K1_EARLY=early, UBPL_K1_PF=0):
+        with _Env(UBPL_K1_EARLY=early):
             stats = torch.zeros(4, dtype=torch.int64, device="cuda")
             outs[early] = (ops.warp_decode(d["teacher"][0], d["theta"], d["flip"], dec, stats=stats), stats.cpu())
     for k in ("idx", "max", "xy"):
@@ -167,7 +166,39 @@ def test_warp_decode_k2_matches_unfused(ops, knobs, mode):
             for k in ("mean", "dist", "legal"):
                 assert torch.equal(r[k], vd[k]), k
         # the workspace cleans up after itself: arrival counters are back to zero
-        assert int(r["ws"][4 + ((J + 3) & ~1):4 + ((J + 3) & ~1) + B * J].abs().sum()) == 0
+        assert int(r["ws"][128 + ((J + 3) & ~1):128 + ((J + 3) & ~1) + B * J].abs().sum()) == 0
+
+
+def test_warp_decode_k2_exhaustive_maps(ops):
+    """Maps that need the exhaustive decode (white noise, NaN, constant, singular transforms) through the fused
+    entry: the queued maps hand their coordinates to K2 from the second kernel, same results as the plain entry."""
+    rng = np.random.default_rng(5)
+    maps, th, fl = _edge_maps()
+    noise = rng.standard_normal((6, 9, 7, 64, 64)).astype(np.float32)          # every map is structure-less
+    noise[:, :, 3] = 0.25                                                      # constant: ties everywhere
+    noise[2, 4, 5, 17, 40] = np.nan
+    noise[1, 2, 6] = -np.abs(noise[1, 2, 6])
+    ang = rng.uniform(-0.6, 0.6, (6, 9)); sc = rng.uniform(0.6, 1.5, (6, 9))
+    thn = np.zeros((6, 9, 2, 3), np.float32)
+    thn[..., 0, 0] = np.cos(ang) * sc; thn[..., 0, 1] = np.sin(ang) * sc
+    thn[..., 1, 0] = -np.sin(ang) * sc; thn[..., 1, 1] = np.cos(ang) * sc
+    thn[0, 0] = 0.0                                                            # singular
+    fln = (rng.random((6, 9)) < 0.5).astype(np.uint8)
+    for (m, t, f) in ((maps, th, fl), (noise, thn, fln)):
+        K, B, J = m.shape[:3]
+        dec = ops.decode_coeffs(torch.full((B, 2), 128.0), torch.full((B,), 1.28), [64, 64]).cuda()
+        stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+        r = ops.warp_decode_k2(cu(m), cu(t), cu(f), dec, 2, S=2, distThrMax=2.0, stats=stats)
+        ref = ops.warp_decode(cu(m), cu(t), cu(f), dec, defer_exhaustive=False)
+        assert torch.equal(r["idx"], ref["idx"])
+        assert np.array_equal(npy(r["max"]), npy(ref["max"]), equal_nan=True)
+        assert torch.equal(r["xy"], ref["xy"])
+        k2 = ops.k2_view_fixed(ref["xy"], 2.0, 2, 256, 256, 4.0, 3.0)
+        for k in ("mean", "dist", "legal", "enable", "gate"):
+            assert torch.equal(r[k], k2[k]), k
+        assert int(r["count"]) == int(k2["count"])
+        if m is noise:
+            assert int(stats[0]) > 0.5 * K * B * J                             # the queue really was exercised
 
 
 def test_warp_decode_k2_golden(ops):

@@ -16,7 +16,7 @@
 
 // resident CTAs per SM the streaming kernel is compiled for: 6 (80 registers, spills) or 5 (102 registers)
 #ifndef UBPL_K3_OCC_DEFAULT
-#define UBPL_K3_OCC_DEFAULT 6
+#define UBPL_K3_OCC_DEFAULT 5
 #endif
 
 namespace ubpl {
@@ -113,13 +113,26 @@ __global__ void __launch_bounds__(128, OCC) render_mse_kernel(
   // streaming loop below is register-bound and must not carry accumulators
   __shared__ double s_red[3][32];
   if (lane == 0) { s_red[0][warp] = 0.0; s_red[1][warp] = 0.0; s_red[2][warp] = 0.0; }
-  for (long long item = (long long)blockIdx.x * wpb + warp; item < BJ; item += (long long)gridDim.x * wpb) {
+  // Work split.  Phase 0: one warp per (sample, joint), as many full rounds of gridDim*wpb items as there are.
+  // Phase 1: the items left over (fewer than one round) are each shared by the wpb warps of a CTA, which split
+  // the map's float4s between them -- a warp that had to stream a second whole item on an otherwise idle GPU
+  // would be latency-bound and stretch the launch by ~10 us.
+  __shared__ float s_part[2][32];
+  const long long round_items = (long long)gridDim.x * wpb;
+  const long long full = (BJ / round_items) * round_items;
+  for (int phase = 0; phase < 2; ++phase) {
+  const int nparts = phase ? wpb : 1, part = phase ? warp : 0;
+  const long long it_step = phase ? (long long)gridDim.x : round_items;
+  const long long it_end = phase ? BJ : full;
+  for (long long item = phase ? full + blockIdx.x : (long long)blockIdx.x * wpb + warp; item < it_end; item += it_step) {
     const int b = (int)(item / J), j = (int)(item % J);
-    if (VEC && lane == 0) {
+    const int q_lo = (int)((long long)nq * part / nparts), q_hi = (int)((long long)nq * (part + 1) / nparts);
+    if (VEC && lane == 0 && q_hi > q_lo) {
       // pull this item's student maps towards L2 while the Gaussian factors are set up; the 128-bit
       // loads below then see L2 latency instead of HBM latency
       for (int st = 0; st < S; ++st)
-        bulk_prefetch_l2(pred + (long long)b * pB + (long long)st * pS + (long long)j * pJ, (uint32_t)HW * 4u);
+        bulk_prefetch_l2(pred + (long long)b * pB + (long long)st * pS + (long long)j * pJ + ((long long)q_lo << 2),
+                         (uint32_t)(q_hi - q_lo) * 16u);
     }
     const Gauss g = gauss_setup(kps[2 * item], kps[2 * item + 1], img_h, img_w, stride, sigma);
     __syncwarp();
@@ -130,7 +143,8 @@ __global__ void __launch_bounds__(128, OCC) render_mse_kernel(
     const float gate = (gate_in ? gate_in[item] : 1.f) * g.vis;
     const float wb = sample_w ? sample_w[b] : 1.f;
     const float gcoef = gs * 2.f * inv_hw * gate * wb;
-    if (lane == 0 && gate_out) gate_out[item] = gate;
+    const bool fin = (part == 0) && (lane == 0);         // the lane that writes this item's scalars
+    if (fin && gate_out) gate_out[item] = gate;
     // support box: exp(-r^2/2s^2) >= 0.01 needs r <= s*sqrt(2 ln 100) = 3.035 s; 3.05 s + 1 is a safe superset
     const float rad = 3.05f * sigma + 1.f;
     const int xlo = (int)floorf((float)g.cx - rad), xhi = (int)ceilf((float)g.cx + rad);
@@ -147,20 +161,20 @@ __global__ void __launch_bounds__(128, OCC) render_mse_kernel(
         sse[ss] = 0.f;
       }
       float* tg = (target && st0 == 0) ? target + item * HW : nullptr;
-      for (int q0 = lane; q0 < nq; q0 += 32 * U) {
+      for (int q0 = q_lo + lane; q0 < q_hi; q0 += 32 * U) {
         float4 pv[SS][U];
 #pragma unroll
         for (int ss = 0; ss < SS; ++ss) {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int q = q0 + 32 * u;
-            if (q < nq) pv[ss][u] = load4(p[ss], q, HW, VEC);
+            if (q < q_hi) pv[ss][u] = load4(p[ss], q, HW, VEC);
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int q = q0 + 32 * u;
-          if (q >= nq) continue;
+          if (q >= q_hi) continue;
           const int k = q << 2;
           float4 t;
           if (VEC) {                                    // W % 4 == 0: the four texels share a row
@@ -200,13 +214,21 @@ __global__ void __launch_bounds__(128, OCC) render_mse_kernel(
       }
 #pragma unroll
       for (int ss = 0; ss < SS; ++ss) {
-        const float tot = warp_sum(sse[ss]);
+        float tot = warp_sum(sse[ss]);
+        if (nparts > 1) {                                // add the warps' partial sums in warp order
+          if (lane == 0) s_part[ss][warp] = tot;
+          __syncthreads();
+          tot = 0.f;
+          for (int w2 = 0; w2 < nparts; ++w2) tot += s_part[ss][w2];
+          __syncthreads();
+        }
         const float pl = ((tot * inv_hw) * gate) * wb;
-        if (lane == 0 && per_loss) per_loss[((long long)b * S + st0 + ss) * J + j] = pl;
-        if (summary && lane == 0) { s_red[0][warp] += (double)pl; s_red[1][warp] += (pl > 0.f) ? 1.0 : 0.0; }
+        if (fin && per_loss) per_loss[((long long)b * S + st0 + ss) * J + j] = pl;
+        if (summary && fin) { s_red[0][warp] += (double)pl; s_red[1][warp] += (pl > 0.f) ? 1.0 : 0.0; }
       }
     }
-    if (summary && lane == 0) s_red[2][warp] += (gate > 0.f) ? 1.0 : 0.0;
+    if (summary && fin) s_red[2][warp] += (gate > 0.f) ? 1.0 : 0.0;
+  }
   }
   if (summary) {
     // Loss reduction fused into this launch (what loss_finalize_kernel computes with mask = NULL): every CTA
@@ -448,14 +470,16 @@ static int render_mse_impl(const float* kps, const float* gate_in, const float* 
     cudaMemcpyToSymbol(g_store_mode, &m, sizeof(int));
     knob_set = true;
   }
-  const bool occ5 = getenv("UBPL_K3_OCC") ? atoi(getenv("UBPL_K3_OCC")) == 5 : (UBPL_K3_OCC_DEFAULT == 5);
   FastDiv divW4;
   divW4.init((unsigned)(W >= 4 ? W / 4 : 1));
+  const bool occ5 = getenv("UBPL_K3_OCC") ? atoi(getenv("UBPL_K3_OCC")) == 5 : (UBPL_K3_OCC_DEFAULT == 5);
   const int wpb = 4;    // small CTAs: one (b,j) item per warp, finer-grained tail
   const size_t smem = (size_t)wpb * (W + H) * sizeof(float);
   UBPL_REQUIRE(smem <= 48 * 1024, "ubpl_render_mse: heat-map sides too large (%d x %d)", H, W);
   const long long need = (BJ + wpb - 1) / wpb;
-  long long cap = (long long)sm_count() * 16;
+  // one resident wave: the kernel loops over whole rounds of grid*wpb items and shares the leftover items
+  // between the warps of a CTA, so a second, partial wave of CTAs would only add a tail
+  long long cap = (long long)sm_count() * (occ5 ? 5 : 6);
   if (cap > 4096) cap = 4096;             // UBPL_RENDER_SUM_WS_BYTES holds 4096 CTA partials
   const int grid = (int)(need < cap ? need : cap);
 #define UBPL_LAUNCH_RENDER(V, SSV)                                                                                     \

@@ -33,9 +33,6 @@
 #ifndef UBPL_K1_EARLY_DEFAULT
 #define UBPL_K1_EARLY_DEFAULT 0
 #endif
-#ifndef UBPL_K1_PF_DEFAULT
-#define UBPL_K1_PF_DEFAULT 0
-#endif
 
 namespace ubpl {
 
@@ -79,9 +76,8 @@ struct WDParams {
   float* out_hm_xy;
   unsigned long long* stats;
   unsigned long long* work;   // global claim counter (zeroed before the launch)
-  int* slow_list;             // [V*B*J] queue of maps left to the exhaustive kernel (NULL: decode in place)
+  int* slow_list;             // [V*B*J] queue of maps left to the exhaustive decode (NULL: decode in place)
   unsigned* slow_count;
-  int pf;                     // 1: the map after next is pulled into L2 with per-line prefetches (two claims ahead)
   K2Fuse k2;                  // optional K2 epilogue run by the warp that decodes the last view of a (sample, joint)
 };
 
@@ -247,14 +243,6 @@ __device__ __forceinline__ void issue_map(const WDParams& p, long long n, float*
                                           uint32_t bytes) {
   mbar_arrive_expect_tx(bar, bytes);
   bulk_g2s(dst, map_src(p, n), bytes, bar, pol);
-}
-
-// Pull a map towards L2 with one prefetch per 128-byte line (LSU path: no registers, no shared memory, and
-// nothing queued on the TMA engine in front of the staged copies).
-__device__ __forceinline__ void prefetch_map_l2(const float* src, uint32_t bytes, int lane) {
-  const char* c = reinterpret_cast<const char*>(src);
-  for (uint32_t o = (uint32_t)lane * 128u; o < bytes; o += 32u * 128u)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -651,42 +639,38 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   const long long N = (long long)p.V * p.B * p.J;
   uint64_t pol = 0;
   // dynamic work distribution: every warp claims the next map index from a global counter, so a
-  // warp that meets an exhaustively decoded map does not delay a fixed share of the work
-  auto claim = [&]() -> long long {
-    unsigned long long n = 0;
-    if (lane == 0) n = atomicAdd(p.work, 1ull);
-    return (long long)__shfl_sync(0xffffffffu, n, 0);
+  // warp that meets an exhaustively decoded map does not delay a fixed share of the work.  The claim is
+  // split in two: the atomic is ISSUED one map ahead (claim_issue) and its result is only read when the
+  // staging buffer is free again (claim_get), so its ~1 us round trip to L2 overlaps the decode instead of
+  // sitting between two maps.
+  unsigned long long claim_reg = 0;                      // lane 0: result of the atomic in flight
+  auto claim_issue = [&]() {
+    if (lane == 0) claim_reg = atomicAdd(p.work, 1ull);
   };
+  auto claim_get = [&]() -> long long { return (long long)__shfl_sync(0xffffffffu, claim_reg, 0); };
   if (p.use_bulk && lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
     pol = l2_evict_first_policy();
   }
   __syncwarp();
-  long long cur = claim(), ahead = N;
+  claim_issue();
+  long long cur = claim_get();
   if (p.use_bulk && lane == 0 && cur < N) issue_map(p, cur, buf0, bar, pol, map_bytes);
-  if (p.pf) {
-    ahead = claim();
-    if (ahead < N) prefetch_map_l2(map_src(p, ahead), map_bytes, lane);
-  }
+  claim_issue();
   // hand the staging buffer to the next map: returns its index (>= N when the work is exhausted)
   auto advance = [&]() -> long long {
-    long long nn;
-    if (p.pf) {
-      nn = ahead;
-      ahead = claim();
-      if (ahead < N) prefetch_map_l2(map_src(p, ahead), map_bytes, lane);
-    } else {
-      nn = claim();
-    }
+    const long long nn = claim_get();
     if (p.use_bulk && lane == 0 && nn < N) issue_map(p, nn, buf0, bar, pol, map_bytes);
+    if (nn < N) claim_issue();
     return nn;
   };
 
   unsigned long long n_slow = 0, n_eval = 0, n_maps = 0, n_miss = 0;
   long long pend_item = -1;                              // K2 ticket of the previous map (see finish_map)
   unsigned pend_old = 0;
-  for (long long it = 0;; ++it) {
+  long long it = 0;                                      // staged copies waited for so far (mbarrier parity)
+  for (;; ++it) {
     const long long n = cur;
     if (n >= N) break;
     const float* s = buf0;
@@ -801,11 +785,13 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       if (exhaustive && p.slow_list) {
         // Maps that need the exhaustive decode are not decoded here: one such map would keep this warp busy
         // for ~25 us while the rest of the grid drains.  They are queued and decoded right after this kernel
-        // by whole CTAs (warp_decode_slow_kernel).
+        // by whole CTAs (warp_decode_slow_kernel).  (Draining the queue inside this launch, by all warps once
+        // the main loop is over, was measured ~4 us slower than the second launch: profiles/README.md.)
         if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = (int)n;
         deferred = true;
         ++n_slow;
-      } else if (exhaustive) {
+      }
+      if (exhaustive && !deferred) {
         decode_exhaustive(s, X.t00, X.t01, X.t02, X.t10, X.t11, X.t12, X.stepx, X.stepy, X.sfx, X.sfy, H, W, X.flip, lane, rv, ri);
         ++n_slow;
         n_eval += HW;
@@ -953,10 +939,8 @@ static int launch_k1(WDParams& p, cudaStream_t stream) {
                (p.sB % 4 == 0) && (p.sJ % 4 == 0);
   // tuning knobs (read per call so that one process can compare them; defaults from B200 measurements):
   //   UBPL_K1_EARLY  1 = release the staging buffer after pass A (window copy), 0 = after the whole map
-  //   UBPL_K1_PF     1 = per-line L2 prefetch of the map after next
   //   UBPL_K1_WARPS  cap on the warps per CTA
   const bool early = p.use_bulk && p.do_warp && (W % 4 == 0) && W >= 4 && env_int("UBPL_K1_EARLY", UBPL_K1_EARLY_DEFAULT) != 0;
-  p.pf = (p.use_bulk && env_int("UBPL_K1_PF", UBPL_K1_PF_DEFAULT) != 0) ? 1 : 0;
   const size_t buf_stride = ((map_bytes + 127) & ~(size_t)127) + (early ? (size_t)kWin * kWin * 4 : 0);
   UBPL_REQUIRE((long long)buf_stride + 64 <= smem_cap, "ubpl_warp_decode: a %dx%d map does not fit in shared memory", H, W);
   int warps = (int)((size_t)smem_cap / (buf_stride + 8));
@@ -1008,10 +992,10 @@ extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64
   return launch_k1(p, (cudaStream_t)stream);
 }
 
-// Workspace of ubpl_warp_decode_k2, int32 words: [0,1] claim counter, [2] queue length, [3] pad,
-// [4, 4+J+2) counts, then the B*J arrival counters, the V*B*J 64-bit hand-off words, and last the queue of
+// Workspace of ubpl_warp_decode_k2, int32 words: [0,1] claim counter, [32] queue length (own 128-byte lines),
+// [128, 128+J+2) counts, then the B*J arrival counters, the V*B*J 64-bit hand-off words, and last the queue of
 // V*B*J map indices.  Everything in front of the queue is cleared by ONE memset node per launch.
-static inline long long k2_ws_arrive_off(int J) { return 4 + ((J + 2 + 1) & ~1); }
+static inline long long k2_ws_arrive_off(int J) { return 128 + ((J + 2 + 1) & ~1); }
 static inline long long k2_ws_slots_off(int B, int J) { return (k2_ws_arrive_off(J) + (long long)B * J + 1) & ~1ll; }
 static inline long long k2_ws_zero_words(int V, int B, int J) { return k2_ws_slots_off(B, J) + 2ll * V * B * J; }
 
@@ -1045,11 +1029,11 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
   p.out_idx = out_idx; p.out_max = out_max; p.out_xy = out_xy; p.out_hm_xy = nullptr;
   p.stats = reinterpret_cast<unsigned long long*>(stats);
   p.work = reinterpret_cast<unsigned long long*>(ws);
-  p.slow_count = reinterpret_cast<unsigned*>(ws + 2);
+  p.slow_count = reinterpret_cast<unsigned*>(ws + 32);
   p.slow_list = ws + zero_words;
   K2Fuse& f = p.k2;
   f.mode = k2_mode; f.K = V;
-  f.counts = ws + 4;
+  f.counts = ws + 128;
   f.arrive = reinterpret_cast<unsigned*>(ws + k2_ws_arrive_off(J));
   f.slots = reinterpret_cast<unsigned long long*>(ws + k2_ws_slots_off(B, J));
   f.distThrMax = distThrMax; f.img_h = img_h; f.img_w = img_w; f.S = S; f.stride = stride; f.sigma = sigma;

@@ -125,7 +125,7 @@ def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stri
               mean.data_ptr(), dist.data_ptr(), legal.data_ptr(), _p(enable), _p(gate), _p(stats), ws.data_ptr(),
               ws_bytes, _stream())
     return dict(idx=out_idx, max=out_max, xy=out_xy, mean=mean, dist=dist, legal=legal, enable=enable, gate=gate,
-                counts=ws[4:4 + J + 1], count=ws[4 + J + 1:4 + J + 2], ws=ws)
+                counts=ws[128:128 + J + 1], count=ws[128 + J + 1:128 + J + 2], ws=ws)
 
 
 def warp_materialize(heatmap, warpmat, isflip):

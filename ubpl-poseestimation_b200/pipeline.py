@@ -195,22 +195,33 @@ class GraphedStep:
         torch.cuda.synchronize()
         pool = None
         self.eager = {}
-        self.overlap_ema = bool(overlap_ema and ema is not None)
+        # overlap_ema: True / "k1" = K4 forked beside K1, "k3" = beside K3, False = after K3
+        self.overlap_ema = ("k3" if overlap_ema == "k3" else "k1") if (overlap_ema and ema is not None) else False
         self._side = torch.cuda.Stream() if self.overlap_ema else None
         self.events = {}
 
-        def k1_fn():
-            if self.overlap_ema:
-                # K4 is independent of the chain: fork it onto a side stream inside the same graph so that it
-                # runs concurrently with K1 (which is not bandwidth-saturated on its own)
-                self._side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(self._side):
-                    self._ema()
-            stage_k1(self.state, stats, cfg)
-            if self.overlap_ema:
-                torch.cuda.current_stream().wait_stream(self._side)
+        def forked(fn):
+            # K4 is independent of the chain: fork it onto a side stream inside the same graph so that it runs
+            # concurrently with the stage (K1 is not bandwidth-saturated on its own)
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                self._ema()
+            fn()
+            torch.cuda.current_stream().wait_stream(self._side)
 
-        stages = [("k1", k1_fn), ("k2", lambda: stage_k2(self.state, cfg, group)), ("k3", lambda: stage_k3(self.state, cfg))]
+        def k1_fn():
+            if self.overlap_ema == "k1":
+                forked(lambda: stage_k1(self.state, stats, cfg))
+            else:
+                stage_k1(self.state, stats, cfg)
+
+        def k3_fn():
+            if self.overlap_ema == "k3":
+                forked(lambda: stage_k3(self.state, cfg))
+            else:
+                stage_k3(self.state, cfg)
+
+        stages = [("k1", k1_fn), ("k2", lambda: stage_k2(self.state, cfg, group)), ("k3", k3_fn)]
         if ema is not None and not self.overlap_ema:
             stages.append(("k4", self._ema))
         from . import dist as _dist
