@@ -177,6 +177,31 @@ int ubpl_select_quantile_dist(const double* dist, const double* legal, int64_t n
                               double reliableThr, double reliableDistMin, double* reliability,
                               uint64_t* keys, uint8_t* enable, float* gate32, int32_t* counts,
                               double* thr_out, void* ws, void* stream);
+/* ---- a13: mixed-distance uncertainty of two teachers (BusinessUtils.pseudo_cal_unc / pseudo_filter_mixUnc(2),
+ * utils/business.py:220-294, 302-346, 378-406) ----------------------------------------------------------------
+ * ubpl_mix_dists, one thread per key point, per teacher m: err_m = dist(pred_m, gt) and the PCK flag acc_m
+ * (gt [B,J,gt_stride] float32 or NULL to skip), score_m = clamp01(scores_m[0][j]) (the reference reads batch row
+ * 0; scores [B,J] float32 or NULL), caug_m [B,J,2] = python-float mean of the A augmented views a_m [B,J,A,2],
+ * int_m = mean pairwise distance of the views; shared ext = dist(pred_1, pred_2), aext = dist(caug_1, caug_2).
+ * All outputs float64 [B,J].  Integer radicands reproduce CPython's pow bit for bit; aext (and err for a
+ * fractional gt) is the IEEE sqrt, <= 1 ulp from CPython. */
+int ubpl_mix_dists(const float* gt, int gt_stride, int ref0, int ref1, double pck_thr,
+                   const float* p1, const float* p2, const float* s1, const float* s2,
+                   const float* a1, const float* a2, int B, int J, int A,
+                   double* err1, double* err2, int32_t* acc1, int32_t* acc2, double* score1, double* score2,
+                   double* caug1, double* caug2, double* int1, double* int2, double* ext, double* aext,
+                   void* stream);
+/* ubpl_mix_unc: the stateful half for ONE teacher.  hist float64 [3][n][3] + hist_len int32 [n] are the device
+ * form of args.mdsN_lma_cache (zero-initialised, updated in place): the call pushes (intDist, extDist,
+ * aExtDist), forms the 0.5/0.3/0.2 moving averages (lma_out [3][n], optional), mixDist (mix_out), unc =
+ * 1-exp(-mixDist/5) or 999 when an average exceeds distThrMax (unc_out), and the fixed rule enable = unc <=
+ * 1-exp(-3*distThrMax/5) with per-joint counts [J+1]; score/score_thr (optional) apply the median-score gate of
+ * pseudo_filter_mixUnc2 first. */
+int ubpl_mix_unc(const double* intDist, const double* extDist, const double* aExtDist, int64_t n, int J,
+                 double distThrMax, double* hist, int32_t* hist_len, const double* score, const double* score_thr,
+                 double* lma_out, double* mix_out, double* unc_out, uint8_t* enable, float* gate32,
+                 int32_t* counts, void* stream);
+
 /* The selector as ONE kernel per GPU (single CTA), single- and multi-GPU:
  *   use_p2p = 0: this GPU's n items are the whole population (k_rank < n; keys = uint64[n] scratch);
  *   use_p2p = 1: every rank stores its distance keys, extrema and item count into its slot of every peer's

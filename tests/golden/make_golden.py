@@ -4,6 +4,7 @@ container only:   python tests/golden/make_golden.py
 The fixtures carry inputs AND the reference's outputs so that tests/test_oracle_golden.py and the
 GPU parity tests can check against the reference where it is not mounted (the GPU box)."""
 import copy
+import json
 import os
 import sys
 import types
@@ -202,8 +203,48 @@ def business_fixture():
     print("business", len(pseudo), "records", sum(cnt[:-1]), "selected")
 
 
+def mixunc_fixture():
+    """a13 (business.py:220-294): four successive calls of pseudo_cal_unc on drifting predictions (the LMA cache
+    carries state), each followed by both filters.  Inputs and the reference's records / filter results."""
+    B, J, A = 5, 6, 4
+    ids = ["im%d" % b for b in range(B)]
+    g = torch.Generator().manual_seed(2024)
+    gt = torch.cat([torch.randint(20, 236, (B, J, 2), generator=g).float() + 0.5 * torch.randint(0, 2, (B, J, 2), generator=g),
+                    torch.ones(B, J, 1)], -1)
+    args = types.SimpleNamespace(pck_ref=[0, 1], pck_thr=0.2, kpsCount=J, distThrMax=2.5, mds1_lma_cache=[], mds2_lma_cache=[])
+    epochs = []
+    for epoch in range(4):
+        inp = {}
+        for m in ("1", "2"):
+            preds = gt[..., :2].round() + torch.randint(-1, 2, (B, J, 2), generator=g).float()
+            aug = preds[:, :, None, :] + torch.randint(-1 - epoch % 2, 2 + epoch % 2, (B, J, A, 2), generator=g).float()
+            aug[0, 0] = preds[0, 0][None]
+            inp["p" + m], inp["a" + m] = preds, aug
+            inp["s" + m] = torch.rand(B, J, generator=g) * 1.2 - 0.1
+            inp["as" + m] = torch.rand(B, J, A, generator=g)
+        r1, r2 = ref.bus.pseudo_cal_unc(ids, gt, inp["p1"], inp["s1"], inp["a1"], inp["as1"], inp["p2"], inp["s2"], inp["a2"],
+                                        inp["as2"], args)
+        ep = {k: v.tolist() for k, v in inp.items()}
+        ep["rec1"], ep["rec2"] = copy.deepcopy(r1), copy.deepcopy(r2)
+        for tag, recs in (("1", r1), ("2", r2)):
+            sel, cnt, errs, accs, thr = ref.bus.pseudo_filter_mixUnc(copy.deepcopy(recs), args)
+            ep["f" + tag] = dict(enable=[it["enable"] for it in sel], counts=cnt, errs=[float(e) for e in errs],
+                                 accs=[float(a) for a in accs], thr=thr)
+            sel, cnt, errs, accs, sthr, thr = ref.bus.pseudo_filter_mixUnc2(copy.deepcopy(recs), args)
+            ep["g" + tag] = dict(enable=[it["enable"] for it in sel], counts=cnt, errs=[float(e) for e in errs],
+                                 accs=[float(a) for a in accs], thr=thr, score_thr=sthr, unc=[it["unc"] for it in sel])
+        epochs.append(ep)
+    out = dict(ids=ids, gt=gt.tolist(), args=dict(pck_ref=[0, 1], pck_thr=0.2, kpsCount=J, distThrMax=2.5), epochs=epochs)
+    json.dump(out, open(os.path.join(HERE, "mixunc.json"), "w"))
+    print("mixunc", len(epochs), "epochs,", sum(e["f1"]["counts"][-1] for e in epochs), "selections")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mixunc":
+        mixunc_fixture()
+        sys.exit(0)
     business_fixture()
+    mixunc_fixture()
     chain_fixture("chain_mt", B=2, K=3, J=3, H=64, W=64, M=1, seed=1388)
     chain_fixture("chain_dual", B=4, K=4, J=5, H=32, W=32, M=2, seed=1389)
     decode_fixture()

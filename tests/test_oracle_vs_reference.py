@@ -176,6 +176,61 @@ def test_assess_and_filter_dual(ref, batch):
         assert cnt[-1] == int(en.sum())
 
 
+def _mix_inputs(batch, epoch):
+    """Inputs of pseudo_cal_unc for one 'epoch': two teachers' predictions, scores, and A = K augmented views per
+    key point in the reference's [B,J,A,2] layout; the views drift with the epoch so the LMA history matters."""
+    g = torch.Generator().manual_seed(100 + epoch)
+    B, J = batch["base_xy"].shape[:2]
+    A = 4
+    gt = torch.cat([batch["base_xy"] * 4 + 1, torch.ones(B, J, 1)], -1)
+    base = (batch["base_xy"] * 4 + 1).round()
+    out = [gt]
+    for m in range(2):
+        preds = base + torch.randint(-1, 2, (B, J, 2), generator=g).float()
+        aug = preds[:, :, None, :] + torch.randint(-1 - epoch % 2, 2 + epoch % 2, (B, J, A, 2), generator=g).float()
+        aug[0, 0] = preds[0, 0][None]                                   # one key point with identical views: intDist 0
+        scores = torch.rand(B, J, generator=g) * 1.2 - 0.1              # some outside [0,1]: _scoreFormat clamps
+        aug_scores = torch.rand(B, J, A, generator=g)
+        out += [preds, scores, aug, aug_scores]
+    return out
+
+
+def test_pseudo_cal_unc_and_mixUnc_filters(ref, batch):
+    """a13: utils/business.py:220-294 over three epochs (the LMA cache carries state between calls)."""
+    B, J = batch["base_xy"].shape[:2]
+    ids = ["im%d" % b for b in range(B)]
+    args = _args(kpsCount=J, distThrMax=2.5, mds1_lma_cache=[], mds2_lma_cache=[])
+    h1, h2 = O.new_lma_history(B * J), O.new_lma_history(B * J)
+    for epoch in range(4):
+        gt, p1, s1, a1, as1, p2, s2, a2, as2 = _mix_inputs(batch, epoch)
+        r1, r2 = ref.bus.pseudo_cal_unc(ids, gt, p1, s1, a1, as1, p2, s2, a2, as2, args)
+        o1, o2 = O.pseudo_cal_unc(gt[..., :2].numpy(), args.pck_ref, args.pck_thr, args.distThrMax, p1.numpy(), s1.numpy(),
+                                  a1.numpy(), as1.numpy(), p2.numpy(), s2.numpy(), a2.numpy(), as2.numpy(), h1, h2)
+        for recs, o in ((r1, o1), (r2, o2)):
+            assert len(recs) == B * J
+            for i, it in enumerate(recs):
+                b, j = divmod(i, J)
+                assert it["kpID"] == "im%d_%d" % (b, j)
+                for k in ("error", "score", "intDist", "extDist", "aExtDist", "intDist_lma", "extDist_lma", "aExtDist_lma",
+                          "mixDist", "unc"):
+                    assert it[k] == o[k][b, j], (epoch, i, k, it[k], o[k][b, j])
+                assert it["acc_flag"] == o["acc_flag"][b, j]
+                assert it["coord_aug"] == o["coord_aug"][b, j].tolist()
+                for k in ("intDistOK", "intDistOK_lma", "extDistOK", "extDistOK_lma", "aExtDistOK", "aExtDistOK_lma"):
+                    assert it[k] == o[k][b, j], (epoch, i, k)
+            sel, cnt, errs, accs, thr = ref.bus.pseudo_filter_mixUnc(copy.deepcopy(recs), args)
+            f = O.pseudo_filter_mixUnc(o["unc"], o["error"], o["acc_flag"], J, args.distThrMax)
+            assert thr == f["uncThr"] and cnt == f["selCounts"] and errs == f["selErrs"] and accs == f["selAccs"]
+            assert [it["enable"] for it in sel] == f["enable"].astype(int).tolist()
+            sel2, cnt2, errs2, accs2, sthr2, thr2 = ref.bus.pseudo_filter_mixUnc2(copy.deepcopy(recs), args)
+            f2 = O.pseudo_filter_mixUnc(o["unc"], o["error"], o["acc_flag"], J, args.distThrMax, score=o["score"])
+            assert sthr2 == f2["scoreThr"] and thr2 == f2["uncThr"] and cnt2 == f2["selCounts"]
+            assert errs2 == f2["selErrs"] and accs2 == f2["selAccs"]
+            assert [it["enable"] for it in sel2] == f2["enable"].astype(int).tolist()
+        if epoch >= 1:
+            assert (o1["unc"] < 999).any() and (o1["unc"] == 999).any()
+
+
 def test_kps_heatmap(ref):
     g = torch.Generator().manual_seed(11)
     kps = torch.rand(40, 3, generator=g) * 270 - 8

@@ -44,6 +44,8 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_select_quantile_dist": [c_void_p, c_void_p, c_i64, c_int, c_i64, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ubpl_mix_dists": [c_void_p, c_int, c_int, c_int, c_double] + [c_void_p] * 6 + [c_int, c_int, c_int] + [c_void_p] * 12 + [c_void_p],
+    "ubpl_mix_unc": [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_double] + [c_void_p] * 10 + [c_void_p],
     "ubpl_select_quantile_fused": [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64, c_double, c_double,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_int, c_int, c_float, c_float, c_int, c_float, c_void_p, c_void_p,

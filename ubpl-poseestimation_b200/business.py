@@ -9,10 +9,14 @@ coord_legal, error, acc_flag, coord_w1, coord_w2, intDist1, intDist2, extDist, r
 enable).  All arithmetic (pairwise dispersions, ensemble weights, errors / PCK flags,
 min-max normalisation, the exact global order statistic and the masks) runs in the float64
 kernels of K2; the host only assembles the python records the API has to return.
-`pseudo_cal_unc` and `pseudo_filter_mixUnc(2)` (the stateful 3-epoch LMA variant, business.py:220-294)
-are not covered yet and stay with the reference.
+`pseudo_cal_unc` / `pseudo_filter_mixUnc(2)` (the stateful 3-epoch LMA variant, business.py:220-294): the
+O(B*J*A^2) pairwise dispersions, the teacher-to-teacher distances and the view means run in ubpl_mix_dists; the
+LMA cache stays in args.mdsN_lma_cache exactly as the reference keeps it (same list of dicts), and the two
+distances whose radicand is not an integer (error against a fractional gt, aExtDist between view means) are
+taken with CPython's own `** 0.5` on the host so that every record field is bit-identical.
 """
 import copy
+import math
 
 import torch
 
@@ -154,3 +158,127 @@ class BusinessUtils:
         for p, r in zip(pseudoArray, rel):
             p["reliability"] = r                                         # the reference mutates its input too (:189)
         return cls._collect(pseudoArray, rel, en, thr, args)
+
+
+    # ---- a13: pseudo_cal_unc / pseudo_filter_mixUnc(2)  (utils/business.py:220-294, 302-406) ------------------
+    @staticmethod
+    def _pydist(c1, c2):
+        return ((c1[0] - c2[0]) ** 2 + (c1[1] - c2[1]) ** 2) ** 0.5      # utils/process.py:53-54, CPython pow
+
+    @staticmethod
+    def _lma_variables(sources):
+        """utils/business.py:395-405."""
+        alphas = [0.5, 0.3, 0.2]
+        if len(sources) == 0:
+            return 999.0
+        if len(sources) == 1:
+            return sources[-1]
+        if len(sources) == 2:
+            return sources[-1] * (alphas[0] + alphas[1]) + sources[-2] * alphas[2]
+        return sources[-1] * alphas[0] + sources[-2] * alphas[1] + sources[-3] * alphas[2]
+
+    @staticmethod
+    def _calUncValue(mixDist):
+        return 1.0 - math.exp(-mixDist / 5)                              # utils/business.py:375-376
+
+    @classmethod
+    def pseudo_cal_unc(cls, imageIDs, preds_gt, preds_mds1, scores_mds1, augPredsArray_mds1, augScoresArray_mds1,
+                       preds_mds2, scores_mds2, augPredsArray_mds2, augScoresArray_mds2, args):
+        """utils/business.py:220-234: per key point and teacher the record of _initKSample (:302-318) completed by
+        _calKSampleExterData (:320-346); args.mds1_lma_cache / args.mds2_lma_cache are appended to like the
+        reference does (kpID-keyed dicts), here through a kpID index instead of a linear search per key point."""
+        a1, a2 = _cuda(augPredsArray_mds1), _cuda(augPredsArray_mds2)
+        B, J = a1.shape[0], a1.shape[1]
+        d = ops.mix_dists(_cuda(preds_mds1), _cuda(scores_mds1), a1, _cuda(preds_mds2), _cuda(scores_mds2), a2)
+        host = {k: v.cpu().tolist() for k, v in d.items() if v is not None}
+        gt = preds_gt.cpu().data.numpy().tolist()
+        norms = [cls._pydist(gt[b][args.pck_ref[0]], gt[b][args.pck_ref[1]]) for b in range(B)]
+        out = []
+        for m, (preds, scores, aug, aug_s) in enumerate(((preds_mds1, scores_mds1, augPredsArray_mds1, augScoresArray_mds1),
+                                                         (preds_mds2, scores_mds2, augPredsArray_mds2, augScoresArray_mds2))):
+            pl = preds.cpu().data.numpy().tolist()
+            al = aug.cpu().data.numpy().tolist()
+            s0 = scores[0].cpu().data.numpy().tolist()                  # batch row 0 for every sample (:310-311)
+            as0 = aug_s[0].cpu().data.numpy().tolist()
+            tag = str(m + 1)
+            recs = []
+            for b in range(B):
+                for j in range(J):
+                    err = cls._pydist(pl[b][j], gt[b][j])
+                    k_scores = [max(0.0, min(1.0, x)) for x in as0[j]] + [max(0.0, min(1.0, s0[j]))]
+                    recs.append({"kpID": "{}_{}".format(imageIDs[b], j), "coord": pl[b][j], "coord_gt": gt[b][j], "error": err,
+                                 "acc_flag": 1 if err / norms[b] < args.pck_thr else 0, "coords_aug": al[b][j],
+                                 "coord_aug": host["caug" + tag][b][j], "scores": k_scores, "score": k_scores[-1],
+                                 "intDist": host["int" + tag][b][j]})
+            out.append(recs)
+        caches = (args.mds1_lma_cache, args.mds2_lma_cache)
+        index = [{it["kpID"]: it for it in c} for c in caches]
+        for i in range(B * J):
+            b, j = divmod(i, J)
+            s1, s2 = out[0][i], out[1][i]
+            s1["extDist"] = s2["extDist"] = host["ext"][b][j]
+            s1["aExtDist"] = s2["aExtDist"] = cls._pydist(s1["coord_aug"], s2["coord_aug"])
+            for smp, cache, idx in ((s1, caches[0], index[0]), (s2, caches[1], index[1])):
+                tgt = idx.get(smp["kpID"])
+                if tgt is None:                                          # getLMAfromCache (:348-355)
+                    tgt = {"kpID": smp["kpID"], "intDist": [], "extDist": [], "aExtDist": [], "intDist_lma": [],
+                           "extDist_lma": [], "aExtDist_lma": []}
+                    cache.append(tgt)
+                    idx[smp["kpID"]] = tgt
+                for q in ("intDist", "extDist", "aExtDist"):
+                    tgt[q].append(smp[q])
+                for q in ("intDist", "extDist", "aExtDist"):
+                    smp[q + "_lma"] = cls._lma_variables(tgt[q])
+                    tgt[q + "_lma"].append(smp[q + "_lma"])
+                smp["mixDist"] = smp["intDist_lma"] + ((smp["extDist_lma"] + smp["aExtDist_lma"]) / 2
+                                                       if smp["extDist_lma"] > 0 else smp["aExtDist_lma"])
+            for smp in (s1, s2):
+                for q in ("intDist", "extDist", "aExtDist"):
+                    smp[q + "OK"] = 1 if smp[q] <= args.distThrMax else 0
+                    smp[q + "OK_lma"] = 1 if smp[q + "_lma"] <= args.distThrMax else 0
+                ok = smp["intDistOK_lma"] > 0 and smp["extDistOK_lma"] > 0 and smp["aExtDistOK_lma"] > 0
+                smp["unc"] = cls._calUncValue(smp["mixDist"]) if ok else 999.0
+        return out[0], out[1]
+
+    @classmethod
+    def _mix_collect(cls, pseudoArray, uncThr, args):
+        """The selection loop of pseudo_filter_mixUnc / pseudo_filter_mixUnc2 (business.py:243-261, 271-293)."""
+        n = args.kpsCount + 1
+        selArray, selCounts, selErrs, selAccs = [], [0] * n, [0] * n, [0] * n
+        for pseudoItem in pseudoArray:
+            item = copy.deepcopy(pseudoItem)
+            if item["unc"] <= uncThr:
+                kID = int(item["kpID"].split("_")[-1])
+                item["enable"] = 1
+                selCounts[-1] += 1
+                selCounts[kID] += 1
+                selErrs[-1] += item["error"]
+                selErrs[kID] += item["error"]
+                selAccs[-1] += item["acc_flag"]
+                selAccs[kID] += item["acc_flag"]
+            else:
+                item["enable"] = 0
+            selArray.append(item)
+        for idx in range(n):
+            if selCounts[idx] > 0:
+                selErrs[idx] = selErrs[idx] / selCounts[idx]
+                selAccs[idx] = selAccs[idx] / selCounts[idx]
+        return selArray, selCounts, selErrs, selAccs
+
+    @classmethod
+    def pseudo_filter_mixUnc(cls, pseudoArray, args):
+        """utils/business.py:237-261: enable = unc <= 1-exp(-3*distThrMax/5)."""
+        uncThr = cls._calUncValue(args.distThrMax * 3)
+        return cls._mix_collect(pseudoArray, uncThr, args) + (uncThr,)
+
+    @classmethod
+    def pseudo_filter_mixUnc2(cls, pseudoArray, args):
+        """utils/business.py:264-294: items scoring below the median score (:357-364) get unc = 999 first; the
+        reference mutates its input records (scoreOK, unc), so does this."""
+        scores_sorted = sorted([item["score"] for item in pseudoArray], reverse=True)
+        scoreThr = scores_sorted[int((len(scores_sorted) - 1) * 0.5)]
+        for pseudoItem in pseudoArray:
+            pseudoItem["scoreOK"] = 0 if pseudoItem["score"] < scoreThr else 1
+            pseudoItem["unc"] = 999.0 if pseudoItem["score"] < scoreThr else pseudoItem["unc"]
+        uncThr = cls._calUncValue(args.distThrMax * 3)
+        return cls._mix_collect(pseudoArray, uncThr, args) + (scoreThr, uncThr)

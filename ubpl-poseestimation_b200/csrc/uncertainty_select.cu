@@ -484,6 +484,101 @@ __global__ void pair_distance_kernel(const double* __restrict__ c1, const double
   if (i < n) out[i] = py_dist(c1[2 * i], c1[2 * i + 1], c2[2 * i], c2[2 * i + 1], T);
 }
 
+// ---------------------------------------------------------------------------------------------
+// a13: the mixed-distance uncertainty of two teachers (utils/business.py:220-234, 302-346, 378-406)
+// ---------------------------------------------------------------------------------------------
+// One thread per key point.  Per teacher m: error = dist(pred_m, gt), PCK flag against the per-sample norm
+// dist(gt[ref0], gt[ref1]) (evaluation.py:78-89), score = clamp01(scores_m[0][j]) (the reference reads batch
+// row 0, business.py:310-311), coord_aug = python-float mean of the A augmented views, intDist = mean pairwise
+// distance of the views in itertools.combinations order (process.py:57-68).  Shared: extDist = dist(pred_1,
+// pred_2), aExtDist = dist(coord_aug_1, coord_aug_2).  Distances with integer radicands reproduce CPython's
+// libm pow bit for bit (PowTab); coord_aug means are not integers, so aExtDist (and error when gt is
+// fractional) is the IEEE sqrt, at most one ulp from CPython -- the drop-in recomputes those two on the host.
+__global__ void mix_dists_kernel(const float* __restrict__ gt, int gt_stride, int ref0, int ref1, double pck_thr,
+                                 const float* __restrict__ p1, const float* __restrict__ p2,
+                                 const float* __restrict__ s1, const float* __restrict__ s2,
+                                 const float* __restrict__ a1, const float* __restrict__ a2, int B, int J, int A,
+                                 double* err1, double* err2, int32_t* acc1, int32_t* acc2, double* score1,
+                                 double* score2, double* caug1, double* caug2, double* int1, double* int2,
+                                 double* ext, double* aext, PowTab T) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)B * J;
+  if (i >= n) return;
+  const int b = (int)(i / J), j = (int)(i % J);
+  double norm = 1.0;
+  if (gt) {
+    const float* g0 = gt + ((long long)b * J + ref0) * gt_stride;
+    const float* g1 = gt + ((long long)b * J + ref1) * gt_stride;
+    norm = py_dist((double)g0[0], (double)g0[1], (double)g1[0], (double)g1[1], T);
+  }
+  double cx[2], cy[2];
+  for (int m = 0; m < 2; ++m) {
+    const float* p = m ? p2 : p1;
+    const float* a = (m ? a2 : a1) + i * A * 2;
+    const float* sc = m ? s2 : s1;
+    if (gt) {
+      const float* g = gt + i * gt_stride;
+      const double e = py_dist((double)p[2 * i], (double)p[2 * i + 1], (double)g[0], (double)g[1], T);
+      (m ? err2 : err1)[i] = e;
+      (m ? acc2 : acc1)[i] = (__ddiv_rn(e, norm) < pck_thr) ? 1 : 0;
+    }
+    if (sc) { const double v = (double)sc[j]; (m ? score2 : score1)[i] = fmax(0.0, fmin(1.0, v)); }
+    double sx = 0.0, sy = 0.0;
+    for (int k = 0; k < A; ++k) { sx = __dadd_rn(sx, (double)a[2 * k]); sy = __dadd_rn(sy, (double)a[2 * k + 1]); }
+    cx[m] = __ddiv_rn(sx, (double)A); cy[m] = __ddiv_rn(sy, (double)A);
+    (m ? caug2 : caug1)[2 * i] = cx[m]; (m ? caug2 : caug1)[2 * i + 1] = cy[m];
+    double s = 0.0;
+    int cnt = 0;
+    for (int u = 0; u < A; ++u)
+      for (int v = u + 1; v < A; ++v) {
+        s = __dadd_rn(s, py_dist((double)a[2 * u], (double)a[2 * u + 1], (double)a[2 * v], (double)a[2 * v + 1], T));
+        ++cnt;
+      }
+    (m ? int2 : int1)[i] = __ddiv_rn(s, (double)cnt);        // A < 2: 0/0 = NaN (the reference raises ZeroDivisionError)
+  }
+  ext[i] = py_dist((double)p1[2 * i], (double)p1[2 * i + 1], (double)p2[2 * i], (double)p2[2 * i + 1], T);
+  aext[i] = py_dist(cx[0], cy[0], cx[1], cy[1], T);
+}
+
+// The stateful half: push (intDist, extDist, aExtDist) into this key point's 3-deep history, take the 0.5/0.3/0.2
+// moving averages (business.py:395-405), mixDist (:327), the three <= distThrMax tests on the averages and
+// unc = 1-exp(-mixDist/5) or 999 (:343); then the fixed rule of pseudo_filter_mixUnc (:237-261): enable =
+// unc <= 1-exp(-3*distThrMax/5), with the score gate of pseudo_filter_mixUnc2 (:264-268) when score != NULL
+// (unc = 999 where score < *score_thr).  hist [3][n][3] float64 (newest last), hist_len [n] int32.
+__global__ void mix_unc_kernel(const double* __restrict__ intd, const double* __restrict__ extd,
+                               const double* __restrict__ aextd, long long n, int J, double distThrMax, double* hist,
+                               int32_t* hist_len, const double* __restrict__ score, const double* __restrict__ score_thr,
+                               double* lma_out, double* mix_out, double* unc_out, uint8_t* enable, float* gate32,
+                               int32_t* counts) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double cur[3] = {intd[i], extd[i], aextd[i]};
+  const int len = hist_len[i];
+  double l[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    double* h = hist + ((long long)q * n + i) * 3;          // h[2] newest
+    const double h1 = h[2], h2 = h[1];                      // previous newest, the one before
+    h[0] = h2; h[1] = h1; h[2] = cur[q];
+    if (len == 0) l[q] = cur[q];
+    else if (len == 1) l[q] = __dadd_rn(__dmul_rn(cur[q], 0.5 + 0.3), __dmul_rn(h1, 0.2));
+    else l[q] = __dadd_rn(__dadd_rn(__dmul_rn(cur[q], 0.5), __dmul_rn(h1, 0.3)), __dmul_rn(h2, 0.2));
+    if (lma_out) lma_out[(long long)q * n + i] = l[q];
+  }
+  hist_len[i] = len < 2 ? len + 1 : 2;
+  const double mix = __dadd_rn(l[0], (l[1] > 0.0) ? __ddiv_rn(__dadd_rn(l[1], l[2]), 2.0) : l[2]);
+  const bool ok = (l[0] <= distThrMax) && (l[1] <= distThrMax) && (l[2] <= distThrMax);
+  double unc = ok ? __dsub_rn(1.0, exp(-__ddiv_rn(mix, 5.0))) : 999.0;
+  if (score && score[i] < *score_thr) unc = 999.0;
+  if (mix_out) mix_out[i] = mix;
+  if (unc_out) unc_out[i] = unc;
+  const double thr = __dsub_rn(1.0, exp(-__ddiv_rn(__dmul_rn(distThrMax, 3.0), 5.0)));
+  const bool en = unc <= thr;
+  if (enable) enable[i] = en ? 1 : 0;
+  if (gate32) gate32[i] = en ? 1.f : 0.f;
+  if (en && counts) { atomicAdd(counts + (int)(i % J), 1); atomicAdd(counts + J, 1); }
+}
+
 static inline int blocks_for(long long n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace ubpl
@@ -645,6 +740,42 @@ extern "C" int ubpl_pair_distance(const double* c1, const double* c2, int64_t n,
   GET_POWTAB(T);
   pair_distance_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(c1, c2, n, out, T);
   return check_launch("ubpl_pair_distance");
+}
+
+extern "C" int ubpl_mix_dists(const float* gt, int gt_stride, int ref0, int ref1, double pck_thr, const float* p1,
+                              const float* p2, const float* s1, const float* s2, const float* a1, const float* a2,
+                              int B, int J, int A, double* err1, double* err2, int32_t* acc1, int32_t* acc2,
+                              double* score1, double* score2, double* caug1, double* caug2, double* int1, double* int2,
+                              double* ext, double* aext, void* stream) {
+  UBPL_REQUIRE(p1 && p2 && a1 && a2 && caug1 && caug2 && int1 && int2 && ext && aext, "ubpl_mix_dists: NULL pointer");
+  UBPL_REQUIRE(B >= 0 && J >= 1 && A >= 1, "ubpl_mix_dists: bad dims");
+  UBPL_REQUIRE(!gt || (gt_stride >= 2 && err1 && err2 && acc1 && acc2 && ref0 >= 0 && ref0 < J && ref1 >= 0 && ref1 < J),
+               "ubpl_mix_dists: gt needs err/acc outputs and valid pck_ref");
+  UBPL_REQUIRE((!s1 || score1) && (!s2 || score2), "ubpl_mix_dists: scores need score outputs");
+  const long long n = (long long)B * J;
+  if (n == 0) return UBPL_OK;
+  GET_POWTAB(T);
+  mix_dists_kernel<<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(gt, gt_stride, ref0, ref1, pck_thr, p1, p2, s1, s2, a1,
+                                                                         a2, B, J, A, err1, err2, acc1, acc2, score1, score2,
+                                                                         caug1, caug2, int1, int2, ext, aext, T);
+  return check_launch("ubpl_mix_dists");
+}
+
+extern "C" int ubpl_mix_unc(const double* intDist, const double* extDist, const double* aExtDist, int64_t n, int J,
+                            double distThrMax, double* hist, int32_t* hist_len, const double* score,
+                            const double* score_thr, double* lma_out, double* mix_out, double* unc_out, uint8_t* enable,
+                            float* gate32, int32_t* counts, void* stream) {
+  UBPL_REQUIRE(intDist && extDist && aExtDist && hist && hist_len && n >= 0 && J >= 1, "ubpl_mix_unc: bad arguments");
+  UBPL_REQUIRE(!score || score_thr, "ubpl_mix_unc: score needs score_thr");
+  if (counts) {
+    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)(J + 1) * sizeof(int32_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("ubpl_mix_unc: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+  }
+  if (n == 0) return UBPL_OK;
+  mix_unc_kernel<<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(intDist, extDist, aExtDist, n, J, distThrMax, hist, hist_len,
+                                                                       score, score_thr, lma_out, mix_out, unc_out, enable,
+                                                                       gate32, counts);
+  return check_launch("ubpl_mix_unc");
 }
 
 #include "nccl_select.inc"

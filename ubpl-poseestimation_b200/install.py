@@ -8,7 +8,8 @@ attributes of the reference's own modules:
     utils.process.ProcessUtils.{kps_fromHeatmap, kps_fromHeatmap_mul, kps_fromHeatmap2, kps_heatmap,
                                 kps_heatmap_mulKps, kps_getLabeledCount}
     utils.evaluation.EvaluationUtils.uncertainty_fromDistance
-    utils.business.BusinessUtils.{assess_pseudo_unc, assess_pseudo_unc2, filter_pseudo, filter_pseudo2}
+    utils.business.BusinessUtils.{assess_pseudo_unc, assess_pseudo_unc2, filter_pseudo, filter_pseudo2,
+                                  pseudo_cal_unc, pseudo_filter_mixUnc, pseudo_filter_mixUnc2, preds_mean}
     utils.parameters.update_ema_variables   (and utils.udaap.utils_mt.update_ema_variables)
 """
 import importlib
@@ -24,7 +25,9 @@ CLASS_PATCHES = {
     ("utils.process", "ProcessUtils"): (process.ProcessUtils, ("kps_fromHeatmap", "kps_fromHeatmap_mul", "kps_fromHeatmap2",
                                                                "kps_heatmap", "kps_heatmap_mulKps", "kps_getLabeledCount")),
     ("utils.evaluation", "EvaluationUtils"): (evaluation.EvaluationUtils, ("uncertainty_fromDistance",)),
-    ("utils.business", "BusinessUtils"): (business.BusinessUtils, ("assess_pseudo_unc", "assess_pseudo_unc2", "filter_pseudo", "filter_pseudo2")),
+    ("utils.business", "BusinessUtils"): (business.BusinessUtils, ("assess_pseudo_unc", "assess_pseudo_unc2", "filter_pseudo", "filter_pseudo2",
+                                                                    "pseudo_cal_unc", "pseudo_filter_mixUnc", "pseudo_filter_mixUnc2",
+                                                                    "preds_mean")),
 }
 
 
@@ -39,7 +42,7 @@ def install():
     for (mod_name, cls_name), (src, names) in CLASS_PATCHES.items():
         cls = getattr(importlib.import_module(mod_name), cls_name)
         for n in names:
-            setattr(cls, n, getattr(src, n))          # classmethod objects rebind to the reference class
+            setattr(cls, n, getattr(src, n))          # bound to THIS package's class: its helpers stay reachable
             done.append("%s.%s.%s" % (mod_name, cls_name, n))
     try:
         um = importlib.import_module("utils.udaap.utils_mt")

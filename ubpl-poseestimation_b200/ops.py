@@ -399,6 +399,67 @@ def select_quantile_nccl(dist, legal, J, k_rank, reliableThr, reliableDistMin):
     return dict(reliability=rel, enable=enable, gate=gate, counts=counts, thr=thr, ext=ws[:4].view(_f64))
 
 
+def mix_dists(p1, s1, a1, p2, s2, a2, gt=None, pck_ref=(0, 1), pck_thr=0.2):
+    """The per-key-point quantities of BusinessUtils.pseudo_cal_unc (utils/business.py:220-234,302-326) for two
+    teachers: p [B,J,2], s [B,J] (or None), a [B,J,A,2] (the A augmented views of every key point), gt [B,J,>=2].
+    Returns float64 [B,J] tensors err1/2, score1/2, int1/2, ext, aext, caug1/2 [B,J,2] and int32 acc1/2."""
+    _need_cuda(p1, p2, a1, a2, s1, s2, gt)
+    p1, p2 = p1.to(_f32).contiguous(), p2.to(_f32).contiguous()
+    a1, a2 = a1.to(_f32).contiguous(), a2.to(_f32).contiguous()
+    B, J, A, _ = a1.shape
+    dev = a1.device
+    s1 = None if s1 is None else s1.to(_f32).contiguous()
+    s2 = None if s2 is None else s2.to(_f32).contiguous()
+    gt = None if gt is None else gt.to(_f32).contiguous()
+    o = {k: torch.empty(B, J, dtype=_f64, device=dev) for k in ("int1", "int2", "ext", "aext")}
+    o["caug1"] = torch.empty(B, J, 2, dtype=_f64, device=dev)
+    o["caug2"] = torch.empty(B, J, 2, dtype=_f64, device=dev)
+    for m in ("1", "2"):
+        o["err" + m] = torch.empty(B, J, dtype=_f64, device=dev) if gt is not None else None
+        o["acc" + m] = torch.empty(B, J, dtype=torch.int32, device=dev) if gt is not None else None
+        o["score" + m] = torch.empty(B, J, dtype=_f64, device=dev) if (s1 if m == "1" else s2) is not None else None
+    _lib.call("ubpl_mix_dists", _p(gt), gt.shape[-1] if gt is not None else 0, int(pck_ref[0]), int(pck_ref[1]), float(pck_thr),
+              p1.data_ptr(), p2.data_ptr(), _p(s1), _p(s2), a1.data_ptr(), a2.data_ptr(), B, J, A,
+              _p(o["err1"]), _p(o["err2"]), _p(o["acc1"]), _p(o["acc2"]), _p(o["score1"]), _p(o["score2"]),
+              o["caug1"].data_ptr(), o["caug2"].data_ptr(), o["int1"].data_ptr(), o["int2"].data_ptr(),
+              o["ext"].data_ptr(), o["aext"].data_ptr(), _stream())
+    return o
+
+
+class MixUncState:
+    """Device form of args.mdsN_lma_cache (utils/business.py:348-355,378-393) for n key points of ONE teacher:
+    the last three (intDist, extDist, aExtDist) of every key point, updated in place by mix_unc."""
+
+    def __init__(self, n, device):
+        self.n = int(n)
+        self.hist = torch.zeros(3, self.n, 3, dtype=_f64, device=device)
+        self.len = torch.zeros(self.n, dtype=torch.int32, device=device)
+
+
+def mix_unc(intDist, extDist, aExtDist, J, distThrMax, state, score=None, score_thr=None):
+    """LMA (0.5/0.3/0.2) of the three distances -> mixDist -> unc (utils/business.py:320-346,395-405) and the
+    fixed rule of pseudo_filter_mixUnc (:237-261); score/score_thr add the gate of pseudo_filter_mixUnc2."""
+    _need_cuda(intDist, extDist, aExtDist, score, score_thr)
+    i, e, a = (t.reshape(-1).to(_f64).contiguous() for t in (intDist, extDist, aExtDist))
+    n = i.numel()
+    if n != state.n:
+        raise ValueError("state holds %d key points, got %d" % (state.n, n))
+    dev = i.device
+    score = None if score is None else score.reshape(-1).to(_f64).contiguous()
+    score_thr = None if score_thr is None else score_thr.reshape(-1).to(_f64).contiguous()
+    lma = torch.empty(3, n, dtype=_f64, device=dev)
+    mix = torch.empty(n, dtype=_f64, device=dev)
+    unc = torch.empty(n, dtype=_f64, device=dev)
+    enable = torch.empty(n, dtype=torch.uint8, device=dev)
+    gate = torch.empty(n, dtype=_f32, device=dev)
+    counts = torch.empty(J + 1, dtype=torch.int32, device=dev)
+    _lib.call("ubpl_mix_unc", i.data_ptr(), e.data_ptr(), a.data_ptr(), n, int(J), float(distThrMax), state.hist.data_ptr(),
+              state.len.data_ptr(), _p(score), _p(score_thr), lma.data_ptr(), mix.data_ptr(), unc.data_ptr(),
+              enable.data_ptr(), gate.data_ptr(), counts.data_ptr(), _stream())
+    return dict(intDist_lma=lma[0], extDist_lma=lma[1], aExtDist_lma=lma[2], mixDist=mix, unc=unc, enable=enable, gate=gate,
+                counts=counts)
+
+
 def select_fixed(dist, legal, J, distThrMax):
     """enable = legal and 1-exp(-dist/5) <= 1-exp(-3*distThrMax/5)  (utils/business.py:237-261)."""
     _need_cuda(dist, legal)
