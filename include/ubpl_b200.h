@@ -322,6 +322,19 @@ int ubpl_gate_prepare(const float* kps, const float* gate_in, int64_t n, int img
  * wrappers; both 16-byte aligned. */
 int ubpl_scale(float* dst, const float* src, int64_t n, const float* scale, void* stream);
 
+/* ---- N2 / N3: PCK evaluation and the feature-decorrelation loss ---------------------------
+ * ubpl_acc_pck: EvaluationUtils.acc_pck (utils/evaluation.py:92-139) on device.  preds [bs,k,p_stride>=2],
+ * gts [bs,k,g_stride>=2] float32; errs/accs float32 [k+1] (per joint, then the mean over joints; accs[k] = -1
+ * for a joint without a visible gt, which the mean skips); dists / dists_ref [k,bs] optional. */
+int ubpl_acc_pck(const float* preds, int p_stride, const float* gts, int g_stride, int bs, int k,
+                 int ref0, int ref1, float pck_thr, float* errs, float* accs, float* dists, float* dists_ref,
+                 void* stream);
+/* ubpl_features_cov: ProcessUtils.features_cov (utils/process.py:19-31) forward + gradient in one pass.
+ * f1, f2 [rows, L] float32 contiguous (rows = bs*n*c, L = h*w); cov [rows] = off-diagonal covariance of the two
+ * rows; *value = mean |cov|; g1, g2 [rows, L] (both or neither) = d value / d f1, d f2. */
+int ubpl_features_cov(const float* f1, const float* f2, int64_t rows, int L, float* cov, float* value,
+                      float* g1, float* g2, void* stream);
+
 /* ---- K4: mean-teacher EMA, all parameter tensors in one launch ---------------------------------
  * update_ema_variables (utils/parameters.py:4-8): ema = ema*alpha + (1-alpha)*param, float32,
  * evaluated as fma(param, 1-alpha, ema*alpha) like ATen.  ema_ptrs/param_ptrs: device arrays of

@@ -275,3 +275,38 @@ def test_business_mixunc(pkg):
     u0 = ops.mix_unc(d["int1"], d["ext"], d["aext"], J, a["distThrMax"], stp)
     gated = (sc.reshape(-1) < thr_t)
     assert torch.all(u1["unc"][gated] == 999.0) and torch.equal(u1["unc"][~gated], u0["unc"][~gated])
+
+
+def test_acc_pck(pkg):
+    """N2 (utils/evaluation.py:92-139) against the oracle; float32, 1e-6 relative (summation order)."""
+    from ubpl_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for (B, J) in ((9, 7), (64, 14), (1, 3)):
+        gts = torch.cat([torch.rand(B, J, 2, generator=g) * 250, torch.ones(B, J, 1)], -1)
+        gts[0, 2, 0] = 0.5
+        gts[:, J - 2, 0] = 0.0                                           # a joint that is never visible: accs = -1
+        preds = gts[..., :2] + torch.randn(B, J, 2, generator=g) * 12
+        for thr in (0.2, 0.5):
+            want_e, want_a = O.acc_pck(preds.numpy(), gts.numpy(), [0, 1], thr)
+            errs, accs = pkg.eval.acc_pck(preds, gts, [0, 1], thr)
+            assert errs.device.type == "cpu" and errs.dtype == torch.float32 and errs.shape == (J + 1,)
+            np.testing.assert_allclose(errs.numpy(), want_e, rtol=1e-6)
+            np.testing.assert_allclose(accs.numpy(), want_a, rtol=1e-6)
+            assert accs[J - 2] == -1
+            e2, a2, d, dr = ops.acc_pck(preds.cuda(), gts.cuda(), [0, 1], thr, want_dists=True)
+            assert d.shape == (J, B) and torch.all(d[J - 2] == -1)
+
+
+def test_features_cov(pkg):
+    """N3 (utils/process.py:19-31): value and both gradients against the oracle, 1e-5 relative."""
+    g = torch.Generator().manual_seed(9)
+    for shape in ((3, 2, 8, 32, 32), (2, 1, 5, 7, 9), (4, 2, 16, 16, 16), (2, 2, 6, 16, 32)):
+        a = torch.randn(*shape, generator=g).cuda().requires_grad_(True)
+        b = (0.3 * a.detach().cpu() + torch.randn(*shape, generator=g)).cuda().requires_grad_(True)
+        val, cnt = pkg.proc.features_cov(a, b)
+        (val * 1.7).backward()
+        v, rows, g1, g2 = O.features_cov(a.detach().cpu().numpy(), b.detach().cpu().numpy(), upstream=1.7)
+        assert cnt == rows and val.dim() == 0
+        np.testing.assert_allclose(val.item(), v, rtol=1e-5)
+        np.testing.assert_allclose(a.grad.cpu().numpy(), g1, rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(b.grad.cpu().numpy(), g2, rtol=1e-4, atol=1e-9)

@@ -231,6 +231,39 @@ def test_pseudo_cal_unc_and_mixUnc_filters(ref, batch):
             assert (o1["unc"] < 999).any() and (o1["unc"] == 999).any()
 
 
+def test_acc_pck(ref, batch):
+    """N2: utils/evaluation.py:92-139 (float32 tensors; sums within 1e-6 relative, the summation order of
+    torch.sum differs from a sequential one)."""
+    g = torch.Generator().manual_seed(5)
+    B, J = 9, 7
+    gts = torch.cat([torch.rand(B, J, 2, generator=g) * 250, torch.ones(B, J, 1)], -1)
+    gts[0, 2, 0] = 0.5                      # invisible key points: gt <= 1
+    gts[3, 2, 1] = 1.0
+    gts[:, 5, 0] = 0.0                      # a joint that is never valid: accs = -1
+    preds = gts[..., :2] + torch.randn(B, J, 2, generator=g) * 12
+    for thr in (0.2, 0.5):
+        want_e, want_a = ref.eval.acc_pck(preds, gts, [0, 1], thr)
+        got_e, got_a = O.acc_pck(preds.numpy(), gts.numpy(), [0, 1], thr)
+        np.testing.assert_allclose(got_e, want_e.numpy(), rtol=1e-6)
+        np.testing.assert_allclose(got_a, want_a.numpy(), rtol=1e-6)
+        assert want_a[5] == -1 and got_a[5] == -1
+
+
+def test_features_cov(ref):
+    """N3: utils/process.py:19-31 and its autograd gradient, 1e-5 relative (float32 matmul / mean orders differ)."""
+    g = torch.Generator().manual_seed(9)
+    for shape in ((3, 2, 8, 16, 16), (2, 1, 5, 7, 9)):
+        a = torch.randn(*shape, generator=g).requires_grad_(True)
+        b = (0.3 * a.detach() + torch.randn(*shape, generator=g)).requires_grad_(True)
+        val, cnt = ref.proc.features_cov(a, b)
+        (val * 1.7).backward()
+        v, rows, g1, g2 = O.features_cov(a.detach().numpy(), b.detach().numpy(), upstream=1.7)
+        assert rows == cnt
+        np.testing.assert_allclose(v, val.item(), rtol=1e-5)
+        np.testing.assert_allclose(g1, a.grad.numpy(), rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(g2, b.grad.numpy(), rtol=1e-4, atol=1e-9)
+
+
 def test_kps_heatmap(ref):
     g = torch.Generator().manual_seed(11)
     kps = torch.rand(40, 3, generator=g) * 270 - 8

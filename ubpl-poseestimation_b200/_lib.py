@@ -76,6 +76,8 @@ SIGNATURES = {
     "ubpl_loss_finalize": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "ubpl_gate_prepare": [c_void_p, c_void_p, c_i64, c_int, c_int, c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_scale": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p],
+    "ubpl_acc_pck": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ubpl_features_cov": [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_ema_multi_tensor": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_float, c_void_p],
     "ubpl_ema_flat": [c_void_p, c_void_p, c_i64, c_float, c_float, c_void_p],
 }
@@ -119,7 +121,7 @@ def lib():
 
 
 # kernels launched per successful call (cudaMemsetAsync is not counted); bench.py's gpu_launches
-LAUNCHES = {"ubpl_dist_extrema": 2, "ubpl_warp_decode": 2, "ubpl_warp_decode_k2": 2, "ubpl_select_quantile_dist": 16, "ubpl_nccl_unique_id": 0,
+LAUNCHES = {"ubpl_dist_extrema": 2, "ubpl_features_cov": 2, "ubpl_warp_decode": 2, "ubpl_warp_decode_k2": 2, "ubpl_select_quantile_dist": 16, "ubpl_nccl_unique_id": 0,
             "ubpl_nccl_init": 0, "ubpl_nccl_destroy": 0, "ubpl_p2p_alloc": 0, "ubpl_p2p_open": 0, "ubpl_p2p_close": 0}
 _launches = 0
 

@@ -6,8 +6,8 @@ attributes of the reference's own modules:
     utils.losses.{JointMSELoss, JointDistLoss, JointPseudoLoss3, JointDistLoss_mt2}
     utils.augment.AugmentUtils.{affine_back2, affine_back2_classification, fliplr_back_tensor}
     utils.process.ProcessUtils.{kps_fromHeatmap, kps_fromHeatmap_mul, kps_fromHeatmap2, kps_heatmap,
-                                kps_heatmap_mulKps, kps_getLabeledCount}
-    utils.evaluation.EvaluationUtils.uncertainty_fromDistance
+                                kps_heatmap_mulKps, kps_getLabeledCount, features_cov}
+    utils.evaluation.EvaluationUtils.{uncertainty_fromDistance, acc_pck}
     utils.business.BusinessUtils.{assess_pseudo_unc, assess_pseudo_unc2, filter_pseudo, filter_pseudo2,
                                   pseudo_cal_unc, pseudo_filter_mixUnc, pseudo_filter_mixUnc2, preds_mean}
     utils.parameters.update_ema_variables   (and utils.udaap.utils_mt.update_ema_variables)
@@ -23,8 +23,9 @@ PATCHES = {
 CLASS_PATCHES = {
     ("utils.augment", "AugmentUtils"): (augment.AugmentUtils, ("affine_back2", "affine_back2_classification", "fliplr_back_tensor")),
     ("utils.process", "ProcessUtils"): (process.ProcessUtils, ("kps_fromHeatmap", "kps_fromHeatmap_mul", "kps_fromHeatmap2",
-                                                               "kps_heatmap", "kps_heatmap_mulKps", "kps_getLabeledCount")),
-    ("utils.evaluation", "EvaluationUtils"): (evaluation.EvaluationUtils, ("uncertainty_fromDistance",)),
+                                                               "kps_heatmap", "kps_heatmap_mulKps", "kps_getLabeledCount",
+                                                               "features_cov")),
+    ("utils.evaluation", "EvaluationUtils"): (evaluation.EvaluationUtils, ("uncertainty_fromDistance", "acc_pck")),
     ("utils.business", "BusinessUtils"): (business.BusinessUtils, ("assess_pseudo_unc", "assess_pseudo_unc2", "filter_pseudo", "filter_pseudo2",
                                                                     "pseudo_cal_unc", "pseudo_filter_mixUnc", "pseudo_filter_mixUnc2",
                                                                     "preds_mean")),

@@ -629,6 +629,43 @@ def scale_inplace(x, s):
 
 
 # -------------------------------------------------------------------------------------------------
+# N2 / N3
+# -------------------------------------------------------------------------------------------------
+def acc_pck(preds, gts, pck_ref, pck_thr, want_dists=False):
+    """EvaluationUtils.acc_pck (utils/evaluation.py:92-139): preds [bs,k,>=2], gts [bs,k,>=2] ->
+    (errs [k+1], accs [k+1]) float32 on the device (+ dists, dists_ref [k,bs] when asked)."""
+    _need_cuda(preds, gts)
+    preds = preds.to(_f32).contiguous()
+    gts = gts.to(_f32).contiguous()
+    bs, k = preds.shape[:2]
+    dev = preds.device
+    errs = torch.empty(k + 1, dtype=_f32, device=dev)
+    accs = torch.empty(k + 1, dtype=_f32, device=dev)
+    dists = torch.empty(k, bs, dtype=_f32, device=dev) if want_dists else None
+    dref = torch.empty(k, bs, dtype=_f32, device=dev) if want_dists else None
+    _lib.call("ubpl_acc_pck", preds.data_ptr(), preds.shape[-1], gts.data_ptr(), gts.shape[-1], bs, k, int(pck_ref[0]),
+              int(pck_ref[1]), float(pck_thr), errs.data_ptr(), accs.data_ptr(), _p(dists), _p(dref), _stream())
+    return (errs, accs, dists, dref) if want_dists else (errs, accs)
+
+
+def features_cov(inp1, inp2, want_grad=True):
+    """ProcessUtils.features_cov (utils/process.py:19-31) forward + gradient: inp [bs,n,c,h,w] ->
+    dict(value 0-d float32, rows, cov [bs,n,c], grad1, grad2)."""
+    _need_cuda(inp1, inp2)
+    a = inp1.to(_f32).contiguous()
+    b = inp2.to(_f32).contiguous()
+    bs, n, c, h, w = a.shape
+    rows, L = bs * n * c, h * w
+    dev = a.device
+    cov = torch.empty(bs, n, c, dtype=_f32, device=dev)
+    value = torch.empty(1, dtype=_f32, device=dev)
+    g1 = torch.empty_like(a) if want_grad else None
+    g2 = torch.empty_like(b) if want_grad else None
+    _lib.call("ubpl_features_cov", a.data_ptr(), b.data_ptr(), rows, L, cov.data_ptr(), value.data_ptr(), _p(g1), _p(g2), _stream())
+    return dict(value=value[0], rows=rows, cov=cov, grad1=g1, grad2=g2)
+
+
+# -------------------------------------------------------------------------------------------------
 # K4
 # -------------------------------------------------------------------------------------------------
 class EmaPlan:

@@ -13,7 +13,34 @@ def _to_cuda(t):
     return t if t.is_cuda else t.cuda()
 
 
+class _FeaturesCovFn(torch.autograd.Function):
+    """value = mean over (b, n, c) of |cov(f1_row, f2_row)| with both gradients produced by the forward kernel."""
+
+    @staticmethod
+    def forward(ctx, inp1, inp2):
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        r = ops.features_cov(inp1.detach(), inp2.detach(), want_grad=need)
+        ctx.g1, ctx.g2, ctx.shape = r["grad1"], r["grad2"], inp1.shape
+        return r["value"]
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.g1 is None:
+            return None, None
+        scale = g.detach().reshape(1).to(torch.float32).contiguous()
+        g1 = ops.scale(ctx.g1, scale).view(ctx.shape) if ctx.needs_input_grad[0] else None
+        g2 = ops.scale(ctx.g2, scale).view(ctx.shape) if ctx.needs_input_grad[1] else None
+        return g1, g2
+
+
 class ProcessUtils:
+    @classmethod
+    def features_cov(cls, inp1, inp2):
+        """utils/process.py:19-31: (mean |off-diagonal covariance| of the two views' feature rows, bs*n*c); one
+        streaming kernel reads each feature map once and writes both gradients."""
+        bs, n, c, h, w = inp1.size()
+        return _FeaturesCovFn.apply(inp1, inp2), bs * n * c
+
     # utils/process.py:53-68 -- scalar helpers on python numbers / 0-d tensors, kept as python
     @classmethod
     def coord_distance(cls, coord1, coord2):
