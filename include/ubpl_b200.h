@@ -219,6 +219,9 @@ int ubpl_select_quantile_fused(const double* dist, const double* legal_f64, cons
                                const float* kps, int img_h, int img_w, float stride, float sigma, int S,
                                float loss_weight, float* grad_scale, int32_t* count_out,
                                int use_p2p, void* stream);
+/* Developer hook: 64 device uint64 that receive globaltimer stamps of the selector's phases ([63] = count);
+ * NULL switches it off. */
+int ubpl_select_debug_stamps(void* dev_u64x64);
 /* Peer-memory exchange buffer of the call above, one per process (= per GPU).  ubpl_p2p_alloc allocates it for
  * `nranks` ranks of at most `max_items` items each and returns its 64-byte CUDA-IPC handle (host buffer); the
  * handles of all ranks, concatenated in rank order (any transport, e.g. torch.distributed all_gather), go to

@@ -50,6 +50,7 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_int, c_int, c_float, c_float, c_int, c_float, c_void_p, c_void_p,
                                    c_int, c_void_p],
+    "ubpl_select_debug_stamps": [c_void_p],
     "ubpl_p2p_buffer_bytes": [c_int, c_i64],
     "ubpl_p2p_alloc": [c_int, c_i64, c_void_p],
     "ubpl_p2p_open": [c_void_p, c_int, c_int],
@@ -122,7 +123,7 @@ def lib():
 
 # kernels launched per successful call (cudaMemsetAsync is not counted); bench.py's gpu_launches
 LAUNCHES = {"ubpl_dist_extrema": 2, "ubpl_features_cov": 2, "ubpl_warp_decode": 2, "ubpl_warp_decode_k2": 2, "ubpl_select_quantile_dist": 16, "ubpl_nccl_unique_id": 0,
-            "ubpl_nccl_init": 0, "ubpl_nccl_destroy": 0, "ubpl_p2p_alloc": 0, "ubpl_p2p_open": 0, "ubpl_p2p_close": 0}
+            "ubpl_nccl_init": 0, "ubpl_nccl_destroy": 0, "ubpl_p2p_alloc": 0, "ubpl_p2p_open": 0, "ubpl_p2p_close": 0, "ubpl_select_debug_stamps": 0}
 _launches = 0
 
 
