@@ -38,9 +38,10 @@ CONFIGS = {
 }
 DIST_THR_MAX = 3.0          # no reference default exists; ~half of the joints pass on the synthetic data
 METRIC = "pseudo-labelled samples/sec"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE warp_decode_kernel launch, from the ncu --set full capture
-# profiles/r01e_k1_k3_full.ncu-rep (c2: 469.93 MB read + 4.14 MB written vs 469.76 MB algorithmic)
-NCU_TRAFFIC = {"c2": 474.08e6}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE warp_decode_kernel launch, from the ncu --set full captures
+# profiles/r01f_k1_k3_full.ncu-rep (c2: 469.97 MB read + 4.03 MB written vs 469.76 MB algorithmic) and
+# profiles/r01f_c4_k1_select_k3_full.ncu-rep (c4: 1141.15 MB + 4.64 MB vs 1140.85 MB algorithmic)
+NCU_TRAFFIC = {"c2": 474.00e6, "c4": 1145.79e6}
 
 
 def algorithmic_bytes_per_sample(c):
