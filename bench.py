@@ -361,7 +361,7 @@ def run_ours(args):
             "stages_note": ("stage edges are event-record nodes inside the step's single CUDA graph; mean of the last "
                             "timed step and 32 further steps" if single else
                             "stage edges are CUDA events recorded around each stage graph in every timed step"),
-            "k2_fused_into_k1": bool(cfg.fuse_k12 and M == 1),
+            "k2_fused_into_k1": bool(cfg.fuse_k12 and M <= 2),
             "stages_gbs": {"k1": k1_bytes / (k1_ms * 1e-3) / 1e9, "k3": k3_bytes / (k3_ms * 1e-3) / 1e9,
                            "k4": ema_bytes / (k4_ms * 1e-3) / 1e9, "chain_k1_k3": chain_gbs},
             "chain_frac_of_peak": chain_gbs / peak, "chain_frac_of_8TBs": chain_gbs / 8000.0,
@@ -418,7 +418,7 @@ def run_ours(args):
                        "launch": ("1 CUDA graph per step" if single else "%d stage launches per step (%s)" % (len(gstep.order), ", ".join(
                                       n + (":eager" if n in gstep.eager else ":graph") for n in gstep.order)))
                                  + ("; EMA forked onto a side stream beside %s" % gstep.overlap_ema.upper() if gstep.overlap_ema else "; EMA after K3"),
-                       "selector": ("fixed rule in K1's epilogue" if c["select"] == "fixed" and cfg.fuse_k12 and M == 1 else
+                       "selector": ("fixed rule in K1's epilogue" if c["select"] == "fixed" and cfg.fuse_k12 and M <= 2 else
                                     "fused one-kernel quantile selector" + (" over NVLink peer memory" if p2p_ok else "")
                                     if (world == 1 or p2p_ok) and c["select"] == "quantile" else
                                     "NCCL histogram all-reduce" if c["select"] == "quantile" else "k2 kernels")},

@@ -73,7 +73,12 @@ int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
  * utils/process.py:262-268, utils/losses.py:29):
  *   k2_mode 1: mean [B,J,2] f32, dist [B,J] f64 (999 where a view is illegal), legal [B,J] u8
  *   k2_mode 2: + enable [B,J] u8, gate [B,J] f32 (= enable * visibility) and the counts below
- * so the chain needs no K2 launch (mode 2) or only the quantile selector (mode 1).
+ *   k2_mode 3: two teachers (V = 2K maps per key point, teacher-major): BusinessUtils.assess_pseudo_unc2
+ *              (utils/business.py:109-161) on the float32 view means p1, p2: mean = float32 ensemble coordinate
+ *              w1*p1 + w2*p2 with w_m = intDist_m / (intDist_1 + intDist_2), dist = extDist (999 = illegal),
+ *              legal; ws[33] counts the key points whose two intDists are both 0 (the reference divides by zero)
+ *   k2_mode 4: + the fixed rule on extDist, gate and counts as in mode 2
+ * so the chain needs no K2 launch (modes 2, 4) or only the quantile selector (modes 1, 3).
  * ws   int32 workspace of ubpl_warp_decode_k2_ws_bytes(V, B, J) bytes, 8-byte aligned; the call clears its
  *      head with one memset node.  After the launch ws[128 .. 128+J) = selected items per joint, ws[128+J] = total
  *      selected, ws[128+J+1] = S * #(gate > 0) (mode 2) -- the `count_in` of ubpl_render_mse.

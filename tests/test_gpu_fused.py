@@ -201,6 +201,36 @@ def test_warp_decode_k2_exhaustive_maps(ops):
             assert int(stats[0]) > 0.5 * K * B * J                             # the queue really was exercised
 
 
+@pytest.mark.parametrize("mode", [3, 4])
+def test_warp_decode_k2_dual_matches_unfused(ops, mode):
+    """Two teachers: the assess_pseudo_unc2 epilogue of K1 equals view_dispersion x2 + assess_dual (+ select_fixed +
+    gate_prepare) on the same decode, bit for bit."""
+    from ubpl_b200 import synth
+    for (B, K, J, seed) in ((8, 4, 6, 1), (19, 8, 9, 2), (3, 2, 3, 3), (2, 16, 2, 4), (5, 9, 4, 5)):
+        d = synth.make_batch(B=B, K=K, J=J, M=2, S=2, seed=seed, jitter=0.7, device="cuda")
+        dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64])
+        t = d["teacher"].reshape(2 * K, B, J, 64, 64)
+        th = d["theta"].unsqueeze(0).expand(2, K, B, 2, 3).reshape(2 * K, B, 2, 3)
+        fl = d["flip"].unsqueeze(0).expand(2, K, B).reshape(2 * K, B)
+        r = ops.warp_decode_k2(t, th, fl, dec, mode, S=2, distThrMax=2.0)
+        ref = ops.warp_decode(t, th, fl, dec)
+        for k in ("idx", "max", "xy"):
+            assert torch.equal(r[k], ref[k]), k
+        xy = ref["xy"].view(2, K, B, J, 2)
+        vd1, vd2 = ops.view_dispersion(xy[0]), ops.view_dispersion(xy[1])
+        ad = ops.assess_dual(vd1["mean"], vd2["mean"], None, xy[0], xy[1])
+        assert torch.equal(r["mean"], ad["coord32"])
+        assert torch.equal(r["dist"], ad["extDist"])
+        assert torch.equal(r["legal"].double(), ad["legal"])
+        assert int(r["zero_div"]) == int(ad["zero_div"])
+        if mode == 4:
+            sel = ops.select_fixed(ad["extDist"], ad["legal"], J, 2.0)
+            gate, gs, cnt = ops.gate_prepare(ad["coord32"], sel["gate"], 2, 256, 256, 4.0, 3.0, 1.0)
+            assert torch.equal(r["enable"].reshape(-1), sel["enable"])
+            assert torch.equal(r["gate"].reshape(-1), gate)
+            assert torch.equal(r["counts"], sel["counts"]) and int(r["count"]) == int(cnt)
+
+
 def test_warp_decode_k2_golden(ops):
     g = load("chain_mt")
     t = g["teacher"]

@@ -44,8 +44,10 @@ unsigned long long* work_counter(cudaStream_t stream);   // api.cu: a zeroed dev
 // (business.py:237-261,375-376, process.py:262-268, losses.py:29) -- the arithmetic of
 // view_dispersion_kernel / k2_view_fixed_kernel, without a second launch.
 struct K2Fuse {
-  int mode;                   // 0 off, 1 dispersion only (mean, dist, legal), 2 + fixed rule, gate and counts
-  int K;                      // views per item (= V)
+  int mode;                   // 0 off; one teacher: 1 dispersion only (mean, dist, legal), 2 + fixed rule, gate and
+                              // counts; two teachers (assess_pseudo_unc2): 3 ensemble coord / extDist / legal, 4 + fixed rule
+  int K;                      // maps per item (= V: K views of one teacher, or 2 x K/2 views of two teachers)
+  int32_t* zero_div;          // modes 3/4: number of items whose two intDists are both 0 (business.py:135 divides by zero)
   unsigned* arrive;           // [B*J] arrival counters, zero before the launch
   unsigned long long* slots;  // [K][B*J] hand-off words ~pack(x, y); 0 = not written yet (zero before the launch)
   double distThrMax;
@@ -343,6 +345,104 @@ __device__ __forceinline__ void k2_item(const WDParams& p, long long item, int j
   }
 }
 
+// K2 of one (sample, joint) with TWO teachers (utils/business.py:109-161 in the array form of assess_dual_kernel,
+// same float op order): lanes [0, Kt) hold teacher 1's views, lanes [Kt, 2Kt) teacher 2's.  p_m = float32 view
+// mean of teacher m; when every coordinate is legal: intDist_m = mean pairwise distance of teacher m's views in
+// itertools.combinations order, w_m = intDist_m / (intDist_1 + intDist_2), coord = w1*p1 + w2*p2 (float64),
+// extDist = mean_k dist(view_k of teacher 1, view_k of teacher 2); otherwise the 999 sentinels and the plain
+// float32 mean of p1 and p2.  Mode 4 adds the fixed rule on extDist, the visibility gate and the counts.
+__device__ __forceinline__ void k2_item_dual(const WDParams& p, long long item, int j, int lane) {
+  const K2Fuse& f = p.k2;
+  const int Kt = f.K >> 1;
+  const long long BJ = (long long)p.B * p.J;
+  float x = 0.f, y = 0.f;
+  if (lane < f.K) {
+    unsigned long long* sp = f.slots + ((long long)lane * BJ + item);
+    unsigned long long v;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(sp) : "memory");
+    } while (v == 0ull);
+    v = ~v;
+    x = __uint_as_float((unsigned)(v & 0xffffffffull));
+    y = __uint_as_float((unsigned)(v >> 32));
+    *sp = 0ull;
+  }
+  const unsigned legal_mask = __ballot_sync(0xffffffffu, (lane < f.K) && (x >= 0.f) && (y >= 0.f));
+  const unsigned m1 = (Kt >= 32) ? 0xffffffffu : ((1u << Kt) - 1u);
+  const bool g1 = (legal_mask & m1) == m1, g2 = ((legal_mask >> Kt) & m1) == m1;
+  float s1x = __shfl_sync(0xffffffffu, x, 0), s1y = __shfl_sync(0xffffffffu, y, 0);
+  float s2x = __shfl_sync(0xffffffffu, x, Kt), s2y = __shfl_sync(0xffffffffu, y, Kt);
+  for (int k = 1; k < Kt; ++k) {
+    s1x = __fadd_rn(s1x, __shfl_sync(0xffffffffu, x, k));
+    s1y = __fadd_rn(s1y, __shfl_sync(0xffffffffu, y, k));
+    s2x = __fadd_rn(s2x, __shfl_sync(0xffffffffu, x, Kt + k));
+    s2y = __fadd_rn(s2y, __shfl_sync(0xffffffffu, y, Kt + k));
+  }
+  const float p1x = __fdiv_rn(s1x, (float)Kt), p1y = __fdiv_rn(s1y, (float)Kt);
+  const float p2x = __fdiv_rn(s2x, (float)Kt), p2y = __fdiv_rn(s2y, (float)Kt);
+  const bool ori_legal = (p1x >= 0.f && p1y >= 0.f) && (p2x >= 0.f && p2y >= 0.f);
+  const bool full = ori_legal && g1 && g2;                                    // warp-uniform
+  double sd[2] = {0.0, 0.0}, se = 0.0;
+  const int P = Kt * (Kt - 1) / 2;
+  if (full) {
+    for (int m = 0; m < 2; ++m) {
+      for (int base = 0; base < P; base += 32) {
+        // pair number base + lane in combinations order -> (u, v)
+        int q = base + lane, u = 0;
+        while (u < Kt - 1 && q >= Kt - 1 - u) { q -= Kt - 1 - u; ++u; }
+        const int vv = u + 1 + q;
+        const bool have = (base + lane) < P;
+        const int su = m * Kt + (have ? u : 0), sv = m * Kt + (have ? vv : 0);
+        const float xu = __shfl_sync(0xffffffffu, x, su), yu = __shfl_sync(0xffffffffu, y, su);
+        const float xv = __shfl_sync(0xffffffffu, x, sv), yv = __shfl_sync(0xffffffffu, y, sv);
+        double d = 0.0;
+        if (have) d = py_dist((double)xu, (double)yu, (double)xv, (double)yv, f.T);
+        const int cnt = min(32, P - base);
+        for (int t = 0; t < cnt; ++t) sd[m] = __dadd_rn(sd[m], __shfl_sync(0xffffffffu, d, t));
+      }
+    }
+    // extDist: view k of teacher 1 against view k of teacher 2
+    const float ox = __shfl_sync(0xffffffffu, x, (lane < Kt) ? lane + Kt : lane);
+    const float oy = __shfl_sync(0xffffffffu, y, (lane < Kt) ? lane + Kt : lane);
+    double de = 0.0;
+    if (lane < Kt) de = py_dist((double)x, (double)y, (double)ox, (double)oy, f.T);
+    for (int k = 0; k < Kt; ++k) se = __dadd_rn(se, __shfl_sync(0xffffffffu, de, k));
+  }
+  if (lane != 0) return;
+  double legal = ori_legal ? 1.0 : 0.0, ext = 999.0;
+  double cx = (double)__fdiv_rn(__fadd_rn(p1x, p2x), 2.f), cy = (double)__fdiv_rn(__fadd_rn(p1y, p2y), 2.f);
+  if (full) {
+    const double d1 = __ddiv_rn(sd[0], (double)P), d2 = __ddiv_rn(sd[1], (double)P);   // K < 2: 0/0 -> NaN
+    const double den = __dadd_rn(d1, d2);
+    double w1 = 0.5, w2 = 0.5;
+    if (den == 0.0) {
+      if (f.zero_div) atomicAdd(f.zero_div, 1);
+    } else {
+      w1 = __ddiv_rn(d1, den);
+      w2 = __ddiv_rn(d2, den);
+    }
+    cx = __dadd_rn(__dmul_rn(w1, (double)p1x), __dmul_rn(w2, (double)p2x));
+    cy = __dadd_rn(__dmul_rn(w1, (double)p1y), __dmul_rn(w2, (double)p2y));
+    legal = 1.0;
+    ext = __ddiv_rn(se, (double)Kt);
+  }
+  const float c32x = (float)cx, c32y = (float)cy;
+  if (f.mean) { f.mean[2 * item] = c32x; f.mean[2 * item + 1] = c32y; }
+  if (f.dist) f.dist[item] = ext;
+  if (f.legal) f.legal[item] = legal > 0.0 ? 1 : 0;
+  if (f.mode == 4) {
+    const double thr = __dsub_rn(1.0, exp(-__ddiv_rn(__dmul_rn(f.distThrMax, 3.0), 5.0)));
+    const double unc = __dsub_rn(1.0, exp(-__ddiv_rn(ext, 5.0)));
+    const bool en = (legal > 0.0) && (unc <= thr);
+    const Gauss g = gauss_setup(c32x, c32y, f.img_h, f.img_w, f.stride, f.sigma);
+    const float gt = (en ? 1.f : 0.f) * g.vis;
+    if (f.enable) f.enable[item] = en ? 1 : 0;
+    f.gate[item] = gt;
+    if (en) { atomicAdd(f.counts + j, 1); atomicAdd(f.counts + p.J, 1); }
+    if (gt > 0.f) atomicAdd(f.counts + p.J + 1, f.S);
+  }
+}
+
 // Epilogue of one map (warp-wide call): arg-max -> heat-map coordinates (mask, optional quarter-offset
 // refinement) -> image-space coordinates -> outputs -> (optional) arrival at the item's K2.
 __device__ __forceinline__ void finish_map(const WDParams& p, long long n, int v, int b, int j, const float* s, const Xform& X,
@@ -412,7 +512,8 @@ __device__ __forceinline__ void k2_resolve(const WDParams& p, long long& pend_it
   if (old == (unsigned)(p.k2.K - 1)) {
     __syncwarp();
     if (lane == 0) p.k2.arrive[pend_item] = 0u;          // ready for the next launch on this workspace
-    k2_item(p, pend_item, (int)(pend_item % p.J), lane);
+    if (p.k2.mode >= 3) k2_item_dual(p, pend_item, (int)(pend_item % p.J), lane);
+    else k2_item(p, pend_item, (int)(pend_item % p.J), lane);
   }
   pend_item = -1;
 }
@@ -1013,8 +1114,9 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
   UBPL_REQUIRE(maps && theta && out_xy && ws, "ubpl_warp_decode_k2: NULL pointer");
   UBPL_REQUIRE(V >= 1 && V <= 32 && B >= 0 && J >= 1 && H > 0 && W > 0, "ubpl_warp_decode_k2: bad dims V=%d B=%d J=%d H=%d W=%d (1 <= V <= 32)", V, B, J, H, W);
   UBPL_REQUIRE(refine >= 0 && refine <= 2, "ubpl_warp_decode_k2: refine must be 0, 1 or 2");
-  UBPL_REQUIRE(k2_mode == 1 || k2_mode == 2, "ubpl_warp_decode_k2: k2_mode must be 1 (dispersion) or 2 (fixed rule)");
-  UBPL_REQUIRE(k2_mode == 1 || (gate && S >= 1 && stride > 0.f && sigma > 0.f), "ubpl_warp_decode_k2: mode 2 needs gate, S, stride, sigma");
+  UBPL_REQUIRE(k2_mode >= 1 && k2_mode <= 4, "ubpl_warp_decode_k2: k2_mode must be 1, 2 (one teacher) or 3, 4 (two teachers)");
+  UBPL_REQUIRE(k2_mode < 3 || (V % 2 == 0), "ubpl_warp_decode_k2: two teachers need an even number of maps per key point (V = 2K)");
+  UBPL_REQUIRE((k2_mode & 1) || (gate && S >= 1 && stride > 0.f && sigma > 0.f), "ubpl_warp_decode_k2: modes 2 and 4 need gate, S, stride, sigma");
   UBPL_REQUIRE(ws_bytes >= ubpl_warp_decode_k2_ws_bytes(V, B, J), "ubpl_warp_decode_k2: workspace too small");
   UBPL_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "ubpl_warp_decode_k2: workspace must be 8-byte aligned");
   const long long zero_words = k2_ws_zero_words(V, B, J);
@@ -1034,6 +1136,7 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
   K2Fuse& f = p.k2;
   f.mode = k2_mode; f.K = V;
   f.counts = ws + 128;
+  f.zero_div = ws + 33;
   f.arrive = reinterpret_cast<unsigned*>(ws + k2_ws_arrive_off(J));
   f.slots = reinterpret_cast<unsigned long long*>(ws + k2_ws_slots_off(B, J));
   f.distThrMax = distThrMax; f.img_h = img_h; f.img_w = img_w; f.S = S; f.stride = stride; f.sigma = sigma;

@@ -94,10 +94,14 @@ def warp_decode(maps, theta=None, flip=None, dec=None, refine=0, stats=None, wan
 
 def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stride=4.0, sigma=3.0, distThrMax=1.0,
                    refine=0, stats=None, want_idx=True):
-    """K1 with the per-joint part of K2 fused into its epilogue (one teacher, maps [K,B,J,H,W], K <= 32).
-    mode 1: + mean [B,J,2], dist [B,J] f64 (999 = illegal), legal [B,J]   (utils/evaluation.py:44-54)
-    mode 2: + enable, gate = enable * visibility, counts [J+1], count = S * #(gate > 0)
-            (utils/business.py:237-261,375-376, utils/process.py:262-268, utils/losses.py:29)."""
+    """K1 with the per-joint part of K2 fused into its epilogue (maps [V,B,J,H,W], V <= 32).
+    One teacher (V = K views):
+      mode 1: + mean [B,J,2], dist [B,J] f64 (999 = illegal), legal [B,J]   (utils/evaluation.py:44-54)
+      mode 2: + enable, gate = enable * visibility, counts [J+1], count = S * #(gate > 0)
+              (utils/business.py:237-261,375-376, utils/process.py:262-268, utils/losses.py:29)
+    Two teachers (V = 2K maps, teacher-major; theta/flip given per map):
+      mode 3: mean = float32 ensemble coordinate, dist = extDist, legal, zero_div (utils/business.py:109-161)
+      mode 4: + the fixed rule on extDist, gate and counts as in mode 2."""
     _need_cuda(maps, theta, flip, dec, stats)
     if maps.dtype != _f32:
         raise _lib.UbplError("heat-maps must be float32")
@@ -115,8 +119,8 @@ def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stri
     mean = torch.empty(B, J, 2, dtype=_f32, device=dev)
     dist = torch.empty(B, J, dtype=_f64, device=dev)
     legal = torch.empty(B, J, dtype=torch.uint8, device=dev)
-    enable = torch.empty(B, J, dtype=torch.uint8, device=dev) if mode == 2 else None
-    gate = torch.empty(B, J, dtype=_f32, device=dev) if mode == 2 else None
+    enable = torch.empty(B, J, dtype=torch.uint8, device=dev) if mode in (2, 4) else None
+    gate = torch.empty(B, J, dtype=_f32, device=dev) if mode in (2, 4) else None
     ws_bytes = int(_lib.lib().ubpl_warp_decode_k2_ws_bytes(K, B, J))
     ws = torch.empty(ws_bytes // 4, dtype=torch.int32, device=dev)
     _lib.call("ubpl_warp_decode_k2", maps.data_ptr(), maps.stride(0), maps.stride(1), maps.stride(2), K, B, J, H, W,
@@ -125,7 +129,7 @@ def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stri
               mean.data_ptr(), dist.data_ptr(), legal.data_ptr(), _p(enable), _p(gate), _p(stats), ws.data_ptr(),
               ws_bytes, _stream())
     return dict(idx=out_idx, max=out_max, xy=out_xy, mean=mean, dist=dist, legal=legal, enable=enable, gate=gate,
-                counts=ws[128:128 + J + 1], count=ws[128 + J + 1:128 + J + 2], ws=ws)
+                counts=ws[128:128 + J + 1], count=ws[128 + J + 1:128 + J + 2], zero_div=ws[33:34], ws=ws)
 
 
 def warp_materialize(heatmap, warpmat, isflip):

@@ -32,7 +32,7 @@ class StepConfig:
     want_target: bool = True         # materialise the rendered targets (counted in the byte model)
     want_grad: bool = True
     fuse_k2: bool = True             # one-launch K2 for the M=1 fixed-threshold path
-    fuse_k12: bool = True            # M=1: the per-joint part of K2 runs in K1's epilogue (no K2 launch on the fixed path)
+    fuse_k12: bool = True            # the per-joint part of K2 runs in K1's epilogue (no K2 launch on the fixed path)
     fuse_sum: bool = True            # the loss reduction runs in K3's last CTA (no loss_finalize launch)
 
 
@@ -49,16 +49,25 @@ def stage_k1(st, stats=None, cfg=None):
     teacher, theta, flip, dec = st["teacher"], st["theta"], st["flip"], st["dec"]
     M, K, B, J, H, W = teacher.shape
     st.pop("k12", None)
-    if cfg is not None and cfg.fuse_k12 and M == 1 and K <= 32 and cfg.select in ("fixed", "quantile"):
+    flat = teacher.stride(0) == K * teacher.stride(1)              # [M,K,...] is one run of M*K maps
+    if (cfg is not None and cfg.fuse_k12 and cfg.select in ("fixed", "quantile") and
+            ((M == 1 and K <= 32) or (M == 2 and K <= 16 and flat))):
         S = st["student"].shape[1]
         sH, sW = st["student"].shape[-2:]
-        r = ops.warp_decode_k2(teacher[0], theta, flip, dec, 2 if cfg.select == "fixed" else 1, S=S,
-                               img_h=int(sH * cfg.stride), img_w=int(sW * cfg.stride), stride=cfg.stride, sigma=cfg.sigma,
-                               distThrMax=cfg.distThrMax, stats=stats)
-        st["xy"], st["max"], st["idx"] = r["xy"].view(1, K, B, J, 2), r["max"].view(1, K, B, J), r["idx"].view(1, K, B, J)
+        mode = (2 if cfg.select == "fixed" else 1) + (2 if M == 2 else 0)
+        if M == 1:
+            maps, th, fl = teacher[0], theta, flip
+        else:                                                      # both teachers see the same K views
+            maps = (teacher.view(M * K, B, J, H, W) if teacher.is_contiguous() else
+                    teacher.as_strided((M * K, B, J, H, W), (teacher.stride(1),) + tuple(teacher.stride()[2:])))
+            th = theta.unsqueeze(0).expand(M, K, B, 2, 3).reshape(M * K, B, 2, 3)
+            fl = flip.unsqueeze(0).expand(M, K, B).reshape(M * K, B)
+        r = ops.warp_decode_k2(maps, th, fl, dec, mode, S=S, img_h=int(sH * cfg.stride), img_w=int(sW * cfg.stride),
+                               stride=cfg.stride, sigma=cfg.sigma, distThrMax=cfg.distThrMax, stats=stats)
+        st["xy"], st["max"], st["idx"] = r["xy"].view(M, K, B, J, 2), r["max"].view(M, K, B, J), r["idx"].view(M, K, B, J)
         st["k12"] = r
         return st
-    if teacher.stride(0) == K * teacher.stride(1):
+    if flat:
         dec_out = ops.warp_decode(teacher.view(M * K, B, J, H, W) if teacher.is_contiguous() else
                                   teacher.as_strided((M * K, B, J, H, W), (teacher.stride(1),) + tuple(teacher.stride()[2:])),
                                   theta.unsqueeze(0).expand(M, K, B, 2, 3).reshape(M * K, B, 2, 3),
@@ -233,7 +242,9 @@ class GraphedStep:
             # an event-record node costs ~1-2 us of device time, so only the edges between stages that launch
             # something are instrumented: on the fixed path with K2 fused into K1 the K2 stage is empty and is
             # folded into the K1 segment
-            k2_empty = cfg.fuse_k12 and teacher.shape[0] == 1 and teacher.shape[1] <= 32 and cfg.select == "fixed"
+            Mt, Kt = teacher.shape[0], teacher.shape[1]
+            k2_empty = (cfg.fuse_k12 and cfg.select == "fixed" and
+                        ((Mt == 1 and Kt <= 32) or (Mt == 2 and Kt <= 16 and teacher.stride(0) == Kt * teacher.stride(1))))
             segs = []
             for name, fn in stages:
                 if name == "k2" and k2_empty:
