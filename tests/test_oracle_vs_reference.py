@@ -231,6 +231,60 @@ def test_pseudo_cal_unc_and_mixUnc_filters(ref, batch):
             assert (o1["unc"] < 999).any() and (o1["unc"] == 999).any()
 
 
+def test_decode_coeffs_random_centres(ref):
+    """The inverse decode transform for 2000 random (centre, scale) pairs, bit for bit: `python_float / tensor` is
+    reciprocal-multiply in torch, which a true division misses by an ulp for a quarter of the pairs."""
+    from utils.udaap.transforms import get_transform
+    g = torch.Generator().manual_seed(23)
+    for dt, kind in ((torch.float32, "f32"), (torch.float64, "f64")):
+        centers = torch.randint(60, 200, (2000, 2), generator=g)
+        scales = (0.6 + torch.rand(2000, generator=g) * 1.2).to(dt)
+        got = O.decode_coeffs(centers.numpy(), scales.numpy(), [64, 64], kind)
+        from ubpl_b200 import ops
+        prod = ops.decode_coeffs(centers, scales, [64, 64]).numpy()
+        for i in range(2000):
+            inv = np.linalg.inv(get_transform(centers[i], scales[i], [64, 64], rot=0))
+            want = [inv[0, 0], inv[0, 2], inv[1, 1], inv[1, 2]]
+            assert got[i].tolist() == want, (kind, i)
+            assert prod[i].tolist() == want, (kind, i)
+
+
+def test_view_matrix_and_view_kps(ref):
+    """N1: get_transform with rotation / transform / affine_kps / kps_fliplr (utils/udaap/transforms.py:119-158,
+    utils/augment.py:151-156, utils/process.py:239-242), with the float32 0-d tensors affine_mulKps hands over
+    and with python floats; integer coordinates bit-exact."""
+    from utils.udaap.transforms import get_transform
+    g = torch.Generator().manual_seed(17)
+    B, J, V, W = 6, 9, 5, 256
+    kps = torch.cat([torch.rand(B, J, 2, generator=g) * 250 + 2, torch.ones(B, J, 1)], -1)
+    kps[1, 3, 1] = 0.0                                    # invisible key point: left alone (but still mirrored)
+    kps[2, 0, :2] = torch.tensor([128.0, 128.0])
+    for kind in ("f32", "f64"):
+        mats = np.zeros((V, B, 3, 3))
+        flips = np.zeros((V, B), bool)
+        want = np.zeros((V, B, J, 3), np.float32)
+        for v in range(V):
+            for b in range(B):
+                flip = bool(torch.rand(1, generator=g) < 0.5)
+                center = [float(torch.randint(100, 156, (1,), generator=g)), float(torch.randint(100, 156, (1,), generator=g))]
+                scale = 1.28 * torch.randn(1, generator=g).mul_(0.25).add_(1).clamp(0.75, 1.25)[0]
+                angle = torch.randn(1, generator=g).mul_(30).clamp(-30, 30)[0]
+                if v == 0:
+                    angle = angle * 0                      # the rot == 0 branch
+                if kind == "f64":
+                    scale, angle = float(scale), float(angle)
+                k = kps[b].clone()
+                if flip:
+                    k = ref.proc.kps_fliplr(k, W)
+                    center[0] = W - center[0]
+                want[v, b] = ref.aug.affine_kps(k, center, scale, [W, W], angle).numpy()
+                got_t = O.view_matrix(center, scale, [W, W], angle, kind)
+                assert np.array_equal(got_t, get_transform(center, scale, [W, W], rot=angle)), (kind, v, b)
+                mats[v, b], flips[v, b] = got_t, flip
+        got = O.view_kps(kps.numpy(), mats, flips, W)
+        assert np.array_equal(got, want), kind
+
+
 def test_acc_pck(ref, batch):
     """N2: utils/evaluation.py:92-139 (float32 tensors; sums within 1e-6 relative, the summation order of
     torch.sum differs from a sequential one)."""
