@@ -330,6 +330,15 @@ int ubpl_gate_prepare(const float* kps, const float* gate_in, int64_t n, int img
  * wrappers; both 16-byte aligned. */
 int ubpl_scale(float* dst, const float* src, int64_t n, const float* scale, void* stream);
 
+/* ---- N1: canonical key points -> the frame of every augmented view --------------------------
+ * ProcessUtils.kps_fliplr (utils/process.py:239-242) + AugmentUtils.affine_kps (utils/augment.py:151-156) /
+ * transform (utils/udaap/transforms.py:151-158) for all views, samples and joints in one launch.
+ * kps [B,J,3] float32 (x, y, weight); mats [V,B,2,3] float64 = rows 0,1 of get_transform(centre, scale, res, rot)
+ * of every (view, sample) (host-built: its sin/cos are numpy's); flips [V,B] uint8 or NULL; out [V,B,J,3].
+ * The result feeds ubpl_render_targets / ubpl_render_mse to render the targets in each student view's frame. */
+int ubpl_view_kps(const float* kps, const double* mats, const uint8_t* flips, float img_w, int V, int B, int J,
+                  float* out, void* stream);
+
 /* ---- N2 / N3: PCK evaluation and the feature-decorrelation loss ---------------------------
  * ubpl_acc_pck: EvaluationUtils.acc_pck (utils/evaluation.py:92-139) on device.  preds [bs,k,p_stride>=2],
  * gts [bs,k,g_stride>=2] float32; errs/accs float32 [k+1] (per joint, then the mean over joints; accs[k] = -1

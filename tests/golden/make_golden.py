@@ -239,12 +239,46 @@ def mixunc_fixture():
     print("mixunc", len(epochs), "epochs,", sum(e["f1"]["counts"][-1] for e in epochs), "selections")
 
 
+def viewkps_fixture():
+    """N1: canonical key points into the frames of V augmented views with the reference's own functions
+    (kps_fliplr, get_transform with the float32 0-d tensors of affine_mulKps, affine_kps)."""
+    from utils.udaap.transforms import get_transform
+    g = torch.Generator().manual_seed(17)
+    B, J, V, W = 6, 9, 5, 256
+    kps = torch.cat([torch.rand(B, J, 2, generator=g) * 250 + 2, torch.ones(B, J, 1)], -1)
+    kps[1, 3, 1] = 0.0
+    kps[2, 0, :2] = torch.tensor([128.0, 128.0])
+    kps[:, :, :2] = (kps[:, :, :2] * 4).round() / 4
+    centers = np.zeros((V, B, 2)); scales = np.zeros((V, B), np.float32); angles = np.zeros((V, B), np.float32)
+    flips = np.zeros((V, B), np.uint8); mats = np.zeros((V, B, 3, 3)); out = np.zeros((V, B, J, 3), np.float32)
+    for v in range(V):
+        for b in range(B):
+            flip = bool(torch.rand(1, generator=g) < 0.5)
+            center = [float(torch.randint(100, 156, (1,), generator=g)), float(torch.randint(100, 156, (1,), generator=g))]
+            scale = 1.28 * torch.randn(1, generator=g).mul_(0.25).add_(1).clamp(0.75, 1.25)[0]
+            angle = torch.randn(1, generator=g).mul_(30).clamp(-30, 30)[0]
+            if v == 0:
+                angle = angle * 0
+            k = kps[b].clone()
+            if flip:
+                k = ref.proc.kps_fliplr(k, W)
+                center[0] = W - center[0]
+            out[v, b] = ref.aug.affine_kps(k, center, scale, [W, W], angle).numpy()
+            mats[v, b] = get_transform(center, scale, [W, W], rot=angle)
+            centers[v, b], scales[v, b], angles[v, b], flips[v, b] = center, scale.item(), angle.item(), flip
+    save("viewkps", kps=kps, centers=centers, scales=scales, angles=angles, flips=flips, mats=mats, out=out, img_w=np.int64(W))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mixunc":
         mixunc_fixture()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "viewkps":
+        viewkps_fixture()
+        sys.exit(0)
     business_fixture()
     mixunc_fixture()
+    viewkps_fixture()
     chain_fixture("chain_mt", B=2, K=3, J=3, H=64, W=64, M=1, seed=1388)
     chain_fixture("chain_dual", B=4, K=4, J=5, H=32, W=32, M=2, seed=1389)
     decode_fixture()

@@ -79,3 +79,16 @@ def test_host_helpers():
     for c in bench.CONFIGS.values():
         assert bench.algorithmic_bytes_per_sample(c) == 4 * c["H"] * c["W"] * c["J"] * (c["M"] * c["K"] + 2 * c["S"] + 1)
     assert bench.algorithmic_bytes_per_sample(bench.CONFIGS["c2"]) == 2981888
+
+
+def test_view_matrix_host_helper():
+    """augment.AugmentUtils.view_matrix (host side of N1) against the reference's matrices in the golden fixture."""
+    from golden_util import load
+    g = load("viewkps")
+    V, B = g["flips"].shape
+    W = int(g["img_w"])
+    for v in range(V):
+        for b in range(B):
+            t = augment.AugmentUtils.view_matrix(g["centers"][v, b].tolist(), torch.tensor(g["scales"][v, b]), [W, W],
+                                                 torch.tensor(g["angles"][v, b]))
+            np.testing.assert_allclose(t, g["mats"][v, b], rtol=1e-15, atol=1e-15)

@@ -310,3 +310,31 @@ def test_features_cov(pkg):
         np.testing.assert_allclose(val.item(), v, rtol=1e-5)
         np.testing.assert_allclose(a.grad.cpu().numpy(), g1, rtol=1e-4, atol=1e-9)
         np.testing.assert_allclose(b.grad.cpu().numpy(), g2, rtol=1e-4, atol=1e-9)
+
+
+def test_view_kps(pkg):
+    """N1: key points into the frame of every augmented view (utils/process.py:239-242, utils/augment.py:151-156,
+    utils/udaap/transforms.py:151-158): integer coordinates bit-exact against the reference's outputs, then the
+    in-frame targets rendered from them equal the targets of the reference's per-view key points."""
+    from ubpl_b200 import ops
+    g = load("viewkps")
+    V, B = g["flips"].shape
+    J = g["kps"].shape[1]
+    W = int(g["img_w"])
+    out = ops.view_kps(T(g["kps"]).cuda(), T(g["mats"]).cuda(), T(g["flips"]).cuda(), W)
+    assert np.array_equal(out.cpu().numpy(), g["out"])
+    assert np.array_equal(out.cpu().numpy(), O.view_kps(g["kps"], g["mats"], g["flips"], W))
+    # single-sample drop-in (no flip inside affine_kps: the Dataset mirrors before, process.py:239-242)
+    for v, b in ((1, 0), (3, 4)):
+        k = T(g["kps"][b]).clone()
+        if g["flips"][v, b]:
+            k[:, 0] = W - k[:, 0]
+        got = pkg.aug.affine_kps(k, g["centers"][v, b].tolist(), torch.tensor(g["scales"][v, b]), [W, W],
+                                 torch.tensor(g["angles"][v, b]))
+        assert got.device.type == "cpu" and np.array_equal(got.numpy(), g["out"][v, b])
+    # in-frame rendering: one launch for all V*B*J targets
+    hm, kout = ops.render_targets(out.reshape(-1, 3), 64, 64, W, W)
+    want_hm, want_k = O.kps_heatmap(g["out"].reshape(-1, 3), (3, W, W), W, 64)
+    assert np.array_equal(hm.cpu().numpy() == 0, want_hm == 0)
+    np.testing.assert_allclose(hm.cpu().numpy(), want_hm, rtol=RTOL)
+    assert np.array_equal(kout.cpu().numpy(), want_k)

@@ -77,6 +77,7 @@ SIGNATURES = {
     "ubpl_loss_finalize": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "ubpl_gate_prepare": [c_void_p, c_void_p, c_i64, c_int, c_int, c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_scale": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p],
+    "ubpl_view_kps": [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p, c_void_p],
     "ubpl_acc_pck": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_features_cov": [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_ema_multi_tensor": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_float, c_void_p],

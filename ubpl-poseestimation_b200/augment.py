@@ -3,6 +3,7 @@ argument meaning.  The forward image augmentation (skimage / cv2, CPU data-loade
 scope and stays with the reference."""
 import math
 
+import numpy as np
 import torch
 
 from . import ops
@@ -50,3 +51,36 @@ class AugmentUtils:
         D = m00 * m11 - m01 * m10
         D = 1.0 / D if D != 0 else 0.0
         return torch.tensor([[m11 * D, m01 * (-D), 0.0], [m10 * (-D), m00 * D, 0.0]], dtype=torch.float64).float()
+
+    @classmethod
+    def view_matrix(cls, center, scale, matrixRes, angle=0):
+        """The 3x3 float64 map of utils/udaap/transforms.py:119-148 (get_transform) for one augmented view: crop of
+        200*scale around `center` onto matrixRes, rotated by `angle` about the frame centre.  Host arithmetic on
+        whatever `scale` / `angle` are (python floats or the 0-d float32 tensors affine_mulKps produces,
+        utils/augment.py:28-29), written in the same expression forms so that the dtype rules the reference goes
+        through (tensor arithmetic stays float32, python_float / tensor is reciprocal-multiply, numpy sin/cos of a
+        float32) apply here too: the matrix is bit-identical, which the integer truncation of the mapped key points
+        needs.  Feed the stacked matrices to ops.view_kps."""
+        side = 200 * scale
+        m = np.zeros((3, 3))
+        m[0, 0], m[1, 1], m[2, 2] = float(matrixRes[1]) / side, float(matrixRes[0]) / side, 1
+        m[0, 2] = matrixRes[1] * (-float(center[0]) / side + .5)
+        m[1, 2] = matrixRes[0] * (-float(center[1]) / side + .5)
+        if not angle == 0:
+            rad = (-angle) * np.pi / 180
+            s, c = np.sin(rad), np.cos(rad)
+            spin = np.array([[c, -s, 0.], [s, c, 0.], [0., 0., 1.]])
+            to_origin, back = np.eye(3), np.eye(3)
+            to_origin[0, 2], to_origin[1, 2] = -matrixRes[1] / 2, -matrixRes[0] / 2
+            back[0, 2], back[1, 2] = -to_origin[0, 2], -to_origin[1, 2]
+            m = np.dot(back, np.dot(spin, np.dot(to_origin, m)))
+        return m
+
+    @classmethod
+    def affine_kps(cls, kpsMap, center, scale, matrixRes, angle=0):
+        """utils/augment.py:151-156: the visible key points (y > 0) of one sample mapped into the augmented frame;
+        returns a new [J,3] tensor on the input's device (the batched form is ops.view_kps)."""
+        dev = kpsMap.device
+        mat = torch.from_numpy(cls.view_matrix(center, scale, matrixRes, angle)).reshape(1, 1, 3, 3)
+        out = ops.view_kps(_to_cuda(kpsMap.detach().to(torch.float32)).unsqueeze(0), mat.cuda(), None, 0.0)
+        return out[0, 0].to(dev).to(kpsMap.dtype)

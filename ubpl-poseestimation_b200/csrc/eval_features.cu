@@ -1,7 +1,8 @@
-// N2 and N3 of SURVEY.md section 8(f): the PCK evaluation of validate() and the multi-view feature
-// decorrelation loss, the two per-step terms next to the pseudo-label chain.
+// N1, N2 and N3 of SURVEY.md section 8(f): key points into the frame of every augmented view (for in-frame
+// target rendering), the PCK evaluation of validate() and the multi-view feature decorrelation loss.
 //
 // Reference semantics (file:line in /root/reference):
+//   utils/udaap/transforms.py:119-158, utils/augment.py:151-156, utils/process.py:239-242  (N1)
 //   utils/evaluation.py:92-139  acc_pck / _acc_calDists / _acc_counting (float32 torch tensors)
 //   utils/process.py:19-31      features_cov / torch_cov
 #include "common.cuh"
@@ -120,6 +121,36 @@ __global__ void __launch_bounds__(256) features_cov_kernel(const float* __restri
   }
 }
 
+// ---- N1 ------------------------------------------------------------------------------------------------
+// Canonical key points -> the frame of every augmented view (what the Dataset does per sample and joint on the
+// host): x <- img_w - x for a flipped view (process.py:239-242, float32), then for the visible key points
+// (y > 0, augment.py:154) transform() of transforms.py:151-158: v = (x-1, y-1, 1) with the subtraction in
+// float32, np.dot(t, v) -- measured on numpy: fma(t00, vx, t01*vy) + t02 in float64 -- truncation, + 1.
+// mats [V*B, 2, 3] float64 are rows 0 and 1 of get_transform for the view (built on the host from the view's
+// centre / scale / angle, whose sin/cos must come from the host's numpy to stay bit-identical).
+__global__ void view_kps_kernel(const float* __restrict__ kps, const double* __restrict__ mats,
+                                const uint8_t* __restrict__ flips, float img_w, int V, int B, int J,
+                                float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)V * B * J;
+  if (i >= n) return;
+  const int j = (int)(i % J);
+  const long long vb = i / J;
+  const int b = (int)(vb % B);
+  const float* k = kps + ((long long)b * J + j) * 3;
+  float x = k[0], y = k[1];
+  if (flips && flips[vb]) x = __fsub_rn(img_w, x);
+  if (y > 0.f) {
+    const double* t = mats + vb * 6;
+    const double vx = (double)__fsub_rn(x, 1.f), vy = (double)__fsub_rn(y, 1.f);
+    const double rx = __dadd_rn(__fma_rn(t[0], vx, __dmul_rn(t[1], vy)), t[2]);
+    const double ry = __dadd_rn(__fma_rn(t[3], vx, __dmul_rn(t[4], vy)), t[5]);
+    x = (float)(trunc(rx) + 1.0);
+    y = (float)(trunc(ry) + 1.0);
+  }
+  out[3 * i] = x; out[3 * i + 1] = y; out[3 * i + 2] = k[2];
+}
+
 // mean of |x| over n values, one CTA, fixed order (reproducible); out[0] = mean
 __global__ void __launch_bounds__(1024) abs_mean_kernel(const float* __restrict__ x, long long n, float* out) {
   __shared__ double red[32];
@@ -149,6 +180,15 @@ extern "C" int ubpl_acc_pck(const float* preds, int p_stride, const float* gts, 
   acc_pck_kernel<<<1, threads, (size_t)2 * k * sizeof(float), (cudaStream_t)stream>>>(preds, p_stride, gts, g_stride, bs, k, ref0,
                                                                                      ref1, pck_thr, errs, accs, dists, dists_ref);
   return check_launch("ubpl_acc_pck");
+}
+
+extern "C" int ubpl_view_kps(const float* kps, const double* mats, const uint8_t* flips, float img_w, int V, int B, int J,
+                             float* out, void* stream) {
+  UBPL_REQUIRE(kps && mats && out && V >= 0 && B >= 0 && J >= 0, "ubpl_view_kps: bad arguments");
+  const long long n = (long long)V * B * J;
+  if (n == 0) return UBPL_OK;
+  view_kps_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kps, mats, flips, img_w, V, B, J, out);
+  return check_launch("ubpl_view_kps");
 }
 
 extern "C" int ubpl_features_cov(const float* f1, const float* f2, int64_t rows, int L, float* cov, float* value,

@@ -4,7 +4,7 @@
 attributes of the reference's own modules:
 
     utils.losses.{JointMSELoss, JointDistLoss, JointPseudoLoss3, JointDistLoss_mt2}
-    utils.augment.AugmentUtils.{affine_back2, affine_back2_classification, fliplr_back_tensor}
+    utils.augment.AugmentUtils.{affine_back2, affine_back2_classification, fliplr_back_tensor, affine_kps}
     utils.process.ProcessUtils.{kps_fromHeatmap, kps_fromHeatmap_mul, kps_fromHeatmap2, kps_heatmap,
                                 kps_heatmap_mulKps, kps_getLabeledCount, features_cov}
     utils.evaluation.EvaluationUtils.{uncertainty_fromDistance, acc_pck}
@@ -21,7 +21,8 @@ PATCHES = {
     "utils.parameters": {"update_ema_variables": parameters.update_ema_variables},
 }
 CLASS_PATCHES = {
-    ("utils.augment", "AugmentUtils"): (augment.AugmentUtils, ("affine_back2", "affine_back2_classification", "fliplr_back_tensor")),
+    ("utils.augment", "AugmentUtils"): (augment.AugmentUtils, ("affine_back2", "affine_back2_classification", "fliplr_back_tensor",
+                                                               "affine_kps")),
     ("utils.process", "ProcessUtils"): (process.ProcessUtils, ("kps_fromHeatmap", "kps_fromHeatmap_mul", "kps_fromHeatmap2",
                                                                "kps_heatmap", "kps_heatmap_mulKps", "kps_getLabeledCount",
                                                                "features_cov")),

@@ -639,6 +639,21 @@ def scale_inplace(x, s):
 # -------------------------------------------------------------------------------------------------
 # N2 / N3
 # -------------------------------------------------------------------------------------------------
+def view_kps(kps, mats, flips, img_w):
+    """Canonical key points [B,J,3] -> every augmented view's frame [V,B,J,3] (utils/process.py:239-242,
+    utils/augment.py:151-156, utils/udaap/transforms.py:151-158).  mats [V,B,3,3] or [V,B,2,3] float64 from
+    augment.AugmentUtils.view_matrix (get_transform of the view), flips [V,B] bool/uint8 or None."""
+    _need_cuda(kps, mats, flips)
+    kps = kps.to(_f32).contiguous()
+    B, J, _ = kps.shape
+    V = mats.shape[0]
+    mats = mats.to(_f64)[..., :2, :].contiguous()
+    flips = None if flips is None else flips.reshape(V, B).to(torch.uint8).contiguous()
+    out = torch.empty(V, B, J, 3, dtype=_f32, device=kps.device)
+    _lib.call("ubpl_view_kps", kps.data_ptr(), mats.data_ptr(), _p(flips), float(img_w), V, B, J, out.data_ptr(), _stream())
+    return out
+
+
 def acc_pck(preds, gts, pck_ref, pck_thr, want_dists=False):
     """EvaluationUtils.acc_pck (utils/evaluation.py:92-139): preds [bs,k,>=2], gts [bs,k,>=2] ->
     (errs [k+1], accs [k+1]) float32 on the device (+ dists, dists_ref [k,bs] when asked)."""
