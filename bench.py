@@ -249,7 +249,9 @@ def run_ours(args):
         p2p_ok = False
     if group is not None and c["select"] == "quantile" and not p2p_ok:
         ubpl_dist.init_nccl(group)                 # the library's own communicator for the histogram all-reduce
-    overlap = {"0": False, "1": "k1", "k1": "k1", "k3": "k3"}[os.environ.get("UBPL_BENCH_OVERLAP_EMA", "k1")]
+    # the EMA runs beside K1 (fixed path) or beside the one-CTA quantile selector (measured: profiles/README.md)
+    overlap = {"0": False, "1": "k1", "k1": "k1", "k2": "k2", "k3": "k3"}[
+        os.environ.get("UBPL_BENCH_OVERLAP_EMA", "k2" if c["select"] == "quantile" else "k1")]
     gstep = pipeline.GraphedStep(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, group=group,
                                  stats=stats, ema=plan, alpha=alpha, overlap_ema=overlap,
                                  mode=os.environ.get("UBPL_BENCH_GRAPH", "single"))
@@ -355,7 +357,7 @@ def run_ours(args):
             "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC.get(args.config), "peak_source": peak_src,
             "stages_ms": {("k1_warp_decode_with_k4_ema_overlapped" if gstep.overlap_ema == "k1" else "k1_warp_decode"): k1_ms,
-                          "k2_uncertainty_select": k2_ms,
+                          ("k2_uncertainty_select_with_k4_ema_overlapped" if gstep.overlap_ema == "k2" else "k2_uncertainty_select"): k2_ms,
                           ("k3_render_mse_with_k4_ema_overlapped" if gstep.overlap_ema == "k3" else "k3_render_mse"): k3_ms,
                           "k4_ema_in_step": k4_inline_ms, "k4_ema_standalone": k4_ms},
             "stages_note": ("stage edges are event-record nodes inside the step's single CUDA graph; mean of the last "

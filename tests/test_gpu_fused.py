@@ -367,3 +367,22 @@ def test_graphed_step_modes(ops, mode, select):
             ms = g.stage_ms()
             assert set(ms) >= {"k1", "k2", "k3"} and all(v >= 0.0 for v in ms.values())
             assert 0.0 < sum(ms.values()) < 50.0
+
+
+def test_empty_and_degenerate_shapes(ops):
+    """Empty batches and single-view / single-joint inputs through the fused entries."""
+    from ubpl_b200 import synth
+    dec0 = torch.zeros(0, 4, dtype=torch.float64, device="cuda")
+    r = ops.warp_decode_k2(torch.zeros(3, 0, 5, 64, 64, device="cuda"), torch.zeros(3, 0, 2, 3, device="cuda"),
+                           torch.zeros(3, 0, dtype=torch.uint8, device="cuda"), dec0, 2)
+    assert r["xy"].shape == (3, 0, 5, 2) and int(r["count"]) == 0 and int(r["counts"].sum()) == 0
+    d = synth.make_batch(B=3, K=1, J=1, M=1, S=1, seed=2, device="cuda")
+    dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64])
+    r = ops.warp_decode_k2(d["teacher"][0], d["theta"], d["flip"], dec, 2, S=1, distThrMax=1.0)
+    ref = ops.warp_decode(d["teacher"][0], d["theta"], d["flip"], dec)
+    assert torch.equal(r["xy"], ref["xy"]) and torch.all(r["dist"][r["legal"] > 0] == 0)      # one view: no dispersion
+    a = ops.render_mse(torch.zeros(0, 4, 2, device="cuda"), None, None, torch.zeros(0, 2, 4, 64, 64, device="cuda"), 256, 256,
+                       want_summary=True)
+    assert a["summary"].tolist() == [0.0, 0.0, 0.0, 0.0]
+    out = ops.view_kps(torch.zeros(0, 4, 3, device="cuda"), torch.zeros(2, 0, 3, 3, dtype=torch.float64, device="cuda"), None, 256)
+    assert out.shape == (2, 0, 4, 3)

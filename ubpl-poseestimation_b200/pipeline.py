@@ -204,8 +204,11 @@ class GraphedStep:
         torch.cuda.synchronize()
         pool = None
         self.eager = {}
-        # overlap_ema: True / "k1" = K4 forked beside K1, "k3" = beside K3, False = after K3
-        self.overlap_ema = ("k3" if overlap_ema == "k3" else "k1") if (overlap_ema and ema is not None) else False
+        # overlap_ema: True / "k1" = K4 forked beside K1, "k2" = beside the quantile selector (a one-CTA kernel that
+        # leaves the rest of the GPU idle), "k3" = beside K3, False = after K3
+        self.overlap_ema = (overlap_ema if overlap_ema in ("k2", "k3") else "k1") if (overlap_ema and ema is not None) else False
+        if self.overlap_ema == "k2" and cfg.select != "quantile":
+            self.overlap_ema = "k1"                       # the fixed path has no K2 launch to hide behind
         self._side = torch.cuda.Stream() if self.overlap_ema else None
         self.events = {}
 
@@ -230,7 +233,13 @@ class GraphedStep:
             else:
                 stage_k3(self.state, cfg)
 
-        stages = [("k1", k1_fn), ("k2", lambda: stage_k2(self.state, cfg, group)), ("k3", k3_fn)]
+        def k2_fn():
+            if self.overlap_ema == "k2":
+                forked(lambda: stage_k2(self.state, cfg, group))
+            else:
+                stage_k2(self.state, cfg, group)
+
+        stages = [("k1", k1_fn), ("k2", k2_fn), ("k3", k3_fn)]
         if ema is not None and not self.overlap_ema:
             stages.append(("k4", self._ema))
         from . import dist as _dist
