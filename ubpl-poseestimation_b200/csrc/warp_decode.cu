@@ -1111,8 +1111,8 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
                                    int img_h, int img_w, float stride, float sigma, int S, float* mean, double* dist,
                                    uint8_t* legal, uint8_t* enable, float* gate, int64_t* stats, int32_t* ws,
                                    int64_t ws_bytes, void* stream) {
-  UBPL_REQUIRE(maps && theta && out_xy && ws, "ubpl_warp_decode_k2: NULL pointer");
   UBPL_REQUIRE(V >= 1 && V <= 32 && B >= 0 && J >= 1 && H > 0 && W > 0, "ubpl_warp_decode_k2: bad dims V=%d B=%d J=%d H=%d W=%d (1 <= V <= 32)", V, B, J, H, W);
+  UBPL_REQUIRE(ws && (B == 0 || (maps && theta && out_xy)), "ubpl_warp_decode_k2: NULL pointer");
   UBPL_REQUIRE(refine >= 0 && refine <= 2, "ubpl_warp_decode_k2: refine must be 0, 1 or 2");
   UBPL_REQUIRE(k2_mode >= 1 && k2_mode <= 4, "ubpl_warp_decode_k2: k2_mode must be 1, 2 (one teacher) or 3, 4 (two teachers)");
   UBPL_REQUIRE(k2_mode < 3 || (V % 2 == 0), "ubpl_warp_decode_k2: two teachers need an even number of maps per key point (V = 2K)");
