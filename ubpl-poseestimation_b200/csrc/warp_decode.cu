@@ -33,19 +33,10 @@
 #ifndef UBPL_K1_EARLY_DEFAULT
 #define UBPL_K1_EARLY_DEFAULT 0
 #endif
-#ifndef UBPL_K1_SPLIT_DEFAULT
-#define UBPL_K1_SPLIT_DEFAULT 0
-#endif
 
 namespace ubpl {
 
 unsigned long long* work_counter(cudaStream_t stream);   // api.cu: a zeroed device counter for this launch
-
-__device__ __forceinline__ unsigned long long globaltimer_ns_wd() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
 // K2 fused into the K1 epilogue (mean-teacher path, M = 1): every map that finishes bumps the arrival
 // counter of its (sample, joint); the warp that brings it to K (all views decoded) computes the dispersion
@@ -89,9 +80,6 @@ struct WDParams {
   unsigned long long* work;   // global claim counter (zeroed before the launch)
   int* slow_list;             // [V*B*J] queue of maps left to the exhaustive decode (NULL: decode in place)
   unsigned* slow_count;
-  // split variant (scan_kernel + decode_kernel running side by side, see below)
-  unsigned long long* rec;    // [2 * V*B*J] per-map hand-off words scan -> decode, zero before the launch
-  unsigned long long* dec_claim;   // claim counter of the decode kernel
   K2Fuse k2;                  // optional K2 epilogue run by the warp that decodes the last view of a (sample, joint)
 };
 
@@ -535,8 +523,6 @@ struct PassA {
   float bv; int bi;                  // warp-uniform source maximum and its first flat index
   float lane_max, lane_max2; int bq; // this lane's best / second-best float4 maximum and the best one's index
   float a, bb, d, e, c0, f0, C00, C01, C10, C11;   // approximate pixel-space affine and its inverse (boxes only)
-  bool have_m2;                      // split kernels: the per-lane maxima are summarised by M2 (see scan_kernel)
-  float M2;                          // largest float4 maximum that is not (a lane's best float4 AND inside the window)
 };
 
 // Phases L, B and C (see the header comment) on a source view.  On return: `exhaustive` asks for the
@@ -642,7 +628,7 @@ __device__ __forceinline__ void decode_late(const WDParams& p, const Src& S, con
       const int w4 = W >> 2;
       const int qy = A.bq / w4, qx = (A.bq - qy * w4) << 2;
       const bool in_win = (qy >= S.y0) & (qy < S.y1) & (qx >= S.x0) & (qx + 3 < S.x1);
-      const bool bad = A.have_m2 ? (A.M2 >= T) : ((A.lane_max2 >= T) || ((A.lane_max >= T) && !in_win));
+      const bool bad = (A.lane_max2 >= T) || ((A.lane_max >= T) && !in_win);
       if (__any_sync(0xffffffffu, bad)) { miss = true; return; }
       const float* win = S.base + S.y0 * S.ld + S.x0;                   // the window's own storage, row stride ld
       const int wq = (S.x1 - S.x0) >> 2, nwq = wq * (S.y1 - S.y0);
@@ -800,7 +786,6 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     Xform X;
     X.H = H; X.W = W; X.flip = false;
     PassA A;
-    A.have_m2 = false; A.M2 = 0.f;
     A.a = A.bb = A.d = A.e = A.c0 = A.f0 = A.C00 = A.C01 = A.C10 = A.C11 = 0.f;
     bool bad_xform = false;
     double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
@@ -927,202 +912,6 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     atomicAdd(p.stats + 1, n_eval);
     atomicAdd(p.stats + 2, n_maps);
     atomicAdd(p.stats + 3, n_miss);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Split variant: the main kernel above is bound by the dependent instruction chain of a map with only 14 warps
-// per SM (one 16 KB staging buffer each).  Here the map's two halves of work run in two kernels side by side on
-// every SM: scan_kernel keeps the staging buffers and does only pass A (lean, few registers, 14 warps), and
-// decode_kernel -- no staging buffer, a 1 KB window per warp, 12 more warps per SM -- does phases L/B/C, the
-// epilogue and the K2 hand-off.  Per map the scan leaves two self-flagging 64-bit words in global memory:
-//   word0 = (arg-max index | 2^31) << 32 | bits(max)          word1 = (flags | 1) << 32 | bits(M2)
-// where M2 is the largest float4 maximum that is not (some lane's best float4 AND inside the 16 x 16 window around
-// the arg-max): "M2 >= T" is exactly the per-lane test of the early-release variant, so the decode can tell
-// from two words whether the window suffices.  The decode claims maps in index order, waits for the map's words,
-// pulls the window out of the map in L2 (the scan's TMA copy just went through it) and proceeds like the
-// early-release variant; window misses (1.2 %) repeat on the map in global memory.  The scan never waits for
-// the decode, so the pair cannot deadlock whatever the launch order; the decode's wait has a time-out.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kDecWarps = 12;
-
-__global__ void __launch_bounds__(512, 1) scan_kernel(const WDParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = p.H, W = p.W, HW = H * W;
-  const uint32_t map_bytes = (uint32_t)HW * 4u;
-  const uint32_t buf_stride = (map_bytes + 127u) & ~127u;
-  float* buf0 = reinterpret_cast<float*>(smem_raw + (size_t)warp * buf_stride);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warps * buf_stride) + warp;
-  const long long N = (long long)p.V * p.B * p.J;
-  uint64_t pol = 0;
-  unsigned long long claim_reg = 0;
-  auto claim_issue = [&]() {
-    if (lane == 0) claim_reg = atomicAdd(p.work, 1ull);
-  };
-  auto claim_get = [&]() -> long long { return (long long)__shfl_sync(0xffffffffu, claim_reg, 0); };
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-    pol = l2_evict_first_policy();
-  }
-  __syncwarp();
-  claim_issue();
-  long long cur = claim_get();
-  if (lane == 0 && cur < N) issue_map(p, cur, buf0, bar, pol, map_bytes);
-  claim_issue();
-  unsigned long long n_maps = 0;
-  const int w4 = W >> 2;
-  for (long long it = 0;; ++it) {
-    const long long n = cur;
-    if (n >= N) break;
-    mbar_wait(bar, (uint32_t)(it & 1));
-    ++n_maps;
-    float bv, bv2, mn; int bq;
-    scan_max<true>(buf0, HW, lane, bv, bq, bv2, mn);
-    const float lane_max = bv, lane_max2 = bv2;
-    int bi = 0x7fffffff;
-    if (bv > -INFINITY) {
-      const float4 x = reinterpret_cast<const float4*>(buf0)[bq];
-      bi = (bq << 2) + ((x.x == bv) ? 0 : (x.y == bv) ? 1 : (x.z == bv) ? 2 : 3);
-    }
-    const bool nonfinite = __any_sync(0xffffffffu, !(mn >= -FLT_MAX) || !(bv <= FLT_MAX));
-    warp_argmax(bv, bi);
-    // the staging buffer is free: start the next copy before the (short) tail of this map
-    __syncwarp();
-    const long long nn = claim_get();
-    if (lane == 0 && nn < N) issue_map(p, nn, buf0, bar, pol, map_bytes);
-    if (nn < N) claim_issue();
-    float M2 = INFINITY;
-    if (!nonfinite && bi != 0x7fffffff) {
-      unsigned biy, bix;
-      p.divW.divmod((unsigned)bi, biy, bix);
-      const int wx0 = (((int)bix - 6) >> 2) << 2, wy0 = (int)biy - 7;
-      const int qy = bq / w4, qx = (bq - qy * w4) << 2;
-      const bool in_win = (qy >= wy0) & (qy < wy0 + kWin) & (qx >= wx0) & (qx + 3 < wx0 + kWin);
-      M2 = warp_max(fmaxf(lane_max2, in_win ? -INFINITY : lane_max));
-    }
-    if (lane == 0) {
-      const unsigned long long w0 = ((unsigned long long)((unsigned)bi | 0x80000000u) << 32) | __float_as_uint(bv);
-      const unsigned long long w1 = ((unsigned long long)((nonfinite ? 2u : 0u) | 1u) << 32) | __float_as_uint(M2);
-      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p.rec + 2 * n), "l"(w0) : "memory");
-      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p.rec + 2 * n + 1), "l"(w1) : "memory");
-    }
-    cur = nn;
-  }
-  if (p.stats && lane == 0 && n_maps) atomicAdd(p.stats + 2, n_maps);
-}
-
-__global__ void __launch_bounds__(kDecWarps * 32, 1) decode_kernel(const WDParams p) {
-  __shared__ __align__(16) float s_win[kDecWarps][kWin * kWin];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = p.H, W = p.W;
-  const long long N = (long long)p.V * p.B * p.J;
-  float* winbuf = s_win[warp];
-  unsigned long long claim_reg = 0;
-  auto claim_issue = [&]() {
-    if (lane == 0) claim_reg = atomicAdd(p.dec_claim, 1ull);
-  };
-  auto claim_get = [&]() -> long long { return (long long)__shfl_sync(0xffffffffu, claim_reg, 0); };
-  claim_issue();
-  long long cur = claim_get();
-  claim_issue();
-  unsigned long long n_slow = 0, n_eval = 0, n_miss = 0;
-  long long pend_item = -1;
-  unsigned pend_old = 0;
-  bool failed = false;
-  while (cur < N && !failed) {
-    const long long n = cur;
-    unsigned vbu, ju, vu, bu;
-    p.divJ.divmod((unsigned)n, vbu, ju);
-    p.divB.divmod(vbu, vu, bu);
-    const int j = (int)ju, b = (int)bu;
-    const float* gsrc = p.maps + (long long)vu * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
-    // transform set-up first: its global loads overlap the wait for the scan
-    Xform X;
-    PassA A;
-    A.have_m2 = true; A.lane_max = INFINITY; A.lane_max2 = INFINITY; A.bq = 0;
-    double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
-    if (p.dec) { const double* c = p.dec + (size_t)b * 4; dc0 = c[0]; dc1 = c[1]; dc2 = c[2]; dc3 = c[3]; }
-    load_xform(X, p.theta, p.flip, (long long)vbu, H, W);
-    X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
-    A.a = X.t00 * X.stepx * X.sfx; A.bb = X.t01 * X.stepy * X.sfx;
-    A.d = X.t10 * X.stepx * X.sfy; A.e = X.t11 * X.stepy * X.sfy;
-    A.c0 = (X.t02 + 1.f - X.t00 - X.t01) * X.sfx; A.f0 = (X.t12 + 1.f - X.t10 - X.t11) * X.sfy;
-    const float det = A.a * A.e - A.bb * A.d;
-    const float nrm = fabsf(A.a) + fabsf(A.bb) + fabsf(A.d) + fabsf(A.e);
-    const bool bad_xform = !(fabsf(det) > 1e-5f * nrm * nrm) || !(nrm < 1e4f) || W <= 1 || H <= 1;
-    const float idet = 1.f / det;
-    A.C00 = A.e * idet; A.C01 = -A.bb * idet; A.C10 = -A.d * idet; A.C11 = A.a * idet;
-    // the scan's two words for this map
-    unsigned long long w0 = 0, w1 = 0;
-    if (lane == 0) {
-      const unsigned long long t0 = globaltimer_ns_wd();
-      for (;;) {
-        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w1) : "l"(p.rec + 2 * n + 1) : "memory");
-        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w0) : "l"(p.rec + 2 * n) : "memory");
-        if (w0 != 0ull && w1 != 0ull) break;
-        if (globaltimer_ns_wd() - t0 > 2000000000ull) { w1 = 0ull; break; }     // 2 s: the scan never produced it
-        __nanosleep(200);
-      }
-    }
-    w0 = __shfl_sync(0xffffffffu, w0, 0);
-    w1 = __shfl_sync(0xffffffffu, w1, 0);
-    if (w1 == 0ull) { failed = true; break; }
-    A.bv = __uint_as_float((unsigned)(w0 & 0xffffffffull));
-    A.bi = (int)((unsigned)(w0 >> 32) & 0x7fffffffu);
-    A.M2 = __uint_as_float((unsigned)(w1 & 0xffffffffull));
-    const bool nonfinite = ((unsigned)(w1 >> 32) & 2u) != 0u;
-    float rv = A.bv; int ri = A.bi;
-    bool exhaustive = nonfinite || bad_xform, deferred = false;
-    if (!exhaustive) {
-      // the window around the arg-max texel, out of the map in L2
-      unsigned biy, bix;
-      p.divW.divmod((unsigned)A.bi, biy, bix);
-      Src win;
-      win.ld = kWin;
-      win.x0 = (((int)bix - 6) >> 2) << 2;
-      win.y0 = (int)biy - 7;
-      win.x1 = win.x0 + kWin; win.y1 = win.y0 + kWin;
-      win.base = winbuf - (win.y0 * kWin + win.x0);
-      __syncwarp();
-      const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-#pragma unroll
-      for (int t = lane; t < kWin * kWin / 4; t += 32) {
-        const int r = t >> 2, c4 = t & 3;
-        const int y = win.y0 + r, x = win.x0 + (c4 << 2);
-        float4 v = ninf;
-        if (y >= 0 && y < H && x >= 0 && x + 3 < W) v = __ldcg(reinterpret_cast<const float4*>(gsrc + y * W + x));
-        reinterpret_cast<float4*>(winbuf)[t] = v;
-      }
-      __syncwarp();
-      bool miss = false;
-      decode_late<true>(p, win, X, A, lane, rv, ri, exhaustive, miss, n_eval);
-      if (miss) {
-        ++n_miss;
-        exhaustive = false; miss = false;
-        const Src full = {gsrc, W, 0, 0, W, H};
-        decode_late<false>(p, full, X, A, lane, rv, ri, exhaustive, miss, n_eval);   // lane_max = +inf: every class is rescanned
-      }
-    }
-    if (exhaustive) {
-      if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = (int)n;
-      deferred = true;
-      ++n_slow;
-    }
-    if (!deferred) {
-      k2_resolve(p, pend_item, pend_old, lane);
-      finish_map(p, n, (int)vu, b, j, gsrc, X, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
-    }
-    __syncwarp();
-    cur = claim_get();
-    if (cur < N) claim_issue();
-  }
-  k2_resolve(p, pend_item, pend_old, lane);
-  if (p.stats && lane == 0) {
-    if (n_slow) atomicAdd(p.stats + 0, n_slow);
-    if (n_eval) atomicAdd(p.stats + 1, n_eval);
-    if (n_miss || failed) atomicAdd(p.stats + 3, n_miss + (failed ? (1ull << 40) : 0ull));
   }
 }
 
@@ -1270,44 +1059,6 @@ static int launch_k1(WDParams& p, cudaStream_t stream) {
   }
   long long need = (N + warps - 1) / warps;
   int grid = (int)(need < sm_count() ? need : sm_count());
-  //   UBPL_K1_SPLIT  1 = pass A and the rest of the decode in two kernels that share every SM (scan_kernel +
-  //                  decode_kernel); needs the hand-off words of the fused entry's workspace
-  const bool split = p.rec && p.use_bulk && p.do_warp && (W % 4 == 0) && W >= 4 && !early &&
-                     env_int("UBPL_K1_SPLIT", UBPL_K1_SPLIT_DEFAULT) != 0;
-  if (split) {
-    // shared memory of one SM must hold the scan CTA (one staging buffer per warp) AND the decode CTA's windows
-    const int dec_smem = kDecWarps * kWin * kWin * 4 + 2048;
-    int sw = (int)(((size_t)smem_optin() - 1024 - dec_smem) / (buf_stride + 8));
-    if (sw > 16) sw = 16;
-    if (env_warps > 0 && env_warps < sw) sw = env_warps;
-    if (sw >= 1) {
-      static cudaStream_t side = nullptr;
-      static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-      if (!side) {
-        if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
-          set_error("ubpl_warp_decode: cannot create the side stream of the split variant");
-          return UBPL_ERR_CUDA;
-        }
-        cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
-      }
-      const size_t ssmem = (size_t)sw * buf_stride + (size_t)sw * 8;
-      long long sneed = (N + sw - 1) / sw;
-      const int sgrid = (int)(sneed < sm_count() ? sneed : sm_count());
-      long long dneed = (N + kDecWarps - 1) / kDecWarps;
-      const int dgrid = (int)(dneed < sm_count() ? dneed : sm_count());
-      cudaEventRecord(ev_fork, stream);
-      cudaStreamWaitEvent(side, ev_fork, 0);
-      scan_kernel<<<sgrid, sw * 32, ssmem, stream>>>(p);
-      decode_kernel<<<dgrid, kDecWarps * 32, 0, side>>>(p);
-      cudaEventRecord(ev_join, side);
-      cudaStreamWaitEvent(stream, ev_join, 0);
-      int rc2 = check_launch("ubpl_warp_decode(split)");
-      if (rc2 != UBPL_OK) return rc2;
-      return launch_slow(p, map_bytes, stream);
-    }
-  }
   if (early) warp_decode_kernel<true><<<grid, warps * 32, smem, stream>>>(p);
   else warp_decode_kernel<false><<<grid, warps * 32, smem, stream>>>(p);
   int rc = check_launch("ubpl_warp_decode");
@@ -1342,14 +1093,12 @@ extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64
   return launch_k1(p, (cudaStream_t)stream);
 }
 
-// Workspace of ubpl_warp_decode_k2, int32 words: [0,1] claim counter, [32] queue length, [64,65] claim counter
-// of the decode kernel (own 128-byte lines), [128, 128+J+2) counts, then the B*J arrival counters, the V*B*J 64-bit
-// K2 hand-off words, the 2*V*B*J 64-bit scan->decode words of the split variant, and last the queue of V*B*J map
-// indices.  Everything in front of the queue is cleared by ONE memset node per launch.
+// Workspace of ubpl_warp_decode_k2, int32 words: [0,1] claim counter, [32] queue length (own 128-byte lines),
+// [128, 128+J+2) counts, then the B*J arrival counters, the V*B*J 64-bit hand-off words, and last the queue of
+// V*B*J map indices.  Everything in front of the queue is cleared by ONE memset node per launch.
 static inline long long k2_ws_arrive_off(int J) { return 128 + ((J + 2 + 1) & ~1); }
 static inline long long k2_ws_slots_off(int B, int J) { return (k2_ws_arrive_off(J) + (long long)B * J + 1) & ~1ll; }
-static inline long long k2_ws_rec_off(int V, int B, int J) { return k2_ws_slots_off(B, J) + 2ll * V * B * J; }
-static inline long long k2_ws_zero_words(int V, int B, int J) { return k2_ws_rec_off(V, B, J) + 4ll * V * B * J; }
+static inline long long k2_ws_zero_words(int V, int B, int J) { return k2_ws_slots_off(B, J) + 2ll * V * B * J; }
 
 extern "C" int64_t ubpl_warp_decode_k2_ws_bytes(int V, int B, int J) {
   if (V < 0 || B < 0 || J < 0) return 0;
@@ -1367,7 +1116,7 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
   UBPL_REQUIRE(refine >= 0 && refine <= 2, "ubpl_warp_decode_k2: refine must be 0, 1 or 2");
   UBPL_REQUIRE(k2_mode >= 1 && k2_mode <= 4, "ubpl_warp_decode_k2: k2_mode must be 1, 2 (one teacher) or 3, 4 (two teachers)");
   UBPL_REQUIRE(k2_mode < 3 || (V % 2 == 0), "ubpl_warp_decode_k2: two teachers need an even number of maps per key point (V = 2K)");
-  UBPL_REQUIRE((k2_mode & 1) || (gate && S >= 1 && stride > 0.f && sigma > 0.f), "ubpl_warp_decode_k2: modes 2 and 4 need gate, S, stride, sigma");
+  UBPL_REQUIRE((k2_mode & 1) || ((gate || B == 0) && S >= 1 && stride > 0.f && sigma > 0.f), "ubpl_warp_decode_k2: modes 2 and 4 need gate, S, stride, sigma");
   UBPL_REQUIRE(ws_bytes >= ubpl_warp_decode_k2_ws_bytes(V, B, J), "ubpl_warp_decode_k2: workspace too small");
   UBPL_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "ubpl_warp_decode_k2: workspace must be 8-byte aligned");
   const long long zero_words = k2_ws_zero_words(V, B, J);
@@ -1384,8 +1133,6 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
   p.work = reinterpret_cast<unsigned long long*>(ws);
   p.slow_count = reinterpret_cast<unsigned*>(ws + 32);
   p.slow_list = ws + zero_words;
-  p.dec_claim = reinterpret_cast<unsigned long long*>(ws + 64);
-  p.rec = reinterpret_cast<unsigned long long*>(ws + k2_ws_rec_off(V, B, J));
   K2Fuse& f = p.k2;
   f.mode = k2_mode; f.K = V;
   f.counts = ws + 128;
