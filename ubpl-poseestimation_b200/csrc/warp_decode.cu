@@ -1291,11 +1291,12 @@ static int launch_k1(WDParams& p, cudaStream_t stream) {
   //   UBPL_K1_WS     1 = warp-specialised kernel (12 scan + 12 decode warps per SM); needs a queue for the exhaustive maps
   const size_t ws_smem = (size_t)kWsScan * buf_stride + (size_t)kWsRing * kWsRecBytes + (size_t)kWsScan * 8;
   const bool wspec = p.slow_list && p.use_bulk && p.do_warp && (W % 4 == 0) && W >= 4 && H >= 1 && !early && N < (1ll << 31) &&
-                     ws_smem <= (size_t)smem_optin() && env_int("UBPL_K1_WS", UBPL_K1_WS_DEFAULT) != 0;
+                     ws_smem + 1024 <= (size_t)smem_optin() && env_int("UBPL_K1_WS", UBPL_K1_WS_DEFAULT) != 0;
   if (wspec) {
     static bool ws_attr = false;
     if (!ws_attr) {
-      cudaError_t e = cudaFuncSetAttribute(warp_decode_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+      // the kernel also has a few hundred bytes of static shared memory (ring state)
+      cudaError_t e = cudaFuncSetAttribute(warp_decode_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin() - 1024);
       if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute(ws): %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
       ws_attr = true;
     }
