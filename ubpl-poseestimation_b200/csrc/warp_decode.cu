@@ -33,9 +33,6 @@
 #ifndef UBPL_K1_EARLY_DEFAULT
 #define UBPL_K1_EARLY_DEFAULT 0
 #endif
-#ifndef UBPL_K1_WS_DEFAULT
-#define UBPL_K1_WS_DEFAULT 0
-#endif
 
 namespace ubpl {
 
@@ -526,8 +523,6 @@ struct PassA {
   float bv; int bi;                  // warp-uniform source maximum and its first flat index
   float lane_max, lane_max2; int bq; // this lane's best / second-best float4 maximum and the best one's index
   float a, bb, d, e, c0, f0, C00, C01, C10, C11;   // approximate pixel-space affine and its inverse (boxes only)
-  bool have_m2;                      // warp-specialised kernel: the per-lane maxima are summarised by M2
-  float M2;                          // largest float4 maximum that is not (a lane's best float4 AND inside the window)
 };
 
 // Phases L, B and C (see the header comment) on a source view.  On return: `exhaustive` asks for the
@@ -633,7 +628,7 @@ __device__ __forceinline__ void decode_late(const WDParams& p, const Src& S, con
       const int w4 = W >> 2;
       const int qy = A.bq / w4, qx = (A.bq - qy * w4) << 2;
       const bool in_win = (qy >= S.y0) & (qy < S.y1) & (qx >= S.x0) & (qx + 3 < S.x1);
-      const bool bad = A.have_m2 ? (A.M2 >= T) : ((A.lane_max2 >= T) || ((A.lane_max >= T) && !in_win));
+      const bool bad = (A.lane_max2 >= T) || ((A.lane_max >= T) && !in_win);
       if (__any_sync(0xffffffffu, bad)) { miss = true; return; }
       const float* win = S.base + S.y0 * S.ld + S.x0;                   // the window's own storage, row stride ld
       const int wq = (S.x1 - S.x0) >> 2, nwq = wq * (S.y1 - S.y0);
@@ -791,7 +786,6 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     Xform X;
     X.H = H; X.W = W; X.flip = false;
     PassA A;
-    A.have_m2 = false; A.M2 = 0.f;
     A.a = A.bb = A.d = A.e = A.c0 = A.f0 = A.C00 = A.C01 = A.C10 = A.C11 = 0.f;
     bool bad_xform = false;
     double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
@@ -919,229 +913,6 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     atomicAdd(p.stats + 2, n_maps);
     atomicAdd(p.stats + 3, n_miss);
   }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Warp-specialised variant.  warp_decode_kernel is bound by the dependent instruction chain of a map with only 14
-// warps per SM (one 16 KB staging buffer each).  Here a CTA has 24 warps in two roles:
-//   scan warps   (12, 56 registers each after setmaxnreg.dec): own the staging buffers, do pass A, copy the
-//                16 x 16 window around the arg-max texel plus a 32-byte header into a ring of records in shared
-//                memory, and hand their buffer to the next TMA copy;
-//   decode warps (12, 104 registers each after setmaxnreg.inc): take records from the ring and do phases L/B/C on
-//                the window, the epilogue and the K2 hand-off; window misses (~1 %) repeat on the map in global
-//                memory (L2).
-// The header carries M2, the largest float4 maximum that is not (some lane's best float4 AND inside the window):
-// "M2 >= T" is exactly the per-lane window test of the early-release variant.  The ring is a bounded
-// multi-producer / multi-consumer queue with per-slot sequence numbers (slot s is free for ticket t when
-// seq[s] == t, full when seq[s] == t + 1, and freed for ticket t + R by its consumer); all waits are on shared
-// memory, inside one CTA, with a time-out that poisons the launch instead of hanging it.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kWsScan = 12, kWsDecode = 12, kWsRing = 32;
-constexpr int kWsRecBytes = kWin * kWin * 4 + 32;        // window + header
-
-struct WsHeader { int n; float bv; int bi; float M2; int flags; int pad[3]; };
-
-__device__ __forceinline__ unsigned ld_shared_volatile(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
-
-__global__ void __launch_bounds__((kWsScan + kWsDecode) * 32, 1) warp_decode_ws_kernel(const WDParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ unsigned s_seq[kWsRing];
-  __shared__ unsigned s_head, s_tail, s_scan_done, s_fail;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = p.H, W = p.W, HW = H * W;
-  const uint32_t map_bytes = (uint32_t)HW * 4u;
-  const uint32_t buf_stride = (map_bytes + 127u) & ~127u;
-  unsigned char* ring = smem_raw + (size_t)kWsScan * buf_stride;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)kWsRing * kWsRecBytes);
-  const long long N = (long long)p.V * p.B * p.J;
-  if (threadIdx.x < kWsRing) s_seq[threadIdx.x] = threadIdx.x;
-  if (threadIdx.x == 0) { s_head = 0u; s_tail = 0u; s_scan_done = 0u; s_fail = 0u; }
-  __syncthreads();
-  const long long t_start = clock64();
-  const long long kTimeout = 4000000000ll;                 // ~2 s of SM clocks
-
-  if (warp < kWsScan) {
-    // ================================ scan warps ================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    float* buf0 = reinterpret_cast<float*>(smem_raw + (size_t)warp * buf_stride);
-    uint64_t* bar = bars + warp;
-    uint64_t pol = 0;
-    unsigned long long claim_reg = 0;
-    auto claim_issue = [&]() {
-      if (lane == 0) claim_reg = atomicAdd(p.work, 1ull);
-    };
-    auto claim_get = [&]() -> long long { return (long long)__shfl_sync(0xffffffffu, claim_reg, 0); };
-    if (lane == 0) {
-      mbar_init(bar, 1);
-      fence_mbar_init();
-      pol = l2_evict_first_policy();
-    }
-    __syncwarp();
-    claim_issue();
-    long long cur = claim_get();
-    if (lane == 0 && cur < N) issue_map(p, cur, buf0, bar, pol, map_bytes);
-    claim_issue();
-    unsigned long long n_maps = 0;
-    const int w4 = W >> 2;
-    bool failed = false;
-    for (long long it = 0; !failed; ++it) {
-      const long long n = cur;
-      if (n >= N) break;
-      mbar_wait(bar, (uint32_t)(it & 1));
-      ++n_maps;
-      float bv, bv2, mn; int bq;
-      scan_max<true>(buf0, HW, lane, bv, bq, bv2, mn);
-      const float lane_max = bv, lane_max2 = bv2;
-      int bi = 0x7fffffff;
-      if (bv > -INFINITY) {
-        const float4 x = reinterpret_cast<const float4*>(buf0)[bq];
-        bi = (bq << 2) + ((x.x == bv) ? 0 : (x.y == bv) ? 1 : (x.z == bv) ? 2 : 3);
-      }
-      const bool nonfinite = __any_sync(0xffffffffu, !(mn >= -FLT_MAX) || !(bv <= FLT_MAX));
-      warp_argmax(bv, bi);
-      int wx0 = 0, wy0 = 0;
-      float M2 = INFINITY;
-      const bool usable = !nonfinite && bi != 0x7fffffff;
-      if (usable) {
-        unsigned biy, bix;
-        p.divW.divmod((unsigned)bi, biy, bix);
-        wx0 = (((int)bix - 6) >> 2) << 2; wy0 = (int)biy - 7;
-        const int qy = bq / w4, qx = (bq - qy * w4) << 2;
-        const bool in_win = (qy >= wy0) & (qy < wy0 + kWin) & (qx >= wx0) & (qx + 3 < wx0 + kWin);
-        M2 = warp_max(fmaxf(lane_max2, in_win ? -INFINITY : lane_max));
-      }
-      // a free record
-      unsigned t = 0;
-      if (lane == 0) {
-        t = atomicAdd(&s_head, 1u);
-        while (ld_shared_volatile(&s_seq[t % kWsRing]) != t) {
-          if (clock64() - t_start > kTimeout) { s_fail = 1u; break; }
-          __nanosleep(32);
-        }
-      }
-      t = __shfl_sync(0xffffffffu, t, 0);
-      if (ld_shared_volatile(&s_fail)) { failed = true; break; }
-      unsigned char* rec = ring + (size_t)(t % kWsRing) * kWsRecBytes;
-      if (usable) {
-        const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-#pragma unroll
-        for (int q = lane; q < kWin * kWin / 4; q += 32) {
-          const int r = q >> 2, c4 = q & 3;
-          const int y = wy0 + r, x = wx0 + (c4 << 2);
-          float4 v = ninf;
-          if (y >= 0 && y < H && x >= 0 && x + 3 < W) v = *reinterpret_cast<const float4*>(buf0 + y * W + x);
-          reinterpret_cast<float4*>(rec)[q] = v;
-        }
-      }
-      if (lane == 0) {
-        WsHeader* h = reinterpret_cast<WsHeader*>(rec + kWin * kWin * 4);
-        h->n = (int)n; h->bv = bv; h->bi = bi; h->M2 = M2; h->flags = nonfinite ? 1 : 0;
-      }
-      __syncwarp();
-      __threadfence_block();
-      if (lane == 0) *reinterpret_cast<volatile unsigned*>(&s_seq[t % kWsRing]) = t + 1u;     // publish
-      // the staging buffer is free
-      const long long nn = claim_get();
-      if (lane == 0 && nn < N) issue_map(p, nn, buf0, bar, pol, map_bytes);
-      if (nn < N) claim_issue();
-      cur = nn;
-    }
-    __syncwarp();
-    if (lane == 0) { __threadfence_block(); atomicAdd(&s_scan_done, 1u); }
-    if (p.stats && lane == 0 && n_maps) atomicAdd(p.stats + 2, n_maps);
-  } else {
-    // ================================ decode warps ================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    unsigned long long n_slow = 0, n_eval = 0, n_miss = 0;
-    long long pend_item = -1;
-    unsigned pend_old = 0;
-    for (;;) {
-      unsigned c = 0;
-      int got = 0;
-      if (lane == 0) {
-        c = atomicAdd(&s_tail, 1u);
-        for (;;) {
-          if (ld_shared_volatile(&s_seq[c % kWsRing]) == c + 1u) { got = 1; break; }
-          if (ld_shared_volatile(&s_scan_done) == (unsigned)kWsScan) {
-            // every scan warp has left its loop: s_head is final
-            if ((int)(c - ld_shared_volatile(&s_head)) >= 0) break;
-          }
-          if (ld_shared_volatile(&s_fail)) break;
-          if (clock64() - t_start > kTimeout) { s_fail = 1u; break; }
-          __nanosleep(32);
-        }
-      }
-      c = __shfl_sync(0xffffffffu, c, 0);
-      got = __shfl_sync(0xffffffffu, got, 0);
-      if (!got) break;
-      __threadfence_block();
-      const unsigned char* rec = ring + (size_t)(c % kWsRing) * kWsRecBytes;
-      const WsHeader* h = reinterpret_cast<const WsHeader*>(rec + kWin * kWin * 4);
-      const long long n = (long long)h->n;
-      PassA A;
-      A.have_m2 = true; A.lane_max = INFINITY; A.lane_max2 = INFINITY; A.bq = 0;
-      A.bv = h->bv; A.bi = h->bi; A.M2 = h->M2;
-      const bool nonfinite = h->flags != 0;
-      unsigned vbu, ju, vu, bu;
-      p.divJ.divmod((unsigned)n, vbu, ju);
-      p.divB.divmod(vbu, vu, bu);
-      const int j = (int)ju, b = (int)bu;
-      const float* gsrc = p.maps + (long long)vu * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
-      Xform X;
-      double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
-      if (p.dec) { const double* cf = p.dec + (size_t)b * 4; dc0 = cf[0]; dc1 = cf[1]; dc2 = cf[2]; dc3 = cf[3]; }
-      load_xform(X, p.theta, p.flip, (long long)vbu, H, W);
-      X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
-      A.a = X.t00 * X.stepx * X.sfx; A.bb = X.t01 * X.stepy * X.sfx;
-      A.d = X.t10 * X.stepx * X.sfy; A.e = X.t11 * X.stepy * X.sfy;
-      A.c0 = (X.t02 + 1.f - X.t00 - X.t01) * X.sfx; A.f0 = (X.t12 + 1.f - X.t10 - X.t11) * X.sfy;
-      const float det = A.a * A.e - A.bb * A.d;
-      const float nrm = fabsf(A.a) + fabsf(A.bb) + fabsf(A.d) + fabsf(A.e);
-      const bool bad_xform = !(fabsf(det) > 1e-5f * nrm * nrm) || !(nrm < 1e4f) || W <= 1 || H <= 1;
-      const float idet = 1.f / det;
-      A.C00 = A.e * idet; A.C01 = -A.bb * idet; A.C10 = -A.d * idet; A.C11 = A.a * idet;
-      float rv = A.bv; int ri = A.bi;
-      bool exhaustive = nonfinite || bad_xform, deferred = false;
-      if (!exhaustive) {
-        unsigned biy, bix;
-        p.divW.divmod((unsigned)A.bi, biy, bix);
-        Src win;
-        win.ld = kWin;
-        win.x0 = (((int)bix - 6) >> 2) << 2;
-        win.y0 = (int)biy - 7;
-        win.x1 = win.x0 + kWin; win.y1 = win.y0 + kWin;
-        win.base = reinterpret_cast<const float*>(rec) - (win.y0 * kWin + win.x0);
-        bool miss = false;
-        decode_late<true>(p, win, X, A, lane, rv, ri, exhaustive, miss, n_eval);
-        if (miss) {
-          ++n_miss;
-          exhaustive = false; miss = false;
-          const Src full = {gsrc, W, 0, 0, W, H};
-          decode_late<false>(p, full, X, A, lane, rv, ri, exhaustive, miss, n_eval);   // lane_max = +inf: every class is rescanned
-        }
-      }
-      // the record is no longer needed: free its slot for ticket c + R
-      __syncwarp();
-      if (lane == 0) *reinterpret_cast<volatile unsigned*>(&s_seq[c % kWsRing]) = c + (unsigned)kWsRing;
-      if (exhaustive) {
-        if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = (int)n;
-        deferred = true;
-        ++n_slow;
-      }
-      if (!deferred) {
-        k2_resolve(p, pend_item, pend_old, lane);
-        finish_map(p, n, (int)vu, b, j, gsrc, X, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
-      }
-      __syncwarp();
-    }
-    k2_resolve(p, pend_item, pend_old, lane);
-    if (p.stats && lane == 0) {
-      if (n_slow) atomicAdd(p.stats + 0, n_slow);
-      if (n_eval) atomicAdd(p.stats + 1, n_eval);
-      if (n_miss) atomicAdd(p.stats + 3, n_miss);
-    }
-  }
-  if (threadIdx.x == 0 && p.stats && ld_shared_volatile(&s_fail)) atomicAdd(p.stats + 3, 1ull << 40);
 }
 
 // Exhaustive decode of the queued maps: one CTA of 16 warps per map (rows split sixteen ways), map staged in
@@ -1288,25 +1059,6 @@ static int launch_k1(WDParams& p, cudaStream_t stream) {
   }
   long long need = (N + warps - 1) / warps;
   int grid = (int)(need < sm_count() ? need : sm_count());
-  //   UBPL_K1_WS     1 = warp-specialised kernel (12 scan + 12 decode warps per SM); needs a queue for the exhaustive maps
-  const size_t ws_smem = (size_t)kWsScan * buf_stride + (size_t)kWsRing * kWsRecBytes + (size_t)kWsScan * 8;
-  const bool wspec = p.slow_list && p.use_bulk && p.do_warp && (W % 4 == 0) && W >= 4 && H >= 1 && !early && N < (1ll << 31) &&
-                     ws_smem + 1024 <= (size_t)smem_optin() && env_int("UBPL_K1_WS", UBPL_K1_WS_DEFAULT) != 0;
-  if (wspec) {
-    static bool ws_attr = false;
-    if (!ws_attr) {
-      // the kernel also has a few hundred bytes of static shared memory (ring state)
-      cudaError_t e = cudaFuncSetAttribute(warp_decode_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin() - 1024);
-      if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute(ws): %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
-      ws_attr = true;
-    }
-    long long wneed = (N + kWsScan - 1) / kWsScan;
-    const int wgrid = (int)(wneed < sm_count() ? wneed : sm_count());
-    warp_decode_ws_kernel<<<wgrid, (kWsScan + kWsDecode) * 32, ws_smem, stream>>>(p);
-    int rcw = check_launch("ubpl_warp_decode(ws)");
-    if (rcw != UBPL_OK) return rcw;
-    return launch_slow(p, map_bytes, stream);
-  }
   if (early) warp_decode_kernel<true><<<grid, warps * 32, smem, stream>>>(p);
   else warp_decode_kernel<false><<<grid, warps * 32, smem, stream>>>(p);
   int rc = check_launch("ubpl_warp_decode");
