@@ -184,9 +184,10 @@ extern "C" int ubpl_acc_pck(const float* preds, int p_stride, const float* gts, 
 
 extern "C" int ubpl_view_kps(const float* kps, const double* mats, const uint8_t* flips, float img_w, int V, int B, int J,
                              float* out, void* stream) {
-  UBPL_REQUIRE(kps && mats && out && V >= 0 && B >= 0 && J >= 0, "ubpl_view_kps: bad arguments");
+  UBPL_REQUIRE(V >= 0 && B >= 0 && J >= 0, "ubpl_view_kps: bad dims");
   const long long n = (long long)V * B * J;
   if (n == 0) return UBPL_OK;
+  UBPL_REQUIRE(kps && mats && out, "ubpl_view_kps: NULL pointer");
   view_kps_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kps, mats, flips, img_w, V, B, J, out);
   return check_launch("ubpl_view_kps");
 }

@@ -747,8 +747,9 @@ extern "C" int ubpl_mix_dists(const float* gt, int gt_stride, int ref0, int ref1
                               int B, int J, int A, double* err1, double* err2, int32_t* acc1, int32_t* acc2,
                               double* score1, double* score2, double* caug1, double* caug2, double* int1, double* int2,
                               double* ext, double* aext, void* stream) {
-  UBPL_REQUIRE(p1 && p2 && a1 && a2 && caug1 && caug2 && int1 && int2 && ext && aext, "ubpl_mix_dists: NULL pointer");
   UBPL_REQUIRE(B >= 0 && J >= 1 && A >= 1, "ubpl_mix_dists: bad dims");
+  if (B == 0) return UBPL_OK;
+  UBPL_REQUIRE(p1 && p2 && a1 && a2 && caug1 && caug2 && int1 && int2 && ext && aext, "ubpl_mix_dists: NULL pointer");
   UBPL_REQUIRE(!gt || (gt_stride >= 2 && err1 && err2 && acc1 && acc2 && ref0 >= 0 && ref0 < J && ref1 >= 0 && ref1 < J),
                "ubpl_mix_dists: gt needs err/acc outputs and valid pck_ref");
   UBPL_REQUIRE((!s1 || score1) && (!s2 || score2), "ubpl_mix_dists: scores need score outputs");
