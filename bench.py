@@ -348,6 +348,19 @@ def run_ours(args):
     ee1.record()
     torch.cuda.synchronize()
     k4_ms = ee0.elapsed_time(ee1) / 20
+    # K1 on its own (no EMA beside it), measured the same way right after the timed region: what the kernel does when
+    # it has the HBM to itself
+    g1 = torch.cuda.CUDAGraph()
+    st1 = dict(gstep.state)
+    with torch.cuda.graph(g1):
+        pipeline.stage_k1(st1, None, cfg)
+    torch.cuda.synchronize()
+    ee0.record()
+    for _ in range(20):
+        g1.replay()
+    ee1.record()
+    torch.cuda.synchronize()
+    k1_alone_ms = ee0.elapsed_time(ee1) / 20
     bytes_sample = algorithmic_bytes_per_sample(c)
     k1_bytes = 4 * H * W * J * M * K * B
     k3_bytes = 4 * H * W * J * (2 * S + 1) * B
@@ -360,7 +373,8 @@ def run_ours(args):
             "stages_ms": {("k1_warp_decode_with_k4_ema_overlapped" if gstep.overlap_ema == "k1" else "k1_warp_decode"): k1_ms,
                           ("k2_uncertainty_select_with_k4_ema_overlapped" if gstep.overlap_ema == "k2" else "k2_uncertainty_select"): k2_ms,
                           ("k3_render_mse_with_k4_ema_overlapped" if gstep.overlap_ema == "k3" else "k3_render_mse"): k3_ms,
-                          "k4_ema_in_step": k4_inline_ms, "k4_ema_standalone": k4_ms},
+                          "k4_ema_in_step": k4_inline_ms, "k4_ema_standalone": k4_ms, "k1_standalone": k1_alone_ms},
+            "k1_standalone_frac": k1_bytes / (k1_alone_ms * 1e-3) / 1e9 / peak,
             "stages_note": ("stage edges are event-record nodes inside the step's single CUDA graph; mean of the last "
                             "timed step and 32 further steps" if single else
                             "stage edges are CUDA events recorded around each stage graph in every timed step"),
