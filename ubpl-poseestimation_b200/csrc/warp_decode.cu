@@ -308,9 +308,10 @@ __device__ __forceinline__ void k2_item(const WDParams& p, long long item, int j
     // is its own flag: no fence on the writer's side, a (rarely taken) spin here
     unsigned long long* sp = f.slots + ((long long)lane * BJ + item);
     unsigned long long v;
-    do {
+    int spins = 0;
+    do {                                                 // bounded: a lost word must not turn into a hung GPU
       asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(sp) : "memory");
-    } while (v == 0ull);
+    } while (v == 0ull && ++spins < (1 << 24));
     v = ~v;
     x = __uint_as_float((unsigned)(v & 0xffffffffull));
     y = __uint_as_float((unsigned)(v >> 32));
@@ -359,9 +360,10 @@ __device__ __forceinline__ void k2_item_dual(const WDParams& p, long long item, 
   if (lane < f.K) {
     unsigned long long* sp = f.slots + ((long long)lane * BJ + item);
     unsigned long long v;
+    int spins = 0;
     do {
       asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(sp) : "memory");
-    } while (v == 0ull);
+    } while (v == 0ull && ++spins < (1 << 24));
     v = ~v;
     x = __uint_as_float((unsigned)(v & 0xffffffffull));
     y = __uint_as_float((unsigned)(v >> 32));
