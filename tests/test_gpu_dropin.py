@@ -338,3 +338,31 @@ def test_view_kps(pkg):
     assert np.array_equal(hm.cpu().numpy() == 0, want_hm == 0)
     np.testing.assert_allclose(hm.cpu().numpy(), want_hm, rtol=RTOL)
     assert np.array_equal(kout.cpu().numpy(), want_k)
+
+
+def test_grouped_criteria(pkg):
+    """N4: all M*A criterion calls of a driver step in one kernel and one sync == the loop of separate calls."""
+    g = torch.Generator().manual_seed(3)
+    G, B, S, J = 6, 5, 2, 4
+    preds = (torch.rand(G, B, S, J, 32, 32, generator=g) * 0.5).cuda().requires_grad_(True)
+    tg_mse = torch.rand(G, B, J, 32, 32, generator=g).cuda()
+    tg_dist = (torch.rand(G, B, S, J, 32, 32, generator=g) * 0.5).cuda()
+    gate = (torch.rand(G, B, J, generator=g) < 0.7).float().cuda()
+    w = (torch.rand(B, 1, generator=g) < 0.6).float().cuda()
+    wts = torch.rand(G, generator=g).cuda()
+    for crit, tg in ((pkg.losses.JointMSELoss(nStack=S, useKPsGate=True, useSampleWeight=True), tg_mse),
+                     (pkg.losses.JointDistLoss(nStack=S, useKPsGate=False, useSampleWeight=True), tg_dist)):
+        sums, counts = pkg.losses.grouped(crit, preds, tg, gate, w)
+        (sums * wts).sum().backward()
+        g_batched = preds.grad.clone()
+        preds.grad = None
+        want_s, want_c = [], []
+        for k in range(G):
+            l, n = crit(preds[k], tg[k], gate[k], w)
+            want_s.append(l)
+            want_c.append(n)
+        (torch.stack(want_s) * wts).sum().backward()
+        assert counts == want_c
+        np.testing.assert_allclose(sums.detach().cpu().numpy(), torch.stack(want_s).detach().cpu().numpy(), rtol=1e-6)
+        np.testing.assert_allclose(g_batched.cpu().numpy(), preds.grad.cpu().numpy(), rtol=1e-6, atol=1e-12)
+        preds.grad = None

@@ -169,3 +169,78 @@ class JointDistLoss_mt2(nn.Module):
             raise RuntimeError("stack expects a non-empty TensorList")  # losses.py:279
         jsm = _score_mean(vt, rows, cnt).mean(0)
         return loss, self.nStack * int(host[3]), int(host[1]), int(host[2]), jsm
+
+
+# ------------------------------------------------------------------------------------------------------
+# N4: the drivers call a criterion once per (model, augmentation) and sync on every call
+# (projects/MT_UBPL.py:246-268).  `grouped` evaluates all G = M*A calls of a JointMSELoss / JointDistLoss in
+# ONE loss+gradient kernel and ONE device->host sync; it is what the loops look like once a maintainer
+# batches them, not a drop-in: the reference's drivers are unchanged without it.
+# ------------------------------------------------------------------------------------------------------
+class _GroupedLossFn(torch.autograd.Function):
+    """per-group loss sums [G] of a [G*B,S,J,H,W] prediction batch against its targets."""
+
+    @staticmethod
+    def forward(ctx, pred5, tgt, coef, gate, G):
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        r = ops.dense_mse(pred5.detach(), tgt.detach(), coef=coef, mask_mode=0, thr=0.0, want_grad=need_grad)
+        GB, S, J = r["per_loss"].shape
+        B = GB // G
+        pl = r["per_loss"].view(G, B, S, J)
+        fins = torch.stack([ops.loss_finalize(pl[g], None, None if gate is None else gate.view(G, B, J)[g]) for g in range(G)])
+        ctx.grad, ctx.G, ctx.tgt_shape = r["grad"], G, tgt.shape
+        ctx.mark_non_differentiable(fins)
+        return fins[:, 0].to(torch.float32), fins
+
+    @staticmethod
+    def backward(ctx, g_loss, unused):
+        g = ctx.grad
+        if g is None:
+            return None, None, None, None, None
+        G = ctx.G
+        gv = g.view((G, g.shape[0] // G) + tuple(g.shape[1:]))
+        out = torch.empty_like(gv)
+        scales = g_loss.detach().to(torch.float32).contiguous()
+        for k in range(G):                                   # one tiny scale launch per group, no host sync
+            ops.scale(gv[k].contiguous(), scales[k:k + 1], out=out[k])
+        out = out.view(g.shape)
+        g_pred = out if ctx.needs_input_grad[0] else None
+        g_tgt = None
+        if ctx.needs_input_grad[1]:
+            gt = -out                                        # d/dt = -d/dp
+            if len(ctx.tgt_shape) == 5:                      # [1,G*B,J,H,W]: one target shared by the stacks
+                gt = gt.sum(1)
+            g_tgt = gt.reshape(ctx.tgt_shape)
+        return g_pred, g_tgt, None, None, None
+
+
+def grouped(criterion, preds, targets, kpsGate=None, sampleWeight=None):
+    """All G calls `criterion(preds[g], targets[g], kpsGate[g], sampleWeight)` of a JointMSELoss / JointDistLoss
+    (utils/losses.py:8-53) at once.  preds [G,B,(S,)J,H,W]; targets [G,B,J,H,W] (JointMSELoss: one target per
+    sample, shared by the stacks) or [G,B,(S,)J,H,W] (JointDistLoss); kpsGate [G,B,J] or None; sampleWeight [B,1]
+    (the same for every group, as in the drivers).  Returns (sums [G] float32 with autograd, counts: list of G
+    python ints) -- the tuples the G separate calls would have returned, with one kernel and one sync."""
+    if not isinstance(criterion, (JointMSELoss, JointDistLoss)):
+        raise TypeError("grouped() batches JointMSELoss / JointDistLoss calls")
+    nS = criterion.nStack
+    G, B = preds.shape[0], preds.shape[1]
+    p5 = preds.reshape((G * B,) + tuple(preds.shape[2:]))
+    p5 = _as5(p5, nS)
+    S, J = p5.shape[1], p5.shape[2]
+    t = _tgt(targets)
+    t = t.reshape((G * B,) + tuple(t.shape[2:]))
+    if isinstance(criterion, JointMSELoss):
+        t = t.unsqueeze(0)                                   # [1,G*B,J,H,W]: shared by the stacks
+    else:
+        t = _as5(t, nS).unsqueeze(0)                         # [1,G*B,S,J,H,W]
+    gate = None if kpsGate is None else kpsGate.detach().to(device=p5.device, dtype=torch.float32).reshape(G * B, J)
+    coef = None
+    if criterion.useKPsGate and gate is not None:
+        coef = gate
+    if criterion.useSampleWeight and sampleWeight is not None:
+        w = sampleWeight.detach().to(device=p5.device, dtype=torch.float32).reshape(1, B, 1).expand(G, B, J).reshape(G * B, J)
+        coef = w if coef is None else coef * w
+    coef = None if coef is None else coef.contiguous()
+    sums, fins = _GroupedLossFn.apply(p5, t, coef, gate, G)
+    counts = [nS * int(c) for c in fins[:, 3].tolist()]      # the one device->host sync
+    return sums, counts
