@@ -332,6 +332,10 @@ def test_view_kps(pkg):
         got = pkg.aug.affine_kps(k, g["centers"][v, b].tolist(), torch.tensor(g["scales"][v, b]), [W, W],
                                  torch.tensor(g["angles"][v, b]))
         assert got.device.type == "cpu" and np.array_equal(got.numpy(), g["out"][v, b])
+    from ubpl_b200 import pipeline
+    hv, kv = pipeline.view_targets(T(g["kps"][..., :2]).cuda(), T(g["kps"][..., 2]).cuda(), T(g["mats"]).cuda(),
+                                   T(g["flips"]).cuda(), 64, 64, W, W)
+    assert hv.shape == (V, B, J, 64, 64) and np.array_equal(kv[..., :2].cpu().numpy(), g["out"][..., :2])
     # in-frame rendering: one launch for all V*B*J targets
     hm, kout = ops.render_targets(out.reshape(-1, 3), 64, 64, W, W)
     want_hm, want_k = O.kps_heatmap(g["out"].reshape(-1, 3), (3, W, W), W, 64)

@@ -177,6 +177,21 @@ def pseudo_label_step(teacher, student, theta, flip, dec, sample_w, cfg: StepCon
     return st
 
 
+def view_targets(kps, gate, mats, flips, H, W, img_h, img_w, stride=None, sigma=3.0):
+    """in-frame targets of the selected pseudo-labels for every augmented student view, on the device.
+    kps [B,J,2] canonical image coordinates (st["kps"]), gate [B,J] (st["gate"], becomes the key-point weight),
+    mats [V,B,3,3] float64 = AugmentUtils.view_matrix of each (view, sample), flips [V,B].  What Dataset.update +
+    the Dataset's own augmentation of the key points + kps_heatmap do per sample and joint on the host
+    (datasets/dataset_mds.py:14-25,98-117, utils/process.py:253-278): returns (heatmaps [V,B,J,H,W],
+    kps_view [V,B,J,3] with weight *= visibility in the view)."""
+    B, J, _ = kps.shape
+    V = mats.shape[0]
+    k3 = torch.cat([kps.to(torch.float32), gate.reshape(B, J, 1).to(torch.float32)], -1)
+    kv = ops.view_kps(k3, mats, flips, img_w)
+    hm, kout = ops.render_targets(kv.reshape(-1, 3), H, W, img_h, img_w, stride, sigma)
+    return hm.view(V, B, J, H, W), kout.view(V, B, J, 3)
+
+
 class GraphedStep:
     """The same chain captured into CUDA graphs for fixed shapes and fixed input buffers: one step is only
     ~0.2 ms of GPU time, so eager launches (plus allocator and Python work) would leave the GPU waiting for
