@@ -481,7 +481,10 @@ static int render_mse_impl(const float* kps, const float* gate_in, const float* 
   // between the warps of a CTA, so a second, partial wave of CTAs would only add a tail
   long long cap = (long long)sm_count() * (occ5 ? 5 : 6);
   if (cap > 4096) cap = 4096;             // UBPL_RENDER_SUM_WS_BYTES holds 4096 CTA partials
-  const int grid = (int)(need < cap ? need : cap);
+  // fewer items than one round of warps: a CTA per item (the kernel's cooperative phase) keeps 4 warps streaming
+  // every item instead of one, which matters when the maps are large and the items few (fly: 128x128, B*J = 1024)
+  (void)need;
+  const int grid = (int)(BJ < cap ? BJ : cap);
 #define UBPL_LAUNCH_RENDER(V, SSV)                                                                                     \
   if (occ5) render_mse_kernel<V, SSV, 5><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(                              \
       kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS, gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
