@@ -386,38 +386,3 @@ def test_empty_and_degenerate_shapes(ops):
     assert a["summary"].tolist() == [0.0, 0.0, 0.0, 0.0]
     out = ops.view_kps(torch.zeros(0, 4, 3, device="cuda"), torch.zeros(2, 0, 3, 3, dtype=torch.float64, device="cuda"), None, 256)
     assert out.shape == (2, 0, 4, 3)
-
-
-@pytest.mark.parametrize("shape", [(128, 128), (96, 128), (128, 64)])
-def test_k1_streamed_large_maps(ops, shape):
-    """Large maps go through the band-streaming kernel (two 8 KB row bands per warp, window from L2): bit-identical
-    to the whole-map staging kernel, with and without the K2 epilogue, including maps that need the exhaustive path."""
-    from ubpl_b200 import synth
-    H, W = shape
-    d = synth.make_batch(B=6, K=4, J=5, H=H, W=W, M=1, S=1, seed=H + W, jitter=0.7, device="cuda")
-    t = d["teacher"][0].clone()
-    rng = np.random.default_rng(H)
-    t[0, 0, 0] = 1.0                                        # constant map
-    t[1, 1, 1] = -torch.rand(H, W, device="cuda") - 0.1     # all negative
-    t[2, 2, 2] = torch.as_tensor(rng.standard_normal((H, W)).astype(np.float32)).cuda()      # white noise
-    t[3, 3, 3, H // 2, W // 2] = float("nan")
-    t[0, 4, 4] = 0.0; t[0, 4, 4, 0, 0] = 2.0                # peaks in the corners: the window hangs over the edge
-    t[1, 5, 0] = 0.0; t[1, 5, 0, H - 1, W - 1] = 2.0
-    t[2, 0, 1] = 0.0; t[2, 0, 1, 3, 5] = 0.5; t[2, 0, 1, H - 4, W - 9] = 0.5      # two far ties: window refused
-    dec = ops.decode_coeffs(d["center"], d["scale"], [H, W])
-    outs = {}
-    for stream in (1, 0):
-        with _Env(UBPL_K1_STREAM=stream):
-            stats = torch.zeros(4, dtype=torch.int64, device="cuda")
-            outs[stream] = (ops.warp_decode(t, d["theta"], d["flip"], dec, stats=stats),
-                            ops.warp_decode_k2(t, d["theta"], d["flip"], dec, 2, S=2, img_h=4 * H, img_w=4 * W, distThrMax=2.0),
-                            stats.cpu())
-    for k in ("idx", "xy"):
-        assert torch.equal(outs[1][0][k], outs[0][0][k]), k
-        assert torch.equal(outs[1][1][k], outs[0][1][k]), k
-    assert np.array_equal(npy(outs[1][0]["max"]), npy(outs[0][0]["max"]), equal_nan=True)
-    for k in ("mean", "dist", "legal", "enable", "gate", "counts"):
-        assert torch.equal(outs[1][1][k], outs[0][1][k]), k
-    assert int(outs[1][2][2]) == 4 * 6 * 5
-    if H * W * 4 >= 49152:
-        assert int(outs[1][2][3]) > 0 or int(outs[1][2][0]) > 0           # the streamed path ran (misses / queue are counted)

@@ -33,9 +33,6 @@
 #ifndef UBPL_K1_EARLY_DEFAULT
 #define UBPL_K1_EARLY_DEFAULT 0
 #endif
-#ifndef UBPL_K1_STREAM_DEFAULT
-#define UBPL_K1_STREAM_DEFAULT 1
-#endif
 
 namespace ubpl {
 
@@ -920,172 +917,6 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Streaming variant for LARGE maps.  A whole-map staging buffer per warp leaves only 3 warps per SM for 128 x 128
-// maps (64 KB each), and with a single buffer the 64 KB copy of the next map cannot overlap anything: the launch
-// is bound by (copy latency + decode) per buffer.  Here a warp owns a ring of two row-band buffers (kStreamBand
-// bytes each, 13 warps per SM): pass A consumes the map band by band while the TMA engine refills the band just consumed with
-// the band after next -- of the same map or of the next one -- so the copies run ahead of the scan all the
-// time.  Nothing of the map is kept in shared memory; the phases after pass A work on the 16 x 16 window
-// around the arg-max texel, pulled out of the map in L2 (the copy just went through it), exactly like the
-// early-release variant (same per-lane window test, same fall-back to the map in global memory on a miss).
-// ---------------------------------------------------------------------------------------------------
-constexpr uint32_t kStreamBand = 8192;
-
-__global__ void __launch_bounds__(512, 1) warp_decode_stream_kernel(const WDParams p, int bands) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = p.H, W = p.W;
-  const uint32_t per_warp = 2u * kStreamBand + kWin * kWin * 4u;
-  float* band0 = reinterpret_cast<float*>(smem_raw + (size_t)warp * per_warp);
-  float* winbuf = band0 + 2 * (kStreamBand >> 2);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warps * per_warp) + 2 * warp;
-  const int band_q = (int)(kStreamBand >> 4);               // float4 per band
-  const long long N = (long long)p.V * p.B * p.J;
-  uint64_t pol = 0;
-  unsigned long long claim_reg = 0;
-  auto claim_issue = [&]() {
-    if (lane == 0) claim_reg = atomicAdd(p.work, 1ull);
-  };
-  auto claim_get = [&]() -> long long { return (long long)__shfl_sync(0xffffffffu, claim_reg, 0); };
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    mbar_init(bar + 1, 1);
-    fence_mbar_init();
-    pol = l2_evict_first_policy();
-  }
-  __syncwarp();
-  // band number `g` (counted over all the maps of this warp) lives in slot g & 1 and completes phase (g >> 1) & 1
-  auto issue_band = [&](long long n, int c, unsigned g) {
-    if (lane == 0 && n < N) {
-      const float* src = map_src(p, n) + (size_t)c * (kStreamBand >> 2);
-      mbar_arrive_expect_tx(bar + (g & 1u), kStreamBand);
-      bulk_g2s(band0 + (size_t)(g & 1u) * (kStreamBand >> 2), src, kStreamBand, bar + (g & 1u), pol);
-    }
-  };
-  claim_issue();
-  long long cur = claim_get();
-  claim_issue();
-  unsigned g_issue = 0, g_take = 0;
-  issue_band(cur, 0, g_issue++);
-  if (bands > 1) issue_band(cur, 1, g_issue++);
-  unsigned long long n_slow = 0, n_eval = 0, n_maps = 0, n_miss = 0;
-  long long pend_item = -1;
-  unsigned pend_old = 0;
-  while (cur < N) {
-    const long long n = cur;
-    const long long nxt = claim_get();                     // known early: the last bands of this map are refilled with it
-    if (nxt < N) claim_issue();
-    unsigned vbu, ju, vu, bu;
-    p.divJ.divmod((unsigned)n, vbu, ju);
-    p.divB.divmod(vbu, vu, bu);
-    const int j = (int)ju, b = (int)bu;
-    const float* gsrc = p.maps + (long long)vu * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
-    Xform X;
-    PassA A;
-    double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
-    if (p.dec) { const double* cf = p.dec + (size_t)b * 4; dc0 = cf[0]; dc1 = cf[1]; dc2 = cf[2]; dc3 = cf[3]; }
-    load_xform(X, p.theta, p.flip, (long long)vbu, H, W);
-    X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
-    A.a = X.t00 * X.stepx * X.sfx; A.bb = X.t01 * X.stepy * X.sfx;
-    A.d = X.t10 * X.stepx * X.sfy; A.e = X.t11 * X.stepy * X.sfy;
-    A.c0 = (X.t02 + 1.f - X.t00 - X.t01) * X.sfx; A.f0 = (X.t12 + 1.f - X.t10 - X.t11) * X.sfy;
-    const float det = A.a * A.e - A.bb * A.d;
-    const float nrm = fabsf(A.a) + fabsf(A.bb) + fabsf(A.d) + fabsf(A.e);
-    const bool bad_xform = !(fabsf(det) > 1e-5f * nrm * nrm) || !(nrm < 1e4f) || W <= 1 || H <= 1;
-    const float idet = 1.f / det;
-    A.C00 = A.e * idet; A.C01 = -A.bb * idet; A.C10 = -A.d * idet; A.C11 = A.a * idet;
-    ++n_maps;
-
-    // ---- pass A, band by band -------------------------------------------------------------------
-    float bv = -INFINITY, bv2 = -INFINITY, mn = INFINITY;
-    int bq = 0, bi = 0x7fffffff;
-    for (int c = 0; c < bands; ++c) {
-      const unsigned slot = g_take & 1u;
-      mbar_wait(bar + slot, (g_take >> 1) & 1u);
-      const float4* s4 = reinterpret_cast<const float4*>(band0 + (size_t)slot * (kStreamBand >> 2));
-      const int q_off = c * band_q;
-      float cbv = -INFINITY; int cbq = -1;                 // this band's best float4 of the lane
-      for (int q = lane; q < band_q; q += 256) {
-        float4 x[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = s4[q + 32 * u];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float m4 = fmaxf(max3(x[u].x, x[u].y, x[u].z), x[u].w);
-          mn = min3_nan(x[u].z, x[u].w, min3_nan(x[u].x, x[u].y, mn));
-          if (m4 > bv) { bv2 = bv; bv = m4; bq = q_off + q + 32 * u; cbv = m4; cbq = q + 32 * u; }
-          else bv2 = fmaxf(bv2, m4);
-        }
-      }
-      if (cbq >= 0) {                                      // the lane's best float4 is in this band: pin the texel now
-        const float4 x = s4[cbq];
-        bi = ((q_off + cbq) << 2) + ((x.x == cbv) ? 0 : (x.y == cbv) ? 1 : (x.z == cbv) ? 2 : 3);
-      }
-      __syncwarp();
-      // refill the slot with the band after next: of this map, or of the next one
-      const int nc = c + 2;
-      if (nc < bands) issue_band(n, nc, g_issue);
-      else issue_band(nxt, nc - bands, g_issue);
-      ++g_issue;
-      ++g_take;
-    }
-    A.lane_max = bv; A.lane_max2 = bv2; A.bq = bq;
-    const bool nonfinite = __any_sync(0xffffffffu, !(mn >= -FLT_MAX) || !(bv <= FLT_MAX));
-    float rv = bv; int ri = bi;
-    warp_argmax(bv, bi);
-    A.bv = bv; A.bi = bi;
-    bool exhaustive = nonfinite || bad_xform, deferred = false;
-    if (!exhaustive) {
-      unsigned biy, bix;
-      p.divW.divmod((unsigned)bi, biy, bix);
-      Src win;
-      win.ld = kWin;
-      win.x0 = (((int)bix - 6) >> 2) << 2;
-      win.y0 = (int)biy - 7;
-      win.x1 = win.x0 + kWin; win.y1 = win.y0 + kWin;
-      win.base = winbuf - (win.y0 * kWin + win.x0);
-      const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-#pragma unroll
-      for (int t = lane; t < kWin * kWin / 4; t += 32) {
-        const int r = t >> 2, c4 = t & 3;
-        const int y = win.y0 + r, x = win.x0 + (c4 << 2);
-        float4 v = ninf;
-        if (y >= 0 && y < H && x >= 0 && x + 3 < W) v = __ldcg(reinterpret_cast<const float4*>(gsrc + y * W + x));
-        reinterpret_cast<float4*>(winbuf)[t] = v;
-      }
-      __syncwarp();
-      bool miss = false;
-      decode_late<true>(p, win, X, A, lane, rv, ri, exhaustive, miss, n_eval);
-      if (miss) {
-        ++n_miss;
-        exhaustive = false; miss = false;
-        const Src full = {gsrc, W, 0, 0, W, H};
-        decode_late<false>(p, full, X, A, lane, rv, ri, exhaustive, miss, n_eval);
-      }
-      __syncwarp();
-    }
-    if (exhaustive) {
-      if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = (int)n;
-      deferred = true;
-      ++n_slow;
-    }
-    if (!deferred) {
-      k2_resolve(p, pend_item, pend_old, lane);
-      finish_map(p, n, (int)vu, b, j, gsrc, X, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
-    }
-    __syncwarp();
-    cur = nxt;
-  }
-  k2_resolve(p, pend_item, pend_old, lane);
-  if (p.stats && lane == 0 && n_maps) {
-    atomicAdd(p.stats + 0, n_slow);
-    atomicAdd(p.stats + 1, n_eval);
-    atomicAdd(p.stats + 2, n_maps);
-    atomicAdd(p.stats + 3, n_miss);
-  }
-}
-
 // Exhaustive decode of the queued maps: one CTA of 16 warps per map (rows split sixteen ways), map staged in
 // shared memory; warp 0 merges the partial arg-maxes and writes the outputs.
 constexpr int kSlowWarps = 16;
@@ -1230,29 +1061,6 @@ static int launch_k1(WDParams& p, cudaStream_t stream) {
   }
   long long need = (N + warps - 1) / warps;
   int grid = (int)(need < sm_count() ? need : sm_count());
-  //   UBPL_K1_STREAM 1 = large maps (whole-map staging would leave fewer than 7 warps per SM) are streamed through a
-  //                  ring of two 8 KB row bands per warp (warp_decode_stream_kernel); needs a queue for the exhaustive maps
-  const bool streamed = p.slow_list && p.use_bulk && p.do_warp && (W % 4 == 0) && W >= 16 && H >= 16 &&
-                        (map_bytes % kStreamBand == 0) && map_bytes >= 2 * (size_t)kStreamBand && warps < 7 &&
-                        env_int("UBPL_K1_STREAM", UBPL_K1_STREAM_DEFAULT) != 0;
-  if (streamed) {
-    const size_t per_warp = 2 * (size_t)kStreamBand + kWin * kWin * 4;
-    int sw = (int)((size_t)smem_cap / (per_warp + 16));
-    if (sw > 16) sw = 16;
-    if (env_warps > 0 && env_warps < sw) sw = env_warps;
-    static bool st_attr = false;
-    if (!st_attr) {
-      cudaError_t e = cudaFuncSetAttribute(warp_decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
-      if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute(stream): %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
-      st_attr = true;
-    }
-    long long sneed = (N + sw - 1) / sw;
-    const int sgrid = (int)(sneed < sm_count() ? sneed : sm_count());
-    warp_decode_stream_kernel<<<sgrid, sw * 32, (size_t)sw * per_warp + (size_t)sw * 16, stream>>>(p, (int)(map_bytes / kStreamBand));
-    int rcs = check_launch("ubpl_warp_decode(stream)");
-    if (rcs != UBPL_OK) return rcs;
-    return launch_slow(p, map_bytes, stream);
-  }
   if (early) warp_decode_kernel<true><<<grid, warps * 32, smem, stream>>>(p);
   else warp_decode_kernel<false><<<grid, warps * 32, smem, stream>>>(p);
   int rc = check_launch("ubpl_warp_decode");
