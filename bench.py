@@ -251,7 +251,7 @@ def run_ours(args):
         ubpl_dist.init_nccl(group)                 # the library's own communicator for the histogram all-reduce
     # the EMA runs beside K1; on the multi-GPU quantile path beside the one-CTA selector, whose cross-GPU wait it
     # fills (on one GPU the two placements measure the same: 340.5 vs 338.8 us per c4 step, profiles/README.md)
-    overlap = {"0": False, "1": "k1", "k1": "k1", "k2": "k2", "k3": "k3"}[
+    overlap = {"0": False, "1": "k1", "k1": "k1", "slow": "slow", "k2": "k2", "k3": "k3"}[
         os.environ.get("UBPL_BENCH_OVERLAP_EMA", "k2" if (c["select"] == "quantile" and world > 1) else "k1")]
     gstep = pipeline.GraphedStep(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, group=group,
                                  stats=stats, ema=plan, alpha=alpha, overlap_ema=overlap,
@@ -370,7 +370,7 @@ def run_ours(args):
     roof = {"bound": "hbm", "kernel": "warp_decode_kernel (K1: %d maps of %d B per launch)" % (M * K * B * J, 4 * H * W),
             "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC.get(args.config), "peak_source": peak_src,
-            "stages_ms": {("k1_warp_decode_with_k4_ema_overlapped" if gstep.overlap_ema == "k1" else "k1_warp_decode"): k1_ms,
+            "stages_ms": {("k1_warp_decode_with_k4_ema_overlapped" if gstep.overlap_ema in ("k1", "slow") else "k1_warp_decode"): k1_ms,
                           ("k2_uncertainty_select_with_k4_ema_overlapped" if gstep.overlap_ema == "k2" else "k2_uncertainty_select"): k2_ms,
                           ("k3_render_mse_with_k4_ema_overlapped" if gstep.overlap_ema == "k3" else "k3_render_mse"): k3_ms,
                           "k4_ema_in_step": k4_inline_ms, "k4_ema_standalone": k4_ms, "k1_standalone": k1_alone_ms},

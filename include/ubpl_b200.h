@@ -82,6 +82,8 @@ int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
  * ws   int32 workspace of ubpl_warp_decode_k2_ws_bytes(V, B, J) bytes, 8-byte aligned; the call clears its
  *      head with one memset node.  After the launch ws[128 .. 128+J) = selected items per joint, ws[128+J] = total
  *      selected, ws[128+J+1] = S * #(gate > 0) (mode 2) -- the `count_in` of ubpl_render_mse.
+ * mid_event (cudaEvent_t or NULL) is recorded on `stream` between the main launch and the short launch that decodes
+ * the queued exhaustive maps: independent work forked on it (the EMA update) runs beside that nearly empty launch.
  * Requires 1 <= V <= 32.  mean/dist/legal/enable may be NULL. */
 int64_t ubpl_warp_decode_k2_ws_bytes(int V, int B, int J);
 int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
@@ -90,7 +92,7 @@ int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
                         int32_t* out_idx, float* out_max, float* out_xy,
                         int k2_mode, double distThrMax, int img_h, int img_w, float stride, float sigma, int S,
                         float* mean, double* dist, uint8_t* legal, uint8_t* enable, float* gate,
-                        int64_t* stats, int32_t* ws, int64_t ws_bytes, void* stream);
+                        int64_t* stats, int32_t* ws, int64_t ws_bytes, void* mid_event, void* stream);
 
 /* Materialises the back-warped (and un-flipped) maps: the tensor AugmentUtils.affine_back2
  * returns (utils/augment.py:37-47).  in [N, C, H, W] strides (sN, sC); out likewise (oN, oC);

@@ -367,6 +367,16 @@ def test_graphed_step_modes(ops, mode, select):
             ms = g.stage_ms()
             assert set(ms) >= {"k1", "k2", "k3"} and all(v >= 0.0 for v in ms.values())
             assert 0.0 < sum(ms.values()) < 50.0
+    # the EMA forked beside K1's short second launch (event recorded by the C call between its two launches)
+    e2 = torch.randn(1000, device="cuda"); p2 = torch.randn(1000, device="cuda")
+    g2 = pipeline.GraphedStep(bufs["teacher"], bufs["student"], bufs["theta"], bufs["flip"], dec, w, cfg, ema=ops.EmaPlan([p2], [e2]),
+                              alpha=0.5, mode=mode, overlap_ema="slow")
+    e_before = e2.clone()
+    st2 = g2.run()
+    torch.cuda.synchronize()
+    for k in ("idx", "enable", "gate", "grad", "summary", "count"):
+        assert torch.equal(st2[k].reshape(-1), ref[k].reshape(-1)), k
+    assert torch.allclose(e2, 0.5 * e_before + 0.5 * p2, rtol=1e-6)
 
 
 def test_empty_and_degenerate_shapes(ops):

@@ -748,7 +748,9 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   // sitting between two maps.
   unsigned long long claim_reg = 0;                      // lane 0: result of the atomic in flight
   auto claim_issue = [&]() {
-    if (lane == 0) claim_reg = atomicAdd(p.work, 1ull);
+    // volatile asm: a plain atomicAdd is sunk by the compiler to the first use of its result (the ncu source
+    // page showed the whole round trip on the shuffle in claim_get), which defeats issuing it a map ahead
+    if (lane == 0) asm volatile("atom.add.relaxed.gpu.global.u64 %0, [%1], 1;" : "=l"(claim_reg) : "l"(p.work) : "memory");
   };
   auto claim_get = [&]() -> long long { return (long long)__shfl_sync(0xffffffffu, claim_reg, 0); };
   if (p.use_bulk && lane == 0) {
@@ -1024,7 +1026,7 @@ static int env_int(const char* name, int dflt) {
 
 // Fills the geometry / tuning fields of p and launches the main kernel (+ the exhaustive kernel when a queue
 // is given).  p.work, p.slow_*, p.k2 and the outputs are set by the caller.
-static int launch_k1(WDParams& p, cudaStream_t stream) {
+static int launch_k1(WDParams& p, cudaStream_t stream, cudaEvent_t mid_event = nullptr) {
   const int H = p.H, W = p.W;
   const long long N = (long long)p.V * p.B * p.J;
   const long long HW = (long long)H * W;
@@ -1064,6 +1066,10 @@ static int launch_k1(WDParams& p, cudaStream_t stream) {
   if (early) warp_decode_kernel<true><<<grid, warps * 32, smem, stream>>>(p);
   else warp_decode_kernel<false><<<grid, warps * 32, smem, stream>>>(p);
   int rc = check_launch("ubpl_warp_decode");
+  if (rc == UBPL_OK && mid_event) {
+    // the caller forks independent work here: it then runs beside the short, nearly empty launch below
+    if (cudaEventRecord(mid_event, stream) != cudaSuccess) { set_error("ubpl_warp_decode: cudaEventRecord(mid_event) failed"); return UBPL_ERR_CUDA; }
+  }
   if (rc != UBPL_OK || !p.slow_list) return rc;
   return launch_slow(p, map_bytes, stream);
 }
@@ -1112,7 +1118,7 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
                                    int32_t* out_idx, float* out_max, float* out_xy, int k2_mode, double distThrMax,
                                    int img_h, int img_w, float stride, float sigma, int S, float* mean, double* dist,
                                    uint8_t* legal, uint8_t* enable, float* gate, int64_t* stats, int32_t* ws,
-                                   int64_t ws_bytes, void* stream) {
+                                   int64_t ws_bytes, void* mid_event, void* stream) {
   UBPL_REQUIRE(V >= 1 && V <= 32 && B >= 0 && J >= 1 && H > 0 && W > 0, "ubpl_warp_decode_k2: bad dims V=%d B=%d J=%d H=%d W=%d (1 <= V <= 32)", V, B, J, H, W);
   UBPL_REQUIRE(ws && (B == 0 || (maps && theta && out_xy)), "ubpl_warp_decode_k2: NULL pointer");
   UBPL_REQUIRE(refine >= 0 && refine <= 2, "ubpl_warp_decode_k2: refine must be 0, 1 or 2");
@@ -1125,7 +1131,10 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
   cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)zero_words * 4, (cudaStream_t)stream);
   if (e != cudaSuccess) { set_error("ubpl_warp_decode_k2: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
   const long long N = (long long)V * B * J;
-  if (N == 0) return UBPL_OK;
+  if (N == 0) {
+    if (mid_event) cudaEventRecord((cudaEvent_t)mid_event, (cudaStream_t)stream);
+    return UBPL_OK;
+  }
   WDParams p;
   memset(&p, 0, sizeof(p));
   p.maps = maps; p.sV = sV; p.sB = sB; p.sJ = sJ; p.V = V; p.B = B; p.J = J; p.H = H; p.W = W;
@@ -1145,7 +1154,7 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
   f.mean = mean; f.dist = dist; f.legal = legal; f.enable = enable; f.gate = gate;
   int rc = pow_table(&f.T.key, &f.T.val, &f.T.bits, &f.T.n, &f.T.rmax);
   if (rc != UBPL_OK) return rc;
-  return launch_k1(p, (cudaStream_t)stream);
+  return launch_k1(p, (cudaStream_t)stream, (cudaEvent_t)mid_event);
 }
 
 extern "C" int ubpl_warp_materialize(const float* in, int64_t sN, int64_t sC, float* out, int64_t oN, int64_t oC,

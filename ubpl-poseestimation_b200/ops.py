@@ -97,7 +97,7 @@ def warp_decode(maps, theta=None, flip=None, dec=None, refine=0, stats=None, wan
 
 
 def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stride=4.0, sigma=3.0, distThrMax=1.0,
-                   refine=0, stats=None, want_idx=True):
+                   refine=0, stats=None, want_idx=True, mid_event=None):
     """K1 with the per-joint part of K2 fused into its epilogue (maps [V,B,J,H,W], V <= 32).
     One teacher (V = K views):
       mode 1: + mean [B,J,2], dist [B,J] f64 (999 = illegal), legal [B,J]   (utils/evaluation.py:44-54)
@@ -105,7 +105,9 @@ def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stri
               (utils/business.py:237-261,375-376, utils/process.py:262-268, utils/losses.py:29)
     Two teachers (V = 2K maps, teacher-major; theta/flip given per map):
       mode 3: mean = float32 ensemble coordinate, dist = extDist, legal, zero_div (utils/business.py:109-161)
-      mode 4: + the fixed rule on extDist, gate and counts as in mode 2."""
+      mode 4: + the fixed rule on extDist, gate and counts as in mode 2.
+    mid_event: a torch.cuda.Event (already recorded once, so that its handle exists) that the call records between
+    its main launch and the short launch for the queued exhaustive maps -- fork independent work on it."""
     _need_cuda(maps, theta, flip, dec, stats)
     if maps.dtype != _f32:
         raise _lib.UbplError("heat-maps must be float32")
@@ -131,7 +133,7 @@ def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stri
               theta.data_ptr(), _p(flip), _p(dec), int(refine), _p(out_idx), out_max.data_ptr(), out_xy.data_ptr(),
               int(mode), float(distThrMax), int(img_h), int(img_w), float(stride), float(sigma), int(S),
               mean.data_ptr(), dist.data_ptr(), legal.data_ptr(), _p(enable), _p(gate), _p(stats), ws.data_ptr(),
-              ws_bytes, _stream())
+              ws_bytes, None if mid_event is None else mid_event.cuda_event, _stream())
     return dict(idx=out_idx, max=out_max, xy=out_xy, mean=mean, dist=dist, legal=legal, enable=enable, gate=gate,
                 counts=ws[128:128 + J + 1], count=ws[128 + J + 1:128 + J + 2], zero_div=ws[33:34], ws=ws)
 

@@ -42,7 +42,7 @@ def nega_weights(islabeled, pseudoWeight):
                        torch.full((), float(pseudoWeight), device=islabeled.device)).to(torch.float32)
 
 
-def stage_k1(st, stats=None, cfg=None):
+def stage_k1(st, stats=None, cfg=None, mid_event=None):
     """K1: back-warp + flip + arg-max decode of every (model, view) map, each read from HBM once.  With one
     teacher (and cfg.fuse_k12) the per-joint dispersion -- and on the fixed path the whole selection -- is
     computed by the warp that decodes the last view of a joint, inside the same launch."""
@@ -63,7 +63,8 @@ def stage_k1(st, stats=None, cfg=None):
             th = theta.unsqueeze(0).expand(M, K, B, 2, 3).reshape(M * K, B, 2, 3)
             fl = flip.unsqueeze(0).expand(M, K, B).reshape(M * K, B)
         r = ops.warp_decode_k2(maps, th, fl, dec, mode, S=S, img_h=int(sH * cfg.stride), img_w=int(sW * cfg.stride),
-                               stride=cfg.stride, sigma=cfg.sigma, distThrMax=cfg.distThrMax, stats=stats)
+                               stride=cfg.stride, sigma=cfg.sigma, distThrMax=cfg.distThrMax, stats=stats, mid_event=mid_event)
+        st["mid_event_used"] = mid_event is not None
         st["xy"], st["max"], st["idx"] = r["xy"].view(M, K, B, J, 2), r["max"].view(M, K, B, J), r["idx"].view(M, K, B, J)
         st["k12"] = r
         return st
@@ -219,9 +220,10 @@ class GraphedStep:
         torch.cuda.synchronize()
         pool = None
         self.eager = {}
-        # overlap_ema: True / "k1" = K4 forked beside K1, "k2" = beside the quantile selector (a one-CTA kernel that
-        # leaves the rest of the GPU idle), "k3" = beside K3, False = after K3
-        self.overlap_ema = (overlap_ema if overlap_ema in ("k2", "k3") else "k1") if (overlap_ema and ema is not None) else False
+        # overlap_ema: True / "k1" = K4 forked beside K1, "slow" = beside K1's short second launch (the queued
+        # exhaustive maps: ~14 us on a nearly idle GPU), "k2" = beside the quantile selector (a one-CTA kernel),
+        # "k3" = beside K3, False = after K3
+        self.overlap_ema = (overlap_ema if overlap_ema in ("slow", "k2", "k3") else "k1") if (overlap_ema and ema is not None) else False
         if self.overlap_ema == "k2" and cfg.select != "quantile":
             self.overlap_ema = "k1"                       # the fixed path has no K2 launch to hide behind
         self._side = torch.cuda.Stream() if self.overlap_ema else None
@@ -236,9 +238,24 @@ class GraphedStep:
             fn()
             torch.cuda.current_stream().wait_stream(self._side)
 
+        self._mid = None
+        if self.overlap_ema == "slow":
+            self._mid = torch.cuda.Event()
+            self._mid.record()                                # creates the CUDA event: its handle is passed to the C call
+
         def k1_fn():
             if self.overlap_ema == "k1":
                 forked(lambda: stage_k1(self.state, stats, cfg))
+            elif self.overlap_ema == "slow":
+                self.state.pop("mid_event_used", None)
+                stage_k1(self.state, stats, cfg, mid_event=self._mid)
+                if self.state.get("mid_event_used"):           # recorded after K1's main launch
+                    self._side.wait_event(self._mid)
+                else:                                          # the unfused K1 path does not take the event
+                    self._side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side):
+                    self._ema()
+                torch.cuda.current_stream().wait_stream(self._side)
             else:
                 stage_k1(self.state, stats, cfg)
 
