@@ -249,10 +249,12 @@ def run_ours(args):
         p2p_ok = False
     if group is not None and c["select"] == "quantile" and not p2p_ok:
         ubpl_dist.init_nccl(group)                 # the library's own communicator for the histogram all-reduce
-    # the EMA runs beside K1; on the multi-GPU quantile path beside the one-CTA selector, whose cross-GPU wait it
-    # fills (on one GPU the two placements measure the same: 340.5 vs 338.8 us per c4 step, profiles/README.md)
+    # the EMA runs beside K1's short second launch (fixed path; 185.6 vs 187.1 us per c2 step beside the main launch)
+    # or beside K1 (quantile path); on the multi-GPU quantile path beside the one-CTA selector, whose cross-GPU wait
+    # it fills (on one GPU the two placements measure the same: 340.5 vs 338.8 us per c4 step, profiles/README.md)
     overlap = {"0": False, "1": "k1", "k1": "k1", "slow": "slow", "k2": "k2", "k3": "k3"}[
-        os.environ.get("UBPL_BENCH_OVERLAP_EMA", "k2" if (c["select"] == "quantile" and world > 1) else "k1")]
+        os.environ.get("UBPL_BENCH_OVERLAP_EMA", "k2" if (c["select"] == "quantile" and world > 1) else
+                       ("slow" if c["select"] == "fixed" else "k1"))]
     gstep = pipeline.GraphedStep(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, group=group,
                                  stats=stats, ema=plan, alpha=alpha, overlap_ema=overlap,
                                  mode=os.environ.get("UBPL_BENCH_GRAPH", "single"))
