@@ -436,7 +436,9 @@ def run_ours(args):
                        "selected_frac": float(r["enable"].float().mean()), "exhaustive_decode_frac": slow_frac,
                        "launch": ("1 CUDA graph per step" if single else "%d stage launches per step (%s)" % (len(gstep.order), ", ".join(
                                       n + (":eager" if n in gstep.eager else ":graph") for n in gstep.order)))
-                                 + ("; EMA forked onto a side stream beside %s" % gstep.overlap_ema.upper() if gstep.overlap_ema else "; EMA after K3"),
+                                 + ("; EMA forked onto a side stream beside %s" % {"k1": "K1", "slow": "K1's second launch", "k2": "the selector",
+                                                                                          "k3": "K3"}[gstep.overlap_ema]
+                                    if gstep.overlap_ema else "; EMA after K3"),
                        "selector": ("fixed rule in K1's epilogue" if c["select"] == "fixed" and cfg.fuse_k12 and M <= 2 else
                                     "fused one-kernel quantile selector" + (" over NVLink peer memory" if p2p_ok else "")
                                     if (world == 1 or p2p_ok) and c["select"] == "quantile" else
