@@ -92,3 +92,25 @@ def test_view_matrix_host_helper():
             t = augment.AugmentUtils.view_matrix(g["centers"][v, b].tolist(), torch.tensor(g["scales"][v, b]), [W, W],
                                                  torch.tensor(g["angles"][v, b]))
             np.testing.assert_allclose(t, g["mats"][v, b], rtol=1e-15, atol=1e-15)
+
+
+def test_workspace_size_helpers():
+    """Pure host functions of the ABI: workspace / exchange-buffer sizes (no device needed)."""
+    L = _lib.lib()
+    # head (128 words) + counts + B*J arrival counters + V*B*J 64-bit hand-off words + the queue of V*B*J indices
+    V, B, J = 8, 256, 14
+    n = V * B * J
+    got = L.ubpl_warp_decode_k2_ws_bytes(V, B, J)
+    assert got >= 4 * (128 + J + 2 + B * J + 2 * n + n) and got % 4 == 0
+    assert L.ubpl_warp_decode_k2_ws_bytes(V, 0, J) > 0                      # an empty batch still has the head
+    assert L.ubpl_warp_decode_k2_ws_bytes(2 * V, B, J) > got
+    # exchange buffer: header + 2 parities x nranks slots x (32-byte slot header + 8 bytes per item)
+    assert L.ubpl_p2p_buffer_bytes(8, 4352) == 256 + 2 * 8 * (32 + 8 * 4352)
+    assert L.ubpl_p2p_buffer_bytes(17, 10) == 0 and L.ubpl_p2p_buffer_bytes(0, 10) == 0      # 1..16 ranks
+    assert L.ubpl_p2p_ranks() == 0 and L.ubpl_p2p_status() == 0            # nothing mapped in this process
+
+
+def test_grouped_rejects_other_criteria():
+    from ubpl_b200 import losses
+    with pytest.raises(TypeError):
+        losses.grouped(losses.JointPseudoLoss3(nStack=2), torch.zeros(1, 1, 2, 1, 8, 8), torch.zeros(1, 1, 1, 8, 8))
