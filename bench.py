@@ -228,7 +228,8 @@ def run_ours(args):
     d = synth.make_batch(B=B, K=K, J=J, H=H, W=W, M=M, S=S, seed=1388, rank=rank, device=dev)
     dec = ops.decode_coeffs(d["center"], d["scale"], [H, W])
     w = pipeline.nega_weights(d["islabeled"], 1.0)
-    cfg = pipeline.StepConfig(select=c["select"], distThrMax=DIST_THR_MAX)
+    cfg = pipeline.StepConfig(select=c["select"], distThrMax=DIST_THR_MAX,
+                              prefetch_student=os.environ.get("UBPL_BENCH_PREFETCH", "1") != "0")
     shapes = json.load(open(os.path.join(ROOT, "ubpl-poseestimation_b200", "hg_param_shapes.json")))[c["hg"]]
     g = torch.Generator(device=dev).manual_seed(5)
     params = [torch.randn(*s, generator=g, device=dev) * 0.02 for s in shapes]
@@ -249,12 +250,10 @@ def run_ours(args):
         p2p_ok = False
     if group is not None and c["select"] == "quantile" and not p2p_ok:
         ubpl_dist.init_nccl(group)                 # the library's own communicator for the histogram all-reduce
-    # the EMA runs beside K1's short second launch (fixed path; 185.6 vs 187.1 us per c2 step beside the main launch)
-    # or beside K1 (quantile path); on the multi-GPU quantile path beside the one-CTA selector, whose cross-GPU wait
-    # it fills (on one GPU the two placements measure the same: 340.5 vs 338.8 us per c4 step, profiles/README.md)
-    overlap = {"0": False, "1": "k1", "k1": "k1", "slow": "slow", "k2": "k2", "k3": "k3"}[
-        os.environ.get("UBPL_BENCH_OVERLAP_EMA", "k2" if (c["select"] == "quantile" and world > 1) else
-                       ("slow" if c["select"] == "fixed" else "k1"))]
+    # the EMA runs beside K1 (latency-bound: the EMA's 101 MB of HBM traffic fit beside it); on the multi-GPU quantile
+    # path beside the one-CTA selector, whose cross-GPU wait it fills
+    overlap = {"0": False, "1": "k1", "k1": "k1", "slow": "k1", "k2": "k2", "k3": "k3"}[
+        os.environ.get("UBPL_BENCH_OVERLAP_EMA", "k2" if (c["select"] == "quantile" and world > 1) else "k1")]
     gstep = pipeline.GraphedStep(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, group=group,
                                  stats=stats, ema=plan, alpha=alpha, overlap_ema=overlap,
                                  mode=os.environ.get("UBPL_BENCH_GRAPH", "single"))
@@ -372,7 +371,7 @@ def run_ours(args):
     roof = {"bound": "hbm", "kernel": "warp_decode_kernel (K1: %d maps of %d B per launch)" % (M * K * B * J, 4 * H * W),
             "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC.get(args.config), "peak_source": peak_src,
-            "stages_ms": {("k1_warp_decode_with_k4_ema_overlapped" if gstep.overlap_ema in ("k1", "slow") else "k1_warp_decode"): k1_ms,
+            "stages_ms": {("k1_warp_decode_with_k4_ema_overlapped" if gstep.overlap_ema == "k1" else "k1_warp_decode"): k1_ms,
                           ("k2_uncertainty_select_with_k4_ema_overlapped" if gstep.overlap_ema == "k2" else "k2_uncertainty_select"): k2_ms,
                           ("k3_render_mse_with_k4_ema_overlapped" if gstep.overlap_ema == "k3" else "k3_render_mse"): k3_ms,
                           "k4_ema_in_step": k4_inline_ms, "k4_ema_standalone": k4_ms, "k1_standalone": k1_alone_ms},
@@ -436,7 +435,7 @@ def run_ours(args):
                        "selected_frac": float(r["enable"].float().mean()), "exhaustive_decode_frac": slow_frac,
                        "launch": ("1 CUDA graph per step" if single else "%d stage launches per step (%s)" % (len(gstep.order), ", ".join(
                                       n + (":eager" if n in gstep.eager else ":graph") for n in gstep.order)))
-                                 + ("; EMA forked onto a side stream beside %s" % {"k1": "K1", "slow": "K1's second launch", "k2": "the selector",
+                                 + ("; EMA forked onto a side stream beside %s" % {"k1": "K1", "k2": "the selector",
                                                                                           "k3": "K3"}[gstep.overlap_ema]
                                     if gstep.overlap_ema else "; EMA after K3"),
                        "selector": ("fixed rule in K1's epilogue" if c["select"] == "fixed" and cfg.fuse_k12 and M <= 2 else

@@ -52,19 +52,23 @@ int ubpl_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_opti
  *         first maximum in row-major order), out_max float32 (unmasked maximum = `scores`),
  *         out_xy float32[2] (image space, integer valued), out_hm_xy float32[2] (1-based heat-map
  *         coordinates after the max<=0 mask and the optional refinement); any may be NULL.
+ * swap_perm optional int32[J] (NULL = none, the reference's live path): output joint j of a FLIPPED
+ *         view is decoded from source channel swap_perm[j] -- the left/right exchange of flip_back
+ *         (utils/udaap/transforms.py:20-57) folded into the un-flip; ignored when flip is NULL.
  * stats   optional int64[4] device counters, incremented: [0] maps decoded by exhaustive
- *         evaluation, [1] output pixels evaluated, [2] maps, [3] maps repeated on the full view after the
- *         early-release window proved too small.
- * slow_ws optional int32[V*B*J + 1] device scratch: with it, the (rare) maps that need the exhaustive
- *         decode are queued and decoded by whole CTAs in a second kernel launched right after the first
- *         (better tail); NULL decodes them in place.
+ *         evaluation, [1] output pixels evaluated, [2] maps, [3] unused.
+ * ws      optional int32[>= 2] device scratch, 8-byte aligned: the launch's private work-claim counter
+ *         (cleared by the call).  NULL takes a slot of a process-wide ring instead, which a captured CUDA
+ *         graph would keep using while eager calls cycle through it -- pass ws when capturing.
+ * Maps that cannot be pruned (NaN/Inf, singular theta, structure-less maps) are decoded exhaustively by
+ * all warps of the CTA together inside the same launch; there is no second kernel.
  */
 int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
                      int V, int B, int J, int H, int W,
-                     const float* theta, const uint8_t* flip, const double* dec,
+                     const float* theta, const uint8_t* flip, const int32_t* swap_perm, const double* dec,
                      int do_warp, int refine,
                      int32_t* out_idx, float* out_max, float* out_xy, float* out_hm_xy,
-                     int64_t* stats, int32_t* slow_ws, void* stream);
+                     int64_t* stats, int32_t* ws, void* stream);
 
 /* K1 with the per-joint part of K2 fused into its epilogue (mean-teacher path: one teacher, V = K views).
  * Decodes like ubpl_warp_decode(do_warp = 1); in addition every decoded map bumps the arrival counter of
@@ -79,27 +83,32 @@ int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
  *              legal; ws[33] counts the key points whose two intDists are both 0 (the reference divides by zero)
  *   k2_mode 4: + the fixed rule on extDist, gate and counts as in mode 2
  * so the chain needs no K2 launch (modes 2, 4) or only the quantile selector (modes 1, 3).
- * ws   int32 workspace of ubpl_warp_decode_k2_ws_bytes(V, B, J) bytes, 8-byte aligned; the call clears its
- *      head with one memset node.  After the launch ws[128 .. 128+J) = selected items per joint, ws[128+J] = total
- *      selected, ws[128+J+1] = S * #(gate > 0) (mode 2) -- the `count_in` of ubpl_render_mse.
- * mid_event (cudaEvent_t or NULL) is recorded on `stream` between the main launch and the short launch that decodes
- * the queued exhaustive maps: independent work forked on it (the EMA update) runs beside that nearly empty launch.
- * Requires 1 <= V <= 32.  mean/dist/legal/enable may be NULL. */
+ * ws   int32 workspace of ubpl_warp_decode_k2_ws_bytes(V, B, J) bytes, 8-byte aligned; the call clears it
+ *      with one memset node.  After the launch ws[128 .. 128+J) = selected items per joint, ws[128+J] = total
+ *      selected, ws[128+J+1] = S * #(gate > 0) (mode 2) -- the `count_in` of ubpl_render_mse; ws[34] = key points
+ *      whose two intDists are both 0 (modes 3/4); ws[35] = status: non-zero when a hand-off word of the K2
+ *      epilogue never arrived (the launch's K2 outputs are then void; the caller must check it and raise).
+ * prefetch / prefetch_bytes (optional, 16-byte aligned): a global range the NEXT kernel will read (the student
+ *      maps of K3).  Warps that have run out of maps pull it into L2 in 32 KB chunks while the last maps finish.
+ * swap_perm as in ubpl_warp_decode.  Requires 1 <= V <= 32.  mean/dist/legal/enable may be NULL. */
 int64_t ubpl_warp_decode_k2_ws_bytes(int V, int B, int J);
 int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
                         int V, int B, int J, int H, int W,
-                        const float* theta, const uint8_t* flip, const double* dec, int refine,
-                        int32_t* out_idx, float* out_max, float* out_xy,
+                        const float* theta, const uint8_t* flip, const int32_t* swap_perm, const double* dec,
+                        int refine, int32_t* out_idx, float* out_max, float* out_xy,
                         int k2_mode, double distThrMax, int img_h, int img_w, float stride, float sigma, int S,
                         float* mean, double* dist, uint8_t* legal, uint8_t* enable, float* gate,
-                        int64_t* stats, int32_t* ws, int64_t ws_bytes, void* mid_event, void* stream);
+                        int64_t* stats, int32_t* ws, int64_t ws_bytes, const void* prefetch, int64_t prefetch_bytes,
+                        void* stream);
 
 /* Materialises the back-warped (and un-flipped) maps: the tensor AugmentUtils.affine_back2
  * returns (utils/augment.py:37-47).  in [N, C, H, W] strides (sN, sC); out likewise (oN, oC);
- * theta [N,2,3]; flip [N] uint8 or NULL.  Bit-identical to ATen's CPU grid_sample op order. */
+ * theta [N,2,3]; flip [N] uint8 or NULL; swap_perm int32[C] or NULL: output channel c of a flipped sample
+ * comes from source channel swap_perm[c] (flip_back's left/right exchange, utils/udaap/transforms.py:20-57).
+ * Bit-identical to ATen's CPU grid_sample op order. */
 int ubpl_warp_materialize(const float* in, int64_t sN, int64_t sC, float* out, int64_t oN, int64_t oC,
                           int N, int C, int H, int W, const float* theta, const uint8_t* flip,
-                          void* stream);
+                          const int32_t* swap_perm, void* stream);
 
 /* AugmentUtils.fliplr_back_tensor (utils/augment.py:247-252): out[r, x] = in[r, W-1-x] for `rows`
  * contiguous rows of W floats. */
@@ -358,10 +367,14 @@ int ubpl_features_cov(const float* f1, const float* f2, int64_t rows, int L, flo
  * update_ema_variables (utils/parameters.py:4-8): ema = ema*alpha + (1-alpha)*param, float32,
  * evaluated as fma(param, 1-alpha, ema*alpha) like ATen.  ema_ptrs/param_ptrs: device arrays of
  * n_tensors device addresses; chunk_tensor/chunk_start: device arrays describing n_chunks work
- * items (tensor id, first element); chunk_elems elements per chunk; numels[n_tensors]. */
+ * items (tensor id, first element); chunk_elems elements per chunk; numels[n_tensors].
+ * alpha_dev (optional, device float[2] = {alpha, 1 - alpha}): when not NULL the kernel reads the two factors
+ * from it instead of the by-value arguments, so a CUDA graph that captured the launch follows the per-epoch
+ * alpha = min(1 - 1/(epo+1), ema_decay) of the reference (the host rewrites the two floats between replays). */
 int ubpl_ema_multi_tensor(const uint64_t* ema_ptrs, const uint64_t* param_ptrs, const int64_t* numels,
                           const int32_t* chunk_tensor, const int64_t* chunk_start, int64_t n_chunks,
-                          int chunk_elems, float alpha, float one_minus_alpha, void* stream);
+                          int chunk_elems, float alpha, float one_minus_alpha, const float* alpha_dev,
+                          void* stream);
 /* Contiguous special case (flattened parameter buffer). */
 int ubpl_ema_flat(float* ema, const float* param, int64_t n, float alpha, float one_minus_alpha,
                   void* stream);

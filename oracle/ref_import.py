@@ -7,15 +7,20 @@ not installed here (skimage, openpyxl, imageio, matplotlib) and one module evalu
 hot-path functions the oracle restates.  This shim is used ONLY to
   * pin `oracle/ubpl_oracle.py` against the reference's own functions (tests/test_oracle_vs_reference.py),
   * generate the committed fixtures under tests/golden/ (tests/golden/make_golden.py).
-It never runs on the GPU box (the reference is not mounted there) and nothing in the product
-package imports it.
+On the GPU box (where /root/reference is not mounted) it resolves to the staged, unmodified copy under
+baseline/_ref/ (tools/stage_reference.py; git-ignored) and additionally serves bench.py's CPU baseline
+(oracle/ref_chain.py).  Nothing in the product package imports it.
 """
 import os
 import sys
 import types
 import contextlib
 
-REFERENCE_ROOT = os.environ.get("UBPL_REFERENCE_ROOT", "/root/reference")
+# /root/reference in the build container; on the GPU box the byte-for-byte staged copy that
+# tools/stage_reference.py leaves under the git-ignored baseline/_ref/
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+REFERENCE_ROOT = os.environ.get("UBPL_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/utils") else _STAGED)
 
 
 def reference_available() -> bool:
@@ -75,6 +80,7 @@ def load_reference():
         ns.parameters = importlib.import_module("utils.parameters")
         ns.udaap_eval = importlib.import_module("utils.udaap.evaluation")
         ns.udaap_tf = importlib.import_module("utils.udaap.transforms")
+        ns.tools = importlib.import_module("projects.tools")
     ns.aug = ns.augment.AugmentUtils
     ns.proc = ns.process.ProcessUtils
     ns.eval = ns.evaluation.EvaluationUtils

@@ -97,11 +97,11 @@ def test_view_matrix_host_helper():
 def test_workspace_size_helpers():
     """Pure host functions of the ABI: workspace / exchange-buffer sizes (no device needed)."""
     L = _lib.lib()
-    # head (128 words) + counts + B*J arrival counters + V*B*J 64-bit hand-off words + the queue of V*B*J indices
+    # head (128 words) + counts + B*J arrival counters + V*B*J 64-bit hand-off words
     V, B, J = 8, 256, 14
     n = V * B * J
     got = L.ubpl_warp_decode_k2_ws_bytes(V, B, J)
-    assert got >= 4 * (128 + J + 2 + B * J + 2 * n + n) and got % 4 == 0
+    assert got >= 4 * (128 + J + 2 + B * J + 2 * n) and got % 4 == 0
     assert L.ubpl_warp_decode_k2_ws_bytes(V, 0, J) > 0                      # an empty batch still has the head
     assert L.ubpl_warp_decode_k2_ws_bytes(2 * V, B, J) > got
     # exchange buffer: header + 2 parities x nranks slots x (32-byte slot header + 8 bytes per item)

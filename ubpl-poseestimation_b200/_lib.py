@@ -18,17 +18,17 @@ SIGNATURES = {
     "ubpl_version": [],
     "ubpl_device_info": [c_void_p] * 4,
     "ubpl_warp_decode": [c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
-                         c_void_p, c_void_p, c_void_p, c_int, c_int,
+                         c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_warp_decode_k2": [c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
-                            c_void_p, c_void_p, c_void_p, c_int,
+                            c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                             c_void_p, c_void_p, c_void_p,
                             c_int, c_double, c_int, c_int, c_float, c_float, c_int,
                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                            c_void_p, c_void_p, c_i64, c_void_p, c_void_p],
+                            c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p],
     "ubpl_warp_decode_k2_ws_bytes": [c_int, c_int, c_int],
     "ubpl_warp_materialize": [c_void_p, c_i64, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_int, c_int,
-                              c_void_p, c_void_p, c_void_p],
+                              c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_view_dispersion": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "ubpl_mirror_w": [c_void_p, c_void_p, c_i64, c_int, c_void_p],
     "ubpl_coord_error": [c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p],
@@ -80,7 +80,7 @@ SIGNATURES = {
     "ubpl_view_kps": [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p, c_void_p],
     "ubpl_acc_pck": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "ubpl_features_cov": [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
-    "ubpl_ema_multi_tensor": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_float, c_void_p],
+    "ubpl_ema_multi_tensor": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_float, c_void_p, c_void_p],
     "ubpl_ema_flat": [c_void_p, c_void_p, c_i64, c_float, c_float, c_void_p],
 }
 
@@ -123,7 +123,7 @@ def lib():
 
 
 # kernels launched per successful call (cudaMemsetAsync is not counted); bench.py's gpu_launches
-LAUNCHES = {"ubpl_dist_extrema": 2, "ubpl_features_cov": 2, "ubpl_warp_decode": 2, "ubpl_warp_decode_k2": 2, "ubpl_select_quantile_dist": 16, "ubpl_nccl_unique_id": 0,
+LAUNCHES = {"ubpl_dist_extrema": 2, "ubpl_features_cov": 2, "ubpl_select_quantile_dist": 16, "ubpl_nccl_unique_id": 0,
             "ubpl_nccl_init": 0, "ubpl_nccl_destroy": 0, "ubpl_p2p_alloc": 0, "ubpl_p2p_open": 0, "ubpl_p2p_close": 0, "ubpl_select_debug_stamps": 0}
 _launches = 0
 

@@ -15,13 +15,15 @@ def _to_cuda(t):
 
 class AugmentUtils:
     @classmethod
-    def affine_back2(cls, heatmap, warpmat, isflip):
+    def affine_back2(cls, heatmap, warpmat, isflip, swap_perm=None):
         """utils/augment.py:37-47: back-warp (affine_grid + bilinear grid_sample, zeros padding,
         align_corners=True) and per-sample W mirror, one kernel; returns a new tensor on the
-        input's device.  Bit-identical to ATen's CPU kernels."""
+        input's device.  Bit-identical to ATen's CPU kernels.  swap_perm (optional, [J]; default None = the
+        reference's behaviour) also exchanges the left/right joint channels of the flipped samples the way
+        utils/udaap/transforms.py:20-57 `flip_back` does (ops.swap_perm_from_pairs builds the table)."""
         dev = heatmap.device
         out = ops.warp_materialize(_to_cuda(heatmap.detach()), _to_cuda(warpmat.detach()),
-                                   _to_cuda(torch.as_tensor(isflip)))
+                                   _to_cuda(torch.as_tensor(isflip)), swap_perm=swap_perm)
         return out.to(dev)
 
     affine_back2_classification = affine_back2      # utils/augment.py:64-74 is the same function

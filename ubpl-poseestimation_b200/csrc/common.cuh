@@ -134,19 +134,38 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
   }
 }
 
-// n / d and n % d for 32-bit n with a host-computed magic pair: q = umulhi(n, mul) >> shr
+// Arg-max over the warp for FINITE values (no NaN among the lanes' v): one CREDUX for the value, one REDUX for the
+// smallest index among the lanes that hold it -- torch.max's first-index rule -- and the winning lane's own value
+// (so a zero maximum keeps the sign the shuffle tree of warp_argmax would return).  Lanes without a candidate pass
+// (-inf, 0x7fffffff).
+__device__ __forceinline__ float warp_redux_max(float v) {
+  float m;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  return m;
+}
+__device__ __forceinline__ void warp_argmax_finite(float& v, int& i) {
+  const float m = warp_redux_max(v);
+  const int c = (v == m) ? i : 0x7fffffff;
+  const int im = __reduce_min_sync(0xffffffffu, c);
+  const unsigned who = __ballot_sync(0xffffffffu, c == im);
+  v = __shfl_sync(0xffffffffu, v, __ffs(who) - 1);
+  i = im;
+}
+
+// n / d and n % d for 32-bit n with a host-computed magic pair: q = umulhi(n, mul) >> shr; a power-of-two
+// divisor (mul == 0) is a plain shift.
 struct FastDiv {
   unsigned mul, shr, d;
   __host__ void init(unsigned div) {
     d = div;
-    if (div == 1) { mul = 0; shr = 0; return; }
     unsigned l = 0;
     while ((1ull << l) < div) ++l;                       // l = ceil(log2 div)
+    if ((1ull << l) == div) { mul = 0; shr = l; return; }
     const unsigned long long m = ((1ull << 32) * ((1ull << l) - div)) / div + 1;
     mul = (unsigned)m; shr = l;
   }
   __device__ __forceinline__ unsigned div(unsigned n) const {
-    if (d == 1) return n;
+    if (mul == 0) return n >> shr;
     const unsigned t = __umulhi(n, mul);
     return (t + ((n - t) >> 1)) >> (shr - 1);
   }

@@ -19,7 +19,11 @@ __global__ void __launch_bounds__(256) ema_multi_kernel(const uint64_t* __restri
                                                          const long long* __restrict__ numels,
                                                          const int32_t* __restrict__ chunk_tensor,
                                                          const long long* __restrict__ chunk_start,
-                                                         long long n_chunks, int chunk_elems, float a, float oma) {
+                                                         long long n_chunks, int chunk_elems, float a, float oma,
+                                                         const float* __restrict__ alpha_dev) {
+  // alpha_dev (optional): {alpha, 1 - alpha} read from device memory, so that a CUDA graph that captured this
+  // launch follows the per-epoch alpha = min(1 - 1/(epo+1), ema_decay) of utils/parameters.py:6 without re-capture
+  if (alpha_dev) { a = alpha_dev[0]; oma = alpha_dev[1]; }
   for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const int t = chunk_tensor[c];
     const long long start = chunk_start[c];
@@ -80,7 +84,8 @@ using namespace ubpl;
 
 extern "C" int ubpl_ema_multi_tensor(const uint64_t* ema_ptrs, const uint64_t* param_ptrs, const int64_t* numels,
                                      const int32_t* chunk_tensor, const int64_t* chunk_start, int64_t n_chunks,
-                                     int chunk_elems, float alpha, float one_minus_alpha, void* stream) {
+                                     int chunk_elems, float alpha, float one_minus_alpha, const float* alpha_dev,
+                                     void* stream) {
   UBPL_REQUIRE(ema_ptrs && param_ptrs && numels && chunk_tensor && chunk_start, "ubpl_ema_multi_tensor: NULL pointer");
   UBPL_REQUIRE(n_chunks >= 0 && chunk_elems > 0 && chunk_elems % 4 == 0, "ubpl_ema_multi_tensor: bad chunking");
   if (n_chunks == 0) return UBPL_OK;
@@ -88,7 +93,7 @@ extern "C" int ubpl_ema_multi_tensor(const uint64_t* ema_ptrs, const uint64_t* p
   const int grid = (int)(n_chunks < cap ? n_chunks : cap);
   ema_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ema_ptrs, param_ptrs, reinterpret_cast<const long long*>(numels),
                                                            chunk_tensor, reinterpret_cast<const long long*>(chunk_start),
-                                                           n_chunks, chunk_elems, alpha, one_minus_alpha);
+                                                           n_chunks, chunk_elems, alpha, one_minus_alpha, alpha_dev);
   return check_launch("ubpl_ema_multi_tensor");
 }
 

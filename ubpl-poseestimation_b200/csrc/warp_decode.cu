@@ -1,8 +1,11 @@
-// K1: back-warp + flip + arg-max decode, fused; and the materialising warp (affine_back2).
+// K1: back-warp + flip (+ optional left/right joint swap) + arg-max decode, fused; and the materialising
+// warp (affine_back2).
 //
 // Reference semantics (file:line in /root/reference):
 //   utils/augment.py:37-47      affine_back2  = F.affine_grid + F.grid_sample(bilinear, zeros,
 //                               align_corners=True) + per-sample W mirror
+//   utils/udaap/transforms.py:20-57   flip_back: mirror + exchange of the left/right joint channels (optional
+//                               here: swap_perm[J]; NULL = the reference's live path, which has no swap)
 //   utils/udaap/evaluation.py:13-30   get_preds (first arg-max, 1-based, zero where max <= 0)
 //   utils/udaap/transforms.py:151-168 transform(invert=1) -> trunc + 1 (image space)
 //   utils/process.py:362-373    quarter-offset refinement (kps_fromHeatmap2)
@@ -19,20 +22,19 @@
 //   A) scans the staged map for its max / min / arg-max (conflict-free 128-bit LDS),
 //   L) evaluates exactly the <= 30 output pixels around the pre-image of the arg-max texel;
 //      their best value L is a lower bound of the warped maximum,
-//   B) rescans for "candidate" texels v >= T = L - (L + max|v|) * 2^-19 (the slack covers every
+//   B) rescans for "candidate" texels v >= T = L - |L| * 2^-19 (the slack covers every
 //      rounding in the interpolation) and takes their bounding box,
 //   C) evaluates exactly every output pixel whose 2x2 footprint can touch that box and reduces
 //      (value, canonical index) with torch.max's first-index tie rule.
 // Pixels outside C have all four corners < T, hence a computed value < L: they cannot win or tie.
-// Maps where this does not apply (max <= 0 after warp, NaN/Inf, singular theta, huge candidate
-// box) are decoded exhaustively by the same warp, so the result is exact in every case.
+// Maps where this does not apply (max <= 0 after warp and not solvable geometrically, NaN/Inf, singular
+// theta, huge candidate box: structure-less maps) are decoded exhaustively -- by ALL warps of the CTA
+// together, straight out of the posting warp's staging buffer (CoopJob below), so the result is exact in
+// every case and no map is left to a second launch.
 #include "common.cuh"
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
-
-#ifndef UBPL_K1_EARLY_DEFAULT
-#define UBPL_K1_EARLY_DEFAULT 0
-#endif
 
 namespace ubpl {
 
@@ -48,9 +50,12 @@ struct K2Fuse {
                               // counts; two teachers (assess_pseudo_unc2): 3 ensemble coord / extDist / legal, 4 + fixed rule
   int K;                      // maps per item (= V: K views of one teacher, or 2 x K/2 views of two teachers)
   int32_t* zero_div;          // modes 3/4: number of items whose two intDists are both 0 (business.py:135 divides by zero)
+  int32_t* status;            // set to 1 when a hand-off word never arrived (bounded spin ran out): the results of
+                              // this launch are void and the host raises (ops.warp_decode_k2 -> "status")
   unsigned* arrive;           // [B*J] arrival counters, zero before the launch
   unsigned long long* slots;  // [K][B*J] hand-off words ~pack(x, y); 0 = not written yet (zero before the launch)
   double distThrMax;
+  double thr;                 // 1 - exp(-3*distThrMax/5), evaluated on the host with the libm CPython uses
   int img_h, img_w, S;
   float stride, sigma;
   float* mean;                // [B*J, 2]
@@ -70,6 +75,7 @@ struct WDParams {
   int V, B, J, H, W;
   const float* theta;
   const uint8_t* flip;
+  const int32_t* swap_perm;   // [J] or NULL: output joint j of a FLIPPED view is decoded from source channel swap_perm[j]
   const double* dec;
   int do_warp, refine, use_bulk;
   int32_t* out_idx;
@@ -78,8 +84,10 @@ struct WDParams {
   float* out_hm_xy;
   unsigned long long* stats;
   unsigned long long* work;   // global claim counter (zeroed before the launch)
-  int* slow_list;             // [V*B*J] queue of maps left to the exhaustive decode (NULL: decode in place)
-  unsigned* slow_count;
+  const unsigned char* pf_ptr;   // optional: a global range (the student maps K3 reads next) that warps which
+  unsigned long long pf_bytes;   // ran out of maps prefetch into L2, chunk by chunk, while the last maps finish
+  unsigned long long* pf_next;   // its chunk counter (zeroed before the launch)
+  int pf_every;                  // an idle warp prefetches one 32 KB chunk every pf_every polls (~0.25 us each)
   K2Fuse k2;                  // optional K2 epilogue run by the warp that decodes the last view of a (sample, joint)
 };
 
@@ -90,16 +98,19 @@ struct Xform {
   bool flip;
 };
 
+struct ArgMax {
+  float v;
+  int i;
+};
+
 __device__ __forceinline__ float lin_coord(int k, int n, float step) {
   if (n <= 1) return 0.f;  // ATen linspace_from_neg_one: a single step sits at 0
   return (k < (n >> 1)) ? __fmaf_rn(step, (float)k, -1.f) : __fmaf_rn(-step, (float)(n - 1 - k), 1.f);
 }
 
-// Exact bilinear sample of output pixel (row i, column jw in the WARPED frame, i.e. before the
-// mirror) from the staged source map s[H*W].
-__device__ __forceinline__ float eval_px(const float* __restrict__ s, const Xform& X, int i, int jw) {
-  const float xl = lin_coord(jw, X.W, X.stepx);
-  const float yl = lin_coord(i, X.H, X.stepy);
+// Bilinear sample at the normalised base-grid coordinates (xl, yl) of one output pixel from the source map
+// s[H*W]: ATen's op order, zero padding.
+__device__ __forceinline__ float eval_at(const float* __restrict__ s, const Xform& X, float xl, float yl) {
   const float gx = __fadd_rn(__fmaf_rn(yl, X.t01, __fmul_rn(xl, X.t00)), X.t02);
   const float gy = __fadd_rn(__fmaf_rn(yl, X.t11, __fmul_rn(xl, X.t10)), X.t12);
   const float ix = __fmul_rn(__fadd_rn(gx, 1.f), X.sfx);
@@ -110,8 +121,8 @@ __device__ __forceinline__ float eval_px(const float* __restrict__ s, const Xfor
   const float nw = __fmul_rn(so, e), ne = __fmul_rn(so, w), sw = __fmul_rn(n, e), se = __fmul_rn(n, w);
   const int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)(X.W + 1));
   const int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)(X.H + 1));
-  const bool xa = (x0 >= 0) & (x0 < X.W), xb = (x0 + 1 >= 0) & (x0 + 1 < X.W);
-  const bool ya = (y0 >= 0) & (y0 < X.H), yb = (y0 + 1 >= 0) & (y0 + 1 < X.H);
+  const bool xa = (unsigned)x0 < (unsigned)X.W, xb = (unsigned)(x0 + 1) < (unsigned)X.W;
+  const bool ya = (unsigned)y0 < (unsigned)X.H, yb = (unsigned)(y0 + 1) < (unsigned)X.H;
   const float* r0 = s + y0 * X.W + x0;
   const float v_nw = (xa & ya) ? r0[0] : 0.f;
   const float v_ne = (xb & ya) ? r0[1] : 0.f;
@@ -124,11 +135,23 @@ __device__ __forceinline__ float eval_px(const float* __restrict__ s, const Xfor
   return acc;
 }
 
+// Exact bilinear sample of output pixel (row i, column jw in the WARPED frame, i.e. before the
+// mirror) from the staged source map s[H*W].
+__device__ __forceinline__ float eval_px(const float* __restrict__ s, const Xform& X, int i, int jw) {
+  return eval_at(s, X, lin_coord(jw, X.W, X.stepx), lin_coord(i, X.H, X.stepy));
+}
+
+// The same with the base grid read from the CTA's tables (lx[W], ly[H] = lin_coord of every column / row).
+__device__ __forceinline__ float eval_tab(const float* __restrict__ s, const Xform& X, const float* lx, const float* ly,
+                                          int i, int jw) {
+  return eval_at(s, X, lx[jw], ly[i]);
+}
+
 // The unnormalised source coordinates (ix, iy) of output pixel (row i, warped column jw), bit-identical
-// to the ones eval_px interpolates at.
-__device__ __forceinline__ void grid_px(const Xform& X, int i, int jw, float& ix, float& iy) {
-  const float xl = lin_coord(jw, X.W, X.stepx);
-  const float yl = lin_coord(i, X.H, X.stepy);
+// to the ones eval_at interpolates at.
+__device__ __forceinline__ void grid_px(const Xform& X, const float* lx, const float* ly, int i, int jw, float& ix,
+                                        float& iy) {
+  const float xl = lx[jw], yl = ly[i];
   const float gx = __fadd_rn(__fmaf_rn(yl, X.t01, __fmul_rn(xl, X.t00)), X.t02);
   const float gy = __fadd_rn(__fmaf_rn(yl, X.t11, __fmul_rn(xl, X.t10)), X.t12);
   ix = __fmul_rn(__fadd_rn(gx, 1.f), X.sfx);
@@ -149,21 +172,20 @@ __device__ __forceinline__ void grid_consts(Xform& X, int H, int W) {
   X.sfy = (float)((double)(H - 1) / 2.0);
 }
 
-// Exhaustive decode of the warped map.  Each lane walks whole columns (the column terms of the
-// affine grid are hoisted), so the tie rule is carried by arg_better's index comparison.
-__device__ __noinline__ void decode_exhaustive(const float* __restrict__ s, float t00, float t01, float t02, float t10,
-                                               float t11, float t12, float stepx, float stepy, float sfx, float sfy,
-                                               int H, int W, bool flip, int lane, float& bv, int& bi, int row0 = 0,
-                                               int row1 = -1) {
-  bv = -INFINITY;
-  bi = 0x7fffffff;
-  if (row1 < 0) row1 = H;
+// Exhaustive decode of rows [row0, row1) of the warped map.  Each lane walks whole columns (the column terms
+// of the affine grid are hoisted), so the tie rule is carried by arg_better's index comparison; NaN aware.
+__device__ __noinline__ ArgMax decode_exhaustive(const float* __restrict__ s, const float* __restrict__ lx,
+                                                 const float* __restrict__ ly, float t00, float t01, float t02,
+                                                 float t10, float t11, float t12, float sfx, float sfy, int H, int W,
+                                                 int flip, int lane, int row0, int row1) {
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
   for (int jo = lane; jo < W; jo += 32) {
     const int jw = flip ? (W - 1 - jo) : jo;
-    const float xl = lin_coord(jw, W, stepx);
+    const float xl = lx[jw];
     const float ax = __fmul_rn(xl, t00), ay = __fmul_rn(xl, t10);
     for (int i = row0; i < row1; ++i) {
-      const float yl = lin_coord(i, H, stepy);
+      const float yl = ly[i];
       const float gx = __fadd_rn(__fmaf_rn(yl, t01, ax), t02);
       const float gy = __fadd_rn(__fmaf_rn(yl, t11, ay), t12);
       const float ix = __fmul_rn(__fadd_rn(gx, 1.f), sfx);
@@ -189,6 +211,98 @@ __device__ __noinline__ void decode_exhaustive(const float* __restrict__ s, floa
     }
   }
   warp_argmax(bv, bi);
+  ArgMax r;
+  r.v = bv; r.i = bi;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cooperative exhaustive decode inside the CTA.  A warp whose map needs all H*W output pixels posts it as a
+// job: the map stays in the poster's staging buffer (shared memory, visible to the whole CTA) and is cut
+// into kBands bands of rows.  Every warp of the CTA looks at the job word once per map (and keeps looking
+// once it has run out of maps); whoever sees an open job claims bands until none is left.  The poster works
+// on its own job too, waits for the last band, merges the kBands partial arg-maxes and carries on -- ~2 us
+// instead of the ~25 us a single warp needs, so such a map no longer produces a tail and needs no second
+// kernel launch.  One job per CTA at a time (a second poster helps the first job while it waits).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBands = 16;
+struct CoopJob {
+  int owner;        // 0 = free, w + 1 = warp w holds the job slot
+  int band_next;    // next band to claim; >= kBands: no open job
+  int bands_done;   // bands whose partial result is written
+  int warps_done;   // warps of the CTA that have run out of maps
+  int flip;
+  const float* src;
+  float t[6];
+  float pv[kBands];
+  int pi[kBands];
+};
+
+__device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// Claims and decodes bands of the open job, if any (warp-wide call).
+__device__ __forceinline__ void coop_help(CoopJob* cj, const WDParams& p, const float* lx, const float* ly, int lane) {
+  for (;;) {
+    int b = kBands;
+    if (lane == 0 && ld_volatile_s32(&cj->band_next) < kBands) b = atomicAdd(&cj->band_next, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= kBands) return;
+    __threadfence_block();                                   // the job's parameters were written before it opened
+    const float* src = *reinterpret_cast<const float* const volatile*>(&cj->src);
+    const volatile float* t = cj->t;
+    const int flip = ld_volatile_s32(&cj->flip);
+    const int r0 = (p.H * b) / kBands, r1 = (p.H * (b + 1)) / kBands;
+    const ArgMax r = decode_exhaustive(src, lx, ly, t[0], t[1], t[2], t[3], t[4], t[5], p.sfx, p.sfy, p.H, p.W, flip,
+                                       lane, r0, r1);
+    if (lane == 0) {
+      *reinterpret_cast<volatile float*>(&cj->pv[b]) = r.v;
+      *reinterpret_cast<volatile int*>(&cj->pi[b]) = r.i;
+      __threadfence_block();
+      atomicAdd(&cj->bands_done, 1);
+    }
+  }
+}
+
+// Posts the map staged at `s` as the CTA's job, works on it, and returns its exact arg-max (warp-wide call).
+__device__ __forceinline__ ArgMax coop_exhaustive(CoopJob* cj, const WDParams& p, const float* s, const Xform& X,
+                                                  const float* lx, const float* ly, int warp, int lane) {
+  for (;;) {                                                 // take the job slot; help whoever holds it meanwhile
+    int got = 0;
+    if (lane == 0) got = (atomicCAS(&cj->owner, 0, warp + 1) == 0) ? 1 : 0;
+    got = __shfl_sync(0xffffffffu, got, 0);
+    if (got) break;
+    coop_help(cj, p, lx, ly, lane);
+  }
+  if (lane == 0) {
+    *reinterpret_cast<const float* volatile*>(&cj->src) = s;
+    volatile float* t = cj->t;
+    t[0] = X.t00; t[1] = X.t01; t[2] = X.t02; t[3] = X.t10; t[4] = X.t11; t[5] = X.t12;
+    *reinterpret_cast<volatile int*>(&cj->flip) = X.flip ? 1 : 0;
+    *reinterpret_cast<volatile int*>(&cj->bands_done) = 0;
+    __threadfence_block();
+    atomicExch(&cj->band_next, 0);                           // opens the job
+  }
+  __syncwarp();
+  coop_help(cj, p, lx, ly, lane);
+  if (lane == 0) {
+    while (ld_volatile_s32(&cj->bands_done) < kBands) {
+    }
+    __threadfence_block();
+  }
+  __syncwarp();
+  ArgMax r;
+  r.v = -INFINITY; r.i = 0x7fffffff;
+  if (lane < kBands) {
+    r.v = *reinterpret_cast<const volatile float*>(&cj->pv[lane]);
+    r.i = ld_volatile_s32(&cj->pi[lane]);
+  }
+  warp_argmax(r.v, r.i);
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    atomicExch(&cj->owner, 0);
+  }
+  return r;
 }
 
 // 3-input float min that PROPAGATES NaN (SASS FMNMX3.NAN): the running minimum turns NaN if any texel
@@ -205,11 +319,9 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 }
 
 // Pass A over the staged map at float4 granularity: per-lane max (value, first float4 index) and a
-// NaN-propagating running min.  TWO = true also keeps the lane's second-best float4 maximum (bv2), which
-// lets the early-release variant prove that every candidate texel of the lane sits in its best float4.
-template <bool TWO>
-__device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float& bv, int& bq, float& bv2, float& mn) {
-  bv = -INFINITY; bv2 = -INFINITY; bq = 0; mn = INFINITY;
+// NaN-propagating running min.
+__device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float& bv, int& bq, float& mn) {
+  bv = -INFINITY; bq = 0; mn = INFINITY;
   const int nq = HW >> 2;
   const float4* s4 = reinterpret_cast<const float4*>(s);
   int q = lane;
@@ -221,23 +333,29 @@ __device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float
     for (int u = 0; u < 8; ++u) {
       const float m4 = fmaxf(max3(x[u].x, x[u].y, x[u].z), x[u].w);
       mn = min3_nan(x[u].z, x[u].w, min3_nan(x[u].x, x[u].y, mn));
-      if (m4 > bv) { if (TWO) bv2 = bv; bv = m4; bq = q + 32 * u; }
-      else if (TWO) bv2 = fmaxf(bv2, m4);
+      if (m4 > bv) { bv = m4; bq = q + 32 * u; }
     }
   }
   for (; q < nq; q += 32) {
     const float4 x = s4[q];
     const float m4 = fmaxf(max3(x.x, x.y, x.z), x.w);
     mn = min3_nan(x.z, x.w, min3_nan(x.x, x.y, mn));
-    if (m4 > bv) { if (TWO) bv2 = bv; bv = m4; bq = q; }
-    else if (TWO) bv2 = fmaxf(bv2, m4);
+    if (m4 > bv) { bv = m4; bq = q; }
   }
+}
+
+// Source channel of output joint j of (view, sample) vb: the joint itself, or its left/right partner when
+// the view is flipped and a swap table is given.
+__device__ __forceinline__ unsigned src_joint(const WDParams& p, unsigned vb, unsigned j) {
+  if (p.swap_perm && p.flip && p.flip[vb]) return (unsigned)p.swap_perm[j];
+  return j;
 }
 
 __device__ __forceinline__ const float* map_src(const WDParams& p, long long n) {
   unsigned vb, j, v, b;
   p.divJ.divmod((unsigned)n, vb, j);
   p.divB.divmod(vb, v, b);
+  j = src_joint(p, vb, j);
   return p.maps + (long long)v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
 }
 
@@ -245,54 +363,6 @@ __device__ __forceinline__ void issue_map(const WDParams& p, long long n, float*
                                           uint32_t bytes) {
   mbar_arrive_expect_tx(bar, bytes);
   bulk_g2s(dst, map_src(p, n), bytes, bar, pol);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Where the phases after pass A read the texels of the current map from: the staged map itself (smem),
-// the map in global memory (L2), or -- early-release variant -- a small window around the arg-max texel
-// copied out of the staging buffer so that the buffer can take the next map while this one is finished.
-// Texel (y, x) is base[y * ld + x]; only [x0, x1) x [y0, y1) may be dereferenced.
-// ---------------------------------------------------------------------------------------------------
-struct Src {
-  const float* base;
-  int ld, x0, y0, x1, y1;
-};
-
-// eval_px on a source view.  WIN = true: a corner that lies inside the map but outside the window sets
-// `miss` (the caller then repeats the map on the full view); nothing outside the window is dereferenced.
-template <bool WIN>
-__device__ __forceinline__ float eval_src(const Src& S, const Xform& X, int i, int jw, bool& miss) {
-  const float xl = lin_coord(jw, X.W, X.stepx);
-  const float yl = lin_coord(i, X.H, X.stepy);
-  const float gx = __fadd_rn(__fmaf_rn(yl, X.t01, __fmul_rn(xl, X.t00)), X.t02);
-  const float gy = __fadd_rn(__fmaf_rn(yl, X.t11, __fmul_rn(xl, X.t10)), X.t12);
-  const float ix = __fmul_rn(__fadd_rn(gx, 1.f), X.sfx);
-  const float iy = __fmul_rn(__fadd_rn(gy, 1.f), X.sfy);
-  const float x0f = floorf(ix), y0f = floorf(iy);
-  const float w = __fsub_rn(ix, x0f), e = __fsub_rn(1.f, w);
-  const float n = __fsub_rn(iy, y0f), so = __fsub_rn(1.f, n);
-  const float nw = __fmul_rn(so, e), ne = __fmul_rn(so, w), sw = __fmul_rn(n, e), se = __fmul_rn(n, w);
-  const int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)(X.W + 1));
-  const int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)(X.H + 1));
-  bool xa = (x0 >= 0) & (x0 < X.W), xb = (x0 + 1 >= 0) & (x0 + 1 < X.W);
-  bool ya = (y0 >= 0) & (y0 < X.H), yb = (y0 + 1 >= 0) & (y0 + 1 < X.H);
-  if (WIN) {
-    const bool wxa = (x0 >= S.x0) & (x0 < S.x1), wxb = (x0 + 1 >= S.x0) & (x0 + 1 < S.x1);
-    const bool wya = (y0 >= S.y0) & (y0 < S.y1), wyb = (y0 + 1 >= S.y0) & (y0 + 1 < S.y1);
-    miss = miss | ((xa & ya) & !(wxa & wya)) | ((xb & ya) & !(wxb & wya)) | ((xa & yb) & !(wxa & wyb)) |
-           ((xb & yb) & !(wxb & wyb));
-    xa &= wxa; xb &= wxb; ya &= wya; yb &= wyb;
-  }
-  const float* r0 = S.base + y0 * S.ld + x0;
-  const float v_nw = (xa & ya) ? r0[0] : 0.f;
-  const float v_ne = (xb & ya) ? r0[1] : 0.f;
-  const float v_sw = (xa & yb) ? r0[S.ld] : 0.f;
-  const float v_se = (xb & yb) ? r0[S.ld + 1] : 0.f;
-  float acc = __fmul_rn(v_nw, nw);
-  acc = __fmaf_rn(v_ne, ne, acc);
-  acc = __fmaf_rn(v_sw, sw, acc);
-  acc = __fmaf_rn(v_se, se, acc);
-  return acc;
 }
 
 // K2 of one (sample, joint), run by the warp that decoded its last view (see K2Fuse).  Same float op order
@@ -312,6 +382,7 @@ __device__ __forceinline__ void k2_item(const WDParams& p, long long item, int j
     do {                                                 // bounded: a lost word must not turn into a hung GPU
       asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(sp) : "memory");
     } while (v == 0ull && ++spins < (1 << 24));
+    if (v == 0ull && f.status) atomicExch(f.status, 1);  // ... but it must not pass silently either
     v = ~v;
     x = __uint_as_float((unsigned)(v & 0xffffffffull));
     y = __uint_as_float((unsigned)(v >> 32));
@@ -334,7 +405,7 @@ __device__ __forceinline__ void k2_item(const WDParams& p, long long item, int j
   if (f.dist) f.dist[item] = dist;
   if (f.legal) f.legal[item] = legal ? 1 : 0;
   if (f.mode == 2) {
-    const double thr = __dsub_rn(1.0, exp(-__ddiv_rn(__dmul_rn(f.distThrMax, 3.0), 5.0)));
+    const double thr = f.thr;
     const double unc = __dsub_rn(1.0, exp(-__ddiv_rn(dist, 5.0)));
     const bool en = legal && (unc <= thr);
     const Gauss g = gauss_setup(mx, my, f.img_h, f.img_w, f.stride, f.sigma);
@@ -364,6 +435,7 @@ __device__ __forceinline__ void k2_item_dual(const WDParams& p, long long item, 
     do {
       asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(sp) : "memory");
     } while (v == 0ull && ++spins < (1 << 24));
+    if (v == 0ull && f.status) atomicExch(f.status, 1);  // ... but it must not pass silently either
     v = ~v;
     x = __uint_as_float((unsigned)(v & 0xffffffffull));
     y = __uint_as_float((unsigned)(v >> 32));
@@ -387,6 +459,7 @@ __device__ __forceinline__ void k2_item_dual(const WDParams& p, long long item, 
   double sd[2] = {0.0, 0.0}, se = 0.0;
   const int P = Kt * (Kt - 1) / 2;
   if (full) {
+#pragma unroll
     for (int m = 0; m < 2; ++m) {
       for (int base = 0; base < P; base += 32) {
         // pair number base + lane in combinations order -> (u, v)
@@ -433,7 +506,7 @@ __device__ __forceinline__ void k2_item_dual(const WDParams& p, long long item, 
   if (f.dist) f.dist[item] = ext;
   if (f.legal) f.legal[item] = legal > 0.0 ? 1 : 0;
   if (f.mode == 4) {
-    const double thr = __dsub_rn(1.0, exp(-__ddiv_rn(__dmul_rn(f.distThrMax, 3.0), 5.0)));
+    const double thr = f.thr;
     const double unc = __dsub_rn(1.0, exp(-__ddiv_rn(ext, 5.0)));
     const bool en = (legal > 0.0) && (unc <= thr);
     const Gauss g = gauss_setup(c32x, c32y, f.img_h, f.img_w, f.stride, f.sigma);
@@ -448,8 +521,8 @@ __device__ __forceinline__ void k2_item_dual(const WDParams& p, long long item, 
 // Epilogue of one map (warp-wide call): arg-max -> heat-map coordinates (mask, optional quarter-offset
 // refinement) -> image-space coordinates -> outputs -> (optional) arrival at the item's K2.
 __device__ __forceinline__ void finish_map(const WDParams& p, long long n, int v, int b, int j, const float* s, const Xform& X,
-                                           float rv, int ri, double dc0, double dc1, double dc2, double dc3, int lane,
-                                           long long& pend_item, unsigned& pend_old) {
+                                           const float* lx, const float* ly, float rv, int ri, double dc0, double dc1,
+                                           double dc2, double dc3, int lane, long long& pend_item, unsigned& pend_old) {
   const int H = p.H, W = p.W;
   unsigned ayu, axu;
   p.divW.divmod((unsigned)ri & 0x7fffffffu, ayu, axu);
@@ -466,7 +539,7 @@ __device__ __forceinline__ void finish_map(const WDParams& p, long long n, int v
         const int di = (lane == 2) ? 1 : (lane == 3 ? -1 : 0);
         const int dj = (lane == 0) ? 1 : (lane == 1 ? -1 : 0);
         const int i = ay + di, jo = ax + dj;
-        nb = p.do_warp ? eval_px(s, X, i, X.flip ? (W - 1 - jo) : jo) : s[i * W + jo];
+        nb = p.do_warp ? eval_tab(s, X, lx, ly, i, X.flip ? (W - 1 - jo) : jo) : s[i * W + jo];
       }
       const float xp = __shfl_sync(0xffffffffu, nb, 0), xm = __shfl_sync(0xffffffffu, nb, 1);
       const float yp = __shfl_sync(0xffffffffu, nb, 2), ym = __shfl_sync(0xffffffffu, nb, 3);
@@ -514,8 +587,10 @@ __device__ __forceinline__ void k2_resolve(const WDParams& p, long long& pend_it
   if (old == (unsigned)(p.k2.K - 1)) {
     __syncwarp();
     if (lane == 0) p.k2.arrive[pend_item] = 0u;          // ready for the next launch on this workspace
-    if (p.k2.mode >= 3) k2_item_dual(p, pend_item, (int)(pend_item % p.J), lane);
-    else k2_item(p, pend_item, (int)(pend_item % p.J), lane);
+    unsigned ib, ij;
+    p.divJ.divmod((unsigned)pend_item, ib, ij);
+    if (p.k2.mode >= 3) k2_item_dual(p, pend_item, (int)ij, lane);
+    else k2_item(p, pend_item, (int)ij, lane);
   }
   pend_item = -1;
 }
@@ -523,22 +598,19 @@ __device__ __forceinline__ void k2_resolve(const WDParams& p, long long& pend_it
 // What pass A leaves for the later phases.
 struct PassA {
   float bv; int bi;                  // warp-uniform source maximum and its first flat index
-  float lane_max, lane_max2; int bq; // this lane's best / second-best float4 maximum and the best one's index
-  float a, bb, d, e, c0, f0, C00, C01, C10, C11;   // approximate pixel-space affine and its inverse (boxes only)
+  float lane_max;                    // this lane's best float4 maximum
+  float c0, f0, C00, C01, C10, C11;  // approximate pixel-space affine offset and inverse (boxes only)
 };
 
-// Phases L, B and C (see the header comment) on a source view.  On return: `exhaustive` asks for the
-// exhaustive decode, otherwise (rv, ri) is the exact result.  WIN = true (window view): `miss` reports that
-// the window did not cover everything the phases had to read -- the result is then void.
-template <bool WIN>
-__device__ __forceinline__ void decode_late(const WDParams& p, const Src& S, const Xform& X, const PassA& A, int lane,
-                                            float& rv, int& ri, bool& exhaustive, bool& miss,
-                                            unsigned long long& n_eval) {
+// Phases L, B and C (see the header comment) on the staged map.  On return: `exhaustive` asks for the
+// exhaustive decode, otherwise (rv, ri) is the exact result.
+__device__ __forceinline__ void decode_pruned(const WDParams& p, const float* __restrict__ s, const Xform& X,
+                                              const float* lx, const float* ly, const PassA& A, int lane, float& rv,
+                                              int& ri, bool& exhaustive, unsigned long long& n_eval) {
   const int H = p.H, W = p.W, HW = H * W;
   const float c0 = A.c0, f0 = A.f0, C00 = A.C00, C01 = A.C01, C10 = A.C10, C11 = A.C11;
   const float bv = A.bv;
   const int bi = A.bi;
-  bool lmiss = false;
   float L = -INFINITY; int Li = 0x7fffffff;
   const float kSlack = 1.9073486328125e-06f;   // 2^-19
   float T = 0.f;
@@ -549,30 +621,17 @@ __device__ __forceinline__ void decode_late(const WDParams& p, const Src& S, con
     p.divW.divmod((unsigned)bi, biy, bix);
     const float sx = (float)bix - c0, sy = (float)biy - f0;
     const float oj = C00 * sx + C01 * sy, oi = C10 * sx + C11 * sy;
-    if (WIN) {
-      // 4 x 4 pixels: their footprints stay within ~6 texels of the arg-max texel, inside the window
-      if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 16) {
-        const int jw = (int)floorf(oj) - 1 + (lane & 3);
-        const int i = (int)floorf(oi) - 1 + (lane >> 2);
-        if (jw >= 0 && jw < W && i >= 0 && i < H) {
-          L = eval_src<WIN>(S, X, i, jw, lmiss);
-          Li = i * W + (X.flip ? (W - 1 - jw) : jw);
-        }
+    if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 30) {
+      const int r = (lane * 43) >> 8;                        // lane / 6 for lane < 30
+      const int jw = (int)floorf(oj) - 2 + (lane - 6 * r);
+      const int i = (int)floorf(oi) - 2 + r;
+      if (jw >= 0 && jw < W && i >= 0 && i < H) {
+        L = eval_tab(s, X, lx, ly, i, jw);
+        Li = i * W + (X.flip ? (W - 1 - jw) : jw);
       }
-      n_eval += 16;
-    } else {
-      if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 30) {
-        const int jw = (int)floorf(oj) - 2 + (lane % 6);
-        const int i = (int)floorf(oi) - 2 + (lane / 6);
-        if (jw >= 0 && jw < W && i >= 0 && i < H) {
-          L = eval_src<WIN>(S, X, i, jw, lmiss);
-          Li = i * W + (X.flip ? (W - 1 - jw) : jw);
-        }
-      }
-      n_eval += 30;
     }
-    if (WIN && __any_sync(0xffffffffu, lmiss)) { miss = true; return; }
-    warp_argmax(L, Li);
+    n_eval += 30;
+    warp_argmax_finite(L, Li);
     // Candidate threshold.  For a pixel whose four (zero-extended) corners are all < T the computed sample
     // is < L: the fma chain rounds by at most 4 ulp of sum(w|v|), and negative corners lower the exact
     // value by more than the rounding they add, so 2^-19 relative slack covers it.
@@ -594,7 +653,7 @@ __device__ __forceinline__ void decode_late(const WDParams& p, const Src& S, con
 #pragma unroll
       for (int endc = 0; endc < 2; ++endc) {
         float ix, iy;
-        grid_px(X, i, endc ? W - 1 : 0, ix, iy);
+        grid_px(X, lx, ly, i, endc ? W - 1 : 0, ix, iy);
         inside = inside && (ix >= 0.f) && (ix <= (float)(W - 1)) && (iy >= 0.f) && (iy <= (float)(H - 1));
         const bool z = (ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H);
         if (z) zrow = min(zrow, i);
@@ -608,12 +667,11 @@ __device__ __forceinline__ void decode_late(const WDParams& p, const Src& S, con
       int zcol = 0x7fffffff;
       for (int jo = lane; jo < W; jo += 32) {
         float ix, iy;
-        grid_px(X, zrow, X.flip ? (W - 1 - jo) : jo, ix, iy);
+        grid_px(X, lx, ly, zrow, X.flip ? (W - 1 - jo) : jo, ix, iy);
         if ((ix <= -1.f) || (ix >= (float)W) || (iy <= -1.f) || (iy >= (float)H)) zcol = min(zcol, jo);
       }
       zcol = __reduce_min_sync(0xffffffffu, zcol);
-      bool nomiss = false;                                               // a Z pixel dereferences no texel at all
-      rv = eval_src<WIN>(S, X, zrow, X.flip ? (W - 1 - zcol) : zcol, nomiss);   // +-0, exactly what the warp produces there
+      rv = eval_tab(s, X, lx, ly, zrow, X.flip ? (W - 1 - zcol) : zcol);   // +-0, exactly what the warp produces there
       ri = zrow * W + zcol;
       solved = true;
       n_eval += 2 * H + W;
@@ -624,67 +682,37 @@ __device__ __forceinline__ void decode_late(const WDParams& p, const Src& S, con
   if (prune && !solved && !exhaustive) {
     // ---- pass B: bounding box of the candidate texels (v >= T) -----------------------
     int txmin = W, txmax = -1, tymin = H, tymax = -1;
-    if (WIN) {
-      // Every candidate must sit inside the window: a lane whose second-best float4 reaches T may hold
-      // candidates anywhere, and a lane whose best float4 reaches T must have it inside the window.
-      const int w4 = W >> 2;
-      const int qy = A.bq / w4, qx = (A.bq - qy * w4) << 2;
-      const bool in_win = (qy >= S.y0) & (qy < S.y1) & (qx >= S.x0) & (qx + 3 < S.x1);
-      const bool bad = (A.lane_max2 >= T) || ((A.lane_max >= T) && !in_win);
-      if (__any_sync(0xffffffffu, bad)) { miss = true; return; }
-      const float* win = S.base + S.y0 * S.ld + S.x0;                   // the window's own storage, row stride ld
-      const int wq = (S.x1 - S.x0) >> 2, nwq = wq * (S.y1 - S.y0);
-      for (int t = lane; t < nwq; t += 32) {
-        const int r = t / wq, c4 = t - r * wq;
-        const int ty = S.y0 + r, tx0 = S.x0 + (c4 << 2);
-        if (ty < 0 || ty >= H || tx0 < 0 || tx0 >= W) continue;         // window cells outside the map
-        const float4 x = *reinterpret_cast<const float4*>(win + r * S.ld + (c4 << 2));
-        if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= T) {
-          const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (xs[c] >= T) {
-              txmin = min(txmin, tx0 + c); txmax = max(txmax, tx0 + c); tymin = min(tymin, ty); tymax = max(tymax, ty);
-            }
-        }
+    const int nq = HW >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+    auto hit = [&](int k) {
+      unsigned ty, tx;
+      p.divW.divmod((unsigned)k, ty, tx);
+      txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
+    };
+    auto visit = [&](const float4& x, int q) {
+      if (fmaxf(max3(x.x, x.y, x.z), x.w) >= T) {
+        if (x.x >= T) hit((q << 2) + 0);
+        if (x.y >= T) hit((q << 2) + 1);
+        if (x.z >= T) hit((q << 2) + 2);
+        if (x.w >= T) hit((q << 2) + 3);
+      }
+    };
+    // lane l scanned the float4s q = l (mod 32) in pass A and knows their maximum (lane_max):
+    // only the residue classes whose maximum reaches T can hold candidates.  All 32 lanes
+    // re-read one such class together (32 float4 per step).
+    unsigned hot = __ballot_sync(0xffffffffu, A.lane_max >= T);
+    if (__popc(hot) <= 12) {
+      while (hot) {
+        const int h = __ffs(hot) - 1;
+        hot &= hot - 1;
+        for (int q = h + 32 * lane; q < nq; q += 1024) visit(s4[q], q);
       }
     } else {
-      const float* s = S.base;
-      const int nq = HW >> 2;
-      const float4* s4 = reinterpret_cast<const float4*>(s);
-      auto visit = [&](const float4& x, int q) {
-        if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) >= T) {
-          const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (xs[c] >= T) {
-              unsigned ty, tx;
-              p.divW.divmod((unsigned)((q << 2) + c), ty, tx);
-              txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
-            }
-        }
-      };
-      // lane l scanned the float4s q = l (mod 32) in pass A and knows their maximum (lane_max):
-      // only the residue classes whose maximum reaches T can hold candidates.  All 32 lanes
-      // re-read one such class together (32 float4 per step).
-      unsigned hot = __ballot_sync(0xffffffffu, A.lane_max >= T);
-      if (__popc(hot) <= 12) {
-        while (hot) {
-          const int h = __ffs(hot) - 1;
-          hot &= hot - 1;
-          for (int q = h + 32 * lane; q < nq; q += 1024) visit(s4[q], q);
-        }
-      } else {
 #pragma unroll 4
-        for (int q = lane; q < nq; q += 32) visit(s4[q], q);
-      }
-      for (int k = (nq << 2) + lane; k < HW; k += 32)
-        if (s[k] >= T) {
-          unsigned ty, tx;
-          p.divW.divmod((unsigned)k, ty, tx);
-          txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
-        }
+      for (int q = lane; q < nq; q += 32) visit(s4[q], q);
     }
+    for (int k = (nq << 2) + lane; k < HW; k += 32)
+      if (s[k] >= T) hit(k);
     txmin = __reduce_min_sync(0xffffffffu, txmin); txmax = __reduce_max_sync(0xffffffffu, txmax);
     tymin = __reduce_min_sync(0xffffffffu, tymin); tymax = __reduce_max_sync(0xffffffffu, tymax);
     // pre-image of [txmin-1, txmax+1] x [tymin-1, tymax+1] -> bounding box in the warped frame
@@ -709,57 +737,56 @@ __device__ __forceinline__ void decode_late(const WDParams& p, const Src& S, con
       for (int t = lane; t < area; t += 32, ci += di, cj += dj) {
         if (cj >= bw) { cj -= bw; ++ci; }
         const int i = imin + ci, jw = jmin + cj;
-        const float v = eval_src<WIN>(S, X, i, jw, lmiss);
+        const float v = eval_tab(s, X, lx, ly, i, jw);
         const int k = i * W + (X.flip ? (W - 1 - jw) : jw);
-        if (arg_better(v, k, rv, ri)) { rv = v; ri = k; }
+        if ((v > rv) || (v == rv && k < ri)) { rv = v; ri = k; }
       }
       n_eval += area;
-      if (WIN && __any_sync(0xffffffffu, lmiss)) { miss = true; return; }
-      warp_argmax(rv, ri);
+      warp_argmax_finite(rv, ri);
     }
   }
 }
 
 // One warp per heat-map, maps claimed from a global counter, each staged in the warp's shared-memory buffer by
-// a 1-D bulk async copy (TMA engine).
-// EARLY = false: the staged map serves every phase; the next copy starts when the map is finished.
-// EARLY = true : after pass A a 16 x 16 window around the arg-max texel is copied aside and the buffer is
-//                handed to the next copy at once, so the copy latency overlaps phases L/B/C of this map.  The
-//                phases run on the window; the few maps whose candidates or footprints leave it are repeated
-//                on the map in global memory (L2), which gives the same exact result.
-constexpr int kWin = 16;                                    // window edge (texels)
-template <bool EARLY>
+// a 1-D bulk async copy (TMA engine); the next copy starts when the map is finished.
 __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, W = p.W, HW = H * W;
   const uint32_t map_bytes = (uint32_t)HW * 4u;
-  const uint32_t buf_stride = ((map_bytes + 127u) & ~127u) + (EARLY ? kWin * kWin * 4u : 0u);   // 128 B aligned
+  const uint32_t buf_stride = (map_bytes + 127u) & ~127u;                                        // 128 B aligned
   float* buf0 = reinterpret_cast<float*>(smem_raw + (size_t)warp * buf_stride);
-  float* winbuf = buf0 + (((map_bytes + 127u) & ~127u) >> 2);                                    // EARLY only
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warps * buf_stride) + warp;
+  unsigned char* tail = smem_raw + (size_t)warps * buf_stride;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tail) + warp;                                      // 16 x 8 bytes
+  CoopJob* cj = reinterpret_cast<CoopJob*>(tail + 128);                                          // 256 bytes
+  float* lx = reinterpret_cast<float*>(tail + 384);                                              // [W] base grid, columns
+  float* ly = lx + W;                                                                            // [H] base grid, rows
 
   const long long N = (long long)p.V * p.B * p.J;
   uint64_t pol = 0;
+  if (threadIdx.x == 0) {
+    cj->owner = 0; cj->band_next = kBands; cj->bands_done = 0; cj->warps_done = 0;
+  }
+  for (int k = threadIdx.x; k < W; k += blockDim.x) lx[k] = lin_coord(k, W, p.stepx);
+  for (int k = threadIdx.x; k < H; k += blockDim.x) ly[k] = lin_coord(k, H, p.stepy);
   // dynamic work distribution: every warp claims the next map index from a global counter, so a
-  // warp that meets an exhaustively decoded map does not delay a fixed share of the work.  The claim is
+  // warp that meets an expensive map does not delay a fixed share of the work.  The claim is
   // split in two: the atomic is ISSUED one map ahead (claim_issue) and its result is only read when the
   // staging buffer is free again (claim_get), so its ~1 us round trip to L2 overlaps the decode instead of
   // sitting between two maps.
   unsigned long long claim_reg = 0;                      // lane 0: result of the atomic in flight
   auto claim_issue = [&]() {
-    // volatile asm: a plain atomicAdd is sunk by the compiler to the first use of its result (the ncu source
-    // page showed the whole round trip on the shuffle in claim_get), which defeats issuing it a map ahead
+    // volatile asm: a plain atomicAdd is sunk by the compiler to the first use of its result
     if (lane == 0) asm volatile("atom.add.relaxed.gpu.global.u64 %0, [%1], 1;" : "=l"(claim_reg) : "l"(p.work) : "memory");
   };
   auto claim_get = [&]() -> long long { return (long long)__shfl_sync(0xffffffffu, claim_reg, 0); };
+  claim_issue();
   if (p.use_bulk && lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
     pol = l2_evict_first_policy();
   }
-  __syncwarp();
-  claim_issue();
+  __syncthreads();
   long long cur = claim_get();
   if (p.use_bulk && lane == 0 && cur < N) issue_map(p, cur, buf0, bar, pol, map_bytes);
   claim_issue();
@@ -771,7 +798,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     return nn;
   };
 
-  unsigned long long n_slow = 0, n_eval = 0, n_maps = 0, n_miss = 0;
+  unsigned long long n_slow = 0, n_eval = 0, n_maps = 0;
   long long pend_item = -1;                              // K2 ticket of the previous map (see finish_map)
   unsigned pend_old = 0;
   long long it = 0;                                      // staged copies waited for so far (mbarrier parity)
@@ -779,46 +806,49 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     const long long n = cur;
     if (n >= N) break;
     const float* s = buf0;
+    // an exhaustive job posted by another warp of this CTA: help before this map (whose copy is in flight)
+    if (p.do_warp && ld_volatile_s32(&cj->band_next) < kBands) coop_help(cj, p, lx, ly, lane);
     unsigned vbu, ju, vu, bu;
     p.divJ.divmod((unsigned)n, vbu, ju);
     p.divB.divmod(vbu, vu, bu);
     const int j = (int)ju, b = (int)bu;
     const long long vb = (long long)vbu;
-    const float* gsrc = p.maps + (long long)vu * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
     // ---- per-map transform set-up, issued BEFORE waiting for the staged map so that the global loads of
     // theta / flip / dec and the inverse-affine arithmetic overlap the copy latency
     Xform X;
     X.H = H; X.W = W; X.flip = false;
+    X.t00 = X.t01 = X.t02 = X.t10 = X.t11 = X.t12 = 0.f;
+    X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
     PassA A;
-    A.a = A.bb = A.d = A.e = A.c0 = A.f0 = A.C00 = A.C01 = A.C10 = A.C11 = 0.f;
+    A.c0 = A.f0 = A.C00 = A.C01 = A.C10 = A.C11 = 0.f;
     bool bad_xform = false;
     double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
     if (p.dec) { const double* c = p.dec + (size_t)b * 4; dc0 = c[0]; dc1 = c[1]; dc2 = c[2]; dc3 = c[3]; }
     if (p.do_warp) {
       load_xform(X, p.theta, p.flip, vb, H, W);
-      X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
       // pixel-space affine  ix = a*jw + bb*i + c0 ; iy = d*jw + e*i + f0  (approximate, for boxes only)
-      A.a = X.t00 * X.stepx * X.sfx; A.bb = X.t01 * X.stepy * X.sfx;
-      A.d = X.t10 * X.stepx * X.sfy; A.e = X.t11 * X.stepy * X.sfy;
+      const float a = X.t00 * X.stepx * X.sfx, bb = X.t01 * X.stepy * X.sfx;
+      const float d = X.t10 * X.stepx * X.sfy, e = X.t11 * X.stepy * X.sfy;
       A.c0 = (X.t02 + 1.f - X.t00 - X.t01) * X.sfx; A.f0 = (X.t12 + 1.f - X.t10 - X.t11) * X.sfy;
-      const float det = A.a * A.e - A.bb * A.d;
-      const float nrm = fabsf(A.a) + fabsf(A.bb) + fabsf(A.d) + fabsf(A.e);
+      const float det = a * e - bb * d;
+      const float nrm = fabsf(a) + fabsf(bb) + fabsf(d) + fabsf(e);
       bad_xform = !(fabsf(det) > 1e-5f * nrm * nrm) || !(nrm < 1e4f) || W <= 1 || H <= 1;
       const float idet = 1.f / det;
-      A.C00 = A.e * idet; A.C01 = -A.bb * idet; A.C10 = -A.d * idet; A.C11 = A.a * idet;
+      A.C00 = e * idet; A.C01 = -bb * idet; A.C10 = -d * idet; A.C11 = a * idet;
     }
     if (p.use_bulk) {
       mbar_wait(bar, (uint32_t)(it & 1));
     } else {
+      const float* gsrc = map_src(p, n);
       for (int k = lane; k < HW; k += 32) buf0[k] = __ldg(gsrc + k);
       __syncwarp();
     }
     ++n_maps;
 
     // ---- pass A: raw max / location / min / finiteness -----------------------------------------
-    float bv, bv2, mn; int bq;
-    scan_max<EARLY>(s, HW, lane, bv, bq, bv2, mn);
-    A.lane_max = bv; A.lane_max2 = bv2; A.bq = bq;   // per-lane float4 maxima (pass B reuses them)
+    float bv, mn; int bq;
+    scan_max(s, HW, lane, bv, bq, mn);
+    A.lane_max = bv;                       // per-lane float4 maximum (pass B reuses it)
     int bi = 0x7fffffff;                  // flat index of the lane's first maximum
     if (bv > -INFINITY) {
       const float4 x = reinterpret_cast<const float4*>(s)[bq];
@@ -832,155 +862,88 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     // NaN -> mn is NaN; -inf -> mn == -inf; +inf -> bv == +inf
     const bool nonfinite = __any_sync(0xffffffffu, !(mn >= -FLT_MAX) || !(bv <= FLT_MAX));
     float rv = bv; int ri = bi;           // result (value, canonical flat index)
-    if (p.do_warp) warp_argmax(bv, bi);   // warp-uniform source max / location
-    A.bv = bv; A.bi = bi;
 
-    long long nxt = N;
-    Src win;
-    if (EARLY) {
-      // copy the window around the arg-max texel aside, then release the staging buffer to the next map
-      unsigned biy = 0, bix = 0;
-      if (p.do_warp && bi != 0x7fffffff) p.divW.divmod((unsigned)bi, biy, bix);
-      win.ld = kWin;
-      win.x0 = (((int)bix - 6) >> 2) << 2;                  // multiple of 4: margins of 6..9 texels either side
-      win.y0 = (int)biy - 7;
-      win.x1 = win.x0 + kWin; win.y1 = win.y0 + kWin;
-      win.base = winbuf - (win.y0 * kWin + win.x0);
-      if (p.do_warp) {
-        const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-#pragma unroll
-        for (int t = lane; t < kWin * kWin / 4; t += 32) {
-          const int r = t >> 2, c4 = t & 3;
-          const int y = win.y0 + r, x = win.x0 + (c4 << 2);
-          float4 v = ninf;
-          if (y >= 0 && y < H && x >= 0 && x + 3 < W) v = *reinterpret_cast<const float4*>(s + y * W + x);
-          reinterpret_cast<float4*>(winbuf)[t] = v;
-        }
-      }
-      __syncwarp();
-      nxt = advance();
-      s = gsrc;                             // anything else reads the map from global memory (L2)
-    }
-
-    bool deferred = false;
     if (!p.do_warp) {
       if (nonfinite) {                    // torch.max: the first NaN wins; +-Inf compare normally
         rv = -INFINITY; ri = 0x7fffffff;
         for (int k = lane; k < HW; k += 32) { const float x = s[k]; if (arg_better(x, k, rv, ri)) { rv = x; ri = k; } }
+        warp_argmax(rv, ri);
+      } else {
+        warp_argmax_finite(rv, ri);
       }
-      warp_argmax(rv, ri);
     } else {
       bool exhaustive = nonfinite || bad_xform;
       if (!exhaustive) {
-        const Src full = {s, W, 0, 0, W, H};
-        bool miss = false;
-        if (EARLY) {
-          decode_late<true>(p, win, X, A, lane, rv, ri, exhaustive, miss, n_eval);
-          if (miss) {
-            ++n_miss;
-            // the window was too small for this map: the hot float4 classes are unknown to pass B of the full
-            // view only through lane_max, which is still valid; repeat on the map in L2
-            exhaustive = false; miss = false;
-            decode_late<false>(p, full, X, A, lane, rv, ri, exhaustive, miss, n_eval);
-          }
-        } else {
-          decode_late<false>(p, full, X, A, lane, rv, ri, exhaustive, miss, n_eval);
-        }
+        warp_argmax_finite(bv, bi);       // warp-uniform source max / location
+        A.bv = bv; A.bi = bi;
+        decode_pruned(p, s, X, lx, ly, A, lane, rv, ri, exhaustive, n_eval);
       }
-      if (exhaustive && p.slow_list) {
-        // Maps that need the exhaustive decode are not decoded here: one such map would keep this warp busy
-        // for ~25 us while the rest of the grid drains.  They are queued and decoded right after this kernel
-        // by whole CTAs (warp_decode_slow_kernel).  (Draining the queue inside this launch, by all warps once
-        // the main loop is over, was measured ~4 us slower than the second launch: profiles/README.md.)
-        if (lane == 0) p.slow_list[atomicAdd(p.slow_count, 1u)] = (int)n;
-        deferred = true;
-        ++n_slow;
-      }
-      if (exhaustive && !deferred) {
-        decode_exhaustive(s, X.t00, X.t01, X.t02, X.t10, X.t11, X.t12, X.stepx, X.stepy, X.sfx, X.sfy, H, W, X.flip, lane, rv, ri);
+      if (exhaustive) {
+        const ArgMax r = coop_exhaustive(cj, p, s, X, lx, ly, warp, lane);
+        rv = r.v; ri = r.i;
         ++n_slow;
         n_eval += HW;
       }
     }
 
-    if (!deferred) {
-      k2_resolve(p, pend_item, pend_old, lane);          // the previous map's ticket has long arrived by now
-      finish_map(p, n, (int)vu, b, j, s, X, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
-    }
+    k2_resolve(p, pend_item, pend_old, lane);            // the previous map's ticket has long arrived by now
+    finish_map(p, n, (int)vu, b, j, s, X, lx, ly, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
     __syncwarp();
-    cur = EARLY ? nxt : advance();
+    cur = advance();
   }
   k2_resolve(p, pend_item, pend_old, lane);
   if (p.stats && lane == 0 && n_maps) {
     atomicAdd(p.stats + 0, n_slow);
     atomicAdd(p.stats + 1, n_eval);
     atomicAdd(p.stats + 2, n_maps);
-    atomicAdd(p.stats + 3, n_miss);
   }
-}
-
-// Exhaustive decode of the queued maps: one CTA of 16 warps per map (rows split sixteen ways), map staged in
-// shared memory; warp 0 merges the partial arg-maxes and writes the outputs.
-constexpr int kSlowWarps = 16;
-__global__ void __launch_bounds__(kSlowWarps * 32) warp_decode_slow_kernel(const WDParams p) {
-  extern __shared__ __align__(16) float sm_map[];
-  __shared__ float s_v[kSlowWarps];
-  __shared__ int s_i[kSlowWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = p.H, W = p.W, HW = H * W;
-  const unsigned count = *p.slow_count;
-  for (unsigned item = blockIdx.x; item < count; item += gridDim.x) {
-    const long long n = p.slow_list[item];
-    unsigned vbu, ju, vu, bu;
-    p.divJ.divmod((unsigned)n, vbu, ju);
-    p.divB.divmod(vbu, vu, bu);
-    const float* src = p.maps + (long long)vu * p.sV + (long long)bu * p.sB + (long long)ju * p.sJ;
-    __syncthreads();
-    if (p.use_bulk) {
-      const float4* s4 = reinterpret_cast<const float4*>(src);
-      float4* d4 = reinterpret_cast<float4*>(sm_map);
-      for (int q = threadIdx.x; q < (HW >> 2); q += blockDim.x) d4[q] = __ldg(s4 + q);
-    } else {
-      for (int k = threadIdx.x; k < HW; k += blockDim.x) sm_map[k] = __ldg(src + k);
-    }
-    __syncthreads();
-    Xform X;
-    load_xform(X, p.theta, p.flip, (long long)vbu, H, W);
-    X.stepx = p.stepx; X.stepy = p.stepy; X.sfx = p.sfx; X.sfy = p.sfy;
-    float rv; int ri;
-    const int r0 = (H * warp) / kSlowWarps, r1 = (H * (warp + 1)) / kSlowWarps;
-    decode_exhaustive(sm_map, X.t00, X.t01, X.t02, X.t10, X.t11, X.t12, X.stepx, X.stepy, X.sfx, X.sfy, H, W, X.flip,
-                      lane, rv, ri, r0, r1);
-    if (lane == 0) { s_v[warp] = rv; s_i[warp] = ri; }
-    __syncthreads();
-    if (warp == 0) {
-      rv = s_v[0]; ri = s_i[0];
-#pragma unroll
-      for (int w = 1; w < kSlowWarps; ++w) if (arg_better(s_v[w], s_i[w], rv, ri)) { rv = s_v[w]; ri = s_i[w]; }
-      double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
-      if (p.dec) { const double* c = p.dec + (size_t)bu * 4; dc0 = c[0]; dc1 = c[1]; dc2 = c[2]; dc3 = c[3]; }
-      long long pend_item = -1;
-      unsigned pend_old = 0;
-      finish_map(p, n, (int)vu, (int)bu, (int)ju, sm_map, X, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
-      k2_resolve(p, pend_item, pend_old, lane);
+  // Out of maps: stay while other warps of the CTA may still post an exhaustive job, and meanwhile pull the
+  // range the next kernel reads (pf_ptr: the student maps of K3) into L2 -- HBM is going idle as the last
+  // maps finish.
+  if (p.do_warp) {
+    __syncwarp();
+    if (lane == 0) atomicAdd(&cj->warps_done, 1);
+    constexpr unsigned kPfChunk = 32768u;
+    bool pf_live = p.pf_ptr != nullptr;
+    int tick = 0;                                        // one chunk per pf_every polls: the idle warps ask for about
+    for (;;) {                                           // the bandwidth they used while they were decoding
+      if (ld_volatile_s32(&cj->warps_done) >= warps) break;
+      if (ld_volatile_s32(&cj->band_next) < kBands) {
+        coop_help(cj, p, lx, ly, lane);
+        continue;
+      }
+      if (pf_live && (tick++ % p.pf_every) == 0) {
+        unsigned long long c = 0;
+        if (lane == 0) c = atomicAdd(p.pf_next, 1ull);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        const unsigned long long off = c * kPfChunk;
+        if (off >= p.pf_bytes) { pf_live = false; continue; }
+        const unsigned long long left = p.pf_bytes - off;
+        if (lane == 0) bulk_prefetch_l2(p.pf_ptr + off, (uint32_t)(left < kPfChunk ? left : kPfChunk));
+      }
+      __nanosleep(200);
     }
   }
 }
 
 // -----------------------------------------------------------------------------------------------
 // affine_back2 materialised: one CTA per map, source staged in shared memory, coalesced stores.
+// swap_perm (optional): output channel c of a FLIPPED sample is warped from source channel swap_perm[c]
+// (utils/udaap/transforms.py:20-57 flip_back); NULL = no exchange (utils/augment.py:37-47).
 // -----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) warp_materialize_kernel(const float* __restrict__ in, long long sN, long long sC,
                                                                float* __restrict__ out, long long oN, long long oC,
                                                                int N, int C, int H, int W,
                                                                const float* __restrict__ theta,
-                                                               const uint8_t* __restrict__ flip) {
+                                                               const uint8_t* __restrict__ flip,
+                                                               const int32_t* __restrict__ swap_perm) {
   extern __shared__ __align__(16) float sm[];
   const int HW = H * W;
   for (long long m = blockIdx.x; m < (long long)N * C; m += gridDim.x) {
     const long long n = m / C;
     const int c = (int)(m % C);
-    const float* src = in + n * sN + (long long)c * sC;
+    const int cs = (swap_perm && flip && flip[n]) ? swap_perm[c] : c;
+    const float* src = in + n * sN + (long long)cs * sC;
     float* dst = out + n * oN + (long long)c * oC;
     __syncthreads();
     for (int k = threadIdx.x; k < HW; k += blockDim.x) sm[k] = __ldg(src + k);
@@ -1008,32 +971,20 @@ __global__ void mirror_w_kernel(const float* __restrict__ in, float* __restrict_
 
 using namespace ubpl;
 
-static int launch_slow(const WDParams& p, size_t map_bytes, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(warp_decode_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin() - 1024);
-    if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute(slow): %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
-    attr_set = true;
-  }
-  warp_decode_slow_kernel<<<sm_count() * 2, kSlowWarps * 32, map_bytes, stream>>>(p);
-  return check_launch("ubpl_warp_decode(slow)");
-}
-
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
 
-// Fills the geometry / tuning fields of p and launches the main kernel (+ the exhaustive kernel when a queue
-// is given).  p.work, p.slow_*, p.k2 and the outputs are set by the caller.
-static int launch_k1(WDParams& p, cudaStream_t stream, cudaEvent_t mid_event = nullptr) {
+// Fills the geometry / tuning fields of p and launches the kernel.  p.work, p.k2, p.pf_* and the outputs are
+// set by the caller.
+static int launch_k1(WDParams& p, cudaStream_t stream) {
   const int H = p.H, W = p.W;
   const long long N = (long long)p.V * p.B * p.J;
   const long long HW = (long long)H * W;
   UBPL_REQUIRE(HW <= (1 << 24), "ubpl_warp_decode: heat-map too large (%lld texels)", HW);
   UBPL_REQUIRE(N < (1ll << 31), "ubpl_warp_decode: too many maps in one call (%lld)", N);
   const size_t map_bytes = (size_t)HW * 4;
-  const int smem_cap = smem_optin() - 2048;
   p.divJ.init((unsigned)p.J); p.divB.init((unsigned)p.B); p.divW.init((unsigned)W);
   p.stepx = (W > 1) ? 2.f / (float)(W - 1) : 0.f;
   p.stepy = (H > 1) ? 2.f / (float)(H - 1) : 0.f;
@@ -1042,83 +993,81 @@ static int launch_k1(WDParams& p, cudaStream_t stream, cudaEvent_t mid_event = n
   // bulk async copy needs 16-byte aligned sources and sizes; otherwise the warp copies the map itself
   p.use_bulk = ((reinterpret_cast<uintptr_t>(p.maps) & 15) == 0) && (map_bytes % 16 == 0) && (p.sV % 4 == 0) &&
                (p.sB % 4 == 0) && (p.sJ % 4 == 0);
-  // tuning knobs (read per call so that one process can compare them; defaults from B200 measurements):
-  //   UBPL_K1_EARLY  1 = release the staging buffer after pass A (window copy), 0 = after the whole map
-  //   UBPL_K1_WARPS  cap on the warps per CTA
-  const bool early = p.use_bulk && p.do_warp && (W % 4 == 0) && W >= 4 && env_int("UBPL_K1_EARLY", UBPL_K1_EARLY_DEFAULT) != 0;
-  const size_t buf_stride = ((map_bytes + 127) & ~(size_t)127) + (early ? (size_t)kWin * kWin * 4 : 0);
-  UBPL_REQUIRE((long long)buf_stride + 64 <= smem_cap, "ubpl_warp_decode: a %dx%d map does not fit in shared memory", H, W);
-  int warps = (int)((size_t)smem_cap / (buf_stride + 8));
+  // shared memory: one staging buffer per warp, then 16 mbarriers (128 B), the CTA's CoopJob (256 B) and the
+  // base-grid tables lx[W], ly[H]
+  static_assert(sizeof(CoopJob) <= 256, "CoopJob must fit its shared-memory slot");
+  const size_t buf_stride = (map_bytes + 127) & ~(size_t)127;
+  const size_t tail = 384 + (((size_t)(W + H) * 4 + 127) & ~(size_t)127);
+  UBPL_REQUIRE(buf_stride + tail <= (size_t)smem_optin(), "ubpl_warp_decode: a %dx%d map does not fit in shared memory", H, W);
+  int warps = (int)(((size_t)smem_optin() - tail) / buf_stride);
+  // tuning knob (read per call so that one process can compare settings): UBPL_K1_WARPS caps the warps per CTA
   const int env_warps = env_int("UBPL_K1_WARPS", 0);
   if (env_warps > 0 && env_warps < warps) warps = env_warps;
   if (warps > 16) warps = 16;
   if (warps < 1) warps = 1;
-  const size_t smem = (size_t)warps * buf_stride + (size_t)warps * 8;
+  const size_t smem = (size_t)warps * buf_stride + tail;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(warp_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(warp_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+    cudaError_t e = cudaFuncSetAttribute(warp_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
     if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
     attr_set = true;
   }
   long long need = (N + warps - 1) / warps;
   int grid = (int)(need < sm_count() ? need : sm_count());
-  if (early) warp_decode_kernel<true><<<grid, warps * 32, smem, stream>>>(p);
-  else warp_decode_kernel<false><<<grid, warps * 32, smem, stream>>>(p);
-  int rc = check_launch("ubpl_warp_decode");
-  if (rc == UBPL_OK && mid_event) {
-    // the caller forks independent work here: it then runs beside the short, nearly empty launch below
-    if (cudaEventRecord(mid_event, stream) != cudaSuccess) { set_error("ubpl_warp_decode: cudaEventRecord(mid_event) failed"); return UBPL_ERR_CUDA; }
-  }
-  if (rc != UBPL_OK || !p.slow_list) return rc;
-  return launch_slow(p, map_bytes, stream);
+  warp_decode_kernel<<<grid, warps * 32, smem, stream>>>(p);
+  return check_launch("ubpl_warp_decode");
 }
 
 extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64_t sJ, int V, int B, int J, int H,
-                                int W, const float* theta, const uint8_t* flip, const double* dec, int do_warp,
-                                int refine, int32_t* out_idx, float* out_max, float* out_xy, float* out_hm_xy,
-                                int64_t* stats, int32_t* slow_ws, void* stream) {
+                                int W, const float* theta, const uint8_t* flip, const int32_t* swap_perm,
+                                const double* dec, int do_warp, int refine, int32_t* out_idx, float* out_max,
+                                float* out_xy, float* out_hm_xy, int64_t* stats, int32_t* ws, void* stream) {
   UBPL_REQUIRE(maps != nullptr, "ubpl_warp_decode: maps is NULL");
   UBPL_REQUIRE(V >= 0 && B >= 0 && J >= 0 && H > 0 && W > 0, "ubpl_warp_decode: bad dims V=%d B=%d J=%d H=%d W=%d", V, B, J, H, W);
   UBPL_REQUIRE(!do_warp || theta != nullptr, "ubpl_warp_decode: theta is NULL with do_warp=1");
   UBPL_REQUIRE(refine >= 0 && refine <= 2, "ubpl_warp_decode: refine must be 0, 1 or 2");
+  UBPL_REQUIRE(!ws || (reinterpret_cast<uintptr_t>(ws) & 7) == 0, "ubpl_warp_decode: ws must be 8-byte aligned");
   const long long N = (long long)V * B * J;
   if (N == 0) return UBPL_OK;
   WDParams p;
   memset(&p, 0, sizeof(p));
   p.maps = maps; p.sV = sV; p.sB = sB; p.sJ = sJ; p.V = V; p.B = B; p.J = J; p.H = H; p.W = W;
-  p.theta = theta; p.flip = flip; p.dec = dec; p.do_warp = do_warp; p.refine = refine;
+  p.theta = theta; p.flip = flip; p.swap_perm = (do_warp && flip) ? swap_perm : nullptr; p.dec = dec;
+  p.do_warp = do_warp; p.refine = refine;
   p.out_idx = out_idx; p.out_max = out_max; p.out_xy = out_xy; p.out_hm_xy = out_hm_xy;
   p.stats = reinterpret_cast<unsigned long long*>(stats);
-  p.work = work_counter((cudaStream_t)stream);
-  if (!p.work) return UBPL_ERR_CUDA;
-  if (slow_ws && do_warp) {
-    p.slow_count = reinterpret_cast<unsigned*>(slow_ws);
-    p.slow_list = slow_ws + 1;
-    cudaError_t e = cudaMemsetAsync(slow_ws, 0, sizeof(int32_t), (cudaStream_t)stream);
+  if (ws) {
+    // the caller's own claim counter: private to this launch (and to a CUDA graph that captured it)
+    cudaError_t e = cudaMemsetAsync(ws, 0, 8, (cudaStream_t)stream);
     if (e != cudaSuccess) { set_error("ubpl_warp_decode: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
+    p.work = reinterpret_cast<unsigned long long*>(ws);
+  } else {
+    p.work = work_counter((cudaStream_t)stream);
+    if (!p.work) return UBPL_ERR_CUDA;
   }
   return launch_k1(p, (cudaStream_t)stream);
 }
 
-// Workspace of ubpl_warp_decode_k2, int32 words: [0,1] claim counter, [32] queue length (own 128-byte lines),
-// [128, 128+J+2) counts, then the B*J arrival counters, the V*B*J 64-bit hand-off words, and last the queue of
-// V*B*J map indices.  Everything in front of the queue is cleared by ONE memset node per launch.
+// Workspace of ubpl_warp_decode_k2, int32 words: [0,1] claim counter, [32,33] prefetch chunk counter, [34] number
+// of items with a zero intDist sum, [35] status (own 128-byte lines for the two counters), [128, 128+J+2) counts,
+// then the B*J arrival counters and the V*B*J 64-bit hand-off words.  All of it is cleared by ONE memset node per
+// launch.
 static inline long long k2_ws_arrive_off(int J) { return 128 + ((J + 2 + 1) & ~1); }
 static inline long long k2_ws_slots_off(int B, int J) { return (k2_ws_arrive_off(J) + (long long)B * J + 1) & ~1ll; }
 static inline long long k2_ws_zero_words(int V, int B, int J) { return k2_ws_slots_off(B, J) + 2ll * V * B * J; }
 
 extern "C" int64_t ubpl_warp_decode_k2_ws_bytes(int V, int B, int J) {
   if (V < 0 || B < 0 || J < 0) return 0;
-  return 4 * (k2_ws_zero_words(V, B, J) + (int64_t)V * B * J + 4);
+  return 4 * (k2_ws_zero_words(V, B, J) + 4);
 }
 
 extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ, int V, int B, int J, int H,
-                                   int W, const float* theta, const uint8_t* flip, const double* dec, int refine,
-                                   int32_t* out_idx, float* out_max, float* out_xy, int k2_mode, double distThrMax,
-                                   int img_h, int img_w, float stride, float sigma, int S, float* mean, double* dist,
-                                   uint8_t* legal, uint8_t* enable, float* gate, int64_t* stats, int32_t* ws,
-                                   int64_t ws_bytes, void* mid_event, void* stream) {
+                                   int W, const float* theta, const uint8_t* flip, const int32_t* swap_perm,
+                                   const double* dec, int refine, int32_t* out_idx, float* out_max, float* out_xy,
+                                   int k2_mode, double distThrMax, int img_h, int img_w, float stride, float sigma,
+                                   int S, float* mean, double* dist, uint8_t* legal, uint8_t* enable, float* gate,
+                                   int64_t* stats, int32_t* ws, int64_t ws_bytes, const void* prefetch,
+                                   int64_t prefetch_bytes, void* stream) {
   UBPL_REQUIRE(V >= 1 && V <= 32 && B >= 0 && J >= 1 && H > 0 && W > 0, "ubpl_warp_decode_k2: bad dims V=%d B=%d J=%d H=%d W=%d (1 <= V <= 32)", V, B, J, H, W);
   UBPL_REQUIRE(ws && (B == 0 || (maps && theta && out_xy)), "ubpl_warp_decode_k2: NULL pointer");
   UBPL_REQUIRE(refine >= 0 && refine <= 2, "ubpl_warp_decode_k2: refine must be 0, 1 or 2");
@@ -1127,39 +1076,45 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
   UBPL_REQUIRE((k2_mode & 1) || ((gate || B == 0) && S >= 1 && stride > 0.f && sigma > 0.f), "ubpl_warp_decode_k2: modes 2 and 4 need gate, S, stride, sigma");
   UBPL_REQUIRE(ws_bytes >= ubpl_warp_decode_k2_ws_bytes(V, B, J), "ubpl_warp_decode_k2: workspace too small");
   UBPL_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "ubpl_warp_decode_k2: workspace must be 8-byte aligned");
+  UBPL_REQUIRE(!prefetch || ((reinterpret_cast<uintptr_t>(prefetch) & 15) == 0 && prefetch_bytes >= 0),
+               "ubpl_warp_decode_k2: the prefetch range must be 16-byte aligned");
   const long long zero_words = k2_ws_zero_words(V, B, J);
   cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)zero_words * 4, (cudaStream_t)stream);
   if (e != cudaSuccess) { set_error("ubpl_warp_decode_k2: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
   const long long N = (long long)V * B * J;
-  if (N == 0) {
-    if (mid_event) cudaEventRecord((cudaEvent_t)mid_event, (cudaStream_t)stream);
-    return UBPL_OK;
-  }
+  if (N == 0) return UBPL_OK;
   WDParams p;
   memset(&p, 0, sizeof(p));
   p.maps = maps; p.sV = sV; p.sB = sB; p.sJ = sJ; p.V = V; p.B = B; p.J = J; p.H = H; p.W = W;
-  p.theta = theta; p.flip = flip; p.dec = dec; p.do_warp = 1; p.refine = refine;
+  p.theta = theta; p.flip = flip; p.swap_perm = flip ? swap_perm : nullptr; p.dec = dec; p.do_warp = 1; p.refine = refine;
   p.out_idx = out_idx; p.out_max = out_max; p.out_xy = out_xy; p.out_hm_xy = nullptr;
   p.stats = reinterpret_cast<unsigned long long*>(stats);
   p.work = reinterpret_cast<unsigned long long*>(ws);
-  p.slow_count = reinterpret_cast<unsigned*>(ws + 32);
-  p.slow_list = ws + zero_words;
+  if (prefetch && prefetch_bytes >= 16) {
+    p.pf_ptr = reinterpret_cast<const unsigned char*>(prefetch);
+    p.pf_bytes = (unsigned long long)prefetch_bytes & ~15ull;
+    p.pf_next = reinterpret_cast<unsigned long long*>(ws + 32);
+    p.pf_every = env_int("UBPL_K1_PF_EVERY", 8);
+    if (p.pf_every < 1) p.pf_every = 1;
+  }
   K2Fuse& f = p.k2;
   f.mode = k2_mode; f.K = V;
   f.counts = ws + 128;
-  f.zero_div = ws + 33;
+  f.zero_div = ws + 34;
+  f.status = ws + 35;
   f.arrive = reinterpret_cast<unsigned*>(ws + k2_ws_arrive_off(J));
   f.slots = reinterpret_cast<unsigned long long*>(ws + k2_ws_slots_off(B, J));
   f.distThrMax = distThrMax; f.img_h = img_h; f.img_w = img_w; f.S = S; f.stride = stride; f.sigma = sigma;
+  f.thr = 1.0 - exp(-(distThrMax * 3.0) / 5.0);       // business.py:375-376 with CPython's libm exp
   f.mean = mean; f.dist = dist; f.legal = legal; f.enable = enable; f.gate = gate;
   int rc = pow_table(&f.T.key, &f.T.val, &f.T.bits, &f.T.n, &f.T.rmax);
   if (rc != UBPL_OK) return rc;
-  return launch_k1(p, (cudaStream_t)stream, (cudaEvent_t)mid_event);
+  return launch_k1(p, (cudaStream_t)stream);
 }
 
 extern "C" int ubpl_warp_materialize(const float* in, int64_t sN, int64_t sC, float* out, int64_t oN, int64_t oC,
                                      int N, int C, int H, int W, const float* theta, const uint8_t* flip,
-                                     void* stream) {
+                                     const int32_t* swap_perm, void* stream) {
   UBPL_REQUIRE(in && out && theta, "ubpl_warp_materialize: NULL pointer");
   UBPL_REQUIRE(N >= 0 && C >= 0 && H > 0 && W > 0, "ubpl_warp_materialize: bad dims");
   if ((long long)N * C == 0) return UBPL_OK;
@@ -1173,7 +1128,8 @@ extern "C" int ubpl_warp_materialize(const float* in, int64_t sN, int64_t sC, fl
   }
   long long maps = (long long)N * C;
   int grid = (int)(maps < (long long)sm_count() * 8 ? maps : (long long)sm_count() * 8);
-  warp_materialize_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, sN, sC, out, oN, oC, N, C, H, W, theta, flip);
+  warp_materialize_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, sN, sC, out, oN, oC, N, C, H, W, theta, flip,
+                                                                      flip ? swap_perm : nullptr);
   return check_launch("ubpl_warp_materialize");
 }
 

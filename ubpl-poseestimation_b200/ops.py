@@ -1,11 +1,14 @@
 """Tensor-level wrappers over the C ABI (include/ubpl_b200.h).  torch is used for device memory,
 streams and (in dist.py) the NCCL plumbing only; every computation is a kernel of libubpl_b200.so.
 All inputs must be CUDA tensors: there is no CPU path."""
+import os
+
 import torch
 
 from . import _lib
 
 _f32, _f64 = torch.float32, torch.float64
+PF_CAP_MB = 64          # cap of K1's tail prefetch of the next kernel's input (MB)
 
 
 def _stream():
@@ -59,12 +62,32 @@ def decode_coeffs(center, scale, res):
     return torch.stack([a00, -(t02 * a00), a11, -(t12 * a11)], -1).contiguous()
 
 
+def _swap_perm(swap_perm, J, dev):
+    """int32[J] device table of flip_back's channel exchange (utils/udaap/transforms.py:20-57), or None."""
+    if swap_perm is None:
+        return None
+    t = torch.as_tensor(swap_perm).reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+    if t.numel() != J:
+        raise _lib.UbplError("swap_perm must have one entry per joint (%d), got %d" % (J, t.numel()))
+    return t
+
+
+def swap_perm_from_pairs(pairs, J):
+    """The source-channel table equivalent to flip_back's SEQUENTIAL pair exchanges
+    (utils/udaap/transforms.py:51-54): after the loop, out[:, j] = mirrored[:, perm[j]].  The '_300w' table of
+    the reference names channel 26 twice, so the result is a general permutation, not an involution."""
+    perm = list(range(J))
+    for a, b in pairs:
+        perm[a], perm[b] = perm[b], perm[a]
+    return torch.tensor(perm, dtype=torch.int32)
+
+
 def warp_decode(maps, theta=None, flip=None, dec=None, refine=0, stats=None, want_idx=True, want_hm=False,
-                defer_exhaustive=True):
+                swap_perm=None):
     """Fused back-warp + flip + arg-max decode (K1).  maps [V,B,J,H,W] or [B,J,H,W] (V=1);
     theta [V,B,2,3] (None = plain decode of the raw maps), flip [V,B] bool/uint8, dec [B,4] float64
-    from decode_coeffs (None = heat-map coordinates).  Returns dict(idx, max, xy[, hm_xy]) shaped
-    like the leading dims of `maps`."""
+    from decode_coeffs (None = heat-map coordinates), swap_perm [J] (None = no left/right exchange, the
+    reference's live path).  Returns dict(idx, max, xy[, hm_xy]) shaped like the leading dims of `maps`."""
     _need_cuda(maps, theta, flip, dec, stats)
     if maps.dtype != _f32:
         raise _lib.UbplError("heat-maps must be float32")
@@ -80,16 +103,15 @@ def warp_decode(maps, theta=None, flip=None, dec=None, refine=0, stats=None, wan
         flip = flip.reshape(V, B).to(torch.uint8).contiguous()
     if dec is not None:
         dec = dec.reshape(B, 4).to(_f64).contiguous()
+    perm = _swap_perm(swap_perm, J, dev)
     out_idx = torch.empty(V, B, J, dtype=torch.int32, device=dev) if want_idx else None
     out_max = torch.empty(V, B, J, dtype=_f32, device=dev)
     out_xy = torch.empty(V, B, J, 2, dtype=_f32, device=dev)
     out_hm = torch.empty(V, B, J, 2, dtype=_f32, device=dev) if want_hm else None
-    slow_ws = torch.empty(V * B * J + 1, dtype=torch.int32, device=dev) if (defer_exhaustive and theta is not None) else None
+    ws = torch.empty(4, dtype=torch.int32, device=dev)          # the launch's private work-claim counter
     _lib.call("ubpl_warp_decode", maps.data_ptr(), maps.stride(0), maps.stride(1), maps.stride(2), V, B, J, H, W,
-              _p(theta), _p(flip), _p(dec), 1 if theta is not None else 0, int(refine),
-              _p(out_idx), _p(out_max), _p(out_xy), _p(out_hm), _p(stats), _p(slow_ws), _stream())
-    if slow_ws is None:
-        _lib._launches -= 1                      # no second (exhaustive) kernel was launched
+              _p(theta), _p(flip), _p(perm), _p(dec), 1 if theta is not None else 0, int(refine),
+              _p(out_idx), _p(out_max), _p(out_xy), _p(out_hm), _p(stats), ws.data_ptr(), _stream())
     res = dict(idx=out_idx, max=out_max, xy=out_xy, hm_xy=out_hm)
     if squeeze:
         res = {k: (v[0] if v is not None else None) for k, v in res.items()}
@@ -97,7 +119,7 @@ def warp_decode(maps, theta=None, flip=None, dec=None, refine=0, stats=None, wan
 
 
 def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stride=4.0, sigma=3.0, distThrMax=1.0,
-                   refine=0, stats=None, want_idx=True, mid_event=None):
+                   refine=0, stats=None, want_idx=True, swap_perm=None, prefetch=None):
     """K1 with the per-joint part of K2 fused into its epilogue (maps [V,B,J,H,W], V <= 32).
     One teacher (V = K views):
       mode 1: + mean [B,J,2], dist [B,J] f64 (999 = illegal), legal [B,J]   (utils/evaluation.py:44-54)
@@ -106,8 +128,9 @@ def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stri
     Two teachers (V = 2K maps, teacher-major; theta/flip given per map):
       mode 3: mean = float32 ensemble coordinate, dist = extDist, legal, zero_div (utils/business.py:109-161)
       mode 4: + the fixed rule on extDist, gate and counts as in mode 2.
-    mid_event: a torch.cuda.Event (already recorded once, so that its handle exists) that the call records between
-    its main launch and the short launch for the queued exhaustive maps -- fork independent work on it."""
+    prefetch: a contiguous tensor the next kernel reads (the student maps of K3): warps that run out of maps pull it
+    into L2 while the last maps finish.  The returned `status` (int32[1], device) is non-zero when a hand-off word of
+    the epilogue never arrived -- check it with check_status() at a point where a sync is acceptable."""
     _need_cuda(maps, theta, flip, dec, stats)
     if maps.dtype != _f32:
         raise _lib.UbplError("heat-maps must be float32")
@@ -119,6 +142,7 @@ def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stri
     theta = theta.reshape(K, B, 2, 3).to(_f32).contiguous()
     flip = None if flip is None else flip.reshape(K, B).to(torch.uint8).contiguous()
     dec = None if dec is None else dec.reshape(B, 4).to(_f64).contiguous()
+    perm = _swap_perm(swap_perm, J, dev)
     out_idx = torch.empty(K, B, J, dtype=torch.int32, device=dev) if want_idx else None
     out_max = torch.empty(K, B, J, dtype=_f32, device=dev)
     out_xy = torch.empty(K, B, J, 2, dtype=_f32, device=dev)
@@ -129,25 +153,41 @@ def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stri
     gate = torch.empty(B, J, dtype=_f32, device=dev) if mode in (2, 4) else None
     ws_bytes = int(_lib.lib().ubpl_warp_decode_k2_ws_bytes(K, B, J))
     ws = torch.empty(ws_bytes // 4, dtype=torch.int32, device=dev)
+    pf_ptr, pf_bytes = None, 0
+    if prefetch is not None and prefetch.is_contiguous() and prefetch.data_ptr() % 16 == 0:
+        # at most PF_CAP_MB: what is pulled in must still be in the 126 MB L2 when the next kernel reads it
+        cap = int(os.environ.get("UBPL_K1_PF_MB", PF_CAP_MB)) << 20
+        pf_ptr, pf_bytes = prefetch.data_ptr(), min(prefetch.numel() * prefetch.element_size(), cap)
     _lib.call("ubpl_warp_decode_k2", maps.data_ptr(), maps.stride(0), maps.stride(1), maps.stride(2), K, B, J, H, W,
-              theta.data_ptr(), _p(flip), _p(dec), int(refine), _p(out_idx), out_max.data_ptr(), out_xy.data_ptr(),
-              int(mode), float(distThrMax), int(img_h), int(img_w), float(stride), float(sigma), int(S),
-              mean.data_ptr(), dist.data_ptr(), legal.data_ptr(), _p(enable), _p(gate), _p(stats), ws.data_ptr(),
-              ws_bytes, None if mid_event is None else mid_event.cuda_event, _stream())
+              theta.data_ptr(), _p(flip), _p(perm), _p(dec), int(refine), _p(out_idx), out_max.data_ptr(),
+              out_xy.data_ptr(), int(mode), float(distThrMax), int(img_h), int(img_w), float(stride), float(sigma),
+              int(S), mean.data_ptr(), dist.data_ptr(), legal.data_ptr(), _p(enable), _p(gate), _p(stats),
+              ws.data_ptr(), ws_bytes, pf_ptr, int(pf_bytes), _stream())
     return dict(idx=out_idx, max=out_max, xy=out_xy, mean=mean, dist=dist, legal=legal, enable=enable, gate=gate,
-                counts=ws[128:128 + J + 1], count=ws[128 + J + 1:128 + J + 2], zero_div=ws[33:34], ws=ws)
+                counts=ws[128:128 + J + 1], count=ws[128 + J + 1:128 + J + 2], zero_div=ws[34:35], status=ws[35:36],
+                ws=ws)
 
 
-def warp_materialize(heatmap, warpmat, isflip):
-    """AugmentUtils.affine_back2 (utils/augment.py:37-47) as one kernel; returns a new tensor."""
+def check_status(status, what="ubpl_warp_decode_k2"):
+    """Raises when a device status word is set (one D2H sync): the K2 epilogue's hand-off timed out, the outputs of
+    that launch are void."""
+    if status is not None and int(status.reshape(-1)[0].item()) != 0:
+        raise _lib.UbplError("%s: device status %d -- a hand-off word never arrived; the results of that launch are "
+                             "void" % (what, int(status.reshape(-1)[0].item())))
+
+
+def warp_materialize(heatmap, warpmat, isflip, swap_perm=None):
+    """AugmentUtils.affine_back2 (utils/augment.py:37-47) as one kernel; returns a new tensor.  swap_perm [C]
+    adds flip_back's left/right channel exchange for the flipped samples (utils/udaap/transforms.py:20-57)."""
     _need_cuda(heatmap, warpmat, isflip)
     x = _inner_contig(heatmap.to(_f32))
     N, C, H, W = x.shape
     out = torch.empty(N, C, H, W, dtype=_f32, device=x.device)
     theta = warpmat.reshape(N, 2, 3).to(_f32).contiguous()
     flip = None if isflip is None else torch.as_tensor(isflip, device=x.device).reshape(N).to(torch.uint8).contiguous()
+    perm = _swap_perm(swap_perm, C, x.device)
     _lib.call("ubpl_warp_materialize", x.data_ptr(), x.stride(0), x.stride(1), out.data_ptr(), out.stride(0),
-              out.stride(1), N, C, H, W, theta.data_ptr(), _p(flip), _stream())
+              out.stride(1), N, C, H, W, theta.data_ptr(), _p(flip), _p(perm), _stream())
     return out
 
 
@@ -732,14 +772,33 @@ class EmaPlan:
         self.chunk_start = torch.tensor(cs, dtype=torch.int64, device=dev)
         self._key = self._ptr_key()
 
-    def step(self, alpha):
+    def set_alpha(self, alpha):
+        """Writes {alpha, 1 - alpha} (float32) into the plan's device buffer; launches made with
+        step(alpha, from_device=True) -- in particular launches captured into a CUDA graph -- read it at run time."""
+        import numpy as np
+        a = np.float32(alpha)
+        vals = torch.tensor([float(a), float(np.float32(1 - alpha))], dtype=_f32)
+        if getattr(self, "alpha_buf", None) is None:
+            self.alpha_buf = torch.empty(2, dtype=_f32, device=self.ema_params[0].device)
+        self.alpha_buf.copy_(vals, non_blocking=False)
+        self.alpha = float(alpha)
+
+    def step(self, alpha, from_device=False):
+        """ema <- ema*alpha + (1-alpha)*param over every tensor, one launch.  from_device=True: alpha is read from the
+        device buffer written by set_alpha (the scalar argument is then only the fallback when no buffer exists)."""
         if self._ptr_key() != self._key:
             self._build()
         import numpy as np
         a = float(np.float32(alpha))
         oma = float(np.float32(1 - alpha))
+        adev = None
+        if from_device:
+            if getattr(self, "alpha_buf", None) is None:
+                self.set_alpha(alpha)
+            adev = self.alpha_buf.data_ptr()
         _lib.call("ubpl_ema_multi_tensor", self.ema_ptrs.data_ptr(), self.param_ptrs.data_ptr(), self.numels.data_ptr(),
-                  self.chunk_tensor.data_ptr(), self.chunk_start.data_ptr(), self.n_chunks, self.CHUNK, a, oma, _stream())
+                  self.chunk_tensor.data_ptr(), self.chunk_start.data_ptr(), self.n_chunks, self.CHUNK, a, oma, adev,
+                  _stream())
 
 
 def ema_flat(ema, param, alpha):

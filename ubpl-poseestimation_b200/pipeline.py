@@ -34,6 +34,9 @@ class StepConfig:
     fuse_k2: bool = True             # one-launch K2 for the M=1 fixed-threshold path
     fuse_k12: bool = True            # the per-joint part of K2 runs in K1's epilogue (no K2 launch on the fixed path)
     fuse_sum: bool = True            # the loss reduction runs in K3's last CTA (no loss_finalize launch)
+    swap_perm: object = None         # optional [J] left/right exchange for flipped views (flip_back,
+                                     # utils/udaap/transforms.py:20-57); None = the reference's live path
+    prefetch_student: bool = True    # K1's idle warps pull the student maps (K3's input) into L2 during K1's tail
 
 
 def nega_weights(islabeled, pseudoWeight):
@@ -42,7 +45,7 @@ def nega_weights(islabeled, pseudoWeight):
                        torch.full((), float(pseudoWeight), device=islabeled.device)).to(torch.float32)
 
 
-def stage_k1(st, stats=None, cfg=None, mid_event=None):
+def stage_k1(st, stats=None, cfg=None):
     """K1: back-warp + flip + arg-max decode of every (model, view) map, each read from HBM once.  With one
     teacher (and cfg.fuse_k12) the per-joint dispersion -- and on the fixed path the whole selection -- is
     computed by the warp that decodes the last view of a joint, inside the same launch."""
@@ -63,21 +66,23 @@ def stage_k1(st, stats=None, cfg=None, mid_event=None):
             th = theta.unsqueeze(0).expand(M, K, B, 2, 3).reshape(M * K, B, 2, 3)
             fl = flip.unsqueeze(0).expand(M, K, B).reshape(M * K, B)
         r = ops.warp_decode_k2(maps, th, fl, dec, mode, S=S, img_h=int(sH * cfg.stride), img_w=int(sW * cfg.stride),
-                               stride=cfg.stride, sigma=cfg.sigma, distThrMax=cfg.distThrMax, stats=stats, mid_event=mid_event)
-        st["mid_event_used"] = mid_event is not None
+                               stride=cfg.stride, sigma=cfg.sigma, distThrMax=cfg.distThrMax, stats=stats,
+                               swap_perm=cfg.swap_perm, prefetch=st["student"] if cfg.prefetch_student else None)
         st["xy"], st["max"], st["idx"] = r["xy"].view(M, K, B, J, 2), r["max"].view(M, K, B, J), r["idx"].view(M, K, B, J)
         st["k12"] = r
         return st
+    perm = cfg.swap_perm if cfg is not None else None
     if flat:
         dec_out = ops.warp_decode(teacher.view(M * K, B, J, H, W) if teacher.is_contiguous() else
                                   teacher.as_strided((M * K, B, J, H, W), (teacher.stride(1),) + tuple(teacher.stride()[2:])),
                                   theta.unsqueeze(0).expand(M, K, B, 2, 3).reshape(M * K, B, 2, 3),
-                                  flip.unsqueeze(0).expand(M, K, B).reshape(M * K, B), dec, stats=stats, want_idx=True)
+                                  flip.unsqueeze(0).expand(M, K, B).reshape(M * K, B), dec, stats=stats, want_idx=True,
+                                  swap_perm=perm)
         st["xy"] = dec_out["xy"].view(M, K, B, J, 2)
         st["max"] = dec_out["max"].view(M, K, B, J)
         st["idx"] = dec_out["idx"].view(M, K, B, J)
     else:
-        outs = [ops.warp_decode(teacher[m], theta, flip, dec, stats=stats) for m in range(M)]
+        outs = [ops.warp_decode(teacher[m], theta, flip, dec, stats=stats, swap_perm=perm) for m in range(M)]
         st["xy"] = torch.stack([o["xy"] for o in outs])
         st["max"] = torch.stack([o["max"] for o in outs])
         st["idx"] = torch.stack([o["idx"] for o in outs])
@@ -220,14 +225,17 @@ class GraphedStep:
         torch.cuda.synchronize()
         pool = None
         self.eager = {}
-        # overlap_ema: True / "k1" = K4 forked beside K1, "slow" = beside K1's short second launch (the queued
-        # exhaustive maps: ~14 us on a nearly idle GPU), "k2" = beside the quantile selector (a one-CTA kernel),
-        # "k3" = beside K3, False = after K3
-        self.overlap_ema = (overlap_ema if overlap_ema in ("slow", "k2", "k3") else "k1") if (overlap_ema and ema is not None) else False
+        # overlap_ema: True / "k1" = K4 forked beside K1 (K1 is latency-bound, the EMA's HBM traffic fits beside it),
+        # "k2" = beside the quantile selector (a one-CTA kernel), "k3" = beside K3, False = after K3
+        if overlap_ema == "slow":                         # round-1 name: K1 no longer has a second launch
+            overlap_ema = "k1"
+        self.overlap_ema = (overlap_ema if overlap_ema in ("k2", "k3") else "k1") if (overlap_ema and ema is not None) else False
         if self.overlap_ema == "k2" and cfg.select != "quantile":
             self.overlap_ema = "k1"                       # the fixed path has no K2 launch to hide behind
         self._side = torch.cuda.Stream() if self.overlap_ema else None
         self.events = {}
+        if ema is not None:
+            ema.set_alpha(alpha)                          # the captured EMA launch reads alpha from device memory
 
         def forked(fn):
             # K4 is independent of the chain: fork it onto a side stream inside the same graph so that it runs
@@ -238,24 +246,9 @@ class GraphedStep:
             fn()
             torch.cuda.current_stream().wait_stream(self._side)
 
-        self._mid = None
-        if self.overlap_ema == "slow":
-            self._mid = torch.cuda.Event()
-            self._mid.record()                                # creates the CUDA event: its handle is passed to the C call
-
         def k1_fn():
             if self.overlap_ema == "k1":
                 forked(lambda: stage_k1(self.state, stats, cfg))
-            elif self.overlap_ema == "slow":
-                self.state.pop("mid_event_used", None)
-                stage_k1(self.state, stats, cfg, mid_event=self._mid)
-                if self.state.get("mid_event_used"):           # recorded after K1's main launch
-                    self._side.wait_event(self._mid)
-                else:                                          # the unfused K1 path does not take the event
-                    self._side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(self._side):
-                    self._ema()
-                torch.cuda.current_stream().wait_stream(self._side)
             else:
                 stage_k1(self.state, stats, cfg)
 
@@ -328,7 +321,20 @@ class GraphedStep:
         self.stage_names = list(self.order)
 
     def _ema(self):
-        self.ema.step(self.alpha)
+        self.ema.step(self.alpha, from_device=True)
+
+    def set_alpha(self, alpha):
+        """The EMA factor of the following replays (utils/parameters.py:6: alpha = min(1 - 1/(epo+1), ema_decay)
+        changes every epoch).  The captured launch reads {alpha, 1-alpha} from a device buffer, so no re-capture."""
+        self.alpha = alpha
+        if self.ema is not None:
+            self.ema.set_alpha(alpha)
+
+    def check(self):
+        """Raises if the K2 epilogue of the most recent replay reported a lost hand-off word (one D2H sync)."""
+        k12 = self.state.get("k12")
+        if k12 is not None:
+            ops.check_status(k12.get("status"))
 
     def _eager(self, stats):
         stage_k1(self.state, stats, self.cfg)
