@@ -114,19 +114,33 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's chain (the reference itself is pure Python and is not
-# mounted on the GPU box), all host cores, one process per core, bounded sample of the workload.
+# CPU arm.  kind "reference": the reference's OWN functions (utils/augment.py, process.py, evaluation.py,
+# business.py, losses.py, parameters.py), imported unmodified by oracle/ref_import.py from /root/reference or,
+# on the GPU box, from the byte-for-byte staged copy under baseline/_ref (tools/stage_reference.py), composed
+# by oracle/ref_chain.py.  kind "port": the numpy oracle, only when no reference tree is present.  All host
+# cores, one single-threaded process per core, a bounded sample of the workload per step.
 # ---------------------------------------------------------------------------------------------------
+def cpu_kind():
+    import ref_import
+    return "reference" if ref_import.reference_available() else "port"
+
+
 def _cpu_worker(args):
-    cfgname, nb, seed = args
-    import numpy as np
+    cfgname, nb, seed, kind = args
     import torch
     torch.set_num_threads(1)
     import ubpl_b200  # noqa: F401
     from ubpl_b200 import synth
-    import ubpl_oracle as O
     c = CONFIGS[cfgname]
     d = synth.make_batch(B=nb, K=c["K"], J=c["J"], H=c["H"], W=c["W"], M=c["M"], S=c["S"], seed=seed)
+    if kind == "reference":
+        import ref_import
+        import ref_chain
+        ref = ref_import.load_reference()
+        t0 = time.perf_counter()
+        ref_chain.reference_chain(ref, d, select=c["select"], distThrMax=DIST_THR_MAX)
+        return time.perf_counter() - t0
+    import ubpl_oracle as O
     n = {k: v.numpy() for k, v in d.items()}
     t0 = time.perf_counter()
     O.pseudo_label_chain(n["teacher"], n["student"], n["theta"], n["flip"], n["center"], n["scale"], n["islabeled"],
@@ -134,24 +148,44 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_chain_throughput(cfgname, per_proc, procs, repeats=1):
-    """samples/s of the oracle chain: `procs` processes x `per_proc` samples each, wall clock of the pool."""
-    import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
-        pool.map(_cpu_worker, [(cfgname, 1, 7 + i) for i in range(procs)])          # warm the workers (imports)
+class CpuChain:
+    """A pool of `procs` single-threaded workers; step() runs `per_proc` samples of the config's chain in each and
+    returns (samples, seconds) by the wall clock of the pool."""
+
+    def __init__(self, cfgname, procs, kind):
+        import multiprocessing as mp
+        self.cfgname, self.procs, self.kind = cfgname, procs, kind
+        self.pool = mp.get_context("spawn").Pool(procs)
+        self.pool.map(_cpu_worker, [(cfgname, 1, 7 + i, kind) for i in range(procs)])     # imports, first-call costs
+        self.calls = 0
+
+    def step(self, per_proc):
         t0 = time.perf_counter()
-        for r in range(repeats):
-            pool.map(_cpu_worker, [(cfgname, per_proc, 1388 + 1000 * r + i) for i in range(procs)])
-        dt = time.perf_counter() - t0
-    return procs * per_proc * repeats / dt, dt
+        self.pool.map(_cpu_worker, [(self.cfgname, per_proc, 1388 + 1000 * self.calls + i, self.kind) for i in range(self.procs)])
+        self.calls += 1
+        return self.procs * per_proc, time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
-def cpu_ema_seconds(hg):
-    """numpy statement of utils/parameters.py:7-8 over the HG2 parameter list (timing variant:
-    plain multiply-add, one core)."""
+def cpu_ema_seconds(c, kind):
+    """One update_ema_variables over an HG2 parameter set: the reference's own function on two reference
+    StackedHourglass models (kind "reference", utils/parameters.py:4-8, all torch threads), else numpy."""
+    if kind == "reference":
+        import torch
+        import ref_import
+        import ref_chain
+        ref = ref_import.load_reference()
+        model, ema = ref_chain.make_hourglass_pair(ref, c["J"])
+        ref_chain.reference_ema(ref, model, ema)                 # warm
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ref_chain.reference_ema(ref, model, ema)
+        return (time.perf_counter() - t0) / 3
     import numpy as np
-    shapes = json.load(open(os.path.join(ROOT, "ubpl-poseestimation_b200", "hg_param_shapes.json")))[hg]
+    shapes = json.load(open(os.path.join(ROOT, "ubpl-poseestimation_b200", "hg_param_shapes.json")))[c["hg"]]
     rng = np.random.default_rng(0)
     ps = [rng.standard_normal(s).astype(np.float32) for s in shapes]
     es = [rng.standard_normal(s).astype(np.float32) for s in shapes]
@@ -163,42 +197,54 @@ def cpu_ema_seconds(hg):
     return time.perf_counter() - t0
 
 
+def cpu_sample_note(kind, n, procs, per_proc, cfgname):
+    src = ("the reference's own functions (oracle/ref_chain.py over the unmodified utils/*.py) + update_ema_variables on "
+           "reference HG2 models" if kind == "reference" else "oracle/ubpl_oracle.py chain + numpy EMA")
+    return "%d samples of %s per step (%d single-threaded processes x %d): %s, EMA pro-rated per batch" % (
+        n, cfgname, procs, per_proc, src)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return                                     # rank 0 alone runs the CPU arm
     c = CONFIGS[args.config]
-    cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64))
-    per_proc = max(1, int(args.ref_samples_per_proc))
-    vals = []
-    # every step is a bounded sample (procs x per_proc samples); the run is capped so that the driver's
-    # default --steps/--warmup still end within a few minutes on the host cores
-    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    for _ in range(warmup):
-        cpu_chain_throughput(args.config, 1, procs)
-    t_steps = []
-    for _ in range(steps):
-        v, dt = cpu_chain_throughput(args.config, per_proc, procs)
-        ema_s = cpu_ema_seconds(c["hg"])
-        n = procs * per_proc
+    kind = cpu_kind()
+    procs = max(1, min(os.cpu_count() or 1, 64))
+    # every step is a bounded sample (procs x per_proc samples), sized so that the driver's --steps/--warmup end
+    # within a few minutes: ~25 samples/s per core at c2 shapes, ~1 sample/s per core at c5's
+    heavy = c["H"] * c["W"] * c["J"] * c["K"] * c["M"] > 64 * 64 * 14 * 8 * 4
+    per_proc = max(1, int(args.ref_samples_per_proc)) if args.ref_samples_per_proc else (1 if heavy else 4)
+    chain = CpuChain(args.config, procs, kind)
+    ema_s = cpu_ema_seconds(c, kind)
+    for _ in range(args.warmup):
+        chain.step(1)
+    vals, t_steps = [], []
+    for _ in range(args.steps):
+        n, dt = chain.step(per_proc)
         tot = dt + ema_s * n / c["B"]               # one EMA per full batch of B samples, pro-rated
         vals.append(n / tot)
         t_steps.append(tot)
-    v = sum(vals) / len(vals)
+    chain.close()
+    v = sum(t_steps) and (procs * per_proc * len(t_steps)) / sum(t_steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * sum(t_steps) / len(t_steps),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t_steps) / len(t_steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.config + ": " + c["desc"], "per_gpu_batch": c["B"], "K": c["K"], "M": c["M"],
-                   "J": c["J"], "S": c["S"], "heatmap": [c["H"], c["W"]], "select": c["select"]},
-        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": procs, "kind": "port",
-                         "sample": "%d samples per step (%d processes x %d), oracle/ubpl_oracle.py chain + pro-rated numpy EMA"
-                                   % (procs * per_proc, procs, per_proc)},
+        "config": workload_config(args.config),
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": procs, "kind": kind,
+                         "sample": cpu_sample_note(kind, procs * per_proc, procs, per_proc, args.config)},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def workload_config(cfgname):
+    """The `config` keys both arms share (the GPU arm adds measurement details under other names)."""
+    c = CONFIGS[cfgname]
+    return {"workload": cfgname + ": " + c["desc"], "per_gpu_batch": c["B"], "K": c["K"], "M": c["M"], "J": c["J"],
+            "S": c["S"], "heatmap": [c["H"], c["W"]], "select": c["select"], "distThrMax": DIST_THR_MAX}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -418,19 +464,25 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            kind = cpu_kind()
             procs = max(1, min(os.cpu_count() or 1, 64))
-            v, dt = cpu_chain_throughput(args.config, 2, procs)
-            ema_s = cpu_ema_seconds(c["hg"])
-            n = procs * 2
-            cpu = {"value": n / (dt + ema_s * n / B), "unit": "samples/s", "cores": procs, "kind": "port",
-                   "sample": "%d samples (%d processes x 2) of %s through oracle/ubpl_oracle.py + pro-rated numpy EMA"
-                             % (n, procs, args.config)}
+            chain = CpuChain(args.config, procs, kind)
+            per_proc = 1 if H * W * J * K * M > 64 * 64 * 14 * 8 * 4 else 4
+            n = dt = 0
+            t_cpu0 = time.perf_counter()
+            while dt < 10.0 and time.perf_counter() - t_cpu0 < 60.0:          # ~10 s of CPU work
+                nn, d_t = chain.step(per_proc)
+                n += nn
+                dt += d_t
+            chain.close()
+            ema_s = cpu_ema_seconds(c, kind)
+            cpu = {"value": n / (dt + ema_s * n / B), "unit": "samples/s", "cores": procs, "kind": kind,
+                   "sample": cpu_sample_note(kind, procs * per_proc, procs, per_proc, args.config) + "; %d samples in %.1f s" % (n, dt)}
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.config + ": " + c["desc"], "per_gpu_batch": B, "K": K, "M": M, "J": J, "S": S,
-                       "heatmap": [H, W], "select": c["select"], "distThrMax": DIST_THR_MAX,
+            "config": dict(workload_config(args.config), **{
                        "ema_params": n_params, "l2": "inputs (%.0f MB/step) larger than L2" % (bytes_sample * B / 1e6),
                        "selected_frac": float(r["enable"].float().mean()), "exhaustive_decode_frac": slow_frac,
                        "launch": ("1 CUDA graph per step" if single else "%d stage launches per step (%s)" % (len(gstep.order), ", ".join(
@@ -441,7 +493,7 @@ def run_ours(args):
                        "selector": ("fixed rule in K1's epilogue" if c["select"] == "fixed" and cfg.fuse_k12 and M <= 2 else
                                     "fused one-kernel quantile selector" + (" over NVLink peer memory" if p2p_ok else "")
                                     if (world == 1 or p2p_ok) and c["select"] == "quantile" else
-                                    "NCCL histogram all-reduce" if c["select"] == "quantile" else "k2 kernels")},
+                                    "NCCL histogram all-reduce" if c["select"] == "quantile" else "k2 kernels")}),
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(t)},
@@ -460,7 +512,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-samples-per-proc", type=int, default=4)
+    ap.add_argument("--ref-samples-per-proc", type=int, default=0, help="CPU arm: samples per process per step (0 = by config)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -112,7 +112,7 @@ def reference_chain(ref, d, select="fixed", distThrMax=1.0, reliableThr=0.0, rel
         loss.backward()
         grad = preds.grad.numpy()
     out = dict(idx=idx.numpy(), max=maxv.numpy(), xy=xy.numpy(), kps=kps.numpy(), enable=enable.numpy(),
-               gate=gate.numpy(), target=target.numpy(), loss=float(loss), count=int(n), grad=grad,
+               gate=gate.numpy(), target=target.numpy(), loss=float(loss.detach()), count=int(n), grad=grad,
                dist=None if dist is None else dist.numpy(), legal=legal.numpy())
     out.update(extra)
     return out

@@ -398,3 +398,35 @@ def test_ema(ref):
         alpha = O.ema_alpha(epo, decay)
         for e0, p, e1 in zip(ema_before, a.parameters(), b.parameters()):
             assert np.array_equal(O.ema_update(e0, p.detach().numpy(), alpha), e1.detach().numpy())
+
+
+def test_flip_back_swap(ref):
+    """utils/udaap/transforms.py:20-57 flip_back (mirror + sequential left/right channel exchange) against the
+    oracle's flip_back_swap, and the channel table the CUDA path uses (ops.swap_perm_from_pairs)."""
+    from ubpl_b200 import ops
+    rng = np.random.default_rng(3)
+    for name, J in (("mpii", 16), ("real_animal", 18)):
+        x = rng.standard_normal((3, J, 8, 12)).astype(np.float32)
+        want = ref.udaap_tf.flip_back(torch.from_numpy(x.copy()), name).numpy()
+        got = O.flip_back_swap(x, O.FLIP_PAIRS[name])
+        assert np.array_equal(got, want)
+        perm = ops.swap_perm_from_pairs(O.FLIP_PAIRS[name], J).numpy()
+        assert np.array_equal(x[..., ::-1][:, perm], want)                  # out[:, j] = mirrored[:, perm[j]]
+
+
+@pytest.mark.parametrize("M,select", [(1, "fixed"), (1, "quantile"), (2, "fixed"), (2, "quantile")])
+def test_reference_chain_matches_oracle_chain(ref, M, select):
+    """oracle/ref_chain.py (the reference's own functions composed into the benchmark's chain -- the CPU baseline
+    bench.py times) against the oracle's restated chain on the same inputs."""
+    import ref_chain
+    d = synth.make_batch(B=6, K=4, J=5, M=M, S=2, seed=77 + M, jitter=0.7)
+    n = {k: v.numpy() for k, v in d.items()}
+    o = O.pseudo_label_chain(n["teacher"], n["student"], n["theta"], n["flip"], n["center"], n["scale"], n["islabeled"],
+                             select=select, distThrMax=2.0, lossWeight=0.7)
+    r = ref_chain.reference_chain(ref, d, select=select, distThrMax=2.0, lossWeight=0.7)
+    for k in ("idx", "xy", "enable", "gate"):
+        assert np.array_equal(np.asarray(o[k]), np.asarray(r[k])), k
+    assert o["count"] == r["count"]
+    np.testing.assert_allclose(r["loss"], o["loss"], rtol=1e-6)
+    np.testing.assert_allclose(r["grad"], o["grad"], rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(r["target"], o["target"], rtol=1e-6, atol=1e-8)

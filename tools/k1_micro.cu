@@ -67,17 +67,26 @@ __device__ __forceinline__ float spin(float v, int work) {
 
 // mode 0 stage, 1 scan, 2 scan + spin
 __global__ void __launch_bounds__(512, 1) k_stage(const float* maps, int N, unsigned long long* counter, float* out, int mode,
-                                                  int work, int use_policy) {
+                                                  int work, int use_policy, int cap) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* buf = reinterpret_cast<float*>(smem + (size_t)warp * kMap * 4);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)warps * kMap * 4) + warp;
+  int* credits = reinterpret_cast<int*>(smem + (size_t)warps * kMap * 4 + 192);     // copies this CTA may still put in flight
   uint64_t pol = 0;
+  if (threadIdx.x == 0) *credits = cap;
   if (lane == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); pol = evict_first(); }
-  __syncwarp();
+  __syncthreads();
   unsigned long long claim = 0;
   auto issue = [&](long long n) {
     if (lane == 0) {
+      if (cap > 0) {
+        for (;;) {
+          if (atomicSub(credits, 1) > 0) break;
+          atomicAdd(credits, 1);
+          __nanosleep(100);
+        }
+      }
       mbar_expect(bar, kMap * 4);
       if (use_policy) bulk_g2s(buf, maps + (size_t)n * kMap, kMap * 4, bar, pol);
       else asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -91,6 +100,7 @@ __global__ void __launch_bounds__(512, 1) k_stage(const float* maps, int N, unsi
   float acc = 0.f;
   for (long long it = 0; cur < N; ++it) {
     mbar_wait(bar, (uint32_t)(it & 1));
+    if (cap > 0 && lane == 0) atomicAdd(credits, 1);
     float v = buf[lane];
     if (mode >= 1) v = scan(buf, lane);
     if (mode >= 2) v = spin(v, work);
@@ -113,10 +123,12 @@ __global__ void __launch_bounds__(1024, 1) k_pair(const float* maps, int N, unsi
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = warp >> 1, side = warp & 1;
   float* buf = reinterpret_cast<float*>(smem + (size_t)b * kMap * 4);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)nbuf * kMap * 4) + b;
-  uint64_t* freeb = full + nbuf;
-  volatile int* fills = reinterpret_cast<volatile int*>(freeb + nbuf) + b;          // fills issued into this buffer
-  volatile int* gone = reinterpret_cast<volatile int*>(freeb + nbuf) + nbuf + 2 * b;  // [2]: this side has left
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)nbuf * kMap * 4);     // full[nbuf], free[nbuf]
+  uint64_t* full = bars + b;
+  uint64_t* freeb = bars + nbuf + b;
+  volatile int* flags = reinterpret_cast<volatile int*>(bars + 2 * nbuf);          // fills[nbuf], gone[nbuf][2]
+  volatile int* fills = flags + b;                                                  // fills issued into this buffer
+  volatile int* gone = flags + nbuf + 2 * b;                                        // [2]: this side has left
   uint64_t pol = 0;
   if (side == 0 && lane == 0) {
     mbar_init(full, 1); mbar_init(freeb, 1);
@@ -196,7 +208,16 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&counter, 8));
   const size_t flush_bytes = 256u << 20;
   CK(cudaMalloc(&flush, flush_bytes));
-  CK(cudaMemset(maps, 0, (size_t)N * kMap * 4));
+  {   // pseudo-random floats (not zeros: the data must not flatter any lossless path in the memory system)
+    float* h = (float*)malloc((size_t)64 << 20);
+    uint32_t x = 12345u;
+    for (size_t i = 0; i < ((size_t)64 << 20) / 4; ++i) { x = x * 1664525u + 1013904223u; h[i] = (float)(x >> 8) * (1.0f / 16777216.0f) - 0.5f; }
+    for (size_t off = 0; off < (size_t)N * kMap * 4; off += (size_t)64 << 20) {
+      size_t n = (size_t)N * kMap * 4 - off; if (n > ((size_t)64 << 20)) n = (size_t)64 << 20;
+      CK(cudaMemcpy((char*)maps + off, h, n, cudaMemcpyHostToDevice));
+    }
+    free(h);
+  }
   int sms = 0, optin = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, 0));
@@ -227,14 +248,19 @@ int main(int argc, char** argv) {
   for (int pol = 1; pol >= 0; --pol)
     for (int w : {14, 7, 4}) {
       snprintf(name, sizeof name, "stage  %2d warps x 16 KB%s", w, pol ? "" : " (no evict_first)");
-      time(name, [&] { k_stage<<<sms, w * 32, (size_t)w * kMap * 4 + 256, 0>>>(maps, N, counter, out, 0, 0, pol); });
+      time(name, [&] { k_stage<<<sms, w * 32, (size_t)w * kMap * 4 + 256, 0>>>(maps, N, counter, out, 0, 0, pol, 0); });
     }
-  time("scan   14 warps x 16 KB", [&] { k_stage<<<sms, 14 * 32, (size_t)14 * kMap * 4 + 256, 0>>>(maps, N, counter, out, 1, 0, 1); });
+  time("scan   14 warps x 16 KB", [&] { k_stage<<<sms, 14 * 32, (size_t)14 * kMap * 4 + 256, 0>>>(maps, N, counter, out, 1, 0, 1, 0); });
   for (int work : {250, 500, 750, 1000, 1500}) {
     snprintf(name, sizeof name, "spin   14 warps x 16 KB, work %4d", work);
-    time(name, [&] { k_stage<<<sms, 14 * 32, (size_t)14 * kMap * 4 + 256, 0>>>(maps, N, counter, out, 2, work, 1); });
+    time(name, [&] { k_stage<<<sms, 14 * 32, (size_t)14 * kMap * 4 + 256, 0>>>(maps, N, counter, out, 2, work, 1, 0); });
   }
-  for (int nbuf : {8, 10, 12, 14})
+  for (int cap : {3, 4, 5, 6, 8})
+    for (int work : {0, 500, 1000, 1500}) {
+      snprintf(name, sizeof name, "cap    14 warps, <= %d copies in flight, work %4d", cap, work);
+      time(name, [&] { k_stage<<<sms, 14 * 32, (size_t)14 * kMap * 4 + 256, 0>>>(maps, N, counter, out, work ? 2 : 1, work, 1, cap); });
+    }
+  for (int nbuf : {8, 10})
     for (int work : {500, 1000, 1500}) {
       snprintf(name, sizeof name, "pair   %2d warps / %2d buffers, work %4d", 2 * nbuf, nbuf, work);
       time(name, [&] { k_pair<<<sms, 2 * nbuf * 32, (size_t)nbuf * kMap * 4 + 1024, 0>>>(maps, N, counter, out, work, nbuf); });

@@ -88,6 +88,11 @@ struct WDParams {
   unsigned long long pf_bytes;   // ran out of maps prefetch into L2, chunk by chunk, while the last maps finish
   unsigned long long* pf_next;   // its chunk counter (zeroed before the launch)
   int pf_every;                  // an idle warp prefetches one 32 KB chunk every pf_every polls (~0.25 us each)
+  int inflight_cap;              // at most this many bulk copies in flight per CTA (0 = one per warp, no cap): with
+                                 // thousands of concurrent 16 KB streams over a large footprint HBM falls into a
+                                 // low-efficiency regime (profiles/README.md, round 2), so the copies are metered
+  int dbg;                       // UBPL_K1_DBG (timing experiments only, results void): 1 skip phases L/B/C and the
+                                 // exhaustive decode, 2 skip the epilogue, 4 skip only the exhaustive decode, 8 skip pass A
   K2Fuse k2;                  // optional K2 epilogue run by the warp that decodes the last view of a (sample, joint)
 };
 
@@ -172,20 +177,30 @@ __device__ __forceinline__ void grid_consts(Xform& X, int H, int W) {
   X.sfy = (float)((double)(H - 1) / 2.0);
 }
 
-// Exhaustive decode of rows [row0, row1) of the warped map.  Each lane walks whole columns (the column terms
-// of the affine grid are hoisted), so the tie rule is carried by arg_better's index comparison; NaN aware.
-__device__ __noinline__ ArgMax decode_exhaustive(const float* __restrict__ s, const float* __restrict__ lx,
-                                                 const float* __restrict__ ly, float t00, float t01, float t02,
-                                                 float t10, float t11, float t12, float sfx, float sfy, int H, int W,
-                                                 int flip, int lane, int row0, int row1) {
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// Exhaustive decode of rows [row0, row1) of the warped map staged in SHARED memory at byte address `sa` (the
+// tables lx / ly at lxa / lya).  Each lane walks whole columns (the column terms of the affine grid are hoisted),
+// so the tie rule is carried by the index comparison.  FINITE = true: the map holds no NaN / Inf, the running
+// arg-max is a branch-free select; false: torch.max's NaN rules (arg_better).
+template <bool FINITE>
+__device__ __forceinline__ ArgMax decode_rows(uint32_t sa, uint32_t lxa, uint32_t lya, float t00, float t01, float t02,
+                                              float t10, float t11, float t12, float sfx, float sfy, int H, int W,
+                                              int flip, int lane, int row0, int row1) {
   float bv = -INFINITY;
   int bi = 0x7fffffff;
+  const float fW1 = (float)(W + 1), fH1 = (float)(H + 1);
   for (int jo = lane; jo < W; jo += 32) {
     const int jw = flip ? (W - 1 - jo) : jo;
-    const float xl = lx[jw];
+    const float xl = lds_f32(lxa + 4u * (uint32_t)jw);
     const float ax = __fmul_rn(xl, t00), ay = __fmul_rn(xl, t10);
+#pragma unroll 4
     for (int i = row0; i < row1; ++i) {
-      const float yl = ly[i];
+      const float yl = lds_f32(lya + 4u * (uint32_t)i);
       const float gx = __fadd_rn(__fmaf_rn(yl, t01, ax), t02);
       const float gy = __fadd_rn(__fmaf_rn(yl, t11, ay), t12);
       const float ix = __fmul_rn(__fadd_rn(gx, 1.f), sfx);
@@ -193,27 +208,41 @@ __device__ __noinline__ ArgMax decode_exhaustive(const float* __restrict__ s, co
       const float x0f = floorf(ix), y0f = floorf(iy);
       const float w = __fsub_rn(ix, x0f), e = __fsub_rn(1.f, w);
       const float n = __fsub_rn(iy, y0f), so = __fsub_rn(1.f, n);
-      const int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)(W + 1));
-      const int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)(H + 1));
+      const int x0 = (int)fminf(fmaxf(x0f, -2.f), fW1);
+      const int y0 = (int)fminf(fmaxf(y0f, -2.f), fH1);
       const bool xa = (unsigned)x0 < (unsigned)W, xb = (unsigned)(x0 + 1) < (unsigned)W;
       const bool ya = (unsigned)y0 < (unsigned)H, yb = (unsigned)(y0 + 1) < (unsigned)H;
-      const float* r0 = s + y0 * W + x0;
-      const float v_nw = (xa & ya) ? r0[0] : 0.f;
-      const float v_ne = (xb & ya) ? r0[1] : 0.f;
-      const float v_sw = (xa & yb) ? r0[W] : 0.f;
-      const float v_se = (xb & yb) ? r0[W + 1] : 0.f;
+      const uint32_t r0 = sa + 4u * (uint32_t)(y0 * W + x0);
+      const float v_nw = (xa & ya) ? lds_f32(r0) : 0.f;
+      const float v_ne = (xb & ya) ? lds_f32(r0 + 4u) : 0.f;
+      const float v_sw = (xa & yb) ? lds_f32(r0 + 4u * (uint32_t)W) : 0.f;
+      const float v_se = (xb & yb) ? lds_f32(r0 + 4u * (uint32_t)W + 4u) : 0.f;
       float acc = __fmul_rn(v_nw, __fmul_rn(so, e));
       acc = __fmaf_rn(v_ne, __fmul_rn(so, w), acc);
       acc = __fmaf_rn(v_sw, __fmul_rn(n, e), acc);
       acc = __fmaf_rn(v_se, __fmul_rn(n, w), acc);
       const int k = i * W + jo;
-      if (arg_better(acc, k, bv, bi)) { bv = acc; bi = k; }
+      if (FINITE) {
+        const bool better = (acc > bv) | ((acc == bv) & (k < bi));
+        bv = better ? acc : bv;
+        bi = better ? k : bi;
+      } else if (arg_better(acc, k, bv, bi)) {
+        bv = acc; bi = k;
+      }
     }
   }
-  warp_argmax(bv, bi);
+  if (FINITE) warp_argmax_finite(bv, bi); else warp_argmax(bv, bi);
   ArgMax r;
   r.v = bv; r.i = bi;
   return r;
+}
+
+__device__ __noinline__ ArgMax decode_exhaustive(uint32_t sa, uint32_t lxa, uint32_t lya, float t00, float t01, float t02,
+                                                 float t10, float t11, float t12, float sfx, float sfy, int H, int W,
+                                                 int flags, int lane, int row0, int row1) {
+  // flags: bit 0 mirror, bit 1 the map may hold NaN / Inf
+  if (flags & 2) return decode_rows<false>(sa, lxa, lya, t00, t01, t02, t10, t11, t12, sfx, sfy, H, W, flags & 1, lane, row0, row1);
+  return decode_rows<true>(sa, lxa, lya, t00, t01, t02, t10, t11, t12, sfx, sfy, H, W, flags & 1, lane, row0, row1);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -231,8 +260,10 @@ struct CoopJob {
   int band_next;    // next band to claim; >= kBands: no open job
   int bands_done;   // bands whose partial result is written
   int warps_done;   // warps of the CTA that have run out of maps
-  int flip;
-  const float* src;
+  unsigned issued;  // copy tickets handed out / copies that have landed: a warp with ticket t issues its copy once
+  unsigned landed;  // t - landed < WDParams::inflight_cap (FIFO, no retry races; both unused when the cap is 0)
+  int flags;        // bit 0: mirrored view, bit 1: the map may hold NaN / Inf (NaN-aware compare)
+  unsigned src;     // shared-memory byte address of the poster's staged map
   float t[6];
   float pv[kBands];
   int pi[kBands];
@@ -248,12 +279,12 @@ __device__ __forceinline__ void coop_help(CoopJob* cj, const WDParams& p, const 
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= kBands) return;
     __threadfence_block();                                   // the job's parameters were written before it opened
-    const float* src = *reinterpret_cast<const float* const volatile*>(&cj->src);
+    const unsigned src = *reinterpret_cast<const volatile unsigned*>(&cj->src);
     const volatile float* t = cj->t;
-    const int flip = ld_volatile_s32(&cj->flip);
+    const int flags = ld_volatile_s32(&cj->flags);
     const int r0 = (p.H * b) / kBands, r1 = (p.H * (b + 1)) / kBands;
-    const ArgMax r = decode_exhaustive(src, lx, ly, t[0], t[1], t[2], t[3], t[4], t[5], p.sfx, p.sfy, p.H, p.W, flip,
-                                       lane, r0, r1);
+    const ArgMax r = decode_exhaustive(src, smem_u32(lx), smem_u32(ly), t[0], t[1], t[2], t[3], t[4], t[5], p.sfx, p.sfy,
+                                       p.H, p.W, flags, lane, r0, r1);
     if (lane == 0) {
       *reinterpret_cast<volatile float*>(&cj->pv[b]) = r.v;
       *reinterpret_cast<volatile int*>(&cj->pi[b]) = r.i;
@@ -265,7 +296,7 @@ __device__ __forceinline__ void coop_help(CoopJob* cj, const WDParams& p, const 
 
 // Posts the map staged at `s` as the CTA's job, works on it, and returns its exact arg-max (warp-wide call).
 __device__ __forceinline__ ArgMax coop_exhaustive(CoopJob* cj, const WDParams& p, const float* s, const Xform& X,
-                                                  const float* lx, const float* ly, int warp, int lane) {
+                                                  bool nan_aware, const float* lx, const float* ly, int warp, int lane) {
   for (;;) {                                                 // take the job slot; help whoever holds it meanwhile
     int got = 0;
     if (lane == 0) got = (atomicCAS(&cj->owner, 0, warp + 1) == 0) ? 1 : 0;
@@ -274,10 +305,10 @@ __device__ __forceinline__ ArgMax coop_exhaustive(CoopJob* cj, const WDParams& p
     coop_help(cj, p, lx, ly, lane);
   }
   if (lane == 0) {
-    *reinterpret_cast<const float* volatile*>(&cj->src) = s;
+    *reinterpret_cast<volatile unsigned*>(&cj->src) = smem_u32(s);
     volatile float* t = cj->t;
     t[0] = X.t00; t[1] = X.t01; t[2] = X.t02; t[3] = X.t10; t[4] = X.t11; t[5] = X.t12;
-    *reinterpret_cast<volatile int*>(&cj->flip) = X.flip ? 1 : 0;
+    *reinterpret_cast<volatile int*>(&cj->flags) = (X.flip ? 1 : 0) | (nan_aware ? 2 : 0);
     *reinterpret_cast<volatile int*>(&cj->bands_done) = 0;
     __threadfence_block();
     atomicExch(&cj->band_next, 0);                           // opens the job
@@ -359,10 +390,18 @@ __device__ __forceinline__ const float* map_src(const WDParams& p, long long n) 
   return p.maps + (long long)v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
 }
 
+// Called by lane 0.  With a cap, first takes a ticket and waits until fewer than `cap` of the CTA's copies are in
+// flight (the waiter of a copy counts it as landed); the other lanes of the warp wait at the next warp-wide
+// operation meanwhile.
 __device__ __forceinline__ void issue_map(const WDParams& p, long long n, float* dst, uint64_t* bar, uint64_t pol,
-                                          uint32_t bytes) {
+                                          uint32_t bytes, CoopJob* cj) {
+  const float* src = map_src(p, n);
+  if (p.inflight_cap > 0) {
+    const unsigned t = atomicAdd(&cj->issued, 1u);
+    while ((int)(t - *reinterpret_cast<volatile unsigned*>(&cj->landed)) >= p.inflight_cap) __nanosleep(64);
+  }
   mbar_arrive_expect_tx(bar, bytes);
-  bulk_g2s(dst, map_src(p, n), bytes, bar, pol);
+  bulk_g2s(dst, src, bytes, bar, pol);
 }
 
 // K2 of one (sample, joint), run by the warp that decoded its last view (see K2Fuse).  Same float op order
@@ -765,7 +804,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   const long long N = (long long)p.V * p.B * p.J;
   uint64_t pol = 0;
   if (threadIdx.x == 0) {
-    cj->owner = 0; cj->band_next = kBands; cj->bands_done = 0; cj->warps_done = 0;
+    cj->owner = 0; cj->band_next = kBands; cj->bands_done = 0; cj->warps_done = 0; cj->issued = 0u; cj->landed = 0u;
   }
   for (int k = threadIdx.x; k < W; k += blockDim.x) lx[k] = lin_coord(k, W, p.stepx);
   for (int k = threadIdx.x; k < H; k += blockDim.x) ly[k] = lin_coord(k, H, p.stepy);
@@ -788,12 +827,12 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   }
   __syncthreads();
   long long cur = claim_get();
-  if (p.use_bulk && lane == 0 && cur < N) issue_map(p, cur, buf0, bar, pol, map_bytes);
+  if (p.use_bulk && lane == 0 && cur < N) issue_map(p, cur, buf0, bar, pol, map_bytes, cj);
   claim_issue();
   // hand the staging buffer to the next map: returns its index (>= N when the work is exhausted)
   auto advance = [&]() -> long long {
     const long long nn = claim_get();
-    if (p.use_bulk && lane == 0 && nn < N) issue_map(p, nn, buf0, bar, pol, map_bytes);
+    if (p.use_bulk && lane == 0 && nn < N) issue_map(p, nn, buf0, bar, pol, map_bytes, cj);
     if (nn < N) claim_issue();
     return nn;
   };
@@ -806,8 +845,14 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     const long long n = cur;
     if (n >= N) break;
     const float* s = buf0;
-    // an exhaustive job posted by another warp of this CTA: help before this map (whose copy is in flight)
-    if (p.do_warp && ld_volatile_s32(&cj->band_next) < kBands) coop_help(cj, p, lx, ly, lane);
+    // an exhaustive job posted by another warp of this CTA: help before this map (whose copy is in flight).  The
+    // decision is taken by lane 0 and broadcast: coop_help is a warp-wide call, every lane must take the same branch
+    // (the lanes are not necessarily converged here -- lane 0 may come late out of issue_map's wait).
+    if (p.do_warp) {
+      int open = 0;
+      if (lane == 0) open = ld_volatile_s32(&cj->band_next) < kBands ? 1 : 0;
+      if (__shfl_sync(0xffffffffu, open, 0)) coop_help(cj, p, lx, ly, lane);
+    }
     unsigned vbu, ju, vu, bu;
     p.divJ.divmod((unsigned)n, vbu, ju);
     p.divB.divmod(vbu, vu, bu);
@@ -838,6 +883,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     }
     if (p.use_bulk) {
       mbar_wait(bar, (uint32_t)(it & 1));
+      if (p.inflight_cap > 0 && lane == 0) atomicAdd(&cj->landed, 1u);
     } else {
       const float* gsrc = map_src(p, n);
       for (int k = lane; k < HW; k += 32) buf0[k] = __ldg(gsrc + k);
@@ -847,7 +893,8 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
 
     // ---- pass A: raw max / location / min / finiteness -----------------------------------------
     float bv, mn; int bq;
-    scan_max(s, HW, lane, bv, bq, mn);
+    if (p.dbg & 8) { bv = s[lane]; bq = lane >> 2; mn = bv; }
+    else scan_max(s, HW, lane, bv, bq, mn);
     A.lane_max = bv;                       // per-lane float4 maximum (pass B reuses it)
     int bi = 0x7fffffff;                  // flat index of the lane's first maximum
     if (bv > -INFINITY) {
@@ -876,18 +923,29 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       if (!exhaustive) {
         warp_argmax_finite(bv, bi);       // warp-uniform source max / location
         A.bv = bv; A.bi = bi;
-        decode_pruned(p, s, X, lx, ly, A, lane, rv, ri, exhaustive, n_eval);
+        if (p.dbg & 1) { rv = bv; ri = bi; }
+        else decode_pruned(p, s, X, lx, ly, A, lane, rv, ri, exhaustive, n_eval);
       }
+      if (exhaustive && (p.dbg & 5)) { exhaustive = false; rv = bv; ri = bi & 0xfff; }
       if (exhaustive) {
-        const ArgMax r = coop_exhaustive(cj, p, s, X, lx, ly, warp, lane);
+        // NaN-aware compare for non-finite maps and for degenerate / huge transforms (their grid can overflow to
+        // Inf - Inf = NaN weights); everything else yields finite samples
+        const ArgMax r = coop_exhaustive(cj, p, s, X, nonfinite || bad_xform, lx, ly, warp, lane);
         rv = r.v; ri = r.i;
         ++n_slow;
         n_eval += HW;
       }
     }
 
-    k2_resolve(p, pend_item, pend_old, lane);            // the previous map's ticket has long arrived by now
-    finish_map(p, n, (int)vu, b, j, s, X, lx, ly, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
+    if (p.do_warp) {                                     // second look at the CTA's job word, half a map after the first
+      int open = 0;
+      if (lane == 0) open = ld_volatile_s32(&cj->band_next) < kBands ? 1 : 0;
+      if (__shfl_sync(0xffffffffu, open, 0)) coop_help(cj, p, lx, ly, lane);
+    }
+    if (!(p.dbg & 2)) {
+      k2_resolve(p, pend_item, pend_old, lane);          // the previous map's ticket has long arrived by now
+      finish_map(p, n, (int)vu, b, j, s, X, lx, ly, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
+    } else if (rv == 123.456f && p.out_max) p.out_max[n] = rv;
     __syncwarp();
     cur = advance();
   }
@@ -907,8 +965,11 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     bool pf_live = p.pf_ptr != nullptr;
     int tick = 0;                                        // one chunk per pf_every polls: the idle warps ask for about
     for (;;) {                                           // the bandwidth they used while they were decoding
-      if (ld_volatile_s32(&cj->warps_done) >= warps) break;
-      if (ld_volatile_s32(&cj->band_next) < kBands) {
+      int st = 0;                                        // lane 0 decides for the warp: 2 leave, 1 help, 0 idle
+      if (lane == 0) st = ld_volatile_s32(&cj->warps_done) >= warps ? 2 : (ld_volatile_s32(&cj->band_next) < kBands ? 1 : 0);
+      st = __shfl_sync(0xffffffffu, st, 0);
+      if (st == 2) break;
+      if (st == 1) {
         coop_help(cj, p, lx, ly, lane);
         continue;
       }
@@ -990,6 +1051,11 @@ static int launch_k1(WDParams& p, cudaStream_t stream) {
   p.stepy = (H > 1) ? 2.f / (float)(H - 1) : 0.f;
   p.sfx = (float)((double)(W - 1) / 2.0);
   p.sfy = (float)((double)(H - 1) / 2.0);
+  p.dbg = env_int("UBPL_K1_DBG", 0);
+  // at most 8 staged copies in flight per SM (1184 over the GPU) by default: measured on B200, more concurrent 16 KB
+  // streams than that can tip HBM into a regime that delivers 4.3-4.6 TB/s instead of 6+ (tools/k1_micro.cu,
+  // profiles/README.md round 2); UBPL_K1_INFLIGHT overrides (0 = no cap)
+  p.inflight_cap = env_int("UBPL_K1_INFLIGHT", 8);
   // bulk async copy needs 16-byte aligned sources and sizes; otherwise the warp copies the map itself
   p.use_bulk = ((reinterpret_cast<uintptr_t>(p.maps) & 15) == 0) && (map_bytes % 16 == 0) && (p.sV % 4 == 0) &&
                (p.sB % 4 == 0) && (p.sJ % 4 == 0);
