@@ -42,6 +42,9 @@ METRIC = "pseudo-labelled samples/sec"
 # profiles/r01f_k1_k3_full.ncu-rep (c2: 469.97 MB read + 4.03 MB written vs 469.76 MB algorithmic) and
 # profiles/r01f_c4_k1_select_k3_full.ncu-rep (c4: 1141.15 MB + 4.64 MB vs 1140.85 MB algorithmic)
 NCU_TRAFFIC = {"c2": 474.00e6, "c4": 1145.79e6}
+# c4 at N = 1 (this repo, B200, `python bench.py --config c4`, profiles/r02/): the denominator of the collective
+# block's `vs_n1` when the driver's N > 1 runs time c4 beside the headline config
+C4_N1 = {"value": None, "ms_per_step": None, "source": "profiles/r02/bench_c4_n1.json"}
 
 
 def algorithmic_bytes_per_sample(c):
@@ -250,26 +253,25 @@ def workload_config(cfgname):
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import ubpl_b200  # noqa: F401
-    from ubpl_b200 import _lib, ops, pipeline, synth
+def _timed_replays(step_fn, n, barrier, torch):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(n):
+        step_fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    group = None
-    if world > 1:
-        import torch.distributed as td
-        td.init_process_group("nccl", device_id=dev)
-        group = td.group.WORLD
-        from ubpl_b200 import dist as ubpl_dist
-        # (the selector's communicator / exchange buffer is created below, once the config is known)
-    c = CONFIGS[args.config]
+
+def measure_config(cfgname, args, env, sample_clocks=True, with_e2e=True):
+    """Times one BASELINE config on this rank's GPU (weak scaling: every rank owns a full per-GPU batch).  Returns a
+    dict with the device-timed step (a CUDA graph WITHOUT instrumentation), the per-stage times of its instrumented
+    twin (same kernels, event-record nodes at the stage edges), K1 / K4 alone, the end-to-end number and the clocks."""
+    torch, td, world, rank, local_rank, dev, group = (env[k] for k in ("torch", "td", "world", "rank", "local_rank", "dev", "group"))
+    from ubpl_b200 import _lib, ops, pipeline, synth
+    from ubpl_b200 import dist as ubpl_dist
+    c = CONFIGS[cfgname]
     B, K, M, S, J, H, W = (c[k] for k in "BKMSJHW")
     d = synth.make_batch(B=B, K=K, J=J, H=H, W=W, M=M, S=S, seed=1388, rank=rank, device=dev)
     dec = ops.decode_coeffs(d["center"], d["scale"], [H, W])
@@ -285,26 +287,36 @@ def run_ours(args):
     alpha = min(1 - 1 / (3 + 1), 0.999)              # args.epo = 3
     stats = torch.zeros(4, dtype=torch.int64, device=dev)
 
-    # The step is captured into four CUDA graphs (K1, K2, K3+reduction, K4) so that the ~12 launches of a
-    # 0.2 ms step do not leave the GPU waiting for the host; stage edges are still CUDA events on the
-    # launching stream, recorded live in the timed region.
-    if group is not None and c["select"] == "quantile" and os.environ.get("UBPL_BENCH_P2P", "1") != "0":
-        # the fused selector exchanges the ranks' keys over NVLink peer memory inside its one kernel; when the
-        # IPC mapping is not possible the NCCL selector (eager K2/K3 stages) stays in use
-        p2p_ok = ubpl_dist.init_p2p(group, max_items=max(B * J, 1))
-    else:
-        p2p_ok = False
-    if group is not None and c["select"] == "quantile" and not p2p_ok:
-        ubpl_dist.init_nccl(group)                 # the library's own communicator for the histogram all-reduce
+    p2p_ok = False
+    if group is not None and c["select"] == "quantile":
+        if os.environ.get("UBPL_BENCH_P2P", "1") != "0":
+            # the selector all-reduces its digit histograms over NVLink peer memory inside its one kernel; when the
+            # IPC mapping is not possible the NCCL selector (eager K2/K3 stages) stays in use
+            if ubpl_dist.p2p_ready(group):
+                ubpl_dist.destroy_p2p()
+            p2p_ok = ubpl_dist.init_p2p(group, max_items=max(B * J, 1))
+        if not p2p_ok:
+            ubpl_dist.init_nccl(group)             # the library's own communicator for the histogram all-reduce
     # the EMA runs beside K1 (latency-bound: the EMA's 101 MB of HBM traffic fit beside it); on the multi-GPU quantile
     # path beside the one-CTA selector, whose cross-GPU wait it fills
     overlap = {"0": False, "1": "k1", "k1": "k1", "slow": "k1", "k2": "k2", "k3": "k3"}[
         os.environ.get("UBPL_BENCH_OVERLAP_EMA", "k2" if (c["select"] == "quantile" and world > 1) else "k1")]
-    gstep = pipeline.GraphedStep(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, group=group,
-                                 stats=stats, ema=plan, alpha=alpha, overlap_ema=overlap,
-                                 mode=os.environ.get("UBPL_BENCH_GRAPH", "single"))
-    r = gstep.state
+    gmode = os.environ.get("UBPL_BENCH_GRAPH", "single")
+    bufs = dict(teacher=d["teacher"], student=d["student"], theta=d["theta"], flip=d["flip"])
+    mk = lambda instrument: pipeline.GraphedStep(bufs["teacher"], bufs["student"], bufs["theta"], bufs["flip"], dec, w, cfg,
+                                                 group=group, stats=stats, ema=plan, alpha=alpha, overlap_ema=overlap,
+                                                 mode=gmode, instrument=instrument)
+    lean_ok = os.environ.get("UBPL_BENCH_LEAN", "1") != "0"
+    gstep = mk(not lean_ok)                                   # the step that is timed: no event nodes inside
     single = gstep.mode == "single"
+    gtwin = mk(True) if (single and lean_ok) else gstep      # its instrumented twin: the per-stage times
+    r = gstep.state
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
     stage_events = []
 
     def step(timed=False):
@@ -319,150 +331,304 @@ def run_ours(args):
         if timed and not single:
             stage_events.append(evs)
 
-    def barrier():
-        if world > 1:
-            td.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    # ---- device-resident timing ---------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    sampler.wait_first()
-    stats.zero_()
+    sampler = None
+    if sample_clocks:
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        sampler.wait_first()
     # launches per step: count them on one eager (un-captured) step
+    stats.zero_()
     _lib.reset_launch_count()
     pipeline.pseudo_label_step(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, group=group)
     plan.step(alpha)
     launches_per_step = _lib.launch_count()
     stats.zero_()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     t_load0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        step(timed=True)
-    e1.record()
-    barrier()
-    launches = launches_per_step * args.steps
-    ms_total = e0.elapsed_time(e1)
+    ms_total = _timed_replays(lambda: step(timed=True), args.steps, barrier, torch)
+    slow_frac = float(stats[0]) / max(1.0, float(stats[2]))
+    # per-stage device times: event-record nodes inside the twin's graph, read after each of 32 replays of the
+    # same loop (a read needs a sync, which must stay out of the timed region)
     stage_samples = []
     if single:
-        # the stage edges are event-record nodes INSIDE the step's graph: every timed step records them; they
-        # are read for the last timed step and for 32 more steps of the same loop (a read needs a sync, which
-        # must stay out of the timed region)
-        stage_samples.append(gstep.stage_ms())
         for _ in range(32):
-            step()
+            gtwin.run()
             torch.cuda.synchronize()
-            stage_samples.append(gstep.stage_ms())
-    # post-roll: keep the same load running (untimed) until nvidia-smi has had >= 0.6 s of it to sample
-    while time.time() - t_load0 < 0.6:
-        for _ in range(20):
-            step()
-        torch.cuda.synchronize()
-    t_load1 = time.time()
-    clocks = sampler.stop(t_load0 + 0.05, t_load1)
+            stage_samples.append(gtwin.stage_ms())
+        ms_twin = _timed_replays(lambda: gtwin.run(), min(args.steps, 50), barrier, torch) / min(args.steps, 50)
+    else:
+        ms_twin = None
+    if sampler is not None:
+        while time.time() - t_load0 < 0.6:          # keep the load running until nvidia-smi has had >= 0.6 s of it
+            for _ in range(20):
+                step()
+            torch.cuda.synchronize()
+        clocks = sampler.stop(t_load0 + 0.05, time.time())
+    else:
+        clocks = None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
     ms_step = float(t) / args.steps
     value = world * B / (ms_step * 1e-3)
 
-    # per-stage device time (CUDA events on the launching stream), averaged over the timed steps
-    def avg(a, b):
-        return sum(ev[a].elapsed_time(ev[b]) for ev in stage_events) / len(stage_events)
-
     def savg(n):
         return sum(sm[n] for sm in stage_samples) / len(stage_samples)
+
+    def avg(a, b):
+        return sum(ev[a].elapsed_time(ev[b]) for ev in stage_events) / len(stage_events)
     if single:
         k1_ms, k2_ms, k3_ms = savg("k1"), savg("k2"), savg("k3")
         k4_inline_ms = savg("k4") if "k4" in stage_samples[0] else None
     else:
         k1_ms, k2_ms, k3_ms = avg("k1_0", "k1_1"), avg("k2_0", "k2_1"), avg("k3_0", "k3_1")
         k4_inline_ms = avg("k4_0", "k4_1") if "k4_0" in stage_events[0] else None
-    # the stand-alone time of K4 (one graph replay per launch), measured outside the timed region
-    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g4 = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g4):
-        plan.step(alpha)
-    torch.cuda.synchronize()
-    ee0.record()
-    for _ in range(20):
-        g4.replay()
-    ee1.record()
-    torch.cuda.synchronize()
-    k4_ms = ee0.elapsed_time(ee1) / 20
-    # K1 on its own (no EMA beside it), measured the same way right after the timed region: what the kernel does when
-    # it has the HBM to itself
-    g1 = torch.cuda.CUDAGraph()
+
+    def alone(fn):                                    # a stage on its own, graph replays back to back
+        gg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gg):
+            fn()
+        torch.cuda.synchronize()
+        return _timed_replays(gg.replay, 20, lambda: torch.cuda.synchronize(), torch) / 20
+    k4_ms = alone(lambda: plan.step(alpha))
     st1 = dict(gstep.state)
-    with torch.cuda.graph(g1):
-        pipeline.stage_k1(st1, None, cfg)
-    torch.cuda.synchronize()
-    ee0.record()
-    for _ in range(20):
-        g1.replay()
-    ee1.record()
-    torch.cuda.synchronize()
-    k1_alone_ms = ee0.elapsed_time(ee1) / 20
+    k1_alone_ms = alone(lambda: pipeline.stage_k1(st1, None, cfg))
+
+    out = dict(cfg=cfg, c=c, value=value, ms_step=ms_step, ms_twin=ms_twin, k1_ms=k1_ms, k2_ms=k2_ms, k3_ms=k3_ms,
+               k4_inline_ms=k4_inline_ms, k4_ms=k4_ms, k1_alone_ms=k1_alone_ms, launches=launches_per_step * args.steps,
+               slow_frac=slow_frac, selected_frac=float(r["enable"].float().mean()), clocks=clocks, n_params=n_params,
+               gstep=gstep, overlap=gstep.overlap_ema, single=single, lean=lean_ok and single, p2p_ok=p2p_ok, stats=stats,
+               bufs=bufs, data=d, step=step, barrier=barrier)
+    gstep.check()                                    # device status words (K2 hand-off, peer-memory selector)
+
+    if with_e2e:
+        # ---- end-to-end: host buffers in, host scalars out, copies inside the timed region -----------------------
+        pin_local_numa(local_rank, torch)
+        host = {k: d[k].cpu().pin_memory() for k in ("teacher", "student", "theta")}
+        host["flip"] = gstep.state["flip"].cpu().pin_memory()
+        devbuf = {k: gstep.state[k] for k in host}               # the graph reads its inputs from these tensors
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+        def e2e_step():
+            for k in host:
+                devbuf[k].copy_(host[k], non_blocking=True)
+            rr = gstep.run()
+            return torch.cat([rr["summary"], rr["grad_scale"].double(), rr["count"].double()]).cpu()   # D2H + sync
+        for _ in range(2):
+            o = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(2, min(args.steps, 10))
+        for _ in range(n_e2e):
+            o = e2e_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        out.update(e2e_val=world * B / (float(t) * 1e-3), e2e_ms=float(t), h2d=h2d, d2h=o.numel() * o.element_size())
+    return out
+
+
+def pin_local_numa(local_rank, torch):
+    """Binds this process to the CPUs next to its GPU before the pinned host buffers are allocated (first touch puts
+    the pages on that NUMA node), so that N ranks do not all stage their H2D copies through node 0."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:00.0/local_cpulist" % (dom, bus)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
+    except Exception:
+        pass
+
+
+def sensitivity_block(m, args, env):
+    """K1's cost depends on the data (maps it can prune vs maps that need every output pixel): the same step on
+    (a) the synthetic set with EVERY all-negative map pure noise (noise_only_frac = 1.0, the pre-5de460d data) and
+    (b) the worst case, every teacher map structure-less noise.  Timed in this run, device resident."""
+    torch = env["torch"]
+    from ubpl_b200 import synth
+    c, d, stats, step, barrier = m["c"], m["data"], m["stats"], m["step"], m["barrier"]
+    B, K, M, S, J, H, W = (c[k] for k in "BKMSJHW")
+    keep = d["teacher"].clone()
+    out = {"noise_only_frac=%.1f (bench default)" % 0.2: {"exhaustive_decode_frac": m["slow_frac"], "ms_per_step": m["ms_step"],
+                                                          "k1_standalone_ms": m["k1_alone_ms"]}}
+    from ubpl_b200 import pipeline
+    variants = [("noise_only_frac=1.0", lambda: synth.make_batch(B=B, K=K, J=J, H=H, W=W, M=M, S=S, seed=1388, rank=env["rank"],
+                                                                 device=env["dev"], noise_only_frac=1.0)["teacher"]),
+                ("worst case: every map white noise", lambda: torch.randn_like(keep) * 0.02)]
+    for name, make in variants:
+        d["teacher"].copy_(make())
+        for _ in range(3):
+            step()
+        stats.zero_()
+        n = max(5, min(args.steps, 30))
+        ms = _timed_replays(step, n, barrier, torch) / n
+        frac = float(stats[0]) / max(1.0, float(stats[2]))
+        st1 = dict(m["gstep"].state)
+        gg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gg):
+            pipeline.stage_k1(st1, None, m["cfg"])
+        torch.cuda.synchronize()
+        k1 = _timed_replays(gg.replay, 10, lambda: torch.cuda.synchronize(), torch) / 10
+        out[name] = {"exhaustive_decode_frac": frac, "ms_per_step": ms, "k1_standalone_ms": k1,
+                     "value": env["world"] * B / (ms * 1e-3)}
+    d["teacher"].copy_(keep)
+    return out
+
+
+def ops_block(cfgname, env, peak):
+    """The kernels behind the criteria the reference's drivers call every step (utils/losses.py:169-210 via
+    ubpl_dense_mse, utils/process.py:19-31 via ubpl_features_cov) and the materialised back-warp
+    (utils/augment.py:37-47): GB/s of algorithmic bytes and fraction of the measured HBM peak, CUDA-graph replays."""
+    torch = env["torch"]
+    from ubpl_b200 import ops
+    c = CONFIGS[cfgname]
+    B, M, S, J, H, W = c["B"], max(c["M"], 1), c["S"], c["J"], c["H"], c["W"]
+    dev = env["dev"]
+    g = torch.Generator(device=dev).manual_seed(9)
+    res = {}
+
+    def bench(fn, nbytes, n=20):
+        for _ in range(3):
+            fn()
+        gg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gg):
+            fn()
+        torch.cuda.synchronize()
+        ms = _timed_replays(gg.replay, n, lambda: torch.cuda.synchronize(), torch) / n
+        return {"ms": ms, "gbs": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak, "algorithmic_bytes": nbytes}
+    pred = torch.rand(B, S, J, H, W, generator=g, device=dev)
+    for Mt in sorted({1, 2, M}):
+        tgt = torch.rand(Mt, B, S, J, H, W, generator=g, device=dev)
+        # JointPseudoLoss3: student maps read once, the last-stack teacher maps of the Mt teachers read once, gradient
+        # written once: 4*HW*J*B*(S + Mt + S)
+        res["dense_mse_kernel as JointPseudoLoss3 (M=%d, %s sizes)" % (Mt, cfgname)] = bench(
+            lambda: ops.dense_mse(pred, tgt[:, :, -1], mask_mode=1, thr=0.95), 4 * H * W * J * B * (S + Mt + S))
+        del tgt
+    f1 = torch.randn(B // 2, S, 256, 32, 32, generator=g, device=dev)
+    f2 = torch.randn(B // 2, S, 256, 32, 32, generator=g, device=dev)
+    res["features_cov_kernel fwd+bwd (%d labeled rows, 16 B/element)" % (B // 2)] = bench(
+        lambda: ops.features_cov(f1, f2), 16 * f1.numel())
+    del f1, f2
+    hm = torch.rand(B, J, H, W, generator=g, device=dev)
+    th = torch.zeros(B, 2, 3, device=dev)
+    th[:, 0, 0] = 0.8
+    th[:, 1, 1] = 0.8
+    fl = torch.zeros(B, dtype=torch.uint8, device=dev)
+    res["warp_materialize_kernel (affine_back2, one view, 8 B/texel)"] = bench(
+        lambda: ops.warp_materialize(hm, th, fl), 8 * hm.numel())
+    return res
+
+
+def run_ours(args):
+    import torch
+    import ubpl_b200  # noqa: F401
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group, td = None, None
+    if world > 1:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=dev)
+        group = td.group.WORLD
+    env = dict(torch=torch, td=td, world=world, rank=rank, local_rank=local_rank, dev=dev, group=group)
+    c = CONFIGS[args.config]
+    B, K, M, S, J, H, W = (c[k] for k in "BKMSJHW")
+    m = measure_config(args.config, args, env)
+    cfg = m["cfg"]
+    k1_ms, k2_ms, k3_ms, k4_ms = m["k1_ms"], m["k2_ms"], m["k3_ms"], m["k4_ms"]
     bytes_sample = algorithmic_bytes_per_sample(c)
     k1_bytes = 4 * H * W * J * M * K * B
     k3_bytes = 4 * H * W * J * (2 * S + 1) * B
-    ema_bytes = 12 * n_params
+    ema_bytes = 12 * m["n_params"]
     peak, peak_src = measured_peaks()
     chain_gbs = bytes_sample * B / ((k1_ms + k2_ms + k3_ms) * 1e-3) / 1e9
+    ov = m["overlap"]
     roof = {"bound": "hbm", "kernel": "warp_decode_kernel (K1: %d maps of %d B per launch)" % (M * K * B * J, 4 * H * W),
             "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC.get(args.config), "peak_source": peak_src,
-            "stages_ms": {("k1_warp_decode_with_k4_ema_overlapped" if gstep.overlap_ema == "k1" else "k1_warp_decode"): k1_ms,
-                          ("k2_uncertainty_select_with_k4_ema_overlapped" if gstep.overlap_ema == "k2" else "k2_uncertainty_select"): k2_ms,
-                          ("k3_render_mse_with_k4_ema_overlapped" if gstep.overlap_ema == "k3" else "k3_render_mse"): k3_ms,
-                          "k4_ema_in_step": k4_inline_ms, "k4_ema_standalone": k4_ms, "k1_standalone": k1_alone_ms},
-            "k1_standalone_frac": k1_bytes / (k1_alone_ms * 1e-3) / 1e9 / peak,
-            "stages_note": ("stage edges are event-record nodes inside the step's single CUDA graph; mean of the last "
-                            "timed step and 32 further steps" if single else
+            "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak,
+            "traffic": NCU_TRAFFIC.get(args.config), "traffic_source": "from profile (ncu --set full capture under profiles/, not measured in this run)",
+            "peak_source": peak_src,
+            "stages_ms": {("k1_warp_decode_with_k4_ema_overlapped" if ov == "k1" else "k1_warp_decode"): k1_ms,
+                          ("k2_uncertainty_select_with_k4_ema_overlapped" if ov == "k2" else "k2_uncertainty_select"): k2_ms,
+                          ("k3_render_mse_with_k4_ema_overlapped" if ov == "k3" else "k3_render_mse"): k3_ms,
+                          "k4_ema_in_step": m["k4_inline_ms"], "k4_ema_standalone": k4_ms, "k1_standalone": m["k1_alone_ms"]},
+            "k1_standalone_frac": k1_bytes / (m["k1_alone_ms"] * 1e-3) / 1e9 / peak,
+            "stages_note": ("`value` times the step as ONE CUDA graph without instrumentation (%.4f ms/step); the stage times are "
+                            "the event-record nodes inside its instrumented twin (same kernels; each event node adds ~1.3 us: "
+                            "%.4f ms/step), mean of 32 replays right after the timed region"
+                            % (m["ms_step"], m["ms_twin"]) if (m["single"] and m["lean"]) else
+                            "stage edges are event-record nodes inside the step's single CUDA graph" if m["single"] else
                             "stage edges are CUDA events recorded around each stage graph in every timed step"),
             "k2_fused_into_k1": bool(cfg.fuse_k12 and M <= 2),
             "stages_gbs": {"k1": k1_bytes / (k1_ms * 1e-3) / 1e9, "k3": k3_bytes / (k3_ms * 1e-3) / 1e9,
                            "k4": ema_bytes / (k4_ms * 1e-3) / 1e9, "chain_k1_k3": chain_gbs},
             "chain_frac_of_peak": chain_gbs / peak, "chain_frac_of_8TBs": chain_gbs / 8000.0,
-            "step_gbs_with_ema": (bytes_sample * B + ema_bytes) / (ms_step * 1e-3) / 1e9,
-            "step_frac_of_peak_with_ema": (bytes_sample * B + ema_bytes) / (ms_step * 1e-3) / 1e9 / peak,
+            "step_gbs_with_ema": (bytes_sample * B + ema_bytes) / (m["ms_step"] * 1e-3) / 1e9,
+            "step_frac_of_peak_with_ema": (bytes_sample * B + ema_bytes) / (m["ms_step"] * 1e-3) / 1e9 / peak,
+            "step_frac_of_8TBs_with_ema": (bytes_sample * B + ema_bytes) / (m["ms_step"] * 1e-3) / 1e9 / 8000.0,
             "algorithmic_bytes_per_sample": bytes_sample}
-    slow_frac = float(stats[0]) / max(1.0, float(stats[2]))
 
-    # ---- end-to-end: host buffers in, host scalars out, copies inside the timed region -------------
-    host = {k: d[k].cpu().pin_memory() for k in ("teacher", "student", "theta")}
-    host["flip"] = gstep.state["flip"].cpu().pin_memory()
-    devbuf = {k: gstep.state[k] for k in host}               # the graphs read their inputs from these tensors
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-
-    def e2e_step():
-        for k in host:
-            devbuf[k].copy_(host[k], non_blocking=True)
-        rr = gstep.run()
-        out = torch.cat([rr["summary"], rr["grad_scale"].double(), rr["count"].double()]).cpu()   # D2H + sync
-        return out
-    for _ in range(2):
-        out = e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    n_e2e = max(2, min(args.steps, 10))
-    for _ in range(n_e2e):
-        out = e2e_step()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    e2e_val = world * B / (float(t) * 1e-3)
-    d2h = out.numel() * out.element_size()
-
+    line = {
+        "metric": METRIC, "value": m["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": m["ms_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(args.config), **{
+            "ema_params": m["n_params"], "l2": "inputs (%.0f MB/step) larger than L2" % (bytes_sample * B / 1e6),
+            "selected_frac": m["selected_frac"], "exhaustive_decode_frac": m["slow_frac"], "noise_only_frac": 0.2,
+            "k1_copies_in_flight_cap": int(os.environ.get("UBPL_K1_INFLIGHT", "8")),
+            "launch": ("1 CUDA graph per step" + (" (no event nodes in the timed graph)" if m["lean"] else "")
+                       if m["single"] else "stage graphs (%s)" % ", ".join(
+                           n + (":eager" if n in m["gstep"].eager else ":graph") for n in m["gstep"].order))
+                      + ("; EMA forked onto a side stream beside %s" % {"k1": "K1", "k2": "the selector", "k3": "K3"}[ov]
+                         if ov else "; EMA after K3"),
+            "selector": ("fixed rule in K1's epilogue" if c["select"] == "fixed" and cfg.fuse_k12 and M <= 2 else
+                         "one-kernel quantile selector" + (", histograms all-reduced over NVLink peer memory" if m["p2p_ok"] else "")
+                         if (world == 1 or m["p2p_ok"]) and c["select"] == "quantile" else
+                         "NCCL histogram all-reduce" if c["select"] == "quantile" else "k2 kernels")}),
+        "roofline": roof, "cpu_baseline": None,
+        "e2e": {"value": m["e2e_val"], "unit": "samples/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                "ms_per_step": m["e2e_ms"],
+                "note": "PCIe-bound: the step's inputs (%.0f MB) cross the host link every step" % (m["h2d"] / 1e6)},
+        "gpu_launches": m["launches"], "clocks": m["clocks"],
+    }
+    if world == 1 and not args.no_extras:
+        line["sensitivity"] = sensitivity_block(m, args, env)
+        line["ops"] = ops_block(args.config, env, peak)
+    del m
+    torch.cuda.empty_cache()
+    if world > 1 and args.config != "c4" and not args.no_extras:
+        # the one config with a collective (global-quantile threshold): timed in the same run at this N so that the
+        # scaling record covers the selector's cross-GPU step; `value` above stays the headline config
+        import copy
+        a2 = copy.copy(args)
+        a2.steps, a2.warmup = max(10, min(args.steps, 100)), max(3, min(args.warmup, 10))
+        mc = measure_config("c4", a2, env, sample_clocks=False, with_e2e=False)
+        cc = CONFIGS["c4"]
+        line["collective"] = {
+            "workload": "c4: " + cc["desc"], "value": mc["value"], "unit": "samples/s", "ms_per_step": mc["ms_step"],
+            "steps": a2.steps, "per_gpu_batch": cc["B"], "k1_stage_us": mc["k1_ms"] * 1e3, "k2_stage_us": mc["k2_ms"] * 1e3,
+            "k3_stage_us": mc["k3_ms"] * 1e3,
+            "selector": ("digit histograms all-reduced over NVLink peer memory inside one kernel (ubpl_select_quantile_fused)"
+                         if mc["p2p_ok"] else "NCCL histogram all-reduce (ubpl_select_quantile_dist)"),
+            "n1_reference": C4_N1,
+            "vs_n1": (mc["value"] / C4_N1["value"]) if C4_N1.get("value") else None,
+            "launch": "1 CUDA graph per step" if mc["single"] else "stage graphs + eager NCCL stage"}
+        del mc
     if rank == 0:
-        cpu = None
         if world == 1 and not args.no_cpu_baseline:
             kind = cpu_kind()
             procs = max(1, min(os.cpu_count() or 1, 64))
@@ -476,29 +642,9 @@ def run_ours(args):
                 dt += d_t
             chain.close()
             ema_s = cpu_ema_seconds(c, kind)
-            cpu = {"value": n / (dt + ema_s * n / B), "unit": "samples/s", "cores": procs, "kind": kind,
-                   "sample": cpu_sample_note(kind, procs * per_proc, procs, per_proc, args.config) + "; %d samples in %.1f s" % (n, dt)}
-        line = {
-            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args.config), **{
-                       "ema_params": n_params, "l2": "inputs (%.0f MB/step) larger than L2" % (bytes_sample * B / 1e6),
-                       "selected_frac": float(r["enable"].float().mean()), "exhaustive_decode_frac": slow_frac,
-                       "launch": ("1 CUDA graph per step" if single else "%d stage launches per step (%s)" % (len(gstep.order), ", ".join(
-                                      n + (":eager" if n in gstep.eager else ":graph") for n in gstep.order)))
-                                 + ("; EMA forked onto a side stream beside %s" % {"k1": "K1", "k2": "the selector",
-                                                                                          "k3": "K3"}[gstep.overlap_ema]
-                                    if gstep.overlap_ema else "; EMA after K3"),
-                       "selector": ("fixed rule in K1's epilogue" if c["select"] == "fixed" and cfg.fuse_k12 and M <= 2 else
-                                    "fused one-kernel quantile selector" + (" over NVLink peer memory" if p2p_ok else "")
-                                    if (world == 1 or p2p_ok) and c["select"] == "quantile" else
-                                    "NCCL histogram all-reduce" if c["select"] == "quantile" else "k2 kernels")}),
-            "roofline": roof, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(t)},
-            "gpu_launches": launches, "clocks": clocks,
-        }
+            line["cpu_baseline"] = {"value": n / (dt + ema_s * n / B), "unit": "samples/s", "cores": procs, "kind": kind,
+                                    "sample": cpu_sample_note(kind, procs * per_proc, procs, per_proc, args.config)
+                                    + "; %d samples in %.1f s" % (n, dt)}
         print(json.dumps(line))
     if world > 1:
         td.destroy_process_group()
@@ -512,6 +658,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sensitivity / ops / collective blocks")
     ap.add_argument("--ref-samples-per-proc", type=int, default=0, help="CPU arm: samples per process per step (0 = by config)")
     args = ap.parse_args()
     if args.impl == "reference":

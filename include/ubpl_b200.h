@@ -220,11 +220,16 @@ int ubpl_mix_unc(const double* intDist, const double* extDist, const double* aEx
 
 /* The selector as ONE kernel per GPU (single CTA), single- and multi-GPU:
  *   use_p2p = 0: this GPU's n items are the whole population (k_rank < n; keys = uint64[n] scratch);
- *   use_p2p = 1: every rank stores its distance keys, extrema and item count into its slot of every peer's
- *                exchange buffer over NVLink (ubpl_p2p_alloc / ubpl_p2p_open), publishes an epoch flag, waits
- *                for the peers' flags and then selects over all ranks' keys locally -- no NCCL call, no host
+ *   use_p2p = 1: the all-reduce of the uncertainty histogram BASELINE.json names, done over NVLink peer memory
+ *                inside the one kernel: every rank keeps its own distance keys and, per radix pass (12 bits, then
+ *                11 at a time), stores the digit histogram of its keys (<= 16 KB) into its slot of every peer's
+ *                exchange buffer (ubpl_p2p_alloc / ubpl_p2p_open), publishes a flag (st.release.sys), waits for
+ *                the peers' flags and adds the R histograms found in its own buffer; once the bin that holds the
+ *                global rank has <= 64 keys the ranks exchange those keys instead of another histogram.  O(n) work
+ *                per rank for any number of ranks, typically three NVLink round trips; no NCCL call, no host
  *                work, capturable in a CUDA graph; k_rank = int((n_total-1)*reliablePCT) over all ranks.
- *                Every rank must make the same sequence of calls (it is a collective).
+ *                Every rank must make the same sequence of calls (it is a collective).  n above 16384 items per
+ *                rank needs the keys scratch.
  * legal: float64[n] or uint8[n] (exactly one non-NULL).  Outputs as ubpl_select_quantile_local.
  * kps != NULL (float32 [n,2], image space) folds ubpl_gate_prepare into the launch: gate32 = enable *
  * visibility, *count_out = S * #(gate32 > 0), *grad_scale = loss_weight / count. */
@@ -235,6 +240,15 @@ int ubpl_select_quantile_fused(const double* dist, const double* legal_f64, cons
                                const float* kps, int img_h, int img_w, float stride, float sigma, int S,
                                float loss_weight, float* grad_scale, int32_t* count_out,
                                int use_p2p, void* stream);
+
+/* Test vehicle of the multi-GPU selector's exchange protocol: R ranks emulated by the R blocks of ONE cooperative
+ * launch on one GPU (for boxes with fewer GPUs than ranks).  Rank r owns items [r*n_stride, r*n_stride + n_per_rank[r])
+ * of dist / legal_u8 / keys / reliability / enable / gate32, row r of counts [R, J+1] and thr_out[r]; n_per_rank is a
+ * HOST array; xbuf holds R zeroed exchange buffers of xbuf_stride >= ubpl_p2p_buffer_bytes(R, cap) bytes each. */
+int ubpl_select_quantile_emul(const double* dist, const uint8_t* legal_u8, int R, const int64_t* n_per_rank,
+                              int64_t n_stride, int J, int64_t k_rank, double reliableThr, double reliableDistMin,
+                              double* reliability, uint64_t* keys, uint8_t* enable, float* gate32, int32_t* counts,
+                              double* thr_out, void* xbuf, int64_t xbuf_stride, int64_t cap, void* stream);
 /* Developer hook: 64 device uint64 that receive globaltimer stamps of the selector's phases ([63] = count);
  * NULL switches it off. */
 int ubpl_select_debug_stamps(void* dev_u64x64);
@@ -242,7 +256,9 @@ int ubpl_select_debug_stamps(void* dev_u64x64);
  * `nranks` ranks of at most `max_items` items each and returns its 64-byte CUDA-IPC handle (host buffer); the
  * handles of all ranks, concatenated in rank order (any transport, e.g. torch.distributed all_gather), go to
  * ubpl_p2p_open, which maps the peers' buffers.  ubpl_p2p_status: 0, or 1 after a launch in which a peer did
- * not arrive within the kernel's 4 s time-out (its outputs are then NaN-poisoned instead of hanging). */
+ * not arrive within the time-out (UBPL_P2P_TIMEOUT_MS, read at ubpl_p2p_alloc, default 60 s); the outputs of
+ * that launch are NaN-poisoned (threshold NaN, every mask 0) instead of hanging -- callers must check the status
+ * at a point where a sync is acceptable (dist.check_p2p) and raise. */
 int64_t ubpl_p2p_buffer_bytes(int nranks, int64_t max_items);
 int ubpl_p2p_alloc(int nranks, int64_t max_items, void* handle_out64_host);
 int ubpl_p2p_open(const void* handles_host, int nranks, int rank);

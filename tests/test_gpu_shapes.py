@@ -217,3 +217,39 @@ def test_swap_perm_vs_oracle(ops, shape):
                          swap_perm=torch.arange(J))
     r4 = ops.warp_decode(torch.from_numpy(maps).cuda(), torch.from_numpy(th).cuda(), torch.from_numpy(fl).cuda(), None)
     assert torch.equal(r3["idx"], r4["idx"])
+
+
+@pytest.mark.parametrize("R,n,J,pct", [(2, 192, 6, 0.5), (8, 4352, 17, 0.5), (4, 1000, 9, 0.25), (8, 700, 14, 0.9),
+                                        (16, 64, 4, 0.5), (3, 20000, 14, 0.5)])
+def test_multirank_selector_emulated(ops, R, n, J, pct):
+    """The multi-GPU selector (histograms exchanged through per-rank buffers, flags, gather of the last few keys) with
+    its R ranks emulated by one cooperative launch on this GPU: every rank's threshold and masks equal the
+    single-GPU selection of the concatenated shards (business.py:173-217 on the whole batch), bit for bit -- with
+    ragged shards, ties, illegal items (999) and all-equal distances among the cases."""
+    rng = np.random.default_rng(R * 1000 + n)
+    npr = [n] * R
+    if R == 4:
+        npr = [1000, 37, 512, 999]                                     # ragged shards
+    d = np.round(rng.gamma(2.0, 2.0, (R, n)) * 4) / 4                   # quarter-pixel grid: many exact ties
+    if R == 16:
+        d[:] = 1.5                                                      # every key equal
+    legal = rng.random((R, n)) > 0.1
+    d[~legal] = 999.0
+    dist = torch.from_numpy(d).cuda()
+    leg = torch.from_numpy(legal.astype(np.uint8)).cuda()
+    r = ops.select_quantile_emul(dist, leg, J, 0.0, pct, 1.0, n_per_rank=npr)
+    assert int(r["status"].abs().sum()) == 0
+    cat_d = torch.cat([dist[i, :npr[i]] for i in range(R)])
+    cat_l = torch.cat([leg[i, :npr[i]] for i in range(R)])
+    one = ops.select_quantile_fused(cat_d, cat_l, J, int((sum(npr) - 1) * pct), 0.0, 1.0)
+    thr = float(one["thr"])
+    assert np.array_equal(npy(r["thr"]), np.full(R, thr))
+    off = 0
+    for i in range(R):
+        assert torch.equal(r["enable"][i, :npr[i]], one["enable"][off:off + npr[i]]), i
+        assert torch.equal(r["reliability"][i, :npr[i]], one["reliability"][off:off + npr[i]]), i
+        off += npr[i]
+    # ... and the oracle's filter on the concatenation gives the same threshold and masks
+    rel, othr, en = O.filter_dual(npy(cat_d), npy(cat_l).astype(np.float64), 0.0, pct, 1.0)
+    assert othr == thr
+    assert np.array_equal(npy(one["enable"]).astype(bool), en.reshape(-1))

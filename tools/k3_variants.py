@@ -25,9 +25,12 @@ kps = (d["base_xy"] * 4 + 1).contiguous()
 gate = (torch.rand(B, J, device="cuda") < 0.6).float()
 w = torch.where(d["islabeled"], 0.0, 1.0).float()
 other = torch.empty(64 * 1024 * 1024, device="cuda")        # 256 MB: flush L2 between runs
-for summ in ((False,) if old else (False, True)):
-    for occ in ((6,) if old else (6, 5)):
+VARIANTS = [(5, 0, 0), (5, 1, 0), (5, 1, 4), (5, 1, 3), (5, 1, 2), (5, 0, 4), (5, 0, 3), (5, 0, 2), (6, 0, 0), (6, 1, 0)]
+for summ in ((False,) if old else (True,)):
+    for occ, coop, ctas in ([(6, 0, 0)] if old else VARIANTS):
         os.environ["UBPL_K3_OCC"] = str(occ)
+        os.environ["UBPL_K3_COOP"] = str(coop)
+        os.environ["UBPL_K3_CTAS"] = str(ctas)
         for it in range(3):
             r = ops.render_mse(kps, gate, w, d["student"], 256, 256, want_summary=summ)
         g = torch.cuda.CUDAGraph()
@@ -47,6 +50,6 @@ for summ in ((False,) if old else (False, True)):
         e1.record(); torch.cuda.synchronize()
         ts.sort()
         nbytes = 4 * 4096 * J * B * 5
-        print("lib=%s summary=%s occ=%d: median %.1f us (%.0f GB/s), back-to-back %.1f us (%.0f GB/s)"
-              % ("old" if old else "new", summ, occ, ts[10] * 1e3, nbytes / ts[10] / 1e6, e0.elapsed_time(e1) / 50 * 1e3,
+        print("lib=%s summary=%s occ=%d coop=%d ctas/SM=%d: median %.1f us (%.0f GB/s), back-to-back %.1f us (%.0f GB/s)"
+              % ("old" if old else "new", summ, occ, coop, ctas, ts[10] * 1e3, nbytes / ts[10] / 1e6, e0.elapsed_time(e1) / 50 * 1e3,
                  nbytes / (e0.elapsed_time(e1) / 50) / 1e6), flush=True)

@@ -50,6 +50,8 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_int, c_int, c_float, c_float, c_int, c_float, c_void_p, c_void_p,
                                    c_int, c_void_p],
+    "ubpl_select_quantile_emul": [c_void_p, c_void_p, c_int, c_void_p, c_i64, c_int, c_i64, c_double, c_double,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p],
     "ubpl_select_debug_stamps": [c_void_p],
     "ubpl_p2p_buffer_bytes": [c_int, c_i64],
     "ubpl_p2p_alloc": [c_int, c_i64, c_void_p],

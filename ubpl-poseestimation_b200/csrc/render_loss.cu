@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(128, OCC) render_mse_kernel(
     long long gS, long long gJ, float* __restrict__ target, int B, int S, int J, int H, int W, int img_h, int img_w,
     float stride, float sigma, const float* __restrict__ grad_scale, const int32_t* __restrict__ count_in,
     float loss_weight, float* __restrict__ grad_scale_out, float* __restrict__ gate_out,
-    float* __restrict__ per_loss, const FastDiv divW4, double* __restrict__ summary, unsigned char* __restrict__ sum_ws) {
+    float* __restrict__ per_loss, const FastDiv divW4, double* __restrict__ summary, unsigned char* __restrict__ sum_ws,
+    int all_coop) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   float* ex = sm + (size_t)warp * (W + H);   // [W]
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(128, OCC) render_mse_kernel(
   // would be latency-bound and stretch the launch by ~10 us.
   __shared__ float s_part[2][32];
   const long long round_items = (long long)gridDim.x * wpb;
-  const long long full = (BJ / round_items) * round_items;
+  const long long full = all_coop ? 0 : (BJ / round_items) * round_items;   // all_coop: every item is shared by a CTA
   for (int phase = 0; phase < 2; ++phase) {
   const int nparts = phase ? wpb : 1, part = phase ? warp : 0;
   const long long it_step = phase ? (long long)gridDim.x : round_items;
@@ -380,6 +381,135 @@ __global__ void __launch_bounds__(MAXT) dense_mse_kernel(
   }
 }
 
+// The same loss for the shapes the drivers use (S <= 2 stacks, maps of <= 4096 texels, 128-bit aligned): every load
+// of an item -- the M teacher maps and the S student maps -- is issued before anything is consumed, the five block
+// reductions of the generic kernel (teacher max, then error sum and student max per stack: ten barriers per item)
+// become ONE multi-value reduction behind ONE barrier (partials double-buffered by item parity), and the gradient
+// is written from registers.  Per-thread accumulation order, the warp tree and the warp-order final sums are those
+// of dense_mse_kernel, so the results are bit-identical.
+template <int S_, bool TPS>     // TPS: the targets have their own stack axis (tS != 0)
+__global__ void __launch_bounds__(256) dense_mse_fast_kernel(
+    const float* __restrict__ pred, long long pB, long long pS, long long pJ, const float* __restrict__ tgt, int M,
+    long long tM, long long tB, long long tS, long long tJ, const float* __restrict__ coef, int mask_mode, float thr,
+    float* __restrict__ grad, long long gB, long long gS, long long gJ, int B, int J, int HW,
+    const float* __restrict__ grad_scale, float* __restrict__ per_loss, float* __restrict__ mask_o,
+    float* __restrict__ vmax_p_o, float* __restrict__ vmax_t_o) {
+  constexpr int CH = 4, TS = TPS ? S_ : 1, NV = 2 * S_ + TS;       // values reduced per item: sse[S], pmax[S], tmax[TS]
+  __shared__ float red[2][NV][8];
+  const int nq = HW >> 2, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+  const float gs = grad_scale ? *grad_scale : 1.f;
+  const float inv_hw = 1.f / (float)HW;
+  const float fM = (float)M;
+  int par = 0;
+  for (long long item = blockIdx.x; item < (long long)B * J; item += gridDim.x, par ^= 1) {
+    const int b = (int)(item / J), j = (int)(item % J);
+    const float cf = coef ? coef[item] : 1.f;
+    float4 tb[TS][CH], d[S_][CH];
+    // ---- all loads of the item in flight at once --------------------------------------------------------------
+#pragma unroll
+    for (int s = 0; s < S_; ++s) {
+      const float4* p4 = reinterpret_cast<const float4*>(pred + (long long)b * pB + (long long)s * pS + (long long)j * pJ);
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int q = t + u * blockDim.x;
+        d[s][u] = (q < nq) ? ldg_stream(p4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < TS; ++s) {
+      const float* t0 = tgt + (long long)b * tB + (long long)s * tS + (long long)j * tJ;
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int q = t + u * blockDim.x;
+        tb[s][u] = (q < nq) ? ldg_stream(reinterpret_cast<const float4*>(t0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int m = 1; m < M; ++m) {                      // float32 mean over the teachers in index order (torch.mean)
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+          const int q = t + u * blockDim.x;
+          if (q < nq) {
+            const float4 c = ldg_stream(reinterpret_cast<const float4*>(t0 + (long long)m * tM) + q);
+            tb[s][u].x = __fadd_rn(tb[s][u].x, c.x); tb[s][u].y = __fadd_rn(tb[s][u].y, c.y);
+            tb[s][u].z = __fadd_rn(tb[s][u].z, c.z); tb[s][u].w = __fadd_rn(tb[s][u].w, c.w);
+          }
+        }
+      }
+    }
+    // ---- per-thread partials ------------------------------------------------------------------------------------
+    float v[NV];
+#pragma unroll
+    for (int s = 0; s < TS; ++s) {
+      float tmx = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int q = t + u * blockDim.x;
+        if (q < nq) {
+          if (M > 1) {
+            tb[s][u].x = __fdiv_rn(tb[s][u].x, fM); tb[s][u].y = __fdiv_rn(tb[s][u].y, fM);
+            tb[s][u].z = __fdiv_rn(tb[s][u].z, fM); tb[s][u].w = __fdiv_rn(tb[s][u].w, fM);
+          }
+          tmx = fmaxf(fmaxf(tmx, fmaxf(tb[s][u].x, tb[s][u].y)), fmaxf(tb[s][u].z, tb[s][u].w));
+        }
+      }
+      v[2 * S_ + s] = tmx;
+    }
+#pragma unroll
+    for (int s = 0; s < S_; ++s) {
+      float sse = 0.f, pmx = -INFINITY;
+      const int ts = TPS ? s : 0;
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int q = t + u * blockDim.x;
+        if (q < nq) {
+          const float4 pv = d[s][u];
+          pmx = fmaxf(fmaxf(pmx, fmaxf(pv.x, pv.y)), fmaxf(pv.z, pv.w));
+          d[s][u] = make_float4(pv.x - tb[ts][u].x, pv.y - tb[ts][u].y, pv.z - tb[ts][u].z, pv.w - tb[ts][u].w);
+          sse += d[s][u].x * d[s][u].x + d[s][u].y * d[s][u].y + d[s][u].z * d[s][u].z + d[s][u].w * d[s][u].w;
+        }
+      }
+      v[s] = sse; v[S_ + s] = pmx;
+    }
+    // ---- one reduction for all of them: warp trees, then the warps' partials in warp order ------------------------
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = (k < S_) ? warp_sum(v[k]) : warp_max(v[k]);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) red[par][k][w] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float a = (k < S_) ? 0.f : -INFINITY;
+      for (int i = 0; i < nw; ++i) a = (k < S_) ? a + red[par][k][i] : fmaxf(a, red[par][k][i]);
+      v[k] = a;
+    }
+    // ---- outputs ------------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int s = 0; s < S_; ++s) {
+      const float vt = v[2 * S_ + (TPS ? s : 0)], vp = v[S_ + s];
+      float mk = 1.f;
+      if (mask_mode == 1) mk = (vp >= thr && vt >= thr) ? 1.f : 0.f;
+      else if (mask_mode == 2) mk = (vt >= thr) ? 1.f : 0.f;
+      const long long o = ((long long)b * S_ + s) * J + j;
+      if (t == 0) {
+        if (per_loss) per_loss[o] = (v[s] * inv_hw) * cf;
+        if (mask_o) mask_o[o] = mk;
+        if (vmax_p_o) vmax_p_o[o] = (mask_mode == 1 || vmax_p_o) ? vp : 0.f;
+        if (vmax_t_o) vmax_t_o[o] = vt;
+      }
+      if (grad) {
+        float4* gr = reinterpret_cast<float4*>(grad + (long long)b * gB + (long long)s * gS + (long long)j * gJ);
+        const float gcoef = gs * 2.f * inv_hw * cf * mk;
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+          const int q = t + u * blockDim.x;
+          if (q < nq) stg_stream(gr + q, make_float4(gcoef * d[s][u].x, gcoef * d[s][u].y, gcoef * d[s][u].z, gcoef * d[s][u].w));
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(1024) loss_finalize_kernel(const float* __restrict__ per_loss,
                                                               const float* __restrict__ mask,
                                                               const float* __restrict__ gate, long long BSJ,
@@ -480,6 +610,11 @@ static int render_mse_impl(const float* kps, const float* gate_in, const float* 
   // one resident wave: the kernel loops over whole rounds of grid*wpb items and shares the leftover items
   // between the warps of a CTA, so a second, partial wave of CTAs would only add a tail
   long long cap = (long long)sm_count() * (occ5 ? 5 : 6);
+  // every item shared by the 4 warps of a CTA (740 CTAs each streaming one item: 2 reads + 3 writes of 16 KB) instead
+  // of one item per warp (2960 warps, 5 streams each): fewer, larger concurrent streams -- 62.0 -> 56.8 us on c2
+  // (profiles/README.md round 2; same HBM concurrency effect as K1's copy cap).  UBPL_K3_COOP=0 restores one warp per item.
+  const int all_coop = getenv("UBPL_K3_COOP") ? atoi(getenv("UBPL_K3_COOP")) : 1;
+  if (getenv("UBPL_K3_CTAS") && atoi(getenv("UBPL_K3_CTAS")) > 0) cap = (long long)sm_count() * atoi(getenv("UBPL_K3_CTAS"));
   if (cap > 4096) cap = 4096;             // UBPL_RENDER_SUM_WS_BYTES holds 4096 CTA partials
   // fewer items than one round of warps: a CTA per item (the kernel's cooperative phase) keeps 4 warps streaming
   // every item instead of one, which matters when the maps are large and the items few (fly: 128x128, B*J = 1024)
@@ -488,10 +623,10 @@ static int render_mse_impl(const float* kps, const float* gate_in, const float* 
 #define UBPL_LAUNCH_RENDER(V, SSV)                                                                                     \
   if (occ5) render_mse_kernel<V, SSV, 5><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(                              \
       kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS, gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
-      grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, sum_ws);                 \
+      grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, sum_ws, all_coop);       \
   else render_mse_kernel<V, SSV, 6><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(                                   \
       kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS, gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
-      grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, sum_ws)
+      grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, sum_ws, all_coop)
   if (vec) {
     if (S % 2 == 0) UBPL_LAUNCH_RENDER(true, 2); else UBPL_LAUNCH_RENDER(true, 1);
   } else {
@@ -556,6 +691,19 @@ extern "C" int ubpl_dense_mse(const float* pred, int64_t pB, int64_t pS, int64_t
   const int nq = (int)((HW + 3) / 4);
   const int grid = (int)(BJ < (long long)sm_count() * 16 ? BJ : (long long)sm_count() * 16);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool fast_ok = vec && S <= 2 && nq <= 4 * 256 && (getenv("UBPL_DENSE_FAST") ? atoi(getenv("UBPL_DENSE_FAST")) != 0 : true);
+  if (fast_ok) {
+    int threads = ((nq + 3) / 4 + 31) / 32 * 32;
+    if (threads < 32) threads = 32;
+    const int g2 = (int)(BJ < (long long)sm_count() * 8 ? BJ : (long long)sm_count() * 8);
+#define UBPL_DENSE_FAST(SV, TP)                                                                                          \
+    dense_mse_fast_kernel<SV, TP><<<g2, threads, 0, st>>>(pred, pB, pS, pJ, tgt, M, tM, tB, tS, tJ, coef, mask_mode, thr, grad, \
+                                                         gB, gS, gJ, B, J, (int)HW, grad_scale, per_loss, mask, vmax_p, vmax_t)
+    if (S == 1) { if (tS != 0) UBPL_DENSE_FAST(1, true); else UBPL_DENSE_FAST(1, false); }
+    else { if (tS != 0) UBPL_DENSE_FAST(2, true); else UBPL_DENSE_FAST(2, false); }
+#undef UBPL_DENSE_FAST
+    return check_launch("ubpl_dense_mse");
+  }
   if (nq <= 4 * 256) {
     int threads = ((nq + 3) / 4 + 31) / 32 * 32;
     if (threads < 32) threads = 32;

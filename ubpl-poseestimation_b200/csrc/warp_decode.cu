@@ -255,11 +255,16 @@ __device__ __noinline__ ArgMax decode_exhaustive(uint32_t sa, uint32_t lxa, uint
 // kernel launch.  One job per CTA at a time (a second poster helps the first job while it waits).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kBands = 16;
+constexpr int kChunk = 8;         // maps per chunk of the work distribution
+constexpr int kChunkRing = 8;     // chunk descriptors kept per CTA
 struct CoopJob {
   int owner;        // 0 = free, w + 1 = warp w holds the job slot
   int band_next;    // next band to claim; >= kBands: no open job
   int bands_done;   // bands whose partial result is written
   int warps_done;   // warps of the CTA that have run out of maps
+  int local_next;   // the CTA's map tickets (see claim_map): ticket s -> chunk s / kChunk, offset s % kChunk
+  int chunk_base[kChunkRing];    // first map index of the chunks the CTA holds, and for which chunk number (+1) each
+  int chunk_ready[kChunkRing];   // ring slot is valid
   unsigned issued;  // copy tickets handed out / copies that have landed: a warp with ticket t issues its copy once
   unsigned landed;  // t - landed < WDParams::inflight_cap (FIFO, no retry races; both unused when the cap is 0)
   int flags;        // bit 0: mirrored view, bit 1: the map may hold NaN / Inf (NaN-aware compare)
@@ -297,12 +302,16 @@ __device__ __forceinline__ void coop_help(CoopJob* cj, const WDParams& p, const 
 // Posts the map staged at `s` as the CTA's job, works on it, and returns its exact arg-max (warp-wide call).
 __device__ __forceinline__ ArgMax coop_exhaustive(CoopJob* cj, const WDParams& p, const float* s, const Xform& X,
                                                   bool nan_aware, const float* lx, const float* ly, int warp, int lane) {
-  for (;;) {                                                 // take the job slot; help whoever holds it meanwhile
+  {
+    // Take the CTA's job slot.  If another warp holds it, structure-less maps are frequent here (several at once in
+    // one CTA): cooperation then only serialises them, so this warp decodes its map on its own -- every warp busy
+    // with a whole map is the best the SM can do when most maps need all their pixels.
     int got = 0;
     if (lane == 0) got = (atomicCAS(&cj->owner, 0, warp + 1) == 0) ? 1 : 0;
     got = __shfl_sync(0xffffffffu, got, 0);
-    if (got) break;
-    coop_help(cj, p, lx, ly, lane);
+    if (!got)
+      return decode_exhaustive(smem_u32(s), smem_u32(lx), smem_u32(ly), X.t00, X.t01, X.t02, X.t10, X.t11, X.t12, p.sfx, p.sfy,
+                               p.H, p.W, (X.flip ? 1 : 0) | (nan_aware ? 2 : 0), lane, 0, p.H);
   }
   if (lane == 0) {
     *reinterpret_cast<volatile unsigned*>(&cj->src) = smem_u32(s);
@@ -388,6 +397,29 @@ __device__ __forceinline__ const float* map_src(const WDParams& p, long long n) 
   p.divB.divmod(vb, v, b);
   j = src_joint(p, vb, j);
   return p.maps + (long long)v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
+}
+
+// Dynamic work distribution in two levels.  Maps are handed out in chunks of kChunk consecutive indices: CTA b owns
+// chunks b and gridDim + b from the start, every further chunk is drawn from the global counter p.work (chunk number
+// 2 * gridDim + counter).  Inside the CTA the warps draw tickets from a shared-memory counter; the warp that draws the
+// first ticket of chunk q fetches chunk q + 2 from the global counter, two chunks (>= one map per warp) ahead of its
+// use.  One global atomic per kChunk maps instead of one per map: the single hot address was a measurable stall (the
+// per-map claims of 2072 warps queued at one L2 atomic unit, ~8 % of the warps' time).  Chunk numbers grow along a
+// CTA's ticket sequence, so the first ticket that lands beyond the last map ends the warp.  Lane 0 only.
+__device__ __forceinline__ long long claim_map(const WDParams& p, CoopJob* cj) {
+  const int s = atomicAdd(&cj->local_next, 1);
+  const int q = s / kChunk, o = s - q * kChunk;
+  if (o == 0) {
+    const unsigned long long g = atomicAdd(p.work, 1ull);
+    const unsigned long long base = (2ull * gridDim.x + g) * kChunk;
+    *reinterpret_cast<volatile int*>(&cj->chunk_base[(q + 2) % kChunkRing]) = base > 0x7fffffffull ? 0x7fffffff : (int)base;
+    __threadfence_block();
+    *reinterpret_cast<volatile int*>(&cj->chunk_ready[(q + 2) % kChunkRing]) = q + 3;
+  }
+  while (ld_volatile_s32(&cj->chunk_ready[q % kChunkRing]) != q + 1) {
+  }
+  __threadfence_block();
+  return (long long)ld_volatile_s32(&cj->chunk_base[q % kChunkRing]) + o;
 }
 
 // Called by lane 0.  With a cap, first takes a ticket and waits until fewer than `cap` of the CTA's copies are in
@@ -805,44 +837,56 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   uint64_t pol = 0;
   if (threadIdx.x == 0) {
     cj->owner = 0; cj->band_next = kBands; cj->bands_done = 0; cj->warps_done = 0; cj->issued = 0u; cj->landed = 0u;
+    cj->local_next = 0;
+    for (int k = 0; k < kChunkRing; ++k) { cj->chunk_base[k] = 0; cj->chunk_ready[k] = 0; }
+    const unsigned long long c0 = (unsigned long long)blockIdx.x * kChunk, c1 = ((unsigned long long)gridDim.x + blockIdx.x) * kChunk;
+    cj->chunk_base[0] = c0 > 0x7fffffffull ? 0x7fffffff : (int)c0; cj->chunk_ready[0] = 1;
+    cj->chunk_base[1] = c1 > 0x7fffffffull ? 0x7fffffff : (int)c1; cj->chunk_ready[1] = 2;
   }
   for (int k = threadIdx.x; k < W; k += blockDim.x) lx[k] = lin_coord(k, W, p.stepx);
   for (int k = threadIdx.x; k < H; k += blockDim.x) ly[k] = lin_coord(k, H, p.stepy);
-  // dynamic work distribution: every warp claims the next map index from a global counter, so a
-  // warp that meets an expensive map does not delay a fixed share of the work.  The claim is
-  // split in two: the atomic is ISSUED one map ahead (claim_issue) and its result is only read when the
-  // staging buffer is free again (claim_get), so its ~1 us round trip to L2 overlaps the decode instead of
-  // sitting between two maps.
-  unsigned long long claim_reg = 0;                      // lane 0: result of the atomic in flight
-  auto claim_issue = [&]() {
-    // volatile asm: a plain atomicAdd is sunk by the compiler to the first use of its result
-    if (lane == 0) asm volatile("atom.add.relaxed.gpu.global.u64 %0, [%1], 1;" : "=l"(claim_reg) : "l"(p.work) : "memory");
+  // The per-map transform (theta, flip) of the NEXT map is loaded as soon as that map is known -- before the epilogue
+  // of the current one -- so that the ~0.3 us of L2 latency is off the path between two maps.
+  struct Next {
+    long long n;
+    float t00, t01, t02, t10, t11, t12;
+    bool flip;
+  } nx;
+  nx.n = N; nx.t00 = nx.t01 = nx.t02 = nx.t10 = nx.t11 = nx.t12 = 0.f; nx.flip = false;
+  auto fetch_next = [&]() {                              // draws the warp's next map and starts its transform loads
+    long long nn = 0;
+    if (lane == 0) nn = claim_map(p, cj);
+    nx.n = (long long)__shfl_sync(0xffffffffu, (unsigned long long)nn, 0);
+    if (nx.n < N && p.do_warp) {
+      const unsigned vb = p.divJ.div((unsigned)nx.n);
+      // volatile asm: the loads are ISSUED here (a plain load may be sunk to its first use, after the epilogue)
+      const float* t = p.theta + (long long)vb * 6;
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(nx.t00) : "l"(t));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(nx.t01) : "l"(t + 1));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(nx.t02) : "l"(t + 2));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(nx.t10) : "l"(t + 3));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(nx.t11) : "l"(t + 4));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(nx.t12) : "l"(t + 5));
+      unsigned fl = 0;
+      if (p.flip) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(fl) : "l"(p.flip + vb));
+      nx.flip = fl != 0;
+    }
   };
-  auto claim_get = [&]() -> long long { return (long long)__shfl_sync(0xffffffffu, claim_reg, 0); };
-  claim_issue();
   if (p.use_bulk && lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
     pol = l2_evict_first_policy();
   }
   __syncthreads();
-  long long cur = claim_get();
-  if (p.use_bulk && lane == 0 && cur < N) issue_map(p, cur, buf0, bar, pol, map_bytes, cj);
-  claim_issue();
-  // hand the staging buffer to the next map: returns its index (>= N when the work is exhausted)
-  auto advance = [&]() -> long long {
-    const long long nn = claim_get();
-    if (p.use_bulk && lane == 0 && nn < N) issue_map(p, nn, buf0, bar, pol, map_bytes, cj);
-    if (nn < N) claim_issue();
-    return nn;
-  };
+  fetch_next();
+  if (p.use_bulk && lane == 0 && nx.n < N) issue_map(p, nx.n, buf0, bar, pol, map_bytes, cj);
 
   unsigned long long n_slow = 0, n_eval = 0, n_maps = 0;
   long long pend_item = -1;                              // K2 ticket of the previous map (see finish_map)
   unsigned pend_old = 0;
   long long it = 0;                                      // staged copies waited for so far (mbarrier parity)
   for (;; ++it) {
-    const long long n = cur;
+    const long long n = nx.n;
     if (n >= N) break;
     const float* s = buf0;
     // an exhaustive job posted by another warp of this CTA: help before this map (whose copy is in flight).  The
@@ -857,7 +901,6 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     p.divJ.divmod((unsigned)n, vbu, ju);
     p.divB.divmod(vbu, vu, bu);
     const int j = (int)ju, b = (int)bu;
-    const long long vb = (long long)vbu;
     // ---- per-map transform set-up, issued BEFORE waiting for the staged map so that the global loads of
     // theta / flip / dec and the inverse-affine arithmetic overlap the copy latency
     Xform X;
@@ -870,7 +913,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
     if (p.dec) { const double* c = p.dec + (size_t)b * 4; dc0 = c[0]; dc1 = c[1]; dc2 = c[2]; dc3 = c[3]; }
     if (p.do_warp) {
-      load_xform(X, p.theta, p.flip, vb, H, W);
+      X.t00 = nx.t00; X.t01 = nx.t01; X.t02 = nx.t02; X.t10 = nx.t10; X.t11 = nx.t11; X.t12 = nx.t12; X.flip = nx.flip;
       // pixel-space affine  ix = a*jw + bb*i + c0 ; iy = d*jw + e*i + f0  (approximate, for boxes only)
       const float a = X.t00 * X.stepx * X.sfx, bb = X.t01 * X.stepy * X.sfx;
       const float d = X.t10 * X.stepx * X.sfy, e = X.t11 * X.stepy * X.sfy;
@@ -937,6 +980,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       }
     }
 
+    fetch_next();                                        // next map + its transform loads, consumed after the epilogue
     if (p.do_warp) {                                     // second look at the CTA's job word, half a map after the first
       int open = 0;
       if (lane == 0) open = ld_volatile_s32(&cj->band_next) < kBands ? 1 : 0;
@@ -947,7 +991,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       finish_map(p, n, (int)vu, b, j, s, X, lx, ly, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
     } else if (rv == 123.456f && p.out_max) p.out_max[n] = rv;
     __syncwarp();
-    cur = advance();
+    if (p.use_bulk && lane == 0 && nx.n < N) issue_map(p, nx.n, buf0, bar, pol, map_bytes, cj);   // buffer handed on
   }
   k2_resolve(p, pend_item, pend_old, lane);
   if (p.stats && lane == 0 && n_maps) {

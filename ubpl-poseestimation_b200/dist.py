@@ -91,6 +91,18 @@ def p2p_status():
     return int(_lib.lib().ubpl_p2p_status())
 
 
+def check_p2p():
+    """Raises if a launch of the peer-memory selector gave up waiting for a peer (status word of the exchange
+    buffer; one D2H copy).  The outputs of such a launch are NaN-poisoned (every mask 0) on the ranks that timed out
+    while the late rank computes a valid result -- the ranks have diverged, so this must stop the run.  Call it where
+    a sync is acceptable: every N steps, at epoch boundaries, before a checkpoint."""
+    st = p2p_status()
+    if st != 0:
+        raise _lib.UbplError("ubpl_b200: the multi-GPU selector timed out waiting for a peer (status %d): the pseudo-label "
+                             "masks of that step are void on this rank; raise UBPL_P2P_TIMEOUT_MS or use the NCCL "
+                             "selector (UBPL_BENCH_P2P=0 / dist.init_nccl)" % st)
+
+
 def destroy_p2p():
     global _p2p_world
     _lib.call("ubpl_p2p_close")

@@ -340,7 +340,7 @@ def select_quantile_fused(dist, legal, J, k_rank, reliableThr, reliableDistMin, 
     n = dist.numel()
     dev = dist.device
     rel = torch.empty(n, dtype=_f64, device=dev)
-    keys = None if p2p else torch.empty(n, dtype=torch.int64, device=dev)
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
     enable = torch.empty(n, dtype=torch.uint8, device=dev)
     g32 = torch.empty(n, dtype=_f32, device=dev)
     counts = torch.empty(J + 1, dtype=torch.int32, device=dev)
@@ -360,6 +360,36 @@ def select_quantile_fused(dist, legal, J, k_rank, reliableThr, reliableDistMin, 
               float(lw), _p(grad_scale), _p(count), 1 if p2p else 0, _stream())
     return dict(reliability=rel, enable=enable, gate=g32, counts=counts, thr=thr, ext=ext, grad_scale=grad_scale,
                 count=count, gate_fused=gate is not None)
+
+
+def select_quantile_emul(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, n_per_rank=None):
+    """The multi-GPU selector with its R ranks emulated on ONE GPU (ubpl_select_quantile_emul: R blocks of one
+    cooperative launch exchange their histograms through R local exchange buffers exactly as R GPUs do over NVLink).
+    dist / legal [R, n]; n_per_rank (optional list) = items rank r really owns (ragged shards).  Returns per-rank
+    enable [R, n] (rows valid up to n_per_rank[r]), counts [R, J+1], thr [R], reliability [R, n]."""
+    import ctypes
+    _need_cuda(dist, legal)
+    R, n = dist.shape
+    dist = dist.to(_f64).contiguous()
+    legal = legal.to(torch.uint8).contiguous()
+    dev = dist.device
+    npr = [n] * R if n_per_rank is None else [int(x) for x in n_per_rank]
+    n_total = sum(npr)
+    cap = max(n, 1)
+    stride = (int(_lib.lib().ubpl_p2p_buffer_bytes(R, cap)) + 255) // 256 * 256
+    xbuf = torch.zeros(R * stride, dtype=torch.uint8, device=dev)
+    rel = torch.zeros(R, n, dtype=_f64, device=dev)
+    keys = torch.empty(R, n, dtype=torch.int64, device=dev)
+    enable = torch.zeros(R, n, dtype=torch.uint8, device=dev)
+    g32 = torch.zeros(R, n, dtype=_f32, device=dev)
+    counts = torch.zeros(R, J + 1, dtype=torch.int32, device=dev)
+    thr = torch.zeros(R, dtype=_f64, device=dev)
+    arr = (ctypes.c_int64 * R)(*npr)
+    _lib.call("ubpl_select_quantile_emul", dist.data_ptr(), legal.data_ptr(), R, ctypes.cast(arr, ctypes.c_void_p), n, J,
+              int((n_total - 1) * reliablePCT), float(reliableThr), float(reliableDistMin), rel.data_ptr(), keys.data_ptr(),
+              enable.data_ptr(), g32.data_ptr(), counts.data_ptr(), thr.data_ptr(), xbuf.data_ptr(), stride, cap, _stream())
+    status = xbuf.view(R, stride)[:, 68:72].contiguous().view(torch.int32).reshape(R)
+    return dict(reliability=rel, enable=enable, gate=g32, counts=counts, thr=thr, status=status)
 
 
 def select_quantile(dist, legal, J, reliableThr, reliablePCT, reliableDistMin, group=None, n_total=None, backend=None,
