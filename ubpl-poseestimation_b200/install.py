@@ -33,23 +33,49 @@ CLASS_PATCHES = {
 }
 
 
+_saved = []          # (object, attribute name, original value or _MISSING) of the last install()
+_MISSING = object()
+
+
+def _swap(obj, name, value):
+    _saved.append((obj, name, obj.__dict__.get(name, _MISSING)))
+    setattr(obj, name, value)
+
+
 def install():
     """Patch the already-importable reference modules in place; returns the list of patched names."""
     done = []
     for mod_name, attrs in PATCHES.items():
         mod = importlib.import_module(mod_name)
         for k, v in attrs.items():
-            setattr(mod, k, v)
+            _swap(mod, k, v)
             done.append("%s.%s" % (mod_name, k))
     for (mod_name, cls_name), (src, names) in CLASS_PATCHES.items():
         cls = getattr(importlib.import_module(mod_name), cls_name)
         for n in names:
-            setattr(cls, n, getattr(src, n))          # bound to THIS package's class: its helpers stay reachable
+            _swap(cls, n, getattr(src, n))            # bound to THIS package's class: its helpers stay reachable
             done.append("%s.%s.%s" % (mod_name, cls_name, n))
     try:
         um = importlib.import_module("utils.udaap.utils_mt")
-        um.update_ema_variables = parameters.update_ema_variables
+        _swap(um, "update_ema_variables", parameters.update_ema_variables)
         done.append("utils.udaap.utils_mt.update_ema_variables")
     except Exception:
         pass
     return done
+
+
+def uninstall():
+    """Puts back what install() replaced (tests compare the reference's own classes with the patched ones in one
+    process); returns the number of attributes restored."""
+    n = 0
+    while _saved:
+        obj, name, old = _saved.pop()
+        if old is _MISSING:
+            try:
+                delattr(obj, name)
+            except AttributeError:
+                pass
+        else:
+            setattr(obj, name, old)
+        n += 1
+    return n
