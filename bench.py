@@ -44,7 +44,8 @@ METRIC = "pseudo-labelled samples/sec"
 NCU_TRAFFIC = {"c2": 474.00e6, "c4": 1145.79e6}
 # c4 at N = 1 (this repo, B200, `python bench.py --config c4`, profiles/r02/): the denominator of the collective
 # block's `vs_n1` when the driver's N > 1 runs time c4 beside the headline config
-C4_N1 = {"value": None, "ms_per_step": None, "source": "profiles/r02/bench_c4_n1.json"}
+C4_N1 = {"value": 827736.0, "ms_per_step": 0.3093, "source": "profiles/r02/bench_c4_n1.json (builder-run, 1 B200); the N = 1 run of this "
+         "script carries its own `collective` block, which is the denominator to use"}
 
 
 def algorithmic_bytes_per_sample(c):
@@ -610,9 +611,10 @@ def run_ours(args):
         line["ops"] = ops_block(args.config, env, peak)
     del m
     torch.cuda.empty_cache()
-    if world > 1 and args.config != "c4" and not args.no_extras:
-        # the one config with a collective (global-quantile threshold): timed in the same run at this N so that the
-        # scaling record covers the selector's cross-GPU step; `value` above stays the headline config
+    if args.config != "c4" and not args.no_extras:
+        # the one config with a collective (global-quantile threshold): timed in the same run at EVERY N (at N = 1 the
+        # selector has no peer to talk to) so that the driver's scaling record covers the selector's cross-GPU step and
+        # its own N = 1 denominator; `value` above stays the headline config
         import copy
         a2 = copy.copy(args)
         a2.steps, a2.warmup = max(10, min(args.steps, 100)), max(3, min(args.warmup, 10))
@@ -623,7 +625,8 @@ def run_ours(args):
             "steps": a2.steps, "per_gpu_batch": cc["B"], "k1_stage_us": mc["k1_ms"] * 1e3, "k2_stage_us": mc["k2_ms"] * 1e3,
             "k3_stage_us": mc["k3_ms"] * 1e3,
             "selector": ("digit histograms all-reduced over NVLink peer memory inside one kernel (ubpl_select_quantile_fused)"
-                         if mc["p2p_ok"] else "NCCL histogram all-reduce (ubpl_select_quantile_dist)"),
+                         if mc["p2p_ok"] else "one-kernel selector, single GPU (no exchange)" if world == 1 else
+                         "NCCL histogram all-reduce (ubpl_select_quantile_dist)"),
             "n1_reference": C4_N1,
             "vs_n1": (mc["value"] / C4_N1["value"]) if C4_N1.get("value") else None,
             "launch": "1 CUDA graph per step" if mc["single"] else "stage graphs + eager NCCL stage"}

@@ -113,4 +113,4 @@ def test_workspace_size_helpers():
 def test_grouped_rejects_other_criteria():
     from ubpl_b200 import losses
     with pytest.raises(TypeError):
-        losses.grouped(losses.JointPseudoLoss3(nStack=2), torch.zeros(1, 1, 2, 1, 8, 8), torch.zeros(1, 1, 1, 8, 8))
+        losses.grouped(losses.JointDistLoss_mt2(nStack=2), torch.zeros(1, 1, 2, 1, 8, 8), torch.zeros(1, 1, 1, 8, 8))

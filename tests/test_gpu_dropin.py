@@ -370,3 +370,39 @@ def test_grouped_criteria(pkg):
         np.testing.assert_allclose(sums.detach().cpu().numpy(), torch.stack(want_s).detach().cpu().numpy(), rtol=1e-6)
         np.testing.assert_allclose(g_batched.cpu().numpy(), preds.grad.cpu().numpy(), rtol=1e-6, atol=1e-12)
         preds.grad = None
+
+
+def test_grouped_pseudo_loss3(pkg):
+    """N4: the M*K JointPseudoLoss3 calls of the epc loop (projects/MT_UBPL.py:270-298) in one kernel and one sync ==
+    the loop of separate calls (sums, python-int counts, joint scores, gradients), with the teacher stacks addressed
+    in place through strides (outs_ema[:, a] of every view, last stack)."""
+    g = torch.Generator().manual_seed(4)
+    M, K, B, S, J, Mt = 2, 3, 5, 2, 4, 2
+    blob = torch.zeros(1, K, B, 1, J, 32, 32)
+    cx = torch.randint(6, 26, (K, B, J), generator=g)
+    cy = torch.randint(6, 26, (K, B, J), generator=g)
+    ys, xs = torch.arange(32).view(32, 1).float(), torch.arange(32).view(1, 32).float()
+    for k in range(K):
+        for b in range(B):
+            for j in range(J):
+                blob[0, k, b, 0, j] = torch.exp(-((xs - cx[k, b, j]) ** 2 + (ys - cy[k, b, j]) ** 2) / 18.0)
+    outs = ((0.8 + 0.3 * torch.rand(M, K, B, S, J, 1, 1, generator=g)) * blob).cuda().requires_grad_(True)
+    outs_ema = ((0.8 + 0.3 * torch.rand(Mt, K, B, S, J, 1, 1, generator=g)) * blob).cuda()
+    w = torch.tensor([[1.0], [1.0], [0.0], [1.0], [0.0]]).cuda()
+    crit = pkg.losses.JointPseudoLoss3(nStack=S, scoreThr=0.95)
+    wts = torch.rand(M * K, generator=g).cuda()
+    preds = outs.reshape(M * K, B, S, J, 32, 32)
+    # group g = m*K + a is compared with the teachers' view a: [Mt, G, B, S, J, H, W] without a copy
+    tg = outs_ema.unsqueeze(1).expand(Mt, M, K, B, S, J, 32, 32).reshape(Mt, M * K, B, S, J, 32, 32)
+    sums, n_pseudo, n_sel, jsm, t1, t2 = pkg.losses.grouped(crit, preds, tg, sampleWeight=w)
+    (sums * wts).sum().backward()
+    g_batched = outs.grad.clone()
+    outs.grad = None
+    want = [crit(outs[m, a], outs_ema.clone()[:, a].detach(), w) for m in range(M) for a in range(K)]
+    (torch.stack([x[0] for x in want]) * wts).sum().backward()
+    assert n_pseudo == [x[1] for x in want] and n_sel == [x[2] for x in want]
+    assert sum(n_sel) > 0
+    np.testing.assert_allclose(sums.detach().cpu().numpy(), torch.stack([x[0] for x in want]).detach().cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(jsm.cpu().numpy(), torch.stack([x[3] for x in want]).cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(g_batched.cpu().numpy(), outs.grad.cpu().numpy(), rtol=1e-6, atol=1e-12)
+    assert t1 == t2 == 0.95

@@ -381,3 +381,28 @@ def test_empty_and_degenerate_shapes(ops):
     assert a["summary"].tolist() == [0.0, 0.0, 0.0, 0.0]
     out = ops.view_kps(torch.zeros(0, 4, 3, device="cuda"), torch.zeros(2, 0, 3, 3, dtype=torch.float64, device="cuda"), None, 256)
     assert out.shape == (2, 0, 4, 3)
+
+
+def test_stream_chunks_matches_per_chunk_steps(ops):
+    """pipeline.stream_chunks (c5: a batch streamed through two device buffer sets, H2D of chunk i+1 beside the chain
+    of chunk i) gives, chunk by chunk, what pseudo_label_step gives on that slice, and hands every chunk's gradient to
+    the callback before its buffers are reused."""
+    from ubpl_b200 import synth, pipeline
+    B, K, J, chunk = 12, 4, 5, 4
+    d = synth.make_batch(B=B, K=K, J=J, M=1, S=2, seed=21, jitter=0.6)
+    dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64]).cuda()
+    w = pipeline.nega_weights(d["islabeled"].cuda(), 1.0)
+    cfg = pipeline.StepConfig(select="fixed", distThrMax=2.0)
+    host = dict(teacher=d["teacher"].pin_memory(), student=d["student"].pin_memory(), theta=d["theta"].pin_memory(),
+                flip=d["flip"].to(torch.uint8).pin_memory())
+    grads = {}
+    out = pipeline.stream_chunks(host, dec, w, cfg, chunk, on_chunk=lambda i, st: grads.__setitem__(i, st["grad"].clone()))
+    torch.cuda.synchronize()
+    assert len(out) == B // chunk
+    for i, b0 in enumerate(range(0, B, chunk)):
+        sl = slice(b0, b0 + chunk)
+        ref = pipeline.pseudo_label_step(d["teacher"][:, :, sl].cuda(), d["student"][sl].cuda(), d["theta"][:, sl].cuda(),
+                                         d["flip"][:, sl].cuda(), dec[sl], w[sl], cfg)
+        assert torch.equal(out[i]["summary"], ref["summary"]), i
+        assert torch.equal(out[i]["grad_scale"], ref["grad_scale"]) and int(out[i]["count"]) == int(ref["count"])
+        assert torch.equal(grads[i], ref["grad"]), i

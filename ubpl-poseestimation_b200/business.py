@@ -16,8 +16,8 @@ distances whose radicand is not an integer (error against a fractional gt, aExtD
 taken with CPython's own `** 0.5` on the host so that every record field is bit-identical.
 """
 import copy
+import numpy as np
 import math
-
 import torch
 
 from . import ops
@@ -118,31 +118,40 @@ class BusinessUtils:
             p["reliability"] = rel[i]
         return cls._collect(pseudoArray, rel, en, thr, args)
 
+    @staticmethod
+    def _tally(items, enabled, kps_count):
+        """Per-joint and overall (count, mean error, mean PCK flag) of the enabled records, slot kps_count = all joints:
+        what the reference accumulates record by record (utils/business.py:69-91,195-217,243-261).  np.bincount adds
+        its weights in array order, i.e. in the order of `items`, so the float sums round like the reference's running
+        `+=`; joints without a selected record keep the integer 0 the reference initialises them with."""
+        n = kps_count + 1
+        on = np.flatnonzero(np.asarray(enabled, dtype=bool))
+        joint = np.array([int(items[i]["kpID"].rsplit("_", 1)[-1]) for i in on], dtype=np.intp)
+        whole = np.full(len(on), kps_count, dtype=np.intp)
+        counts = (np.bincount(joint, minlength=n)[:n] + np.bincount(whole, minlength=n)[:n]).tolist()
+        means = []
+        for field in ("error", "acc_flag"):
+            w = np.array([items[i][field] for i in on], dtype=np.float64)
+            tot = np.bincount(joint, weights=w, minlength=n)[:n] + np.bincount(whole, weights=w, minlength=n)[:n]
+            means.append([float(tot[k]) / counts[k] if counts[k] > 0 else 0 for k in range(n)])
+        return counts, means[0], means[1]
+
+    @classmethod
+    def _emit(cls, items, enabled, kps_count):
+        """Deep copies of `items` (the reference hands out copies) carrying their `enable` flag, plus the tallies."""
+        out = []
+        for it, e in zip(items, enabled):
+            rec = copy.deepcopy(it)
+            rec["enable"] = 1 if e else 0
+            out.append(rec)
+        return (out,) + cls._tally(items, enabled, kps_count)
+
     @classmethod
     def _collect(cls, pseudoArray, rel, en, thr, args):
-        """The selection loop shared by filter_pseudo / filter_pseudo2 (business.py:69-91,195-217)."""
-        order = sorted(range(len(pseudoArray)), key=lambda i: rel[i], reverse=True)   # stable, like sorted(..., reverse=True)
-        n = args.kpsCount + 1
-        selArray, selCounts, selErrs, selAccs = [], [0] * n, [0] * n, [0] * n
-        for i in order:
-            item = copy.deepcopy(pseudoArray[i])
-            if en[i]:
-                kID = int(item["kpID"].split("_")[-1])
-                item["enable"] = 1
-                selCounts[-1] += 1
-                selCounts[kID] += 1
-                selErrs[-1] += item["error"]
-                selErrs[kID] += item["error"]
-                selAccs[-1] += item["acc_flag"]
-                selAccs[kID] += item["acc_flag"]
-            else:
-                item["enable"] = 0
-            selArray.append(item)
-        for idx in range(n):
-            if selCounts[idx] > 0:
-                selErrs[idx] = selErrs[idx] / selCounts[idx]
-                selAccs[idx] = selAccs[idx] / selCounts[idx]
-        return selArray, selCounts, selErrs, selAccs, thr
+        """Output of filter_pseudo / filter_pseudo2: the records ordered by falling reliability (stable, like the
+        reference's sorted(..., reverse=True)), their enable flags from the device masks, the tallies, the threshold."""
+        order = sorted(range(len(pseudoArray)), key=rel.__getitem__, reverse=True)
+        return cls._emit([pseudoArray[i] for i in order], [en[i] for i in order], args.kpsCount) + (thr,)
 
     @classmethod
     def filter_pseudo2(cls, pseudoArray, args):
@@ -165,17 +174,23 @@ class BusinessUtils:
     def _pydist(c1, c2):
         return ((c1[0] - c2[0]) ** 2 + (c1[1] - c2[1]) ** 2) ** 0.5      # utils/process.py:53-54, CPython pow
 
-    @staticmethod
-    def _lma_variables(sources):
-        """utils/business.py:395-405."""
-        alphas = [0.5, 0.3, 0.2]
-        if len(sources) == 0:
+    _LMA = (0.5, 0.3, 0.2)                                                # weights of the newest, previous, oldest epoch
+
+    @classmethod
+    def _lma_variables(cls, sources):
+        """utils/business.py:395-405: moving average over the last (up to) three epochs, newest weighted most; with
+        two epochs the newest takes the first two weights; 999 before the first.  Same products and left-to-right
+        sums as the reference, so the cached values are bit-identical."""
+        recent = sources[:-4:-1]                                          # newest first
+        if not recent:
             return 999.0
-        if len(sources) == 1:
-            return sources[-1]
-        if len(sources) == 2:
-            return sources[-1] * (alphas[0] + alphas[1]) + sources[-2] * alphas[2]
-        return sources[-1] * alphas[0] + sources[-2] * alphas[1] + sources[-3] * alphas[2]
+        if len(recent) == 1:
+            return recent[0]
+        w = cls._LMA if len(recent) == 3 else (cls._LMA[0] + cls._LMA[1], cls._LMA[2])
+        acc = recent[0] * w[0]
+        for x, wk in zip(recent[1:], w[1:]):
+            acc = acc + x * wk
+        return acc
 
     @staticmethod
     def _calUncValue(mixDist):
@@ -242,28 +257,9 @@ class BusinessUtils:
 
     @classmethod
     def _mix_collect(cls, pseudoArray, uncThr, args):
-        """The selection loop of pseudo_filter_mixUnc / pseudo_filter_mixUnc2 (business.py:243-261, 271-293)."""
-        n = args.kpsCount + 1
-        selArray, selCounts, selErrs, selAccs = [], [0] * n, [0] * n, [0] * n
-        for pseudoItem in pseudoArray:
-            item = copy.deepcopy(pseudoItem)
-            if item["unc"] <= uncThr:
-                kID = int(item["kpID"].split("_")[-1])
-                item["enable"] = 1
-                selCounts[-1] += 1
-                selCounts[kID] += 1
-                selErrs[-1] += item["error"]
-                selErrs[kID] += item["error"]
-                selAccs[-1] += item["acc_flag"]
-                selAccs[kID] += item["acc_flag"]
-            else:
-                item["enable"] = 0
-            selArray.append(item)
-        for idx in range(n):
-            if selCounts[idx] > 0:
-                selErrs[idx] = selErrs[idx] / selCounts[idx]
-                selAccs[idx] = selAccs[idx] / selCounts[idx]
-        return selArray, selCounts, selErrs, selAccs
+        """Output of pseudo_filter_mixUnc / pseudo_filter_mixUnc2 (business.py:243-261, 271-293): records in their given
+        order, enabled where unc <= uncThr."""
+        return cls._emit(pseudoArray, [it["unc"] <= uncThr for it in pseudoArray], args.kpsCount)
 
     @classmethod
     def pseudo_filter_mixUnc(cls, pseudoArray, args):
@@ -275,10 +271,12 @@ class BusinessUtils:
     def pseudo_filter_mixUnc2(cls, pseudoArray, args):
         """utils/business.py:264-294: items scoring below the median score (:357-364) get unc = 999 first; the
         reference mutates its input records (scoreOK, unc), so does this."""
-        scores_sorted = sorted([item["score"] for item in pseudoArray], reverse=True)
-        scoreThr = scores_sorted[int((len(scores_sorted) - 1) * 0.5)]
-        for pseudoItem in pseudoArray:
-            pseudoItem["scoreOK"] = 0 if pseudoItem["score"] < scoreThr else 1
-            pseudoItem["unc"] = 999.0 if pseudoItem["score"] < scoreThr else pseudoItem["unc"]
+        ranked = sorted((it["score"] for it in pseudoArray), reverse=True)
+        scoreThr = ranked[int((len(ranked) - 1) * 0.5)]                   # the median score (:357-364)
+        for it in pseudoArray:
+            low = it["score"] < scoreThr
+            it["scoreOK"] = 0 if low else 1
+            if low:
+                it["unc"] = 999.0
         uncThr = cls._calUncValue(args.distThrMax * 3)
         return cls._mix_collect(pseudoArray, uncThr, args) + (scoreThr, uncThr)

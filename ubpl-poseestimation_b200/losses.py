@@ -214,14 +214,79 @@ class _GroupedLossFn(torch.autograd.Function):
         return g_pred, g_tgt, None, None, None
 
 
+class _GroupedPseudoFn(torch.autograd.Function):
+    """JointPseudoLoss3 over G groups at once: per-group masked loss sums [G] of a [G*B,S,J,H,W] prediction batch
+    against the mean of the Mt teacher maps [Mt,G*B,J,H,W] (last stack), score masks and gradient in the same pass."""
+
+    @staticmethod
+    def forward(ctx, pred5, tgt, coef, thr, G):
+        need_grad = ctx.needs_input_grad[0]
+        r = ops.dense_mse(pred5.detach(), tgt.detach(), coef=coef, mask_mode=1, thr=thr, want_grad=need_grad, want_scores=True)
+        GB, S, J = r["per_loss"].shape
+        B = GB // G
+        pl, mk = r["per_loss"].view(G, B, S, J), r["mask"].view(G, B, S, J)
+        fins = torch.stack([ops.loss_finalize(pl[g], mk[g], None) for g in range(G)])
+        ctx.grad, ctx.G = r["grad"], G
+        ctx.mark_non_differentiable(fins, r["vmax_p"], r["vmax_t"])
+        return fins[:, 0].to(torch.float32), fins, r["vmax_p"], r["vmax_t"]
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        g = ctx.grad
+        if g is None:
+            return None, None, None, None, None
+        G = ctx.G
+        gv = g.view((G, g.shape[0] // G) + tuple(g.shape[1:]))
+        out = torch.empty_like(gv)
+        scales = g_loss.detach().to(torch.float32).contiguous()
+        for k in range(G):                                   # one tiny scale launch per group, no host sync
+            ops.scale(gv[k], scales[k:k + 1], out=out[k])
+        return out.view(g.shape), None, None, None, None
+
+
+def _grouped_pseudo(criterion, preds, targets, sampleWeight):
+    """All G calls `JointPseudoLoss3(preds[g], targets[:, g], sampleWeight)` (utils/losses.py:169-210; the epc loop of
+    projects/MT_UBPL.py:270-298 makes M * K of them per step, each with O(B*J*S) host syncs in the reference) in ONE
+    loss+gradient kernel and ONE device->host sync.  preds [G,B,(S,)J,H,W]; targets [Mt,G,B,(S,)J,H,W] -- the teacher
+    stacks each group is compared with, treated as constants like the drivers' `.clone().detach()`; sampleWeight [B,1]
+    (the same for every group).  Returns (sums [G] with autograd, num_pseudo list, num_selected list,
+    joint_score_mean [G,J], scoreThr, scoreThr)."""
+    nS = criterion.nStack
+    G, B = preds.shape[0], preds.shape[1]
+    p5 = _as5(preds.reshape((G * B,) + tuple(preds.shape[2:])), nS)
+    S, J = p5.shape[1], p5.shape[2]
+    t = targets.detach()
+    t = t if nS == 1 else t[:, :, :, -1]                          # [Mt,G,B,J,H,W]: the last stack, losses.py:179
+    Mt = t.shape[0]
+    if t.stride(1) == B * t.stride(2):
+        t = t.as_strided((Mt, G * B) + tuple(t.shape[3:]), (t.stride(0), t.stride(2)) + tuple(t.stride()[3:]))
+    else:
+        t = t.reshape((Mt, G * B) + tuple(t.shape[3:]))
+    w = sampleWeight.detach().to(device=p5.device, dtype=torch.float32).reshape(B)
+    coef = w.reshape(1, B, 1).expand(G, B, J).reshape(G * B, J).contiguous()
+    sums, fins, vp, vt = _GroupedPseudoFn.apply(p5, t, coef, float(criterion.scoreThr), G)
+    rows = (w > 0).to(torch.float32)
+    cnt = rows.sum()
+    host = torch.cat([fins.reshape(-1), cnt.reshape(1).double()]).tolist()      # the one device->host sync
+    if host[-1] == 0:
+        raise RuntimeError("stack expects a non-empty TensorList")              # losses.py:201 on an all-labeled batch
+    vp, vt = vp.view(G, B, S, J), vt.view(G, B, S, J)
+    jsm = torch.stack([((_score_mean(vp[g], rows, cnt) + _score_mean(vt[g], rows, cnt)) / 2).mean(0) for g in range(G)])
+    n_pseudo = [int(host[4 * g + 1]) for g in range(G)]
+    n_sel = [int(host[4 * g + 2]) for g in range(G)]
+    return sums, n_pseudo, n_sel, jsm, criterion.scoreThr, criterion.scoreThr
+
+
 def grouped(criterion, preds, targets, kpsGate=None, sampleWeight=None):
     """All G calls `criterion(preds[g], targets[g], kpsGate[g], sampleWeight)` of a JointMSELoss / JointDistLoss
-    (utils/losses.py:8-53) at once.  preds [G,B,(S,)J,H,W]; targets [G,B,J,H,W] (JointMSELoss: one target per
+    (utils/losses.py:8-53) at once; a JointPseudoLoss3 goes to _grouped_pseudo (its targets are [Mt,G,B,...]).  preds [G,B,(S,)J,H,W]; targets [G,B,J,H,W] (JointMSELoss: one target per
     sample, shared by the stacks) or [G,B,(S,)J,H,W] (JointDistLoss); kpsGate [G,B,J] or None; sampleWeight [B,1]
     (the same for every group, as in the drivers).  Returns (sums [G] float32 with autograd, counts: list of G
     python ints) -- the tuples the G separate calls would have returned, with one kernel and one sync."""
+    if isinstance(criterion, JointPseudoLoss3):
+        return _grouped_pseudo(criterion, preds, targets, sampleWeight)
     if not isinstance(criterion, (JointMSELoss, JointDistLoss)):
-        raise TypeError("grouped() batches JointMSELoss / JointDistLoss calls")
+        raise TypeError("grouped() batches JointMSELoss / JointDistLoss / JointPseudoLoss3 calls")
     nS = criterion.nStack
     G, B = preds.shape[0], preds.shape[1]
     p5 = preds.reshape((G * B,) + tuple(preds.shape[2:]))

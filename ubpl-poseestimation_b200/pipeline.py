@@ -376,3 +376,64 @@ class GraphedStep:
         if not self.events:
             return None
         return {n: (self.events[n][0].elapsed_time(self.events[n][1]) if n in self.events else 0.0) for n in self.stage_names}
+
+
+def stream_chunks(host, dec, sample_w, cfg: StepConfig, chunk, group=None, ema=None, alpha=None, on_chunk=None):
+    """A batch that does not fit one GPU (BASELINE config 5: B = 4096, K = 16, J = 32, 128x128 is 180 GB of maps) streamed
+    through the chain in chunks of `chunk` samples: two device buffer sets, each with its own captured step, so that the
+    host->device copy of chunk i+1 (copy stream, pinned host memory) overlaps the chain of chunk i (compute stream).
+    host: dict of PINNED CPU tensors teacher [M,K,B,J,H,W], student [B,S,J,H,W], theta [K,B,2,3], flip [K,B] (uint8);
+    dec [B,4] float64 and sample_w [B] may live on the device already (tiny).  The global-quantile selection is per
+    chunk (a chunk is the selector's population).  Returns a list with, per chunk, the float64[4] loss summary,
+    grad_scale and the open-gate count (device tensors, cloned); on_chunk(i, state) -- if given -- is called on the
+    compute stream after chunk i's step, before its buffers are reused (copy the gradient out there).  The EMA
+    (`ema`, an ops.EmaPlan) runs once, with the last chunk."""
+    B = host["student"].shape[0]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    starts = list(range(0, B, chunk))
+    if B % chunk:
+        raise ValueError("stream_chunks: the batch (%d) must be a multiple of the chunk (%d)" % (B, chunk))
+    copy_s = torch.cuda.Stream()
+    comp = torch.cuda.current_stream()
+    sets, steps, filled, freed = [], [], [], []
+    dec = dec.to(dev)
+    sample_w = sample_w.to(dev)
+    for s in range(2):
+        b0 = starts[min(s, len(starts) - 1)]
+        bufs = dict(teacher=host["teacher"][:, :, b0:b0 + chunk].to(dev), student=host["student"][b0:b0 + chunk].to(dev),
+                    theta=host["theta"][:, b0:b0 + chunk].to(dev), flip=host["flip"][:, b0:b0 + chunk].to(dev).to(torch.uint8),
+                    dec=dec[b0:b0 + chunk].clone(), w=sample_w[b0:b0 + chunk].clone())
+        sets.append(bufs)
+        steps.append(GraphedStep(bufs["teacher"], bufs["student"], bufs["theta"], bufs["flip"], bufs["dec"], bufs["w"], cfg,
+                                 group=group, ema=None, instrument=False))
+        filled.append(torch.cuda.Event())
+        freed.append(torch.cuda.Event())
+        freed[s].record(comp)
+
+    def upload(i):
+        s, b0 = i % 2, starts[i]
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(freed[s])                       # the step that read this set has finished
+            sets[s]["teacher"].copy_(host["teacher"][:, :, b0:b0 + chunk], non_blocking=True)
+            sets[s]["student"].copy_(host["student"][b0:b0 + chunk], non_blocking=True)
+            sets[s]["theta"].copy_(host["theta"][:, b0:b0 + chunk], non_blocking=True)
+            sets[s]["flip"].copy_(host["flip"][:, b0:b0 + chunk], non_blocking=True)
+            sets[s]["dec"].copy_(dec[b0:b0 + chunk], non_blocking=True)
+            sets[s]["w"].copy_(sample_w[b0:b0 + chunk], non_blocking=True)
+            filled[s].record(copy_s)
+
+    out = []
+    upload(0)
+    for i in range(len(starts)):
+        s = i % 2
+        if i + 1 < len(starts):
+            upload(i + 1)                                     # overlaps the chain of chunk i
+        comp.wait_event(filled[s])
+        st = steps[s].run()
+        if ema is not None and i == len(starts) - 1:
+            ema.step(alpha)
+        if on_chunk is not None:
+            on_chunk(i, st)
+        out.append(dict(summary=st["summary"].clone(), grad_scale=st["grad_scale"].clone(), count=st["count"].clone()))
+        freed[s].record(comp)
+    return out
