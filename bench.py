@@ -33,8 +33,9 @@ CONFIGS = {
                desc="DualPose_UBPL FLIC J=9 B=1024/8 per GPU K=8 dual teachers"),
     "c4": dict(B=256, K=16, M=1, S=2, J=17, H=64, W=64, select="quantile", hg="hg2_j17",
                desc="AP-10K J=17 B=2048/8 per GPU K=16 global-quantile threshold (NCCL histogram all-reduce)"),
-    "c5": dict(B=32, K=16, M=1, S=2, J=32, H=128, W=128, select="fixed", hg="hg2_j32",
-               desc="fly J=32 128x128 K=16 bandwidth stress, chunk of 32 samples per step"),
+    "c5": dict(B=256, K=16, M=1, S=2, J=32, H=128, W=128, select="fixed", hg="hg2_j32",
+               desc="fly J=32 128x128 K=16 bandwidth stress, one resident chunk of 256 of the 4096 samples per step "
+                    "(9.6 GB; pipeline.stream_chunks streams the rest)"),
 }
 DIST_THR_MAX = 3.0          # no reference default exists; ~half of the joints pass on the synthetic data
 METRIC = "pseudo-labelled samples/sec"

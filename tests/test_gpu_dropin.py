@@ -168,6 +168,11 @@ def test_business(pkg):
     assert [it["enable"] for it in sel] == [it["enable"] for it in g["fp_sel"]]
     assert [it["reliability"] for it in sel] == [it["reliability"] for it in g["fp_sel"]]
     assert [it["dist"] for it in sel] == [it["dist"] for it in g["fp_sel"]]
+    np.testing.assert_allclose(errs, g["fp_errs"], rtol=1e-12) if "fp_errs" in g else None
+    # the two teachers agree everywhere: dist_max == dist_min == 0, the reference divides by zero (business.py:63)
+    same = [copy.deepcopy(ori_a[0]), copy.deepcopy(ori_a[0]), copy.deepcopy(ori_a[2])]
+    with pytest.raises(ZeroDivisionError):
+        pkg.bus.filter_pseudo(same, args)
 
 
 def test_update_ema_variables(pkg):

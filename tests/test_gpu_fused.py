@@ -406,3 +406,27 @@ def test_stream_chunks_matches_per_chunk_steps(ops):
         assert torch.equal(out[i]["summary"], ref["summary"]), i
         assert torch.equal(out[i]["grad_scale"], ref["grad_scale"]) and int(out[i]["count"]) == int(ref["count"])
         assert torch.equal(grads[i], ref["grad"]), i
+
+
+def test_step_is_repeatable_under_load(ops):
+    """Race check by repetition (compute-sanitizer is closed on this pool, profiles/README.md): the c2-size step -- dynamic
+    claims, the copy cap, the cooperative exhaustive decode, the fence-free K2 hand-off, the loss reduction in K3's last
+    CTA -- replayed 25 times gives bit-identical outputs every time, and the device status word stays clear."""
+    from ubpl_b200 import synth, pipeline
+    B, K, J = 256, 8, 14
+    d = synth.make_batch(B=B, K=K, J=J, M=1, S=2, seed=1388, device="cuda", noise_only_frac=1.0)
+    dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64])
+    w = pipeline.nega_weights(d["islabeled"], 1.0)
+    cfg = pipeline.StepConfig(select="fixed", distThrMax=3.0)
+    g = pipeline.GraphedStep(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, instrument=False)
+    keys = ("idx", "max", "xy", "kps", "dist", "enable", "gate", "grad", "target", "summary", "count")
+    first = None
+    for it in range(25):
+        st = g.run()
+        snap = {k: st[k].clone() for k in keys}
+        if first is None:
+            first = snap
+        else:
+            for k in keys:
+                assert torch.equal(first[k], snap[k]), (it, k)
+    g.check()

@@ -108,9 +108,18 @@ class BusinessUtils:
         legal = torch.tensor([1.0 if (a["coord_legal"] and b["coord_legal"]) else 0.0
                               for a, b in zip(predsArray_mds1, predsArray_mds2)], dtype=torch.float64).cuda()
         dist = ops.pair_distance(c1, c2)
-        # same kernels as filter_pseudo2: identical arithmetic as long as no distance equals the 999 sentinel
+        dl = dist.cpu().tolist()
+        # The selector kernel is filter_pseudo2's: it treats 999 as "no distance" and replaces an all-zero maximum by
+        # 999 (business.py:176-182).  filter_pseudo normalises with the plain np.max / np.min (:59-60), so the two agree
+        # unless a distance reaches 999 (impossible between coordinates of a 256-pixel frame) or all distances are
+        # equal, where the reference divides by zero (:63) -- both are refused here instead of being answered differently.
+        if max(dl) >= 999.0:
+            raise ValueError("filter_pseudo: a teacher-to-teacher distance of %g pixels (>= 999, the sentinel of "
+                             "filter_pseudo2's kernel) cannot be ranked like utils/business.py:59-63 does" % max(dl))
+        if max(dl) == min(min(dl), args.reliableDistMin) and any(bool(v) for v in legal.cpu().tolist()):
+            raise ZeroDivisionError("float division by zero")            # (dist-dist_min)/(dist_max-dist_min), business.py:63
         s = ops.select_quantile(dist, legal, args.kpsCount, args.reliableThr, args.reliablePCT, args.reliableDistMin)
-        dl, rel, en = dist.cpu().tolist(), s["reliability"].cpu().tolist(), s["enable"].cpu().tolist()
+        rel, en = s["reliability"].cpu().tolist(), s["enable"].cpu().tolist()
         thr = float(s["thr"].item())
         for i, p in enumerate(pseudoArray):
             p["dist"] = dl[i]

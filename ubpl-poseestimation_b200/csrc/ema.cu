@@ -7,6 +7,7 @@
 // (tensor, offset) work items; 12 bytes of HBM traffic per parameter, 128-bit accesses where the
 // chunk is 16-byte aligned.  Rounding follows ATen: t = ema*alpha (rounded), fma(param, 1-alpha, t).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ubpl {
 
@@ -89,7 +90,11 @@ extern "C" int ubpl_ema_multi_tensor(const uint64_t* ema_ptrs, const uint64_t* p
   UBPL_REQUIRE(ema_ptrs && param_ptrs && numels && chunk_tensor && chunk_start, "ubpl_ema_multi_tensor: NULL pointer");
   UBPL_REQUIRE(n_chunks >= 0 && chunk_elems > 0 && chunk_elems % 4 == 0, "ubpl_ema_multi_tensor: bad chunking");
   if (n_chunks == 0) return UBPL_OK;
-  const long long cap = (long long)sm_count() * 8;
+  // resident CTAs per SM: 8 by default; UBPL_EMA_CTAS lowers it (the update usually runs beside K1, where fewer,
+  // longer streams disturb the staged copies less)
+  const char* ev = getenv("UBPL_EMA_CTAS");
+  const int per_sm = (ev && atoi(ev) > 0) ? atoi(ev) : 8;
+  const long long cap = (long long)sm_count() * per_sm;
   const int grid = (int)(n_chunks < cap ? n_chunks : cap);
   ema_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ema_ptrs, param_ptrs, reinterpret_cast<const long long*>(numels),
                                                            chunk_tensor, reinterpret_cast<const long long*>(chunk_start),

@@ -13,6 +13,7 @@
 // float64 for the rare pixel within 1e-5 of it so the support is identical to the reference's.
 #include "common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 // resident CTAs per SM the streaming kernel is compiled for: 6 (80 registers, spills) or 5 (102 registers)
 #ifndef UBPL_K3_OCC_DEFAULT
@@ -98,6 +99,10 @@ __global__ void __launch_bounds__(128, OCC) render_mse_kernel(
     int all_coop) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  // Programmatic dependent launch: when the kernel is launched with programmatic stream serialization its CTAs are
+  // scheduled as soon as the SMs of the preceding kernel (K1 or the selector) free up, and wait HERE until that
+  // kernel has completed and its results (key points, gates, count) are visible; a no-op for a plain launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   float* ex = sm + (size_t)warp * (W + H);   // [W]
   float* ey = ex + W;                        // [H]
   const int HW = H * W, nq = (HW + 3) >> 2;
@@ -620,12 +625,21 @@ static int render_mse_impl(const float* kps, const float* gate_in, const float* 
   // every item instead of one, which matters when the maps are large and the items few (fly: 128x128, B*J = 1024)
   (void)need;
   const int grid = (int)(BJ < cap ? BJ : cap);
+  // launched with programmatic stream serialization (UBPL_K3_PDL=0 switches it off): see griddepcontrol.wait in the kernel
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3((unsigned)(wpb * 32)); lc.dynamicSmemBytes = smem; lc.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  lattr[0].val.programmaticStreamSerializationAllowed = 1;
+  const bool pdl = getenv("UBPL_K3_PDL") ? atoi(getenv("UBPL_K3_PDL")) != 0 : true;
+  lc.attrs = lattr; lc.numAttrs = pdl ? 1 : 0;
 #define UBPL_LAUNCH_RENDER(V, SSV)                                                                                     \
-  if (occ5) render_mse_kernel<V, SSV, 5><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(                              \
-      kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS, gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
+  if (occ5) cudaLaunchKernelEx(&lc, render_mse_kernel<V, SSV, 5>,                                                      \
+      kps, gate_in, sample_w, pred, (long long)pB, (long long)pS, (long long)pJ, grad, (long long)gB, (long long)gS, (long long)gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
       grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, sum_ws, all_coop);       \
-  else render_mse_kernel<V, SSV, 6><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(                                   \
-      kps, gate_in, sample_w, pred, pB, pS, pJ, grad, gB, gS, gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
+  else cudaLaunchKernelEx(&lc, render_mse_kernel<V, SSV, 6>,                                                           \
+      kps, gate_in, sample_w, pred, (long long)pB, (long long)pS, (long long)pJ, grad, (long long)gB, (long long)gS, (long long)gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
       grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, sum_ws, all_coop)
   if (vec) {
     if (S % 2 == 0) UBPL_LAUNCH_RENDER(true, 2); else UBPL_LAUNCH_RENDER(true, 1);

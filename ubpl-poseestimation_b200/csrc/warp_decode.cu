@@ -1041,7 +1041,7 @@ __global__ void __launch_bounds__(256) warp_materialize_kernel(const float* __re
                                                                int N, int C, int H, int W,
                                                                const float* __restrict__ theta,
                                                                const uint8_t* __restrict__ flip,
-                                                               const int32_t* __restrict__ swap_perm) {
+                                                               const int32_t* __restrict__ swap_perm, int vec) {
   extern __shared__ __align__(16) float sm[];
   const int HW = H * W;
   for (long long m = blockIdx.x; m < (long long)N * C; m += gridDim.x) {
@@ -1051,14 +1051,34 @@ __global__ void __launch_bounds__(256) warp_materialize_kernel(const float* __re
     const float* src = in + n * sN + (long long)cs * sC;
     float* dst = out + n * oN + (long long)c * oC;
     __syncthreads();
-    for (int k = threadIdx.x; k < HW; k += blockDim.x) sm[k] = __ldg(src + k);
+    if (vec) {                                               // 128-bit streaming loads of the source map
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      for (int q = threadIdx.x; q < (HW >> 2); q += blockDim.x) reinterpret_cast<float4*>(sm)[q] = ldg_stream(s4 + q);
+    } else {
+      for (int k = threadIdx.x; k < HW; k += blockDim.x) sm[k] = __ldg(src + k);
+    }
     __syncthreads();
     Xform X;
     load_xform(X, theta, flip, n, H, W);
     grid_consts(X, H, W);
-    for (int k = threadIdx.x; k < HW; k += blockDim.x) {
-      const int i = k / W, jo = k - i * W;
-      dst[k] = eval_px(sm, X, i, X.flip ? (W - 1 - jo) : jo);
+    if (vec) {
+      // four consecutive output pixels of a row per thread (the row term of the grid is shared), one 128-bit store
+      const int w4 = W >> 2;
+      for (int q = threadIdx.x; q < (HW >> 2); q += blockDim.x) {
+        const int i = q / w4, jo = (q - i * w4) << 2;
+        const float yl = lin_coord(i, H, X.stepy);
+        float4 o;
+        o.x = eval_at(sm, X, lin_coord(X.flip ? (W - 1 - jo) : jo, W, X.stepx), yl);
+        o.y = eval_at(sm, X, lin_coord(X.flip ? (W - 2 - jo) : jo + 1, W, X.stepx), yl);
+        o.z = eval_at(sm, X, lin_coord(X.flip ? (W - 3 - jo) : jo + 2, W, X.stepx), yl);
+        o.w = eval_at(sm, X, lin_coord(X.flip ? (W - 4 - jo) : jo + 3, W, X.stepx), yl);
+        stg_stream(reinterpret_cast<float4*>(dst) + q, o);
+      }
+    } else {
+      for (int k = threadIdx.x; k < HW; k += blockDim.x) {
+        const int i = k / W, jo = k - i * W;
+        dst[k] = eval_px(sm, X, i, X.flip ? (W - 1 - jo) : jo);
+      }
     }
   }
 }
@@ -1238,8 +1258,10 @@ extern "C" int ubpl_warp_materialize(const float* in, int64_t sN, int64_t sC, fl
   }
   long long maps = (long long)N * C;
   int grid = (int)(maps < (long long)sm_count() * 8 ? maps : (long long)sm_count() * 8);
+  const int vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                  sN % 4 == 0 && sC % 4 == 0 && oN % 4 == 0 && oC % 4 == 0;
   warp_materialize_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, sN, sC, out, oN, oC, N, C, H, W, theta, flip,
-                                                                      flip ? swap_perm : nullptr);
+                                                                      flip ? swap_perm : nullptr, vec);
   return check_launch("ubpl_warp_materialize");
 }
 

@@ -598,15 +598,32 @@ _sum_ws = {}
 _SUM_WS_WORDS = (16 + 24 * 4096) // 4 + 12          # UBPL_RENDER_SUM_WS_BYTES, padded to a multiple of 64 B
 
 
+_GRAPH_WS_POOL = 16
+
+
 def _sum_workspace(dev):
     """A zero-initialised workspace for kernels that elect their last CTA (the kernel returns its ticket word to
-    zero).  8 slots per device, handed out round-robin so that launches on different streams rarely share one."""
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
-    ring = _sum_ws.get(key)
-    if ring is None:
-        ring = _sum_ws[key] = [torch.zeros(8, _SUM_WS_WORDS, dtype=torch.int32, device=dev), 0]
-    ring[1] = (ring[1] + 1) % 8
-    return ring[0][ring[1]]
+    zero, so a buffer can serve any number of launches that do not overlap in time).  Eager launches use ONE buffer
+    per (device, stream): launches on a stream are ordered, so they never share a live ticket.  A launch that is being
+    captured into a CUDA graph takes a buffer of its own from a pool zeroed beforehand -- the graph keeps replaying
+    with it while eager calls and other graphs never touch it (when the pool is empty the buffer is zeroed inside the
+    capture, one extra memset node)."""
+    didx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (dev.type, didx)
+    st = _sum_ws.get(key)
+    if st is None:
+        st = _sum_ws[key] = {"streams": {}, "pool": []}
+    if torch.cuda.is_current_stream_capturing():
+        if st["pool"]:
+            return st["pool"].pop()
+        return torch.zeros(_SUM_WS_WORDS, dtype=torch.int32, device=dev)
+    if not st["pool"]:
+        st["pool"] = list(torch.zeros(_GRAPH_WS_POOL, _SUM_WS_WORDS, dtype=torch.int32, device=dev).unbind(0))
+    sid = torch.cuda.current_stream(didx).cuda_stream
+    ws = st["streams"].get(sid)
+    if ws is None:
+        ws = st["streams"][sid] = torch.zeros(_SUM_WS_WORDS, dtype=torch.int32, device=dev)
+    return ws
 
 
 def render_mse(kps, gate, sample_w, pred, img_h, img_w, stride=None, sigma=3.0, grad_scale=None,

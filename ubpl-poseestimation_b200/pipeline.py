@@ -11,6 +11,7 @@ filter_pseudo2 (global quantile) or the fixed rule of pseudo_filter_mixUnc -> Da
 (coords + enable) -> kps_heatmap -> JointMSELoss(useKPsGate, useSampleWeight) with the
 `getSampleWeight_nega` weights (unlabeled rows get pseudoWeight) -> weight * sum / n
 (MT_UBPL.py:266) and its gradient."""
+import os
 from dataclasses import dataclass
 
 import torch
@@ -237,14 +238,27 @@ class GraphedStep:
         if ema is not None:
             ema.set_alpha(alpha)                          # the captured EMA launch reads alpha from device memory
 
+        self._join_late = mode == "single" and os.environ.get("UBPL_EMA_JOIN", "late") == "late"
+        self._pending_join = False
+
         def forked(fn):
             # K4 is independent of the chain: fork it onto a side stream inside the same graph so that it runs
-            # concurrently with the stage (K1 is not bandwidth-saturated on its own)
+            # concurrently with the stage (K1 is not bandwidth-saturated on its own).  In the single-graph step the side
+            # stream joins at the END of the step (nothing in the chain reads the teacher weights), so the next stage
+            # follows its predecessor kernel directly -- which is what lets K3 start with programmatic dependent launch
             self._side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._side):
                 self._ema()
             fn()
-            torch.cuda.current_stream().wait_stream(self._side)
+            if self._join_late:
+                self._pending_join = True
+            else:
+                torch.cuda.current_stream().wait_stream(self._side)
+
+        def join():
+            if self._pending_join:
+                torch.cuda.current_stream().wait_stream(self._side)
+                self._pending_join = False
 
         def k1_fn():
             if self.overlap_ema == "k1":
@@ -297,6 +311,7 @@ class GraphedStep:
                     for name, fns in segs:
                         for fn in fns:
                             fn()
+                    join()
                 self.graphs["step"] = g
                 self.order = ["step"]
                 self.stage_names = [n for n, _ in stages]
@@ -308,6 +323,8 @@ class GraphedStep:
                     for i, (name, fns) in enumerate(segs):
                         for fn in fns:
                             fn()
+                        if i == len(segs) - 1:
+                            join()                        # the EMA's tail (if any) is charged to the last stage
                         ev[i + 1].record()
                 self.graphs["step"] = g
                 self.events = {name: (ev[i], ev[i + 1]) for i, (name, _) in enumerate(segs)}
