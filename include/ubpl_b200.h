@@ -101,6 +101,22 @@ int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
                         int64_t* stats, int32_t* ws, int64_t ws_bytes, const void* prefetch, int64_t prefetch_bytes,
                         void* stream);
 
+/* K1 + K2 epilogue as above, with K4 inside: the warps that have run out of maps do the mean-teacher EMA of
+ * ubpl_ema_multi_tensor (same tables, same arithmetic, update_ema_variables utils/parameters.py:4-8) chunk by chunk
+ * while the last maps are decoded -- K1's launch ends with ~2 map times in which HBM is no longer saturated by the
+ * staged copies, and the EMA depends on nothing in the chain.  A separate EMA kernel cannot run beside K1 (K1's CTAs
+ * hold all of an SM's shared memory), so this is the only way to overlap the two.  n_chunks = 0: no EMA. */
+int ubpl_warp_decode_k2_ema(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
+                        int V, int B, int J, int H, int W,
+                        const float* theta, const uint8_t* flip, const int32_t* swap_perm, const double* dec,
+                        int refine, int32_t* out_idx, float* out_max, float* out_xy,
+                        int k2_mode, double distThrMax, int img_h, int img_w, float stride, float sigma, int S,
+                        float* mean, double* dist, uint8_t* legal, uint8_t* enable, float* gate,
+                        int64_t* stats, int32_t* ws, int64_t ws_bytes, const void* prefetch, int64_t prefetch_bytes,
+                        const uint64_t* ema_ptrs, const uint64_t* param_ptrs, const int64_t* numels,
+                            const int32_t* chunk_tensor, const int64_t* chunk_start, int64_t n_chunks, int chunk_elems,
+                            float alpha, float one_minus_alpha, const float* alpha_dev, void* stream);
+
 /* Materialises the back-warped (and un-flipped) maps: the tensor AugmentUtils.affine_back2
  * returns (utils/augment.py:37-47).  in [N, C, H, W] strides (sN, sC); out likewise (oN, oC);
  * theta [N,2,3]; flip [N] uint8 or NULL; swap_perm int32[C] or NULL: output channel c of a flipped sample

@@ -430,3 +430,72 @@ def test_step_is_repeatable_under_load(ops):
             for k in keys:
                 assert torch.equal(first[k], snap[k]), (it, k)
     g.check()
+
+
+@pytest.mark.parametrize("B,K,J", [(8, 4, 6), (64, 8, 14), (0, 4, 6)])
+def test_k1_with_ema_in_its_tail(ops, B, K, J):
+    """ubpl_warp_decode_k2_ema: the warps that run out of maps do the mean-teacher EMA (utils/parameters.py:4-8).
+    K1 / K2 outputs identical to the launch without it; every parameter updated exactly once, bit-identical to the
+    oracle's update -- also for tensors smaller than a chunk, of odd length and at unaligned offsets."""
+    from ubpl_b200 import synth
+    rng = np.random.default_rng(5)
+    sizes = [1, 3, 4, 7, 33 * 17, 8192, 8193, 3 * 8192 + 5, 70000]
+    base = torch.randn(sum(sizes) + 64, device="cuda")
+    params, emas, off = [], [], 1                        # off = 1: the first tensors are not 16-byte aligned
+    for n in sizes:
+        params.append(base[off:off + n])
+        emas.append(cu(rng.standard_normal(n).astype(np.float32)))
+        off += n
+    plan = ops.EmaPlan(params, emas)
+    alpha = O.ema_alpha(3, 0.999)
+    want = [O.ema_update(npy(e), npy(p), alpha) for e, p in zip(emas, params)]
+    if B == 0:
+        t = torch.zeros(K, 0, J, 64, 64, device="cuda")
+        th = torch.zeros(K, 0, 2, 3, device="cuda"); fl = torch.zeros(K, 0, dtype=torch.uint8, device="cuda")
+        dec = torch.zeros(0, 4, dtype=torch.float64, device="cuda")
+        ops.warp_decode_k2(t, th, fl, dec, 2, S=2, distThrMax=2.0, ema=plan, alpha=alpha)
+    else:
+        d = synth.make_batch(B=B, K=K, J=J, M=1, S=2, seed=31, jitter=0.5, device="cuda")
+        dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64])
+        a = ops.warp_decode_k2(d["teacher"][0], d["theta"], d["flip"], dec, 2, S=2, distThrMax=2.0)
+        b = ops.warp_decode_k2(d["teacher"][0], d["theta"], d["flip"], dec, 2, S=2, distThrMax=2.0, ema=plan, alpha=alpha,
+                               prefetch=d["student"])
+        ops.check_status(b["status"])
+        for k in ("idx", "max", "xy", "mean", "dist", "legal", "enable", "gate", "counts", "count"):
+            assert torch.equal(a[k], b[k]), k
+    torch.cuda.synchronize()
+    for i, (e, w) in enumerate(zip(emas, want)):
+        assert np.array_equal(npy(e), w), (i, sizes[i])
+    # alpha from the plan's device buffer (what a captured graph uses), second update on top of the first
+    plan.set_alpha(0.25)
+    want2 = [O.ema_update(w, npy(p), 0.25) for w, p in zip(want, params)]
+    if B > 0:
+        ops.warp_decode_k2(d["teacher"][0], d["theta"], d["flip"], dec, 1, ema=plan, alpha=0.9, alpha_from_device=True)
+        torch.cuda.synchronize()
+        for i, (e, w) in enumerate(zip(emas, want2)):
+            assert np.array_equal(npy(e), w), (i, sizes[i])
+
+
+def test_graphed_step_with_ema_in_k1_tail(ops):
+    """overlap_ema="tail": the step's EMA rides in K1's launch; same outputs as the eager chain, EMA applied once per replay
+    with the alpha of set_alpha()."""
+    from ubpl_b200 import synth, pipeline
+    d = synth.make_batch(B=16, K=4, J=6, M=1, S=2, seed=15, jitter=0.5, device="cuda")
+    dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64])
+    w = pipeline.nega_weights(d["islabeled"], 1.0)
+    for select in ("fixed", "quantile"):
+        cfg = pipeline.StepConfig(select=select, distThrMax=2.0)
+        e = torch.randn(50000, device="cuda"); p = torch.randn(50000, device="cuda")
+        g = pipeline.GraphedStep(d["teacher"].clone(), d["student"].clone(), d["theta"].clone(), d["flip"].clone(), dec, w, cfg,
+                                 ema=ops.EmaPlan([p], [e]), alpha=0.5, overlap_ema="tail")
+        assert g.overlap_ema == "tail"
+        ref = pipeline.pseudo_label_step(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg)
+        for alpha in (0.5, 0.9):
+            g.set_alpha(alpha)
+            before = npy(e).copy()
+            st = g.run()
+            torch.cuda.synchronize()
+            g.check()
+            for k in ("idx", "max", "xy", "enable", "gate", "grad", "target", "summary", "grad_scale", "count"):
+                assert torch.equal(st[k].reshape(-1), ref[k].reshape(-1)), (select, k)
+            assert np.array_equal(npy(e), O.ema_update(before, npy(p), alpha)), (select, alpha)

@@ -25,12 +25,15 @@ kps = (d["base_xy"] * 4 + 1).contiguous()
 gate = (torch.rand(B, J, device="cuda") < 0.6).float()
 w = torch.where(d["islabeled"], 0.0, 1.0).float()
 other = torch.empty(64 * 1024 * 1024, device="cuda")        # 256 MB: flush L2 between runs
-VARIANTS = [(5, 0, 0), (5, 1, 0), (5, 1, 4), (5, 1, 3), (5, 1, 2), (5, 0, 4), (5, 0, 3), (5, 0, 2), (6, 0, 0), (6, 1, 0)]
+# (generic kernel's occupancy, item shared by a CTA, CTAs per SM override, lean kernel: 0 off / 4, 5, 6 = its occupancy)
+VARIANTS = [(5, 1, 0, 0), (5, 1, 0, 5), (5, 1, 0, 4), (5, 1, 0, 6), (5, 1, 4, 5), (5, 1, 6, 5), (5, 1, 5, 4)]
 for summ in ((False,) if old else (True,)):
-    for occ, coop, ctas in ([(6, 0, 0)] if old else VARIANTS):
+    for occ, coop, ctas, fast in ([(6, 0, 0, 0)] if old else VARIANTS):
         os.environ["UBPL_K3_OCC"] = str(occ)
         os.environ["UBPL_K3_COOP"] = str(coop)
         os.environ["UBPL_K3_CTAS"] = str(ctas)
+        os.environ["UBPL_K3_FAST"] = "1" if fast else "0"
+        os.environ["UBPL_K3_FAST_OCC"] = str(fast or 5)
         for it in range(3):
             r = ops.render_mse(kps, gate, w, d["student"], 256, 256, want_summary=summ)
         g = torch.cuda.CUDAGraph()
@@ -50,6 +53,6 @@ for summ in ((False,) if old else (True,)):
         e1.record(); torch.cuda.synchronize()
         ts.sort()
         nbytes = 4 * 4096 * J * B * 5
-        print("lib=%s summary=%s occ=%d coop=%d ctas/SM=%d: median %.1f us (%.0f GB/s), back-to-back %.1f us (%.0f GB/s)"
-              % ("old" if old else "new", summ, occ, coop, ctas, ts[10] * 1e3, nbytes / ts[10] / 1e6, e0.elapsed_time(e1) / 50 * 1e3,
+        print("lib=%s summary=%s occ=%d coop=%d ctas/SM=%d lean=%d: median %.1f us (%.0f GB/s), back-to-back %.1f us (%.0f GB/s)"
+              % ("old" if old else "new", summ, occ, coop, ctas, fast, ts[10] * 1e3, nbytes / ts[10] / 1e6, e0.elapsed_time(e1) / 50 * 1e3,
                  nbytes / (e0.elapsed_time(e1) / 50) / 1e6), flush=True)

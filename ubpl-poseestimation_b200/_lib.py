@@ -26,6 +26,14 @@ SIGNATURES = {
                             c_int, c_double, c_int, c_int, c_float, c_float, c_int,
                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p],
+    "ubpl_warp_decode_k2_ema": [c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                c_void_p, c_void_p, c_void_p,
+                                c_int, c_double, c_int, c_int, c_float, c_float, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_i64, c_void_p, c_i64,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_float, c_void_p,
+                                c_void_p],
     "ubpl_warp_decode_k2_ws_bytes": [c_int, c_int, c_int],
     "ubpl_warp_materialize": [c_void_p, c_i64, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p],

@@ -53,6 +53,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a hardware-defined time)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -94,6 +108,12 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w)
                : "memory");
+}
+
+// mean-teacher EMA of one element with ATen's rounding: t = ema*alpha (rounded), then fma(param, 1-alpha, t)
+// (utils/parameters.py:8: ema.mul_(alpha).add_(param, alpha=1-alpha))
+__device__ __forceinline__ float ema1(float e, float p, float a, float oma) {
+  return __fmaf_rn(p, oma, __fmul_rn(e, a));
 }
 
 // ---------------------------------------------------------------------------------------------

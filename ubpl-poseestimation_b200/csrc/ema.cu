@@ -11,10 +11,6 @@
 
 namespace ubpl {
 
-__device__ __forceinline__ float ema1(float e, float p, float a, float oma) {
-  return __fmaf_rn(p, oma, __fmul_rn(e, a));
-}
-
 __global__ void __launch_bounds__(256) ema_multi_kernel(const uint64_t* __restrict__ ema_ptrs,
                                                          const uint64_t* __restrict__ param_ptrs,
                                                          const long long* __restrict__ numels,

@@ -86,6 +86,14 @@ __device__ __forceinline__ float gauss_px(const float* ex, const float* ey, int 
   return (v < 0.01f) ? 0.f : v;
 }
 
+// the same with the two separable factors already in registers
+__device__ __forceinline__ float gauss_px_v(float exv, float eyv, int x, int y, int kx, int ky, float stride, float sigma) {
+  const float v = exv * eyv;
+  if (fabsf(v - 0.01f) < 1e-5f)      // centre recomputed as in gauss_setup: only the integer key point stays live
+    return gauss_px_exact(x, y, (double)kx * 1.0 / (double)stride, (double)ky * 1.0 / (double)stride, sigma);
+  return (v < 0.01f) ? 0.f : v;
+}
+
 // One WARP per (sample, joint): no block barriers; every lane keeps 8 independent 128-bit loads in
 // flight; the separable Gaussian factors live in a per-warp shared-memory slice.
 template <bool VEC, int SS, int OCC>
@@ -266,6 +274,177 @@ __global__ void __launch_bounds__(128, OCC) render_mse_kernel(
         double u0 = 0.0, u1 = 0.0, u2 = 0.0;
         for (int i = 0; i < wpb; ++i) { u0 += s_red[0][i]; u1 += s_red[1][i]; u2 += s_red[2][i]; }
         summary[0] = u0; summary[1] = u1; summary[2] = (double)(BJ * S); summary[3] = u2;
+        *ticket = 0u;
+      }
+    }
+  }
+}
+
+// The lean form of render_mse_kernel for the shapes the drivers run (128-bit aligned maps, S = 1 or 2, W/4 a power
+// of two <= 128, H*W a multiple of 4096): same arithmetic per texel, ~3x fewer instructions per item.  The generic
+// kernel above spends 1.4 k warp instructions per item and warp on index arithmetic, guards and the per-warp
+// Gaussian set-up (ncu: issue-bound at 43 % with 20 warps per SM, DRAM 51 % busy).  Here a CTA of 128 threads owns
+// an item; thread t handles the float4 column t % (W/4) of rows t / (W/4) + R*u (R = 128 / (W/4)), so the column
+// factors of the separable Gaussian are four registers per item and a position costs one row factor; ALL loads of an
+// item (8 positions x S stacks per thread and chunk) are issued before the Gaussian tables are built, the next item's
+// key point / gate are fetched a whole item ahead, and there is ONE block barrier per item (tables and partial sums
+// are double-buffered).  Partial sums are added in warp order: reproducible, not bit-identical to the generic kernel
+// (different split of the texels over the warps), inside the 1e-5 the tests allow for the loss.
+template <int SS, int OCC>
+__global__ void __launch_bounds__(128, OCC) render_mse_fast_kernel(
+    const float* __restrict__ kps, const float* __restrict__ gate_in, const float* __restrict__ sample_w,
+    const float* __restrict__ pred, long long pB, long long pS, long long pJ, float* __restrict__ grad, long long gB,
+    long long gS, long long gJ, float* __restrict__ target, int B, int J, int H, int W, int img_h, int img_w,
+    float stride, float sigma, const float* __restrict__ grad_scale, const int32_t* __restrict__ count_in,
+    float loss_weight, float* __restrict__ grad_scale_out, float* __restrict__ gate_out,
+    float* __restrict__ per_loss, double* __restrict__ summary, unsigned char* __restrict__ sum_ws, int w4_shift) {
+  extern __shared__ float sm[];                          // two tables of W + H Gaussian factors
+  __shared__ float s_part[2][SS][4];
+  __shared__ float s_meta[2][2];                         // gate and sample weight of the item whose partials are pending
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // see render_mse_kernel
+  const int HW = H * W, nq = HW >> 2, WH = W + H;
+  float gs = grad_scale ? *grad_scale : 1.f;
+  if (count_in) {
+    const int cnt = *count_in;
+    gs = (cnt > 0) ? loss_weight / (float)cnt : loss_weight;
+    if (grad_scale_out && blockIdx.x == 0 && tid == 0) *grad_scale_out = gs;
+  }
+  const float inv_hw = 1.f / (float)HW;
+  const long long BJ = (long long)B * J;
+  const int x4 = tid & ((1 << w4_shift) - 1), yb = tid >> w4_shift, R = 128 >> w4_shift;
+  const int x = x4 << 2;
+  const float rad = 3.05f * sigma + 1.f;                 // support box, as in render_mse_kernel
+  __shared__ double s_acc[3];                            // thread 0: this CTA's share of the fused reduction
+  if (tid == 0) { s_acc[0] = 0.0; s_acc[1] = 0.0; s_acc[2] = 0.0; }
+
+  // key point, gate and sample weight of an item are fetched one item ahead by threads 0..3 and handed to the CTA
+  // through shared memory (s_next[parity]): no global-load latency at the top of an item, no registers held for it
+  __shared__ float s_next[2][4];
+  auto fetch_meta = [&](int it, int par) {               // threads 0..3; visible after the next block barrier
+    if (tid < 4 && it < (int)BJ) {
+      float v;
+      if (tid < 2) v = kps[2 * (long long)it + tid];
+      else if (tid == 2) v = gate_in ? gate_in[it] : 1.f;
+      else v = sample_w ? sample_w[it / J] : 1.f;
+      s_next[par][tid] = v;
+    }
+  };
+  auto finalize = [&](int it, int par) {                 // thread 0: scalars of a finished item
+    const int b = it / J, j = it - b * J;
+    const float gate = s_meta[par][0], wb = s_meta[par][1];
+#pragma unroll
+    for (int ss = 0; ss < SS; ++ss) {
+      const float tot = ((s_part[par][ss][0] + s_part[par][ss][1]) + s_part[par][ss][2]) + s_part[par][ss][3];
+      const float pl = ((tot * inv_hw) * gate) * wb;
+      if (per_loss) per_loss[((long long)b * SS + ss) * J + j] = pl;
+      s_acc[0] += (double)pl; s_acc[1] += (pl > 0.f) ? 1.0 : 0.0;
+    }
+    s_acc[2] += (gate > 0.f) ? 1.0 : 0.0;
+  };
+  int item = (int)blockIdx.x, prev = -1;
+  fetch_meta(item, 0);
+  __syncthreads();
+  for (int k = 0; item < (int)BJ; item += (int)gridDim.x, ++k) {
+    const int par = k & 1;
+    const int b = item / J, j = item - b * J;
+    const float kx = s_next[par][0], ky = s_next[par][1], gate_raw = s_next[par][2], wb = s_next[par][3];
+    const float* p[SS];
+    float* gr[SS];
+#pragma unroll
+    for (int ss = 0; ss < SS; ++ss) {
+      p[ss] = pred + (long long)b * pB + (long long)ss * pS + (long long)j * pJ;
+      gr[ss] = grad ? grad + (long long)b * gB + (long long)ss * gS + (long long)j * gJ : nullptr;
+    }
+    float* tg = target ? target + (long long)item * HW : nullptr;
+    float4 pv[SS][8];
+#pragma unroll
+    for (int ss = 0; ss < SS; ++ss)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) pv[ss][u] = ldg_stream(reinterpret_cast<const float4*>(p[ss]) + tid + 128 * u);
+    fetch_meta(item + (int)gridDim.x, par ^ 1);          // consumed one item later
+    const Gauss g = gauss_setup(kx, ky, img_h, img_w, stride, sigma);
+    float* ex = sm + par * WH;
+    float* ey = ex + W;
+    for (int i = tid; i < WH; i += 128) ex[i] = (i < W) ? gauss_1d(i, g.cx, sigma) : gauss_1d(i - W, g.cy, sigma);
+    const float gate = gate_raw * g.vis;
+    if (tid == 0) {
+      s_meta[par][0] = gate; s_meta[par][1] = wb;
+      if (gate_out) gate_out[item] = gate;
+    }
+    __syncthreads();                                     // tables of this item, partial sums of the previous one
+    if (tid == 0 && prev >= 0) finalize(prev, par ^ 1);
+    const float gcoef = gs * 2.f * inv_hw * gate * wb;
+    const int xlo = (int)floorf((float)g.cx - rad), xhi = (int)ceilf((float)g.cx + rad);
+    const int ylo = (int)floorf((float)g.cy - rad), yhi = (int)ceilf((float)g.cy + rad);
+    const bool col_in = !(x + 3 < xlo || x > xhi);
+    const int gkx = g.kx, gky = g.ky;
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+    if (col_in) { e0 = ex[x]; e1 = ex[x + 1]; e2 = ex[x + 2]; e3 = ex[x + 3]; }
+    float sse[SS];
+#pragma unroll
+    for (int ss = 0; ss < SS; ++ss) sse[ss] = 0.f;
+    for (int q0 = 0; q0 < nq; q0 += 1024) {
+      if (q0) {
+#pragma unroll
+        for (int ss = 0; ss < SS; ++ss)
+#pragma unroll
+          for (int u = 0; u < 8; ++u) pv[ss][u] = ldg_stream(reinterpret_cast<const float4*>(p[ss]) + q0 + tid + 128 * u);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int q = q0 + tid + 128 * u;
+        const int y = (q0 >> w4_shift) + yb + R * u;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_in && y >= ylo && y <= yhi) {
+          const float ev = ey[y];
+          t.x = gauss_px_v(e0, ev, x, y, gkx, gky, stride, sigma); t.y = gauss_px_v(e1, ev, x + 1, y, gkx, gky, stride, sigma);
+          t.z = gauss_px_v(e2, ev, x + 2, y, gkx, gky, stride, sigma); t.w = gauss_px_v(e3, ev, x + 3, y, gkx, gky, stride, sigma);
+        }
+#pragma unroll
+        for (int ss = 0; ss < SS; ++ss) {
+          const float4 v = pv[ss][u];
+          const float4 d = make_float4(v.x - t.x, v.y - t.y, v.z - t.z, v.w - t.w);
+          sse[ss] += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+          if (gr[ss]) stg_stream(reinterpret_cast<float4*>(gr[ss]) + q, make_float4(gcoef * d.x, gcoef * d.y, gcoef * d.z, gcoef * d.w));
+        }
+        if (tg) stg_stream(reinterpret_cast<float4*>(tg) + q, t);
+      }
+    }
+#pragma unroll
+    for (int ss = 0; ss < SS; ++ss) {
+      const float tot = warp_sum(sse[ss]);
+      if (lane == 0) s_part[par][ss][warp] = tot;
+    }
+    prev = item;
+  }
+  __syncthreads();
+  if (tid == 0 && prev >= 0) finalize(prev, ((prev - (int)blockIdx.x) / (int)gridDim.x) & 1);
+  if (summary) {
+    // the fused loss reduction of render_mse_kernel: per-CTA partials, the CTA with the last ticket adds them in CTA order
+    __shared__ unsigned s_last;
+    __shared__ double s_fin[3][4];
+    double* part = reinterpret_cast<double*>(sum_ws + 16);
+    unsigned* ticket = reinterpret_cast<unsigned*>(sum_ws);
+    if (tid == 0) {
+      part[3 * blockIdx.x] = s_acc[0]; part[3 * blockIdx.x + 1] = s_acc[1]; part[3 * blockIdx.x + 2] = s_acc[2];
+      __threadfence();
+      s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+      for (unsigned c = tid; c < gridDim.x; c += 128) {
+        t0 += __ldcg(part + 3 * c); t1 += __ldcg(part + 3 * c + 1); t2 += __ldcg(part + 3 * c + 2);
+      }
+      t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2);
+      if (lane == 0) { s_fin[0][warp] = t0; s_fin[1][warp] = t1; s_fin[2][warp] = t2; }
+      __syncthreads();
+      if (tid == 0) {
+        double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+        for (int i = 0; i < 4; ++i) { u0 += s_fin[0][i]; u1 += s_fin[1][i]; u2 += s_fin[2][i]; }
+        summary[0] = u0; summary[1] = u1; summary[2] = (double)(BJ * SS); summary[3] = u2;
         *ticket = 0u;
       }
     }
@@ -634,6 +813,35 @@ static int render_mse_impl(const float* kps, const float* gate_in, const float* 
   lattr[0].val.programmaticStreamSerializationAllowed = 1;
   const bool pdl = getenv("UBPL_K3_PDL") ? atoi(getenv("UBPL_K3_PDL")) != 0 : true;
   lc.attrs = lattr; lc.numAttrs = pdl ? 1 : 0;
+  // the lean kernel for the drivers' shapes (see render_mse_fast_kernel) is opt-in (UBPL_K3_FAST=1): measured on c2 it
+  // is no faster than the generic kernel (57.2 vs 56.5 us back to back) although it executes ~3x fewer instructions
+  // -- K3 is bound by the memory system's read/write mix, not by issue slots (profiles/README.md round 2)
+  const int w4 = W / 4;
+  const bool fast_ok = vec && (S == 1 || S == 2) && w4 >= 1 && w4 <= 128 && (w4 & (w4 - 1)) == 0 && (HW % 4096 == 0) &&
+                       (getenv("UBPL_K3_FAST") && atoi(getenv("UBPL_K3_FAST")) != 0) && !getenv("UBPL_K3_STORE") &&
+                       all_coop;
+  if (fast_ok) {
+    int sh = 0;
+    while ((1 << sh) < w4) ++sh;
+    // resident CTAs per SM the lean kernel is compiled for (UBPL_K3_FAST_OCC = 4, 5 or 6; one resident wave)
+    int focc = getenv("UBPL_K3_FAST_OCC") ? atoi(getenv("UBPL_K3_FAST_OCC")) : 5;
+    if (focc < 4) focc = 4;
+    if (focc > 6) focc = 6;
+    long long fcap = (long long)sm_count() * focc;
+    if (getenv("UBPL_K3_CTAS") && atoi(getenv("UBPL_K3_CTAS")) > 0) fcap = (long long)sm_count() * atoi(getenv("UBPL_K3_CTAS"));
+    if (fcap > 4096) fcap = 4096;
+    lc.gridDim = dim3((unsigned)(BJ < fcap ? BJ : fcap));
+    lc.dynamicSmemBytes = 2 * (size_t)(W + H) * sizeof(float);
+#define UBPL_LAUNCH_FAST(SSV, OCCV)                                                                                    \
+    cudaLaunchKernelEx(&lc, render_mse_fast_kernel<SSV, OCCV>, kps, gate_in, sample_w, pred, (long long)pB, (long long)pS, \
+                       (long long)pJ, grad, (long long)gB, (long long)gS, (long long)gJ, target, B, J, H, W, img_h, img_w,  \
+                       stride, sigma, grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, summary,   \
+                       sum_ws, sh)
+    if (S == 2) { if (focc == 4) UBPL_LAUNCH_FAST(2, 4); else if (focc == 5) UBPL_LAUNCH_FAST(2, 5); else UBPL_LAUNCH_FAST(2, 6); }
+    else { if (focc == 4) UBPL_LAUNCH_FAST(1, 4); else if (focc == 5) UBPL_LAUNCH_FAST(1, 5); else UBPL_LAUNCH_FAST(1, 6); }
+#undef UBPL_LAUNCH_FAST
+    return check_launch("ubpl_render_mse");
+  }
 #define UBPL_LAUNCH_RENDER(V, SSV)                                                                                     \
   if (occ5) cudaLaunchKernelEx(&lc, render_mse_kernel<V, SSV, 5>,                                                      \
       kps, gate_in, sample_w, pred, (long long)pB, (long long)pS, (long long)pJ, grad, (long long)gB, (long long)gS, (long long)gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \

@@ -67,6 +67,24 @@ struct K2Fuse {
   PowTab T;
 };
 
+// K4 inside K1 (optional, ubpl_warp_decode_k2_ema): the mean-teacher EMA of ubpl_ema_multi_tensor, chunk by chunk,
+// done by the warps that have run out of maps.  K1's launch ends with ~2 map times (~20 us on c2) in which ever fewer
+// warps still decode and HBM is no longer saturated by the staged copies; the EMA depends on nothing in the chain, so
+// its 12 bytes per parameter fill that tail instead of costing a launch of their own (a separate EMA kernel cannot run
+// beside K1: a CTA that holds 225 KB of shared memory has the SM to itself, so "beside K1" was "in front of K1").
+struct TailEma {
+  const uint64_t* ema_ptrs;
+  const uint64_t* param_ptrs;
+  const long long* numels;
+  const int32_t* chunk_tensor;
+  const long long* chunk_start;
+  long long n_chunks;            // 0: no EMA in this launch
+  int chunk_elems;
+  float a, oma;
+  const float* alpha_dev;        // optional {alpha, 1 - alpha} in device memory (CUDA-graph replays follow the epoch)
+  unsigned long long* next;      // piece counter (kEmaPiece elements each), zero before the launch
+};
+
 struct WDParams {
   FastDiv divJ, divB, divW;
   float stepx, stepy, sfx, sfy;
@@ -92,8 +110,11 @@ struct WDParams {
                                  // thousands of concurrent 16 KB streams over a large footprint HBM falls into a
                                  // low-efficiency regime (profiles/README.md, round 2), so the copies are metered
   int dbg;                       // UBPL_K1_DBG (timing experiments only, results void): 1 skip phases L/B/C and the
-                                 // exhaustive decode, 2 skip the epilogue, 4 skip only the exhaustive decode, 8 skip pass A
+                                 // exhaustive decode, 2 skip the epilogue, 4 skip only the exhaustive decode, 8 skip pass A;
+                                 // 16 (results valid) leaves a %globaltimer timeline in stats[8..19], 32 adds per-warp
+                                 // records from stats[32] on (stats must then hold 32 + 2*16*gridDim words), see tl_now
   K2Fuse k2;                  // optional K2 epilogue run by the warp that decodes the last view of a (sample, joint)
+  TailEma ema;                // optional K4 done by the warps that have run out of maps
 };
 
 struct Xform {
@@ -107,6 +128,17 @@ struct ArgMax {
   float v;
   int i;
 };
+
+// Timeline probe of UBPL_K1_DBG=16 (tools/k1_ab.py prints it): stats[8]/[9] first / last CTA start, [10]/[11] first /
+// last "first map landed" over the warps, [12]/[13] first / last "warp ran out of maps", [14] last warp exit,
+// [15] ns summed over the warps waiting for staged copies, [16] ns waiting for a copy ticket, [17] ns in the
+// exhaustive decode (own job or alone), [18] ns helping other warps' jobs, [19] ns between a warp's first landed map
+// and its running out of maps.  The min slots are initialised to a large value by the host.
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ float lin_coord(int k, int n, float step) {
   if (n <= 1) return 0.f;  // ATen linspace_from_neg_one: a single step sits at 0
@@ -343,6 +375,48 @@ __device__ __forceinline__ ArgMax coop_exhaustive(CoopJob* cj, const WDParams& p
     atomicExch(&cj->owner, 0);
   }
   return r;
+}
+
+// One PIECE (kEmaPiece elements of one chunk) of the EMA (see TailEma) by one warp, the arithmetic of ema_multi_kernel
+// (csrc/ema.cu).  A piece is one memory round trip: all of a lane's 4 + 4 128-bit loads are in flight together (a whole
+// 8192-element chunk per warp would be 16 dependent round trips, ~20 us -- longer than the tail it is meant to fill;
+// 8 + 8 loads per lane made the register allocator spill in the decode loop and cost K1 12 %).
+constexpr int kEmaPiece = 512;
+__device__ __forceinline__ void ema_piece(const TailEma& E, unsigned c, int pieces, float a, float oma, int lane) {
+  const unsigned chunk = c / (unsigned)pieces;             // 32-bit: a 64-bit division is a call
+  const int lo = (int)(c - chunk * (unsigned)pieces) * kEmaPiece;
+  const int t = E.chunk_tensor[chunk];
+  const long long start = E.chunk_start[chunk];
+  const long long rem = E.numels[t] - start;
+  const int n = (int)(rem < E.chunk_elems ? rem : E.chunk_elems);
+  const int hi = min(n, lo + kEmaPiece);
+  if (lo >= hi) return;
+  float* e = reinterpret_cast<float*>(E.ema_ptrs[t]) + start + lo;
+  const float* q = reinterpret_cast<const float*>(E.param_ptrs[t]) + start + lo;
+  const int m = hi - lo;
+  if ((((uintptr_t)e | (uintptr_t)q) & 15) == 0) {
+    const int n4 = m >> 2;                                 // <= 128: at most 4 float4 per lane
+    float4* e4 = reinterpret_cast<float4*>(e);
+    const float4* q4 = reinterpret_cast<const float4*>(q);
+    float4 ev[4], pv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = lane + 32 * u;
+      if (i < n4) { ev[u] = e4[i]; pv[u] = ldg_stream(q4 + i); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = lane + 32 * u;
+      if (i < n4) {
+        ev[u].x = ema1(ev[u].x, pv[u].x, a, oma); ev[u].y = ema1(ev[u].y, pv[u].y, a, oma);
+        ev[u].z = ema1(ev[u].z, pv[u].z, a, oma); ev[u].w = ema1(ev[u].w, pv[u].w, a, oma);
+        e4[i] = ev[u];
+      }
+    }
+    for (int k = (n4 << 2) + lane; k < m; k += 32) e[k] = ema1(e[k], __ldg(q + k), a, oma);
+  } else {
+    for (int k = lane; k < m; k += 32) e[k] = ema1(e[k], __ldg(q + k), a, oma);
+  }
 }
 
 // 3-input float min that PROPAGATES NaN (SASS FMNMX3.NAN): the running minimum turns NaN if any texel
@@ -820,6 +894,8 @@ __device__ __forceinline__ void decode_pruned(const WDParams& p, const float* __
 
 // One warp per heat-map, maps claimed from a global counter, each staged in the warp's shared-memory buffer by
 // a 1-D bulk async copy (TMA engine); the next copy starts when the map is finished.
+// TL: the %globaltimer probe of UBPL_K1_DBG=16 is compiled in (its accumulators cost registers).
+template <bool TL>
 __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -835,6 +911,9 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
 
   const long long N = (long long)p.V * p.B * p.J;
   uint64_t pol = 0;
+  const bool tl = TL && p.stats;
+  unsigned long long tl_first = 0, tl_wait = 0, tl_ticket = 0, tl_exh = 0, tl_help = 0;
+  if (tl && threadIdx.x == 0) { const unsigned long long t = tl_now(); atomicMin(p.stats + 8, t); atomicMax(p.stats + 9, t); }
   if (threadIdx.x == 0) {
     cj->owner = 0; cj->band_next = kBands; cj->bands_done = 0; cj->warps_done = 0; cj->issued = 0u; cj->landed = 0u;
     cj->local_next = 0;
@@ -879,7 +958,11 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   }
   __syncthreads();
   fetch_next();
-  if (p.use_bulk && lane == 0 && nx.n < N) issue_map(p, nx.n, buf0, bar, pol, map_bytes, cj);
+  if (p.use_bulk && lane == 0 && nx.n < N) {
+    const unsigned long long t0 = tl ? tl_now() : 0ull;
+    issue_map(p, nx.n, buf0, bar, pol, map_bytes, cj);
+    if (tl) tl_ticket += tl_now() - t0;
+  }
 
   unsigned long long n_slow = 0, n_eval = 0, n_maps = 0;
   long long pend_item = -1;                              // K2 ticket of the previous map (see finish_map)
@@ -895,7 +978,11 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     if (p.do_warp) {
       int open = 0;
       if (lane == 0) open = ld_volatile_s32(&cj->band_next) < kBands ? 1 : 0;
-      if (__shfl_sync(0xffffffffu, open, 0)) coop_help(cj, p, lx, ly, lane);
+      if (__shfl_sync(0xffffffffu, open, 0)) {
+        const unsigned long long t0 = tl ? tl_now() : 0ull;
+        coop_help(cj, p, lx, ly, lane);
+        if (tl) tl_help += tl_now() - t0;
+      }
     }
     unsigned vbu, ju, vu, bu;
     p.divJ.divmod((unsigned)n, vbu, ju);
@@ -925,7 +1012,13 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       A.C00 = e * idet; A.C01 = -bb * idet; A.C10 = -d * idet; A.C11 = a * idet;
     }
     if (p.use_bulk) {
+      const unsigned long long t0 = tl ? tl_now() : 0ull;
       mbar_wait(bar, (uint32_t)(it & 1));
+      if (tl) {
+        const unsigned long long t1 = tl_now();
+        tl_wait += t1 - t0;
+        if (it == 0) tl_first = t1;
+      }
       if (p.inflight_cap > 0 && lane == 0) atomicAdd(&cj->landed, 1u);
     } else {
       const float* gsrc = map_src(p, n);
@@ -973,7 +1066,9 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       if (exhaustive) {
         // NaN-aware compare for non-finite maps and for degenerate / huge transforms (their grid can overflow to
         // Inf - Inf = NaN weights); everything else yields finite samples
+        const unsigned long long t0 = tl ? tl_now() : 0ull;
         const ArgMax r = coop_exhaustive(cj, p, s, X, nonfinite || bad_xform, lx, ly, warp, lane);
+        if (tl) tl_exh += tl_now() - t0;
         rv = r.v; ri = r.i;
         ++n_slow;
         n_eval += HW;
@@ -984,37 +1079,71 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     if (p.do_warp) {                                     // second look at the CTA's job word, half a map after the first
       int open = 0;
       if (lane == 0) open = ld_volatile_s32(&cj->band_next) < kBands ? 1 : 0;
-      if (__shfl_sync(0xffffffffu, open, 0)) coop_help(cj, p, lx, ly, lane);
+      if (__shfl_sync(0xffffffffu, open, 0)) {
+        const unsigned long long t0 = tl ? tl_now() : 0ull;
+        coop_help(cj, p, lx, ly, lane);
+        if (tl) tl_help += tl_now() - t0;
+      }
     }
     if (!(p.dbg & 2)) {
       k2_resolve(p, pend_item, pend_old, lane);          // the previous map's ticket has long arrived by now
       finish_map(p, n, (int)vu, b, j, s, X, lx, ly, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
     } else if (rv == 123.456f && p.out_max) p.out_max[n] = rv;
     __syncwarp();
-    if (p.use_bulk && lane == 0 && nx.n < N) issue_map(p, nx.n, buf0, bar, pol, map_bytes, cj);   // buffer handed on
+    if (p.use_bulk && lane == 0 && nx.n < N) {                                                    // buffer handed on
+      const unsigned long long t0 = tl ? tl_now() : 0ull;
+      issue_map(p, nx.n, buf0, bar, pol, map_bytes, cj);
+      if (tl) tl_ticket += tl_now() - t0;
+    }
   }
   k2_resolve(p, pend_item, pend_old, lane);
+  if (tl && lane == 0 && n_maps) {
+    const unsigned long long t = tl_now();
+    atomicMin(p.stats + 10, tl_first); atomicMax(p.stats + 11, tl_first);
+    atomicMin(p.stats + 12, t); atomicMax(p.stats + 13, t);
+    atomicAdd(p.stats + 15, tl_wait); atomicAdd(p.stats + 16, tl_ticket);
+    atomicAdd(p.stats + 17, tl_exh); atomicAdd(p.stats + 18, tl_help); atomicAdd(p.stats + 19, t - tl_first);
+    if (p.dbg & 32) {                                    // per-warp record: stats[32 + 2*g] = time out of maps,
+      const unsigned g = blockIdx.x * 16u + (unsigned)warp;   // [33 + 2*g] = maps | exhaustive << 16 | exhaustive ns << 32
+      p.stats[32 + 2 * g] = t;
+      p.stats[33 + 2 * g] = n_maps | (n_slow << 16) | (tl_exh << 32);
+    }
+  }
   if (p.stats && lane == 0 && n_maps) {
     atomicAdd(p.stats + 0, n_slow);
     atomicAdd(p.stats + 1, n_eval);
     atomicAdd(p.stats + 2, n_maps);
   }
-  // Out of maps: stay while other warps of the CTA may still post an exhaustive job, and meanwhile pull the
-  // range the next kernel reads (pf_ptr: the student maps of K3) into L2 -- HBM is going idle as the last
-  // maps finish.
+  // Out of maps: stay while other warps of the CTA may still post an exhaustive job.  Meanwhile -- HBM is going idle as
+  // the last maps finish -- do the EMA's pieces (TailEma: real work that would otherwise be a launch of its own; the
+  // warp leaves only when no piece is left), then pull the range the next kernel reads (pf_ptr: the student maps of
+  // K3) into L2 for as long as other warps are still decoding.
   if (p.do_warp) {
     __syncwarp();
     if (lane == 0) atomicAdd(&cj->warps_done, 1);
     constexpr unsigned kPfChunk = 32768u;
     bool pf_live = p.pf_ptr != nullptr;
+    bool ema_live = p.ema.n_chunks > 0;
+    const int ema_pieces = (p.ema.chunk_elems + kEmaPiece - 1) / kEmaPiece;
+    const unsigned ema_total = (unsigned)p.ema.n_chunks * (unsigned)ema_pieces;
+    float ea = p.ema.a, eoma = p.ema.oma;
+    if (ema_live && p.ema.alpha_dev) { ea = p.ema.alpha_dev[0]; eoma = p.ema.alpha_dev[1]; }
     int tick = 0;                                        // one chunk per pf_every polls: the idle warps ask for about
     for (;;) {                                           // the bandwidth they used while they were decoding
       int st = 0;                                        // lane 0 decides for the warp: 2 leave, 1 help, 0 idle
-      if (lane == 0) st = ld_volatile_s32(&cj->warps_done) >= warps ? 2 : (ld_volatile_s32(&cj->band_next) < kBands ? 1 : 0);
+      if (lane == 0) st = (!ema_live && ld_volatile_s32(&cj->warps_done) >= warps) ? 2 : (ld_volatile_s32(&cj->band_next) < kBands ? 1 : 0);
       st = __shfl_sync(0xffffffffu, st, 0);
       if (st == 2) break;
       if (st == 1) {
         coop_help(cj, p, lx, ly, lane);
+        continue;
+      }
+      if (ema_live) {
+        unsigned long long c = 0;
+        if (lane == 0) c = atomicAdd(p.ema.next, 1ull);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= (unsigned long long)ema_total) { ema_live = false; continue; }
+        ema_piece(p.ema, (unsigned)c, ema_pieces, ea, eoma, lane);
         continue;
       }
       if (pf_live && (tick++ % p.pf_every) == 0) {
@@ -1029,6 +1158,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       __nanosleep(200);
     }
   }
+  if (tl && lane == 0) atomicMax(p.stats + 14, tl_now());
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -1138,13 +1268,15 @@ static int launch_k1(WDParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)warps * buf_stride + tail;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(warp_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+    cudaError_t e = cudaFuncSetAttribute(warp_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(warp_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
     if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
     attr_set = true;
   }
   long long need = (N + warps - 1) / warps;
   int grid = (int)(need < sm_count() ? need : sm_count());
-  warp_decode_kernel<<<grid, warps * 32, smem, stream>>>(p);
+  if ((p.dbg & 16) && p.stats) warp_decode_kernel<true><<<grid, warps * 32, smem, stream>>>(p);
+  else warp_decode_kernel<false><<<grid, warps * 32, smem, stream>>>(p);
   return check_launch("ubpl_warp_decode");
 }
 
@@ -1191,13 +1323,13 @@ extern "C" int64_t ubpl_warp_decode_k2_ws_bytes(int V, int B, int J) {
   return 4 * (k2_ws_zero_words(V, B, J) + 4);
 }
 
-extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ, int V, int B, int J, int H,
-                                   int W, const float* theta, const uint8_t* flip, const int32_t* swap_perm,
-                                   const double* dec, int refine, int32_t* out_idx, float* out_max, float* out_xy,
-                                   int k2_mode, double distThrMax, int img_h, int img_w, float stride, float sigma,
-                                   int S, float* mean, double* dist, uint8_t* legal, uint8_t* enable, float* gate,
-                                   int64_t* stats, int32_t* ws, int64_t ws_bytes, const void* prefetch,
-                                   int64_t prefetch_bytes, void* stream) {
+static int warp_decode_k2_impl(const float* maps, int64_t sV, int64_t sB, int64_t sJ, int V, int B, int J, int H,
+                               int W, const float* theta, const uint8_t* flip, const int32_t* swap_perm,
+                               const double* dec, int refine, int32_t* out_idx, float* out_max, float* out_xy,
+                               int k2_mode, double distThrMax, int img_h, int img_w, float stride, float sigma,
+                               int S, float* mean, double* dist, uint8_t* legal, uint8_t* enable, float* gate,
+                               int64_t* stats, int32_t* ws, int64_t ws_bytes, const void* prefetch,
+                               int64_t prefetch_bytes, const TailEma* ema, void* stream) {
   UBPL_REQUIRE(V >= 1 && V <= 32 && B >= 0 && J >= 1 && H > 0 && W > 0, "ubpl_warp_decode_k2: bad dims V=%d B=%d J=%d H=%d W=%d (1 <= V <= 32)", V, B, J, H, W);
   UBPL_REQUIRE(ws && (B == 0 || (maps && theta && out_xy)), "ubpl_warp_decode_k2: NULL pointer");
   UBPL_REQUIRE(refine >= 0 && refine <= 2, "ubpl_warp_decode_k2: refine must be 0, 1 or 2");
@@ -1212,9 +1344,19 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
   cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)zero_words * 4, (cudaStream_t)stream);
   if (e != cudaSuccess) { set_error("ubpl_warp_decode_k2: memset: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
   const long long N = (long long)V * B * J;
-  if (N == 0) return UBPL_OK;
+  if (N == 0) {                                        // nothing to decode: the EMA still has to happen
+    if (ema && ema->n_chunks > 0)
+      return ubpl_ema_multi_tensor(ema->ema_ptrs, ema->param_ptrs, reinterpret_cast<const int64_t*>(ema->numels), ema->chunk_tensor,
+                                   reinterpret_cast<const int64_t*>(ema->chunk_start), ema->n_chunks, ema->chunk_elems, ema->a,
+                                   ema->oma, ema->alpha_dev, stream);
+    return UBPL_OK;
+  }
   WDParams p;
   memset(&p, 0, sizeof(p));
+  if (ema && ema->n_chunks > 0) {
+    p.ema = *ema;
+    p.ema.next = reinterpret_cast<unsigned long long*>(ws + 64);    // its own 128-byte line, cleared by the memset above
+  }
   p.maps = maps; p.sV = sV; p.sB = sB; p.sJ = sJ; p.V = V; p.B = B; p.J = J; p.H = H; p.W = W;
   p.theta = theta; p.flip = flip; p.swap_perm = flip ? swap_perm : nullptr; p.dec = dec; p.do_warp = 1; p.refine = refine;
   p.out_idx = out_idx; p.out_max = out_max; p.out_xy = out_xy; p.out_hm_xy = nullptr;
@@ -1240,6 +1382,41 @@ extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, in
   int rc = pow_table(&f.T.key, &f.T.val, &f.T.bits, &f.T.n, &f.T.rmax);
   if (rc != UBPL_OK) return rc;
   return launch_k1(p, (cudaStream_t)stream);
+}
+
+extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ, int V, int B, int J, int H,
+                                   int W, const float* theta, const uint8_t* flip, const int32_t* swap_perm,
+                                   const double* dec, int refine, int32_t* out_idx, float* out_max, float* out_xy,
+                                   int k2_mode, double distThrMax, int img_h, int img_w, float stride, float sigma,
+                                   int S, float* mean, double* dist, uint8_t* legal, uint8_t* enable, float* gate,
+                                   int64_t* stats, int32_t* ws, int64_t ws_bytes, const void* prefetch,
+                                   int64_t prefetch_bytes, void* stream) {
+  return warp_decode_k2_impl(maps, sV, sB, sJ, V, B, J, H, W, theta, flip, swap_perm, dec, refine, out_idx, out_max, out_xy,
+                             k2_mode, distThrMax, img_h, img_w, stride, sigma, S, mean, dist, legal, enable, gate, stats, ws,
+                             ws_bytes, prefetch, prefetch_bytes, nullptr, stream);
+}
+
+extern "C" int ubpl_warp_decode_k2_ema(const float* maps, int64_t sV, int64_t sB, int64_t sJ, int V, int B, int J, int H,
+                                       int W, const float* theta, const uint8_t* flip, const int32_t* swap_perm,
+                                       const double* dec, int refine, int32_t* out_idx, float* out_max, float* out_xy,
+                                       int k2_mode, double distThrMax, int img_h, int img_w, float stride, float sigma,
+                                       int S, float* mean, double* dist, uint8_t* legal, uint8_t* enable, float* gate,
+                                       int64_t* stats, int32_t* ws, int64_t ws_bytes, const void* prefetch,
+                                       int64_t prefetch_bytes, const uint64_t* ema_ptrs, const uint64_t* param_ptrs,
+                                       const int64_t* numels, const int32_t* chunk_tensor, const int64_t* chunk_start,
+                                       int64_t n_chunks, int chunk_elems, float alpha, float one_minus_alpha,
+                                       const float* alpha_dev, void* stream) {
+  UBPL_REQUIRE(n_chunks >= 0 && (n_chunks == 0 || (ema_ptrs && param_ptrs && numels && chunk_tensor && chunk_start)),
+               "ubpl_warp_decode_k2_ema: NULL pointer in the EMA tables");
+  UBPL_REQUIRE(n_chunks == 0 || (chunk_elems > 0 && chunk_elems % 4 == 0), "ubpl_warp_decode_k2_ema: bad chunking");
+  TailEma E;
+  memset(&E, 0, sizeof(E));
+  E.ema_ptrs = ema_ptrs; E.param_ptrs = param_ptrs; E.numels = reinterpret_cast<const long long*>(numels);
+  E.chunk_tensor = chunk_tensor; E.chunk_start = reinterpret_cast<const long long*>(chunk_start);
+  E.n_chunks = n_chunks; E.chunk_elems = chunk_elems; E.a = alpha; E.oma = one_minus_alpha; E.alpha_dev = alpha_dev;
+  return warp_decode_k2_impl(maps, sV, sB, sJ, V, B, J, H, W, theta, flip, swap_perm, dec, refine, out_idx, out_max, out_xy,
+                             k2_mode, distThrMax, img_h, img_w, stride, sigma, S, mean, dist, legal, enable, gate, stats, ws,
+                             ws_bytes, prefetch, prefetch_bytes, &E, stream);
 }
 
 extern "C" int ubpl_warp_materialize(const float* in, int64_t sN, int64_t sC, float* out, int64_t oN, int64_t oC,

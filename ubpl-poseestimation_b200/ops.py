@@ -119,7 +119,8 @@ def warp_decode(maps, theta=None, flip=None, dec=None, refine=0, stats=None, wan
 
 
 def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stride=4.0, sigma=3.0, distThrMax=1.0,
-                   refine=0, stats=None, want_idx=True, swap_perm=None, prefetch=None):
+                   refine=0, stats=None, want_idx=True, swap_perm=None, prefetch=None, ema=None, alpha=None,
+                   alpha_from_device=False):
     """K1 with the per-joint part of K2 fused into its epilogue (maps [V,B,J,H,W], V <= 32).
     One teacher (V = K views):
       mode 1: + mean [B,J,2], dist [B,J] f64 (999 = illegal), legal [B,J]   (utils/evaluation.py:44-54)
@@ -129,7 +130,11 @@ def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stri
       mode 3: mean = float32 ensemble coordinate, dist = extDist, legal, zero_div (utils/business.py:109-161)
       mode 4: + the fixed rule on extDist, gate and counts as in mode 2.
     prefetch: a contiguous tensor the next kernel reads (the student maps of K3): warps that run out of maps pull it
-    into L2 while the last maps finish.  The returned `status` (int32[1], device) is non-zero when a hand-off word of
+    into L2 while the last maps finish.
+    ema (an EmaPlan) + alpha: K4 inside the same launch (ubpl_warp_decode_k2_ema) -- the warps that have run out of maps
+    do the mean-teacher EMA while the last maps are decoded; alpha_from_device=True reads {alpha, 1-alpha} from the
+    plan's device buffer (EmaPlan.set_alpha), which is what a captured CUDA graph needs.
+    The returned `status` (int32[1], device) is non-zero when a hand-off word of
     the epilogue never arrived -- check it with check_status() at a point where a sync is acceptable."""
     _need_cuda(maps, theta, flip, dec, stats)
     if maps.dtype != _f32:
@@ -158,11 +163,15 @@ def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stri
         # at most PF_CAP_MB: what is pulled in must still be in the 126 MB L2 when the next kernel reads it
         cap = int(os.environ.get("UBPL_K1_PF_MB", PF_CAP_MB)) << 20
         pf_ptr, pf_bytes = prefetch.data_ptr(), min(prefetch.numel() * prefetch.element_size(), cap)
-    _lib.call("ubpl_warp_decode_k2", maps.data_ptr(), maps.stride(0), maps.stride(1), maps.stride(2), K, B, J, H, W,
-              theta.data_ptr(), _p(flip), _p(perm), _p(dec), int(refine), _p(out_idx), out_max.data_ptr(),
-              out_xy.data_ptr(), int(mode), float(distThrMax), int(img_h), int(img_w), float(stride), float(sigma),
-              int(S), mean.data_ptr(), dist.data_ptr(), legal.data_ptr(), _p(enable), _p(gate), _p(stats),
-              ws.data_ptr(), ws_bytes, pf_ptr, int(pf_bytes), _stream())
+    args = (maps.data_ptr(), maps.stride(0), maps.stride(1), maps.stride(2), K, B, J, H, W,
+            theta.data_ptr(), _p(flip), _p(perm), _p(dec), int(refine), _p(out_idx), out_max.data_ptr(),
+            out_xy.data_ptr(), int(mode), float(distThrMax), int(img_h), int(img_w), float(stride), float(sigma),
+            int(S), mean.data_ptr(), dist.data_ptr(), legal.data_ptr(), _p(enable), _p(gate), _p(stats),
+            ws.data_ptr(), ws_bytes, pf_ptr, int(pf_bytes))
+    if ema is not None:
+        _lib.call("ubpl_warp_decode_k2_ema", *args, *ema.launch_args(alpha, alpha_from_device), _stream())
+    else:
+        _lib.call("ubpl_warp_decode_k2", *args, _stream())
     return dict(idx=out_idx, max=out_max, xy=out_xy, mean=mean, dist=dist, legal=legal, enable=enable, gate=gate,
                 counts=ws[128:128 + J + 1], count=ws[128 + J + 1:128 + J + 2], zero_div=ws[34:35], status=ws[35:36],
                 ws=ws)
@@ -830,9 +839,8 @@ class EmaPlan:
         self.alpha_buf.copy_(vals, non_blocking=False)
         self.alpha = float(alpha)
 
-    def step(self, alpha, from_device=False):
-        """ema <- ema*alpha + (1-alpha)*param over every tensor, one launch.  from_device=True: alpha is read from the
-        device buffer written by set_alpha (the scalar argument is then only the fallback when no buffer exists)."""
+    def launch_args(self, alpha, from_device=False):
+        """The EMA arguments shared by ubpl_ema_multi_tensor and ubpl_warp_decode_k2_ema (tables, chunking, alpha)."""
         if self._ptr_key() != self._key:
             self._build()
         import numpy as np
@@ -843,9 +851,13 @@ class EmaPlan:
             if getattr(self, "alpha_buf", None) is None:
                 self.set_alpha(alpha)
             adev = self.alpha_buf.data_ptr()
-        _lib.call("ubpl_ema_multi_tensor", self.ema_ptrs.data_ptr(), self.param_ptrs.data_ptr(), self.numels.data_ptr(),
-                  self.chunk_tensor.data_ptr(), self.chunk_start.data_ptr(), self.n_chunks, self.CHUNK, a, oma, adev,
-                  _stream())
+        return (self.ema_ptrs.data_ptr(), self.param_ptrs.data_ptr(), self.numels.data_ptr(), self.chunk_tensor.data_ptr(),
+                self.chunk_start.data_ptr(), self.n_chunks, self.CHUNK, a, oma, adev)
+
+    def step(self, alpha, from_device=False):
+        """ema <- ema*alpha + (1-alpha)*param over every tensor, one launch.  from_device=True: alpha is read from the
+        device buffer written by set_alpha (the scalar argument is then only the fallback when no buffer exists)."""
+        _lib.call("ubpl_ema_multi_tensor", *self.launch_args(alpha, from_device), _stream())
 
 
 def ema_flat(ema, param, alpha):

@@ -46,10 +46,12 @@ def nega_weights(islabeled, pseudoWeight):
                        torch.full((), float(pseudoWeight), device=islabeled.device)).to(torch.float32)
 
 
-def stage_k1(st, stats=None, cfg=None):
+def stage_k1(st, stats=None, cfg=None, ema=None, alpha=None):
     """K1: back-warp + flip + arg-max decode of every (model, view) map, each read from HBM once.  With one
     teacher (and cfg.fuse_k12) the per-joint dispersion -- and on the fixed path the whole selection -- is
-    computed by the warp that decodes the last view of a joint, inside the same launch."""
+    computed by the warp that decodes the last view of a joint, inside the same launch.  ema (an ops.EmaPlan,
+    alpha read from its device buffer): K4 inside the same launch, done by the warps that have run out of maps
+    (fused path only; returns st["ema_done"] = True when the EMA went along)."""
     teacher, theta, flip, dec = st["teacher"], st["theta"], st["flip"], st["dec"]
     M, K, B, J, H, W = teacher.shape
     st.pop("k12", None)
@@ -68,10 +70,13 @@ def stage_k1(st, stats=None, cfg=None):
             fl = flip.unsqueeze(0).expand(M, K, B).reshape(M * K, B)
         r = ops.warp_decode_k2(maps, th, fl, dec, mode, S=S, img_h=int(sH * cfg.stride), img_w=int(sW * cfg.stride),
                                stride=cfg.stride, sigma=cfg.sigma, distThrMax=cfg.distThrMax, stats=stats,
-                               swap_perm=cfg.swap_perm, prefetch=st["student"] if cfg.prefetch_student else None)
+                               swap_perm=cfg.swap_perm, prefetch=st["student"] if cfg.prefetch_student else None,
+                               ema=ema, alpha=alpha, alpha_from_device=ema is not None)
         st["xy"], st["max"], st["idx"] = r["xy"].view(M, K, B, J, 2), r["max"].view(M, K, B, J), r["idx"].view(M, K, B, J)
         st["k12"] = r
+        st["ema_done"] = ema is not None
         return st
+    st["ema_done"] = False
     perm = cfg.swap_perm if cfg is not None else None
     if flat:
         dec_out = ops.warp_decode(teacher.view(M * K, B, J, H, W) if teacher.is_contiguous() else
@@ -226,14 +231,17 @@ class GraphedStep:
         torch.cuda.synchronize()
         pool = None
         self.eager = {}
-        # overlap_ema: True / "k1" = K4 forked beside K1 (K1 is latency-bound, the EMA's HBM traffic fits beside it),
+        # overlap_ema: True / "tail" = K4 INSIDE K1's launch (ubpl_warp_decode_k2_ema): the warps that have run out of maps do
+        # the EMA while the last maps are decoded (the fused K1+K2 path only; otherwise K4 follows K1 on the same
+        # stream); "k1" = K4 forked onto a side stream beside K1 (it then runs in front of K1: K1's CTAs do not
+        # share an SM with other kernels),
         # "k2" = beside the quantile selector (a one-CTA kernel), "k3" = beside K3, False = after K3
         if overlap_ema == "slow":                         # round-1 name: K1 no longer has a second launch
             overlap_ema = "k1"
-        self.overlap_ema = (overlap_ema if overlap_ema in ("k2", "k3") else "k1") if (overlap_ema and ema is not None) else False
+        self.overlap_ema = (overlap_ema if overlap_ema in ("k1", "k2", "k3") else "tail") if (overlap_ema and ema is not None) else False
         if self.overlap_ema == "k2" and cfg.select != "quantile":
-            self.overlap_ema = "k1"                       # the fixed path has no K2 launch to hide behind
-        self._side = torch.cuda.Stream() if self.overlap_ema else None
+            self.overlap_ema = "tail"                     # the fixed path has no K2 launch to hide behind
+        self._side = torch.cuda.Stream() if (self.overlap_ema and self.overlap_ema != "tail") else None
         self.events = {}
         if ema is not None:
             ema.set_alpha(alpha)                          # the captured EMA launch reads alpha from device memory
@@ -263,6 +271,10 @@ class GraphedStep:
         def k1_fn():
             if self.overlap_ema == "k1":
                 forked(lambda: stage_k1(self.state, stats, cfg))
+            elif self.overlap_ema == "tail":
+                stage_k1(self.state, stats, cfg, ema=self.ema, alpha=self.alpha)
+                if not self.state.get("ema_done"):
+                    self._ema()
             else:
                 stage_k1(self.state, stats, cfg)
 
