@@ -499,3 +499,21 @@ def test_graphed_step_with_ema_in_k1_tail(ops):
             for k in ("idx", "max", "xy", "enable", "gate", "grad", "target", "summary", "grad_scale", "count"):
                 assert torch.equal(st[k].reshape(-1), ref[k].reshape(-1)), (select, k)
             assert np.array_equal(npy(e), O.ema_update(before, npy(p), alpha)), (select, alpha)
+
+
+@pytest.mark.parametrize("M,select", [(1, "fixed"), (2, "quantile")])
+def test_eager_step_with_ema(ops, M, select):
+    """pseudo_label_step(ema=plan, alpha=a): same chain outputs, the EMA applied once with `a` (by value: no sync)."""
+    from ubpl_b200 import synth, pipeline
+    d = synth.make_batch(B=8, K=4, J=6, M=M, S=2, seed=21, jitter=0.5, device="cuda")
+    dec = ops.decode_coeffs(d["center"], d["scale"], [64, 64])
+    w = pipeline.nega_weights(d["islabeled"], 1.0)
+    cfg = pipeline.StepConfig(select=select, distThrMax=2.0)
+    e = torch.randn(30001, device="cuda"); p = torch.randn(30001, device="cuda")
+    before = npy(e).copy()
+    ref = pipeline.pseudo_label_step(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg)
+    st = pipeline.pseudo_label_step(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, ema=ops.EmaPlan([p], [e]), alpha=0.8)
+    torch.cuda.synchronize()
+    for k in ("idx", "max", "xy", "enable", "gate", "grad", "target", "summary", "grad_scale", "count"):
+        assert torch.equal(st[k].reshape(-1), ref[k].reshape(-1)), k
+    assert np.array_equal(npy(e), O.ema_update(before, npy(p), 0.8))

@@ -23,8 +23,7 @@ emas = [torch.randn(*s, device="cuda") * 0.02 for s in shapes]
 plan = ops.EmaPlan(params, emas)
 stats = torch.zeros(4, dtype=torch.int64, device="cuda")
 for _ in range(steps):
-    r = pipeline.pseudo_label_step(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, stats=stats)
-    plan.step(0.75)
+    r = pipeline.pseudo_label_step(d["teacher"], d["student"], d["theta"], d["flip"], dec, w, cfg, stats=stats, ema=plan, alpha=0.75)
 torch.cuda.synchronize()
 s = stats.tolist()
 print("maps", s[2], "exhaustive", s[0], "evaluated px per map", s[1] / max(1, s[2]), "loss", float(r["summary"][0]) * float(r["grad_scale"]))

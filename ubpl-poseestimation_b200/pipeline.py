@@ -46,12 +46,12 @@ def nega_weights(islabeled, pseudoWeight):
                        torch.full((), float(pseudoWeight), device=islabeled.device)).to(torch.float32)
 
 
-def stage_k1(st, stats=None, cfg=None, ema=None, alpha=None):
+def stage_k1(st, stats=None, cfg=None, ema=None, alpha=None, alpha_from_device=True):
     """K1: back-warp + flip + arg-max decode of every (model, view) map, each read from HBM once.  With one
     teacher (and cfg.fuse_k12) the per-joint dispersion -- and on the fixed path the whole selection -- is
-    computed by the warp that decodes the last view of a joint, inside the same launch.  ema (an ops.EmaPlan,
-    alpha read from its device buffer): K4 inside the same launch, done by the warps that have run out of maps
-    (fused path only; returns st["ema_done"] = True when the EMA went along)."""
+    computed by the warp that decodes the last view of a joint, inside the same launch.  ema (an ops.EmaPlan; alpha
+    read from its device buffer unless alpha_from_device=False): K4 inside the same launch, done by the warps that
+    have run out of maps (fused path only; st["ema_done"] = True when the EMA went along)."""
     teacher, theta, flip, dec = st["teacher"], st["theta"], st["flip"], st["dec"]
     M, K, B, J, H, W = teacher.shape
     st.pop("k12", None)
@@ -71,7 +71,7 @@ def stage_k1(st, stats=None, cfg=None, ema=None, alpha=None):
         r = ops.warp_decode_k2(maps, th, fl, dec, mode, S=S, img_h=int(sH * cfg.stride), img_w=int(sW * cfg.stride),
                                stride=cfg.stride, sigma=cfg.sigma, distThrMax=cfg.distThrMax, stats=stats,
                                swap_perm=cfg.swap_perm, prefetch=st["student"] if cfg.prefetch_student else None,
-                               ema=ema, alpha=alpha, alpha_from_device=ema is not None)
+                               ema=ema, alpha=alpha, alpha_from_device=alpha_from_device and ema is not None)
         st["xy"], st["max"], st["idx"] = r["xy"].view(M, K, B, J, 2), r["max"].view(M, K, B, J), r["idx"].view(M, K, B, J)
         st["k12"] = r
         st["ema_done"] = ema is not None
@@ -171,16 +171,23 @@ def stage_k3(st, cfg):
 
 
 def pseudo_label_step(teacher, student, theta, flip, dec, sample_w, cfg: StepConfig, group=None, stats=None,
-                      timer=None):
+                      timer=None, ema=None, alpha=None):
     """teacher [M,K,B,J,H,W] (last-stack teacher maps of the K augmented views), student
     [B,S,J,H,W], theta [K,B,2,3], flip [K,B], dec [B,4] (ops.decode_coeffs), sample_w [B].
     Returns a dict of DEVICE tensors: summary float64[4] = (loss_sum, #loss>0, #mask>0, #gate>0),
     grad_scale, count, grad, target, gate, kps, enable, dist, decode outputs.  The scalar loss of
-    MT_UBPL.py:266 is summary[0] * grad_scale.  No host synchronisation anywhere."""
+    MT_UBPL.py:266 is summary[0] * grad_scale.  No host synchronisation anywhere.
+    ema (an ops.EmaPlan) + alpha: the step's mean-teacher update (utils/parameters.py:4-8) goes along -- inside K1's
+    launch on the fused path (the warps that run out of maps do it), as a launch of its own behind K1 otherwise."""
     mark = timer if timer is not None else (lambda name: None)
     st = dict(teacher=teacher, student=student, theta=theta, flip=flip, dec=dec, sample_w=sample_w)
     mark("k1_0")
-    stage_k1(st, stats, cfg)
+    if ema is not None:
+        stage_k1(st, stats, cfg, ema=ema, alpha=alpha, alpha_from_device=False)
+        if not st.get("ema_done"):
+            ema.step(alpha)
+    else:
+        stage_k1(st, stats, cfg)
     mark("k1_1")
     stage_k2(st, cfg, group)
     mark("k3_0")
