@@ -25,8 +25,8 @@ except Exception as e:
 PY
 done
 # launch list (shares of the step; serialised and cold under ncu) and one full capture of the step's kernels
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_c2.csv \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_launches_ncu.log 2>&1; echo "launch list rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"ubpl|warp_decode|render_mse|ema_|dense_mse|select_|k2_" -c 400 --csv \
+    --log-file gpurun_out/${tag}_launches_c2.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_launches_ncu.log 2>&1; echo "launch list rc=$?"
 python tools/prof_step.py c2 4 > gpurun_out/${tag}_prof_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"warp_decode_kernel|render_mse_kernel" -s 4 -c 2 \
     -o gpurun_out/${tag}_k1_k3_full python tools/prof_step.py c2 4 > gpurun_out/${tag}_prof_ncu.log 2>&1; echo "ncu rc=$?"
