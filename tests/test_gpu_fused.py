@@ -517,3 +517,43 @@ def test_eager_step_with_ema(ops, M, select):
     for k in ("idx", "max", "xy", "enable", "gate", "grad", "target", "summary", "grad_scale", "count"):
         assert torch.equal(st[k].reshape(-1), ref[k].reshape(-1)), k
     assert np.array_equal(npy(e), O.ema_update(before, npy(p), 0.8))
+
+
+@pytest.mark.parametrize("hw", [(64, 64), (48, 80)])
+def test_k1_border_pixels_vs_oracle(ops, hw):
+    """Maps whose warped maximum is not positive and whose frame pokes out of the source map (zero padding at the ends
+    of the rows) -- the cases K1 solves geometrically, prunes with the all-inside bound, or decodes exhaustively.
+    Non-positive noise, non-positive smooth bumps, an exact-zero plateau, low-contrast negatives and maps sprinkled
+    with zeros, under random rotations / scales / shifts; indices, values (the sign of a zero too) and coordinates
+    bit-exact against the oracle."""
+    H, W = hw
+    rng = np.random.default_rng(77)
+    V, B, J = 6, 8, 5
+    maps = np.empty((V, B, J, H, W), np.float32)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    for v in range(V):
+        for b in range(B):
+            maps[v, b, 0] = -np.abs(rng.standard_normal((H, W))).astype(np.float32) - 1e-3          # negative noise
+            cx, cy = rng.uniform(0, W), rng.uniform(0, H)
+            maps[v, b, 1] = -1.0 + 0.9 * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / 18.0)            # negative bump
+            maps[v, b, 2] = np.minimum(maps[v, b, 1] + 0.2, 0.0)                                      # zero plateau
+            maps[v, b, 3] = (rng.standard_normal((H, W)) * 0.1 - 0.5).astype(np.float32)              # negative, low contrast
+            maps[v, b, 4] = -np.abs(rng.standard_normal((H, W))).astype(np.float32) * (rng.random((H, W)) < 0.9)  # zeros sprinkled
+    ang = rng.uniform(-0.6, 0.6, (V, B)); sc = rng.uniform(0.75, 1.15, (V, B))
+    th = np.zeros((V, B, 2, 3), np.float32)
+    th[..., 0, 0] = sc * np.cos(ang); th[..., 0, 1] = -sc * np.sin(ang); th[..., 0, 2] = rng.uniform(-0.2, 0.2, (V, B))
+    th[..., 1, 0] = sc * np.sin(ang); th[..., 1, 1] = sc * np.cos(ang); th[..., 1, 2] = rng.uniform(-0.2, 0.2, (V, B))
+    fl = (rng.random((V, B)) < 0.5).astype(np.uint8)
+    center = np.full((B, 2), 128.0, np.float32)
+    scale = np.full((B,), 1.28, np.float32)
+    back = np.stack([O.affine_back2(maps[v], th[v], fl[v]) for v in range(V)])
+    val, idx = O.argmax_first(back)
+    xy = np.stack([O.final_preds(back[v], center, scale, [H, W], "f32") for v in range(V)])
+    dec = ops.decode_coeffs(torch.as_tensor(center), torch.as_tensor(scale), [H, W]).cuda()
+    stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    r = ops.warp_decode(cu(maps), cu(th), cu(fl), dec, stats=stats)
+    assert np.array_equal(npy(r["idx"]).astype(np.int64), idx)
+    assert np.array_equal(npy(r["max"]), val)
+    assert np.array_equal(np.signbit(npy(r["max"])), np.signbit(val))         # the sign of a zero maximum too
+    assert np.array_equal(npy(r["xy"]), xy)
+    assert int(stats[2]) == V * B * J
