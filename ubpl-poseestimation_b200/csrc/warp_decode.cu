@@ -895,7 +895,11 @@ __device__ __forceinline__ void decode_pruned(const WDParams& p, const float* __
 // One warp per heat-map, maps claimed from a global counter, each staged in the warp's shared-memory buffer by
 // a 1-D bulk async copy (TMA engine); the next copy starts when the map is finished.
 // TL: the %globaltimer probe of UBPL_K1_DBG=16 is compiled in (its accumulators cost registers).
-template <bool TL>
+// EMA: the idle phase can do the mean-teacher EMA (TailEma).  A separate instance because the mere presence of that
+// code costs the decode loop 2-4 % (measured A/B on c2 / c3 / c5 with the EMA never executed: 98.2 -> 100.3 us,
+// 52.0 -> 53.7 us, 1714 -> 1779 us; same registers, no spills -- code placement): launches without an EMA keep the
+// instance that does not have it.
+template <bool TL, bool EMA>
 __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1123,7 +1127,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     if (lane == 0) atomicAdd(&cj->warps_done, 1);
     constexpr unsigned kPfChunk = 32768u;
     bool pf_live = p.pf_ptr != nullptr;
-    bool ema_live = p.ema.n_chunks > 0;
+    bool ema_live = EMA && p.ema.n_chunks > 0;
     const int ema_pieces = (p.ema.chunk_elems + kEmaPiece - 1) / kEmaPiece;
     const unsigned ema_total = (unsigned)p.ema.n_chunks * (unsigned)ema_pieces;
     float ea = p.ema.a, eoma = p.ema.oma;
@@ -1268,15 +1272,17 @@ static int launch_k1(WDParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)warps * buf_stride + tail;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(warp_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(warp_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+    cudaError_t e = cudaFuncSetAttribute(warp_decode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(warp_decode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(warp_decode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
     if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
     attr_set = true;
   }
   long long need = (N + warps - 1) / warps;
   int grid = (int)(need < sm_count() ? need : sm_count());
-  if ((p.dbg & 16) && p.stats) warp_decode_kernel<true><<<grid, warps * 32, smem, stream>>>(p);
-  else warp_decode_kernel<false><<<grid, warps * 32, smem, stream>>>(p);
+  if ((p.dbg & 16) && p.stats) warp_decode_kernel<true, true><<<grid, warps * 32, smem, stream>>>(p);
+  else if (p.ema.n_chunks > 0) warp_decode_kernel<false, true><<<grid, warps * 32, smem, stream>>>(p);
+  else warp_decode_kernel<false, false><<<grid, warps * 32, smem, stream>>>(p);
   return check_launch("ubpl_warp_decode");
 }
 
@@ -1353,9 +1359,18 @@ static int warp_decode_k2_impl(const float* maps, int64_t sV, int64_t sB, int64_
   }
   WDParams p;
   memset(&p, 0, sizeof(p));
+  // The EMA rides in this launch when the launch is short enough for that to pay: the kernel instance that can do the
+  // EMA decodes 2-4 % slower (see warp_decode_kernel), a launch of its own costs the EMA ~10 us more than K1's tail
+  // does -- break-even around 1.9 GB of maps.  Above 1.5 GB (UBPL_K1_EMA_MAX_MB) the EMA follows as its own launch.
+  bool ema_after = false;
   if (ema && ema->n_chunks > 0) {
-    p.ema = *ema;
-    p.ema.next = reinterpret_cast<unsigned long long*>(ws + 64);    // its own 128-byte line, cleared by the memset above
+    const long long max_mb = env_int("UBPL_K1_EMA_MAX_MB", 1536);
+    if (N * (long long)H * W * 4 <= (max_mb << 20)) {
+      p.ema = *ema;
+      p.ema.next = reinterpret_cast<unsigned long long*>(ws + 64);    // its own 128-byte line, cleared by the memset above
+    } else {
+      ema_after = true;
+    }
   }
   p.maps = maps; p.sV = sV; p.sB = sB; p.sJ = sJ; p.V = V; p.B = B; p.J = J; p.H = H; p.W = W;
   p.theta = theta; p.flip = flip; p.swap_perm = flip ? swap_perm : nullptr; p.dec = dec; p.do_warp = 1; p.refine = refine;
@@ -1381,7 +1396,12 @@ static int warp_decode_k2_impl(const float* maps, int64_t sV, int64_t sB, int64_
   f.mean = mean; f.dist = dist; f.legal = legal; f.enable = enable; f.gate = gate;
   int rc = pow_table(&f.T.key, &f.T.val, &f.T.bits, &f.T.n, &f.T.rmax);
   if (rc != UBPL_OK) return rc;
-  return launch_k1(p, (cudaStream_t)stream);
+  rc = launch_k1(p, (cudaStream_t)stream);
+  if (rc == UBPL_OK && ema_after)
+    rc = ubpl_ema_multi_tensor(ema->ema_ptrs, ema->param_ptrs, reinterpret_cast<const int64_t*>(ema->numels), ema->chunk_tensor,
+                               reinterpret_cast<const int64_t*>(ema->chunk_start), ema->n_chunks, ema->chunk_elems, ema->a,
+                               ema->oma, ema->alpha_dev, stream);
+  return rc;
 }
 
 extern "C" int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ, int V, int B, int J, int H,

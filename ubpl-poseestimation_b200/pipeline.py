@@ -178,7 +178,9 @@ def pseudo_label_step(teacher, student, theta, flip, dec, sample_w, cfg: StepCon
     grad_scale, count, grad, target, gate, kps, enable, dist, decode outputs.  The scalar loss of
     MT_UBPL.py:266 is summary[0] * grad_scale.  No host synchronisation anywhere.
     ema (an ops.EmaPlan) + alpha: the step's mean-teacher update (utils/parameters.py:4-8) goes along -- inside K1's
-    launch on the fused path (the warps that run out of maps do it), as a launch of its own behind K1 otherwise."""
+    launch on the fused path (the warps that run out of maps do it), as a launch of its own behind K1 otherwise.
+    Mind the order: the reference updates the teacher after optimizer.step(), before the next forward pass; an update
+    that rides in this call lands after the forward passes that produced `teacher` / `student`."""
     mark = timer if timer is not None else (lambda name: None)
     st = dict(teacher=teacher, student=student, theta=theta, flip=flip, dec=dec, sample_w=sample_w)
     mark("k1_0")
