@@ -145,11 +145,8 @@ __device__ __forceinline__ float lin_coord(int k, int n, float step) {
   return (k < (n >> 1)) ? __fmaf_rn(step, (float)k, -1.f) : __fmaf_rn(-step, (float)(n - 1 - k), 1.f);
 }
 
-// Bilinear sample at the normalised base-grid coordinates (xl, yl) of one output pixel from the source map
-// s[H*W]: ATen's op order, zero padding.
-__device__ __forceinline__ float eval_at(const float* __restrict__ s, const Xform& X, float xl, float yl) {
-  const float gx = __fadd_rn(__fmaf_rn(yl, X.t01, __fmul_rn(xl, X.t00)), X.t02);
-  const float gy = __fadd_rn(__fmaf_rn(yl, X.t11, __fmul_rn(xl, X.t10)), X.t12);
+// Bilinear sample at the normalised grid coordinates (gx, gy): ATen's op order, zero padding.
+__device__ __forceinline__ float sample_at(const float* __restrict__ s, const Xform& X, float gx, float gy) {
   const float ix = __fmul_rn(__fadd_rn(gx, 1.f), X.sfx);
   const float iy = __fmul_rn(__fadd_rn(gy, 1.f), X.sfy);
   const float x0f = floorf(ix), y0f = floorf(iy);
@@ -170,6 +167,20 @@ __device__ __forceinline__ float eval_at(const float* __restrict__ s, const Xfor
   acc = __fmaf_rn(v_sw, sw, acc);
   acc = __fmaf_rn(v_se, se, acc);
   return acc;
+}
+// Bilinear sample at the normalised base-grid coordinates (xl, yl) of one output pixel from the source map
+// s[H*W]: ATen's op order, zero padding.
+__device__ __forceinline__ float eval_at(const float* __restrict__ s, const Xform& X, float xl, float yl) {
+  const float gx = __fadd_rn(__fmaf_rn(yl, X.t01, __fmul_rn(xl, X.t00)), X.t02);
+  const float gy = __fadd_rn(__fmaf_rn(yl, X.t11, __fmul_rn(xl, X.t10)), X.t12);
+  return sample_at(s, X, gx, gy);
+}
+// The same with the column's products ax = xl * t00, ay = xl * t10 formed once per column (separately rounded
+// products, so the bits are those of eval_at).
+__device__ __forceinline__ float eval_col(const float* __restrict__ s, const Xform& X, float ax, float ay, float yl) {
+  const float gx = __fadd_rn(__fmaf_rn(yl, X.t01, ax), X.t02);
+  const float gy = __fadd_rn(__fmaf_rn(yl, X.t11, ay), X.t12);
+  return sample_at(s, X, gx, gy);
 }
 
 // Exact bilinear sample of output pixel (row i, column jw in the WARPED frame, i.e. before the
@@ -1196,17 +1207,36 @@ __global__ void __launch_bounds__(256) warp_materialize_kernel(const float* __re
     load_xform(X, theta, flip, n, H, W);
     grid_consts(X, H, W);
     if (vec) {
-      // four consecutive output pixels of a row per thread (the row term of the grid is shared), one 128-bit store
+      // four consecutive output pixels of a row per thread, one 128-bit store.  When the CTA covers whole rows per sweep
+      // (blockDim % (W/4) == 0) a thread keeps its four columns for the whole map: their base-grid coordinates and the
+      // products with t00 / t10 are formed once (12 registers) and a pixel costs its row term plus the sample
       const int w4 = W >> 2;
-      for (int q = threadIdx.x; q < (HW >> 2); q += blockDim.x) {
-        const int i = q / w4, jo = (q - i * w4) << 2;
-        const float yl = lin_coord(i, H, X.stepy);
-        float4 o;
-        o.x = eval_at(sm, X, lin_coord(X.flip ? (W - 1 - jo) : jo, W, X.stepx), yl);
-        o.y = eval_at(sm, X, lin_coord(X.flip ? (W - 2 - jo) : jo + 1, W, X.stepx), yl);
-        o.z = eval_at(sm, X, lin_coord(X.flip ? (W - 3 - jo) : jo + 2, W, X.stepx), yl);
-        o.w = eval_at(sm, X, lin_coord(X.flip ? (W - 4 - jo) : jo + 3, W, X.stepx), yl);
-        stg_stream(reinterpret_cast<float4*>(dst) + q, o);
+      if ((int)blockDim.x % w4 == 0) {
+        const int rows = (int)blockDim.x / w4, i0 = (int)threadIdx.x / w4, jo = ((int)threadIdx.x - i0 * w4) << 2;
+        float ax[4], ay[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float xl = lin_coord(X.flip ? (W - 1 - u - jo) : jo + u, W, X.stepx);
+          ax[u] = __fmul_rn(xl, X.t00); ay[u] = __fmul_rn(xl, X.t10);
+        }
+        for (int i = i0; i < H; i += rows) {
+          const float yl = lin_coord(i, H, X.stepy);
+          float4 o;
+          o.x = eval_col(sm, X, ax[0], ay[0], yl); o.y = eval_col(sm, X, ax[1], ay[1], yl);
+          o.z = eval_col(sm, X, ax[2], ay[2], yl); o.w = eval_col(sm, X, ax[3], ay[3], yl);
+          stg_stream(reinterpret_cast<float4*>(dst) + i * w4 + (jo >> 2), o);
+        }
+      } else {
+        for (int q = threadIdx.x; q < (HW >> 2); q += blockDim.x) {
+          const int i = q / w4, jo = (q - i * w4) << 2;
+          const float yl = lin_coord(i, H, X.stepy);
+          float4 o;
+          o.x = eval_at(sm, X, lin_coord(X.flip ? (W - 1 - jo) : jo, W, X.stepx), yl);
+          o.y = eval_at(sm, X, lin_coord(X.flip ? (W - 2 - jo) : jo + 1, W, X.stepx), yl);
+          o.z = eval_at(sm, X, lin_coord(X.flip ? (W - 3 - jo) : jo + 2, W, X.stepx), yl);
+          o.w = eval_at(sm, X, lin_coord(X.flip ? (W - 4 - jo) : jo + 3, W, X.stepx), yl);
+          stg_stream(reinterpret_cast<float4*>(dst) + q, o);
+        }
       }
     } else {
       for (int k = threadIdx.x; k < HW; k += blockDim.x) {
