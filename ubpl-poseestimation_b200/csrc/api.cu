@@ -140,7 +140,7 @@ unsigned long long* work_counter(cudaStream_t stream) {
 }  // namespace ubpl
 
 extern "C" const char* ubpl_last_error(void) { return ubpl::g_err; }
-extern "C" int ubpl_version(void) { return 101; }
+extern "C" int ubpl_version(void) { return 202; }   // round 2, second ABI addition (ubpl_warp_decode_k2_ema)
 extern "C" int ubpl_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_optin_bytes) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
