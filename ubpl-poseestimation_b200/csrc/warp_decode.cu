@@ -117,6 +117,13 @@ struct WDParams {
   TailEma ema;                // optional K4 done by the warps that have run out of maps
 };
 
+// FAST (template): the kernel instance for the call the fused chain makes -- warp on, maps staged by bulk copies, no
+// quarter-offset refinement, no joint swap, no heat-map-space coordinates, no timing masks.  With these decided at
+// compile time the decode loop is 5-8 % faster (c2 98.8 -> 93.5 us, c4 195 -> 184 us, c5 1713 -> 1574 us): the code is
+// a third shorter and -- without the refinement in the epilogue -- the map's transform is dead after the decode.
+// Every other call takes the generic instance, where the same fields are read at run time.
+#define UBPL_F(expr, constant) (FAST ? (constant) : (expr))
+
 struct Xform {
   float t00, t01, t02, t10, t11, t12;
   float stepx, stepy, sfx, sfy;
@@ -471,16 +478,18 @@ __device__ __forceinline__ void scan_max(const float* s, int HW, int lane, float
 
 // Source channel of output joint j of (view, sample) vb: the joint itself, or its left/right partner when
 // the view is flipped and a swap table is given.
+template <bool FAST>
 __device__ __forceinline__ unsigned src_joint(const WDParams& p, unsigned vb, unsigned j) {
-  if (p.swap_perm && p.flip && p.flip[vb]) return (unsigned)p.swap_perm[j];
+  if (UBPL_F(p.swap_perm, (const int32_t*)nullptr) && p.flip && p.flip[vb]) return (unsigned)p.swap_perm[j];
   return j;
 }
 
+template <bool FAST>
 __device__ __forceinline__ const float* map_src(const WDParams& p, long long n) {
   unsigned vb, j, v, b;
   p.divJ.divmod((unsigned)n, vb, j);
   p.divB.divmod(vb, v, b);
-  j = src_joint(p, vb, j);
+  j = src_joint<FAST>(p, vb, j);
   return p.maps + (long long)v * p.sV + (long long)b * p.sB + (long long)j * p.sJ;
 }
 
@@ -510,9 +519,10 @@ __device__ __forceinline__ long long claim_map(const WDParams& p, CoopJob* cj) {
 // Called by lane 0.  With a cap, first takes a ticket and waits until fewer than `cap` of the CTA's copies are in
 // flight (the waiter of a copy counts it as landed); the other lanes of the warp wait at the next warp-wide
 // operation meanwhile.
+template <bool FAST>
 __device__ __forceinline__ void issue_map(const WDParams& p, long long n, float* dst, uint64_t* bar, uint64_t pol,
                                           uint32_t bytes, CoopJob* cj) {
-  const float* src = map_src(p, n);
+  const float* src = map_src<FAST>(p, n);
   if (p.inflight_cap > 0) {
     const unsigned t = atomicAdd(&cj->issued, 1u);
     while ((int)(t - *reinterpret_cast<volatile unsigned*>(&cj->landed)) >= p.inflight_cap) __nanosleep(64);
@@ -676,6 +686,7 @@ __device__ __forceinline__ void k2_item_dual(const WDParams& p, long long item, 
 
 // Epilogue of one map (warp-wide call): arg-max -> heat-map coordinates (mask, optional quarter-offset
 // refinement) -> image-space coordinates -> outputs -> (optional) arrival at the item's K2.
+template <bool FAST>
 __device__ __forceinline__ void finish_map(const WDParams& p, long long n, int v, int b, int j, const float* s, const Xform& X,
                                            const float* lx, const float* ly, float rv, int ri, double dc0, double dc1,
                                            double dc2, double dc3, int lane, long long& pend_item, unsigned& pend_old) {
@@ -686,7 +697,8 @@ __device__ __forceinline__ void finish_map(const WDParams& p, long long n, int v
   float hx = 0.f, hy = 0.f;
   const bool keep = rv > 0.f;                          // maxval.gt(0): NaN -> masked
   if (keep) { hx = (float)(ax + 1); hy = (float)(ay + 1); }
-  const bool do_ref = (p.refine == 2) || (p.refine == 1 && j < 2);
+  const int refine = UBPL_F(p.refine, 0);
+  const bool do_ref = (refine == 2) || (refine == 1 && j < 2);
   if (do_ref) {
     // process.py:366-371: 1 < px < res[0] and 1 < py < res[1] on the 1-based coordinates
     if (keep && ax >= 1 && ax <= W - 2 && ay >= 1 && ay <= H - 2) {
@@ -695,7 +707,7 @@ __device__ __forceinline__ void finish_map(const WDParams& p, long long n, int v
         const int di = (lane == 2) ? 1 : (lane == 3 ? -1 : 0);
         const int dj = (lane == 0) ? 1 : (lane == 1 ? -1 : 0);
         const int i = ay + di, jo = ax + dj;
-        nb = p.do_warp ? eval_tab(s, X, lx, ly, i, X.flip ? (W - 1 - jo) : jo) : s[i * W + jo];
+        nb = UBPL_F(p.do_warp, 1) ? eval_tab(s, X, lx, ly, i, X.flip ? (W - 1 - jo) : jo) : s[i * W + jo];
       }
       const float xp = __shfl_sync(0xffffffffu, nb, 0), xm = __shfl_sync(0xffffffffu, nb, 1);
       const float yp = __shfl_sync(0xffffffffu, nb, 2), ym = __shfl_sync(0xffffffffu, nb, 3);
@@ -704,12 +716,12 @@ __device__ __forceinline__ void finish_map(const WDParams& p, long long n, int v
       hy += (dy > 0.f) ? 0.25f : ((dy < 0.f) ? -0.25f : 0.f);
     }
   }
-  if (p.refine != 0) { hx += 0.5f; hy += 0.5f; }      // process.py:372 (+0.5 for every joint)
+  if (refine != 0) { hx += 0.5f; hy += 0.5f; }        // process.py:372 (+0.5 for every joint)
   float ox = hx, oy = hy;
   if (lane == 0) {
     if (p.out_idx) p.out_idx[n] = ri;
     if (p.out_max) p.out_max[n] = rv;
-    if (p.out_hm_xy) { p.out_hm_xy[2 * n] = hx; p.out_hm_xy[2 * n + 1] = hy; }
+    if (UBPL_F(p.out_hm_xy, (float*)nullptr)) { p.out_hm_xy[2 * n] = hx; p.out_hm_xy[2 * n + 1] = hy; }
     if (p.out_xy) {
       if (p.dec) {
         // np.dot row: (a00*(x-1) + 0*(y-1)) + a02, astype(int) truncation, +1
@@ -910,9 +922,10 @@ __device__ __forceinline__ void decode_pruned(const WDParams& p, const float* __
 // code costs the decode loop 2-4 % (measured A/B on c2 / c3 / c5 with the EMA never executed: 98.2 -> 100.3 us,
 // 52.0 -> 53.7 us, 1714 -> 1779 us; same registers, no spills -- code placement): launches without an EMA keep the
 // instance that does not have it.
-template <bool TL, bool EMA>
+template <bool TL, bool EMA, bool FAST>
 __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int do_warp = UBPL_F(p.do_warp, 1), use_bulk = UBPL_F(p.use_bulk, 1), dbg = UBPL_F(p.dbg, 0);
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, W = p.W, HW = H * W;
   const uint32_t map_bytes = (uint32_t)HW * 4u;
@@ -951,7 +964,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     long long nn = 0;
     if (lane == 0) nn = claim_map(p, cj);
     nx.n = (long long)__shfl_sync(0xffffffffu, (unsigned long long)nn, 0);
-    if (nx.n < N && p.do_warp) {
+    if (nx.n < N && do_warp) {
       const unsigned vb = p.divJ.div((unsigned)nx.n);
       // volatile asm: the loads are ISSUED here (a plain load may be sunk to its first use, after the epilogue)
       const float* t = p.theta + (long long)vb * 6;
@@ -966,16 +979,16 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       nx.flip = fl != 0;
     }
   };
-  if (p.use_bulk && lane == 0) {
+  if (use_bulk && lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
     pol = l2_evict_first_policy();
   }
   __syncthreads();
   fetch_next();
-  if (p.use_bulk && lane == 0 && nx.n < N) {
+  if (use_bulk && lane == 0 && nx.n < N) {
     const unsigned long long t0 = tl ? tl_now() : 0ull;
-    issue_map(p, nx.n, buf0, bar, pol, map_bytes, cj);
+    issue_map<FAST>(p, nx.n, buf0, bar, pol, map_bytes, cj);
     if (tl) tl_ticket += tl_now() - t0;
   }
 
@@ -990,7 +1003,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     // an exhaustive job posted by another warp of this CTA: help before this map (whose copy is in flight).  The
     // decision is taken by lane 0 and broadcast: coop_help is a warp-wide call, every lane must take the same branch
     // (the lanes are not necessarily converged here -- lane 0 may come late out of issue_map's wait).
-    if (p.do_warp) {
+    if (do_warp) {
       int open = 0;
       if (lane == 0) open = ld_volatile_s32(&cj->band_next) < kBands ? 1 : 0;
       if (__shfl_sync(0xffffffffu, open, 0)) {
@@ -1014,7 +1027,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     bool bad_xform = false;
     double dc0 = 0.0, dc1 = 0.0, dc2 = 0.0, dc3 = 0.0;
     if (p.dec) { const double* c = p.dec + (size_t)b * 4; dc0 = c[0]; dc1 = c[1]; dc2 = c[2]; dc3 = c[3]; }
-    if (p.do_warp) {
+    if (do_warp) {
       X.t00 = nx.t00; X.t01 = nx.t01; X.t02 = nx.t02; X.t10 = nx.t10; X.t11 = nx.t11; X.t12 = nx.t12; X.flip = nx.flip;
       // pixel-space affine  ix = a*jw + bb*i + c0 ; iy = d*jw + e*i + f0  (approximate, for boxes only)
       const float a = X.t00 * X.stepx * X.sfx, bb = X.t01 * X.stepy * X.sfx;
@@ -1026,7 +1039,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       const float idet = 1.f / det;
       A.C00 = e * idet; A.C01 = -bb * idet; A.C10 = -d * idet; A.C11 = a * idet;
     }
-    if (p.use_bulk) {
+    if (use_bulk) {
       const unsigned long long t0 = tl ? tl_now() : 0ull;
       mbar_wait(bar, (uint32_t)(it & 1));
       if (tl) {
@@ -1036,7 +1049,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       }
       if (p.inflight_cap > 0 && lane == 0) atomicAdd(&cj->landed, 1u);
     } else {
-      const float* gsrc = map_src(p, n);
+      const float* gsrc = map_src<FAST>(p, n);
       for (int k = lane; k < HW; k += 32) buf0[k] = __ldg(gsrc + k);
       __syncwarp();
     }
@@ -1044,7 +1057,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
 
     // ---- pass A: raw max / location / min / finiteness -----------------------------------------
     float bv, mn; int bq;
-    if (p.dbg & 8) { bv = s[lane]; bq = lane >> 2; mn = bv; }
+    if (dbg & 8) { bv = s[lane]; bq = lane >> 2; mn = bv; }
     else scan_max(s, HW, lane, bv, bq, mn);
     A.lane_max = bv;                       // per-lane float4 maximum (pass B reuses it)
     int bi = 0x7fffffff;                  // flat index of the lane's first maximum
@@ -1061,7 +1074,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     const bool nonfinite = __any_sync(0xffffffffu, !(mn >= -FLT_MAX) || !(bv <= FLT_MAX));
     float rv = bv; int ri = bi;           // result (value, canonical flat index)
 
-    if (!p.do_warp) {
+    if (!do_warp) {
       if (nonfinite) {                    // torch.max: the first NaN wins; +-Inf compare normally
         rv = -INFINITY; ri = 0x7fffffff;
         for (int k = lane; k < HW; k += 32) { const float x = s[k]; if (arg_better(x, k, rv, ri)) { rv = x; ri = k; } }
@@ -1074,10 +1087,10 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       if (!exhaustive) {
         warp_argmax_finite(bv, bi);       // warp-uniform source max / location
         A.bv = bv; A.bi = bi;
-        if (p.dbg & 1) { rv = bv; ri = bi; }
+        if (dbg & 1) { rv = bv; ri = bi; }
         else decode_pruned(p, s, X, lx, ly, A, lane, rv, ri, exhaustive, n_eval);
       }
-      if (exhaustive && (p.dbg & 5)) { exhaustive = false; rv = bv; ri = bi & 0xfff; }
+      if (exhaustive && (dbg & 5)) { exhaustive = false; rv = bv; ri = bi & 0xfff; }
       if (exhaustive) {
         // NaN-aware compare for non-finite maps and for degenerate / huge transforms (their grid can overflow to
         // Inf - Inf = NaN weights); everything else yields finite samples
@@ -1091,7 +1104,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     }
 
     fetch_next();                                        // next map + its transform loads, consumed after the epilogue
-    if (p.do_warp) {                                     // second look at the CTA's job word, half a map after the first
+    if (do_warp) {                                     // second look at the CTA's job word, half a map after the first
       int open = 0;
       if (lane == 0) open = ld_volatile_s32(&cj->band_next) < kBands ? 1 : 0;
       if (__shfl_sync(0xffffffffu, open, 0)) {
@@ -1100,14 +1113,14 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
         if (tl) tl_help += tl_now() - t0;
       }
     }
-    if (!(p.dbg & 2)) {
+    if (!(dbg & 2)) {
       k2_resolve(p, pend_item, pend_old, lane);          // the previous map's ticket has long arrived by now
-      finish_map(p, n, (int)vu, b, j, s, X, lx, ly, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
+      finish_map<FAST>(p, n, (int)vu, b, j, s, X, lx, ly, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
     } else if (rv == 123.456f && p.out_max) p.out_max[n] = rv;
     __syncwarp();
-    if (p.use_bulk && lane == 0 && nx.n < N) {                                                    // buffer handed on
+    if (use_bulk && lane == 0 && nx.n < N) {                                                    // buffer handed on
       const unsigned long long t0 = tl ? tl_now() : 0ull;
-      issue_map(p, nx.n, buf0, bar, pol, map_bytes, cj);
+      issue_map<FAST>(p, nx.n, buf0, bar, pol, map_bytes, cj);
       if (tl) tl_ticket += tl_now() - t0;
     }
   }
@@ -1118,7 +1131,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
     atomicMin(p.stats + 12, t); atomicMax(p.stats + 13, t);
     atomicAdd(p.stats + 15, tl_wait); atomicAdd(p.stats + 16, tl_ticket);
     atomicAdd(p.stats + 17, tl_exh); atomicAdd(p.stats + 18, tl_help); atomicAdd(p.stats + 19, t - tl_first);
-    if (p.dbg & 32) {                                    // per-warp record: stats[32 + 2*g] = time out of maps,
+    if (dbg & 32) {                                    // per-warp record: stats[32 + 2*g] = time out of maps,
       const unsigned g = blockIdx.x * 16u + (unsigned)warp;   // [33 + 2*g] = maps | exhaustive << 16 | exhaustive ns << 32
       p.stats[32 + 2 * g] = t;
       p.stats[33 + 2 * g] = n_maps | (n_slow << 16) | (tl_exh << 32);
@@ -1133,7 +1146,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   // the last maps finish -- do the EMA's pieces (TailEma: real work that would otherwise be a launch of its own; the
   // warp leaves only when no piece is left), then pull the range the next kernel reads (pf_ptr: the student maps of
   // K3) into L2 for as long as other warps are still decoding.
-  if (p.do_warp) {
+  if (do_warp) {
     __syncwarp();
     if (lane == 0) atomicAdd(&cj->warps_done, 1);
     constexpr unsigned kPfChunk = 32768u;
@@ -1265,9 +1278,14 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
+// The call the fused chain makes (see UBPL_F): it gets the specialised kernel instance.  UBPL_K1_FAST=0 forces the generic one.
+static bool k1_fast(const WDParams& p) {
+  return p.do_warp && p.use_bulk && p.refine == 0 && !p.swap_perm && !p.out_hm_xy && p.dbg == 0 && env_int("UBPL_K1_FAST", 1) != 0;
+}
+
 // Fills the geometry / tuning fields of p and launches the kernel.  p.work, p.k2, p.pf_* and the outputs are
 // set by the caller.
-static int launch_k1(WDParams& p, cudaStream_t stream) {
+static int launch_k1(WDParams& p, cudaStream_t stream, bool* ema_carried = nullptr) {
   const int H = p.H, W = p.W;
   const long long N = (long long)p.V * p.B * p.J;
   const long long HW = (long long)H * W;
@@ -1302,17 +1320,24 @@ static int launch_k1(WDParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)warps * buf_stride + tail;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(warp_decode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(warp_decode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(warp_decode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
+    cudaError_t e = cudaSuccess;
+    const void* inst[] = {(const void*)warp_decode_kernel<false, false, false>, (const void*)warp_decode_kernel<false, false, true>,
+                          (const void*)warp_decode_kernel<false, true, true>, (const void*)warp_decode_kernel<true, true, false>};
+    for (const void* f : inst)
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
     if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
     attr_set = true;
   }
   long long need = (N + warps - 1) / warps;
   int grid = (int)(need < sm_count() ? need : sm_count());
-  if ((p.dbg & 16) && p.stats) warp_decode_kernel<true, true><<<grid, warps * 32, smem, stream>>>(p);
-  else if (p.ema.n_chunks > 0) warp_decode_kernel<false, true><<<grid, warps * 32, smem, stream>>>(p);
-  else warp_decode_kernel<false, false><<<grid, warps * 32, smem, stream>>>(p);
+  // the EMA rides along only in the specialised instance (and in the probe build); otherwise the caller issues it
+  const bool probe = (p.dbg & 16) && p.stats;
+  if (p.ema.n_chunks > 0 && !probe && !k1_fast(p)) p.ema.n_chunks = 0;
+  if (ema_carried) *ema_carried = p.ema.n_chunks > 0;
+  if (probe) warp_decode_kernel<true, true, false><<<grid, warps * 32, smem, stream>>>(p);
+  else if (k1_fast(p) && p.ema.n_chunks > 0) warp_decode_kernel<false, true, true><<<grid, warps * 32, smem, stream>>>(p);
+  else if (k1_fast(p)) warp_decode_kernel<false, false, true><<<grid, warps * 32, smem, stream>>>(p);
+  else warp_decode_kernel<false, false, false><<<grid, warps * 32, smem, stream>>>(p);
   return check_launch("ubpl_warp_decode");
 }
 
@@ -1426,7 +1451,9 @@ static int warp_decode_k2_impl(const float* maps, int64_t sV, int64_t sB, int64_
   f.mean = mean; f.dist = dist; f.legal = legal; f.enable = enable; f.gate = gate;
   int rc = pow_table(&f.T.key, &f.T.val, &f.T.bits, &f.T.n, &f.T.rmax);
   if (rc != UBPL_OK) return rc;
-  rc = launch_k1(p, (cudaStream_t)stream);
+  bool carried = false;
+  rc = launch_k1(p, (cudaStream_t)stream, &carried);
+  if (ema && ema->n_chunks > 0 && !carried) ema_after = true;
   if (rc == UBPL_OK && ema_after)
     rc = ubpl_ema_multi_tensor(ema->ema_ptrs, ema->param_ptrs, reinterpret_cast<const int64_t*>(ema->numels), ema->chunk_tensor,
                                reinterpret_cast<const int64_t*>(ema->chunk_start), ema->n_chunks, ema->chunk_elems, ema->a,
