@@ -124,6 +124,15 @@ struct WDParams {
 // Every other call takes the generic instance, where the same fields are read at run time.
 #define UBPL_F(expr, constant) (FAST ? (constant) : (expr))
 
+// CH, CW (template): the map's height / width when the instance is compiled for one shape (64x64, 128x128), 0 = read
+// from the parameters.  With the shape known the divisions by W are shifts, pass A is four (sixteen) straight
+// batches, pass B's sweep over a residue class is one load: c2's K1 93.4 -> 85.5 us, c3's 49.0 -> 40.8 us, c4's
+// 184 -> 176 us, and ptxas needs 100 registers instead of 124.
+template <int CW>
+__device__ __forceinline__ void divmod_w(const FastDiv& d, unsigned n, unsigned& q, unsigned& r) {
+  if (CW) { q = n / (unsigned)CW; r = n - q * (unsigned)CW; } else d.divmod(n, q, r);
+}
+
 struct Xform {
   float t00, t01, t02, t10, t11, t12;
   float stepx, stepy, sfx, sfy;
@@ -327,7 +336,9 @@ struct CoopJob {
 __device__ __forceinline__ int ld_volatile_s32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 // Claims and decodes bands of the open job, if any (warp-wide call).
+template <int CH, int CW>
 __device__ __forceinline__ void coop_help(CoopJob* cj, const WDParams& p, const float* lx, const float* ly, int lane) {
+  const int H = CH ? CH : p.H, W = CW ? CW : p.W;
   for (;;) {
     int b = kBands;
     if (lane == 0 && ld_volatile_s32(&cj->band_next) < kBands) b = atomicAdd(&cj->band_next, 1);
@@ -337,9 +348,9 @@ __device__ __forceinline__ void coop_help(CoopJob* cj, const WDParams& p, const 
     const unsigned src = *reinterpret_cast<const volatile unsigned*>(&cj->src);
     const volatile float* t = cj->t;
     const int flags = ld_volatile_s32(&cj->flags);
-    const int r0 = (p.H * b) / kBands, r1 = (p.H * (b + 1)) / kBands;
+    const int r0 = (H * b) / kBands, r1 = (H * (b + 1)) / kBands;
     const ArgMax r = decode_exhaustive(src, smem_u32(lx), smem_u32(ly), t[0], t[1], t[2], t[3], t[4], t[5], p.sfx, p.sfy,
-                                       p.H, p.W, flags, lane, r0, r1);
+                                       H, W, flags, lane, r0, r1);
     if (lane == 0) {
       *reinterpret_cast<volatile float*>(&cj->pv[b]) = r.v;
       *reinterpret_cast<volatile int*>(&cj->pi[b]) = r.i;
@@ -350,6 +361,7 @@ __device__ __forceinline__ void coop_help(CoopJob* cj, const WDParams& p, const 
 }
 
 // Posts the map staged at `s` as the CTA's job, works on it, and returns its exact arg-max (warp-wide call).
+template <int CH, int CW>
 __device__ __forceinline__ ArgMax coop_exhaustive(CoopJob* cj, const WDParams& p, const float* s, const Xform& X,
                                                   bool nan_aware, const float* lx, const float* ly, int warp, int lane) {
   {
@@ -361,7 +373,7 @@ __device__ __forceinline__ ArgMax coop_exhaustive(CoopJob* cj, const WDParams& p
     got = __shfl_sync(0xffffffffu, got, 0);
     if (!got)
       return decode_exhaustive(smem_u32(s), smem_u32(lx), smem_u32(ly), X.t00, X.t01, X.t02, X.t10, X.t11, X.t12, p.sfx, p.sfy,
-                               p.H, p.W, (X.flip ? 1 : 0) | (nan_aware ? 2 : 0), lane, 0, p.H);
+                               CH ? CH : p.H, CW ? CW : p.W, (X.flip ? 1 : 0) | (nan_aware ? 2 : 0), lane, 0, CH ? CH : p.H);
   }
   if (lane == 0) {
     *reinterpret_cast<volatile unsigned*>(&cj->src) = smem_u32(s);
@@ -373,7 +385,7 @@ __device__ __forceinline__ ArgMax coop_exhaustive(CoopJob* cj, const WDParams& p
     atomicExch(&cj->band_next, 0);                           // opens the job
   }
   __syncwarp();
-  coop_help(cj, p, lx, ly, lane);
+  coop_help<CH, CW>(cj, p, lx, ly, lane);
   if (lane == 0) {
     while (ld_volatile_s32(&cj->bands_done) < kBands) {
     }
@@ -686,13 +698,13 @@ __device__ __forceinline__ void k2_item_dual(const WDParams& p, long long item, 
 
 // Epilogue of one map (warp-wide call): arg-max -> heat-map coordinates (mask, optional quarter-offset
 // refinement) -> image-space coordinates -> outputs -> (optional) arrival at the item's K2.
-template <bool FAST>
+template <bool FAST, int CH, int CW>
 __device__ __forceinline__ void finish_map(const WDParams& p, long long n, int v, int b, int j, const float* s, const Xform& X,
                                            const float* lx, const float* ly, float rv, int ri, double dc0, double dc1,
                                            double dc2, double dc3, int lane, long long& pend_item, unsigned& pend_old) {
-  const int H = p.H, W = p.W;
+  const int H = CH ? CH : p.H, W = CW ? CW : p.W;
   unsigned ayu, axu;
-  p.divW.divmod((unsigned)ri & 0x7fffffffu, ayu, axu);
+  divmod_w<CW>(p.divW, (unsigned)ri & 0x7fffffffu, ayu, axu);
   const int ax = (int)axu, ay = (int)ayu;             // 0-based arg-max, canonical frame
   float hx = 0.f, hy = 0.f;
   const bool keep = rv > 0.f;                          // maxval.gt(0): NaN -> masked
@@ -772,10 +784,11 @@ struct PassA {
 
 // Phases L, B and C (see the header comment) on the staged map.  On return: `exhaustive` asks for the
 // exhaustive decode, otherwise (rv, ri) is the exact result.
+template <int CH, int CW>
 __device__ __forceinline__ void decode_pruned(const WDParams& p, const float* __restrict__ s, const Xform& X,
                                               const float* lx, const float* ly, const PassA& A, int lane, float& rv,
                                               int& ri, bool& exhaustive, unsigned long long& n_eval) {
-  const int H = p.H, W = p.W, HW = H * W;
+  const int H = CH ? CH : p.H, W = CW ? CW : p.W, HW = H * W;
   const float c0 = A.c0, f0 = A.f0, C00 = A.C00, C01 = A.C01, C10 = A.C10, C11 = A.C11;
   const float bv = A.bv;
   const int bi = A.bi;
@@ -786,7 +799,7 @@ __device__ __forceinline__ void decode_pruned(const WDParams& p, const float* __
   {
     // ---- phase L: lower bound from the pixels around the pre-image of the arg-max texel
     unsigned biy, bix;
-    p.divW.divmod((unsigned)bi, biy, bix);
+    divmod_w<CW>(p.divW, (unsigned)bi, biy, bix);
     const float sx = (float)bix - c0, sy = (float)biy - f0;
     const float oj = C00 * sx + C01 * sy, oi = C10 * sx + C11 * sy;
     if (oj > -4.f && oj < (float)W + 4.f && oi > -4.f && oi < (float)H + 4.f && lane < 30) {
@@ -854,7 +867,7 @@ __device__ __forceinline__ void decode_pruned(const WDParams& p, const float* __
     const float4* s4 = reinterpret_cast<const float4*>(s);
     auto hit = [&](int k) {
       unsigned ty, tx;
-      p.divW.divmod((unsigned)k, ty, tx);
+      divmod_w<CW>(p.divW, (unsigned)k, ty, tx);
       txmin = min(txmin, (int)tx); txmax = max(txmax, (int)tx); tymin = min(tymin, (int)ty); tymax = max(tymax, (int)ty);
     };
     auto visit = [&](const float4& x, int q) {
@@ -922,12 +935,12 @@ __device__ __forceinline__ void decode_pruned(const WDParams& p, const float* __
 // code costs the decode loop 2-4 % (measured A/B on c2 / c3 / c5 with the EMA never executed: 98.2 -> 100.3 us,
 // 52.0 -> 53.7 us, 1714 -> 1779 us; same registers, no spills -- code placement): launches without an EMA keep the
 // instance that does not have it.
-template <bool TL, bool EMA, bool FAST>
+template <bool TL, bool EMA, bool FAST, int CH, int CW>
 __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int do_warp = UBPL_F(p.do_warp, 1), use_bulk = UBPL_F(p.use_bulk, 1), dbg = UBPL_F(p.dbg, 0);
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = p.H, W = p.W, HW = H * W;
+  const int H = CH ? CH : p.H, W = CW ? CW : p.W, HW = H * W;
   const uint32_t map_bytes = (uint32_t)HW * 4u;
   const uint32_t buf_stride = (map_bytes + 127u) & ~127u;                                        // 128 B aligned
   float* buf0 = reinterpret_cast<float*>(smem_raw + (size_t)warp * buf_stride);
@@ -1008,7 +1021,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       if (lane == 0) open = ld_volatile_s32(&cj->band_next) < kBands ? 1 : 0;
       if (__shfl_sync(0xffffffffu, open, 0)) {
         const unsigned long long t0 = tl ? tl_now() : 0ull;
-        coop_help(cj, p, lx, ly, lane);
+        coop_help<CH, CW>(cj, p, lx, ly, lane);
         if (tl) tl_help += tl_now() - t0;
       }
     }
@@ -1088,14 +1101,14 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
         warp_argmax_finite(bv, bi);       // warp-uniform source max / location
         A.bv = bv; A.bi = bi;
         if (dbg & 1) { rv = bv; ri = bi; }
-        else decode_pruned(p, s, X, lx, ly, A, lane, rv, ri, exhaustive, n_eval);
+        else decode_pruned<CH, CW>(p, s, X, lx, ly, A, lane, rv, ri, exhaustive, n_eval);
       }
       if (exhaustive && (dbg & 5)) { exhaustive = false; rv = bv; ri = bi & 0xfff; }
       if (exhaustive) {
         // NaN-aware compare for non-finite maps and for degenerate / huge transforms (their grid can overflow to
         // Inf - Inf = NaN weights); everything else yields finite samples
         const unsigned long long t0 = tl ? tl_now() : 0ull;
-        const ArgMax r = coop_exhaustive(cj, p, s, X, nonfinite || bad_xform, lx, ly, warp, lane);
+        const ArgMax r = coop_exhaustive<CH, CW>(cj, p, s, X, nonfinite || bad_xform, lx, ly, warp, lane);
         if (tl) tl_exh += tl_now() - t0;
         rv = r.v; ri = r.i;
         ++n_slow;
@@ -1109,13 +1122,13 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       if (lane == 0) open = ld_volatile_s32(&cj->band_next) < kBands ? 1 : 0;
       if (__shfl_sync(0xffffffffu, open, 0)) {
         const unsigned long long t0 = tl ? tl_now() : 0ull;
-        coop_help(cj, p, lx, ly, lane);
+        coop_help<CH, CW>(cj, p, lx, ly, lane);
         if (tl) tl_help += tl_now() - t0;
       }
     }
     if (!(dbg & 2)) {
       k2_resolve(p, pend_item, pend_old, lane);          // the previous map's ticket has long arrived by now
-      finish_map<FAST>(p, n, (int)vu, b, j, s, X, lx, ly, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
+      finish_map<FAST, CH, CW>(p, n, (int)vu, b, j, s, X, lx, ly, rv, ri, dc0, dc1, dc2, dc3, lane, pend_item, pend_old);
     } else if (rv == 123.456f && p.out_max) p.out_max[n] = rv;
     __syncwarp();
     if (use_bulk && lane == 0 && nx.n < N) {                                                    // buffer handed on
@@ -1163,7 +1176,7 @@ __global__ void __launch_bounds__(512, 1) warp_decode_kernel(const WDParams p) {
       st = __shfl_sync(0xffffffffu, st, 0);
       if (st == 2) break;
       if (st == 1) {
-        coop_help(cj, p, lx, ly, lane);
+        coop_help<CH, CW>(cj, p, lx, ly, lane);
         continue;
       }
       if (ema_live) {
@@ -1321,8 +1334,10 @@ static int launch_k1(WDParams& p, cudaStream_t stream, bool* ema_carried = nullp
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaSuccess;
-    const void* inst[] = {(const void*)warp_decode_kernel<false, false, false>, (const void*)warp_decode_kernel<false, false, true>,
-                          (const void*)warp_decode_kernel<false, true, true>, (const void*)warp_decode_kernel<true, true, false>};
+    const void* inst[] = {(const void*)warp_decode_kernel<false, false, false, 0, 0>, (const void*)warp_decode_kernel<true, true, false, 0, 0>,
+                          (const void*)warp_decode_kernel<false, false, true, 0, 0>, (const void*)warp_decode_kernel<false, true, true, 0, 0>,
+                          (const void*)warp_decode_kernel<false, false, true, 64, 64>, (const void*)warp_decode_kernel<false, true, true, 64, 64>,
+                          (const void*)warp_decode_kernel<false, false, true, 128, 128>, (const void*)warp_decode_kernel<false, true, true, 128, 128>};
     for (const void* f : inst)
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin());
     if (e != cudaSuccess) { set_error("ubpl_warp_decode: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UBPL_ERR_CUDA; }
@@ -1334,10 +1349,17 @@ static int launch_k1(WDParams& p, cudaStream_t stream, bool* ema_carried = nullp
   const bool probe = (p.dbg & 16) && p.stats;
   if (p.ema.n_chunks > 0 && !probe && !k1_fast(p)) p.ema.n_chunks = 0;
   if (ema_carried) *ema_carried = p.ema.n_chunks > 0;
-  if (probe) warp_decode_kernel<true, true, false><<<grid, warps * 32, smem, stream>>>(p);
-  else if (k1_fast(p) && p.ema.n_chunks > 0) warp_decode_kernel<false, true, true><<<grid, warps * 32, smem, stream>>>(p);
-  else if (k1_fast(p)) warp_decode_kernel<false, false, true><<<grid, warps * 32, smem, stream>>>(p);
-  else warp_decode_kernel<false, false, false><<<grid, warps * 32, smem, stream>>>(p);
+  // instance: probe build / generic / the fused chain's call, the latter compiled for 64x64 and 128x128 maps as well
+  // (UBPL_K1_SHAPES=0: shapes read at run time)
+  const bool fast = k1_fast(p), ema = p.ema.n_chunks > 0;
+  const int shape = (fast && env_int("UBPL_K1_SHAPES", 1)) ? ((H == 64 && W == 64) ? 64 : (H == 128 && W == 128) ? 128 : 0) : 0;
+#define UBPL_K1_LAUNCH(...) warp_decode_kernel<__VA_ARGS__><<<grid, warps * 32, smem, stream>>>(p)
+  if (probe) UBPL_K1_LAUNCH(true, true, false, 0, 0);
+  else if (!fast) UBPL_K1_LAUNCH(false, false, false, 0, 0);
+  else if (shape == 64) { if (ema) UBPL_K1_LAUNCH(false, true, true, 64, 64); else UBPL_K1_LAUNCH(false, false, true, 64, 64); }
+  else if (shape == 128) { if (ema) UBPL_K1_LAUNCH(false, true, true, 128, 128); else UBPL_K1_LAUNCH(false, false, true, 128, 128); }
+  else { if (ema) UBPL_K1_LAUNCH(false, true, true, 0, 0); else UBPL_K1_LAUNCH(false, false, true, 0, 0); }
+#undef UBPL_K1_LAUNCH
   return check_launch("ubpl_warp_decode");
 }
 
