@@ -105,7 +105,9 @@ int ubpl_warp_decode_k2(const float* maps, int64_t sV, int64_t sB, int64_t sJ,
  * ubpl_ema_multi_tensor (same tables, same arithmetic, update_ema_variables utils/parameters.py:4-8) chunk by chunk
  * while the last maps are decoded -- K1's launch ends with ~2 map times in which HBM is no longer saturated by the
  * staged copies, and the EMA depends on nothing in the chain.  A separate EMA kernel cannot run beside K1 (K1's CTAs
- * hold all of an SM's shared memory), so this is the only way to overlap the two.  n_chunks = 0: no EMA.  For a
+ * hold all of an SM's shared memory), so this is the only way to overlap the two.  n_chunks = 0: no EMA.  A warp
+ * claims 1024 elements of a chunk at a time (one memory round trip), so a table with chunk_elems = 1024 -- one claim per
+ * work item, no empty claims on small tensors -- is the efficient one here (the Python side keeps both).  For a
  * launch of more than 1.5 GB of maps (UBPL_K1_EMA_MAX_MB) the call issues the EMA as a launch of its own right behind
  * K1 instead: the kernel instance that carries the EMA code decodes 2-4 % slower, which only pays on short launches. */
 int ubpl_warp_decode_k2_ema(const float* maps, int64_t sV, int64_t sB, int64_t sJ,

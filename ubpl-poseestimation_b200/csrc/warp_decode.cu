@@ -408,10 +408,12 @@ __device__ __forceinline__ ArgMax coop_exhaustive(CoopJob* cj, const WDParams& p
 }
 
 // One PIECE (kEmaPiece elements of one chunk) of the EMA (see TailEma) by one warp, the arithmetic of ema_multi_kernel
-// (csrc/ema.cu).  A piece is one memory round trip: all of a lane's 4 + 4 128-bit loads are in flight together (a whole
-// 8192-element chunk per warp would be 16 dependent round trips, ~20 us -- longer than the tail it is meant to fill;
-// 8 + 8 loads per lane made the register allocator spill in the decode loop and cost K1 12 %).
-constexpr int kEmaPiece = 512;
+// (csrc/ema.cu).  A piece is one memory round trip: all of a lane's 8 + 8 128-bit loads are in flight together (a whole
+// 8192-element chunk per warp would be 16 dependent round trips, ~20 us -- longer than the tail it is meant to fill).
+// 8 + 8 loads fit since the specialised instances need ~100 registers (in the 128-register generic code they made the
+// decode loop spill and cost K1 12 %; there the pieces were 512 elements).  The caller's table should have
+// chunk_elems = kEmaPiece: one claim per work item, no empty claims on small tensors (c2 step 161.9 -> 157 us).
+constexpr int kEmaPiece = 1024;
 __device__ __forceinline__ void ema_piece(const TailEma& E, unsigned c, int pieces, float a, float oma, int lane) {
   const unsigned chunk = c / (unsigned)pieces;             // 32-bit: a 64-bit division is a call
   const int lo = (int)(c - chunk * (unsigned)pieces) * kEmaPiece;
@@ -425,17 +427,17 @@ __device__ __forceinline__ void ema_piece(const TailEma& E, unsigned c, int piec
   const float* q = reinterpret_cast<const float*>(E.param_ptrs[t]) + start + lo;
   const int m = hi - lo;
   if ((((uintptr_t)e | (uintptr_t)q) & 15) == 0) {
-    const int n4 = m >> 2;                                 // <= 128: at most 4 float4 per lane
+    const int n4 = m >> 2;                                 // <= 256: at most 8 float4 per lane
     float4* e4 = reinterpret_cast<float4*>(e);
     const float4* q4 = reinterpret_cast<const float4*>(q);
-    float4 ev[4], pv[4];
+    float4 ev[8], pv[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int i = lane + 32 * u;
       if (i < n4) { ev[u] = e4[i]; pv[u] = ldg_stream(q4 + i); }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int i = lane + 32 * u;
       if (i < n4) {
         ev[u].x = ema1(ev[u].x, pv[u].x, a, oma); ev[u].y = ema1(ev[u].y, pv[u].y, a, oma);

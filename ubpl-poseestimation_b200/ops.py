@@ -169,7 +169,7 @@ def warp_decode_k2(maps, theta, flip, dec, mode, S=1, img_h=256, img_w=256, stri
             int(S), mean.data_ptr(), dist.data_ptr(), legal.data_ptr(), _p(enable), _p(gate), _p(stats),
             ws.data_ptr(), ws_bytes, pf_ptr, int(pf_bytes))
     if ema is not None:
-        _lib.call("ubpl_warp_decode_k2_ema", *args, *ema.launch_args(alpha, alpha_from_device), _stream())
+        _lib.call("ubpl_warp_decode_k2_ema", *args, *ema.launch_args(alpha, alpha_from_device, pieces=True), _stream())
     else:
         _lib.call("ubpl_warp_decode_k2", *args, _stream())
     return dict(idx=out_idx, max=out_max, xy=out_xy, mean=mean, dist=dist, legal=legal, enable=enable, gate=gate,
@@ -792,7 +792,9 @@ def features_cov(inp1, inp2, want_grad=True):
 class EmaPlan:
     """Device-side pointer/chunk tables for the one-launch EMA of a (student, teacher) model pair
     (utils/parameters.py:4-8).  Rebuilt automatically if any parameter storage moved."""
-    CHUNK = 8192
+    CHUNK = 8192          # elements per work item of the standalone kernel (one CTA sweep)
+    PIECE = 1024          # elements per work item when the update rides in K1's launch (one warp, one memory round trip;
+                          # kEmaPiece in csrc/warp_decode.cu): its own table, so that a small tensor is ONE claim
 
     def __init__(self, params, ema_params):
         self.params = list(params)
@@ -826,6 +828,14 @@ class EmaPlan:
         self.numels = torch.tensor(numels, dtype=torch.int64, device=dev)
         self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=dev)
         self.chunk_start = torch.tensor(cs, dtype=torch.int64, device=dev)
+        pt, ps = [], []
+        for t, n in enumerate(numels):
+            for s in range(0, n, self.PIECE):
+                pt.append(t)
+                ps.append(s)
+        self.n_pieces = len(pt)
+        self.piece_tensor = torch.tensor(pt, dtype=torch.int32, device=dev)
+        self.piece_start = torch.tensor(ps, dtype=torch.int64, device=dev)
         self._key = self._ptr_key()
 
     def set_alpha(self, alpha):
@@ -839,8 +849,9 @@ class EmaPlan:
         self.alpha_buf.copy_(vals, non_blocking=False)
         self.alpha = float(alpha)
 
-    def launch_args(self, alpha, from_device=False):
-        """The EMA arguments shared by ubpl_ema_multi_tensor and ubpl_warp_decode_k2_ema (tables, chunking, alpha)."""
+    def launch_args(self, alpha, from_device=False, pieces=False):
+        """The EMA arguments shared by ubpl_ema_multi_tensor and ubpl_warp_decode_k2_ema (tables, chunking, alpha);
+        pieces=True: the finer table for the launch that rides in K1."""
         if self._ptr_key() != self._key:
             self._build()
         import numpy as np
@@ -851,6 +862,9 @@ class EmaPlan:
             if getattr(self, "alpha_buf", None) is None:
                 self.set_alpha(alpha)
             adev = self.alpha_buf.data_ptr()
+        if pieces:
+            return (self.ema_ptrs.data_ptr(), self.param_ptrs.data_ptr(), self.numels.data_ptr(), self.piece_tensor.data_ptr(),
+                    self.piece_start.data_ptr(), self.n_pieces, self.PIECE, a, oma, adev)
         return (self.ema_ptrs.data_ptr(), self.param_ptrs.data_ptr(), self.numels.data_ptr(), self.chunk_tensor.data_ptr(),
                 self.chunk_start.data_ptr(), self.n_chunks, self.CHUNK, a, oma, adev)
 
