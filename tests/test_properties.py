@@ -9,7 +9,10 @@ from hypothesis import strategies as st
 
 import ubpl_oracle as O
 
-SET = dict(deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+# derandomize: the same examples in every run (a parity suite must not depend on the day's random seed); database=None:
+# nothing is written next to the tests
+SET = dict(deadline=None, derandomize=True, database=None,
+           suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 
 
 def _theta(rng, n):
