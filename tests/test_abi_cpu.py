@@ -114,3 +114,18 @@ def test_grouped_rejects_other_criteria():
     from ubpl_b200 import losses
     with pytest.raises(TypeError):
         losses.grouped(losses.JointDistLoss_mt2(nStack=2), torch.zeros(1, 1, 2, 1, 8, 8), torch.zeros(1, 1, 1, 8, 8))
+
+
+def test_ema_work_items_cover_every_tensor_once():
+    """The chunk / piece tables of the EMA launches (ops.EmaPlan): disjoint work items that cover each tensor exactly."""
+    rng = np.random.default_rng(3)
+    numels = [1, 3, 1024, 1025, 8192, 8193, 70000] + rng.integers(1, 5000, 20).tolist()
+    for size in (ops.EmaPlan.PIECE, ops.EmaPlan.CHUNK, 7):
+        which, start = ops.ema_work_items(numels, size)
+        assert len(which) == len(start) == sum(-(-n // size) for n in numels)
+        seen = [np.zeros(n, np.int32) for n in numels]
+        for t, s0 in zip(which, start):
+            seen[t][s0:min(s0 + size, numels[t])] += 1
+        assert all((v == 1).all() for v in seen)
+        assert which == sorted(which)                       # tensor order
+    assert ops.EmaPlan.PIECE == 1024 and ops.EmaPlan.CHUNK % ops.EmaPlan.PIECE == 0     # kEmaPiece in csrc/warp_decode.cu

@@ -789,6 +789,17 @@ def features_cov(inp1, inp2, want_grad=True):
 # -------------------------------------------------------------------------------------------------
 # K4
 # -------------------------------------------------------------------------------------------------
+def ema_work_items(numels, size):
+    """The (tensor, first element) table of an EMA launch: every tensor cut into work items of at most `size` elements,
+    in tensor order.  Pure host function (tested on CPU): the items of a tensor are disjoint and cover it exactly."""
+    which, start = [], []
+    for t, n in enumerate(numels):
+        for s in range(0, int(n), int(size)):
+            which.append(t)
+            start.append(s)
+    return which, start
+
+
 class EmaPlan:
     """Device-side pointer/chunk tables for the one-launch EMA of a (student, teacher) model pair
     (utils/parameters.py:4-8).  Rebuilt automatically if any parameter storage moved."""
@@ -816,11 +827,7 @@ class EmaPlan:
             if p.numel() != e.numel():
                 raise ValueError("parameter shape mismatch between student and teacher")
         numels = [p.numel() for p in self.params]
-        ct, cs = [], []
-        for t, n in enumerate(numels):
-            for s in range(0, n, self.CHUNK):
-                ct.append(t)
-                cs.append(s)
+        ct, cs = ema_work_items(numels, self.CHUNK)
         self.n_chunks = len(ct)
         self.n_elems = sum(numels)
         self.ema_ptrs = torch.tensor([e.data_ptr() for e in self.ema_params], dtype=torch.int64, device=dev)
@@ -828,11 +835,7 @@ class EmaPlan:
         self.numels = torch.tensor(numels, dtype=torch.int64, device=dev)
         self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=dev)
         self.chunk_start = torch.tensor(cs, dtype=torch.int64, device=dev)
-        pt, ps = [], []
-        for t, n in enumerate(numels):
-            for s in range(0, n, self.PIECE):
-                pt.append(t)
-                ps.append(s)
+        pt, ps = ema_work_items(numels, self.PIECE)
         self.n_pieces = len(pt)
         self.piece_tensor = torch.tensor(pt, dtype=torch.int32, device=dev)
         self.piece_start = torch.tensor(ps, dtype=torch.int64, device=dev)
