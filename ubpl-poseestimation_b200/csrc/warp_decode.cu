@@ -1510,6 +1510,8 @@ extern "C" int ubpl_warp_decode_k2_ema(const float* maps, int64_t sV, int64_t sB
   UBPL_REQUIRE(n_chunks >= 0 && (n_chunks == 0 || (ema_ptrs && param_ptrs && numels && chunk_tensor && chunk_start)),
                "ubpl_warp_decode_k2_ema: NULL pointer in the EMA tables");
   UBPL_REQUIRE(n_chunks == 0 || (chunk_elems > 0 && chunk_elems % 4 == 0), "ubpl_warp_decode_k2_ema: bad chunking");
+  UBPL_REQUIRE(n_chunks * (int64_t)((chunk_elems + kEmaPiece - 1) / kEmaPiece) < (1ll << 31),
+               "ubpl_warp_decode_k2_ema: too many EMA work items (%lld chunks of %d elements)", (long long)n_chunks, chunk_elems);
   TailEma E;
   memset(&E, 0, sizeof(E));
   E.ema_ptrs = ema_ptrs; E.param_ptrs = param_ptrs; E.numels = reinterpret_cast<const long long*>(numels);
