@@ -96,17 +96,21 @@ __device__ __forceinline__ float gauss_px_v(float exv, float eyv, int x, int y, 
 
 // One WARP per (sample, joint): no block barriers; every lane keeps 8 independent 128-bit loads in
 // flight; the separable Gaussian factors live in a per-warp shared-memory slice.
-template <bool VEC, int SS, int OCC>
+// CH, CW: the map's shape when the instance is compiled for it (64x64, 128x128: then also S == SS stacks, four warps per
+// CTA and every item shared by its CTA), 0 = everything read from the arguments.  Knowing the shape takes the kernel
+// from 57.0 to 54.8 us on c2 -- onto the read/write-mix bound of tools/rw_micro.cu (53.2-55.3 us).
+template <bool VEC, int SS, int OCC, int CH, int CW>
 __global__ void __launch_bounds__(128, OCC) render_mse_kernel(
     const float* __restrict__ kps, const float* __restrict__ gate_in, const float* __restrict__ sample_w,
     const float* __restrict__ pred, long long pB, long long pS, long long pJ, float* __restrict__ grad, long long gB,
-    long long gS, long long gJ, float* __restrict__ target, int B, int S, int J, int H, int W, int img_h, int img_w,
+    long long gS, long long gJ, float* __restrict__ target, int B, int S_, int J, int H_, int W_, int img_h, int img_w,
     float stride, float sigma, const float* __restrict__ grad_scale, const int32_t* __restrict__ count_in,
     float loss_weight, float* __restrict__ grad_scale_out, float* __restrict__ gate_out,
     float* __restrict__ per_loss, const FastDiv divW4, double* __restrict__ summary, unsigned char* __restrict__ sum_ws,
-    int all_coop) {
+    int all_coop_) {
   extern __shared__ float sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int H = CH ? CH : H_, W = CW ? CW : W_, S = CH ? SS : S_, all_coop = CH ? 1 : all_coop_;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = CH ? 4 : (int)(blockDim.x >> 5);
   // Programmatic dependent launch: when the kernel is launched with programmatic stream serialization its CTAs are
   // scheduled as soon as the SMs of the preceding kernel (K1 or the selector) free up, and wait HERE until that
   // kernel has completed and its results (key points, gates, count) are visible; a no-op for a plain launch.
@@ -193,7 +197,8 @@ __global__ void __launch_bounds__(128, OCC) render_mse_kernel(
           float4 t;
           if (VEC) {                                    // W % 4 == 0: the four texels share a row
             unsigned yu, xu;
-            divW4.divmod((unsigned)q, yu, xu);
+            if (CW) { yu = (unsigned)q / (unsigned)(CW / 4 ? CW / 4 : 1); xu = (unsigned)q - yu * (unsigned)(CW / 4 ? CW / 4 : 1); }
+            else divW4.divmod((unsigned)q, yu, xu);
             const int y = (int)yu, x = (int)(xu << 2);
             // outside the Gaussian's support box the target is exactly 0 (the 0.01 cut, process.py:275)
             if (y < ylo || y > yhi || x + 3 < xlo || x > xhi) {
@@ -842,11 +847,25 @@ static int render_mse_impl(const float* kps, const float* gate_in, const float* 
 #undef UBPL_LAUNCH_FAST
     return check_launch("ubpl_render_mse");
   }
+  // instances compiled for 64x64 / 128x128 maps (see the kernel; UBPL_K3_SHAPES=0: shapes read at run time)
+  const int shape = (vec && occ5 && all_coop && (S == 1 || S == 2) && wpb == 4 &&
+                     !(getenv("UBPL_K3_SHAPES") && atoi(getenv("UBPL_K3_SHAPES")) == 0))
+                        ? ((H == 64 && W == 64) ? 64 : (H == 128 && W == 128) ? 128 : 0) : 0;
+#define UBPL_LAUNCH_SHAPED(SSV, C)                                                                                     \
+  cudaLaunchKernelEx(&lc, render_mse_kernel<true, SSV, 5, C, C>,                                                       \
+      kps, gate_in, sample_w, pred, (long long)pB, (long long)pS, (long long)pJ, grad, (long long)gB, (long long)gS, (long long)gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
+      grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, sum_ws, all_coop)
+  if (shape) {
+    if (shape == 64) { if (S == 2) UBPL_LAUNCH_SHAPED(2, 64); else UBPL_LAUNCH_SHAPED(1, 64); }
+    else { if (S == 2) UBPL_LAUNCH_SHAPED(2, 128); else UBPL_LAUNCH_SHAPED(1, 128); }
+    return check_launch("ubpl_render_mse");
+  }
+#undef UBPL_LAUNCH_SHAPED
 #define UBPL_LAUNCH_RENDER(V, SSV)                                                                                     \
-  if (occ5) cudaLaunchKernelEx(&lc, render_mse_kernel<V, SSV, 5>,                                                      \
+  if (occ5) cudaLaunchKernelEx(&lc, render_mse_kernel<V, SSV, 5, 0, 0>,                                                \
       kps, gate_in, sample_w, pred, (long long)pB, (long long)pS, (long long)pJ, grad, (long long)gB, (long long)gS, (long long)gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
       grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, sum_ws, all_coop);       \
-  else cudaLaunchKernelEx(&lc, render_mse_kernel<V, SSV, 6>,                                                           \
+  else cudaLaunchKernelEx(&lc, render_mse_kernel<V, SSV, 6, 0, 0>,                                                     \
       kps, gate_in, sample_w, pred, (long long)pB, (long long)pS, (long long)pJ, grad, (long long)gB, (long long)gS, (long long)gJ, target, B, S, J, H, W, img_h, img_w, stride, sigma, \
       grad_scale, count_in, loss_weight, grad_scale_out, gate_out, per_loss, divW4, summary, sum_ws, all_coop)
   if (vec) {
