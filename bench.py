@@ -46,7 +46,7 @@ METRIC = "pseudo-labelled samples/sec"
 NCU_TRAFFIC = {"c2": 542.46e6, "c4": 1145.79e6}
 # c4 at N = 1 (this repo, B200, `python bench.py --config c4`, profiles/r02/): the denominator of the collective
 # block's `vs_n1` when the driver's N > 1 runs time c4 beside the headline config
-C4_N1 = {"value": 881613.0, "ms_per_step": 0.2904, "source": "profiles/r02/final_bench_c4.json (builder-run, 1 B200); the N = 1 run of this "
+C4_N1 = {"value": 885398.0, "ms_per_step": 0.2891, "source": "profiles/r02/final_bench_c4.json (builder-run, 1 B200); the N = 1 run of this "
          "script carries its own `collective` block, which is the denominator to use"}
 
 
