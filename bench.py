@@ -40,10 +40,10 @@ CONFIGS = {
 DIST_THR_MAX = 3.0          # no reference default exists; ~half of the joints pass on the synthetic data
 METRIC = "pseudo-labelled samples/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE warp_decode_kernel launch, from the ncu --set full captures
-# profiles/r02/final_k1_k3_full.ncu-rep (c2, K1 with the EMA in its tail: 537.50 MB read = 469.76 MB of teacher maps +
-# 67.4 MB of EMA operands, 4.97 MB written before the launch ends -- the EMA's 33.7 MB of results are still in L2 then)
+# profiles/r02/final_k1_k3_full.ncu-rep (c2, K1 with the EMA in its tail: 539.10 MB read = 469.76 MB of teacher maps +
+# 67.4 MB of EMA operands, 4.74 MB written before the launch ends -- the EMA's 33.7 MB of results are still in L2 then)
 # and, for c4, round 1's profiles/r01f_c4_k1_select_k3_full.ncu-rep (1141.15 MB + 4.64 MB vs 1140.85 MB algorithmic)
-NCU_TRAFFIC = {"c2": 542.46e6, "c4": 1145.79e6}
+NCU_TRAFFIC = {"c2": 543.84e6, "c4": 1145.79e6}
 # c4 at N = 1 (this repo, B200, `python bench.py --config c4`, profiles/r02/): the denominator of the collective
 # block's `vs_n1` when the driver's N > 1 runs time c4 beside the headline config
 C4_N1 = {"value": 885398.0, "ms_per_step": 0.2891, "source": "profiles/r02/final_bench_c4.json (builder-run, 1 B200); the N = 1 run of this "
