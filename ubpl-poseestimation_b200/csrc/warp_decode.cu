@@ -1395,8 +1395,9 @@ extern "C" int ubpl_warp_decode(const float* maps, int64_t sV, int64_t sB, int64
   return launch_k1(p, (cudaStream_t)stream);
 }
 
-// Workspace of ubpl_warp_decode_k2, int32 words: [0,1] claim counter, [32,33] prefetch chunk counter, [34] number
-// of items with a zero intDist sum, [35] status (own 128-byte lines for the two counters), [128, 128+J+2) counts,
+// Workspace of ubpl_warp_decode_k2(_ema), int32 words: [0,1] claim counter, [32,33] prefetch chunk counter, [34] number
+// of items with a zero intDist sum, [35] status, [64,65] EMA work-item counter (own 128-byte lines for the three
+// counters), [128, 128+J+2) counts,
 // then the B*J arrival counters and the V*B*J 64-bit hand-off words.  All of it is cleared by ONE memset node per
 // launch.
 static inline long long k2_ws_arrive_off(int J) { return 128 + ((J + 2 + 1) & ~1); }
